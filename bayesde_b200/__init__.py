@@ -1,0 +1,12 @@
+"""bayesde_b200 -- B200-native (sm_100a) implementation of bayeSDE's fixed-grid SDE-BNN hot path.
+
+Public surface (same names / call shapes as the reference):
+    sdeint_ito_fixed_grid(f, g, y0, ts, rng, args=(), dt=1e-6, method='milstein', rep=0)
+    brax.SDEBNN(...), brax.MeanField, brax.bnn_serial, arch.MLP, arch.build_fx, arch.Augment, ...
+All arithmetic on the hot path runs in libbsde.so (hand-written CUDA, C ABI in include/bsde.h);
+there is no CPU / eager fallback.
+"""
+from . import arch, brax  # noqa: F401
+from .sdeint import sdeint_ito_fixed_grid  # noqa: F401
+
+__all__ = ["sdeint_ito_fixed_grid", "arch", "brax"]

@@ -1,0 +1,215 @@
+"""Structured route of `sdeint_ito_fixed_grid` for SDEBNN dynamics: K1 (weight-SDE rows) + K2/K3
+(x rows, forward scan and hand-written reverse pass) through the C ABI of libbsde.so.
+
+What the reference computes in one `lax.scan` over the concatenated state [x, w, kl]
+(jaxsde/jaxsde/sdeint.py:103-110,135 with f_aug/g_aug of brax/_impl/brax.py:49-78) is split by data
+dependence: the [w, kl] rows never read x, so their whole trajectory is integrated first (one
+cooperative launch), then the x rows consume w(t_k) step by step.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .arch import fw_layers
+
+
+def reference_time_grid(ts, mode="reference"):
+    """(t_k, dt_k) of every scan iteration in fp32, as jaxsde/jaxsde/sdeint.py:103-110 evaluates
+    them (mode="reference": next_t = target_t - curr_t; t_delta = next_t - curr_t -- quirk Q1) or on
+    the intended uniform grid (mode="uniform")."""
+    ts = np.asarray(ts, dtype=np.float32)
+    tk, dtk = [], []
+    if mode == "reference":
+        curr = ts[0]
+        for k in range(1, len(ts)):
+            nxt = np.float32(ts[k] - curr)
+            tk.append(curr)
+            dtk.append(np.float32(nxt - curr))
+            curr = nxt
+    elif mode == "uniform":
+        for k in range(1, len(ts)):
+            tk.append(ts[k - 1])
+            dtk.append(np.float32(ts[k] - ts[k - 1]))
+    else:
+        raise ValueError(f"time_grid must be 'reference' or 'uniform', got {mode!r}")
+    return np.asarray(tk, dtype=np.float32), np.asarray(dtk, dtype=np.float32)
+
+
+def _fw_struct(layers, P, hidden_dims, actfn):
+    """Fill a bsde_fw_params with the device pointers of the (W,b,w_t,w_tb,b_t) tensors."""
+    fp = _lib.FwParams()
+    fp.P = P
+    fp.nhid = len(hidden_dims)
+    for i, d in enumerate(hidden_dims):
+        fp.dims[i] = d
+    fp.act = _lib.ACT[actfn]
+    assert len(layers) == len(hidden_dims) + 1
+    for name, t in zip(("W1", "b1", "wt1", "wtb1", "bt1"), layers[0]):
+        setattr(fp, name, _lib.ptr(t).value)
+    for i, lay in enumerate(layers[1:-1]):
+        for name, t in zip(("Wm", "bm", "wtm", "wtbm", "btm"), lay):
+            getattr(fp, name)[i] = _lib.ptr(t).value
+    for name, t in zip(("W4", "b4", "wt4", "wtb4", "bt4"), layers[-1]):
+        setattr(fp, name, _lib.ptr(t).value)
+    return fp
+
+
+class BlockConfig:
+    """Static description of one SDEBNN block's fused solve."""
+
+    def __init__(self, fx_spec, fw_spec, S, B, nsteps, diff_coef, stl, time_grid, math="fp32", kl_weight=1.0,
+                 ou_coef=0.0, ts=None):
+        self.fx, self.fw = fx_spec, fw_spec
+        self.S, self.B, self.nsteps = S, B, nsteps
+        self.nit = nsteps - 1
+        self.sigma, self.stl = float(diff_coef), bool(stl)
+        self.math = math
+        self.kl_weight, self.ou_coef = kl_weight, ou_coef
+        ts = np.linspace(0.0, 1.0, nsteps, dtype=np.float32) if ts is None else ts  # brax.py:31
+        self.tk, self.dtk = reference_time_grid(ts, time_grid)
+        self.P = fx_spec.P
+        self.x_numel = S * B * fx_spec.H * fx_spec.W * fx_spec.C
+        self._dev = {}
+
+    def grid_on(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = (torch.from_numpy(self.tk).to(device), torch.from_numpy(self.dtk).to(device))
+        return self._dev[key]
+
+    def xdesc(self):
+        d = _lib.XpathDesc()
+        d.S, d.B, d.nit = self.S, self.B, self.nit
+        layers = self.fx.conv_layer_structs()
+        d.nlayers = len(layers)
+        d.act = _lib.ACT[self.fx.actfn]
+        d.math = _lib.MATH[self.math]
+        d.P = self.P
+        d.x_numel = self.x_numel
+        for i, L in enumerate(layers):
+            d.layers[i] = L
+        return d
+
+    def wdesc(self, seed, stream_id, w0_per_sample):
+        d = _lib.WsdeDesc()
+        d.S, d.nit, d.stl = self.S, self.nit, int(self.stl)
+        d.w0_per_sample = int(w0_per_sample)
+        d.sigma, d.kl_weight, d.ou_coef = self.sigma, self.kl_weight, self.ou_coef
+        d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        d.stream_id = int(stream_id) & 0xFFFFFFFF
+        return d
+
+
+def wsde_forward(cfg, w0, layers, dW, seed, stream_id, w_stale):
+    """K1 forward.  Returns (wtraj [S,nit+1,P], z1 (opaque), kl [S])."""
+    L = _lib.lib()
+    dev = w0.device
+    S, nit, P = cfg.S, cfg.nit, cfg.P
+    w0_per_sample = w0.dim() == 2
+    d = cfg.wdesc(seed, stream_id, w0_per_sample)
+    fp = _fw_struct(layers, P, cfg.fw["hidden_dims"], cfg.fw["actfn"])
+    wtraj = torch.empty(S, nit + 1, P, device=dev, dtype=torch.float32)
+    z1 = torch.empty(nit * S * cfg.fw["hidden_dims"][0], device=dev, dtype=torch.float32)
+    kl = torch.empty(S, device=dev, dtype=torch.float32)
+    nbytes = L.bsde_wsde_workspace_bytes(C.byref(d), C.byref(fp))
+    ws = _lib.workspace(nbytes, dev, "wsde")
+    tk, dtk = cfg.grid_on(dev)
+    if dW is not None and tuple(dW.shape) != (S, nit, P):
+        raise ValueError(f"increments must have shape {(S, nit, P)}, got {tuple(dW.shape)}")
+    st = L.bsde_wsde_fwd(C.byref(d), C.byref(fp), _lib.ptr(w0), _lib.ptr(tk), _lib.ptr(dtk), _lib.ptr(dW),
+                         _lib.ptr(w_stale) if cfg.stl else None, _lib.ptr(wtraj), _lib.ptr(z1), _lib.ptr(kl),
+                         C.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr())
+    _lib.check(st, "bsde_wsde_fwd")
+    return wtraj, z1, kl
+
+
+def wsde_backward(cfg, layers, wtraj, z1, gw_traj, gkl, gwT, w0_per_sample):
+    L = _lib.lib()
+    dev = wtraj.device
+    S, P = cfg.S, cfg.P
+    d = cfg.wdesc(0, 0, w0_per_sample)
+    fp = _fw_struct(layers, P, cfg.fw["hidden_dims"], cfg.fw["actfn"])
+    glayers = [tuple(torch.empty_like(t) for t in lay) for lay in layers]
+    gfp = _fw_struct(glayers, P, cfg.fw["hidden_dims"], cfg.fw["actfn"])
+    gw0 = torch.empty((S, P) if w0_per_sample else (P,), device=dev, dtype=torch.float32)
+    nbytes = L.bsde_wsde_workspace_bytes(C.byref(d), C.byref(fp))
+    ws = _lib.workspace(nbytes, dev, "wsde")
+    tk, dtk = cfg.grid_on(dev)
+    st = L.bsde_wsde_bwd(C.byref(d), C.byref(fp), _lib.ptr(tk), _lib.ptr(dtk), _lib.ptr(wtraj), _lib.ptr(z1),
+                         _lib.ptr(gw_traj), _lib.ptr(gkl), _lib.ptr(gwT), _lib.ptr(gw0), C.byref(gfp),
+                         C.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr())
+    _lib.check(st, "bsde_wsde_bwd")
+    return gw0, glayers
+
+
+def xpath_forward(cfg, x, wtraj):
+    """K2 forward scan.  x: [S,B,H,W,C].  Returns xs [nit+1, S,B,H,W,C] (slot 0 = x)."""
+    L = _lib.lib()
+    d = cfg.xdesc()
+    xs = torch.empty((cfg.nit + 1,) + tuple(x.shape), device=x.device, dtype=torch.float32)
+    xs[0].copy_(x)
+    nbytes = L.bsde_xpath_workspace_bytes(C.byref(d), 0)
+    ws = _lib.workspace(nbytes, x.device, "xpath")
+    st = L.bsde_xpath_fwd(C.byref(d), _lib.host_floats(cfg.tk), _lib.host_floats(cfg.dtk), _lib.ptr(wtraj),
+                          _lib.ptr(xs), C.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr())
+    _lib.check(st, "bsde_xpath_fwd")
+    return xs
+
+
+def xpath_backward(cfg, xs, wtraj, gx):
+    """K3: reverse pass over the x rows.  Returns (gx0, gw_traj [S,nit,P])."""
+    L = _lib.lib()
+    d = cfg.xdesc()
+    gx = gx.contiguous().clone()
+    gw_traj = torch.empty(cfg.S, cfg.nit, cfg.P, device=xs.device, dtype=torch.float32)
+    nbytes = L.bsde_xpath_workspace_bytes(C.byref(d), 1)
+    ws = _lib.workspace(nbytes, xs.device, "xpath")
+    st = L.bsde_xpath_bwd(C.byref(d), _lib.host_floats(cfg.tk), _lib.host_floats(cfg.dtk), _lib.ptr(wtraj),
+                          _lib.ptr(xs), _lib.ptr(gx), _lib.ptr(gw_traj), C.c_void_p(ws.data_ptr()), ws.numel(),
+                          _lib.stream_ptr())
+    _lib.check(st, "bsde_xpath_bwd")
+    return gx, gw_traj
+
+
+class SDEBNNSolve(torch.autograd.Function):
+    """ys[-1] of sdeint_ito_fixed_grid(f_aug, g_aug, [x,w0,0], ts, ...) for S samples at once.
+
+    forward(x [S,B,H,W,C], w0 [P] or [S,P], *fw tensors) -> (x_T, kl [S], wtraj [S,nit+1,P])"""
+
+    @staticmethod
+    def forward(ctx, cfg, dW, seed, stream_id, w_stale, x, w0, *fw_flat):
+        layers = [tuple(fw_flat[i:i + 5]) for i in range(0, len(fw_flat), 5)]
+        x = x.contiguous()
+        w0c = w0.contiguous()
+        layers = [tuple(t.contiguous() for t in lay) for lay in layers]
+        wtraj, z1, kl = wsde_forward(cfg, w0c, layers, dW, seed, stream_id, w_stale)
+        xs = xpath_forward(cfg, x, wtraj)
+        ctx.cfg = cfg
+        ctx.layers = layers
+        ctx.w0_per_sample = w0.dim() == 2
+        ctx.save_for_backward(wtraj, z1, xs)
+        ctx.mark_non_differentiable(wtraj)
+        return xs[cfg.nit], kl, wtraj
+
+    @staticmethod
+    def backward(ctx, gx, gkl, _gwtraj):
+        cfg = ctx.cfg
+        wtraj, z1, xs = ctx.saved_tensors
+        dev = xs.device
+        if gx is None:
+            gx = torch.zeros_like(xs[0])
+        if gkl is None:
+            gkl = torch.zeros(cfg.S, device=dev)
+        gx0, gw_traj = xpath_backward(cfg, xs, wtraj, gx.to(torch.float32))
+        gw0, glayers = wsde_backward(cfg, ctx.layers, wtraj, z1, gw_traj, gkl.contiguous().float(), None,
+                                     ctx.w0_per_sample)
+        flat = [t for lay in glayers for t in lay]
+        return (None, None, None, None, None, gx0, gw0, *flat)
+
+
+def zero_fw_layers(P, device):
+    """f_w == 0 (w_drift=False, brax.py:56-57): a P->1->P stack with zero weights."""
+    z = lambda *s: torch.zeros(*s, device=device)
+    return [(z(P, 1), z(1), z(1), z(1), z(1)), (z(1, P), z(P), z(P), z(P), z(P))]

@@ -1,0 +1,148 @@
+"""ctypes binding of libbsde.so (include/bsde.h).  There is NO fallback: if the library is missing
+or a call fails, an exception is raised."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libbsde.so")
+
+FW_MAX_MID = 4
+FW_MAX_EDGE = 4
+FW_MAX_HID = 256
+MAX_LAYERS = 4
+
+ACT = {"softplus": 0, "tanh": 1, "elu": 2, "none": 3}
+METHOD = {"euler_maruyama": 0, "milstein": 1, "euler_heun": 2}
+MATH = {"fp32": 0, "tc": 1}
+EPI_BIAS, EPI_BIAS_ACT, EPI_EULER, EPI_DACT, EPI_ACCUM = range(5)
+
+_fp = C.POINTER(C.c_float)
+
+
+class FwParams(C.Structure):
+    _fields_ = ([("P", C.c_int32), ("nhid", C.c_int32), ("dims", C.c_int32 * (FW_MAX_MID + 2)), ("act", C.c_int32)]
+                + [(n, C.c_void_p) for n in ("W1", "b1", "wt1", "wtb1", "bt1")]
+                + [(n, C.c_void_p * FW_MAX_MID) for n in ("Wm", "bm", "wtm", "wtbm", "btm")]
+                + [(n, C.c_void_p) for n in ("W4", "b4", "wt4", "wtb4", "bt4")])
+
+
+class WsdeDesc(C.Structure):
+    _fields_ = [("S", C.c_int32), ("nit", C.c_int32), ("stl", C.c_int32), ("w0_per_sample", C.c_int32),
+                ("sigma", C.c_float), ("kl_weight", C.c_float), ("ou_coef", C.c_float),
+                ("seed", C.c_uint64), ("stream_id", C.c_uint32)]
+
+
+class ConvLayer(C.Structure):
+    _fields_ = [("cin", C.c_int32), ("cout", C.c_int32), ("ksize", C.c_int32),
+                ("hin", C.c_int32), ("win", C.c_int32), ("hout", C.c_int32), ("wout", C.c_int32),
+                ("sn", C.c_int32), ("kn", C.c_int32), ("off", C.c_int32), ("sd", C.c_int32),
+                ("has_time", C.c_int32), ("time_first", C.c_int32),
+                ("w_off", C.c_int64), ("b_off", C.c_int64),
+                ("w_tap_stride", C.c_int64), ("w_k_stride", C.c_int64), ("w_n_stride", C.c_int64)]
+
+
+class XpathDesc(C.Structure):
+    _fields_ = [("S", C.c_int32), ("B", C.c_int32), ("nit", C.c_int32), ("nlayers", C.c_int32),
+                ("act", C.c_int32), ("math", C.c_int32), ("P", C.c_int64), ("x_numel", C.c_int64),
+                ("layers", ConvLayer * MAX_LAYERS)]
+
+
+class BsdeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_EXPORTS = ["bsde_version", "bsde_last_error", "bsde_wsde_workspace_bytes", "bsde_wsde_fwd", "bsde_wsde_bwd",
+            "bsde_tconv_fwd", "bsde_tconv_wgrad_workspace_bytes", "bsde_tconv_wgrad",
+            "bsde_xpath_workspace_bytes", "bsde_xpath_fwd", "bsde_xpath_bwd", "bsde_step_update",
+            "bsde_philox_increments"]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise BsdeError(f"{_LIB_PATH} is missing: run `python -m bayesde_b200.build` (there is no CPU/eager fallback)")
+    L = C.CDLL(_LIB_PATH)
+    for name in _EXPORTS:
+        if not hasattr(L, name):
+            raise BsdeError(f"libbsde.so does not export {name}")
+    L.bsde_version.restype = C.c_int
+    L.bsde_last_error.restype = C.c_char_p
+    L.bsde_wsde_workspace_bytes.restype = C.c_size_t
+    L.bsde_wsde_workspace_bytes.argtypes = [C.POINTER(WsdeDesc), C.POINTER(FwParams)]
+    vp = C.c_void_p
+    L.bsde_wsde_fwd.argtypes = [C.POINTER(WsdeDesc), C.POINTER(FwParams), vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                C.c_size_t, vp]
+    L.bsde_wsde_bwd.argtypes = [C.POINTER(WsdeDesc), C.POINTER(FwParams), vp, vp, vp, vp, vp, vp, vp, vp,
+                                C.POINTER(FwParams), vp, C.c_size_t, vp]
+    L.bsde_tconv_fwd.argtypes = [C.POINTER(ConvLayer), C.c_int32, C.c_int32, vp, vp, C.c_int64, C.c_float,
+                                 C.c_int32, C.c_int32, C.c_float, vp, vp, C.c_int32, vp]
+    L.bsde_tconv_wgrad_workspace_bytes.restype = C.c_size_t
+    L.bsde_tconv_wgrad_workspace_bytes.argtypes = [C.POINTER(ConvLayer), C.c_int32, C.c_int32]
+    L.bsde_tconv_wgrad.argtypes = [C.POINTER(ConvLayer), C.c_int32, C.c_int32, vp, vp, C.c_float, C.c_float, vp,
+                                   C.c_int64, C.c_int32, vp, C.c_size_t, vp]
+    L.bsde_xpath_workspace_bytes.restype = C.c_size_t
+    L.bsde_xpath_workspace_bytes.argtypes = [C.POINTER(XpathDesc), C.c_int32]
+    L.bsde_xpath_fwd.argtypes = [C.POINTER(XpathDesc), _fp, _fp, vp, vp, vp, C.c_size_t, vp]
+    L.bsde_xpath_bwd.argtypes = [C.POINTER(XpathDesc), _fp, _fp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.bsde_step_update.argtypes = [C.c_int32, C.c_int64, C.c_float, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.bsde_philox_increments.argtypes = [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_int64, vp, vp, vp]
+    for name in _EXPORTS:
+        f = getattr(L, name)
+        if f.restype is C.c_int and name != "bsde_version":
+            pass
+    if L.bsde_version() != 100:
+        raise BsdeError(f"libbsde.so version {L.bsde_version()} != 100: rebuild")
+    _lib = L
+    return L
+
+
+def check(status, what):
+    if status == 0:
+        return
+    msg = lib().bsde_last_error().decode()
+    if status == -1:
+        raise ValueError(f"{what}: {msg}")
+    if status == -2:
+        raise NotImplementedError(f"{what}: {msg}")
+    raise BsdeError(f"{what}: status {status}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32 CUDA tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise BsdeError("bayesde_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError(f"expected a contiguous float32 tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device, tag="ws"):
+    """Grow-only scratch buffer per (device, stream, tag); owned by PyTorch's allocator."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _ws_cache.pop(key, None)
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def host_floats(vals):
+    arr = (C.c_float * len(vals))(*[float(v) for v in vals])
+    return arr

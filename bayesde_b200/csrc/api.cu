@@ -1,0 +1,282 @@
+// C-ABI surface of libbsde.so: error plumbing, K2 entry points, the x-path scan drivers (K2+K3),
+// the generic flat-state step and the Philox increment materialiser.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace bsde {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// fp32 path (tconv_simt.cu)
+int tconv_fwd_simt(const bsde_conv_layer* L, int S, int B, const float* in, const float* w,
+                   long long w_sample_stride, float t, int act, int epi, float scale, const float* aux,
+                   float* out, cudaStream_t st);
+size_t tconv_wgrad_ws_simt(const bsde_conv_layer* L, int S, int B);
+int tconv_wgrad_simt(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t,
+                     float scale, float* gw, long long gw_sample_stride, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+// tensor-core path (tconv_tc.cu)
+bool tconv_tc_supported(const bsde_conv_layer* L, int epi);
+int tconv_fwd_tc(const bsde_conv_layer* L, int S, int B, const float* in, const float* w,
+                 long long w_sample_stride, float t, int act, int epi, float scale, const float* aux,
+                 float* out, cudaStream_t st);
+
+static int conv_fwd(const bsde_conv_layer* L, int S, int B, const float* in, const float* w,
+                    long long wss, float t, int act, int epi, float scale, const float* aux, float* out,
+                    int math, cudaStream_t st) {
+  if (math == BSDE_MATH_TC && tconv_tc_supported(L, epi))
+    return tconv_fwd_tc(L, S, B, in, w, wss, t, act, epi, scale, aux, out, st);
+  return tconv_fwd_simt(L, S, B, in, w, wss, t, act, epi, scale, aux, out, st);
+}
+
+// data-gradient descriptor of a forward layer: reduce over cout, produce cin, inverted spatial map
+static bsde_conv_layer dgrad_layer(const bsde_conv_layer& F) {
+  bsde_conv_layer D = F;
+  D.cin = F.cout;
+  D.cout = F.cin;
+  D.hin = F.hout; D.win = F.wout; D.hout = F.hin; D.wout = F.win;
+  // forward: i = (o*sn + k*kn + off)/sd  <=>  o = (i*sd - k*kn - off)/sn
+  D.sn = F.sd; D.kn = -F.kn; D.off = -F.off; D.sd = F.sn;
+  D.has_time = 0; D.time_first = 0;
+  D.b_off = -1;
+  // weight index = w_off + tap*ts + row(c)*ks + n*ns ; real channel c lives in row c + (time_first?1:0)
+  D.w_off = F.w_off + ((F.has_time && F.time_first) ? F.w_k_stride : 0);
+  D.w_k_stride = F.w_n_stride;  // reduction runs over the forward output channel
+  D.w_n_stride = F.w_k_stride;  // output runs over the forward input channel
+  return D;
+}
+
+static size_t act_elems(const bsde_xpath_desc* d, int l) {  // output of layer l
+  const bsde_conv_layer& L = d->layers[l];
+  return (size_t)d->S * d->B * L.hout * L.wout * L.cout;
+}
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace bsde
+
+using namespace bsde;
+
+extern "C" int bsde_version(void) { return BSDE_VERSION; }
+extern "C" const char* bsde_last_error(void) { return g_err; }
+
+extern "C" int bsde_tconv_fwd(const bsde_conv_layer* L, int32_t S, int32_t B, const float* d_in,
+                              const float* d_w, int64_t w_sample_stride, float t, int32_t act,
+                              int32_t epilogue, float scale, const float* d_aux, float* d_out, int32_t math,
+                              void* stream) {
+  BSDE_CHECK_ARG(d_in && d_w && d_out, "NULL tensor pointer");
+  return conv_fwd(L, S, B, d_in, d_w, w_sample_stride, t, act, epilogue, scale, d_aux, d_out, math,
+                  (cudaStream_t)stream);
+}
+
+extern "C" size_t bsde_tconv_wgrad_workspace_bytes(const bsde_conv_layer* L, int32_t S, int32_t B) {
+  if (!L) return 0;
+  return tconv_wgrad_ws_simt(L, S, B);
+}
+
+extern "C" int bsde_tconv_wgrad(const bsde_conv_layer* L, int32_t S, int32_t B, const float* d_in,
+                                const float* d_dy, float t, float scale, float* d_gw,
+                                int64_t gw_sample_stride, int32_t math, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  BSDE_CHECK_ARG(d_in && d_dy && d_gw, "NULL tensor pointer");
+  (void)math;
+  return tconv_wgrad_simt(L, S, B, d_in, d_dy, t, scale, d_gw, gw_sample_stride, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// x-path scan.  Workspace layout:  a_0..a_{n-2} (layer outputs), [bwd: dz_0..dz_{n-2}, wgrad scratch]
+// ---------------------------------------------------------------------------------------------
+static int xpath_check(const bsde_xpath_desc* d) {
+  BSDE_CHECK_ARG(d != nullptr, "NULL descriptor");
+  BSDE_CHECK_ARG(d->nlayers >= 2 && d->nlayers <= BSDE_MAX_LAYERS, "nlayers=%d unsupported", d->nlayers);
+  BSDE_CHECK_ARG(d->S >= 1 && d->B >= 1 && d->nit >= 1, "S, B, nit must be positive");
+  BSDE_CHECK_ARG(d->act >= BSDE_ACT_SOFTPLUS && d->act <= BSDE_ACT_ELU, "fx activation %d unsupported", d->act);
+  const bsde_conv_layer& L0 = d->layers[0];
+  const bsde_conv_layer& Ln = d->layers[d->nlayers - 1];
+  BSDE_CHECK_ARG(L0.cin == Ln.cout && L0.hin == Ln.hout && L0.win == Ln.wout,
+                 "fx must map its input shape to itself (brax.py:40)");
+  BSDE_CHECK_ARG((int64_t)d->S * d->B * L0.hin * L0.win * L0.cin == d->x_numel, "x_numel mismatch");
+  for (int l = 0; l + 1 < d->nlayers; ++l)
+    BSDE_CHECK_ARG(d->layers[l].cout == d->layers[l + 1].cin && d->layers[l].hout == d->layers[l + 1].hin &&
+                       d->layers[l].wout == d->layers[l + 1].win,
+                   "layer %d output does not match layer %d input", l, l + 1);
+  return 0;
+}
+
+extern "C" size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t backward) {
+  if (!d || d->nlayers < 2 || d->nlayers > BSDE_MAX_LAYERS) return 0;
+  size_t tot = 0;
+  for (int l = 0; l + 1 < d->nlayers; ++l) tot += align_up(act_elems(d, l) * sizeof(float)) * (backward ? 2 : 1);
+  if (backward) {
+    size_t wg = 0;
+    for (int l = 0; l < d->nlayers; ++l) {
+      size_t b = tconv_wgrad_ws_simt(&d->layers[l], d->S, d->B);
+      if (b > wg) wg = b;
+    }
+    tot += align_up(wg);
+  }
+  return tot;
+}
+
+static int xpath_recompute(const bsde_xpath_desc* d, const float* x, const float* wk, float t, float* const* a,
+                           cudaStream_t st) {
+  const int n = d->nlayers;
+  const long long wss = (long long)(d->nit + 1) * d->P;
+  const float* in = x;
+  for (int l = 0; l + 1 < n; ++l) {
+    if (int e = conv_fwd(&d->layers[l], d->S, d->B, in, wk, wss, t, d->act, BSDE_EPI_BIAS_ACT, 1.f, nullptr,
+                         a[l], d->math, st))
+      return e;
+    in = a[l];
+  }
+  return 0;
+}
+
+extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const float* h_dtk,
+                              const float* d_wtraj, float* d_xs, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  if (int e = xpath_check(d)) return e;
+  BSDE_CHECK_ARG(h_tk && h_dtk && d_wtraj && d_xs, "NULL pointer");
+  const size_t need = bsde_xpath_workspace_bytes(d, 0);
+  if (!workspace || workspace_bytes < need) {
+    set_error("xpath_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
+    return BSDE_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = d->nlayers;
+  float* a[BSDE_MAX_LAYERS];
+  char* ws = (char*)workspace;
+  for (int l = 0; l + 1 < n; ++l) { a[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
+  const long long wss = (long long)(d->nit + 1) * d->P;
+  for (int k = 0; k < d->nit; ++k) {
+    const float* xk = d_xs + (size_t)k * d->x_numel;
+    float* xn = d_xs + (size_t)(k + 1) * d->x_numel;
+    const float* wk = d_wtraj + (size_t)k * d->P;
+    if (int e = xpath_recompute(d, xk, wk, h_tk[k], a, st)) return e;
+    // last conv + Euler update: x_{k+1} = x_k + dt_k (conv(a_{n-2}) + b)   (sdeint.py:48-50, g_x = 0)
+    if (int e = conv_fwd(&d->layers[n - 1], d->S, d->B, a[n - 2], wk, wss, h_tk[k], d->act, BSDE_EPI_EULER,
+                         h_dtk[k], xk, xn, d->math, st))
+      return e;
+  }
+  return 0;
+}
+
+extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const float* h_dtk,
+                              const float* d_wtraj, const float* d_xs, float* d_gx, float* d_gw_traj,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = xpath_check(d)) return e;
+  BSDE_CHECK_ARG(h_tk && h_dtk && d_wtraj && d_xs && d_gx && d_gw_traj, "NULL pointer");
+  const size_t need = bsde_xpath_workspace_bytes(d, 1);
+  if (!workspace || workspace_bytes < need) {
+    set_error("xpath_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
+    return BSDE_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = d->nlayers;
+  float* a[BSDE_MAX_LAYERS];
+  float* dz[BSDE_MAX_LAYERS];
+  char* ws = (char*)workspace;
+  for (int l = 0; l + 1 < n; ++l) { a[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
+  for (int l = 0; l + 1 < n; ++l) { dz[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
+  void* wg_ws = ws;
+  const size_t wg_bytes = workspace_bytes - (size_t)(ws - (char*)workspace);
+  const long long wss = (long long)(d->nit + 1) * d->P;
+  const long long gss = (long long)d->nit * d->P;
+
+  bsde_conv_layer D[BSDE_MAX_LAYERS];
+  for (int l = 0; l < n; ++l) D[l] = dgrad_layer(d->layers[l]);
+
+  for (int k = d->nit - 1; k >= 0; --k) {
+    const float t = h_tk[k], dt = h_dtk[k];
+    const float* xk = d_xs + (size_t)k * d->x_numel;
+    const float* wk = d_wtraj + (size_t)k * d->P;
+    float* gwk = d_gw_traj + (size_t)k * d->P;
+    if (int e = xpath_recompute(d, xk, wk, t, a, st)) return e;
+    // walk the stack backwards; `dy` is dL/d(conv output of layer l)
+    const float* dy = d_gx;  // for the last layer dL/d(conv out) = dt * gx  (scale folded below)
+    for (int l = n - 1; l >= 0; --l) {
+      const float* lin = l == 0 ? xk : a[l - 1];
+      const float sc = (l == n - 1) ? dt : 1.f;
+      if (int e = tconv_wgrad_simt(&d->layers[l], d->S, d->B, lin, dy, t, sc, gwk, gss, wg_ws, wg_bytes, st)) return e;
+      if (l > 0) {
+        // dz_{l-1} = sc * dgrad(dy) * act'(a_{l-1})
+        if (int e = conv_fwd(&D[l], d->S, d->B, dy, wk, wss, t, d->act, BSDE_EPI_DACT, sc, a[l - 1], dz[l - 1],
+                             BSDE_MATH_FP32, st))
+          return e;
+        dy = dz[l - 1];
+      } else {
+        // gx_k = gx_{k+1} + dgrad_0(dz_0)   (identity path of the Euler update)
+        if (int e = conv_fwd(&D[0], d->S, d->B, dy, wk, wss, t, d->act, BSDE_EPI_ACCUM, sc, d_gx, d_gx,
+                             BSDE_MATH_FP32, st))
+          return e;
+      }
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic flat-state step (jaxsde/jaxsde/sdeint.py:36-50) and Philox increments
+// ---------------------------------------------------------------------------------------------
+namespace bsde {
+__global__ void step_update_kernel(int method, long long n, float dt, const float* __restrict__ y,
+                                   const float* __restrict__ f, const float* __restrict__ g,
+                                   const float* __restrict__ dW, const float* __restrict__ gdg,
+                                   const float* __restrict__ g2, float* __restrict__ y1) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float w = dW[i];
+    float v = y[i] + dt * f[i];
+    if (method == BSDE_EULER_HEUN && g2) v += 0.5f * (g[i] + g2[i]) * w;
+    else v += g[i] * w;
+    if (method == BSDE_MILSTEIN && gdg) v += 0.5f * gdg[i] * (w * w - dt);
+    y1[i] = v;
+  }
+}
+
+__global__ void philox_increments_kernel(uint64_t seed, uint32_t stream_id, int S, int nit, long long P,
+                                         const float* __restrict__ dtk, float* __restrict__ out) {
+  const long long total = (long long)S * nit * P;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % P;
+    const long long r = i / P;
+    const int k = (int)(r % nit), s = (int)(r / nit);
+    out[i] = sqrtf(fmaxf(dtk[k], 0.f)) * philox_normal(seed, (uint32_t)p, (uint32_t)k, (uint32_t)s, stream_id);
+  }
+}
+}  // namespace bsde
+
+extern "C" int bsde_step_update(int32_t method, int64_t n, float dt, const float* d_y, const float* d_f,
+                                const float* d_g, const float* d_dW, const float* d_gdg, const float* d_g2,
+                                float* d_y1, void* stream) {
+  BSDE_CHECK_ARG(method >= BSDE_EULER_MARUYAMA && method <= BSDE_EULER_HEUN, "Unknown method: %d", method);
+  BSDE_CHECK_ARG(n >= 0, "n must be >= 0");
+  if (n == 0) return 0;
+  BSDE_CHECK_ARG(d_y && d_f && d_g && d_dW && d_y1, "NULL tensor pointer");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  step_update_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(method, n, dt, d_y, d_f, d_g, d_dW, d_gdg, d_g2, d_y1);
+  BSDE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bsde_philox_increments(uint64_t seed, uint32_t stream_id, int32_t S, int32_t nit, int64_t P,
+                                      const float* d_dtk, float* d_out, void* stream) {
+  BSDE_CHECK_ARG(S >= 1 && nit >= 1 && P >= 1, "S, nit, P must be positive");
+  BSDE_CHECK_ARG(d_dtk && d_out, "NULL tensor pointer");
+  const long long total = (long long)S * nit * P;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  philox_increments_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(seed, stream_id, S, nit, P, d_dtk, d_out);
+  BSDE_CUDA_OK(cudaGetLastError());
+  return 0;
+}

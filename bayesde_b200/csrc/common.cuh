@@ -1,0 +1,100 @@
+// Shared device helpers for libbsde.so (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/bsde.h"
+
+namespace bsde {
+
+void set_error(const char* fmt, ...);
+
+#define BSDE_CHECK_ARG(cond, ...)        \
+  do {                                   \
+    if (!(cond)) {                       \
+      bsde::set_error(__VA_ARGS__);      \
+      return BSDE_ERR_INVALID_ARG;       \
+    }                                    \
+  } while (0)
+
+#define BSDE_CUDA_OK(expr)                                                          \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      bsde::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return BSDE_ERR_CUDA;                                                         \
+    }                                                                               \
+  } while (0)
+
+// ---- activations (brax/_impl/arch.py:31-32; torch.nn.Softplus threshold 20 is also what
+// jax.nn.softplus = logaddexp(x,0) evaluates to in fp32 for x > 20) -------------------------------
+__device__ __forceinline__ float act_fwd(int act, float x) {
+  switch (act) {
+    case BSDE_ACT_SOFTPLUS: return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
+    case BSDE_ACT_TANH: return tanhf(x);
+    case BSDE_ACT_ELU: return x > 0.f ? x : expm1f(x);
+    default: return x;
+  }
+}
+// derivative expressed through the activation OUTPUT a = act(x)
+__device__ __forceinline__ float act_grad_from_out(int act, float a) {
+  switch (act) {
+    case BSDE_ACT_SOFTPLUS: return -expm1f(-a);  // sigmoid(x) = 1 - exp(-softplus(x))
+    case BSDE_ACT_TANH: return 1.f - a * a;
+    case BSDE_ACT_ELU: return a > 0.f ? 1.f : a + 1.f;
+    default: return 1.f;
+  }
+}
+// derivative expressed through the pre-activation x
+__device__ __forceinline__ float act_grad(int act, float x) {
+  switch (act) {
+    case BSDE_ACT_SOFTPLUS: return 1.f / (1.f + expf(-x));
+    case BSDE_ACT_TANH: { float a = tanhf(x); return 1.f - a * a; }
+    case BSDE_ACT_ELU: return x > 0.f ? 1.f : expf(x);
+    default: return 1.f;
+  }
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter-based ----------------------------------------
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+  const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+  c[0] = hi1 ^ c[1] ^ k0;
+  c[1] = lo1;
+  c[2] = hi0 ^ c[3] ^ k1;
+  c[3] = lo0;
+}
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+// one standard normal for (element p, iteration k, sample s, stream id)
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t p, uint32_t k, uint32_t s,
+                                               uint32_t stream_id) {
+  uint32_t c[4] = {p, k, s, stream_id};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  // Box-Muller on two 32-bit uniforms in (0,1]
+  const float u1 = ((float)c[0] + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+  const float u2 = (float)c[1] * 2.3283064365386963e-10f;           // [0,1)
+  const float r = sqrtf(-2.0f * logf(fmaxf(u1, 1e-37f)));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  (void)sn;
+  return r * cs;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace bsde

@@ -1,0 +1,214 @@
+/*
+ * bsde.h -- C ABI of libbsde.so: the B200 (sm_100a) kernels behind bayeSDE's fixed-grid
+ * SDE-BNN hot path.  Plain pointers and sizes only; no torch / C++ types cross this line.
+ *
+ * Conventions
+ *   - every pointer named d_* / documented "device" is a CUDA device pointer owned by the
+ *     CALLER (PyTorch).  The library never allocates or frees tensor memory; scratch space
+ *     is passed in as `workspace` and sized with the *_workspace_bytes() queries.
+ *   - every entry point is stream-ordered on `stream` (a cudaStream_t passed as void*),
+ *     never synchronises the device, and returns 0 on success or a negative bsde_status.
+ *     bsde_last_error() returns a thread-local message for the last failure.
+ *   - all arithmetic is fp32 (the reference examples run in fp32).
+ *
+ * Reference interfaces replaced (paths relative to the xwinxu/bayeSDE tree):
+ *   bsde_wsde_fwd/bwd        f_aug's dw/dkl rows + g_aug + the Euler/Milstein update of the
+ *                            [w, kl] rows for all scan iterations:
+ *                            brax/_impl/brax.py:49-78, brax/_impl/arch.py:34-74,
+ *                            brax/_impl/diffeq_layers.py:73-96, jaxsde/jaxsde/sdeint.py:36-50,103-110
+ *   bsde_tconv_fwd/wgrad     one ConcatConv2D (time channel appended, 3x3 / 1x1, SAME, stride 2,
+ *                            transposed) with weights taken from the state w(t):
+ *                            brax/_impl/diffeq_layers.py:124-150, torchbnn/_impl/diffeq_layers.py:75-166
+ *   bsde_xpath_fwd/bwd       the x rows of the same scan (f_x conv stack + Euler update) for all
+ *                            iterations, and its hand-written reverse pass with recomputation:
+ *                            brax/_impl/arch.py:171-210, brax/_impl/brax.py:52,113,131-132,
+ *                            jaxsde/jaxsde/sdeint.py:103-110,135
+ *   bsde_step_update         ito_euler_step / ito_milstein_step on a flat state for arbitrary
+ *                            user f, g: jaxsde/jaxsde/sdeint.py:36-50 (+ euler_heun, :73-74 stub)
+ *   bsde_philox_increments   replaces make_brownian_motion / virtual_brownian_tree queries
+ *                            bm(next_t)-bm(curr_t): jaxsde/jaxsde/brownian.py:26-95, sdeint.py:108
+ */
+#ifndef BSDE_H_
+#define BSDE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSDE_VERSION 100
+
+typedef enum {
+  BSDE_OK = 0,
+  BSDE_ERR_INVALID_ARG = -1,
+  BSDE_ERR_UNSUPPORTED = -2,
+  BSDE_ERR_CUDA = -3,
+  BSDE_ERR_WORKSPACE = -4
+} bsde_status;
+
+/* activations: brax/_impl/arch.py:31-32 ACTFNS (swish carries trainable state: unsupported here) */
+typedef enum { BSDE_ACT_SOFTPLUS = 0, BSDE_ACT_TANH = 1, BSDE_ACT_ELU = 2, BSDE_ACT_NONE = 3 } bsde_act;
+
+typedef enum { BSDE_EULER_MARUYAMA = 0, BSDE_MILSTEIN = 1, BSDE_EULER_HEUN = 2 } bsde_method;
+
+/* conv arithmetic mode: exact fp32 FMA on CUDA cores, or tcgen05 tensor-core tiles */
+typedef enum { BSDE_MATH_FP32 = 0, BSDE_MATH_TC = 1 } bsde_math;
+
+int bsde_version(void);
+const char* bsde_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1: weight-SDE path  (one SDEBNN block, S Monte-Carlo samples, all scan iterations)
+ * ---------------------------------------------------------------------------------------- */
+
+#define BSDE_FW_MAX_MID 4   /* ConcatSquashLinear layers strictly between the first and last  */
+#define BSDE_FW_MAX_EDGE 4  /* max width of the first hidden layer d1 and the last hidden dL   */
+#define BSDE_FW_MAX_HID 256 /* max width of a middle hidden layer                               */
+
+/* f_w = MLP(fw_dims, xt=True): P -> d[0] -> ... -> d[n-1] -> P, every layer a
+ * ConcatSquashLinear (W,b,w_t,w_tb,b_t).  The same struct shape carries the gradients. */
+typedef struct {
+  int32_t P;       /* w_dim */
+  int32_t nhid;    /* len(fw_dims) >= 1 */
+  int32_t dims[BSDE_FW_MAX_MID + 2]; /* fw_dims */
+  int32_t act;     /* bsde_act between layers (fw_actfn) */
+  /* first layer  P -> d1 :  W1 [P][d1] row-major, then b,w_t,w_tb,b_t [d1] each */
+  float* W1; float* b1; float* wt1; float* wtb1; float* bt1;
+  /* middle layers i=0..nhid-2 : d[i] -> d[i+1] :  W [d[i]][d[i+1]], b,w_t,w_tb,b_t [d[i+1]] */
+  float* Wm[BSDE_FW_MAX_MID]; float* bm[BSDE_FW_MAX_MID]; float* wtm[BSDE_FW_MAX_MID];
+  float* wtbm[BSDE_FW_MAX_MID]; float* btm[BSDE_FW_MAX_MID];
+  /* last layer  dL -> P :  W4 [dL][P] row-major, b,w_t,w_tb,b_t [P] each */
+  float* W4; float* b4; float* wt4; float* wtb4; float* bt4;
+} bsde_fw_params;
+
+typedef struct {
+  int32_t S;          /* Monte-Carlo samples integrated together */
+  int32_t nit;        /* scan iterations = len(ts)-1 */
+  int32_t stl;        /* 0: g_kl = 0; 1: kl += u(w_stale, t_k) * dW_k  (brax.py:64-78, quirk Q2) */
+  int32_t w0_per_sample; /* 0: w0 is [P] shared by all samples; 1: w0 is [S][P] */
+  float sigma;        /* diff_coef */
+  float kl_weight;    /* integrand is kl_weight * u^2 : 1 for brax (brax.py:61) */
+  float ou_coef;      /* drift = f_w(w,t) + ou_coef*w : 0 for brax as shipped (quirk Q3), -1 for
+                         torchbnn (models.py:165); u = (f_w + (ou_coef+1) w)/sigma (prior drift -w) */
+  uint64_t seed;      /* Philox key when d_dW == NULL */
+  uint32_t stream_id; /* Philox sub-stream (block index in the network) */
+} bsde_wsde_desc;
+
+size_t bsde_wsde_workspace_bytes(const bsde_wsde_desc* d, const bsde_fw_params* fw);
+
+/* Forward.  d_tk,d_dtk: [nit] device floats (t_k, dt_k of each scan iteration).
+ * d_dW: [S][nit][P] supplied increments or NULL for in-kernel Philox.
+ * d_w_stale: [P] (only read when stl=1).
+ * Outputs: d_wtraj [S][nit+1][P] (w_0..w_nit), d_z1 nit*S*d1 floats (first-layer dots, opaque, kept for
+ * the reverse pass), d_kl [S] (sum over P of the kl rows at the final time, brax.py:119). */
+int bsde_wsde_fwd(const bsde_wsde_desc* d, const bsde_fw_params* fw, const float* d_w0,
+                  const float* d_tk, const float* d_dtk, const float* d_dW, const float* d_w_stale,
+                  float* d_wtraj, float* d_z1, float* d_kl, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* Reverse pass.  d_gw_traj: [S][nit][P] dL/dw_k contributions from the x rows (conv wgrads,
+ * already multiplied by dt_k) or NULL; d_gkl [S] = dL/dkl_s; d_gwT [S][P] = dL/dw_nit or NULL.
+ * Outputs: d_gw0 ([P] summed over samples, or [S][P] when w0_per_sample), `gfw` = gradient
+ * buffers with the layout of `fw` (overwritten, summed over samples). */
+int bsde_wsde_bwd(const bsde_wsde_desc* d, const bsde_fw_params* fw, const float* d_tk,
+                  const float* d_dtk, const float* d_wtraj, const float* d_z1,
+                  const float* d_gw_traj, const float* d_gkl, const float* d_gwT, float* d_gw0,
+                  const bsde_fw_params* gfw, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2: time-dependent convolution with weights taken from a flat weight vector
+ * ---------------------------------------------------------------------------------------- */
+
+/* One ConcatConv2D-style layer.  Activations are always NHWC in device memory (the torch front
+ * end keeps its NCHW tensors in channels-last storage).  The kernel layout is described by
+ * strides: HWIO with the time channel LAST for the JAX front end, OIHW / IOHW with the time
+ * channel FIRST for the torch front end.  Spatial map (per axis):
+ *     num = o*sn + k*kn + off ;  valid iff num >= 0, num % sd == 0, num/sd < in_size ; i = num/sd
+ * which covers SAME / explicit padding, stride 2, lhs-dilated (transposed) convs and all their
+ * data gradients. */
+typedef struct {
+  int32_t cin, cout;         /* real channels (time channel excluded) */
+  int32_t ksize;             /* 1 or 3 */
+  int32_t hin, win, hout, wout;
+  int32_t sn, kn, off, sd;   /* spatial map */
+  int32_t has_time;          /* 1: a constant channel t takes part in the reduction */
+  int32_t time_first;        /* weight row of the time channel: 0 -> index cin, 1 -> index 0 */
+  int64_t w_off, b_off;      /* offsets into the flat weight vector; b_off < 0: no bias */
+  int64_t w_tap_stride, w_k_stride, w_n_stride; /* weight index = w_off + tap*ts + kc*ks + n*ns */
+} bsde_conv_layer;
+
+typedef enum {
+  BSDE_EPI_BIAS = 0,      /* y = acc + b                                  */
+  BSDE_EPI_BIAS_ACT = 1,  /* y = act(acc + b)                             */
+  BSDE_EPI_EULER = 2,     /* y = aux + scale*(acc + b)      (aux = x_k)   */
+  BSDE_EPI_DACT = 3,      /* y = scale*acc*act'(aux)        (aux = act output at y's position) */
+  BSDE_EPI_ACCUM = 4      /* y = aux + scale*acc            (aux may alias y) */
+} bsde_epilogue;
+
+/* y[n,...] = epilogue( sum_{tap,c} in(n, map(o,tap), c) * w[sample(n)][tap,c,:] ).
+ * images n in [0, S*B); image n uses the weight vector d_w + (n / B) * w_sample_stride. */
+int bsde_tconv_fwd(const bsde_conv_layer* L, int32_t S, int32_t B, const float* d_in,
+                   const float* d_w, int64_t w_sample_stride, float t, int32_t act,
+                   int32_t epilogue, float scale, const float* d_aux, float* d_out, int32_t math,
+                   void* stream);
+
+size_t bsde_tconv_wgrad_workspace_bytes(const bsde_conv_layer* L, int32_t S, int32_t B);
+
+/* d_gw[s][w_off + ...] = scale * sum_{n in sample s, o} in(n, map(o,tap), c) * dy[n,o,:]  (and the
+ * bias / time-channel rows), written with the layer's weight strides. */
+int bsde_tconv_wgrad(const bsde_conv_layer* L, int32_t S, int32_t B, const float* d_in,
+                     const float* d_dy, float t, float scale, float* d_gw, int64_t gw_sample_stride,
+                     int32_t math, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2+K3: the x rows of one SDEBNN block over all scan iterations, and the reverse pass
+ * ---------------------------------------------------------------------------------------- */
+
+#define BSDE_MAX_LAYERS 4
+
+typedef struct {
+  int32_t S, B;            /* samples, images per sample */
+  int32_t nit;             /* scan iterations */
+  int32_t nlayers;         /* convs in f_x (arch.py:176-205: 4, 3 or 2) */
+  int32_t act;             /* fx_actfn */
+  int32_t math;            /* bsde_math */
+  int64_t P;               /* w_dim: stride between w_k and w_{k+1} in d_wtraj */
+  int64_t x_numel;         /* S*B*H*W*C */
+  bsde_conv_layer layers[BSDE_MAX_LAYERS];
+} bsde_xpath_desc;
+
+size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t backward);
+
+/* h_tk,h_dtk: HOST arrays [nit].  d_wtraj: [S][nit+1][P].  d_xs: [nit+1][x_numel]; slot 0 holds
+ * x_0 on entry, slot k+1 is written with x_{k+1} = x_k + dt_k f_x(x_k, t_k; w_k). */
+int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const float* h_dtk,
+                   const float* d_wtraj, float* d_xs, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+/* d_gx: [x_numel] holds dL/dx_nit on entry and dL/dx_0 on return.  d_gw_traj: [S][nit][P] receives
+ * dL/dw_k through the convolutions (every element of every slot is written). */
+int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const float* h_dtk,
+                   const float* d_wtraj, const float* d_xs, float* d_gx, float* d_gw_traj,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * generic flat-state step and Brownian increments
+ * ---------------------------------------------------------------------------------------- */
+
+/* y1 = y + dt*f + g*dW  [+ 0.5*gdg*(dW^2 - dt)  (milstein, d_gdg = J_g (.) g, may be NULL)]
+ *                       [heun: y + dt*f + 0.5*(g + g2)*dW, d_g2 = g(y + g dW, t+dt)]          */
+int bsde_step_update(int32_t method, int64_t n, float dt, const float* d_y, const float* d_f,
+                     const float* d_g, const float* d_dW, const float* d_gdg, const float* d_g2,
+                     float* d_y1, void* stream);
+
+/* out[s][k][p] = sqrt(max(dt_k,0)) * N(0,1) from Philox4x32-10 keyed (seed) with counter
+ * (p, k, s, stream_id): the stream bsde_wsde_fwd consumes when d_dW == NULL. */
+int bsde_philox_increments(uint64_t seed, uint32_t stream_id, int32_t S, int32_t nit, int64_t P,
+                           const float* d_dtk, float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSDE_H_ */

@@ -1,0 +1,324 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the reference-shaped Python API) against
+the CPU oracle on the same seeded inputs and the same Brownian increments.
+
+Tolerances (fp32 path, `math="fp32"`; the reference states none -- SURVEY.md 8.3):
+  * single conv / MLP evaluation vs fp64 oracle:      rtol 1e-5, atol 1e-5
+  * w trajectory after all scan iterations:          rtol 1e-5, atol 1e-6
+  * sum-KL, loss:                                    rtol 1e-4
+  * gradients vs fp64 oracle autograd:               rtol 1e-3 (atol scaled to the tensor's max)
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import jax_path as jp
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _close(a, b, rtol, atol, what=""):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{a.numel()} mismatches, max err {err.max():.3e} " \
+                          f"(ref max {b.abs().max():.3e})"
+
+
+def _gclose(a, b, rtol=1e-3, what=""):
+    b64 = b.detach().double().cpu()
+    _close(a, b, rtol, rtol * 1e-2 * float(b64.abs().max()) + 1e-12, what)
+
+
+def _conv_struct(L):
+    from bayesde_b200 import _lib
+    c = _lib.ConvLayer()
+    c.cin, c.cout, c.ksize = L["cin"], L["cout"], L["k"]
+    c.hin, c.win, c.hout, c.wout = L["hin"], L["win"], L["hout"], L["wout"]
+    c.sn, c.kn, c.off, c.sd = L["sn"], L["kn"], L["off"], L["sd"]
+    c.has_time, c.time_first = 1, 0
+    c.w_off, c.b_off = L["w_off"], L["b_off"]
+    c.w_tap_stride, c.w_k_stride, c.w_n_stride = (L["cin"] + 1) * L["cout"], L["cout"], 1
+    return c
+
+
+@pytest.mark.parametrize("C_in,fx_dim,H", [(5, 64, 8), (3, 8, 6), (20, 64, 16), (80, 16, 4)])
+def test_tconv_layers_forward_and_wgrad(built_lib, C_in, fx_dim, H):
+    """Every conv geometry of build_fx block_type 0 (stride 1 SAME, stride 2 SAME, transposed, Cout=C)
+    against the oracle's ConcatConv2D, plus the weight gradient against fp64 autograd."""
+    from bayesde_b200 import _lib
+    from bayesde_b200.arch import FxSpec
+    L = _lib.lib()
+    S, B, t = 2, 3, 0.37
+    fx = FxSpec(0, (1, H, H, C_in), fx_dim, "softplus")
+    layout, P = jp.fx_layout(0, C_in, fx_dim)
+    assert P == fx.P
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(S, P, generator=g, dtype=torch.float64) * 0.2
+    conv_entries = [e for e in layout if e["kind"] == "conv"]
+    for li, (Ld, e) in enumerate(zip(fx.layers, conv_entries)):
+        x = torch.randn(S, B, Ld["hin"], Ld["win"], Ld["cin"], generator=g, dtype=torch.float64)
+        n = e["k"] ** 2 * (e["cin"] + 1) * e["cout"]
+        refs = []
+        for s in range(S):
+            ws = w[s].clone().requires_grad_(True)
+            refs.append((jp.concat_conv2d(x[s], t, ws[e["w_off"]:e["w_off"] + n].reshape(e["w_shape"]),
+                                          ws[e["b_off"]:e["b_off"] + e["cout"]], e["stride"], e["transpose"]), ws))
+        ref = torch.stack([r[0] for r in refs])
+        assert ref.shape[2] == Ld["hout"] and ref.shape[4] == Ld["cout"]
+        cs = _conv_struct(Ld)
+        xd = x.float().to(DEV).contiguous()
+        wd = w.float().to(DEV).contiguous()
+        out = torch.empty(ref.shape, device=DEV)
+        st = L.bsde_tconv_fwd(C.byref(cs), S, B, _lib.ptr(xd), _lib.ptr(wd), P, t, 0, _lib.EPI_BIAS, 1.0, None,
+                              _lib.ptr(out), 0, _lib.stream_ptr())
+        _lib.check(st, "tconv_fwd")
+        _close(out, ref, 1e-5, 1e-5, f"conv layer {li} forward")
+        # weight gradient
+        dy = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+        gref = []
+        for s in range(S):
+            (gw,) = torch.autograd.grad((refs[s][0] * dy[s]).sum(), refs[s][1])
+            gref.append(gw)
+        gref = torch.stack(gref)
+        gw = torch.zeros(S, P, device=DEV)
+        nb = L.bsde_tconv_wgrad_workspace_bytes(C.byref(cs), S, B)
+        ws_buf = torch.empty(nb, dtype=torch.uint8, device=DEV)
+        st = L.bsde_tconv_wgrad(C.byref(cs), S, B, _lib.ptr(xd), _lib.ptr(dy.float().to(DEV).contiguous()), t, 0.5,
+                                _lib.ptr(gw), P, 0, C.c_void_p(ws_buf.data_ptr()), nb, _lib.stream_ptr())
+        _lib.check(st, "tconv_wgrad")
+        _gclose(gw, 0.5 * gref, 1e-4, f"conv layer {li} wgrad")
+
+
+def _product_fw_params(fw_layers, device):
+    """oracle list of 5-tuples -> reference-shaped pytree ((), [lay, (), ..., lay]) on device."""
+    tree = []
+    for i, lay in enumerate(fw_layers):
+        tree.append(tuple(t.float().to(device).contiguous().requires_grad_(True) for t in lay))
+        if i < len(fw_layers) - 1:
+            tree.append(())
+    return ((), tree)
+
+
+def _block_case(S=2, B=2, H=8, C_in=5, fx_dim=8, nsteps=6, sigma=0.2, stl=False, fw_dims=(2, 16, 2),
+                time_grid="reference", seed=0, fx_actfn="softplus", fw_actfn="softplus"):
+    g = torch.Generator().manual_seed(seed)
+    blk = jp.SDEBNNBlock((B, H, H, C_in), 0, fx_dim, fx_actfn, fw_actfn, sigma, stl, nsteps,
+                         time_grid_mode=time_grid)
+    w0 = jp.init_fx(blk.layout, blk.P, g, torch.float64)
+    fw = jp.init_fw(blk.P, fw_dims, g, torch.float64, last_std=0.05)
+    x = torch.randn(S, B, H, H, C_in, generator=g, dtype=torch.float64)
+    dW = torch.stack([jp.sample_increments(blk.P, nsteps, g, torch.float64, time_grid) for _ in range(S)])
+    return blk, w0, fw, x, dW
+
+
+def _oracle_block(blk, w0, fw, x, dW, gx_seed=1, kl_w=1e-3):
+    """Per-sample oracle solves (the reference's vmap) + a scalar objective for gradients."""
+    w0 = w0.clone().requires_grad_(True)
+    fw = [tuple(t.clone().requires_grad_(True) for t in lay) for lay in fw]
+    x = x.clone().requires_grad_(True)
+    xs, kls, ws = [], [], []
+    for s in range(x.shape[0]):
+        xo, kl, wtraj = blk.apply((w0, fw), x[s], dW[s])
+        xs.append(xo), kls.append(kl), ws.append(wtraj)
+    xo, kl, wt = torch.stack(xs), torch.stack(kls), torch.stack(ws)
+    g = torch.Generator().manual_seed(gx_seed)
+    cot = torch.randn(xo.shape, generator=g, dtype=torch.float64)
+    obj = (xo * cot).sum() + kl_w * kl.sum()
+    grads = torch.autograd.grad(obj, [x, w0] + [t for lay in fw for t in lay])
+    return xo, kl, wt, cot, grads
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(stl=True), dict(time_grid="uniform", nsteps=5),
+                                dict(S=1, B=3, H=4, C_in=20, fx_dim=16, fw_dims=(1, 8, 1)),
+                                dict(fx_actfn="tanh", fw_actfn="tanh", fw_dims=(2,)),
+                                dict(fx_actfn="elu", fw_actfn="elu", fw_dims=(2, 8, 8, 2), sigma=1e-2)])
+def test_sdebnn_block_forward_backward(built_lib, kw):
+    """One SDEBNN block through the reference-shaped API vs the oracle: x_T, per-sample KL, the whole
+    w trajectory (full_output), and gradients w.r.t. x, w0 and every f_w tensor."""
+    from bayesde_b200 import arch, brax
+    blk, w0, fw, x, dW = _block_case(**kw)
+    stl = kw.get("stl", False)
+    fw_layer = arch.MLP(kw.get("fw_dims", (2, 16, 2)), actfn=kw.get("fw_actfn", "softplus"), xt=True, ou_dw=True)
+    layer = brax.SDEBNN(0, blk.layout[0]["cout"], kw.get("fx_actfn", "softplus"), fw_layer, diff_coef=blk.diff_coef,
+                        stl=stl, xt=True, nsteps=blk.nsteps, time_grid=blk.time_grid_mode)
+    # the oracle's stale vector must be the product's (fx.init(PRNGKey(0)) stand-in), brax.py:38-41
+    _, (w_stale_like, _, _) = layer.init(0, tuple(x.shape[1:]))
+    blk.w_stale = w_stale_like.double()
+    xo_r, kl_r, wt_r, cot, grads_r = _oracle_block(blk, w0, fw, x, dW)
+
+    w0d = w0.float().to(DEV).requires_grad_(True)
+    fwd = _product_fw_params(fw, DEV)
+    xd = x.float().to(DEV).requires_grad_(True)
+    xo, kl, info = layer.apply((w0d, (), fwd), xd, dW.float().to(DEV), full_output=True)
+    _close(xo, xo_r, 1e-4, 1e-5, "x_T")
+    _close(info["sdebnn_w"], wt_r, 1e-5, 1e-6, "w trajectory")
+    _close(kl, kl_r, 1e-4, 1e-6, "sum KL")
+    obj = (xo * cot.float().to(DEV)).sum() + 1e-3 * kl.sum()
+    leaves = [xd, w0d] + [t for lay in arch.fw_layers(fwd) for t in lay]
+    grads = torch.autograd.grad(obj, leaves)
+    names = ["x", "w0"] + [f"fw[{i}].{n}" for i in range(len(fw)) for n in ("W", "b", "w_t", "w_tb", "b_t")]
+    for n, a, b in zip(names, grads, grads_r):
+        _gclose(a, b, 1e-3, f"grad {n}")
+
+
+def test_block_types_1_and_2(built_lib):
+    """arch.py:189-205: block_type 1 (3x3, 1x1, 3x3) and 2 (3x3, 3x3)."""
+    from bayesde_b200 import arch, brax
+    for bt in (1, 2):
+        g = torch.Generator().manual_seed(3)
+        S, B, H, Cc, nsteps = 1, 2, 6, 4, 4
+        blk = jp.SDEBNNBlock((B, H, H, Cc), bt, 8, "softplus", "softplus", 0.1, False, nsteps)
+        w0 = jp.init_fx(blk.layout, blk.P, g, torch.float64)
+        fw = jp.init_fw(blk.P, (2, 8, 2), g, torch.float64, last_std=0.05)
+        x = torch.randn(S, B, H, H, Cc, generator=g, dtype=torch.float64)
+        dW = torch.stack([jp.sample_increments(blk.P, nsteps, g, torch.float64)])
+        xo_r, kl_r, wt_r, cot, grads_r = _oracle_block(blk, w0, fw, x, dW)
+        layer = brax.SDEBNN(bt, 8, "softplus", arch.MLP((2, 8, 2), xt=True, ou_dw=True), diff_coef=0.1, xt=True,
+                            nsteps=nsteps)
+        w0d = w0.float().to(DEV).requires_grad_(True)
+        fwd = _product_fw_params(fw, DEV)
+        xd = x.float().to(DEV).requires_grad_(True)
+        xo, kl = layer.apply((w0d, (), fwd), xd, dW.float().to(DEV))
+        _close(xo, xo_r, 1e-4, 1e-5, f"block_type {bt} x_T")
+        _close(kl, kl_r, 1e-4, 1e-6, f"block_type {bt} KL")
+        grads = torch.autograd.grad((xo * cot.float().to(DEV)).sum() + 1e-3 * kl.sum(), [xd, w0d])
+        _gclose(grads[0], grads_r[0], 1e-3, "grad x")
+        _gclose(grads[1], grads_r[1], 1e-3, "grad w0")
+
+
+def test_methods_coincide_for_sdebnn(built_lib):
+    """g_aug is state-independent (quirk Q2) => milstein == euler_maruyama == euler_heun; the oracle's
+    generic solver (autograd Jacobian) confirms it, and the fused path accepts all three names."""
+    from bayesde_b200 import arch, brax
+    blk, w0, fw, x, dW = _block_case(S=1, B=1, H=4, C_in=3, fx_dim=4, nsteps=4)
+    outs = {}
+    for m in ("euler_maruyama", "milstein", "euler_heun"):
+        blk.method = m
+        xo, kl, _ = blk.apply((w0, fw), x[0], dW[0])
+        outs[m] = (xo, kl)
+        layer = brax.SDEBNN(0, 4, "softplus", arch.MLP((2, 16, 2), xt=True, ou_dw=True), diff_coef=0.2, xt=True,
+                            nsteps=4, method=m)
+        xo_d, kl_d = layer.apply((w0.float().to(DEV), (), _product_fw_params(fw, DEV)), x.float().to(DEV),
+                                 dW.float().to(DEV))
+        _close(xo_d[0], xo, 1e-4, 1e-5, m)
+        _close(kl_d[0], kl, 1e-4, 1e-6, m)
+    _close(outs["milstein"][0], outs["euler_maruyama"][0], 1e-12, 1e-12)
+    _close(outs["euler_heun"][1], outs["euler_maruyama"][1], 1e-12, 1e-12)
+    with pytest.raises(ValueError):
+        brax.SDEBNN(0, 4, "softplus", arch.MLP((2, 16, 2), xt=True), xt=True, nsteps=4, method="rk4").apply(
+            (w0.float().to(DEV), (), _product_fw_params(fw, DEV)), x.float().to(DEV), dW.float().to(DEV))
+
+
+def test_generic_route_vs_oracle(built_lib):
+    """Arbitrary callables f, g (state-dependent diagonal g) through the generic route, all methods,
+    against the oracle's restatement of sdeint.py on the same increments; gradient w.r.t. args."""
+    from bayesde_b200 import sdeint_ito_fixed_grid
+    D, T = 257, 9
+    g_ = torch.Generator().manual_seed(5)
+    y0 = torch.randn(D, generator=g_, dtype=torch.float64)
+    A = torch.randn(D, generator=g_, dtype=torch.float64) * 0.5
+    inc = torch.randn(T - 1, D, generator=g_, dtype=torch.float64) * math.sqrt(1.0 / (T - 1))
+    f = lambda y, t, a: -a * y + torch.sin(t + y)
+    g = lambda y, t, a: 0.3 * torch.cos(y) + 0.1 * a
+    ts = torch.linspace(0.0, 1.0, T)
+    for method in ("euler_maruyama", "milstein", "euler_heun"):
+        for tg in ("reference", "uniform"):
+            a_r = A.clone().requires_grad_(True)
+            ys_r = jp.sdeint_ito_fixed_grid(f, g, y0, ts.double(), inc, a_r, method=method, time_grid_mode=tg)
+            (gr,) = torch.autograd.grad(ys_r[-1].pow(2).sum(), a_r)
+            a_d = A.float().to(DEV).requires_grad_(True)
+            ys = sdeint_ito_fixed_grid(f, g, y0.float().to(DEV), ts, inc.float().to(DEV), a_d, method=method,
+                                       time_grid=tg)
+            assert ys.shape == (T, D)
+            _close(ys, ys_r, 1e-5, 1e-5, f"{method}/{tg}")
+            (gd,) = torch.autograd.grad(ys[-1].pow(2).sum(), a_d)
+            _gclose(gd, gr, 1e-3, f"{method}/{tg} grad")
+    with pytest.raises(ValueError, match="Unknown method"):
+        sdeint_ito_fixed_grid(f, g, y0.float().to(DEV), ts, 0, A.float().to(DEV), method="heun")
+
+
+def test_philox_increments_law_and_in_kernel_stream(built_lib):
+    """(i) mean 0 / variance dt_k (analogue of jaxsde/tests/test_brownian.py:15-45);
+    (ii) the in-kernel stream of K1 equals the materialised one: solving with rng=seed matches solving
+    with the materialised increments passed explicitly; (iii) rep tying (brownian.py:69-74)."""
+    from bayesde_b200 import arch, brax, sdeint_ito_fixed_grid
+    from bayesde_b200.sdeint import philox_increments
+    dtk = np.array([0.05, 0.0, 0.2, 0.05], dtype=np.float32)
+    z = philox_increments(1234, 7, 3, dtk, 200_000, DEV)
+    assert z.shape == (3, 4, 200_000)
+    for k, h in enumerate(dtk):
+        v = z[:, k].double()
+        if h == 0:
+            assert v.abs().max() == 0
+            continue
+        assert abs(v.mean().item()) < 4 * math.sqrt(h / v.numel())
+        assert abs(v.var().item() / h - 1) < 0.01
+        assert abs((v ** 4).mean().item() / (3 * h * h) - 1) < 0.03  # Gaussian kurtosis
+    assert abs(torch.corrcoef(torch.stack([z[0, 0], z[1, 0]]))[0, 1].item()) < 0.01
+    assert not torch.equal(philox_increments(1234, 8, 1, dtk, 1000, DEV), z[:1, :, :1000])
+
+    blk, w0, fw, x, _ = _block_case(S=3, B=1, H=4, C_in=3, fx_dim=4, nsteps=5)
+    layer = brax.SDEBNN(0, 4, "softplus", arch.MLP((2, 16, 2), xt=True, ou_dw=True), diff_coef=0.2, xt=True,
+                        nsteps=5, stream_id=11)
+    params = (w0.float().to(DEV), (), _product_fw_params(fw, DEV))
+    from bayesde_b200._fused import reference_time_grid
+    _, dtk5 = reference_time_grid(np.linspace(0, 1, 5, dtype=np.float32))
+    dW = philox_increments(99, 11, 3, dtk5, blk.P, DEV)
+    xa, kla = layer.apply(params, x.float().to(DEV), 99)
+    xb, klb = layer.apply(params, x.float().to(DEV), dW)
+    assert torch.equal(xa, xb) and torch.equal(kla, klb)
+
+    ys = sdeint_ito_fixed_grid(lambda y, t, a: 0 * y, lambda y, t, a: torch.ones_like(y), torch.zeros(12, device=DEV),
+                               torch.linspace(0, 1, 5), 3, rep=4, time_grid="uniform")
+    assert torch.equal(ys[:, 8:], ys[:, 4:8]) and not torch.equal(ys[:, 0:4], ys[:, 4:8])
+
+
+def test_classifier_loss_and_grads(built_lib):
+    """examples/jax/sdebnn_classification.py model (Augment -> SDEBNN blocks -> squeeze -> ... -> mean-field
+    Dense head), loss = nll + kl*kl_coef/train_size averaged over S samples, gradients of every parameter."""
+    from bayesde_b200.classification import SDEBNNClassifier
+    S, B = 2, 2
+    kw = dict(input_size=(8, 8, 3), aug=1, nblocks=(1, 1), fx_dim=8, fw_dims=(2, 8, 2), diff_coef=0.1, nsteps=5)
+    net_r = jp.SDEBNNClassifier(batch=B, **kw)
+    params_r, head_r = net_r.init(0, torch.float64, fw_last_std=0.05)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, 8, 8, 3, generator=g, dtype=torch.float64)
+    labels = torch.tensor([1, 7])
+    onehot = torch.nn.functional.one_hot(labels, 10).double()
+    dWs = [torch.stack([jp.sample_increments(b.P, 5, g, torch.float64) for _ in range(S)]) for b in net_r.blocks()]
+    eps = torch.randn(S, net_r.feat * 10 + 10, generator=g, dtype=torch.float64)
+    kl_scale = 1e-3 / 100.0
+
+    leaves_r = []
+    pr = []
+    for (w0, fw) in params_r:
+        w0 = w0.clone().requires_grad_(True)
+        fw = [tuple(t.clone().requires_grad_(True) for t in lay) for lay in fw]
+        pr.append((w0, fw))
+        leaves_r += [w0] + [t for lay in fw for t in lay]
+    hr = tuple(tuple(t.clone().requires_grad_(True) for t in pair) for pair in head_r)
+    leaves_r += [hr[0][0], hr[0][1], hr[1][0], hr[1][1]]
+    losses = []
+    for s in range(S):
+        loss, nll, kl, _ = net_r.loss(pr, hr, x, onehot, [d[s] for d in dWs], eps[s], kl_scale)
+        losses.append(loss)
+    loss_r = torch.stack(losses).mean()  # mean over samples of per-sample grads (script :231)
+    grads_r = torch.autograd.grad(loss_r, leaves_r)
+
+    net = SDEBNNClassifier(nsamples=S, device=DEV, **kw)
+    net.load_oracle_params(params_r, head_r)
+    loss, nll, kl = net.loss(x.float().to(DEV), labels.to(DEV), kl_scale,
+                             rng=net.explicit_rng([d.float().to(DEV) for d in dWs], eps.float().to(DEV)))
+    _close(loss, loss_r, 1e-4, 1e-6, "loss")
+    loss.backward()
+    leaves = net.oracle_ordered_parameters()
+    assert len(leaves) == len(leaves_r)
+    for i, (p, gr) in enumerate(zip(leaves, grads_r)):
+        _gclose(p.grad, gr, 2e-3, f"param {i} grad")
