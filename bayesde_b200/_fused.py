@@ -173,6 +173,27 @@ def xpath_backward(cfg, xs, wtraj, gx):
     return gx, gw_traj
 
 
+# Optional CUDA-event bookkeeping for bench.py: when PROFILE is a dict, every K1 / K2 / K3 call is
+# bracketed by events on the launching (current) stream; bench.py sums them after the timed region.
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, key):
+        self.key = key
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.setdefault(self.key, []).append((self.e0, self.e1))
+
+
 class SDEBNNSolve(torch.autograd.Function):
     """ys[-1] of sdeint_ito_fixed_grid(f_aug, g_aug, [x,w0,0], ts, ...) for S samples at once.
 
@@ -184,14 +205,16 @@ class SDEBNNSolve(torch.autograd.Function):
         x = x.contiguous()
         w0c = w0.contiguous()
         layers = [tuple(t.contiguous() for t in lay) for lay in layers]
-        wtraj, z1, kl = wsde_forward(cfg, w0c, layers, dW, seed, stream_id, w_stale)
-        xs = xpath_forward(cfg, x, wtraj)
+        with _Timed("k1_fwd"):
+            wtraj, z1, kl = wsde_forward(cfg, w0c, layers, dW, seed, stream_id, w_stale)
+        with _Timed("k2_fwd"):
+            xs = xpath_forward(cfg, x, wtraj)
         ctx.cfg = cfg
         ctx.layers = layers
         ctx.w0_per_sample = w0.dim() == 2
         ctx.save_for_backward(wtraj, z1, xs)
         ctx.mark_non_differentiable(wtraj)
-        return xs[cfg.nit], kl, wtraj
+        return xs[cfg.nit].clone(), kl, wtraj
 
     @staticmethod
     def backward(ctx, gx, gkl, _gwtraj):
@@ -202,9 +225,11 @@ class SDEBNNSolve(torch.autograd.Function):
             gx = torch.zeros_like(xs[0])
         if gkl is None:
             gkl = torch.zeros(cfg.S, device=dev)
-        gx0, gw_traj = xpath_backward(cfg, xs, wtraj, gx.to(torch.float32))
-        gw0, glayers = wsde_backward(cfg, ctx.layers, wtraj, z1, gw_traj, gkl.contiguous().float(), None,
-                                     ctx.w0_per_sample)
+        with _Timed("k3_bwd"):
+            gx0, gw_traj = xpath_backward(cfg, xs, wtraj, gx.to(torch.float32))
+        with _Timed("k1_bwd"):
+            gw0, glayers = wsde_backward(cfg, ctx.layers, wtraj, z1, gw_traj, gkl.contiguous().float(), None,
+                                         ctx.w0_per_sample)
         flat = [t for lay in glayers for t in lay]
         return (None, None, None, None, None, gx0, gw0, *flat)
 

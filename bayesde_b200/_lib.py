@@ -55,7 +55,7 @@ class BsdeError(RuntimeError):
 
 _lib = None
 
-_EXPORTS = ["bsde_version", "bsde_last_error", "bsde_wsde_workspace_bytes", "bsde_wsde_fwd", "bsde_wsde_bwd",
+_EXPORTS = ["bsde_version", "bsde_last_error", "bsde_launch_count", "bsde_wsde_workspace_bytes", "bsde_wsde_fwd", "bsde_wsde_bwd",
             "bsde_tconv_fwd", "bsde_tconv_wgrad_workspace_bytes", "bsde_tconv_wgrad",
             "bsde_xpath_workspace_bytes", "bsde_xpath_fwd", "bsde_xpath_bwd", "bsde_step_update",
             "bsde_philox_increments"]
@@ -73,6 +73,7 @@ def lib():
             raise BsdeError(f"libbsde.so does not export {name}")
     L.bsde_version.restype = C.c_int
     L.bsde_last_error.restype = C.c_char_p
+    L.bsde_launch_count.restype = C.c_uint64
     L.bsde_wsde_workspace_bytes.restype = C.c_size_t
     L.bsde_wsde_workspace_bytes.argtypes = [C.POINTER(WsdeDesc), C.POINTER(FwParams)]
     vp = C.c_void_p

@@ -1,6 +1,8 @@
 // C-ABI surface of libbsde.so: error plumbing, K2 entry points, the x-path scan drivers (K2+K3),
 // the generic flat-state step and the Philox increment materialiser.
 #include <stdarg.h>
+
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -8,6 +10,8 @@
 namespace bsde {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -68,6 +72,7 @@ using namespace bsde;
 
 extern "C" int bsde_version(void) { return BSDE_VERSION; }
 extern "C" const char* bsde_last_error(void) { return g_err; }
+extern "C" uint64_t bsde_launch_count(void) { return g_launches.load(); }
 
 extern "C" int bsde_tconv_fwd(const bsde_conv_layer* L, int32_t S, int32_t B, const float* d_in,
                               const float* d_w, int64_t w_sample_stride, float t, int32_t act,
@@ -265,6 +270,7 @@ extern "C" int bsde_step_update(int32_t method, int64_t n, float dt, const float
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   step_update_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(method, n, dt, d_y, d_f, d_g, d_dW, d_gdg, d_g2, d_y1);
+  count_launch();
   BSDE_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -277,6 +283,7 @@ extern "C" int bsde_philox_increments(uint64_t seed, uint32_t stream_id, int32_t
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   philox_increments_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(seed, stream_id, S, nit, P, d_dtk, d_out);
+  count_launch();
   BSDE_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -9,6 +9,7 @@
 namespace bsde {
 
 void set_error(const char* fmt, ...);
+void count_launch(int n = 1);  // bookkeeping for bsde_launch_count()
 
 #define BSDE_CHECK_ARG(cond, ...)        \
   do {                                   \

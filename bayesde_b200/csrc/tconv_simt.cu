@@ -41,6 +41,18 @@ __device__ __forceinline__ bool map_axis(int o, int k, int sn, int kn, int off, 
 
 constexpr int BK = 16;
 
+// valid taps along one axis for output parity `par` (sd == 2), or all taps (sd == 1)
+__device__ __forceinline__ int valid_taps(int ksize, int sn, int kn, int off, int sd, int par, int* kv) {
+  int n = 0;
+  for (int k = 0; k < ksize; ++k)
+    if (sd == 1 || (((par * sn + k * kn + off) & 1) == 0)) kv[n++] = k;
+  return n;
+}
+
+// When sd == 2 (lhs-dilated "transposed" conv, or the data gradient of a stride-2 conv) only the taps
+// whose parity matches the output pixel's parity touch real data.  Output pixels are therefore
+// processed per parity class (blockIdx.y selects the class): each class is a dense conv over its
+// 1, 2 or 4 valid taps, so no multiply-by-structural-zero work is issued.
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256) conv_gather_kernel(ConvArgs a) {
   static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
@@ -51,7 +63,18 @@ __global__ void __launch_bounds__(256) conv_gather_kernel(ConvArgs a) {
   const int tid = threadIdx.x;
   const int s = blockIdx.z;
   const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
+  const int ncls = a.sd == 2 ? 4 : 1;
+  const int cls = blockIdx.y % ncls;
+  const int n0 = (blockIdx.y / ncls) * BN;
+  const int py = cls >> 1, px = cls & 1;
+  const int step = a.sd == 2 ? 2 : 1;
+  const int hq = (a.hout - py + step - 1) / step, wq = (a.wout - px + step - 1) / step;
+  const int Mcls = a.B * hq * wq;
+  if (m0 >= Mcls) return;
+  int khv[3], kwv[3];
+  const int nkh = valid_taps(a.ksize, a.sn, a.kn, a.off, a.sd, py, khv);
+  const int nkw = valid_taps(a.ksize, a.sn, a.kn, a.off, a.sd, px, kwv);
+  const int Ktot = nkh * nkw * a.Kc;
   const float* __restrict__ in = a.in + (long long)s * a.B * a.hin * a.win * a.cin;
   const float* __restrict__ w = a.w + (long long)s * a.w_sample_stride;
 
@@ -62,13 +85,14 @@ __global__ void __launch_bounds__(256) conv_gather_kernel(ConvArgs a) {
 #pragma unroll
   for (int i = 0; i < PPT; ++i) {
     int m = m0 + ml0 + i * 16;
-    if (m < a.Mper) {
-      int hw = a.hout * a.wout;
+    if (m < Mcls) {
+      int hw = hq * wq;
       int img = m / hw;
       int r = m - img * hw;
+      int qy = r / wq;
       p_img[i] = img;
-      p_oy[i] = r / a.wout;
-      p_ox[i] = r - p_oy[i] * a.wout;
+      p_oy[i] = qy * step + py;
+      p_ox[i] = (r - qy * wq) * step + px;
     } else {
       p_img[i] = -1; p_oy[i] = 0; p_ox[i] = 0;
     }
@@ -82,14 +106,14 @@ __global__ void __launch_bounds__(256) conv_gather_kernel(ConvArgs a) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < a.Ktot; k0 += BK) {
+  for (int k0 = 0; k0 < Ktot; k0 += BK) {
     // ---- gather A tile
     {
       const int k = k0 + kl;
-      const bool kvalid = k < a.Ktot;
-      int tap = 0, c = 0;
-      if (kvalid) { tap = k / a.Kc; c = k - tap * a.Kc; }
-      const int kh = tap / a.ksize, kw = tap - kh * a.ksize;
+      const bool kvalid = k < Ktot;
+      int tl = 0, c = 0;
+      if (kvalid) { tl = k / a.Kc; c = k - tl * a.Kc; }
+      const int kh = khv[tl / nkw], kw = kwv[tl % nkw];
       const bool is_time = a.has_time && (c == a.Kc - 1);
 #pragma unroll
       for (int i = 0; i < PPT; ++i) {
@@ -110,8 +134,9 @@ __global__ void __launch_bounds__(256) conv_gather_kernel(ConvArgs a) {
       const int kk = idx / BN, nn = idx - kk * BN;
       const int k = k0 + kk, n = n0 + nn;
       float v = 0.f;
-      if (k < a.Ktot && n < a.cout) {
-        const int tap = k / a.Kc, c = k - tap * a.Kc;
+      if (k < Ktot && n < a.cout) {
+        const int tl = k / a.Kc, c = k - tl * a.Kc;
+        const int tap = khv[tl / nkw] * a.ksize + kwv[tl % nkw];
         const int row = (a.has_time && c == a.Kc - 1) ? a.time_row : c + a.real_base;
         v = __ldg(w + a.w_off + tap * a.ts + row * a.ks + n * a.ns);
       }
@@ -150,12 +175,20 @@ __global__ void __launch_bounds__(256) conv_gather_kernel(ConvArgs a) {
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty * TM + i;
-    if (m >= a.Mper) continue;
+    if (m >= Mcls) continue;
+    long long pix = m;
+    if (a.sd == 2) {
+      const int hw = hq * wq;
+      const int img = m / hw;
+      const int r = m - img * hw;
+      const int qy = r / wq;
+      pix = ((long long)img * a.hout + (qy * 2 + py)) * a.wout + ((r - qy * wq) * 2 + px);
+    }
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tx * TN + j;
       if (n >= a.cout) continue;
-      const long long o = (long long)m * a.cout + n;
+      const long long o = pix * a.cout + n;
       float v = acc[i][j];
       const float b = (a.b_off >= 0 && a.epi <= BSDE_EPI_EULER) ? __ldg(w + a.b_off + n) : 0.f;
       switch (a.epi) {
@@ -171,19 +204,28 @@ __global__ void __launch_bounds__(256) conv_gather_kernel(ConvArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// weight gradient:  G[i][j] = sum_m A(m, i) * dy[m][j],  i over (tap, channel) rows plus one
-// trailing "ones" row that yields the bias gradient.  Pixels are split across CTAs; partial
-// tiles go to the workspace and a second kernel reduces them in a fixed order (deterministic).
+// weight gradient:  G[i][j] = sum_m A(m, i) * Bm[m][j]
+//   direct form  (forward layers with sd == 1): m runs over OUTPUT pixels, A = gathered input
+//       (rows i = (tap, channel incl. time) plus one trailing "ones" row = bias gradient), Bm = dy.
+//   swapped form (forward layers with sd == 2, i.e. lhs-dilated convs): m runs over INPUT pixels,
+//       A = dy gathered through the data-gradient map (rows i = (tap, cout)), Bm = [x, t]
+//       (columns j = input channel incl. time); G is stored transposed.  This keeps the pixel loop
+//       dense: the direct form would multiply 3/4 structural zeros.  The bias gradient is a
+//       separate column sum.
+// Pixels are split across CTAs; partial tiles go to the workspace and a second kernel reduces
+// them in a fixed order (deterministic, no float atomics).
 // ---------------------------------------------------------------------------------------------
 struct WgradArgs {
-  const float* in;
-  const float* dy;
-  float* partial;  // [S][splits][rows][cout]
+  const float* in;   // gathered operand
+  const float* bm;   // plain operand [pixels][bcols]
+  float* partial;    // [S][splits][rows][cols]
   int S, B, splits, chunk;
-  int cin, cout, ksize, hin, win, hout, wout, sn, kn, off, sd;
-  int has_time;
+  int cin, ksize, hin, win, hout, wout, sn, kn, off, sd;  // gather geometry; (hout,wout) = pixel loop space
+  int has_time;      // gathered side carries the time channel (direct form)
+  int bias_row;      // trailing ones row (direct form)
+  int bcols, b_time; // plain operand: real columns, +1 constant-t column (swapped form)
   float t;
-  int Kc, Ktot, rows, Mper;
+  int Kc, Ktot, rows, cols, Mper;
 };
 
 template <int BI, int BJ, int TM, int TN>
@@ -197,7 +239,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
   const int i0 = blockIdx.x * BI;
   const int j0 = blockIdx.y * BJ;
   const float* __restrict__ in = a.in + (long long)s * a.B * a.hin * a.win * a.cin;
-  const float* __restrict__ dy = a.dy + (long long)s * a.Mper * a.cout;
+  const float* __restrict__ bm = a.bm + (long long)s * a.Mper * a.bcols;
   const int mbeg = split * a.chunk;
   const int mend = min(a.Mper, mbeg + a.chunk);
   const int hw = a.hout * a.wout;
@@ -215,7 +257,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
     r_kh = tap / a.ksize;
     r_kw = tap - r_kh * a.ksize;
     r_kind = (a.has_time && r_c == a.Kc - 1) ? 2 : 1;
-  } else if (i_row == a.Ktot) {
+  } else if (i_row == a.Ktot && a.bias_row) {
     r_kind = 3;
   }
 
@@ -253,7 +295,12 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
     for (int idx = tid; idx < BK * BJ; idx += 256) {
       const int mm = idx / BJ, jj = idx - mm * BJ;
       const int m = mb + mm, j = j0 + jj;
-      Bs[mm][jj] = (m < mend && j < a.cout) ? __ldg(dy + (long long)m * a.cout + j) : 0.f;
+      float v = 0.f;
+      if (m < mend) {
+        if (j < a.bcols) v = __ldg(bm + (long long)m * a.bcols + j);
+        else if (j == a.bcols && a.b_time) v = a.t;
+      }
+      Bs[mm][jj] = v;
     }
     __syncthreads();
 #pragma unroll
@@ -281,7 +328,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
     }
     __syncthreads();
   }
-  float* __restrict__ part = a.partial + ((long long)(s * a.splits + split) * a.rows) * a.cout;
+  float* __restrict__ part = a.partial + ((long long)(s * a.splits + split) * a.rows) * a.cols;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int row = i0 + ty * TM + i;
@@ -289,39 +336,78 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int col = j0 + tx * TN + j;
-      if (col < a.cout) part[(long long)row * a.cout + col] = acc[i][j];
+      if (col < a.cols) part[(long long)row * a.cols + col] = acc[i][j];
     }
+  }
+}
+
+// column sums of dy per (sample, pixel chunk): partial[s][split][c]   (bias gradient, swapped form)
+__global__ void colsum_partial_kernel(const float* __restrict__ dy, float* __restrict__ partial, int Mper, int cout,
+                                      int splits, int chunk) {
+  const int s = blockIdx.y, split = blockIdx.x;
+  const int mbeg = split * chunk, mend = min(Mper, mbeg + chunk);
+  const float* __restrict__ d = dy + (long long)s * Mper * cout;
+  __shared__ float red[256];
+  // threads: column c = tid % cpad, pixel lane = tid / cpad
+  for (int c0 = 0; c0 < cout; c0 += 64) {
+    const int cw = min(64, cout - c0);
+    const int c = threadIdx.x % 64, lane = threadIdx.x / 64;  // 4 pixel lanes
+    float v = 0.f;
+    if (c < cw)
+      for (int m = mbeg + lane; m < mend; m += 4) v += __ldg(d + (long long)m * cout + c0 + c);
+    red[threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.x < 64 && c < cw)
+      partial[((long long)s * splits + split) * cout + c0 + c] = red[c] + red[64 + c] + red[128 + c] + red[192 + c];
+    __syncthreads();
   }
 }
 
 struct WreduceArgs {
   const float* partial;
+  const float* bias_partial;  // swapped form: [S][splits][cout] column sums, else NULL
   float* gw;
   long long gw_sample_stride;
-  int S, splits, rows, cout, Kc, Ktot, has_time, time_row, real_base;
+  int S, splits, rows, cols, Kc, Ktot, has_time, time_row, real_base, swapped, cin, cout;
   long long w_off, b_off, ts, ks, ns;
   float scale;
 };
 
 __global__ void wgrad_reduce_kernel(WreduceArgs a) {
-  const long long per = (long long)a.rows * a.cout;
+  const long long per = (long long)a.rows * a.cols;
   const long long total = per * a.S;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int s = (int)(idx / per);
     const long long e = idx - s * per;
-    const int row = (int)(e / a.cout), col = (int)(e - (long long)row * a.cout);
+    const int row = (int)(e / a.cols), col = (int)(e - (long long)row * a.cols);
     const float* p = a.partial + (long long)s * a.splits * per + e;
     float v = 0.f;
     for (int q = 0; q < a.splits; ++q) v += p[q * per];
     v *= a.scale;
     float* g = a.gw + s * a.gw_sample_stride;
-    if (row == a.Ktot) {
-      if (a.b_off >= 0) g[a.b_off + col] = v;
-    } else {
-      const int tap = row / a.Kc, c = row - tap * a.Kc;
-      const int wr = (a.has_time && c == a.Kc - 1) ? a.time_row : c + a.real_base;
-      g[a.w_off + tap * a.ts + wr * a.ks + col * a.ns] = v;
+    if (!a.swapped) {
+      if (row == a.Ktot) {
+        if (a.b_off >= 0) g[a.b_off + col] = v;
+      } else {
+        const int tap = row / a.Kc, c = row - tap * a.Kc;
+        const int wr = (a.has_time && c == a.Kc - 1) ? a.time_row : c + a.real_base;
+        g[a.w_off + tap * a.ts + wr * a.ks + col * a.ns] = v;
+      }
+    } else {  // row = (tap, cout), col = input channel (last = time)
+      const int tap = row / a.cout, co = row - tap * a.cout;
+      const int wr = (a.has_time && col == a.cin) ? a.time_row : col + a.real_base;
+      g[a.w_off + tap * a.ts + wr * a.ks + co * a.ns] = v;
+    }
+  }
+  if (a.swapped && a.bias_partial && a.b_off >= 0) {
+    const long long tb = (long long)a.S * a.cout;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tb;
+         idx += (long long)gridDim.x * blockDim.x) {
+      const int s = (int)(idx / a.cout), c = (int)(idx - (long long)s * a.cout);
+      float v = 0.f;
+      for (int q = 0; q < a.splits; ++q) v += a.bias_partial[((long long)s * a.splits + q) * a.cout + c];
+      a.gw[s * a.gw_sample_stride + a.b_off + c] = v * a.scale;
     }
   }
 }
@@ -353,81 +439,134 @@ int tconv_fwd_simt(const bsde_conv_layer* L, int S, int B, const float* in, cons
   a.Kc = L->cin + (L->has_time ? 1 : 0);
   a.Ktot = L->ksize * L->ksize * a.Kc;
   a.Mper = B * L->hout * L->wout;
+  BSDE_CHECK_ARG(L->sd == 1 || (L->sn & 1), "sd=2 needs an odd sn");
+  const int ncls = L->sd == 2 ? 4 : 1;
+  const int Mcls = L->sd == 2 ? B * ((L->hout + 1) / 2) * ((L->wout + 1) / 2) : a.Mper;  // largest class
   if (L->cout > 16) {
-    dim3 g((a.Mper + 127) / 128, (L->cout + 63) / 64, S);
+    dim3 g((Mcls + 127) / 128, ((L->cout + 63) / 64) * ncls, S);
     conv_gather_kernel<128, 64, 8, 4><<<g, 256, 0, st>>>(a);
   } else if (L->cout > 8) {
-    dim3 g((a.Mper + 255) / 256, 1, S);
+    dim3 g((Mcls + 255) / 256, ncls, S);
     conv_gather_kernel<256, 16, 4, 4><<<g, 256, 0, st>>>(a);
   } else {
-    dim3 g((a.Mper + 255) / 256, 1, S);
+    dim3 g((Mcls + 255) / 256, ncls, S);
     conv_gather_kernel<256, 8, 4, 2><<<g, 256, 0, st>>>(a);
   }
+  count_launch();
   BSDE_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-static void wgrad_plan(const bsde_conv_layer* L, int S, int B, int& rows, int& splits, int& chunk,
-                       int& ti, int& tj, int& bi, int& bj) {
-  const int Kc = L->cin + (L->has_time ? 1 : 0);
-  rows = L->ksize * L->ksize * Kc + 1;
-  if (L->cout > 16) { bi = 128; bj = 64; }
-  else if (L->cout > 8) { bi = 256; bj = 16; }
-  else { bi = 256; bj = 8; }
-  ti = (rows + bi - 1) / bi;
-  tj = (L->cout + bj - 1) / bj;
-  const int Mper = B * L->hout * L->wout;
-  int want = (148 * 4 + ti * tj * S - 1) / (ti * tj * S);
-  int maxs = (Mper + 511) / 512;
-  splits = want < 1 ? 1 : (want > maxs ? maxs : want);
-  if (splits < 1) splits = 1;
-  chunk = (Mper + splits - 1) / splits;
-  chunk = (chunk + BK - 1) / BK * BK;
-  splits = (Mper + chunk - 1) / chunk;
+struct WgradPlan {
+  int swapped, rows, cols, splits, chunk, ti, tj, bi, bj, Mper;
+  size_t main_floats, bias_floats;
+};
+
+static WgradPlan wgrad_plan(const bsde_conv_layer* L, int S, int B) {
+  WgradPlan p;
+  const int taps = L->ksize * L->ksize;
+  p.swapped = L->sd == 2;
+  if (!p.swapped) {
+    p.rows = taps * (L->cin + (L->has_time ? 1 : 0)) + 1;
+    p.cols = L->cout;
+    p.Mper = B * L->hout * L->wout;
+  } else {
+    p.rows = taps * L->cout;
+    p.cols = L->cin + (L->has_time ? 1 : 0);
+    p.Mper = B * L->hin * L->win;
+  }
+  if (p.cols > 16) { p.bi = 128; p.bj = 64; }
+  else if (p.cols > 8) { p.bi = 256; p.bj = 16; }
+  else { p.bi = 256; p.bj = 8; }
+  p.ti = (p.rows + p.bi - 1) / p.bi;
+  p.tj = (p.cols + p.bj - 1) / p.bj;
+  int want = (148 * 4 + p.ti * p.tj * S - 1) / (p.ti * p.tj * S);
+  int maxs = (p.Mper + 511) / 512;
+  p.splits = want < 1 ? 1 : (want > maxs ? maxs : want);
+  if (p.splits < 1) p.splits = 1;
+  p.chunk = (p.Mper + p.splits - 1) / p.splits;
+  p.chunk = (p.chunk + BK - 1) / BK * BK;
+  p.splits = (p.Mper + p.chunk - 1) / p.chunk;
+  p.main_floats = (size_t)S * p.splits * p.rows * p.cols;
+  p.bias_floats = p.swapped ? (size_t)S * 64 * L->cout : 0;
+  return p;
 }
 
 size_t tconv_wgrad_ws_simt(const bsde_conv_layer* L, int S, int B) {
-  int rows, splits, chunk, ti, tj, bi, bj;
-  wgrad_plan(L, S, B, rows, splits, chunk, ti, tj, bi, bj);
-  return (size_t)S * splits * rows * L->cout * sizeof(float);
+  WgradPlan p = wgrad_plan(L, S, B);
+  return (p.main_floats + p.bias_floats) * sizeof(float);
 }
 
 int tconv_wgrad_simt(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t,
                      float scale, float* gw, long long gw_sample_stride, void* ws, size_t ws_bytes,
                      cudaStream_t st) {
   if (int e = check_layer(L)) return e;
-  int rows, splits, chunk, ti, tj, bi, bj;
-  wgrad_plan(L, S, B, rows, splits, chunk, ti, tj, bi, bj);
-  const size_t need = (size_t)S * splits * rows * L->cout * sizeof(float);
+  WgradPlan p = wgrad_plan(L, S, B);
+  const size_t need = (p.main_floats + p.bias_floats) * sizeof(float);
   if (ws == nullptr || ws_bytes < need) {
     set_error("tconv_wgrad: workspace %zu < %zu bytes", ws_bytes, need);
     return BSDE_ERR_WORKSPACE;
   }
   WgradArgs a;
-  a.in = in; a.dy = dy; a.partial = (float*)ws; a.S = S; a.B = B; a.splits = splits; a.chunk = chunk;
-  a.cin = L->cin; a.cout = L->cout; a.ksize = L->ksize; a.hin = L->hin; a.win = L->win;
-  a.hout = L->hout; a.wout = L->wout; a.sn = L->sn; a.kn = L->kn; a.off = L->off; a.sd = L->sd;
-  a.has_time = L->has_time; a.t = t;
-  a.Kc = L->cin + (L->has_time ? 1 : 0);
+  a.partial = (float*)ws; a.S = S; a.B = B; a.splits = p.splits; a.chunk = p.chunk;
+  a.ksize = L->ksize; a.t = t; a.rows = p.rows; a.cols = p.cols; a.Mper = p.Mper;
+  if (!p.swapped) {
+    a.in = in; a.bm = dy;
+    a.cin = L->cin; a.hin = L->hin; a.win = L->win; a.hout = L->hout; a.wout = L->wout;
+    a.sn = L->sn; a.kn = L->kn; a.off = L->off; a.sd = L->sd;
+    a.has_time = L->has_time; a.bias_row = 1; a.bcols = L->cout; a.b_time = 0;
+    a.Kc = L->cin + (L->has_time ? 1 : 0);
+  } else {
+    // gather dy through the data-gradient map, looping over the forward layer's input pixels
+    a.in = dy; a.bm = in;
+    a.cin = L->cout; a.hin = L->hout; a.win = L->wout; a.hout = L->hin; a.wout = L->win;
+    a.sn = L->sd; a.kn = -L->kn; a.off = -L->off; a.sd = L->sn;
+    BSDE_CHECK_ARG(a.sd == 1, "wgrad: forward layer with sd=2 needs sn=1");
+    a.has_time = 0; a.bias_row = 0; a.bcols = L->cin; a.b_time = L->has_time;
+    a.Kc = L->cout;
+  }
   a.Ktot = L->ksize * L->ksize * a.Kc;
-  a.rows = rows;
-  a.Mper = B * L->hout * L->wout;
-  dim3 g(ti, tj, S * splits);
-  if (bi == 128) conv_wgrad_kernel<128, 64, 8, 4><<<g, 256, 0, st>>>(a);
-  else if (bj == 16) conv_wgrad_kernel<256, 16, 4, 4><<<g, 256, 0, st>>>(a);
+  dim3 g(p.ti, p.tj, S * p.splits);
+  if (p.bi == 128) conv_wgrad_kernel<128, 64, 8, 4><<<g, 256, 0, st>>>(a);
+  else if (p.bj == 16) conv_wgrad_kernel<256, 16, 4, 4><<<g, 256, 0, st>>>(a);
   else conv_wgrad_kernel<256, 8, 4, 2><<<g, 256, 0, st>>>(a);
   BSDE_CUDA_OK(cudaGetLastError());
+  count_launch();
+  float* bias_partial = nullptr;
+  int bsplits = 0;
+  if (p.swapped && L->b_off >= 0) {
+    bias_partial = (float*)ws + p.main_floats;
+    const int Mout = B * L->hout * L->wout;
+    bsplits = 64;
+    int bchunk = (Mout + bsplits - 1) / bsplits;
+    if (bchunk < 1) bchunk = 1;
+    bsplits = (Mout + bchunk - 1) / bchunk;
+    colsum_partial_kernel<<<dim3(bsplits, S), 256, 0, st>>>(dy, bias_partial, Mout, L->cout, bsplits, bchunk);
+    BSDE_CUDA_OK(cudaGetLastError());
+    count_launch();
+  }
   WreduceArgs r;
-  r.partial = (const float*)ws; r.gw = gw; r.gw_sample_stride = gw_sample_stride; r.S = S; r.splits = splits;
-  r.rows = rows; r.cout = L->cout; r.Kc = a.Kc; r.Ktot = a.Ktot; r.has_time = L->has_time;
-  r.time_row = L->time_first ? 0 : L->cin; r.real_base = (L->has_time && L->time_first) ? 1 : 0;
+  r.partial = (const float*)ws; r.bias_partial = bias_partial; r.gw = gw; r.gw_sample_stride = gw_sample_stride;
+  r.S = S; r.splits = p.splits; r.rows = p.rows; r.cols = p.cols; r.Kc = a.Kc; r.Ktot = a.Ktot;
+  r.has_time = L->has_time; r.time_row = L->time_first ? 0 : L->cin;
+  r.real_base = (L->has_time && L->time_first) ? 1 : 0; r.swapped = p.swapped; r.cin = L->cin; r.cout = L->cout;
   r.w_off = L->w_off; r.b_off = L->b_off; r.ts = L->w_tap_stride; r.ks = L->w_k_stride; r.ns = L->w_n_stride;
   r.scale = scale;
-  const long long total = (long long)S * rows * L->cout;
+  const long long total = (long long)S * p.rows * p.cols;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
+  if (bias_partial) {
+    // bias partials use their own split count: reduce them with a dedicated tiny launch
+    WreduceArgs rb = r;
+    rb.partial = nullptr; rb.rows = 0; rb.cols = 1; rb.splits = bsplits;
+    wgrad_reduce_kernel<<<(S * L->cout + 255) / 256, 256, 0, st>>>(rb);
+    BSDE_CUDA_OK(cudaGetLastError());
+    count_launch();
+    r.bias_partial = nullptr;
+  }
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(r);
   BSDE_CUDA_OK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

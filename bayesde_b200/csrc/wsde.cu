@@ -491,7 +491,6 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
 // =============================================================================================
 static std::mutex g_mu;
 static int g_num_sms = 0;
-static int g_fwd_occ = 0, g_bwd_occ = 0;
 
 static int fill_tiny(const bsde_fw_params* fw, TinyDims& td) {
   BSDE_CHECK_ARG(fw->nhid >= 1 && fw->nhid <= BSDE_FW_MAX_MID + 1, "len(fw_dims)=%d unsupported", fw->nhid);
@@ -598,6 +597,7 @@ extern "C" int bsde_wsde_fwd(const bsde_wsde_desc* d, const bsde_fw_params* fw, 
     void* args[] = {&A};
     BSDE_CUDA_OK(cudaLaunchCooperativeKernel((void*)wsde_fwd_kernel, dim3(G), dim3(NTHREADS), args, smem,
                                              (cudaStream_t)stream));
+    count_launch();
   }
   return 0;
 }
@@ -641,6 +641,7 @@ extern "C" int bsde_wsde_bwd(const bsde_wsde_desc* d, const bsde_fw_params* fw, 
     void* args[] = {&A};
     BSDE_CUDA_OK(cudaLaunchCooperativeKernel((void*)wsde_bwd_kernel, dim3(G), dim3(NTHREADS), args, smem,
                                              (cudaStream_t)stream));
+    count_launch();
   }
   return 0;
 }

@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- SDE-BNN training throughput on the fused B200 path (BASELINE.json metric).
+
+A "step" = one optimiser step of examples/jax/sdebnn_classification.py's `update` on one batch of
+synthetic 32x32x3 images: forward through Augment -> 6 SDEBNN blocks (nblocks 2-2-2, fx_dim 64,
+fw_dims 2-64-2, nsteps 20 => 19 drift evaluations per block) -> mean-field Dense head, reverse pass
+through the solver (recompute from per-iteration x checkpoints), gradient mean over the S Monte-Carlo
+samples (+ NCCL all-reduce over ranks), Adam.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
+    python bench.py --impl reference ...                       CPU oracle port on the host cores
+
+`value` counts distinct training images per second; each image is integrated under `nsamples`
+weight paths (examples/jax/sdebnn_classification.py:218 vmaps grad(loss) over the sample rngs).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SDE-BNN train images/s (32x32, nsteps=20)"
+UNIT = "images/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--batch", type=int, default=128, help="images per GPU per step")
+    p.add_argument("--nsamples", type=int, default=8)
+    p.add_argument("--math", default=os.environ.get("BSDE_MATH", "fp32"), choices=["fp32", "tc"])
+    p.add_argument("--time_grid", default="reference", choices=["reference", "uniform"])
+    p.add_argument("--diff_coef", type=float, default=0.2)
+    p.add_argument("--cpu_batch", type=int, default=8, help="images in the bounded CPU sample")
+    p.add_argument("--no_cpu_baseline", action="store_true")
+    return p.parse_args()
+
+
+MODEL_KW = dict(input_size=(32, 32, 3), aug=2, nblocks=(2, 2, 2), fx_dim=64, fw_dims=(2, 64, 2), nsteps=20,
+                fx_actfn="softplus", fw_actfn="softplus")
+
+
+def conv_flops_per_image_eval():
+    """2*MAC of the conv stacks of the 6 blocks for one image and one drift evaluation (dense taps,
+    time channel included: SURVEY.md 8.4 -> 175.1 MFLOP)."""
+    from bayesde_b200.arch import FxSpec
+    total = 0
+    shape = (1, 32, 32, 5)
+    for gi, nb in enumerate(MODEL_KW["nblocks"]):
+        fx = FxSpec(0, shape, MODEL_KW["fx_dim"], "softplus")
+        per = 0
+        for L in fx.layers:
+            pix = L["hout"] * L["wout"] if L["sd"] == 1 else L["hin"] * L["win"]  # transposed: per input pixel
+            per += 2 * pix * L["k"] * L["k"] * (L["cin"] + 1) * L["cout"]
+        total += nb * per
+        shape = (1, shape[1] // 2, shape[2] // 2, shape[3] * 4)
+    return total
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_images_per_s(args, steps, warmup):
+    """The oracle's torch-CPU fp32 restatement of the JAX path (the reference itself needs JAX 0.1.77,
+    which cannot be installed here), all host threads, bounded sample: `cpu_batch` images x 1 MC
+    sample per step, scaled to the metric's unit (images/s at nsamples samples per image)."""
+    import torch
+    from oracle import jax_path as jp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.cpu_batch
+    net = jp.SDEBNNClassifier(batch=B, diff_coef=args.diff_coef, time_grid_mode=args.time_grid,
+                              **{k: v for k, v in MODEL_KW.items()})
+    params, head = net.init(0, torch.float32)
+    leaves = []
+    for (w0, fw) in params:
+        w0.requires_grad_(True)
+        leaves.append(w0)
+        for lay in fw:
+            for t in lay:
+                t.requires_grad_(True)
+                leaves.append(t)
+    for pair in head:
+        for t in pair:
+            t.requires_grad_(True)
+            leaves.append(t)
+    opt = torch.optim.Adam(leaves, lr=1e-3)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, 32, 32, 3, generator=g)
+    onehot = torch.nn.functional.one_hot(torch.randint(0, 10, (B,), generator=g), 10).float()
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        dWs = [jp.sample_increments(b.P, 20, g, torch.float32, args.time_grid) for b in net.blocks()]
+        eps = torch.randn(net.feat * 10 + 10, generator=g)
+        opt.zero_grad()
+        loss, _, _, _ = net.loss(params, head, x, onehot, dWs, eps, 1e-3 / 45000)
+        loss.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    t_step = sum(times) / len(times)
+    value = B / (t_step * args.nsamples)
+    sample = (f"{steps} timed + {warmup} warm-up train steps (fwd+bwd+Adam) of the oracle port at "
+              f"{B} images x 1 MC sample, {t_step:.2f} s/step; value = {B}/(s_per_step*{args.nsamples} samples)")
+    return value, cores, sample, t_step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warmup = 1 if args.warmup > 0 else 0
+    v, cores, sample, t_step = cpu_reference_images_per_s(args, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "config4: SDEBNN 32x32x3 CIFAR-10-shape synthetic, aug 2, nblocks 2-2-2, fx_dim 64, "
+                        "fw_dims 2-64-2, softplus, nsteps 20 (19 drift evaluations/block), euler_maruyama",
+            "batch_per_gpu": args.batch, "nsamples": args.nsamples, "diff_coef": args.diff_coef,
+            "time_grid": args.time_grid, "conv_math": args.math, "parallelism": f"dp{args.gpus} (batch sharded)",
+            "l2_policy": "per-step working set (checkpoints+activations, >2 GB) exceeds the 126 MB L2; no flush"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bayesde_b200 import _fused, _lib
+    from bayesde_b200.classification import SDEBNNClassifier, Trainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    model = SDEBNNClassifier(nsamples=args.nsamples, diff_coef=args.diff_coef, time_grid=args.time_grid,
+                             math=args.math, w_init=1e-2, b_init=1e-2, seed=0, device=dev, **MODEL_KW)
+    trainer = Trainer(model, lr=1e-3, kl_coef=1e-3, train_size=45000)
+    B = args.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_host = 4
+    host_x = [torch.randn(B, 32, 32, 3, generator=g).pin_memory() for _ in range(n_host)]
+    host_y = [torch.randint(0, 10, (B,), generator=g).pin_memory() for _ in range(n_host)]
+    dev_x = [t.to(dev) for t in host_x]
+    dev_y = [t.to(dev) for t in host_y]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    seed_base = [0]
+
+    def step_resident(i):
+        trainer.step(dev_x[i % n_host], dev_y[i % n_host], seed=seed_base[0] + i)
+
+    last = {}
+
+    def step_e2e(i):
+        x = host_x[i % n_host].to(dev, non_blocking=True)
+        y = host_y[i % n_host].to(dev, non_blocking=True)
+        loss, _, _ = trainer.step(x, y, seed=seed_base[0] + i)
+        last["loss"] = loss.item()  # device -> host read of the step's result
+
+    for i in range(args.warmup):
+        step_resident(i)
+    seed_base[0] = 1000
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _fused.PROFILE = {}
+    n0 = L.bsde_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = L.bsde_launch_count() - n0
+    prof = _fused.PROFILE
+    _fused.PROFILE = None
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    ktime = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in prof.items()}
+
+    seed_base[0] = 2000
+    ms_e2e = timed(step_e2e, args.steps)
+
+    images = B * world * args.steps
+    value = images / (ms * 1e-3)
+    e2e_value = images / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    peak_hbm = peaks.get("hbm_gbs", 6650.0)
+    fl_eval = conv_flops_per_image_eval()
+    nit = MODEL_KW["nsteps"] - 1
+    alg_flops_step = 3.0 * fl_eval * nit * B * args.nsamples  # fwd + dgrad + wgrad (recompute not counted)
+    conv_ms = (ktime.get("k2_fwd", 0.0) + ktime.get("k3_bwd", 0.0)) / args.steps
+    achieved = alg_flops_step / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    # K1 (weight-SDE) against the 48*P HBM model of SURVEY.md 8.4 (fwd) and 2x for the reverse pass
+    sumP = sum(blk[0].numel() for blk in model.block_params())
+    k1_bytes = 3 * 48.0 * sumP * nit * args.nsamples
+    k1_ms = (ktime.get("k1_fwd", 0.0) + ktime.get("k1_bwd", 0.0)) / args.steps
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.math == "fp32" else "bf16x-tc/f32-accum", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (32 * 32 * 3 * 4 + 8),
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "K2/K3 time-dependent conv stack (conv_gather / conv_wgrad)",
+                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                     "peak_source": peak_src, "traffic": None,
+                     "algorithmic_flops_per_step": alg_flops_step, "kernel_ms_per_step": conv_ms,
+                     "share_of_step": conv_ms / (ms / args.steps)},
+        "roofline_k1": {"bound": "hbm", "kernel": "K1 wsde_fwd/bwd (cooperative persistent)",
+                        "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0, "peak": peak_hbm,
+                        "unit": "GB/s", "frac": (k1_bytes / (k1_ms * 1e-3) / 1e9 / peak_hbm) if k1_ms > 0 else 0.0,
+                        "algorithmic_bytes_per_step": k1_bytes, "kernel_ms_per_step": k1_ms,
+                        "note": "48*P B per (sample, block, iteration) fwd, 2x bwd; state is L2-resident so "
+                                "frac may exceed 1"},
+        "kernel_ms_per_step": {k: v / args.steps for k, v in ktime.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, sample, _ = cpu_reference_images_per_s(args, 2, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -58,6 +58,8 @@ typedef enum { BSDE_MATH_FP32 = 0, BSDE_MATH_TC = 1 } bsde_math;
 
 int bsde_version(void);
 const char* bsde_last_error(void);
+/* number of kernels this library has launched in this process (bench bookkeeping) */
+uint64_t bsde_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * K1: weight-SDE path  (one SDEBNN block, S Monte-Carlo samples, all scan iterations)
