@@ -1,0 +1,164 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/bsde.h declares; host logic
+(layouts, time grid, pytrees, mean-field head, error behaviour) against the oracle; world_size-2 gloo
+test of the gradient all-reduce."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import jax_path as jp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "bsde.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(bsde_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 14
+    lib = C.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(lib, name), f"libbsde.so does not export {name}"
+    nm = subprocess.run(["nm", "-D", "--defined-only", built_lib], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (bsde_[a-z0-9_]+)", nm))
+    assert declared <= exported
+    lib.bsde_version.restype = C.c_int
+    assert lib.bsde_version() == 100
+
+
+def test_struct_sizes_match_c(built_lib, tmp_path):
+    """ctypes mirrors of the POD structs have the C compiler's sizes."""
+    from bayesde_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "bsde.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(bsde_fw_params),'
+                   'sizeof(bsde_wsde_desc), sizeof(bsde_conv_layer), sizeof(bsde_xpath_desc));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    assert sizes == [C.sizeof(_lib.FwParams), C.sizeof(_lib.WsdeDesc), C.sizeof(_lib.ConvLayer), C.sizeof(_lib.XpathDesc)]
+
+
+def test_no_cpu_fallback_and_error_mapping(built_lib):
+    from bayesde_b200 import _lib, sdeint_ito_fixed_grid
+    with pytest.raises(_lib.BsdeError):
+        _lib.ptr(torch.zeros(3))
+    with pytest.raises(ValueError, match="Unknown method"):
+        sdeint_ito_fixed_grid(None, None, torch.zeros(3), torch.linspace(0, 1, 3), 0, method="heun")
+    with pytest.raises(_lib.BsdeError):
+        sdeint_ito_fixed_grid(lambda y, t, a: y, lambda y, t, a: y, torch.zeros(3), torch.linspace(0, 1, 3), 0)
+    L = _lib.lib()
+    st = L.bsde_step_update(7, 4, 0.1, None, None, None, None, None, None, None, None)
+    assert st == -1 and b"Unknown method" in L.bsde_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(st, "bsde_step_update")
+
+
+def test_fx_spec_matches_oracle_layout():
+    from bayesde_b200.arch import FxSpec
+    for bt in (0, 1, 2):
+        for C_in, H in ((5, 32), (20, 16), (80, 8)):
+            fx = FxSpec(bt, (1, H, H, C_in), 64, "softplus")
+            lay, P = jp.fx_layout(bt, C_in, 64)
+            assert fx.P == P
+            for a, b in zip(fx.layers, [e for e in lay if e["kind"] == "conv"]):
+                assert (a["w_off"], a["b_off"], a["cin"], a["cout"], a["k"]) == (b["w_off"], b["b_off"], b["cin"], b["cout"], b["k"])
+    with pytest.raises(AssertionError):  # quirk Q10: 7x7 does not survive the stride-2 / transpose pair
+        FxSpec(0, (1, 7, 7, 4), 8, "softplus")
+    with pytest.raises(ValueError):
+        FxSpec(3, (1, 8, 8, 4), 8, "softplus")
+
+
+def test_time_grid_matches_oracle():
+    from bayesde_b200._fused import reference_time_grid
+    for n in (2, 5, 20):
+        ts = torch.linspace(0, 1, n)
+        for mode in ("reference", "uniform"):
+            tk, dtk = reference_time_grid(ts.numpy(), mode)
+            tk_o, dtk_o = jp.time_grid(ts, mode)
+            assert np.array_equal(tk, tk_o.numpy()) and np.array_equal(dtk, dtk_o.numpy())
+    with pytest.raises(ValueError):
+        reference_time_grid(np.linspace(0, 1, 3), "adaptive")
+
+
+def test_parameter_free_layers_and_head_match_oracle():
+    from bayesde_b200 import arch, brax
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 4, 4, 6, generator=g)
+    assert torch.equal(arch.Augment(2).apply((), x), jp.augment(x, 2))
+    assert torch.equal(arch.SqueezeDownsample(2).apply((), x), jp.squeeze_downsample(x))
+    xs = torch.stack([x, 2 * x])
+    assert torch.equal(arch.SqueezeDownsample(2).apply((), xs)[1], jp.squeeze_downsample(2 * x))
+    # mean-field head, two MC samples with explicit noise (brax.py:138-168)
+    head = brax.MeanField(arch.serial(arch.Flatten, arch.Dense(10), arch.LogSoftmax))
+    _, params = head.init(1, (3, 4, 4, 6))
+    (mean, logstd) = params
+    eps = torch.randn(2, 96 * 10 + 10, generator=g)
+    logp, kl = head.apply(params, xs, (0, eps), mc_samples=2)
+    for s in range(2):
+        lp_o, kl_o = jp.meanfield_dense_head((mean[1], logstd[1]), xs[s], eps[s])
+        assert torch.allclose(logp[s], lp_o, atol=1e-5) and torch.allclose(kl[s], kl_o, rtol=1e-5)
+
+
+def test_mlp_apply_quirk_q3_and_param_tree():
+    from bayesde_b200 import arch
+    fw = arch.MLP((2, 8, 2), xt=True, ou_dw=True, nonzero_w=0.05, nonzero_b=0.05)
+    _, params = fw.init(3, (50,))
+    assert params[0] == () and len(params[1]) == 7 and params[1][1] == ()
+    w = torch.randn(50)
+    t = torch.tensor(0.3)
+    out, t2 = fw.apply(params, (w, t))
+    ref = jp.fw_apply(arch.fw_layers(params), w, t)
+    assert torch.allclose(out, ref) and torch.allclose(t2, 2 * t)  # Additive returns (mlp_out, 2t): OU term NOT added
+    with pytest.raises(NotImplementedError):
+        arch.MLP((2, 8, 2), xt=False)
+    with pytest.raises(ValueError):
+        arch.MLP((8, 8, 2), xt=True)
+
+
+def test_classifier_parameter_count_and_split_determinism():
+    from bayesde_b200 import arch
+    from bayesde_b200.classification import SDEBNNClassifier
+    m = SDEBNNClassifier(device="cpu")
+    assert sum(p.numel() for p in m.parameters()) == 6386760  # ~6.39 M
+    assert arch.split(5, 3) == arch.split(5, 3) and len(set(arch.split(5, 3))) == 3
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from bayesde_b200.classification import Trainer
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo")
+lin = torch.nn.Linear(4, 3)
+with torch.no_grad():
+    for p in lin.parameters():
+        p.fill_(0.5)
+tr = Trainer(lin.__class__(4, 3), lr=0.0) if False else None
+class T(Trainer):
+    def __init__(self, model):
+        self.model = model
+t = T(lin)
+for i, p in enumerate(lin.parameters()):
+    p.grad = torch.full_like(p, float(rank + 1 + i))
+t._allreduce()
+for i, p in enumerate(lin.parameters()):
+    assert torch.allclose(p.grad, torch.full_like(p, 1.5 + i)), (rank, p.grad)
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gradient_allreduce_gloo_world2(tmp_path):
+    """The only collective on the path: mean of parameter gradients over ranks."""
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", str(script), ROOT],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
