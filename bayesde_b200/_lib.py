@@ -56,7 +56,7 @@ class BsdeError(RuntimeError):
 _lib = None
 
 _EXPORTS = ["bsde_version", "bsde_last_error", "bsde_launch_count", "bsde_wsde_workspace_bytes", "bsde_wsde_fwd", "bsde_wsde_bwd",
-            "bsde_tconv_fwd", "bsde_tconv_wgrad_workspace_bytes", "bsde_tconv_wgrad",
+            "bsde_tconv_fwd", "bsde_tconv_fwd_workspace_bytes", "bsde_tconv_wgrad_workspace_bytes", "bsde_tconv_wgrad",
             "bsde_xpath_workspace_bytes", "bsde_xpath_fwd", "bsde_xpath_bwd", "bsde_step_update",
             "bsde_philox_increments"]
 
@@ -82,7 +82,9 @@ def lib():
     L.bsde_wsde_bwd.argtypes = [C.POINTER(WsdeDesc), C.POINTER(FwParams), vp, vp, vp, vp, vp, vp, vp, vp,
                                 C.POINTER(FwParams), vp, C.c_size_t, vp]
     L.bsde_tconv_fwd.argtypes = [C.POINTER(ConvLayer), C.c_int32, C.c_int32, vp, vp, C.c_int64, C.c_float,
-                                 C.c_int32, C.c_int32, C.c_float, vp, vp, C.c_int32, vp]
+                                 C.c_int32, C.c_int32, C.c_float, vp, vp, C.c_int32, vp, C.c_size_t, vp]
+    L.bsde_tconv_fwd_workspace_bytes.restype = C.c_size_t
+    L.bsde_tconv_fwd_workspace_bytes.argtypes = [C.POINTER(ConvLayer), C.c_int32, C.c_int32]
     L.bsde_tconv_wgrad_workspace_bytes.restype = C.c_size_t
     L.bsde_tconv_wgrad_workspace_bytes.argtypes = [C.POINTER(ConvLayer), C.c_int32, C.c_int32]
     L.bsde_tconv_wgrad.argtypes = [C.POINTER(ConvLayer), C.c_int32, C.c_int32, vp, vp, C.c_float, C.c_float, vp,

@@ -2,6 +2,7 @@
 // the generic flat-state step and the Philox increment materialiser.
 #include <stdarg.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string.h>
 
@@ -30,15 +31,34 @@ int tconv_wgrad_simt(const bsde_conv_layer* L, int S, int B, const float* in, co
                      cudaStream_t st);
 // tensor-core path (tconv_tc.cu)
 bool tconv_tc_supported(const bsde_conv_layer* L, int epi);
+size_t tconv_tc_ws_bytes(const bsde_conv_layer* L, int S);
 int tconv_fwd_tc(const bsde_conv_layer* L, int S, int B, const float* in, const float* w,
                  long long w_sample_stride, float t, int act, int epi, float scale, const float* aux,
-                 float* out, cudaStream_t st);
+                 float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+
+bool tconv_wgrad_tc_supported(const bsde_conv_layer* L, int S, int B);
+size_t tconv_wgrad_ws_tc(const bsde_conv_layer* L, int S, int B);
+int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
+                   float* gw, long long gw_sample_stride, void* ws, size_t ws_bytes, cudaStream_t st);
+
+static size_t wgrad_ws(const bsde_conv_layer* L, int S, int B, int math) {
+  size_t b = tconv_wgrad_ws_simt(L, S, B);
+  if (math == BSDE_MATH_TC && tconv_wgrad_tc_supported(L, S, B)) b = std::max(b, tconv_wgrad_ws_tc(L, S, B));
+  return b;
+}
+
+static int conv_wgrad(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
+                      float* gw, long long gss, int math, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (math == BSDE_MATH_TC && tconv_wgrad_tc_supported(L, S, B))
+    return tconv_wgrad_tc(L, S, B, in, dy, t, scale, gw, gss, ws, ws_bytes, st);
+  return tconv_wgrad_simt(L, S, B, in, dy, t, scale, gw, gss, ws, ws_bytes, st);
+}
 
 static int conv_fwd(const bsde_conv_layer* L, int S, int B, const float* in, const float* w,
                     long long wss, float t, int act, int epi, float scale, const float* aux, float* out,
-                    int math, cudaStream_t st) {
+                    int math, void* tc_ws, size_t tc_ws_bytes, cudaStream_t st) {
   if (math == BSDE_MATH_TC && tconv_tc_supported(L, epi))
-    return tconv_fwd_tc(L, S, B, in, w, wss, t, act, epi, scale, aux, out, st);
+    return tconv_fwd_tc(L, S, B, in, w, wss, t, act, epi, scale, aux, out, tc_ws, tc_ws_bytes, st);
   return tconv_fwd_simt(L, S, B, in, w, wss, t, act, epi, scale, aux, out, st);
 }
 
@@ -77,15 +97,20 @@ extern "C" uint64_t bsde_launch_count(void) { return g_launches.load(); }
 extern "C" int bsde_tconv_fwd(const bsde_conv_layer* L, int32_t S, int32_t B, const float* d_in,
                               const float* d_w, int64_t w_sample_stride, float t, int32_t act,
                               int32_t epilogue, float scale, const float* d_aux, float* d_out, int32_t math,
-                              void* stream) {
+                              void* workspace, size_t workspace_bytes, void* stream) {
   BSDE_CHECK_ARG(d_in && d_w && d_out, "NULL tensor pointer");
-  return conv_fwd(L, S, B, d_in, d_w, w_sample_stride, t, act, epilogue, scale, d_aux, d_out, math,
-                  (cudaStream_t)stream);
+  return conv_fwd(L, S, B, d_in, d_w, w_sample_stride, t, act, epilogue, scale, d_aux, d_out, math, workspace,
+                  workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t bsde_tconv_fwd_workspace_bytes(const bsde_conv_layer* L, int32_t S, int32_t math) {
+  if (!L || math != BSDE_MATH_TC || !tconv_tc_supported(L, 0)) return 0;
+  return tconv_tc_ws_bytes(L, S);
 }
 
 extern "C" size_t bsde_tconv_wgrad_workspace_bytes(const bsde_conv_layer* L, int32_t S, int32_t B) {
   if (!L) return 0;
-  return tconv_wgrad_ws_simt(L, S, B);
+  return wgrad_ws(L, S, B, BSDE_MATH_TC);
 }
 
 extern "C" int bsde_tconv_wgrad(const bsde_conv_layer* L, int32_t S, int32_t B, const float* d_in,
@@ -93,9 +118,8 @@ extern "C" int bsde_tconv_wgrad(const bsde_conv_layer* L, int32_t S, int32_t B, 
                                 int64_t gw_sample_stride, int32_t math, void* workspace,
                                 size_t workspace_bytes, void* stream) {
   BSDE_CHECK_ARG(d_in && d_dy && d_gw, "NULL tensor pointer");
-  (void)math;
-  return tconv_wgrad_simt(L, S, B, d_in, d_dy, t, scale, d_gw, gw_sample_stride, workspace, workspace_bytes,
-                          (cudaStream_t)stream);
+  return conv_wgrad(L, S, B, d_in, d_dy, t, scale, d_gw, gw_sample_stride, math, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -118,14 +142,27 @@ static int xpath_check(const bsde_xpath_desc* d) {
   return 0;
 }
 
+static size_t xpath_tc_bytes(const bsde_xpath_desc* d, int backward) {
+  if (d->math != BSDE_MATH_TC) return 0;
+  size_t m = 0;
+  for (int l = 0; l < d->nlayers; ++l) {
+    if (tconv_tc_supported(&d->layers[l], 0)) m = std::max(m, tconv_tc_ws_bytes(&d->layers[l], d->S));
+    if (backward) {
+      bsde_conv_layer D = dgrad_layer(d->layers[l]);
+      if (tconv_tc_supported(&D, 0)) m = std::max(m, tconv_tc_ws_bytes(&D, d->S));
+    }
+  }
+  return align_up(m);
+}
+
 extern "C" size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t backward) {
   if (!d || d->nlayers < 2 || d->nlayers > BSDE_MAX_LAYERS) return 0;
-  size_t tot = 0;
+  size_t tot = xpath_tc_bytes(d, backward);
   for (int l = 0; l + 1 < d->nlayers; ++l) tot += align_up(act_elems(d, l) * sizeof(float)) * (backward ? 2 : 1);
   if (backward) {
     size_t wg = 0;
     for (int l = 0; l < d->nlayers; ++l) {
-      size_t b = tconv_wgrad_ws_simt(&d->layers[l], d->S, d->B);
+      size_t b = wgrad_ws(&d->layers[l], d->S, d->B, d->math);
       if (b > wg) wg = b;
     }
     tot += align_up(wg);
@@ -134,13 +171,13 @@ extern "C" size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t b
 }
 
 static int xpath_recompute(const bsde_xpath_desc* d, const float* x, const float* wk, float t, float* const* a,
-                           cudaStream_t st) {
+                           void* tc_ws, size_t tc_bytes, cudaStream_t st) {
   const int n = d->nlayers;
   const long long wss = (long long)(d->nit + 1) * d->P;
   const float* in = x;
   for (int l = 0; l + 1 < n; ++l) {
     if (int e = conv_fwd(&d->layers[l], d->S, d->B, in, wk, wss, t, d->act, BSDE_EPI_BIAS_ACT, 1.f, nullptr,
-                         a[l], d->math, st))
+                         a[l], d->math, tc_ws, tc_bytes, st))
       return e;
     in = a[l];
   }
@@ -161,16 +198,19 @@ extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const
   const int n = d->nlayers;
   float* a[BSDE_MAX_LAYERS];
   char* ws = (char*)workspace;
+  void* tc_ws = ws;
+  const size_t tc_bytes = xpath_tc_bytes(d, 0);
+  ws += tc_bytes;
   for (int l = 0; l + 1 < n; ++l) { a[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
   const long long wss = (long long)(d->nit + 1) * d->P;
   for (int k = 0; k < d->nit; ++k) {
     const float* xk = d_xs + (size_t)k * d->x_numel;
     float* xn = d_xs + (size_t)(k + 1) * d->x_numel;
     const float* wk = d_wtraj + (size_t)k * d->P;
-    if (int e = xpath_recompute(d, xk, wk, h_tk[k], a, st)) return e;
+    if (int e = xpath_recompute(d, xk, wk, h_tk[k], a, tc_ws, tc_bytes, st)) return e;
     // last conv + Euler update: x_{k+1} = x_k + dt_k (conv(a_{n-2}) + b)   (sdeint.py:48-50, g_x = 0)
     if (int e = conv_fwd(&d->layers[n - 1], d->S, d->B, a[n - 2], wk, wss, h_tk[k], d->act, BSDE_EPI_EULER,
-                         h_dtk[k], xk, xn, d->math, st))
+                         h_dtk[k], xk, xn, d->math, tc_ws, tc_bytes, st))
       return e;
   }
   return 0;
@@ -191,6 +231,9 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
   float* a[BSDE_MAX_LAYERS];
   float* dz[BSDE_MAX_LAYERS];
   char* ws = (char*)workspace;
+  void* tc_ws = ws;
+  const size_t tc_bytes = xpath_tc_bytes(d, 1);
+  ws += tc_bytes;
   for (int l = 0; l + 1 < n; ++l) { a[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
   for (int l = 0; l + 1 < n; ++l) { dz[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
   void* wg_ws = ws;
@@ -206,23 +249,23 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
     const float* xk = d_xs + (size_t)k * d->x_numel;
     const float* wk = d_wtraj + (size_t)k * d->P;
     float* gwk = d_gw_traj + (size_t)k * d->P;
-    if (int e = xpath_recompute(d, xk, wk, t, a, st)) return e;
+    if (int e = xpath_recompute(d, xk, wk, t, a, tc_ws, tc_bytes, st)) return e;
     // walk the stack backwards; `dy` is dL/d(conv output of layer l)
     const float* dy = d_gx;  // for the last layer dL/d(conv out) = dt * gx  (scale folded below)
     for (int l = n - 1; l >= 0; --l) {
       const float* lin = l == 0 ? xk : a[l - 1];
       const float sc = (l == n - 1) ? dt : 1.f;
-      if (int e = tconv_wgrad_simt(&d->layers[l], d->S, d->B, lin, dy, t, sc, gwk, gss, wg_ws, wg_bytes, st)) return e;
+      if (int e = conv_wgrad(&d->layers[l], d->S, d->B, lin, dy, t, sc, gwk, gss, d->math, wg_ws, wg_bytes, st)) return e;
       if (l > 0) {
         // dz_{l-1} = sc * dgrad(dy) * act'(a_{l-1})
         if (int e = conv_fwd(&D[l], d->S, d->B, dy, wk, wss, t, d->act, BSDE_EPI_DACT, sc, a[l - 1], dz[l - 1],
-                             BSDE_MATH_FP32, st))
+                             d->math, tc_ws, tc_bytes, st))
           return e;
         dy = dz[l - 1];
       } else {
         // gx_k = gx_{k+1} + dgrad_0(dz_0)   (identity path of the Euler update)
         if (int e = conv_fwd(&D[0], d->S, d->B, dy, wk, wss, t, d->act, BSDE_EPI_ACCUM, sc, d_gx, d_gx,
-                             BSDE_MATH_FP32, st))
+                             d->math, tc_ws, tc_bytes, st))
           return e;
       }
     }

@@ -92,6 +92,18 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t p, uint32
   return r * cs;
 }
 
+// arguments of the fixed-order split reduction of weight-gradient partial tiles (tconv_simt.cu)
+struct WreduceArgs {
+  const float* partial;
+  const float* bias_partial;  // swapped form: [S][splits][cout] column sums, else NULL
+  float* gw;
+  long long gw_sample_stride;
+  int S, splits, rows, cols, Kc, Ktot, has_time, time_row, real_base, swapped, cin, cout;
+  long long w_off, b_off, ts, ks, ns;
+  float scale;
+};
+int launch_wgrad_reduce(const WreduceArgs& a, int blocks, cudaStream_t st);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

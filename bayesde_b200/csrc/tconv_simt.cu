@@ -363,15 +363,6 @@ __global__ void colsum_partial_kernel(const float* __restrict__ dy, float* __res
   }
 }
 
-struct WreduceArgs {
-  const float* partial;
-  const float* bias_partial;  // swapped form: [S][splits][cout] column sums, else NULL
-  float* gw;
-  long long gw_sample_stride;
-  int S, splits, rows, cols, Kc, Ktot, has_time, time_row, real_base, swapped, cin, cout;
-  long long w_off, b_off, ts, ks, ns;
-  float scale;
-};
 
 __global__ void wgrad_reduce_kernel(WreduceArgs a) {
   const long long per = (long long)a.rows * a.cols;
@@ -410,6 +401,13 @@ __global__ void wgrad_reduce_kernel(WreduceArgs a) {
       a.gw[s * a.gw_sample_stride + a.b_off + c] = v * a.scale;
     }
   }
+}
+
+int launch_wgrad_reduce(const WreduceArgs& a, int blocks, cudaStream_t st) {
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(a);
+  BSDE_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
 }
 
 static int check_layer(const bsde_conv_layer* L) {

@@ -1,0 +1,451 @@
+// K3 weight gradient on tcgen05 tensor cores (TF32 operands, fp32 accumulation in TMEM).
+//
+//   G[(tap, ka)][nb] = sum over pixels m of  A(m; tap, ka) * Bm(m; nb)
+//
+// The reduction index is the PIXEL, so both operands are consumed "MN-major" exactly as they lie in
+// NHWC memory (channels contiguous per pixel): a k-block is KP=16 pixels, every 128-byte (32-channel)
+// slice of a pixel row is one row of a SWIZZLE_128B_BASE32B MN block.  Per k-block the producers gather the nine
+// shifted copies of the A rows (zero-filled outside the image) plus the plain Bm rows with cp.async;
+// one thread issues M=128 MMAs, each covering four consecutive (tap, 32-channel) blocks, all
+// accumulating in TMEM for the whole pixel chunk of the CTA.  Chunks are split across CTAs; partial
+// tiles go to the workspace and the fixed-order reduction kernel of tconv_simt.cu finishes (no atomics).
+//   direct form  (forward layers with sd == 1): A = layer input gathered by the forward map, Bm = dy.
+//   swapped form (lhs-dilated layers, sd == 2): A = dy gathered by the data-gradient map, Bm = input.
+// The time-channel rows (t * sum of dy over the pixels where the tap is inside the image) and the bias
+// row (sum of dy) are tap-masked column sums of dy; a small CUDA-core kernel adds them to the partials.
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace bsde {
+
+constexpr int WG_KP = 16;        // pixels per k-block
+constexpr int WG_PROD = 256;
+constexpr int WG_THREADS = WG_PROD + 32;
+constexpr int WG_REGION = WG_KP * 128;  // bytes of one MN block of one k-block
+
+struct WgTcArgs {
+  const float* ga;   // gathered operand  [S][B*hA*wA][CA]
+  const float* bm;   // plain operand     [S][Mper][CB]
+  float* partial;    // [S][splits][rows][cols]
+  int S, B, splits, chunk;
+  int CA, CB, ksize, hA, wA, hM, wM, sn, kn, off, sd;  // gather geometry; (hM,wM) = pixel loop space
+  int rows, cols, Mper;
+  int row_stride_tap;   // partial row = tap*row_stride_tap + channel
+  int bt, nblk, nmma, npad, nbB, stages, tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t wg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wg_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void wg_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void wg_cp16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void wg_cp4(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ bool wg_map_axis(int o, int k, int sn, int kn, int off, int sd, int size, int& i) {
+  int num = o * sn + k * kn + off;
+  if (num < 0) return false;
+  if (sd == 2) {
+    if (num & 1) return false;
+    num >>= 1;
+  }
+  i = num;
+  return num < size;
+}
+// MN-major TF32 operands must use the SWIZZLE_128B_BASE32B layout (verified on hardware with
+// tools/umma_probe.cu): rows of 128 B (32 channels of one pixel), the four 32-byte granules of a row
+// XOR-permuted with (k & 3), k-atoms of 4 rows = 512 B (SBO), MN blocks `lbo` bytes apart (LBO).
+__device__ __forceinline__ uint64_t wg_desc_mn_sw128(uint32_t saddr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+template <bool VA, bool VB>
+__global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s = blockIdx.x / a.splits, split = blockIdx.x - s * a.splits;
+  const int mbeg = split * a.chunk;
+  const int mend = min(a.Mper, mbeg + a.chunk);
+  const int NKB = (mend - mbeg + WG_KP - 1) / WG_KP;
+  const int ntap = a.ksize * a.ksize;
+
+  const uint32_t raw = wg_smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const int a_bytes = a.nblk * WG_REGION, b_bytes = a.nbB * WG_REGION;
+  const int stage_bytes = a_bytes + b_bytes;
+  const uint32_t bars = base + a.stages * stage_bytes;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + a.stages * stage_bytes + 8 * (2 * 4 + 1));
+  auto full_bar = [&](int st) { return bars + 8u * st; };
+  auto empty_bar = [&](int st) { return bars + 8u * (4 + st); };
+  const uint32_t tmem_full_bar = bars + 8u * 8;
+
+  const float* __restrict__ ga = a.ga + (long long)s * a.B * a.hA * a.wA * a.CA;
+  const float* __restrict__ bm = a.bm + (long long)s * a.Mper * a.CB;
+
+  // zero all stages once: padded channels / padded blocks are never written by the gathers
+  for (int i = tid; i < a.stages * stage_bytes / 16; i += WG_THREADS)
+    reinterpret_cast<uint4*>(gen)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == WG_PROD / 32) {
+    if (lane == 0) {
+      for (int i = 0; i < a.stages; ++i) { wg_mbar_init(full_bar(i), WG_PROD); wg_mbar_init(empty_bar(i), 1); }
+      wg_mbar_init(tmem_full_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wg_smem_u32(tmem_slot)),
+                 "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic zero-fill -> visible to the MMA's async proxy
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < WG_PROD / 32) {
+    // =============================== producers ===============================
+    const int ncA = VA ? a.CA / 4 : a.CA;   // copy units per pixel row of A (16 B or 4 B)
+    const int ncB = VB ? a.CB / 4 : a.CB;
+    const int hw = a.hM * a.wM;
+#pragma unroll 1
+    for (int kb = 0; kb < NKB; ++kb) {
+      const int st = kb % a.stages;
+      if (kb >= a.stages) wg_mbar_wait(empty_bar(st), ((kb / a.stages) & 1) ^ 1);
+      const uint32_t sA = base + st * stage_bytes;
+      const uint32_t sB = sA + a_bytes;
+      const int mb = mbeg + kb * WG_KP;
+      // ---- A: nine shifted gathers of KP pixel rows
+#pragma unroll 1
+      for (int idx = tid; idx < WG_KP * ncA; idx += WG_PROD) {
+        const int p = idx / ncA, c = idx - p * ncA;
+        const int m = mb + p;
+        const bool mval = m < mend;
+        int img = 0, oy = 0, ox = 0;
+        if (mval) {
+          img = m / hw;
+          const int r = m - img * hw;
+          oy = r / a.wM;
+          ox = r - oy * a.wM;
+        }
+        const int ch = VA ? c * 4 : c;                  // first channel of this unit
+        const int blk_in_tap = ch >> 5;                 // 32-channel MN block
+        const int byte_in_row = (ch & 31) * 4;
+        const uint32_t swz = ((uint32_t)((byte_in_row >> 5) ^ (p & 3)) << 5) | (uint32_t)(byte_in_row & 31);
+        const uint32_t dst0 = sA + (uint32_t)blk_in_tap * WG_REGION + (uint32_t)p * 128u + swz;
+#pragma unroll 1
+        for (int tap = 0; tap < ntap; ++tap) {
+          const int kh = tap / a.ksize, kw = tap - kh * a.ksize;
+          int iy = 0, ix = 0;
+          const bool ok = mval && wg_map_axis(oy, kh, a.sn, a.kn, a.off, a.sd, a.hA, iy) &&
+                          wg_map_axis(ox, kw, a.sn, a.kn, a.off, a.sd, a.wA, ix);
+          const float* src = ok ? ga + (((long long)img * a.hA + iy) * a.wA + ix) * a.CA + ch : ga;
+          const uint32_t dst = dst0 + (uint32_t)(tap * a.bt) * WG_REGION;
+          if (VA) wg_cp16(dst, src, ok); else wg_cp4(dst, src, ok);
+        }
+      }
+      // ---- Bm: KP plain pixel rows
+#pragma unroll 1
+      for (int idx = tid; idx < WG_KP * ncB; idx += WG_PROD) {
+        const int p = idx / ncB, c = idx - p * ncB;
+        const int m = mb + p;
+        const bool ok = m < mend;
+        const int ch = VB ? c * 4 : c;
+        const int byte_in_row = (ch & 31) * 4;
+        const uint32_t swz = ((uint32_t)((byte_in_row >> 5) ^ (p & 3)) << 5) | (uint32_t)(byte_in_row & 31);
+        const uint32_t dst = sB + (uint32_t)(ch >> 5) * WG_REGION + (uint32_t)p * 128u + swz;
+        const float* src = ok ? bm + (long long)m * a.CB + ch : bm;
+        if (VB) wg_cp16(dst, src, ok); else wg_cp4(dst, src, ok);
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(st)) : "memory");
+    }
+
+    // =============================== epilogue ===============================
+    wg_mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* __restrict__ part = a.partial + ((long long)(s * a.splits + split) * a.rows) * a.cols;
+    const int q = warp & 3;            // TMEM lane quarter
+    const int r = q * 32 + lane;       // row inside an M=128 accumulator
+#pragma unroll 1
+    for (int i = 0; i < a.nmma; ++i) {
+      const int blk = 4 * i + (r >> 5);
+      const int tap = blk / a.bt;
+      const int ch = (blk - tap * a.bt) * 32 + (r & 31);
+      const bool rval = tap < ntap && ch < a.CA;
+      const long long prow = (long long)(tap * a.row_stride_tap + ch) * a.cols;
+#pragma unroll 1
+      for (int n0 = (warp >> 2) * 16; n0 < a.npad; n0 += 32) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * a.npad + n0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (rval) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + j < a.CB) part[prow + n0 + j] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  } else {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      // TF32 x TF32 -> F32, both operands MN-major, M=128, N=npad
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(a.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+#pragma unroll 1
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int st = kb % a.stages;
+        wg_mbar_wait(full_bar(st), (kb / a.stages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sA = base + st * stage_bytes;
+        const uint32_t sB = sA + a_bytes;
+#pragma unroll 1
+        for (int i = 0; i < a.nmma; ++i) {
+#pragma unroll
+          for (int j = 0; j < WG_KP / 8; ++j) {
+            const uint64_t ad = wg_desc_mn_sw128(sA + (uint32_t)(4 * i) * WG_REGION + (uint32_t)j * 1024u, WG_REGION);
+            const uint64_t bd = wg_desc_mn_sw128(sB + (uint32_t)j * 1024u, WG_REGION);
+            const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_base + (uint32_t)(i * a.npad)),
+                "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
+                : "memory");
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty_bar(st)) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tmem_full_bar) : "memory");
+    }
+    __syncwarp();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == WG_PROD / 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
+}
+
+// ---- tap-masked column sums of dy over OUTPUT pixels (forward validity): time rows + bias row ----
+struct TapSumArgs {
+  const float* dy;
+  float* partial;       // main partial array
+  float* bias_partial;  // swapped form only: [S][splits][cout]
+  int S, B, splits, chunk, cout, ksize, hin, win, hout, wout, sn, kn, off, sd;
+  int rows, cols, swapped, has_time, Kc, Ktot, cin;
+  float t;
+};
+
+__global__ void tap_colsum_kernel(TapSumArgs a) {
+  const int split = blockIdx.x, s = blockIdx.y;
+  const int Mout = a.B * a.hout * a.wout;
+  const int mbeg = split * a.chunk, mend = min(Mout, mbeg + a.chunk);
+  const float* __restrict__ dy = a.dy + (long long)s * Mout * a.cout;
+  float* __restrict__ part = a.partial + ((long long)(s * a.splits + split) * a.rows) * a.cols;
+  const int ntap = a.ksize * a.ksize;
+  const int hw = a.hout * a.wout;
+  __shared__ float red[4][10][64];
+  for (int c0 = 0; c0 < a.cout; c0 += 64) {
+    const int cw = min(64, a.cout - c0);
+    const int c = threadIdx.x & 63, pl = threadIdx.x >> 6;
+    float acc[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+    for (int m = mbeg + pl; m < mend; m += 4) {
+      const int img = m / hw;
+      const int r = m - img * hw;
+      const int oy = r / a.wout, ox = r - oy * a.wout;
+      const float v = c < cw ? __ldg(dy + (long long)m * a.cout + c0 + c) : 0.f;
+      acc[9] += v;
+      if (a.has_time) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          if (tap < ntap) {
+            const int kh = tap / a.ksize, kw = tap - kh * a.ksize;
+            int iy, ix;
+            if (wg_map_axis(oy, kh, a.sn, a.kn, a.off, a.sd, a.hin, iy) &&
+                wg_map_axis(ox, kw, a.sn, a.kn, a.off, a.sd, a.win, ix))
+              acc[tap] += v;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) red[pl][i][c] = acc[i];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 10 * 64; idx += blockDim.x) {
+      const int i = idx >> 6, cc = idx & 63;
+      if (cc >= cw) continue;
+      const float v = red[0][i][cc] + red[1][i][cc] + red[2][i][cc] + red[3][i][cc];
+      const int co = c0 + cc;
+      if (i == 9) {
+        if (!a.swapped) part[(long long)a.Ktot * a.cols + co] = v;
+        else if (a.bias_partial) a.bias_partial[((long long)s * a.splits + split) * a.cout + co] = v;
+      } else if (i < ntap && a.has_time) {
+        if (!a.swapped) part[(long long)(i * a.Kc + a.Kc - 1) * a.cols + co] = a.t * v;
+        else part[(long long)(i * a.cout + co) * a.cols + a.cin] = a.t * v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct WgTcPlan {
+  int swapped, rows, cols, splits, chunk, Mper, CA, CB, bt, nblk, nmma, npad, nbB, stages, tmem_cols, Mout, chunk_o;
+  size_t main_floats, bias_floats, smem;
+  bool ok;
+};
+
+static WgTcPlan wg_plan(const bsde_conv_layer* L, int S, int B) {
+  WgTcPlan p;
+  memset(&p, 0, sizeof(p));
+  const int taps = L->ksize * L->ksize;
+  p.swapped = L->sd == 2;
+  p.Mout = B * L->hout * L->wout;
+  if (!p.swapped) {
+    p.CA = L->cin; p.CB = L->cout;
+    p.rows = taps * (L->cin + (L->has_time ? 1 : 0)) + 1;
+    p.cols = L->cout;
+    p.Mper = p.Mout;
+  } else {
+    p.CA = L->cout; p.CB = L->cin;
+    p.rows = taps * L->cout;
+    p.cols = L->cin + (L->has_time ? 1 : 0);
+    p.Mper = B * L->hin * L->win;
+  }
+  p.bt = (p.CA + 31) / 32;
+  p.nmma = (taps * p.bt + 3) / 4;
+  p.nblk = p.nmma * 4;
+  p.npad = (p.CB + 15) / 16 * 16;
+  p.nbB = (p.CB + 31) / 32;
+  const int cols_needed = p.nmma * p.npad;
+  p.tmem_cols = cols_needed <= 32 ? 32 : cols_needed <= 64 ? 64 : cols_needed <= 128 ? 128 : cols_needed <= 256 ? 256 : 512;
+  const int stage_bytes = (p.nblk + p.nbB) * WG_REGION;
+  p.stages = std::min(4, (200 * 1024) / stage_bytes);
+  p.smem = 1024 + (size_t)p.stages * stage_bytes + 8 * 9 + 16;
+  p.ok = cols_needed <= 512 && p.stages >= 2 && p.npad <= 256 && !(p.swapped && L->sn != 1);
+  int want = (148 * 2 + S - 1) / S;
+  int maxs = (p.Mper + 1023) / 1024;
+  p.splits = std::max(1, std::min(want, maxs));
+  p.chunk = (p.Mper + p.splits - 1) / p.splits;
+  p.chunk = (p.chunk + WG_KP - 1) / WG_KP * WG_KP;
+  p.splits = (p.Mper + p.chunk - 1) / p.chunk;
+  p.chunk_o = (p.Mout + p.splits - 1) / p.splits;
+  p.main_floats = (size_t)S * p.splits * p.rows * p.cols;
+  p.bias_floats = p.swapped ? (size_t)S * p.splits * L->cout : 0;
+  return p;
+}
+
+bool tconv_wgrad_tc_supported(const bsde_conv_layer* L, int S, int B) {
+  if (!L || (L->ksize != 1 && L->ksize != 3)) return false;
+  return wg_plan(L, S, B).ok;
+}
+
+size_t tconv_wgrad_ws_tc(const bsde_conv_layer* L, int S, int B) {
+  WgTcPlan p = wg_plan(L, S, B);
+  return (p.main_floats + p.bias_floats) * sizeof(float);
+}
+
+int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
+                   float* gw, long long gw_sample_stride, void* ws, size_t ws_bytes, cudaStream_t st) {
+  WgTcPlan p = wg_plan(L, S, B);
+  BSDE_CHECK_ARG(p.ok, "layer not supported by the tensor-core wgrad");
+  const size_t need = (p.main_floats + p.bias_floats) * sizeof(float);
+  if (!ws || ws_bytes < need) {
+    set_error("tconv_wgrad(tc): workspace %zu < %zu bytes", ws_bytes, need);
+    return BSDE_ERR_WORKSPACE;
+  }
+  float* partial = (float*)ws;
+  float* bias_partial = p.swapped ? partial + p.main_floats : nullptr;
+  const int Kc = L->cin + (L->has_time ? 1 : 0);
+  const int Ktot = L->ksize * L->ksize * Kc;
+
+  WgTcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.partial = partial; a.S = S; a.B = B; a.splits = p.splits; a.chunk = p.chunk;
+  a.CA = p.CA; a.CB = p.CB; a.ksize = L->ksize; a.rows = p.rows; a.cols = p.cols; a.Mper = p.Mper;
+  a.bt = p.bt; a.nblk = p.nblk; a.nmma = p.nmma; a.npad = p.npad; a.nbB = p.nbB; a.stages = p.stages; a.tmem_cols = p.tmem_cols;
+  if (!p.swapped) {
+    a.ga = in; a.bm = dy;
+    a.hA = L->hin; a.wA = L->win; a.hM = L->hout; a.wM = L->wout;
+    a.sn = L->sn; a.kn = L->kn; a.off = L->off; a.sd = L->sd;
+    a.row_stride_tap = Kc;
+  } else {
+    a.ga = dy; a.bm = in;
+    a.hA = L->hout; a.wA = L->wout; a.hM = L->hin; a.wM = L->win;
+    a.sn = L->sd; a.kn = -L->kn; a.off = -L->off; a.sd = L->sn;
+    a.row_stride_tap = L->cout;
+  }
+  const bool va = p.CA % 4 == 0, vb = p.CB % 4 == 0;
+#define WG_LAUNCH(VA_, VB_)                                                                                            \
+  do {                                                                                                                 \
+    BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<VA_, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
+    wgrad_tc_kernel<VA_, VB_><<<S * p.splits, WG_THREADS, p.smem, st>>>(a);                                            \
+  } while (0)
+  if (va && vb) WG_LAUNCH(true, true);
+  else if (va) WG_LAUNCH(true, false);
+  else if (vb) WG_LAUNCH(false, true);
+  else WG_LAUNCH(false, false);
+#undef WG_LAUNCH
+  BSDE_CUDA_OK(cudaGetLastError());
+  count_launch();
+
+  TapSumArgs ta;
+  memset(&ta, 0, sizeof(ta));
+  ta.dy = dy; ta.partial = partial; ta.bias_partial = (L->b_off >= 0) ? bias_partial : nullptr;
+  ta.S = S; ta.B = B; ta.splits = p.splits; ta.chunk = p.chunk_o; ta.cout = L->cout; ta.ksize = L->ksize;
+  ta.hin = L->hin; ta.win = L->win; ta.hout = L->hout; ta.wout = L->wout;
+  ta.sn = L->sn; ta.kn = L->kn; ta.off = L->off; ta.sd = L->sd;
+  ta.rows = p.rows; ta.cols = p.cols; ta.swapped = p.swapped; ta.has_time = L->has_time; ta.Kc = Kc; ta.Ktot = Ktot;
+  ta.cin = L->cin; ta.t = t;
+  tap_colsum_kernel<<<dim3(p.splits, S), 256, 0, st>>>(ta);
+  BSDE_CUDA_OK(cudaGetLastError());
+  count_launch();
+
+  WreduceArgs r;
+  memset(&r, 0, sizeof(r));
+  r.partial = partial; r.bias_partial = nullptr; r.gw = gw; r.gw_sample_stride = gw_sample_stride;
+  r.S = S; r.splits = p.splits; r.rows = p.rows; r.cols = p.cols; r.Kc = Kc; r.Ktot = Ktot;
+  r.has_time = L->has_time; r.time_row = L->time_first ? 0 : L->cin;
+  r.real_base = (L->has_time && L->time_first) ? 1 : 0; r.swapped = p.swapped; r.cin = L->cin; r.cout = L->cout;
+  r.w_off = L->w_off; r.b_off = L->b_off; r.ts = L->w_tap_stride; r.ks = L->w_k_stride; r.ns = L->w_n_stride;
+  r.scale = scale;
+  if (p.swapped && L->b_off >= 0) {
+    WreduceArgs rb = r;
+    rb.partial = nullptr; rb.bias_partial = bias_partial; rb.rows = 0; rb.cols = 1;
+    if (int e = launch_wgrad_reduce(rb, (S * L->cout + 255) / 256, st)) return e;
+  }
+  const long long total = (long long)S * p.rows * p.cols;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  return launch_wgrad_reduce(r, blocks, st);
+}
+
+}  // namespace bsde

@@ -53,7 +53,8 @@ typedef enum { BSDE_ACT_SOFTPLUS = 0, BSDE_ACT_TANH = 1, BSDE_ACT_ELU = 2, BSDE_
 
 typedef enum { BSDE_EULER_MARUYAMA = 0, BSDE_MILSTEIN = 1, BSDE_EULER_HEUN = 2 } bsde_method;
 
-/* conv arithmetic mode: exact fp32 FMA on CUDA cores, or tcgen05 tensor-core tiles */
+/* conv arithmetic mode: exact fp32 FMA on CUDA cores, or tcgen05 tensor-core tiles
+ * (kind::tf32 operands, fp32 accumulation in TMEM) */
 typedef enum { BSDE_MATH_FP32 = 0, BSDE_MATH_TC = 1 } bsde_math;
 
 int bsde_version(void);
@@ -154,7 +155,10 @@ typedef enum {
 int bsde_tconv_fwd(const bsde_conv_layer* L, int32_t S, int32_t B, const float* d_in,
                    const float* d_w, int64_t w_sample_stride, float t, int32_t act,
                    int32_t epilogue, float scale, const float* d_aux, float* d_out, int32_t math,
-                   void* stream);
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* scratch for the repacked weight tiles of the tensor-core path (0 for BSDE_MATH_FP32) */
+size_t bsde_tconv_fwd_workspace_bytes(const bsde_conv_layer* L, int32_t S, int32_t math);
 
 size_t bsde_tconv_wgrad_workspace_bytes(const bsde_conv_layer* L, int32_t S, int32_t B);
 

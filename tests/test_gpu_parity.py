@@ -77,7 +77,7 @@ def test_tconv_layers_forward_and_wgrad(built_lib, C_in, fx_dim, H):
         wd = w.float().to(DEV).contiguous()
         out = torch.empty(ref.shape, device=DEV)
         st = L.bsde_tconv_fwd(C.byref(cs), S, B, _lib.ptr(xd), _lib.ptr(wd), P, t, 0, _lib.EPI_BIAS, 1.0, None,
-                              _lib.ptr(out), 0, _lib.stream_ptr())
+                              _lib.ptr(out), 0, None, 0, _lib.stream_ptr())
         _lib.check(st, "tconv_fwd")
         _close(out, ref, 1e-5, 1e-5, f"conv layer {li} forward")
         # weight gradient
@@ -322,3 +322,108 @@ def test_classifier_loss_and_grads(built_lib):
     assert len(leaves) == len(leaves_r)
     for i, (p, gr) in enumerate(zip(leaves, grads_r)):
         _gclose(p.grad, gr, 2e-3, f"param {i} grad")
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core path (math="tc": tcgen05 kind::tf32 operands, fp32 accumulation).  TF32 keeps 10 mantissa
+# bits, so the tolerance is stated relative to the tensor's scale: 2e-3 * max|ref| per conv evaluation.
+# ------------------------------------------------------------------------------------------------
+def _tc_close(a, b, rel, what):
+    b64 = b.detach().double().cpu()
+    _close(a, b, 0.0, rel * float(b64.abs().max()) + 1e-12, what)
+
+
+@pytest.mark.parametrize("C_in,fx_dim,H,B", [(5, 64, 8, 3), (20, 64, 16, 2), (80, 64, 8, 5), (4, 16, 6, 3)])
+def test_tconv_tc_layers_forward_and_dgrad(built_lib, C_in, fx_dim, H, B):
+    """Every forward geometry and every data gradient on the tcgen05 path vs the fp64 oracle."""
+    from bayesde_b200 import _lib
+    from bayesde_b200.arch import FxSpec
+    L = _lib.lib()
+    S, t = 2, 0.61
+    fx = FxSpec(0, (1, H, H, C_in), fx_dim, "softplus")
+    layout, P = jp.fx_layout(0, C_in, fx_dim)
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(S, P, generator=g, dtype=torch.float64) * 0.2
+    conv_entries = [e for e in layout if e["kind"] == "conv"]
+    for li, (Ld, e) in enumerate(zip(fx.layers, conv_entries)):
+        x = torch.randn(S, B, Ld["hin"], Ld["win"], Ld["cin"], generator=g, dtype=torch.float64)
+        n = e["k"] ** 2 * (e["cin"] + 1) * e["cout"]
+        xr = x.clone().requires_grad_(True)
+        ref = torch.stack([jp.concat_conv2d(xr[s], t, w[s, e["w_off"]:e["w_off"] + n].reshape(e["w_shape"]),
+                                            w[s, e["b_off"]:e["b_off"] + e["cout"]], e["stride"], e["transpose"])
+                           for s in range(S)])
+        cs = _conv_struct(Ld)
+        xd, wd = x.float().to(DEV).contiguous(), w.float().to(DEV).contiguous()
+        out = torch.empty(ref.shape, device=DEV)
+        nb = L.bsde_tconv_fwd_workspace_bytes(C.byref(cs), S, 1)
+        assert nb > 0
+        ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+        st = L.bsde_tconv_fwd(C.byref(cs), S, B, _lib.ptr(xd), _lib.ptr(wd), P, t, 0, _lib.EPI_BIAS, 1.0, None,
+                              _lib.ptr(out), 1, C.c_void_p(ws.data_ptr()), nb, _lib.stream_ptr())
+        _lib.check(st, "tconv_fwd tc")
+        torch.cuda.synchronize()
+        _tc_close(out, ref, 2e-3, f"tc conv layer {li} forward")
+        # data gradient through the same kernel: dgrad descriptor built like csrc/api.cu dgrad_layer()
+        dy = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+        (gx_ref,) = torch.autograd.grad((ref * dy).sum(), xr)
+        D = _lib.ConvLayer()
+        for f_, _t in _lib.ConvLayer._fields_:
+            setattr(D, f_, getattr(cs, f_))
+        D.cin, D.cout = cs.cout, cs.cin
+        D.hin, D.win, D.hout, D.wout = cs.hout, cs.wout, cs.hin, cs.win
+        D.sn, D.kn, D.off, D.sd = cs.sd, -cs.kn, -cs.off, cs.sn
+        D.has_time, D.time_first, D.b_off = 0, 0, -1
+        D.w_k_stride, D.w_n_stride = cs.w_n_stride, cs.w_k_stride
+        gx = torch.zeros(x.shape, device=DEV)
+        nb = L.bsde_tconv_fwd_workspace_bytes(C.byref(D), S, 1)
+        ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+        st = L.bsde_tconv_fwd(C.byref(D), S, B, _lib.ptr(dy.float().to(DEV).contiguous()), _lib.ptr(wd), P, t, 0,
+                              _lib.EPI_ACCUM, 1.0, _lib.ptr(gx), _lib.ptr(gx), 1, C.c_void_p(ws.data_ptr()), nb,
+                              _lib.stream_ptr())
+        _lib.check(st, "tconv dgrad tc")
+        torch.cuda.synchronize()
+        _tc_close(gx, gx_ref, 2e-3, f"tc conv layer {li} dgrad")
+        # weight gradient on the tensor cores (direct form, or swapped form for the lhs-dilated layer)
+        gref = []
+        for s_ in range(S):
+            ws_ = w[s_].clone().requires_grad_(True)
+            o_ = jp.concat_conv2d(x[s_], t, ws_[e["w_off"]:e["w_off"] + n].reshape(e["w_shape"]),
+                                  ws_[e["b_off"]:e["b_off"] + e["cout"]], e["stride"], e["transpose"])
+            (g_,) = torch.autograd.grad((o_ * dy[s_]).sum(), ws_)
+            gref.append(g_)
+        gref = torch.stack(gref)
+        gwd = torch.zeros(S, P, device=DEV)
+        nb = L.bsde_tconv_wgrad_workspace_bytes(C.byref(cs), S, B)
+        ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+        st = L.bsde_tconv_wgrad(C.byref(cs), S, B, _lib.ptr(xd), _lib.ptr(dy.float().to(DEV).contiguous()), t, 0.5,
+                                _lib.ptr(gwd), P, 1, C.c_void_p(ws.data_ptr()), nb, _lib.stream_ptr())
+        _lib.check(st, "tconv_wgrad tc")
+        torch.cuda.synchronize()
+        lo, hi = e["w_off"], e["b_off"] + e["cout"]
+        _tc_close(gwd[:, lo:hi], 0.5 * gref[:, lo:hi], 2e-3, f"tc conv layer {li} wgrad")
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(S=1, B=3, H=4, C_in=20, fx_dim=16, fw_dims=(1, 8, 1)),
+                                dict(S=2, B=4, H=8, C_in=80, fx_dim=64, nsteps=4)])
+def test_sdebnn_block_tc(built_lib, kw):
+    """One SDEBNN block with math="tc" vs the fp64 oracle.  Stated tolerance (TF32 operands, 10-bit
+    mantissa, nsteps-1 Euler steps): 5e-3 * max|ref| on x_T, 2e-2 * max|ref| on every gradient (the reverse
+    pass chains 4 TF32 data-gradient convs per iteration); the w path and the KL never touch the tensor
+    cores and keep the fp32 tolerances."""
+    from bayesde_b200 import arch, brax
+    blk, w0, fw, x, dW = _block_case(**kw)
+    xo_r, kl_r, wt_r, cot, grads_r = _oracle_block(blk, w0, fw, x, dW)
+    layer = brax.SDEBNN(0, blk.layout[0]["cout"], "softplus", arch.MLP(kw.get("fw_dims", (2, 16, 2)), xt=True, ou_dw=True),
+                        diff_coef=blk.diff_coef, xt=True, nsteps=blk.nsteps, math="tc")
+    w0d = w0.float().to(DEV).requires_grad_(True)
+    fwd = _product_fw_params(fw, DEV)
+    xd = x.float().to(DEV).requires_grad_(True)
+    xo, kl, info = layer.apply((w0d, (), fwd), xd, dW.float().to(DEV), full_output=True)
+    _tc_close(xo, xo_r, 5e-3, "tc x_T")
+    _close(info["sdebnn_w"], wt_r, 1e-5, 1e-6, "w trajectory")
+    _close(kl, kl_r, 1e-4, 1e-6, "sum KL")
+    obj = (xo * cot.float().to(DEV)).sum() + 1e-3 * kl.sum()
+    leaves = [xd, w0d] + [t for lay in arch.fw_layers(fwd) for t in lay]
+    grads = torch.autograd.grad(obj, leaves)
+    for i, (a, b) in enumerate(zip(grads, grads_r)):
+        _tc_close(a, b, 2e-2, f"tc grad {i}")
