@@ -35,6 +35,7 @@ struct WgTcArgs {
   int rows, cols, Mper;
   int row_stride_tap;   // partial row = tap*row_stride_tap + channel
   int bt, nblk, nmma, npad, nbB, stages, tmem_cols;
+  int dbg;  // tools/ only: 2 skip MMA, 4 skip A gathers
 };
 
 __device__ __forceinline__ uint32_t wg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,9 +130,59 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgTcArgs a) {
 
   if (warp < WG_PROD / 32) {
     // =============================== producers ===============================
+    // The gather map of this kernel always has sd == 1 (direct form: forward layers with sd == 1;
+    // swapped form: the data-gradient map of an lhs-dilated layer), so i = o*sn + (k*kn + off).
     const int ncA = VA ? a.CA / 4 : a.CA;   // copy units per pixel row of A (16 B or 4 B)
     const int ncB = VB ? a.CB / 4 : a.CB;
-    const int hw = a.hM * a.wM;
+    constexpr int MAXU = 3;
+    // fixed (pixel-in-block, channel) units of this thread, and its running pixel coordinates
+    int uA_n = 0, uA_ch[MAXU], uA_img[MAXU], uA_oy[MAXU], uA_ox[MAXU];
+    uint32_t uA_dst[MAXU];
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      const int idx = tid + u * WG_PROD;
+      uA_ch[u] = 0; uA_img[u] = 0; uA_oy[u] = 0; uA_ox[u] = 0; uA_dst[u] = 0;
+      if (idx < WG_KP * ncA) {
+        uA_n = u + 1;
+        const int p = idx / ncA, c = idx - p * ncA;
+        const int ch = VA ? c * 4 : c;
+        const int byte_in_row = (ch & 31) * 4;
+        uA_ch[u] = ch;
+        uA_dst[u] = (uint32_t)(ch >> 5) * WG_REGION + (uint32_t)p * 128u +
+                    (((uint32_t)((byte_in_row >> 5) ^ (p & 3)) << 5) | (uint32_t)(byte_in_row & 31));
+        const int m = mbeg + p;
+        const int hw = a.hM * a.wM;
+        uA_img[u] = m / hw;
+        const int r = m - uA_img[u] * hw;
+        uA_oy[u] = r / a.wM;
+        uA_ox[u] = r - uA_oy[u] * a.wM;
+      }
+    }
+    int uB_n = 0, uB_ch[MAXU], uB_p[MAXU];
+    uint32_t uB_dst[MAXU];
+#pragma unroll
+    for (int u = 0; u < MAXU; ++u) {
+      const int idx = tid + u * WG_PROD;
+      uB_ch[u] = 0; uB_p[u] = 0; uB_dst[u] = 0;
+      if (idx < WG_KP * ncB) {
+        uB_n = u + 1;
+        const int p = idx / ncB, c = idx - p * ncB;
+        const int ch = VB ? c * 4 : c;
+        const int byte_in_row = (ch & 31) * 4;
+        uB_ch[u] = ch; uB_p[u] = p;
+        uB_dst[u] = (uint32_t)(ch >> 5) * WG_REGION + (uint32_t)p * 128u +
+                    (((uint32_t)((byte_in_row >> 5) ^ (p & 3)) << 5) | (uint32_t)(byte_in_row & 31));
+      }
+    }
+    // per-tap displacement table
+    __shared__ int s_ty[9], s_tx[9], s_toff[9];
+    if (tid < ntap) {
+      const int kh = tid / a.ksize, kw = tid - kh * a.ksize;
+      s_ty[tid] = kh * a.kn + a.off;
+      s_tx[tid] = kw * a.kn + a.off;
+      s_toff[tid] = (s_ty[tid] * a.wA + s_tx[tid]) * a.CA;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(WG_PROD) : "memory");
 #pragma unroll 1
     for (int kb = 0; kb < NKB; ++kb) {
       const int st = kb % a.stages;
@@ -139,47 +190,35 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgTcArgs a) {
       const uint32_t sA = base + st * stage_bytes;
       const uint32_t sB = sA + a_bytes;
       const int mb = mbeg + kb * WG_KP;
-      // ---- A: nine shifted gathers of KP pixel rows
+#pragma unroll
+      for (int u = 0; u < MAXU; ++u) {
+        if (u < uA_n) {
+          const bool mval = (uA_img[u] < a.B) && (mb + (int)((uA_dst[u] >> 7) & (WG_KP - 1)) < mend);
+          const int by = uA_oy[u] * a.sn, bx = uA_ox[u] * a.sn;
+          const int boff = ((uA_img[u] * a.hA + by) * a.wA + bx) * a.CA + uA_ch[u];
 #pragma unroll 1
-      for (int idx = tid; idx < WG_KP * ncA; idx += WG_PROD) {
-        const int p = idx / ncA, c = idx - p * ncA;
-        const int m = mb + p;
-        const bool mval = m < mend;
-        int img = 0, oy = 0, ox = 0;
-        if (mval) {
-          img = m / hw;
-          const int r = m - img * hw;
-          oy = r / a.wM;
-          ox = r - oy * a.wM;
-        }
-        const int ch = VA ? c * 4 : c;                  // first channel of this unit
-        const int blk_in_tap = ch >> 5;                 // 32-channel MN block
-        const int byte_in_row = (ch & 31) * 4;
-        const uint32_t swz = ((uint32_t)((byte_in_row >> 5) ^ (p & 3)) << 5) | (uint32_t)(byte_in_row & 31);
-        const uint32_t dst0 = sA + (uint32_t)blk_in_tap * WG_REGION + (uint32_t)p * 128u + swz;
-#pragma unroll 1
-        for (int tap = 0; tap < ntap; ++tap) {
-          const int kh = tap / a.ksize, kw = tap - kh * a.ksize;
-          int iy = 0, ix = 0;
-          const bool ok = mval && wg_map_axis(oy, kh, a.sn, a.kn, a.off, a.sd, a.hA, iy) &&
-                          wg_map_axis(ox, kw, a.sn, a.kn, a.off, a.sd, a.wA, ix);
-          const float* src = ok ? ga + (((long long)img * a.hA + iy) * a.wA + ix) * a.CA + ch : ga;
-          const uint32_t dst = dst0 + (uint32_t)(tap * a.bt) * WG_REGION;
-          if (VA) wg_cp16(dst, src, ok); else wg_cp4(dst, src, ok);
+          for (int tap = 0; tap < ((a.dbg & 4) ? 0 : ntap); ++tap) {
+            const bool ok = mval && (unsigned)(by + s_ty[tap]) < (unsigned)a.hA && (unsigned)(bx + s_tx[tap]) < (unsigned)a.wA;
+            const float* src = ok ? ga + (boff + s_toff[tap]) : ga;
+            const uint32_t dst = sA + uA_dst[u] + (uint32_t)(tap * a.bt) * WG_REGION;
+            if (VA) wg_cp16(dst, src, ok); else wg_cp4(dst, src, ok);
+          }
+          // advance this unit's pixel by KP for the next k-block
+          uA_ox[u] += WG_KP;
+          while (uA_ox[u] >= a.wM) {
+            uA_ox[u] -= a.wM;
+            if (++uA_oy[u] == a.hM) { uA_oy[u] = 0; ++uA_img[u]; }
+          }
         }
       }
-      // ---- Bm: KP plain pixel rows
-#pragma unroll 1
-      for (int idx = tid; idx < WG_KP * ncB; idx += WG_PROD) {
-        const int p = idx / ncB, c = idx - p * ncB;
-        const int m = mb + p;
-        const bool ok = m < mend;
-        const int ch = VB ? c * 4 : c;
-        const int byte_in_row = (ch & 31) * 4;
-        const uint32_t swz = ((uint32_t)((byte_in_row >> 5) ^ (p & 3)) << 5) | (uint32_t)(byte_in_row & 31);
-        const uint32_t dst = sB + (uint32_t)(ch >> 5) * WG_REGION + (uint32_t)p * 128u + swz;
-        const float* src = ok ? bm + (long long)m * a.CB + ch : bm;
-        if (VB) wg_cp16(dst, src, ok); else wg_cp4(dst, src, ok);
+#pragma unroll
+      for (int u = 0; u < MAXU; ++u) {
+        if (u < uB_n) {
+          const int m = mb + uB_p[u];
+          const bool ok = m < mend;
+          const float* src = ok ? bm + (long long)m * a.CB + uB_ch[u] : bm;
+          if (VB) wg_cp16(sB + uB_dst[u], src, ok); else wg_cp4(sB + uB_dst[u], src, ok);
+        }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(st)) : "memory");
     }
@@ -228,7 +267,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgTcArgs a) {
         const uint32_t sA = base + st * stage_bytes;
         const uint32_t sB = sA + a_bytes;
 #pragma unroll 1
-        for (int i = 0; i < a.nmma; ++i) {
+        for (int i = 0; i < ((a.dbg & 2) ? 0 : a.nmma); ++i) {
 #pragma unroll
           for (int j = 0; j < WG_KP / 8; ++j) {
             const uint64_t ad = wg_desc_mn_sw128(sA + (uint32_t)(4 * i) * WG_REGION + (uint32_t)j * 1024u, WG_REGION);
@@ -263,58 +302,84 @@ struct TapSumArgs {
   float t;
 };
 
-__global__ void tap_colsum_kernel(TapSumArgs a) {
+__global__ void __launch_bounds__(1024) tap_colsum_kernel(TapSumArgs a) {
+  // threads = (pixel lane, column): `cp` columns (power of two >= cout, at most 64 per pass)
   const int split = blockIdx.x, s = blockIdx.y;
   const int Mout = a.B * a.hout * a.wout;
   const int mbeg = split * a.chunk, mend = min(Mout, mbeg + a.chunk);
   const float* __restrict__ dy = a.dy + (long long)s * Mout * a.cout;
   float* __restrict__ part = a.partial + ((long long)(s * a.splits + split) * a.rows) * a.cols;
   const int ntap = a.ksize * a.ksize;
+  __shared__ float red[10][1024];
+  __shared__ unsigned s_rowmask[64], s_colmask[64];  // per output row / column: valid kh / kw bits
+  for (int i = threadIdx.x; i < a.hout + a.wout; i += blockDim.x) {
+    const bool isrow = i < a.hout;
+    const int o = isrow ? i : i - a.hout;
+    unsigned mk = 0;
+    for (int k = 0; k < a.ksize; ++k) {
+      int ii;
+      if (wg_map_axis(o, k, a.sn, a.kn, a.off, a.sd, isrow ? a.hin : a.win, ii)) mk |= 1u << k;
+    }
+    if (isrow) s_rowmask[o] = mk; else s_colmask[o] = mk;
+  }
+  __syncthreads();
+  int cp = 1;
+  while (cp < a.cout && cp < 64) cp <<= 1;
+  const int lanes = 1024 / cp;
+  const int c = threadIdx.x & (cp - 1), pl = threadIdx.x / cp;
   const int hw = a.hout * a.wout;
-  __shared__ float red[4][10][64];
   for (int c0 = 0; c0 < a.cout; c0 += 64) {
-    const int cw = min(64, a.cout - c0);
-    const int c = threadIdx.x & 63, pl = threadIdx.x >> 6;
+    const bool cval = c0 + c < a.cout;
     float acc[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] = 0.f;
-    for (int m = mbeg + pl; m < mend; m += 4) {
-      const int img = m / hw;
-      const int r = m - img * hw;
-      const int oy = r / a.wout, ox = r - oy * a.wout;
-      const float v = c < cw ? __ldg(dy + (long long)m * a.cout + c0 + c) : 0.f;
+    int m = mbeg + pl;
+    int img = m / hw;
+    int r = m - img * hw;
+    int oy = r / a.wout, ox = r - oy * a.wout;
+#pragma unroll 1
+    for (; m < mend; m += lanes) {
+      const float v = cval ? __ldg(dy + (long long)m * a.cout + c0 + c) : 0.f;
       acc[9] += v;
       if (a.has_time) {
+        const unsigned rm = s_rowmask[oy], cm = s_colmask[ox];
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          if (tap < ntap) {
-            const int kh = tap / a.ksize, kw = tap - kh * a.ksize;
-            int iy, ix;
-            if (wg_map_axis(oy, kh, a.sn, a.kn, a.off, a.sd, a.hin, iy) &&
-                wg_map_axis(ox, kw, a.sn, a.kn, a.off, a.sd, a.win, ix))
-              acc[tap] += v;
-          }
-        }
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+            if (((rm >> kh) & 1) && ((cm >> kw) & 1)) acc[kh * 3 + kw] += v;
+      }
+      ox += lanes;
+      while (ox >= a.wout) {
+        ox -= a.wout;
+        if (++oy == a.hout) oy = 0;
       }
     }
 #pragma unroll
-    for (int i = 0; i < 10; ++i) red[pl][i][c] = acc[i];
+    for (int i = 0; i < 10; ++i) red[i][threadIdx.x] = acc[i];
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 10 * 64; idx += blockDim.x) {
-      const int i = idx >> 6, cc = idx & 63;
-      if (cc >= cw) continue;
-      const float v = red[0][i][cc] + red[1][i][cc] + red[2][i][cc] + red[3][i][cc];
+    for (int idx = threadIdx.x; idx < 10 * cp; idx += blockDim.x) {
+      const int i = idx / cp, cc = idx - i * cp;
       const int co = c0 + cc;
+      if (co >= a.cout) continue;
+      float v = 0.f;
+      for (int l = 0; l < lanes; ++l) v += red[i][l * cp + cc];
       if (i == 9) {
         if (!a.swapped) part[(long long)a.Ktot * a.cols + co] = v;
         else if (a.bias_partial) a.bias_partial[((long long)s * a.splits + split) * a.cout + co] = v;
-      } else if (i < ntap && a.has_time) {
-        if (!a.swapped) part[(long long)(i * a.Kc + a.Kc - 1) * a.cols + co] = a.t * v;
-        else part[(long long)(i * a.cout + co) * a.cols + a.cin] = a.t * v;
+      } else if (a.has_time) {
+        // accumulators are indexed kh*3+kw; for ksize 1 only (0,0) exists
+        const int kh = i / 3, kw = i - kh * 3;
+        if (kh < a.ksize && kw < a.ksize) {
+          const int tap = kh * a.ksize + kw;
+          if (!a.swapped) part[(long long)(tap * a.Kc + a.Kc - 1) * a.cols + co] = a.t * v;
+          else part[(long long)(tap * a.cout + co) * a.cols + a.cin] = a.t * v;
+        }
       }
     }
     __syncthreads();
   }
+  (void)ntap;
 }
 
 struct WgTcPlan {
@@ -403,6 +468,8 @@ int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, cons
     a.sn = L->sd; a.kn = -L->kn; a.off = -L->off; a.sd = L->sn;
     a.row_stride_tap = L->cout;
   }
+  static const int wg_dbg = getenv("BSDE_WG_DBG") ? atoi(getenv("BSDE_WG_DBG")) : 0;
+  a.dbg = wg_dbg;
   const bool va = p.CA % 4 == 0, vb = p.CB % 4 == 0;
 #define WG_LAUNCH(VA_, VB_)                                                                                            \
   do {                                                                                                                 \
@@ -425,7 +492,8 @@ int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, cons
   ta.sn = L->sn; ta.kn = L->kn; ta.off = L->off; ta.sd = L->sd;
   ta.rows = p.rows; ta.cols = p.cols; ta.swapped = p.swapped; ta.has_time = L->has_time; ta.Kc = Kc; ta.Ktot = Ktot;
   ta.cin = L->cin; ta.t = t;
-  tap_colsum_kernel<<<dim3(p.splits, S), 256, 0, st>>>(ta);
+  if (!(wg_dbg & 1))
+  tap_colsum_kernel<<<dim3(p.splits, S), 1024, 0, st>>>(ta);
   BSDE_CUDA_OK(cudaGetLastError());
   count_launch();
 

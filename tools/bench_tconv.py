@@ -66,5 +66,25 @@ for g in [int(v) for v in a.groups.split(",")]:
             if kind == "dgrad" and cs.sd == 1 and cs.sn == 2:
                 pix = cs.hout * cs.wout
             fl = 2.0 * a.S * a.B * pix * lay.ksize ** 2 * (lay.cin + lay.has_time) * lay.cout
+            if kind == "fwd":
+                dy = torch.randn(a.S, a.B, cs.hout, cs.wout, cs.cout, device=dev)
+                gw = torch.zeros(a.S, fx.P, device=dev)
+                nbw = L.bsde_tconv_wgrad_workspace_bytes(C.byref(cs), a.S, a.B)
+                wsw = torch.empty(nbw, dtype=torch.uint8, device=dev)
+
+                def runw():
+                    st = L.bsde_tconv_wgrad(C.byref(cs), a.S, a.B, _lib.ptr(x), _lib.ptr(dy), 0.3, 1.0, _lib.ptr(gw), fx.P, math,
+                                            C.c_void_p(wsw.data_ptr()), nbw, _lib.stream_ptr())
+                    _lib.check(st, "wgrad")
+                for _ in range(2):
+                    runw()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(a.reps):
+                    runw()
+                e1.record()
+                torch.cuda.synchronize()
+                usw = e0.elapsed_time(e1) * 1e3 / a.reps
+                print(f"g{g} L{li} wgrad                                        : {usw:9.1f} us  {fl / usw / 1e6:8.2f} TFLOP/s", flush=True)
             print(f"g{g} L{li} {kind:5s} cin {lay.cin:3d} cout {lay.cout:3d} {lay.hin:2d}->{lay.hout:2d} sd{lay.sd} sn{lay.sn}: "
                   f"{us:9.1f} us  {fl / us / 1e6:8.2f} TFLOP/s", flush=True)
