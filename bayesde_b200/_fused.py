@@ -60,7 +60,8 @@ class BlockConfig:
     """Static description of one SDEBNN block's fused solve."""
 
     def __init__(self, fx_spec, fw_spec, S, B, nsteps, diff_coef, stl, time_grid, math="fp32", kl_weight=1.0,
-                 ou_coef=0.0, ts=None):
+                 ou_coef=0.0, ts=None, remat=False):
+        self.remat = remat
         self.fx, self.fw = fx_spec, fw_spec
         self.S, self.B, self.nsteps = S, B, nsteps
         self.nit = nsteps - 1
@@ -144,21 +145,24 @@ def wsde_backward(cfg, layers, wtraj, z1, gw_traj, gkl, gwT, w0_per_sample):
     return gw0, glayers
 
 
-def xpath_forward(cfg, x, wtraj):
-    """K2 forward scan.  x: [S,B,H,W,C].  Returns xs [nit+1, S,B,H,W,C] (slot 0 = x)."""
+def xpath_forward(cfg, x, wtraj, keep_acts):
+    """K2 forward scan.  x: [S,B,H,W,C].  Returns (xs [nit+1, S,B,H,W,C] (slot 0 = x), acts or None)."""
     L = _lib.lib()
     d = cfg.xdesc()
     xs = torch.empty((cfg.nit + 1,) + tuple(x.shape), device=x.device, dtype=torch.float32)
     xs[0].copy_(x)
+    acts = None
+    if keep_acts:
+        acts = torch.empty(L.bsde_xpath_acts_bytes(C.byref(d)) // 4, device=x.device, dtype=torch.float32)
     nbytes = L.bsde_xpath_workspace_bytes(C.byref(d), 0)
     ws = _lib.workspace(nbytes, x.device, "xpath")
     st = L.bsde_xpath_fwd(C.byref(d), _lib.host_floats(cfg.tk), _lib.host_floats(cfg.dtk), _lib.ptr(wtraj),
-                          _lib.ptr(xs), C.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr())
+                          _lib.ptr(xs), _lib.ptr(acts), C.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr())
     _lib.check(st, "bsde_xpath_fwd")
-    return xs
+    return xs, acts
 
 
-def xpath_backward(cfg, xs, wtraj, gx):
+def xpath_backward(cfg, xs, wtraj, gx, acts=None):
     """K3: reverse pass over the x rows.  Returns (gx0, gw_traj [S,nit,P])."""
     L = _lib.lib()
     d = cfg.xdesc()
@@ -167,7 +171,7 @@ def xpath_backward(cfg, xs, wtraj, gx):
     nbytes = L.bsde_xpath_workspace_bytes(C.byref(d), 1)
     ws = _lib.workspace(nbytes, xs.device, "xpath")
     st = L.bsde_xpath_bwd(C.byref(d), _lib.host_floats(cfg.tk), _lib.host_floats(cfg.dtk), _lib.ptr(wtraj),
-                          _lib.ptr(xs), _lib.ptr(gx), _lib.ptr(gw_traj), C.c_void_p(ws.data_ptr()), ws.numel(),
+                          _lib.ptr(xs), _lib.ptr(acts), _lib.ptr(gx), _lib.ptr(gw_traj), C.c_void_p(ws.data_ptr()), ws.numel(),
                           _lib.stream_ptr())
     _lib.check(st, "bsde_xpath_bwd")
     return gx, gw_traj
@@ -208,10 +212,11 @@ class SDEBNNSolve(torch.autograd.Function):
         with _Timed("k1_fwd"):
             wtraj, z1, kl = wsde_forward(cfg, w0c, layers, dW, seed, stream_id, w_stale)
         with _Timed("k2_fwd"):
-            xs = xpath_forward(cfg, x, wtraj)
+            xs, acts = xpath_forward(cfg, x, wtraj, keep_acts=(not cfg.remat) and any(ctx.needs_input_grad))
         ctx.cfg = cfg
         ctx.layers = layers
         ctx.w0_per_sample = w0.dim() == 2
+        ctx.acts = acts
         ctx.save_for_backward(wtraj, z1, xs)
         ctx.mark_non_differentiable(wtraj)
         return xs[cfg.nit].clone(), kl, wtraj
@@ -226,7 +231,8 @@ class SDEBNNSolve(torch.autograd.Function):
         if gkl is None:
             gkl = torch.zeros(cfg.S, device=dev)
         with _Timed("k3_bwd"):
-            gx0, gw_traj = xpath_backward(cfg, xs, wtraj, gx.to(torch.float32))
+            gx0, gw_traj = xpath_backward(cfg, xs, wtraj, gx.to(torch.float32), ctx.acts)
+            ctx.acts = None
         with _Timed("k1_bwd"):
             gw0, glayers = wsde_backward(cfg, ctx.layers, wtraj, z1, gw_traj, gkl.contiguous().float(), None,
                                          ctx.w0_per_sample)

@@ -57,7 +57,7 @@ _lib = None
 
 _EXPORTS = ["bsde_version", "bsde_last_error", "bsde_launch_count", "bsde_wsde_workspace_bytes", "bsde_wsde_fwd", "bsde_wsde_bwd",
             "bsde_tconv_fwd", "bsde_tconv_fwd_workspace_bytes", "bsde_tconv_wgrad_workspace_bytes", "bsde_tconv_wgrad",
-            "bsde_xpath_workspace_bytes", "bsde_xpath_fwd", "bsde_xpath_bwd", "bsde_step_update",
+            "bsde_xpath_workspace_bytes", "bsde_xpath_acts_bytes", "bsde_xpath_fwd", "bsde_xpath_bwd", "bsde_step_update",
             "bsde_philox_increments"]
 
 
@@ -91,8 +91,10 @@ def lib():
                                    C.c_int64, C.c_int32, vp, C.c_size_t, vp]
     L.bsde_xpath_workspace_bytes.restype = C.c_size_t
     L.bsde_xpath_workspace_bytes.argtypes = [C.POINTER(XpathDesc), C.c_int32]
-    L.bsde_xpath_fwd.argtypes = [C.POINTER(XpathDesc), _fp, _fp, vp, vp, vp, C.c_size_t, vp]
-    L.bsde_xpath_bwd.argtypes = [C.POINTER(XpathDesc), _fp, _fp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.bsde_xpath_fwd.argtypes = [C.POINTER(XpathDesc), _fp, _fp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.bsde_xpath_bwd.argtypes = [C.POINTER(XpathDesc), _fp, _fp, vp, vp, vp, vp, vp, vp, C.c_size_t, vp]
+    L.bsde_xpath_acts_bytes.restype = C.c_size_t
+    L.bsde_xpath_acts_bytes.argtypes = [C.POINTER(XpathDesc)]
     L.bsde_step_update.argtypes = [C.c_int32, C.c_int64, C.c_float, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bsde_philox_increments.argtypes = [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_int64, vp, vp, vp]
     for name in _EXPORTS:

@@ -26,7 +26,8 @@ class _AugDynamics:
     methods to `sdeint_ito_fixed_grid` selects the fused kernels."""
     _bsde_structured = True
 
-    def __init__(self, fx_spec, fw_spec, x_shape, diff_coef, stl, w_drift, math_mode, w_stale, stream_id):
+    def __init__(self, fx_spec, fw_spec, x_shape, diff_coef, stl, w_drift, math_mode, w_stale, stream_id, remat=False):
+        self.remat = remat
         self.fx, self.fw = fx_spec, fw_spec
         self.x_shape = tuple(x_shape)  # (S,B,H,W,C)
         self.diff_coef, self.stl, self.w_drift, self.math = diff_coef, stl, w_drift, math_mode
@@ -59,7 +60,7 @@ class _AugDynamics:
         nsteps = len(ts)
         ts_np = ts.detach().cpu().numpy() if isinstance(ts, torch.Tensor) else np.asarray(ts, dtype=np.float32)
         cfg = _fused.BlockConfig(self.fx, self.fw, S, B, nsteps, self.diff_coef, bool(rep), time_grid, self.math,
-                                 ts=ts_np)
+                                 ts=ts_np, remat=self.remat)
         if self.w_drift:
             layers = fw_layers(args)
         else:
@@ -80,8 +81,9 @@ def SDEBNN(fx_block_type, fx_dim, fx_actfn, fw, diff_coef=1e-4, name="sdebnn", s
            method="euler_maruyama", time_grid="reference", math="fp32", stream_id=0):
     """brax/_impl/brax.py:15-135.  Returns Layer(init_fun, apply_fun).
 
-    `remat` is accepted for compatibility: the reverse pass always recomputes the conv
-    intermediates of a scan iteration from the stored x_k (the jax.checkpoint analogue, brax.py:131)."""
+    `remat=True`: the reverse pass recomputes the conv intermediates of every scan iteration from the
+    stored x_k (the jax.checkpoint analogue, brax.py:131-132); `remat=False` (default, as in the reference)
+    keeps them from the forward pass (more memory, ~15 % less arithmetic)."""
     if not xt:
         raise NotImplementedError("SDEBNN(xt=False): build_fx layers are time-dependent (arch.py:176-205); "
                                   "the reference script always passes xt=True")
@@ -121,7 +123,8 @@ def SDEBNN(fx_block_type, fx_dim, fx_actfn, fw, diff_coef=1e-4, name="sdebnn", s
         S = x.shape[0]
         fx, w_stale = make_layer(x.shape[1:])
         P = fx.P
-        dyn = _AugDynamics(fx, fw.spec, x.shape, diff_coef, stl, w_drift, math, w_stale.to(x.device), stream_id)
+        dyn = _AugDynamics(fx, fw.spec, x.shape, diff_coef, stl, w_drift, math, w_stale.to(x.device), stream_id,
+                           remat=remat)
         kl = x.new_zeros(S)
         if infer_initial_state:  # brax.py:100-106
             if isinstance(rng, (tuple, list)) and len(rng) == 2 and isinstance(rng[1], torch.Tensor):

@@ -31,7 +31,7 @@ class SDEBNNClassifier(nn.Module):
     def __init__(self, input_size=(32, 32, 3), aug=2, nblocks=(2, 2, 2), fx_dim=64, fw_dims=(2, 64, 2),
                  fx_actfn="softplus", fw_actfn="softplus", diff_coef=1e-4, stl=False, nsteps=20, block_type=0,
                  num_classes=10, nsamples=1, ou_dw=True, w_init=-1.0, b_init=-1.0, time_grid="reference",
-                 math="fp32", method="euler_maruyama", seed=0, device="cuda"):
+                 math="fp32", method="euler_maruyama", remat=False, seed=0, device="cuda"):
         super().__init__()
         self.nsamples, self.input_size = nsamples, tuple(input_size)
         mf = brax.MeanField
@@ -41,7 +41,7 @@ class SDEBNNClassifier(nn.Module):
             fw = arch.MLP(fw_dims, actfn=fw_actfn, xt=True, ou_dw=ou_dw, nonzero_w=w_init, nonzero_b=b_init)
             for _ in range(nb):
                 layers.append(brax.SDEBNN(block_type, fx_dim, fx_actfn, fw, diff_coef=diff_coef, stl=stl, xt=True,
-                                          nsteps=nsteps, method=method, time_grid=time_grid, math=math,
+                                          nsteps=nsteps, remat=remat, method=method, time_grid=time_grid, math=math,
                                           stream_id=nb_i))
                 kinds.append("sde")
                 nb_i += 1

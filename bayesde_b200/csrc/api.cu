@@ -170,6 +170,17 @@ extern "C" size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t b
   return tot;
 }
 
+static size_t xpath_acts_floats(const bsde_xpath_desc* d) {  // stored layer outputs of one scan iteration
+  size_t tot = 0;
+  for (int l = 0; l + 1 < d->nlayers; ++l) tot += align_up(act_elems(d, l) * sizeof(float)) / sizeof(float);
+  return tot;
+}
+
+extern "C" size_t bsde_xpath_acts_bytes(const bsde_xpath_desc* d) {
+  if (!d || d->nlayers < 2 || d->nlayers > BSDE_MAX_LAYERS) return 0;
+  return xpath_acts_floats(d) * sizeof(float) * (size_t)d->nit;
+}
+
 static int xpath_recompute(const bsde_xpath_desc* d, const float* x, const float* wk, float t, float* const* a,
                            void* tc_ws, size_t tc_bytes, cudaStream_t st) {
   const int n = d->nlayers;
@@ -185,8 +196,8 @@ static int xpath_recompute(const bsde_xpath_desc* d, const float* x, const float
 }
 
 extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const float* h_dtk,
-                              const float* d_wtraj, float* d_xs, void* workspace, size_t workspace_bytes,
-                              void* stream) {
+                              const float* d_wtraj, float* d_xs, float* d_acts, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   if (int e = xpath_check(d)) return e;
   BSDE_CHECK_ARG(h_tk && h_dtk && d_wtraj && d_xs, "NULL pointer");
   const size_t need = bsde_xpath_workspace_bytes(d, 0);
@@ -203,7 +214,12 @@ extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const
   ws += tc_bytes;
   for (int l = 0; l + 1 < n; ++l) { a[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
   const long long wss = (long long)(d->nit + 1) * d->P;
+  const size_t acts_step = xpath_acts_floats(d);
   for (int k = 0; k < d->nit; ++k) {
+    if (d_acts) {  // keep this iteration's layer outputs for the reverse pass (remat = False)
+      float* p = d_acts + (size_t)k * acts_step;
+      for (int l = 0; l + 1 < n; ++l) { a[l] = p; p += align_up(act_elems(d, l) * sizeof(float)) / sizeof(float); }
+    }
     const float* xk = d_xs + (size_t)k * d->x_numel;
     float* xn = d_xs + (size_t)(k + 1) * d->x_numel;
     const float* wk = d_wtraj + (size_t)k * d->P;
@@ -217,8 +233,8 @@ extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const
 }
 
 extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const float* h_dtk,
-                              const float* d_wtraj, const float* d_xs, float* d_gx, float* d_gw_traj,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+                              const float* d_wtraj, const float* d_xs, const float* d_acts, float* d_gx,
+                              float* d_gw_traj, void* workspace, size_t workspace_bytes, void* stream) {
   if (int e = xpath_check(d)) return e;
   BSDE_CHECK_ARG(h_tk && h_dtk && d_wtraj && d_xs && d_gx && d_gw_traj, "NULL pointer");
   const size_t need = bsde_xpath_workspace_bytes(d, 1);
@@ -249,7 +265,12 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
     const float* xk = d_xs + (size_t)k * d->x_numel;
     const float* wk = d_wtraj + (size_t)k * d->P;
     float* gwk = d_gw_traj + (size_t)k * d->P;
-    if (int e = xpath_recompute(d, xk, wk, t, a, tc_ws, tc_bytes, st)) return e;
+    if (d_acts) {
+      float* p = const_cast<float*>(d_acts) + (size_t)k * xpath_acts_floats(d);
+      for (int l = 0; l + 1 < n; ++l) { a[l] = p; p += align_up(act_elems(d, l) * sizeof(float)) / sizeof(float); }
+    } else if (int e = xpath_recompute(d, xk, wk, t, a, tc_ws, tc_bytes, st)) {
+      return e;
+    }
     // walk the stack backwards; `dy` is dL/d(conv output of layer l)
     const float* dy = d_gx;  // for the last layer dL/d(conv out) = dt * gx  (scale folded below)
     for (int l = n - 1; l >= 0; --l) {

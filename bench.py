@@ -36,7 +36,8 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=128, help="images per GPU per step")
     p.add_argument("--nsamples", type=int, default=8)
-    p.add_argument("--math", default=os.environ.get("BSDE_MATH", "fp32"), choices=["fp32", "tc"])
+    p.add_argument("--math", default=os.environ.get("BSDE_MATH", "tc"), choices=["fp32", "tc"])
+    p.add_argument("--remat", action="store_true", help="recompute conv intermediates in the reverse pass")
     p.add_argument("--time_grid", default="reference", choices=["reference", "uniform"])
     p.add_argument("--diff_coef", type=float, default=0.2)
     p.add_argument("--cpu_batch", type=int, default=8, help="images in the bounded CPU sample")
@@ -180,7 +181,7 @@ def workload_config(args):
     return {"workload": "config4: SDEBNN 32x32x3 CIFAR-10-shape synthetic, aug 2, nblocks 2-2-2, fx_dim 64, "
                         "fw_dims 2-64-2, softplus, nsteps 20 (19 drift evaluations/block), euler_maruyama",
             "batch_per_gpu": args.batch, "nsamples": args.nsamples, "diff_coef": args.diff_coef,
-            "time_grid": args.time_grid, "conv_math": args.math, "parallelism": f"dp{args.gpus} (batch sharded)",
+            "time_grid": args.time_grid, "conv_math": args.math, "remat": bool(getattr(args, "remat", False)), "parallelism": f"dp{args.gpus} (batch sharded)",
             "l2_policy": "per-step working set (checkpoints+activations, >2 GB) exceeds the 126 MB L2; no flush"}
 
 
@@ -203,7 +204,7 @@ def run_ours(args):
     L = _lib.lib()
 
     model = SDEBNNClassifier(nsamples=args.nsamples, diff_coef=args.diff_coef, time_grid=args.time_grid,
-                             math=args.math, w_init=1e-2, b_init=1e-2, seed=0, device=dev, **MODEL_KW)
+                             math=args.math, remat=args.remat, w_init=1e-2, b_init=1e-2, seed=0, device=dev, **MODEL_KW)
     trainer = Trainer(model, lr=1e-3, kl_coef=1e-3, train_size=45000)
     B = args.batch
     g = torch.Generator().manual_seed(1234 + rank)
@@ -294,7 +295,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.math == "fp32" else "bf16x-tc/f32-accum", "data": "synthetic",
+        "dtype": "f32" if args.math == "fp32" else "tf32 (tcgen05 kind::tf32 operands, f32 accumulate)", "data": "synthetic",
         "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (32 * 32 * 3 * 4 + 8),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},

@@ -187,17 +187,22 @@ typedef struct {
 
 size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t backward);
 
+/* bytes of the optional per-iteration activation store (all nit iterations) */
+size_t bsde_xpath_acts_bytes(const bsde_xpath_desc* d);
+
 /* h_tk,h_dtk: HOST arrays [nit].  d_wtraj: [S][nit+1][P].  d_xs: [nit+1][x_numel]; slot 0 holds
- * x_0 on entry, slot k+1 is written with x_{k+1} = x_k + dt_k f_x(x_k, t_k; w_k). */
+ * x_0 on entry, slot k+1 is written with x_{k+1} = x_k + dt_k f_x(x_k, t_k; w_k).
+ * d_acts: NULL (the reverse pass recomputes the conv intermediates from x_k: the jax.checkpoint /
+ * --remat analogue, brax.py:131-132) or bsde_xpath_acts_bytes() bytes that receive them. */
 int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const float* h_dtk,
-                   const float* d_wtraj, float* d_xs, void* workspace, size_t workspace_bytes,
-                   void* stream);
+                   const float* d_wtraj, float* d_xs, float* d_acts, void* workspace,
+                   size_t workspace_bytes, void* stream);
 
 /* d_gx: [x_numel] holds dL/dx_nit on entry and dL/dx_0 on return.  d_gw_traj: [S][nit][P] receives
  * dL/dw_k through the convolutions (every element of every slot is written). */
 int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const float* h_dtk,
-                   const float* d_wtraj, const float* d_xs, float* d_gx, float* d_gw_traj,
-                   void* workspace, size_t workspace_bytes, void* stream);
+                   const float* d_wtraj, const float* d_xs, const float* d_acts, float* d_gx,
+                   float* d_gw_traj, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * generic flat-state step and Brownian increments

@@ -427,3 +427,163 @@ def test_sdebnn_block_tc(built_lib, kw):
     grads = torch.autograd.grad(obj, leaves)
     for i, (a, b) in enumerate(zip(grads, grads_r)):
         _tc_close(a, b, 2e-2, f"tc grad {i}")
+
+
+@pytest.mark.parametrize("math", ["fp32", "tc"])
+def test_remat_modes_agree(built_lib, math):
+    """remat=True (recompute conv intermediates from x_k, the jax.checkpoint analogue of brax.py:131-132)
+    and remat=False (keep them) run the same kernels on the same data: identical outputs and gradients."""
+    from bayesde_b200 import arch, brax
+    blk, w0, fw, x, dW = _block_case(S=2, B=3, H=8, C_in=5, fx_dim=16, nsteps=5)
+    res = []
+    for remat in (False, True):
+        layer = brax.SDEBNN(0, 16, "softplus", arch.MLP((2, 16, 2), xt=True, ou_dw=True), diff_coef=0.2, xt=True,
+                            nsteps=5, remat=remat, math=math)
+        w0d = w0.float().to(DEV).requires_grad_(True)
+        xd = x.float().to(DEV).requires_grad_(True)
+        xo, kl = layer.apply((w0d, (), _product_fw_params(fw, DEV)), xd, dW.float().to(DEV))
+        g = torch.autograd.grad(xo.square().sum() + 1e-3 * kl.sum(), [xd, w0d])
+        res.append((xo.detach(), kl.detach(), g[0], g[1]))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases and full-size, size-independent properties
+# ------------------------------------------------------------------------------------------------
+def test_edge_cases_vs_oracle(built_lib):
+    """S > 8 (K1 runs in sample chunks), nsteps = 2 (one scan iteration), B = 1, diff_coef = 0 (u := 0,
+    brax.py:59-60), w_drift = False (dw := 0, brax.py:56-57)."""
+    from bayesde_b200 import arch, brax
+    # S = 11 > 8, B = 1
+    blk, w0, fw, x, dW = _block_case(S=11, B=1, H=4, C_in=3, fx_dim=4, nsteps=4, fw_dims=(2, 4, 2))
+    xo_r, kl_r, wt_r, cot, grads_r = _oracle_block(blk, w0, fw, x, dW)
+    layer = brax.SDEBNN(0, 4, "softplus", arch.MLP((2, 4, 2), xt=True, ou_dw=True), diff_coef=0.2, xt=True, nsteps=4)
+    w0d = w0.float().to(DEV).requires_grad_(True)
+    fwd = _product_fw_params(fw, DEV)
+    xd = x.float().to(DEV).requires_grad_(True)
+    xo, kl = layer.apply((w0d, (), fwd), xd, dW.float().to(DEV))
+    _close(xo, xo_r, 1e-4, 1e-5, "S=11 x_T")
+    _close(kl, kl_r, 1e-4, 1e-6, "S=11 KL")
+    grads = torch.autograd.grad((xo * cot.float().to(DEV)).sum() + 1e-3 * kl.sum(),
+                                [xd, w0d] + [t for lay in arch.fw_layers(fwd) for t in lay])
+    for i, (a, b) in enumerate(zip(grads, grads_r)):
+        _gclose(a, b, 1e-3, f"S=11 grad {i}")
+    # nsteps = 2, diff_coef = 0
+    for kw, okw in ((dict(nsteps=2), {}), (dict(sigma=0.0), {}), (dict(), dict(w_drift=False))):
+        blk, w0, fw, x, dW = _block_case(S=2, B=2, H=4, C_in=3, fx_dim=4, fw_dims=(2, 4, 2), **({"nsteps": 4} | kw))
+        blk.w_drift = okw.get("w_drift", True)
+        outs = [blk.apply((w0, fw), x[s_], dW[s_]) for s_ in range(x.shape[0])]
+        xo_r, kl_r, wt_r = (torch.stack([o[i] for o in outs]) for i in range(3))
+        layer = brax.SDEBNN(0, 4, "softplus", arch.MLP((2, 4, 2), xt=True, ou_dw=True), diff_coef=blk.diff_coef,
+                            xt=True, nsteps=blk.nsteps, **okw)
+        params = (w0.float().to(DEV), (), _product_fw_params(fw, DEV) if blk.w_drift else ())
+        xo, kl, info = layer.apply(params, x.float().to(DEV), dW.float().to(DEV), full_output=True)
+        _close(xo, xo_r, 1e-4, 1e-5, f"{kw}{okw} x_T")
+        _close(info["sdebnn_w"], wt_r, 1e-5, 1e-6, f"{kw}{okw} w path")
+        _close(kl, kl_r, 1e-4, 1e-6, f"{kw}{okw} KL")
+
+
+def test_infer_initial_state_vs_oracle(built_lib):
+    """brax.py:84-87,100-106: Gaussian w0 with KL_0 against the N(0, prior_std) prior."""
+    from bayesde_b200 import arch, brax
+    blk, w0, fw, x, dW = _block_case(S=3, B=2, H=4, C_in=3, fx_dim=4, nsteps=4, fw_dims=(2, 4, 2))
+    g = torch.Generator().manual_seed(9)
+    eps = torch.randn(3, blk.P, generator=g, dtype=torch.float64)
+    mean = w0.clone().requires_grad_(True)
+    logstd = torch.full_like(w0, -4.0).requires_grad_(True)
+    xs, kls = [], []
+    for s in range(3):
+        w0s = eps[s] * torch.exp(logstd) + mean
+        kl0 = (jp.normal_logprob(w0s, mean, logstd) - jp.normal_logprob(
+            w0s, torch.zeros((), dtype=torch.float64), torch.tensor(math.log(0.1), dtype=torch.float64))).sum()
+        xo, kl, _ = blk.apply((w0s, fw), x[s], dW[s])
+        xs.append(xo), kls.append(kl + kl0)
+    xo_r, kl_r = torch.stack(xs), torch.stack(kls)
+    g_r = torch.autograd.grad(xo_r.sum() + 1e-3 * kl_r.sum(), [mean, logstd])
+    layer = brax.SDEBNN(0, 4, "softplus", arch.MLP((2, 4, 2), xt=True, ou_dw=True), diff_coef=0.2, xt=True, nsteps=4,
+                        infer_initial_state=True, initial_state_prior_std=0.1)
+    md = w0.float().to(DEV).requires_grad_(True)
+    ld = torch.full_like(md, -4.0).requires_grad_(True)
+    xo, kl = layer.apply((md, ld, _product_fw_params(fw, DEV)), x.float().to(DEV), (dW.float().to(DEV), eps.float().to(DEV)))
+    _close(xo, xo_r, 1e-4, 1e-5, "x_T")
+    _close(kl, kl_r, 1e-4, 1e-4, "KL incl. KL_0")
+    g_d = torch.autograd.grad(xo.sum() + 1e-3 * kl.sum(), [md, ld])
+    _gclose(g_d[0], g_r[0], 1e-3, "grad mean_w0")
+    _gclose(g_d[1], g_r[1], 1e-3, "grad logstd_w0")
+
+
+@pytest.mark.parametrize("math", ["fp32", "tc"])
+def test_full_size_properties(built_lib, math):
+    """Config-4 block at full size (32x32x5, fx_dim 64, P = 81 458, nsteps 20, S = 8, B = 128 for tc / 16 for
+    fp32) through properties that do not need the oracle at that size:
+      * determinism: same seed -> bit-identical outputs and gradients;
+      * sample independence (the reference's vmap over rngs): sample s of the S = 8 solve equals an S = 1
+        solve with that sample's increments;
+      * batch independence: images [0:B/2] of the B solve equal a B/2 solve on those images (same w path);
+      * the w path and the KL do not depend on x (brax.py:55-61);
+      * dt_k = 0 iterations of the reference time grid (quirk Q1) leave x and w unchanged."""
+    from bayesde_b200 import arch, brax
+    from bayesde_b200._fused import reference_time_grid
+    from bayesde_b200.sdeint import philox_increments
+    S, B, nsteps = 8, (128 if math == "tc" else 16), 20
+    fwl = arch.MLP((2, 64, 2), xt=True, ou_dw=True, nonzero_w=1e-2, nonzero_b=1e-2)
+    layer = brax.SDEBNN(0, 64, "softplus", fwl, diff_coef=0.2, xt=True, nsteps=nsteps, math=math, stream_id=3)
+    _, (w0, _, fwp) = layer.init(5, (B, 32, 32, 5))
+    assert w0.numel() == 81458
+    w0 = w0.to(DEV).requires_grad_(True)
+    fwp = brax._to_device(fwp, DEV)
+    x = torch.randn(S, B, 32, 32, 5, device=DEV, generator=torch.Generator(DEV).manual_seed(1))
+
+    def run(xx, rng, ww=w0):
+        xo, kl, info = layer.apply((ww, (), fwp), xx, rng, full_output=True)
+        (gw,) = torch.autograd.grad(xo.square().mean() + 1e-6 * kl.sum(), ww)
+        return xo.detach(), kl.detach(), info["sdebnn_w"].detach(), gw
+
+    a = run(x, 77)
+    b = run(x, 77)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v), "not deterministic"
+    assert torch.isfinite(a[0]).all() and torch.isfinite(a[3]).all()
+    _, dtk = reference_time_grid(torch.linspace(0.0, 1.0, nsteps).numpy())  # brax.py:31 evaluates linspace in fp32
+    dW = philox_increments(77, 3, S, dtk, 81458, DEV)
+    c = run(x, dW)
+    assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    s = 5
+    d = run(x[s:s + 1], dW[s:s + 1])
+    tol = dict(rtol=0, atol=0) if math == "fp32" else dict(rtol=0, atol=0)
+    assert torch.allclose(d[0][0], a[0][s], **tol) and torch.allclose(d[1][0], a[1][s], **tol)
+    assert torch.equal(d[2][0], a[2][s])
+    e = run(x[:, :B // 2].contiguous(), dW)
+    assert torch.allclose(e[0], a[0][:, :B // 2], **tol)
+    assert torch.equal(e[1], a[1]) and torch.equal(e[2], a[2])
+    f = run(torch.zeros_like(x), dW)
+    assert torch.equal(f[1], a[1]) and torch.equal(f[2], a[2])
+    wt = a[2]
+    for k in range(nsteps - 1):
+        if dtk[k] == 0:
+            assert torch.equal(wt[:, k + 1], wt[:, k])
+
+
+@pytest.mark.parametrize("name", ["jax_block_a", "jax_block_b"])
+def test_cuda_path_matches_committed_golden(built_lib, name):
+    """The CUDA path against the committed fixtures (tests/golden/*.npz, generated by make_golden.py)."""
+    import os
+    from bayesde_b200 import arch, brax
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    S, B, H, C_in, fx_dim, nsteps, nfw = [int(v) for v in z["meta"][:7]]
+    fw_dims = tuple(int(v) for v in z["meta"][7:7 + nfw])
+    fw = [tuple(torch.from_numpy(z[f"fw{i}_{n}"]) for n in ("W", "b", "wt", "wtb", "bt")) for i in range(nfw + 1)]
+    layer = brax.SDEBNN(0, fx_dim, "softplus", arch.MLP(fw_dims, xt=True, ou_dw=True), diff_coef=float(z["sigma"]),
+                        xt=True, nsteps=nsteps, time_grid=str(z["time_grid"]))
+    w0d = torch.from_numpy(z["w0"]).float().to(DEV).requires_grad_(True)
+    fwd = _product_fw_params(fw, DEV)
+    xd = torch.from_numpy(z["x"]).float().to(DEV).requires_grad_(True)
+    xo, kl, info = layer.apply((w0d, (), fwd), xd, torch.from_numpy(z["dW"]).float().to(DEV), full_output=True)
+    _close(xo, torch.from_numpy(z["xT"]), 1e-4, 1e-5, "x_T")
+    _close(kl, torch.from_numpy(z["kl"]), 1e-4, 1e-6, "KL")
+    _close(info["sdebnn_w"], torch.from_numpy(z["wtraj"]), 1e-5, 1e-6, "w trajectory")
+    leaves = [xd, w0d] + [t for lay in arch.fw_layers(fwd) for t in lay]
+    grads = torch.autograd.grad((xo * torch.from_numpy(z["cot"]).float().to(DEV)).sum() + 1e-3 * kl.sum(), leaves)
+    for i, g_ in enumerate(grads):
+        _gclose(g_, torch.from_numpy(z[f"grad{i}"]), 1e-3, f"grad {i}")
