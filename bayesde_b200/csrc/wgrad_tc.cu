@@ -21,6 +21,8 @@
 
 namespace bsde {
 
+__device__ long long* g_wg_dbg = nullptr;  // tools/: accumulated clock64 phases of CTA 0
+
 constexpr int WG_KP = 16;        // pixels per k-block
 constexpr int WG_PROD = 256;
 constexpr int WG_THREADS = WG_PROD + 32;
@@ -174,19 +176,24 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgTcArgs a) {
                     (((uint32_t)((byte_in_row >> 5) ^ (p & 3)) << 5) | (uint32_t)(byte_in_row & 31));
       }
     }
-    // per-tap displacement table
-    __shared__ int s_ty[9], s_tx[9], s_toff[9];
-    if (tid < ntap) {
-      const int kh = tid / a.ksize, kw = tid - kh * a.ksize;
-      s_ty[tid] = kh * a.kn + a.off;
-      s_tx[tid] = kw * a.kn + a.off;
-      s_toff[tid] = (s_ty[tid] * a.wA + s_tx[tid]) * a.CA;
+    // per-tap displacements, register resident (ksize is 1 or 3)
+    int r_ty[9], r_tx[9], r_toff[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int kh = a.ksize == 3 ? tap / 3 : 0, kw = a.ksize == 3 ? tap % 3 : 0;
+      r_ty[tap] = kh * a.kn + a.off;
+      r_tx[tap] = kw * a.kn + a.off;
+      r_toff[tap] = (r_ty[tap] * a.wA + r_tx[tap]) * a.CA;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(WG_PROD) : "memory");
+    long long t_wait = 0, t_issue = 0;
+    const bool dbgt = g_wg_dbg && blockIdx.x == 0 && tid == 0;
 #pragma unroll 1
     for (int kb = 0; kb < NKB; ++kb) {
       const int st = kb % a.stages;
+      long long c0 = dbgt ? clock64() : 0;
       if (kb >= a.stages) wg_mbar_wait(empty_bar(st), ((kb / a.stages) & 1) ^ 1);
+      long long c1 = dbgt ? clock64() : 0;
+      t_wait += c1 - c0;
       const uint32_t sA = base + st * stage_bytes;
       const uint32_t sB = sA + a_bytes;
       const int mb = mbeg + kb * WG_KP;
@@ -196,12 +203,15 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgTcArgs a) {
           const bool mval = (uA_img[u] < a.B) && (mb + (int)((uA_dst[u] >> 7) & (WG_KP - 1)) < mend);
           const int by = uA_oy[u] * a.sn, bx = uA_ox[u] * a.sn;
           const int boff = ((uA_img[u] * a.hA + by) * a.wA + bx) * a.CA + uA_ch[u];
-#pragma unroll 1
-          for (int tap = 0; tap < ((a.dbg & 4) ? 0 : ntap); ++tap) {
-            const bool ok = mval && (unsigned)(by + s_ty[tap]) < (unsigned)a.hA && (unsigned)(bx + s_tx[tap]) < (unsigned)a.wA;
-            const float* src = ok ? ga + (boff + s_toff[tap]) : ga;
-            const uint32_t dst = sA + uA_dst[u] + (uint32_t)(tap * a.bt) * WG_REGION;
-            if (VA) wg_cp16(dst, src, ok); else wg_cp4(dst, src, ok);
+          const uint32_t tap_stride = (uint32_t)a.bt * WG_REGION;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            if (tap < ntap) {
+              const bool ok = mval && (unsigned)(by + r_ty[tap]) < (unsigned)a.hA && (unsigned)(bx + r_tx[tap]) < (unsigned)a.wA;
+              const float* src = ok ? ga + (boff + r_toff[tap]) : ga;
+              const uint32_t dst = sA + uA_dst[u] + (uint32_t)tap * tap_stride;
+              if (VA) wg_cp16(dst, src, ok); else wg_cp4(dst, src, ok);
+            }
           }
           // advance this unit's pixel by KP for the next k-block
           uA_ox[u] += WG_KP;
@@ -221,7 +231,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgTcArgs a) {
         }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(st)) : "memory");
+      if (dbgt) t_issue += clock64() - c1;
     }
+    if (dbgt) { g_wg_dbg[0] = t_wait; g_wg_dbg[1] = t_issue; g_wg_dbg[2] = NKB; }
 
     // =============================== epilogue ===============================
     wg_mbar_wait(tmem_full_bar, 0);
@@ -259,10 +271,15 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgTcArgs a) {
       // TF32 x TF32 -> F32, both operands MN-major, M=128, N=npad
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(a.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      long long m_wait = 0, m_issue = 0;
+      const bool dbgm = g_wg_dbg && blockIdx.x == 0;
 #pragma unroll 1
       for (int kb = 0; kb < NKB; ++kb) {
         const int st = kb % a.stages;
+        long long c0 = dbgm ? clock64() : 0;
         wg_mbar_wait(full_bar(st), (kb / a.stages) & 1);
+        long long c1 = dbgm ? clock64() : 0;
+        m_wait += c1 - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sA = base + st * stage_bytes;
         const uint32_t sB = sA + a_bytes;
@@ -281,7 +298,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgTcArgs a) {
           }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty_bar(st)) : "memory");
+        if (dbgm) m_issue += clock64() - c1;
       }
+      if (dbgm) { g_wg_dbg[3] = m_wait; g_wg_dbg[4] = m_issue; }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tmem_full_bar) : "memory");
     }
     __syncwarp();
@@ -517,3 +536,7 @@ int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, cons
 }
 
 }  // namespace bsde
+
+extern "C" int bsde_debug_set_wg_stamps(long long* d_buf) {
+  return cudaMemcpyToSymbol(bsde::g_wg_dbg, &d_buf, sizeof(d_buf)) == cudaSuccess ? 0 : -3;
+}
