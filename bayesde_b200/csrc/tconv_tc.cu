@@ -152,7 +152,21 @@ struct __align__(8) TcTap {
 
 // ---- weight repack: flat w(t_k) -> swizzled K-major [kb][npad][32] tile images, plus (last block of
 // the grid) the class' epilogue table {bias, sum of time rows, time row per tap} and gather table ----
+struct RepackClass {
+  int cls_off, tb_off, tap_off, Kcls, nkh, nkw, nkb, py, px, blk0;
+  int khv[3], kwv[3];
+};
 struct RepackArgs {
+  const float* w;
+  float* img;
+  long long w_sample_stride, img_sample_stride;
+  int ncls, Kc, ksize, cout, npad, real_base, vec;
+  int sn, kn, off, sd, win, cin, has_time, time_row, use_bias;
+  long long w_off, b_off, ts, ks, ns;
+  RepackClass c[4];
+};
+// per-class view with the field names the body uses
+struct RepackView {
   const float* w;
   float* img;
   long long w_sample_stride, img_sample_stride;
@@ -162,8 +176,19 @@ struct RepackArgs {
   long long w_off, b_off, ts, ks, ns;
 };
 
-__global__ void tc_repack_kernel(RepackArgs a) {
-  const int kb = blockIdx.x, s = blockIdx.y;
+__global__ void tc_repack_kernel(RepackArgs A) {
+  // blockIdx.x enumerates (class, k-block) pairs; the last block of every class writes its tables
+  int ci = 0;
+  while (ci + 1 < A.ncls && (int)blockIdx.x >= A.c[ci + 1].blk0) ++ci;
+  RepackView a;
+  a.w = A.w; a.img = A.img; a.w_sample_stride = A.w_sample_stride; a.img_sample_stride = A.img_sample_stride;
+  a.cls_off = A.c[ci].cls_off; a.tb_off = A.c[ci].tb_off; a.tap_off = A.c[ci].tap_off; a.Kc = A.Kc; a.Kcls = A.c[ci].Kcls;
+  a.ksize = A.ksize; a.nkh = A.c[ci].nkh; a.nkw = A.c[ci].nkw; a.cout = A.cout; a.npad = A.npad; a.real_base = A.real_base;
+  a.nkb = A.c[ci].nkb; a.vec = A.vec; a.py = A.c[ci].py; a.px = A.c[ci].px; a.sn = A.sn; a.kn = A.kn; a.off = A.off; a.sd = A.sd;
+  a.win = A.win; a.cin = A.cin; a.has_time = A.has_time; a.time_row = A.time_row; a.use_bias = A.use_bias;
+  for (int i = 0; i < 3; ++i) { a.khv[i] = A.c[ci].khv[i]; a.kwv[i] = A.c[ci].kwv[i]; }
+  a.w_off = A.w_off; a.b_off = A.b_off; a.ts = A.ts; a.ks = A.ks; a.ns = A.ns;
+  const int kb = (int)blockIdx.x - A.c[ci].blk0, s = blockIdx.y;
   const float* __restrict__ w = a.w + (long long)s * a.w_sample_stride;
   if (kb == a.nkb) {
     const int ntap = a.nkh * a.nkw;
@@ -598,29 +623,33 @@ int tconv_fwd_tc(const bsde_conv_layer* L, int S, int B, const float* in, const 
   a.Kc = L->cin; a.Mper = B * L->hout * L->wout; a.npad = npad;
   a.tmem_cols = npad <= 32 ? 32 : (npad <= 64 ? 64 : 128);
   { const char* e = getenv("BSDE_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
-  // repack w(t_k) into tile images, one launch per parity class
-  int off = 0;
-  for (int c = 0; c < ncls; ++c) {
+  // repack w(t_k) into tile images + tables: one launch covering every parity class
+  {
     RepackArgs r;
     memset(&r, 0, sizeof(r));
-    int nkh, nkw;
-    tc_class_info(L, c, r.khv, r.kwv, nkh, nkw);
     r.w = w; r.img = (float*)ws; r.w_sample_stride = w_sample_stride; r.img_sample_stride = a.bimg_sample_stride;
-    r.cls_off = off; r.Kc = L->cin; r.Kcls = nkh * nkw * L->cin; r.ksize = L->ksize; r.nkh = nkh; r.nkw = nkw;
-    r.cout = L->cout; r.npad = npad; r.real_base = (L->has_time && L->time_first) ? 1 : 0;
+    r.ncls = ncls; r.Kc = L->cin; r.ksize = L->ksize; r.cout = L->cout; r.npad = npad;
+    r.real_base = (L->has_time && L->time_first) ? 1 : 0; r.vec = L->cin % 4 == 0;
+    r.sn = L->sn; r.kn = L->kn; r.off = L->off; r.sd = L->sd; r.win = L->win; r.cin = L->cin;
+    r.has_time = L->has_time; r.time_row = a.time_row; r.use_bias = epi <= BSDE_EPI_EULER;
     r.w_off = L->w_off; r.b_off = L->b_off; r.ts = L->w_tap_stride; r.ks = L->w_k_stride; r.ns = L->w_n_stride;
-    const int nkb = (r.Kcls + TC_KB - 1) / TC_KB;
-    const int vec = L->cin % 4 == 0;
-    r.nkb = nkb; r.vec = vec; r.py = c >> 1; r.px = c & 1; r.sn = L->sn; r.kn = L->kn; r.off = L->off; r.sd = L->sd;
-    r.win = L->win; r.cin = L->cin; r.has_time = L->has_time; r.time_row = a.time_row; r.use_bias = epi <= BSDE_EPI_EULER;
-    a.cls_off[c] = off;
-    off += nkb * npad * TC_KB;
-    r.tb_off = off; a.cls_tb_off[c] = off;
-    off += 11 * npad;
-    r.tap_off = off; a.cls_tap_off[c] = off;
-    off += nkb * (vec ? 8 : 32) * 2;
-    off = (off + 3) & ~3;  // keep every class block 16-byte aligned
-    tc_repack_kernel<<<dim3(nkb + 1, S), 256, 0, st>>>(r);
+    int off = 0, blk = 0;
+    for (int c = 0; c < ncls; ++c) {
+      RepackClass& rc = r.c[c];
+      tc_class_info(L, c, rc.khv, rc.kwv, rc.nkh, rc.nkw);
+      rc.Kcls = rc.nkh * rc.nkw * L->cin;
+      rc.nkb = (rc.Kcls + TC_KB - 1) / TC_KB;
+      rc.py = c >> 1; rc.px = c & 1; rc.blk0 = blk;
+      blk += rc.nkb + 1;
+      rc.cls_off = off; a.cls_off[c] = off;
+      off += rc.nkb * npad * TC_KB;
+      rc.tb_off = off; a.cls_tb_off[c] = off;
+      off += 11 * npad;
+      rc.tap_off = off; a.cls_tap_off[c] = off;
+      off += rc.nkb * (r.vec ? 8 : 32) * 2;
+      off = (off + 3) & ~3;  // keep every class block 16-byte aligned
+    }
+    tc_repack_kernel<<<dim3(blk, S), 256, 0, st>>>(r);
     BSDE_CUDA_OK(cudaGetLastError());
     count_launch();
   }
@@ -635,13 +664,15 @@ int tconv_fwd_tc(const bsde_conv_layer* L, int S, int B, const float* in, const 
                       (size_t)maxkb * (L->cin % 4 == 0 ? 8 : 32) * 8;
   const int Mcls = L->sd == 2 ? B * ((L->hout + 1) / 2) * ((L->wout + 1) / 2) : a.Mper;
   dim3 grid((Mcls + TC_BM - 1) / TC_BM, ncls, S);
-  if (L->cin % 4 == 0) {
-    BSDE_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(a);
-  } else {
-    BSDE_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a);
+  // opt in to the large dynamic shared memory once per kernel (the attribute is sticky per device context)
+  static bool attr_set = false;
+  if (!attr_set) {
+    BSDE_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BSDE_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
   }
+  if (L->cin % 4 == 0) conv_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(a);
+  else conv_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a);
   BSDE_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

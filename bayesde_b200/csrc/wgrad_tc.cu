@@ -321,14 +321,15 @@ struct TapSumArgs {
   float t;
 };
 
+template <int VW>
 __global__ void __launch_bounds__(1024) tap_colsum_kernel(TapSumArgs a) {
-  // threads = (pixel lane, column): `cp` columns (power of two >= cout, at most 64 per pass)
+  // threads = (pixel lane, column group of VW channels).  Interior pixels (every tap inside the image) add
+  // into one accumulator; only border pixels pay the per-tap predicated adds.
   const int split = blockIdx.x, s = blockIdx.y;
   const int Mout = a.B * a.hout * a.wout;
   const int mbeg = split * a.chunk, mend = min(Mout, mbeg + a.chunk);
   const float* __restrict__ dy = a.dy + (long long)s * Mout * a.cout;
   float* __restrict__ part = a.partial + ((long long)(s * a.splits + split) * a.rows) * a.cols;
-  const int ntap = a.ksize * a.ksize;
   __shared__ float red[10][1024];
   __shared__ unsigned s_rowmask[64], s_colmask[64];  // per output row / column: valid kh / kw bits
   for (int i = threadIdx.x; i < a.hout + a.wout; i += blockDim.x) {
@@ -342,31 +343,51 @@ __global__ void __launch_bounds__(1024) tap_colsum_kernel(TapSumArgs a) {
     if (isrow) s_rowmask[o] = mk; else s_colmask[o] = mk;
   }
   __syncthreads();
+  const unsigned fullmask = (1u << a.ksize) - 1u;
+  const int ngrp = (a.cout + VW - 1) / VW;      // column groups
   int cp = 1;
-  while (cp < a.cout && cp < 64) cp <<= 1;
+  while (cp < ngrp && cp < 64) cp <<= 1;
   const int lanes = 1024 / cp;
   const int c = threadIdx.x & (cp - 1), pl = threadIdx.x / cp;
   const int hw = a.hout * a.wout;
-  for (int c0 = 0; c0 < a.cout; c0 += 64) {
-    const bool cval = c0 + c < a.cout;
-    float acc[10];
+  for (int g0 = 0; g0 < ngrp; g0 += 64) {
+    const bool cval = g0 + c < ngrp;
+    const int ch = (g0 + c) * VW;
+    float acc_all[VW], acc_bt[VW], acc[9][VW];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+    for (int e = 0; e < VW; ++e) {
+      acc_all[e] = 0.f; acc_bt[e] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) acc[i][e] = 0.f;
+    }
     int m = mbeg + pl;
     int img = m / hw;
     int r = m - img * hw;
     int oy = r / a.wout, ox = r - oy * a.wout;
-#pragma unroll 1
+#pragma unroll 2
     for (; m < mend; m += lanes) {
-      const float v = cval ? __ldg(dy + (long long)m * a.cout + c0 + c) : 0.f;
-      acc[9] += v;
-      if (a.has_time) {
-        const unsigned rm = s_rowmask[oy], cm = s_colmask[ox];
+      float v[VW];
+      if (VW == 4) {
+        const float4 q = cval ? __ldg(reinterpret_cast<const float4*>(dy + (long long)m * a.cout + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[0] = q.x; v[1 % VW] = q.y; v[2 % VW] = q.z; v[3 % VW] = q.w;
+      } else {
+        v[0] = cval ? __ldg(dy + (long long)m * a.cout + ch) : 0.f;
+      }
+      const unsigned rm = s_rowmask[oy], cm = s_colmask[ox];
+      if (rm == fullmask && cm == fullmask) {
+#pragma unroll
+        for (int e = 0; e < VW; ++e) acc_all[e] += v[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < VW; ++e) acc_bt[e] += v[e];
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw)
-            if (((rm >> kh) & 1) && ((cm >> kw) & 1)) acc[kh * 3 + kw] += v;
+            if (((rm >> kh) & 1) && ((cm >> kw) & 1)) {
+#pragma unroll
+              for (int e = 0; e < VW; ++e) acc[kh * 3 + kw][e] += v[e];
+            }
       }
       ox += lanes;
       while (ox >= a.wout) {
@@ -375,30 +396,34 @@ __global__ void __launch_bounds__(1024) tap_colsum_kernel(TapSumArgs a) {
       }
     }
 #pragma unroll
-    for (int i = 0; i < 10; ++i) red[i][threadIdx.x] = acc[i];
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 10 * cp; idx += blockDim.x) {
-      const int i = idx / cp, cc = idx - i * cp;
-      const int co = c0 + cc;
-      if (co >= a.cout) continue;
-      float v = 0.f;
-      for (int l = 0; l < lanes; ++l) v += red[i][l * cp + cc];
-      if (i == 9) {
-        if (!a.swapped) part[(long long)a.Ktot * a.cols + co] = v;
-        else if (a.bias_partial) a.bias_partial[((long long)s * a.splits + split) * a.cout + co] = v;
-      } else if (a.has_time) {
-        // accumulators are indexed kh*3+kw; for ksize 1 only (0,0) exists
-        const int kh = i / 3, kw = i - kh * 3;
-        if (kh < a.ksize && kw < a.ksize) {
-          const int tap = kh * a.ksize + kw;
-          if (!a.swapped) part[(long long)(tap * a.Kc + a.Kc - 1) * a.cols + co] = a.t * v;
-          else part[(long long)(tap * a.cout + co) * a.cols + a.cin] = a.t * v;
+    for (int e = 0; e < VW; ++e) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 9; ++i) red[i][threadIdx.x] = acc[i][e] + acc_all[e];
+      red[9][threadIdx.x] = acc_all[e] + acc_bt[e];
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < 10 * cp; idx += blockDim.x) {
+        const int i = idx / cp, cc = idx - i * cp;
+        const int co = (g0 + cc) * VW + e;
+        if (g0 + cc >= ngrp || co >= a.cout) continue;
+        float vs = 0.f;
+        for (int l = 0; l < lanes; ++l) vs += red[i][l * cp + cc];
+        if (i == 9) {
+          if (!a.swapped) part[(long long)a.Ktot * a.cols + co] = vs;
+          else if (a.bias_partial) a.bias_partial[((long long)s * a.splits + split) * a.cout + co] = vs;
+        } else if (a.has_time) {
+          // accumulators are indexed kh*3+kw; for ksize 1 only (0,0) exists
+          const int kh = i / 3, kw = i - kh * 3;
+          if (kh < a.ksize && kw < a.ksize) {
+            const int tap = kh * a.ksize + kw;
+            if (!a.swapped) part[(long long)(tap * a.Kc + a.Kc - 1) * a.cols + co] = a.t * vs;
+            else part[(long long)(tap * a.cout + co) * a.cols + a.cin] = a.t * vs;
+          }
         }
       }
     }
     __syncthreads();
   }
-  (void)ntap;
 }
 
 struct WgTcPlan {
@@ -435,7 +460,8 @@ static WgTcPlan wg_plan(const bsde_conv_layer* L, int S, int B) {
   p.stages = std::min(4, (200 * 1024) / stage_bytes);
   p.smem = 1024 + (size_t)p.stages * stage_bytes + 8 * 9 + 16;
   p.ok = cols_needed <= 512 && p.stages >= 2 && p.npad <= 256 && !(p.swapped && L->sn != 1);
-  int want = (148 * 2 + S - 1) / S;
+  int want = 148 / S;  // one CTA per SM (TMEM / smem allow a single resident CTA): a single wave
+  if (want < 1) want = 1;
   int maxs = (p.Mper + 1023) / 1024;
   p.splits = std::max(1, std::min(want, maxs));
   p.chunk = (p.Mper + p.splits - 1) / p.splits;
@@ -490,11 +516,15 @@ int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, cons
   static const int wg_dbg = getenv("BSDE_WG_DBG") ? atoi(getenv("BSDE_WG_DBG")) : 0;
   a.dbg = wg_dbg;
   const bool va = p.CA % 4 == 0, vb = p.CB % 4 == 0;
-#define WG_LAUNCH(VA_, VB_)                                                                                            \
-  do {                                                                                                                 \
-    BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<VA_, VB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)); \
-    wgrad_tc_kernel<VA_, VB_><<<S * p.splits, WG_THREADS, p.smem, st>>>(a);                                            \
-  } while (0)
+  static bool attr_set = false;
+  if (!attr_set) {
+    BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+#define WG_LAUNCH(VA_, VB_) wgrad_tc_kernel<VA_, VB_><<<S * p.splits, WG_THREADS, p.smem, st>>>(a)
   if (va && vb) WG_LAUNCH(true, true);
   else if (va) WG_LAUNCH(true, false);
   else if (vb) WG_LAUNCH(false, true);
@@ -512,7 +542,8 @@ int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, cons
   ta.rows = p.rows; ta.cols = p.cols; ta.swapped = p.swapped; ta.has_time = L->has_time; ta.Kc = Kc; ta.Ktot = Ktot;
   ta.cin = L->cin; ta.t = t;
   if (!(wg_dbg & 1))
-  tap_colsum_kernel<<<dim3(p.splits, S), 1024, 0, st>>>(ta);
+  if (L->cout % 4 == 0) tap_colsum_kernel<4><<<dim3(p.splits, S), 1024, 0, st>>>(ta);
+  else tap_colsum_kernel<1><<<dim3(p.splits, S), 1024, 0, st>>>(ta);
   BSDE_CUDA_OK(cudaGetLastError());
   count_launch();
 
