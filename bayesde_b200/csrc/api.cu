@@ -36,6 +36,13 @@ int tconv_fwd_tc(const bsde_conv_layer* L, int S, int B, const float* in, const 
                  long long w_sample_stride, float t, int act, int epi, float scale, const float* aux,
                  float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// window-staged persistent tensor-core path (tconv_win.cu)
+bool tconv_win_supported(const bsde_conv_layer* L, int S, int B);
+size_t tconv_win_ws_bytes(const bsde_conv_layer* L, int S);
+int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const float* w, long long w_sample_stride,
+                  float t, int act, int epi, float scale, const float* aux, float* out, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
+
 bool tconv_wgrad_tc_supported(const bsde_conv_layer* L, int S, int B);
 size_t tconv_wgrad_ws_tc(const bsde_conv_layer* L, int S, int B);
 int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
@@ -57,6 +64,8 @@ static int conv_wgrad(const bsde_conv_layer* L, int S, int B, const float* in, c
 static int conv_fwd(const bsde_conv_layer* L, int S, int B, const float* in, const float* w,
                     long long wss, float t, int act, int epi, float scale, const float* aux, float* out,
                     int math, void* tc_ws, size_t tc_ws_bytes, cudaStream_t st) {
+  if (math == BSDE_MATH_TC && tconv_win_supported(L, S, B))
+    return tconv_fwd_win(L, S, B, in, w, wss, t, act, epi, scale, aux, out, tc_ws, tc_ws_bytes, st);
   if (math == BSDE_MATH_TC && tconv_tc_supported(L, epi))
     return tconv_fwd_tc(L, S, B, in, w, wss, t, act, epi, scale, aux, out, tc_ws, tc_ws_bytes, st);
   return tconv_fwd_simt(L, S, B, in, w, wss, t, act, epi, scale, aux, out, st);
@@ -77,6 +86,14 @@ static bsde_conv_layer dgrad_layer(const bsde_conv_layer& F) {
   D.w_k_stride = F.w_n_stride;  // reduction runs over the forward output channel
   D.w_n_stride = F.w_k_stride;  // output runs over the forward input channel
   return D;
+}
+
+// scratch of the tensor-core forward / data-gradient paths for one layer (either kernel may be chosen at run time)
+static size_t conv_tc_ws(const bsde_conv_layer* L, int S) {
+  size_t m = 0;
+  if (tconv_tc_supported(L, 0)) m = std::max(m, tconv_tc_ws_bytes(L, S));
+  m = std::max(m, tconv_win_ws_bytes(L, S));
+  return m;
 }
 
 static size_t act_elems(const bsde_xpath_desc* d, int l) {  // output of layer l
@@ -104,8 +121,8 @@ extern "C" int bsde_tconv_fwd(const bsde_conv_layer* L, int32_t S, int32_t B, co
 }
 
 extern "C" size_t bsde_tconv_fwd_workspace_bytes(const bsde_conv_layer* L, int32_t S, int32_t math) {
-  if (!L || math != BSDE_MATH_TC || !tconv_tc_supported(L, 0)) return 0;
-  return tconv_tc_ws_bytes(L, S);
+  if (!L || math != BSDE_MATH_TC) return 0;
+  return conv_tc_ws(L, S);
 }
 
 extern "C" size_t bsde_tconv_wgrad_workspace_bytes(const bsde_conv_layer* L, int32_t S, int32_t B) {
@@ -146,10 +163,10 @@ static size_t xpath_tc_bytes(const bsde_xpath_desc* d, int backward) {
   if (d->math != BSDE_MATH_TC) return 0;
   size_t m = 0;
   for (int l = 0; l < d->nlayers; ++l) {
-    if (tconv_tc_supported(&d->layers[l], 0)) m = std::max(m, tconv_tc_ws_bytes(&d->layers[l], d->S));
+    m = std::max(m, conv_tc_ws(&d->layers[l], d->S));
     if (backward) {
       bsde_conv_layer D = dgrad_layer(d->layers[l]);
-      if (tconv_tc_supported(&D, 0)) m = std::max(m, tconv_tc_ws_bytes(&D, d->S));
+      m = std::max(m, conv_tc_ws(&D, d->S));
     }
   }
   return align_up(m);

@@ -17,6 +17,8 @@ p.add_argument("--S", type=int, default=8)
 p.add_argument("--math", default="tc")
 p.add_argument("--groups", default="0,1,2")
 p.add_argument("--reps", type=int, default=10)
+p.add_argument("--warm", type=int, default=3)
+p.add_argument("--no_wgrad", action="store_true")
 a = p.parse_args()
 L = _lib.lib()
 dev = "cuda:0"
@@ -52,7 +54,7 @@ for g in [int(v) for v in a.groups.split(",")]:
                 st = L.bsde_tconv_fwd(C.byref(lay), a.S, a.B, _lib.ptr(x), _lib.ptr(w), fx.P, 0.3, 0, epi, 1.0, None,
                                       _lib.ptr(out), math, C.c_void_p(ws.data_ptr()), nb, _lib.stream_ptr())
                 _lib.check(st, "tconv")
-            for _ in range(3):
+            for _ in range(a.warm):
                 run()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -66,7 +68,7 @@ for g in [int(v) for v in a.groups.split(",")]:
             if kind == "dgrad" and cs.sd == 1 and cs.sn == 2:
                 pix = cs.hout * cs.wout
             fl = 2.0 * a.S * a.B * pix * lay.ksize ** 2 * (lay.cin + lay.has_time) * lay.cout
-            if kind == "fwd":
+            if kind == "fwd" and not a.no_wgrad:
                 dy = torch.randn(a.S, a.B, cs.hout, cs.wout, cs.cout, device=dev)
                 gw = torch.zeros(a.S, fx.P, device=dev)
                 nbw = L.bsde_tconv_wgrad_workspace_bytes(C.byref(cs), a.S, a.B)
