@@ -6,21 +6,24 @@
 // consecutive q (one accumulator row each); a tap displaced by (sy, sx) reads position q + sy*(Wq+1) + sx,
 // and the pad column / pad row supply the zero padding of every border.  So the A operand of every tap is
 // the SAME staged window, addressed through a shared-memory descriptor whose start address is shifted by
-// `shift` positions (tools/umma_probe2.cu: shifted starts are exact for the no-swizzle K-major layout).
+// `shift` rows (tools/umma_probe2.cu: the 128B swizzle is a function of absolute smem address bits, so
+// row-shifted starts are exact with base_offset = 0).
 //
-// Shared memory (all K-major, no swizzle, "chunk planes": [16-byte channel chunk][row][16 B], SBO = 128 B,
-// LBO = plane stride):
-//   * weights of the whole layer, repacked once per (sample, iteration) by win_repack_kernel, stay resident
-//     for all tiles of the CTA (<= 184 KB);
-//   * the window streams through a ring of K-slabs (8 input channels = one MMA k-step each), filled by four
-//     producer warps with 16-byte cp.async (zero-fill at pads): every input element is read ONCE per tile;
+// Shared memory:
+//   * window: per 32-channel group ("half") one K-major SWIZZLE_128B region [NPOSw rows][128 B]; the four
+//     producer warps fill it with 16-byte cp.async (zero-fill at pads), 8 lanes per row, so that BOTH sides of
+//     an LDGSTS are whole 128-byte lines (4 global lines + 4 smem rows per warp instruction).  Every input
+//     element is read ONCE per tile.  Slabs (all halves of a tile, or one half) cycle through a ring.
+//   * weights of the whole layer, repacked once per (sample, iteration) by win_repack_kernel into K-major
+//     no-swizzle chunk planes, stay resident for all tiles of the CTA (<= 184 KB);
 //   * stride-2 convolutions stage the four input parity planes (taps pick plane + shift); lhs-dilated
 //     (transposed) convolutions keep four accumulators, one per output parity class, over one window.
-// One thread issues tcgen05.mma.kind::tf32 (M=128, N=npad, K=8) per (k-slab, tap); accumulators are double
-// buffered in TMEM so the four epilogue warps (tcgen05.ld -> warp-private smem transpose -> coalesced
-// bias / time-channel / activation / Euler / data-gradient epilogue) overlap the next tile's MMAs.
-// The time channel never enters the GEMM (spatially constant): t * sum of the time rows of the taps that
-// fall inside the image, from a per-row tap mask.
+// One warp issues tcgen05.mma.kind::tf32 (M=128, N=npad, K=8) per (k-step, tap) from descriptor tables;
+// accumulators are double buffered in TMEM so the eight epilogue warps overlap the next tile's MMAs:
+// tcgen05.ld -> bias / time term / activation in registers (one accumulator row per lane) -> warp-private
+// swizzled smem transpose -> coalesced Euler / data-gradient combine and store.
+// The time channel never enters the GEMM (spatially constant): t * (sum of the time rows of the taps that
+// fall inside the image), looked up from a 16-entry border-class table per accumulator.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -50,17 +53,19 @@ struct WinArgs {
   const float* wimg;
   long long wimg_sample_stride;  // floats
   int S, B, G, ntiles;
-  int cin, cout, npad, nks;
+  int cin, cout, npad, nks, nhalf;
   int hin, win, hout, wout, sn, kn, off, sd, has_time, mode;
   int Hq, Wq, pitch, IP, Q, lead, NPOSw, NP, NA, nent;
-  int ring, slab_bytes, w_bytes, tb_floats, tab_units, nbuf, tmem_cols;
-  int kslab, nslab, pstride;  // k-steps per slab, slabs per tile, bytes between consecutive 16-byte chunk planes
+  int ring, slab_bytes, w_bytes, tb_floats, nbuf, tmem_cols;
+  int hslab, nslab, region;  // halves per slab, slabs per tile, bytes of one (plane, half) region
   float t, scale;
-  int act, epi;
+  uint32_t aoff[WN_MAXENT];  // A start offset of each entry in 16-byte units (plane region + shifted row)
+  uint32_t dcol[WN_MAXENT];  // accumulator column offset | (first tap of its accumulator) << 31
+  int dbg;  // tools/ only (BSDE_WIN_DBG): 1 skip window copies, 2 skip MMAs, 4 skip epilogue stores
   WinEntry ent[WN_MAXENT];
 };
 
-__device__ __forceinline__ bool wn_map_axis(int o, int k, int sn, int kn, int off, int sd, int size) {
+__device__ __host__ __forceinline__ bool wn_map_axis(int o, int k, int sn, int kn, int off, int sd, int size) {
   int num = o * sn + k * kn + off;
   if (num < 0) return false;
   if (sd == 2) {
@@ -72,15 +77,20 @@ __device__ __forceinline__ bool wn_map_axis(int o, int k, int sn, int kn, int of
 
 // ---- weight repack: flat w(t_k) -> the CTA's resident smem image --------------------------------------
 //   tiles  [(entry e, k-step ks)][chunk c in 0..1][n in 0..npad)[4 floats]   (K-major chunk planes)
-//   tables [0] bias, [1+e] time row of entry e, [1+nent+a] sum of the time rows of accumulator a
+//   tables [0] bias; with a time channel: [1 + acc*16 + cls] = sum of the time rows of the taps of accumulator
+//          `acc` that are inside the image for border class cls = fy*4 + fx,
+//          fy = (y == 0) | (y == Hq-1) << 1 in position space (fx alike)
 struct WinRepackArgs {
   const float* w;
   float* img;
   long long w_sample_stride, img_sample_stride;
-  int nent, nks, npad, cin, cout, ksize, NA, real_base, has_time, time_row, use_bias, w_floats;
+  int nent, nks, npad, cin, cout, ksize, NA, real_base, has_time, time_row, use_bias, w_floats, tb_rows;
+  int mode, Hq, Wq, hin, win, sn, kn, off, sd;
   long long w_off, b_off, ts, ks, ns;
-  int ent_tap[WN_MAXENT], ent_acc[WN_MAXENT];
+  int ent_tap[WN_MAXENT], ent_acc[WN_MAXENT], ent_kh[WN_MAXENT], ent_kw[WN_MAXENT];
 };
+
+__device__ __forceinline__ int wn_class_rep(int f, int size) { return f == 0 ? 1 : (f == 2 ? size - 1 : 0); }
 
 __global__ void win_repack_kernel(WinRepackArgs a) {
   const int s = blockIdx.y;
@@ -88,17 +98,22 @@ __global__ void win_repack_kernel(WinRepackArgs a) {
   float* __restrict__ img = a.img + (long long)s * a.img_sample_stride;
   if ((int)blockIdx.x == a.nent * a.nks) {
     float* tb = img + a.w_floats;
-    const int rows = 1 + a.nent + a.NA;
-    for (int idx = threadIdx.x; idx < rows * a.npad; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < a.tb_rows * a.npad; idx += blockDim.x) {
       const int r = idx / a.npad, n = idx - r * a.npad;
       float v = 0.f;
       if (n < a.cout) {
         if (r == 0) {
           v = (a.b_off >= 0 && a.use_bias) ? __ldg(w + a.b_off + n) : 0.f;
-        } else if (a.has_time) {
+        } else {
+          const int ac = (r - 1) >> 4, cls = (r - 1) & 15;
+          const int y = wn_class_rep(cls >> 2, a.Hq), x = wn_class_rep(cls & 3, a.Wq);
+          const int oy = a.mode == 3 ? 2 * y + (ac >> 1) : y, ox = a.mode == 3 ? 2 * x + (ac & 1) : x;
           for (int e = 0; e < a.nent; ++e) {
-            const bool take = r <= a.nent ? (e == r - 1) : (a.ent_acc[e] == r - 1 - a.nent);
-            if (take) v += __ldg(w + a.w_off + a.ent_tap[e] * a.ts + (long long)a.time_row * a.ks + (long long)n * a.ns);
+            if (a.ent_acc[e] != ac) continue;
+            if (!wn_map_axis(oy, a.ent_kh[e], a.sn, a.kn, a.off, a.sd, a.hin) ||
+                !wn_map_axis(ox, a.ent_kw[e], a.sn, a.kn, a.off, a.sd, a.win))
+              continue;
+            v += __ldg(w + a.w_off + a.ent_tap[e] * a.ts + (long long)a.time_row * a.ks + (long long)n * a.ns);
           }
         }
       }
@@ -110,7 +125,6 @@ __global__ void win_repack_kernel(WinRepackArgs a) {
   float* __restrict__ tile = img + (long long)blockIdx.x * a.npad * 8;
   const int tap = a.ent_tap[e];
   for (int idx = threadIdx.x; idx < a.npad * 8; idx += blockDim.x) {
-    // idx enumerates (n, kk) with n fastest for coalesced-ish reads along the output channel
     const int n = idx % a.npad, kk = idx / a.npad;
     const int c = ks * 8 + kk;
     float v = 0.f;
@@ -121,26 +135,36 @@ __global__ void win_repack_kernel(WinRepackArgs a) {
 }
 
 // ---- main kernel -----------------------------------------------------------------------------------------
+__device__ __forceinline__ float wn_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float wn_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <int ACT>
 __device__ __forceinline__ float wn_act_fwd(float x) {
   if (ACT == BSDE_ACT_SOFTPLUS) {
-    const float r = __logf(1.f + __expf(fminf(x, 15.f)));
+    const float r = 0.69314718f * wn_lg2(1.f + wn_ex2(1.44269504f * fminf(x, 15.f)));
     return x > 15.f ? x : r;
   }
   if (ACT == BSDE_ACT_TANH) return tanhf(x);
-  if (ACT == BSDE_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
+  if (ACT == BSDE_ACT_ELU) return x > 0.f ? x : wn_ex2(1.44269504f * x) - 1.f;
   return x;
 }
 template <int ACT>
 __device__ __forceinline__ float wn_act_grad_out(float a) {
-  if (ACT == BSDE_ACT_SOFTPLUS) return 1.f - __expf(-a);
+  if (ACT == BSDE_ACT_SOFTPLUS) return 1.f - wn_ex2(-1.44269504f * a);
   if (ACT == BSDE_ACT_TANH) return 1.f - a * a;
   if (ACT == BSDE_ACT_ELU) return a > 0.f ? 1.f : a + 1.f;
   return 1.f;
 }
+// second half of the epilogue (needs the value already stored at the output position)
 template <int EPI, int ACT>
-__device__ __forceinline__ float wn_epi(float q, float x, float scale) {
-  if (EPI == BSDE_EPI_BIAS_ACT) return wn_act_fwd<ACT>(q);
+__device__ __forceinline__ float wn_combine(float q, float x, float scale) {
   if (EPI == BSDE_EPI_DACT) return scale * q * wn_act_grad_out<ACT>(x);
   if (EPI == BSDE_EPI_EULER || EPI == BSDE_EPI_ACCUM) return fmaf(scale, q, x);
   return q;
@@ -153,21 +177,16 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
   const int s = blockIdx.x / a.G, g = blockIdx.x - s * a.G;
 
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 127u) & ~127u;
+  const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw);
-  // carve
+  // carve: ring first (1024-byte aligned swizzle regions), then weights, tables, epilogue scratch
   int soff = 0;
-  const uint32_t s_w = base;                                    soff += a.w_bytes;
+  const uint32_t s_ring = base;  uint8_t* g_ring = gen;         soff += a.ring * a.slab_bytes;
+  const uint32_t s_w = base + soff;                             soff += a.w_bytes;
   float* s_tb = reinterpret_cast<float*>(gen + soff);           soff += a.tb_floats * 4;
-  soff = (soff + 127) & ~127;
-  const uint32_t s_ring = base + soff;  uint8_t* g_ring = gen + soff;  soff += a.ring * a.slab_bytes;
   float* s_stage = reinterpret_cast<float*>(gen + soff);        soff += WN_EPI_WARPS * 32 * 16 * 4;
   int* s_tab = reinterpret_cast<int*>(gen + soff);              soff += a.NP * a.NPOSw * 4;
   int* s_pix = reinterpret_cast<int*>(gen + soff);              soff += WN_EPI_WARPS * 32 * 4;
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(gen + soff);   soff += WN_EPI_WARPS * 32 * 4;
-  uint64_t* s_bdesc = reinterpret_cast<uint64_t*>(gen + soff);  soff += a.nks * a.nent * 8;   // [ks][e] B descriptors
-  uint32_t* s_aoff = reinterpret_cast<uint32_t*>(gen + soff);   soff += WN_MAXENT * 4;        // A start offset (16 B units)
-  uint32_t* s_dcol = reinterpret_cast<uint32_t*>(gen + soff);   soff += WN_MAXENT * 4;        // acc column | first-tap flag << 31
   const uint32_t bars = base + soff;                            soff += 8 * (2 * WN_MAXRING + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + soff);
   auto full_bar = [&](int st) { return bars + 8u * st; };
@@ -194,19 +213,6 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
-    // descriptor tables of the issue loop
-    const uint64_t b_hi = desc_hi((uint32_t)a.npad * 16u, 128u, 0);
-    for (int idx = lane; idx < a.nks * a.nent; idx += 32) {
-      const int ks = idx / a.nent, e = idx - ks * a.nent;
-      s_bdesc[idx] = b_hi | desc_addr(s_w + (uint32_t)((e * a.nks + ks) * a.npad * 32));
-    }
-    if (lane < a.nent) {
-      const WinEntry en = a.ent[lane];
-      s_aoff[lane] = ((uint32_t)(en.plane * a.kslab * 2) * (uint32_t)a.pstride + (uint32_t)((a.lead + en.shift) * 16)) >> 4;
-      bool first = true;
-      for (int e = 0; e < lane; ++e) first &= a.ent[e].acc != en.acc;
-      s_dcol[lane] = (uint32_t)(en.acc * a.npad) | (first ? 0x80000000u : 0u);
-    }
   }
   fence_proxy_async();
   tc_fence_before();
@@ -218,6 +224,8 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
     // =============================== producers ===============================
     const float* __restrict__ in = a.in + (long long)s * a.B * a.hin * a.win * a.cin;
     const int pt = tid - WN_EPI_WARPS * 32;
+    const int c = pt & 7;  // 16-byte chunk inside the 128-byte row: 8 lanes cover one row / one global line
+    const float rIP = 1.0f / (float)a.IP, rpitch = 1.0f / (float)a.pitch;
     uint32_t cnt = 0;
 #pragma unroll 1
     for (int tile = g; tile < a.ntiles; tile += a.G) {
@@ -230,10 +238,14 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
         int img = 0, y = 0, x = 0;
         bool pv = q >= 0 && q < a.Q;
         if (pv) {
-          img = q / a.IP;
-          const int r = q - img * a.IP;
-          y = r / a.pitch;
+          // q / IP and r / pitch through fp32 reciprocals with a +-1 fix-up (q < 2^24 is not required: the
+          // fix-up loop makes the result exact for any estimate within one of the quotient)
+          img = (int)((float)q * rIP);
+          int r = q - img * a.IP;
+          if (r < 0) { --img; r += a.IP; } else if (r >= a.IP) { ++img; r -= a.IP; }
+          y = (int)((float)r * rpitch);
           x = r - y * a.pitch;
+          if (x < 0) { --y; x += a.pitch; } else if (x >= a.pitch) { ++y; x -= a.pitch; }
           pv = y < a.Hq && x < a.Wq;
         }
         for (int plane = 0; plane < a.NP; ++plane) {
@@ -252,30 +264,36 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
         const int slot = cnt % a.ring;
         if (cnt >= (uint32_t)a.ring) mbar_wait(empty_bar(slot), ((cnt / a.ring) & 1) ^ 1);
         const uint32_t sb = s_ring + slot * a.slab_bytes;
-        const int cbase = sl * a.kslab * 8;                       // first channel of this slab
-        if (VEC) {
-          // lanes run over the 16-byte chunks of a position first: a warp reads whole 128-byte lines
-          const int nch = min(a.kslab * 2, (a.cin - cbase + 3) >> 2);   // real chunks in this slab
-          const int nchp = a.kslab * 2;                                   // chunk planes per plane set
-          int cpw = 1;                                                    // power of two >= nchp
-          while (cpw < nchp) cpw <<= 1;
-          const int c = pt & (cpw - 1), pstep = WN_PROD / cpw;
+        const int h0 = sl * a.hslab;
+        const int hend = min(a.hslab, a.nhalf - h0);
+        if (a.dbg & 1) {
+        } else if (VEC) {
+          // thread = (chunk c, rows i0 + 16 k): i & 7 is constant per thread, so the swizzled chunk slot is too
+          const int i0 = pt >> 3;
+          const uint32_t swz = (uint32_t)((c ^ (i0 & 7)) << 4);
+          const float* __restrict__ inc = in + h0 * 32 + c * 4;
+          const int cfirst = h0 * 32 + c * 4;
 #pragma unroll 1
           for (int plane = 0; plane < a.NP; ++plane) {
-            const uint32_t d0 = sb + (uint32_t)(plane * nchp + c) * (uint32_t)a.pstride;
-            if (c < nchp) {
-#pragma unroll 2
-              for (int i = pt / cpw; i < a.NPOSw; i += pstep) {
-                const int src = s_tab[plane * a.NPOSw + i];
-                const bool ok = src >= 0 && c < nch;
-                cp_async16(d0 + i * 16, in + (ok ? src + cbase + c * 4 : 0), ok);
+            const uint32_t reg = sb + (uint32_t)(plane * a.hslab) * (uint32_t)a.region + swz;
+            const int* tabp = s_tab + plane * a.NPOSw;
+#pragma unroll 4
+            for (int i = i0; i < a.NPOSw; i += WN_PROD / 8) {
+              const int src = tabp[i];
+              const float* gp = inc + (src >= 0 ? src : 0);
+              uint32_t d = reg + i * 128;
+              for (int hs = 0; hs < hend; ++hs) {
+                const bool ok = src >= 0 && cfirst + hs * 32 < a.cin;
+                cp_async16(d, ok ? gp + hs * 32 : in, ok);
+                d += a.region;
               }
             }
           }
         } else {
 #pragma unroll 1
           for (int plane = 0; plane < a.NP; ++plane) {
-            const uint32_t d0 = sb + (uint32_t)(plane * 2) * (uint32_t)a.pstride;
+            const uint32_t reg = sb + (uint32_t)(plane * a.hslab) * (uint32_t)a.region;
+            const int cbase = h0 * 32;
 #pragma unroll 1
             for (int i = pt; i < a.NPOSw; i += WN_PROD) {
               const int src = s_tab[plane * a.NPOSw + i];
@@ -283,7 +301,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
 #pragma unroll
               for (int ch = 0; ch < 8; ++ch)
                 if (cbase + ch < a.cin)
-                  cp_async4(d0 + (ch >> 2) * a.pstride + i * 16 + (ch & 3) * 4, in + (ok ? src + cbase + ch : 0), ok);
+                  cp_async4(reg + i * 128 + (((ch >> 2) ^ (i & 7)) << 4) + (ch & 3) * 4, ok ? in + src + cbase + ch : in, ok);
             }
           }
         }
@@ -292,11 +310,14 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
     }
   } else if (warp == WN_MMA_WARP) {
     // =============================== MMA issuer ===============================
-    // the whole warp runs the loop (uniform address arithmetic); lane 0 issues
+    // The whole warp runs the loop; every operand is built from kernel parameters and loop counters only, so
+    // the descriptors live in uniform registers and one elected lane issues each tcgen05.mma.
     {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint64_t a_hi = desc_hi((uint32_t)a.pstride, 128u, 0);
-      const uint32_t kstep16 = (uint32_t)(2 * a.pstride) >> 4;
+      const uint64_t a_hi = desc_hi(16u, 1024u, 2);  // K-major SWIZZLE_128B, 8-row groups 1024 B apart
+      const uint64_t b_hi = desc_hi((uint32_t)a.npad * 16u, 128u, 0);
+      const uint32_t w16 = s_w >> 4, bstep = (uint32_t)(a.npad * 32) >> 4, region16 = (uint32_t)a.region >> 4;
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t cnt = 0;
       int it = 0;
 #pragma unroll 1
@@ -306,7 +327,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
           mbar_wait(acce_bar(buf), ((it / a.nbuf) & 1) ^ 1);
           tc_fence_after();
         }
-        const uint32_t dbase = tmem_base + (uint32_t)(buf * a.NA * a.npad);
+        const uint32_t dbase = tm + (uint32_t)(buf * a.NA * a.npad);
 #pragma unroll 1
         for (int sl = 0; sl < a.nslab; ++sl, ++cnt) {
           const int slot = cnt % a.ring;
@@ -314,24 +335,35 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
           fence_proxy_async();
           tc_fence_after();
           const uint32_t sb16 = (s_ring + slot * a.slab_bytes) >> 4;
-          const int kend = min(a.kslab, a.nks - sl * a.kslab);
+          const int ks0 = sl * a.hslab * 4;
+          const int kend = min(a.hslab * 4, a.nks - ks0);
+          if (!(a.dbg & 2)) {
 #pragma unroll 1
-          for (int kk = 0; kk < kend; ++kk) {
-            const int ks = sl * a.kslab + kk;
-            const uint32_t ka = sb16 + kk * kstep16;
-            const uint64_t* bd = s_bdesc + ks * a.nent;
-            const uint32_t later = ks > 0 ? 1u : 0u;
-#pragma unroll 3
-            for (int e = 0; e < a.nent; ++e) {
-              const uint32_t dc = s_dcol[e];
-              const uint64_t ad = a_hi | (uint64_t)((ka + s_aoff[e]) & 0x3FFFu);
-              if (lane == 0) umma_tf32(dbase + (dc & 0xFFFFu), ad, bd[e], idesc, later | ((dc >> 31) ^ 1u));
+            for (int kk = 0; kk < kend; ++kk) {
+              // k-step kk of the slab: half kk >> 2 (region stride), 32-byte step kk & 3 inside the 128-byte row
+              const uint32_t ka = sb16 + (uint32_t)(kk >> 2) * region16 + (uint32_t)(kk & 3) * 2u;
+              const uint32_t kb = w16 + (uint32_t)(ks0 + kk) * bstep;
+              const uint32_t later = (ks0 + kk) > 0 ? 1u : 0u;
+#define WN_ISSUE(e)                                                                                         \
+  {                                                                                                         \
+    const uint32_t dc = a.dcol[e];                                                                          \
+    const uint64_t ad = a_hi | (uint64_t)((ka + a.aoff[e]) & 0x3FFFu);                                      \
+    const uint64_t bd = b_hi | (uint64_t)((kb + (uint32_t)((e) * a.nks) * bstep) & 0x3FFFu);                \
+    umma_tf32_elect(dbase + (dc & 0xFFFFu), ad, bd, idesc, later | ((dc >> 31) ^ 1u));                      \
+  }
+              if (a.nent == 9) {
+#pragma unroll
+                for (int e = 0; e < 9; ++e) WN_ISSUE(e)
+              } else {
+#pragma unroll 1
+                for (int e = 0; e < a.nent; ++e) WN_ISSUE(e)
+              }
+#undef WN_ISSUE
             }
           }
-          __syncwarp();
-          if (lane == 0) umma_commit(empty_bar(slot));
+          umma_commit_elect(empty_bar(slot));
         }
-        if (lane == 0) umma_commit(accf_bar(buf));
+        umma_commit_elect(accf_bar(buf));
       }
     }
     __syncwarp();
@@ -341,7 +373,6 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
     const int quarter = warp & 3, half = warp >> 2;
     float* stage = s_stage + warp * 32 * 16;
     int* w_pix = s_pix + warp * 32;
-    uint32_t* w_mask = s_mask + warp * 32;
     float* __restrict__ out = a.out + (long long)s * a.B * a.hout * a.wout * a.cout;
     const float* __restrict__ aux = a.aux ? a.aux + (long long)s * a.B * a.hout * a.wout * a.cout : nullptr;
     const bool vec_out = (a.cout & 3) == 0;
@@ -361,68 +392,65 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
         x = r - y * a.pitch;
         valid = y < a.Hq && x < a.Wq;
       }
-      // every tap of an interior position falls inside the image
-      const bool interior = y >= 1 && x >= 1 && y < a.Hq - 2 && x < a.Wq - 2;
+      // border class of this position (selects the time-term row)
+      const int cls = (((y == 0) | ((y == a.Hq - 1) << 1)) << 2) | ((x == 0) | ((x == a.Wq - 1) << 1));
       mbar_wait(accf_bar(buf), (it / a.nbuf) & 1);
       tc_fence_after();
       int last_ac = -1;
 #pragma unroll 1
-      for (int item = half; item < a.NA * nchunk; item += 2) {
+      for (int item = half; item < ((a.dbg & 8) ? 0 : a.NA * nchunk); item += 2) {
         const int ac = item / nchunk, n0 = (item - ac * nchunk) * 16;
         if (ac != last_ac) {
           last_ac = ac;
           int oy = y, ox = x;
           if (a.mode == 3) { oy = 2 * y + (ac >> 1); ox = 2 * x + (ac & 1); }
-          const bool oval = valid && oy < a.hout && ox < a.wout;
-          uint32_t mask = 0xFFFFFFFFu;
-          if (a.has_time && oval && !interior) {
-            mask = 0;
-            bool all = true;
-            for (int e = 0; e < a.nent; ++e) {
-              if (a.ent[e].acc != ac) continue;
-              const bool ok = wn_map_axis(oy, a.ent[e].kh, a.sn, a.kn, a.off, a.sd, a.hin) &&
-                              wn_map_axis(ox, a.ent[e].kw, a.sn, a.kn, a.off, a.sd, a.win);
-              if (ok) mask |= 1u << e; else all = false;
-            }
-            if (all) mask = 0xFFFFFFFFu;
-          }
           __syncwarp();
-          w_pix[lane] = oval ? (img * a.hout + oy) * a.wout + ox : -1;
-          w_mask[lane] = mask;
+          w_pix[lane] = valid ? (img * a.hout + oy) * a.wout + ox : -1;
         }
-        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * a.NA + ac) * a.npad);
-        const float* tsum = s_tb + (1 + a.nent + ac) * a.npad;
         uint32_t v[16];
-        tmem_ld16(trow + n0, v);
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * a.NA + ac) * a.npad + n0), v);
+        // row form: bias, time term, activation on this lane's 16 accumulator columns
+        float f[16];
+        {
+          const float4* bt = reinterpret_cast<const float4*>(s_tb + n0);
+          const float4* tt = reinterpret_cast<const float4*>(s_tb + (1 + ac * 16 + cls) * a.npad + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = bt[j];
+            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+            if (a.has_time) {
+              const float4 t4 = tt[j];
+              f[4 * j + 0] = fmaf(a.t, t4.x, f[4 * j + 0]); f[4 * j + 1] = fmaf(a.t, t4.y, f[4 * j + 1]);
+              f[4 * j + 2] = fmaf(a.t, t4.z, f[4 * j + 2]); f[4 * j + 3] = fmaf(a.t, t4.w, f[4 * j + 3]);
+            }
+          }
+          if (EPI == BSDE_EPI_BIAS_ACT) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = wn_act_fwd<ACT>(f[j]);
+          }
+        }
         __syncwarp();  // readers of the previous chunk are done with the staging rows
         {
           // row `lane`: 16-byte chunk c stored at position c ^ ((lane >> 1) & 3)  (conflict-free both ways)
-          uint4* dst = reinterpret_cast<uint4*>(stage + lane * 16);
-          const int f = (lane >> 1) & 3;
-          dst[0 ^ f] = make_uint4(v[0], v[1], v[2], v[3]);
-          dst[1 ^ f] = make_uint4(v[4], v[5], v[6], v[7]);
-          dst[2 ^ f] = make_uint4(v[8], v[9], v[10], v[11]);
-          dst[3 ^ f] = make_uint4(v[12], v[13], v[14], v[15]);
+          float4* dst = reinterpret_cast<float4*>(stage + lane * 16);
+          const int fz = (lane >> 1) & 3;
+          dst[0 ^ fz] = make_float4(f[0], f[1], f[2], f[3]);
+          dst[1 ^ fz] = make_float4(f[4], f[5], f[6], f[7]);
+          dst[2 ^ fz] = make_float4(f[8], f[9], f[10], f[11]);
+          dst[3 ^ fz] = make_float4(f[12], f[13], f[14], f[15]);
         }
         __syncwarp();
         const int ncol = min(16, a.cout - n0);
         if (vec_out && ncol == 16) {
-          // lane -> fixed column group c4, rows r8 + 8 j
+          // lane -> fixed column group c4, rows r8 + 8 j: 64 contiguous bytes per row
           const int n = n0 + c4 * 4;
-          const float4 b4 = *reinterpret_cast<const float4*>(s_tb + n);
-          float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.has_time) {
-            t4 = *reinterpret_cast<const float4*>(tsum + n);
-            t4.x *= a.t; t4.y *= a.t; t4.z *= a.t; t4.w *= a.t;
-          }
           int pp[4];
-          uint32_t mk[4];
           float4 qv[4], xv[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int rr = r8 + 8 * j;
             pp[j] = w_pix[rr];
-            mk[j] = w_mask[rr];
             qv[j] = *reinterpret_cast<const float4*>(stage + rr * 16 + ((c4 ^ ((rr >> 1) & 3)) << 2));
           }
           if (EPI >= BSDE_EPI_EULER) {
@@ -432,47 +460,27 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (pp[j] < 0) continue;
+            if (pp[j] < 0 || (a.dbg & 4)) continue;
             float4 qq = qv[j];
-            qq.x += b4.x; qq.y += b4.y; qq.z += b4.z; qq.w += b4.w;
-            if (a.has_time) {
-              if (mk[j] == 0xFFFFFFFFu) {
-                qq.x += t4.x; qq.y += t4.y; qq.z += t4.z; qq.w += t4.w;
-              } else {
-                for (int e = 0; e < a.nent; ++e)
-                  if ((mk[j] >> e) & 1) {
-                    const float4 tt = *reinterpret_cast<const float4*>(s_tb + (1 + e) * a.npad + n);
-                    qq.x = fmaf(a.t, tt.x, qq.x); qq.y = fmaf(a.t, tt.y, qq.y); qq.z = fmaf(a.t, tt.z, qq.z); qq.w = fmaf(a.t, tt.w, qq.w);
-                  }
-              }
+            if (EPI >= BSDE_EPI_EULER) {
+              qq.x = wn_combine<EPI, ACT>(qq.x, xv[j].x, a.scale); qq.y = wn_combine<EPI, ACT>(qq.y, xv[j].y, a.scale);
+              qq.z = wn_combine<EPI, ACT>(qq.z, xv[j].z, a.scale); qq.w = wn_combine<EPI, ACT>(qq.w, xv[j].w, a.scale);
             }
-            qq.x = wn_epi<EPI, ACT>(qq.x, xv[j].x, a.scale); qq.y = wn_epi<EPI, ACT>(qq.y, xv[j].y, a.scale);
-            qq.z = wn_epi<EPI, ACT>(qq.z, xv[j].z, a.scale); qq.w = wn_epi<EPI, ACT>(qq.w, xv[j].w, a.scale);
             *reinterpret_cast<float4*>(out + (long long)pp[j] * a.cout + n) = qq;
           }
         } else {
-          // generic tail / scalar path (cout not a multiple of 4, or a partial chunk): rows r8 + 8 j, columns c4 + 4 i
+          // partial chunk / cout not a multiple of 4: rows r8 + 8 j, columns c4 + 4 i
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) {
             const int rr = r8 + 8 * j;
             const int pq = w_pix[rr];
             if (pq < 0) continue;
-            const uint32_t mkk = w_mask[rr];
 #pragma unroll 1
             for (int cc = c4; cc < ncol; cc += 4) {
-              const int n = n0 + cc;
-              float qq = stage[rr * 16 + ((((cc >> 2) ^ ((rr >> 1) & 3)) << 2) | (cc & 3))] + s_tb[n];
-              if (a.has_time) {
-                if (mkk == 0xFFFFFFFFu) {
-                  qq = fmaf(a.t, tsum[n], qq);
-                } else {
-                  for (int e = 0; e < a.nent; ++e)
-                    if ((mkk >> e) & 1) qq = fmaf(a.t, s_tb[(1 + e) * a.npad + n], qq);
-                }
-              }
-              const long long o = (long long)pq * a.cout + n;
+              const float qq = stage[rr * 16 + ((((cc >> 2) ^ ((rr >> 1) & 3)) << 2) | (cc & 3))];
+              const long long o = (long long)pq * a.cout + n0 + cc;
               const float xx = EPI >= BSDE_EPI_EULER ? aux[o] : 0.f;
-              out[o] = wn_epi<EPI, ACT>(qq, xx, a.scale);
+              out[o] = wn_combine<EPI, ACT>(qq, xx, a.scale);
             }
           }
         }
@@ -492,7 +500,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
 struct WinPlan {
   bool ok;
   int mode, NA, NP, nent, Hq, Wq, pitch, IP, lead, trail, NPOSw, nks, npad, ring, slab_bytes, w_bytes, tb_floats;
-  int tab_units, nbuf, tmem_cols, vec, kslab, nslab, pstride;
+  int tab_units, nbuf, tmem_cols, vec, nhalf, hslab, nslab, region, tb_rows;
   size_t smem, img_floats;
   WinEntry ent[WN_MAXENT];
   int ent_tap[WN_MAXENT];
@@ -562,33 +570,28 @@ static WinPlan win_plan(const bsde_conv_layer* L) {
   p.NPOSw = (p.lead + 128 + p.trail + 7) & ~7;  // plane stride = NPOSw*16 B (multiple of 128 B)
   p.nks = (L->cin + 7) / 8;
   p.npad = (L->cout + 15) / 16 * 16;
-  p.pstride = p.NPOSw * 16 + 16;  // +16 B: consecutive chunk planes start 4 banks apart (conflict-free producer writes)
+  p.nhalf = (L->cin + 31) / 32;
+  p.region = p.NPOSw * 128;  // one (plane, 32-channel half) SWIZZLE_128B region; NPOSw % 8 == 0 keeps it 1024-byte aligned
   p.w_bytes = p.nent * p.nks * p.npad * 32;
-  p.tb_floats = (1 + p.nent + p.NA) * p.npad;
+  p.tb_rows = L->has_time ? 1 + 16 * p.NA : 1;
+  p.tb_floats = p.tb_rows * p.npad;
   p.tab_units = p.NP * p.NPOSw;
   p.nbuf = (2 * p.NA * p.npad <= 512) ? 2 : 1;
   if (p.NA * p.npad > 512) return p;
   p.tmem_cols = wn_pow2_cols(p.nbuf * p.NA * p.npad);
-  const size_t fixed = 128 + (size_t)p.w_bytes + (size_t)p.tb_floats * 4 + 128 + WN_EPI_WARPS * 32 * 16 * 4 + (size_t)p.tab_units * 4 +
-                       2 * WN_EPI_WARPS * 32 * 4 + 8 * (2 * WN_MAXRING + 4) + 16 + (size_t)p.nks * p.nent * 8 + 2 * WN_MAXENT * 4;
+  const size_t fixed = 1024 + (size_t)p.w_bytes + (size_t)p.tb_floats * 4 + WN_EPI_WARPS * 32 * 16 * 4 + (size_t)p.tab_units * 4 +
+                       WN_EPI_WARPS * 32 * 4 + 8 * (2 * WN_MAXRING + 4) + 16;
   const size_t cap = 227 * 1024;
-  // k-steps per slab: as many as fit with a ring of >= 2 slabs (>= 3 when a tile needs several slabs), so that a
-  // warp-level cp.async covers whole 128-byte lines (4 k-steps = 32 channels) instead of 32-byte sectors
-  p.kslab = 0;
-  const int cands[5] = {p.nks, 8, 4, 2, 1};
-  for (int ci = 0; ci < 5 && !p.kslab; ++ci) {
+  // slab = all 32-channel halves of a tile's window (ring >= 2), else one half per slab (ring >= 2)
+  p.hslab = 0;
+  const int cands[2] = {p.nhalf, 1};
+  for (int ci = 0; ci < 2 && !p.hslab; ++ci) {
     const int k = cands[ci];
-    if (k > p.nks || k < 1) continue;
-    if (!p.vec && k != 1) continue;
-    const size_t slab = (size_t)p.NP * k * 2 * p.pstride;
-    const int need = (k >= p.nks) ? 2 : (k >= 4 ? 2 : 3);
-    if (fixed + need * slab <= cap) { p.kslab = k; p.slab_bytes = (int)slab; }
+    const size_t slab = (size_t)p.NP * k * p.region;
+    if (fixed + 2 * slab <= cap) { p.hslab = k; p.slab_bytes = (int)slab; }
   }
-  if (!p.kslab) return p;
-  // 8-channel slabs make every lane of a cp.async touch its own 128-byte line (measured ~3 B/cycle/SM): leave such
-  // shapes (stride-2 layers with 64x64 weights resident) to the per-tap gather kernel of tconv_tc.cu
-  if (p.vec && p.kslab < 4 && p.nks >= 4) return p;
-  p.nslab = (p.nks + p.kslab - 1) / p.kslab;
+  if (!p.hslab) return p;
+  p.nslab = (p.nhalf + p.hslab - 1) / p.hslab;
   p.ring = (int)std::min<size_t>(WN_MAXRING, (cap - fixed) / p.slab_bytes);
   p.ring = std::min(p.ring, std::max(2, 3 * p.nslab));
   p.smem = fixed + (size_t)p.ring * p.slab_bytes;
@@ -607,7 +610,7 @@ bool tconv_win_supported(const bsde_conv_layer* L, int S, int B) {
   WinPlan p = win_plan(L);
   if (!p.ok) return false;
   // 32-bit position / offset arithmetic inside the kernel
-  if ((long long)B * p.IP + 1024 > 0x7FFFFFFFLL) return false;
+  if ((long long)B * p.IP + 1024 > (1LL << 24)) return false;  // fp32-reciprocal position decode is exact below 2^24
   if ((long long)B * L->hin * L->win * L->cin > 0x7FFFFFFFLL) return false;
   if ((long long)B * L->hout * L->wout * L->cout > 0x7FFFFFFFLL) return false;
   return true;
@@ -637,7 +640,11 @@ int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const
     r.real_base = (L->has_time && L->time_first) ? 1 : 0; r.has_time = L->has_time;
     r.time_row = L->time_first ? 0 : L->cin; r.use_bias = epi <= BSDE_EPI_EULER; r.w_floats = p.w_bytes / 4;
     r.w_off = L->w_off; r.b_off = L->b_off; r.ts = L->w_tap_stride; r.ks = L->w_k_stride; r.ns = L->w_n_stride;
-    for (int e = 0; e < p.nent; ++e) { r.ent_tap[e] = p.ent_tap[e]; r.ent_acc[e] = p.ent[e].acc; }
+    r.tb_rows = p.tb_rows; r.mode = p.mode; r.Hq = p.Hq; r.Wq = p.Wq; r.hin = L->hin; r.win = L->win;
+    r.sn = L->sn; r.kn = L->kn; r.off = L->off; r.sd = L->sd;
+    for (int e = 0; e < p.nent; ++e) {
+      r.ent_tap[e] = p.ent_tap[e]; r.ent_acc[e] = p.ent[e].acc; r.ent_kh[e] = p.ent[e].kh; r.ent_kw[e] = p.ent[e].kw;
+    }
     win_repack_kernel<<<dim3(p.nent * p.nks + 1, S), 256, 0, st>>>(r);
     BSDE_CUDA_OK(cudaGetLastError());
     count_launch();
@@ -650,15 +657,22 @@ int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const
   a.Q = B * p.IP;
   a.ntiles = (a.Q + 127) / 128;
   a.G = std::min(a.G, a.ntiles);
-  a.cin = L->cin; a.cout = L->cout; a.npad = p.npad; a.nks = p.nks;
+  a.cin = L->cin; a.cout = L->cout; a.npad = p.npad; a.nks = p.nks; a.nhalf = p.nhalf;
   a.hin = L->hin; a.win = L->win; a.hout = L->hout; a.wout = L->wout;
   a.sn = L->sn; a.kn = L->kn; a.off = L->off; a.sd = L->sd; a.has_time = L->has_time; a.mode = p.mode;
   a.Hq = p.Hq; a.Wq = p.Wq; a.pitch = p.pitch; a.IP = p.IP; a.lead = p.lead; a.NPOSw = p.NPOSw; a.NP = p.NP; a.NA = p.NA;
   a.nent = p.nent; a.ring = p.ring; a.slab_bytes = p.slab_bytes; a.w_bytes = p.w_bytes; a.tb_floats = p.tb_floats;
-  a.tab_units = p.tab_units; a.nbuf = p.nbuf; a.tmem_cols = p.tmem_cols;
-  a.kslab = p.kslab; a.nslab = p.nslab; a.pstride = p.pstride;
-  a.t = t; a.scale = scale; a.act = act; a.epi = epi;
-  for (int e = 0; e < p.nent; ++e) a.ent[e] = p.ent[e];
+  a.nbuf = p.nbuf; a.tmem_cols = p.tmem_cols;
+  a.hslab = p.hslab; a.nslab = p.nslab; a.region = p.region;
+  a.t = t; a.scale = scale;
+  { static const int dbg = getenv("BSDE_WIN_DBG") ? atoi(getenv("BSDE_WIN_DBG")) : 0; a.dbg = dbg; }
+  for (int e = 0; e < p.nent; ++e) {
+    a.ent[e] = p.ent[e];
+    a.aoff[e] = ((uint32_t)(p.ent[e].plane * p.hslab) * (uint32_t)p.region + (uint32_t)((p.lead + p.ent[e].shift) * 128)) >> 4;
+    bool first = true;
+    for (int f = 0; f < e; ++f) first &= p.ent[f].acc != p.ent[e].acc;
+    a.dcol[e] = (uint32_t)(p.ent[e].acc * p.npad) | (first ? 0x80000000u : 0u);
+  }
   // one instantiation per (producer path, epilogue, activation); activation only matters for BIAS_ACT / DACT
   using KernelFn = void (*)(const WinArgs);
   KernelFn fn = nullptr;
