@@ -48,14 +48,23 @@ size_t tconv_wgrad_ws_tc(const bsde_conv_layer* L, int S, int B);
 int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
                    float* gw, long long gw_sample_stride, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// window-staged tensor-core weight gradient (wgrad_win.cu)
+bool tconv_wgrad_win_supported(const bsde_conv_layer* L, int S, int B);
+size_t tconv_wgrad_ws_win(const bsde_conv_layer* L, int S, int B);
+int tconv_wgrad_win(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
+                    float* gw, long long gw_sample_stride, void* ws, size_t ws_bytes, cudaStream_t st);
+
 static size_t wgrad_ws(const bsde_conv_layer* L, int S, int B, int math) {
   size_t b = tconv_wgrad_ws_simt(L, S, B);
+  if (math == BSDE_MATH_TC) b = std::max(b, tconv_wgrad_ws_win(L, S, B));
   if (math == BSDE_MATH_TC && tconv_wgrad_tc_supported(L, S, B)) b = std::max(b, tconv_wgrad_ws_tc(L, S, B));
   return b;
 }
 
 static int conv_wgrad(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
                       float* gw, long long gss, int math, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (math == BSDE_MATH_TC && tconv_wgrad_win_supported(L, S, B))
+    return tconv_wgrad_win(L, S, B, in, dy, t, scale, gw, gss, ws, ws_bytes, st);
   if (math == BSDE_MATH_TC && tconv_wgrad_tc_supported(L, S, B))
     return tconv_wgrad_tc(L, S, B, in, dy, t, scale, gw, gss, ws, ws_bytes, st);
   return tconv_wgrad_simt(L, S, B, in, dy, t, scale, gw, gss, ws, ws_bytes, st);

@@ -101,6 +101,7 @@ struct WreduceArgs {
   int S, splits, rows, cols, Kc, Ktot, has_time, time_row, real_base, swapped, cin, cout;
   long long w_off, b_off, ts, ks, ns;
   float scale;
+  int nbias;  // bias partial rows Ktot .. Ktot+nbias-1 are summed (0 means 1)
 };
 int launch_wgrad_reduce(const WreduceArgs& a, int blocks, cudaStream_t st);
 

@@ -9,6 +9,8 @@
 // The same gather kernel evaluates forward convs (stride 1/2, SAME, lhs-dilated "transposed") and
 // every data gradient, by the per-axis map   num = o*sn + k*kn + off,  i = num/sd  (see bsde.h).
 // fp32 FMA accumulation: this is the bit-faithful path; BSDE_MATH_TC is the tensor-core path.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace bsde {
@@ -378,7 +380,13 @@ __global__ void wgrad_reduce_kernel(WreduceArgs a) {
     v *= a.scale;
     float* g = a.gw + s * a.gw_sample_stride;
     if (!a.swapped) {
+      if (row > a.Ktot) continue;  // extra bias rows are folded into row Ktot below
       if (row == a.Ktot) {
+        for (int b = 1; b < a.nbias; ++b) {
+          float vb = 0.f;
+          for (int q = 0; q < a.splits; ++q) vb += p[q * per + (long long)b * a.cols];
+          v += vb * a.scale;
+        }
         if (a.b_off >= 0) g[a.b_off + col] = v;
       } else {
         const int tap = row / a.Kc, c = row - tap * a.Kc;
@@ -544,6 +552,7 @@ int tconv_wgrad_simt(const bsde_conv_layer* L, int S, int B, const float* in, co
     count_launch();
   }
   WreduceArgs r;
+  memset(&r, 0, sizeof(r));
   r.partial = (const float*)ws; r.bias_partial = bias_partial; r.gw = gw; r.gw_sample_stride = gw_sample_stride;
   r.S = S; r.splits = p.splits; r.rows = p.rows; r.cols = p.cols; r.Kc = a.Kc; r.Ktot = a.Ktot;
   r.has_time = L->has_time; r.time_row = L->time_first ? 0 : L->cin;

@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace bsde {
 
@@ -532,23 +533,27 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(TcArgs a) {
     }
   } else {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // whole warp, uniform operands, one elected lane issues (no per-MMA R2UR waterfall)
+    {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.npad >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint64_t hi = um::desc_hi(16u, 1024u, 2);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
 #pragma unroll 1
       for (int kb = 0; kb < NKB; ++kb) {
         const int st = kb % TC_STAGES;
         mbar_wait(full_bar(st), (kb / TC_STAGES) & 1);
         tc_fence_after();
-        const uint32_t sA = base + st * stage_bytes;
-        const uint64_t adesc = make_desc_k_sw128(sA);
-        const uint64_t bdesc = make_desc_k_sw128(sA + TC_A_BYTES);
-        if (!(a.dbg & 4))
+        const uint32_t sA16 = (base + st * stage_bytes) >> 4;
+        const uint32_t sB16 = sA16 + (TC_A_BYTES >> 4);
+        if (!(a.dbg & 4)) {
 #pragma unroll
-        for (int k = 0; k < TC_KB / 8; ++k)
-          umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-        umma_commit(empty_bar(st));
+          for (int k = 0; k < TC_KB / 8; ++k)
+            um::umma_tf32_elect(tm, hi | (uint64_t)((sA16 + (uint32_t)(k * 2)) & 0x3FFFu), hi | (uint64_t)((sB16 + (uint32_t)(k * 2)) & 0x3FFFu),
+                                idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        um::umma_commit_elect(empty_bar(st));
       }
-      umma_commit(tmem_full_bar);
+      um::umma_commit_elect(tmem_full_bar);
     }
     TC_STAMP(3);
     __syncwarp();

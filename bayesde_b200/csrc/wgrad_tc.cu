@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace bsde {
 
@@ -267,41 +268,32 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgTcArgs a) {
     }
   } else {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // whole warp, uniform operands (kernel parameters + loop counters), one elected lane issues
+    {
       // TF32 x TF32 -> F32, both operands MN-major, M=128, N=npad
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(a.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      long long m_wait = 0, m_issue = 0;
-      const bool dbgm = g_wg_dbg && blockIdx.x == 0;
+      const uint64_t hi = um::desc_hi(WG_REGION, 512u, 1);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
 #pragma unroll 1
       for (int kb = 0; kb < NKB; ++kb) {
         const int st = kb % a.stages;
-        long long c0 = dbgm ? clock64() : 0;
         wg_mbar_wait(full_bar(st), (kb / a.stages) & 1);
-        long long c1 = dbgm ? clock64() : 0;
-        m_wait += c1 - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sA = base + st * stage_bytes;
-        const uint32_t sB = sA + a_bytes;
+        const uint32_t sA16 = (base + st * stage_bytes) >> 4;
+        const uint32_t sB16 = sA16 + ((uint32_t)a_bytes >> 4);
 #pragma unroll 1
         for (int i = 0; i < ((a.dbg & 2) ? 0 : a.nmma); ++i) {
 #pragma unroll
           for (int j = 0; j < WG_KP / 8; ++j) {
-            const uint64_t ad = wg_desc_mn_sw128(sA + (uint32_t)(4 * i) * WG_REGION + (uint32_t)j * 1024u, WG_REGION);
-            const uint64_t bd = wg_desc_mn_sw128(sB + (uint32_t)j * 1024u, WG_REGION);
-            const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_base + (uint32_t)(i * a.npad)),
-                "l"(ad), "l"(bd), "r"(idesc), "r"(acc)
-                : "memory");
+            const uint64_t ad = hi | (uint64_t)((sA16 + (uint32_t)(4 * i) * (WG_REGION >> 4) + (uint32_t)j * 64u) & 0x3FFFu);
+            const uint64_t bd = hi | (uint64_t)((sB16 + (uint32_t)j * 64u) & 0x3FFFu);
+            um::umma_tf32_elect(tm + (uint32_t)(i * a.npad), ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
           }
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty_bar(st)) : "memory");
-        if (dbgm) m_issue += clock64() - c1;
+        um::umma_commit_elect(empty_bar(st));
       }
-      if (dbgm) { g_wg_dbg[3] = m_wait; g_wg_dbg[4] = m_issue; }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tmem_full_bar) : "memory");
+      um::umma_commit_elect(tmem_full_bar);
     }
     __syncwarp();
   }

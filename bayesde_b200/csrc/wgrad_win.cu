@@ -1,0 +1,502 @@
+// K3 weight gradient, window-staged (tcgen05 kind::tf32, fp32 accumulation in TMEM).
+//
+//   G[tap][ci][co] = sum over positions q of  in(q + s_tap)[ci] * dY(q)[co]
+//
+// on the flattened, zero-padded position grid of tconv_win.cu (one pad column per row, one pad row per
+// image: a neighbour that would wrap around lands on a pad, which both operands hold as zeros).  The
+// reduction index is the POSITION, so both operands are MN-major exactly as NHWC memory has them: one
+// position = one 128-byte row per 32-channel block, SWIZZLE_128B_BASE32B.  Every tap uses the SAME staged
+// rows; only the start address of the shifted operand's descriptor moves (tools/umma_probe2.cu, test T_C):
+//
+//   D_e[m][n] += sum_k  U_{up(e)}(q_k)[m] * V_{vp(e)}(q_k + sh(e))[n]          one MMA (M=128, K=8) per k-step
+//
+//   U = unshifted operand on the M side (128 accumulator rows), V = shifted operand on the N side.
+//     forward stride 1 : U = input (+ ones), V = dY shifted by -s_tap;  when cin + 1 <= 32 instead
+//                        U = dY, V = input (+ ones) shifted by +s_tap
+//     forward stride 2 : U = the four input parity planes (+ ones), V = dY shifted by -s
+//     lhs-dilated fwd  : U = input (+ ones), V = the four dY parity classes shifted by -s
+//   "ones" is an extra channel that is 1 at valid positions: its accumulator row/column is the tap-masked
+//   column sum of dY, i.e. the time-channel row (times t) and, for the always-valid tap, the bias row.
+//   When the shifted operand has <= 32 channels its three horizontally adjacent taps are consecutive rows of the
+//   same region, so ONE MMA with N = 96 and LBO = 128 B covers them ("packed": 3 MMAs per k-step, not 9).
+// CTAs split the positions of a sample (and, when 9 accumulators exceed the 512 TMEM columns, the taps);
+// partial tiles go to the workspace in the layout of wgrad_reduce_kernel (tconv_simt.cu), which finishes
+// in a fixed order (no atomics: run-to-run deterministic).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace bsde {
+
+using namespace um;
+
+constexpr int WW_PROD_WARPS = 8;
+constexpr int WW_PROD = WW_PROD_WARPS * 32;  // warps 0-7 producers (warps 0-3 also run the epilogue)
+constexpr int WW_MMA_WARP = WW_PROD_WARPS;
+constexpr int WW_THREADS = (WW_PROD_WARPS + 1) * 32;
+constexpr int WW_MAXENT = 9;
+constexpr int WW_MAXSTAGES = 4;
+
+struct WwArgs {
+  const float* U;
+  const float* V;
+  float* partial;
+  int S, B, Hq, Wq, pitch, IP, Q;
+  int cu, cv, u_ones, v_ones;     // real channels; append a ones channel at index cu / cv
+  int nbU, nbV, NPU, NPV;         // 32-channel blocks, parity planes of each operand
+  int hU, wU, hV, wV;             // spatial extent of the tensors behind U and V
+  int KS, NPOSw, lead, regU, regV, stage_bytes, v_off, nstages;  // rows per stage, V window rows, region bytes
+  int SPL, TG, chunk;             // position splits, tap groups, positions per split (multiple of KS)
+  int Nmma;                       // N of every MMA
+  uint32_t lboB;                  // LBO of the B descriptor: regV (channel blocks) or 128 (packed taps)
+  int tmem_cols;
+  // per tap group: entries
+  int ncnt[2];
+  uint32_t aoff[2][WW_MAXENT];    // A start (16-byte units) relative to the stage base: U plane
+  uint32_t boff[2][WW_MAXENT];    // B start relative to the stage base: V plane + (lead + shift) rows
+  int tapj[2][WW_MAXENT][3];      // weight tap of N-block j (packed) or of the entry ([0])
+  int bias_row[2][WW_MAXENT][3];  // >= 0: this (entry, block)'s ones sum is bias partial row Ktot + bias_row
+  int packed, u_is_input;
+  int cin, cout, Kc, Ktot, has_time, rows, cols;
+  float t;
+};
+
+// position -> source pixel offset (floats) inside one sample, or -1
+__device__ __forceinline__ int ww_src(int q, int Q, int IP, int pitch, int Hq, int Wq, float rIP, float rpitch, int np, int plane,
+                                      int h, int w, int c) {
+  if (q < 0 || q >= Q) return -1;
+  int img = (int)((float)q * rIP);
+  int r = q - img * IP;
+  if (r < 0) { --img; r += IP; } else if (r >= IP) { ++img; r -= IP; }
+  int y = (int)((float)r * rpitch);
+  int x = r - y * pitch;
+  if (x < 0) { --y; x += pitch; } else if (x >= pitch) { ++y; x -= pitch; }
+  if (y >= Hq || x >= Wq) return -1;
+  if (np == 4) { y = 2 * y + (plane >> 1); x = 2 * x + (plane & 1); }
+  if (y >= h || x >= w) return -1;
+  return ((img * h + y) * w + x) * c;
+}
+
+__global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_constant__ WwArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s = blockIdx.x / (a.TG * a.SPL);
+  const int rem = blockIdx.x - s * a.TG * a.SPL;
+  const int tg = rem / a.SPL, split = rem - tg * a.SPL;
+  const int qbeg = split * a.chunk, qend = min(a.Q, qbeg + a.chunk);
+  const int nst = qend > qbeg ? (qend - qbeg + a.KS - 1) / a.KS : 0;
+
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const int ring_bytes = a.nstages * a.stage_bytes;
+  int* s_tabU = reinterpret_cast<int*>(gen + ring_bytes);                      // [NPU][KS]
+  int* s_tabV = s_tabU + a.NPU * a.KS;                                          // [NPV][NPOSw]
+  const uint32_t bars = base + ring_bytes + (a.NPU * a.KS + a.NPV * a.NPOSw) * 4;  // full[4], empty[4], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + ring_bytes + (a.NPU * a.KS + a.NPV * a.NPOSw) * 4 + 8 * 9);
+  auto full_bar = [&](int st) { return bars + 8u * st; };
+  auto empty_bar = [&](int st) { return bars + 8u * (4 + st); };
+  const uint32_t done_bar = bars + 8u * 8;
+
+  // zero both stages once: padded channels / unused blocks are never written by the producers
+  for (int i = tid; i < ring_bytes >> 4; i += WW_THREADS) reinterpret_cast<uint4*>(gen)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == WW_MMA_WARP) {
+    if (lane == 0) {
+      for (int i = 0; i < a.nstages; ++i) { mbar_init(full_bar(i), WW_PROD); mbar_init(empty_bar(i), 1); }
+      mbar_init(done_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < WW_PROD_WARPS) {
+    // =============================== producers ===============================
+    const float* __restrict__ U = a.U + (long long)s * a.B * a.hU * a.wU * a.cu;
+    const float* __restrict__ V = a.V + (long long)s * a.B * a.hV * a.wV * a.cv;
+    const float rIP = 1.0f / (float)a.IP, rpitch = 1.0f / (float)a.pitch;
+    const int c = tid & 7, r0 = tid >> 3;  // chunk of the 128-byte row; rows r0 + 32 k
+    const bool uvec = (a.cu & 3) == 0, vvec = (a.cv & 3) == 0;
+#pragma unroll 1
+    for (int it = 0; it < nst; ++it) {
+      const int st = it % a.nstages;
+      const int q0 = qbeg + it * a.KS;
+      // source tables of this stage (shared by the producer threads)
+      asm volatile("bar.sync 1, %0;" ::"n"(WW_PROD) : "memory");
+      for (int i = tid; i < a.KS; i += WW_PROD) {
+        const int q = q0 + i;
+        for (int p = 0; p < a.NPU; ++p)
+          s_tabU[p * a.KS + i] = q < qend ? ww_src(q, a.Q, a.IP, a.pitch, a.Hq, a.Wq, rIP, rpitch, a.NPU, p, a.hU, a.wU, a.cu) : -1;
+      }
+      for (int i = tid; i < a.NPOSw; i += WW_PROD) {
+        const int q = q0 - a.lead + i;
+        for (int p = 0; p < a.NPV; ++p)
+          s_tabV[p * a.NPOSw + i] = ww_src(q, a.Q, a.IP, a.pitch, a.Hq, a.Wq, rIP, rpitch, a.NPV, p, a.hV, a.wV, a.cv);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(WW_PROD) : "memory");
+      if (it >= a.nstages) mbar_wait(empty_bar(st), ((it / a.nstages) & 1) ^ 1);
+      const uint32_t sb = base + st * a.stage_bytes;
+      uint8_t* gb = gen + st * a.stage_bytes;
+      // ---- U rows: [plane][block][KS rows][128 B], granule g of row r at g ^ (r & 3)
+#pragma unroll 1
+      for (int p = 0; p < a.NPU; ++p) {
+#pragma unroll 1
+        for (int b = 0; b < a.nbU; ++b) {
+          const uint32_t reg = (uint32_t)((p * a.nbU + b) * a.regU);
+          const int ch = b * 32 + c * 4;
+          for (int r = r0; r < a.KS; r += WW_PROD / 8) {
+            const int src = s_tabU[p * a.KS + r];
+            const uint32_t d = reg + r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));
+            if (uvec) {
+              if (ch < a.cu) cp_async16(sb + d, src >= 0 ? U + src + ch : U, src >= 0);
+            } else {
+              for (int e = 0; e < 4; ++e)
+                if (ch + e < a.cu) cp_async4(sb + d + e * 4, src >= 0 ? U + src + ch + e : U, src >= 0);
+            }
+            if (a.u_ones && a.cu >= ch && a.cu < ch + 4)
+              *reinterpret_cast<float*>(gb + d + (a.cu - ch) * 4) = src >= 0 ? 1.f : 0.f;
+          }
+        }
+      }
+      // ---- V window rows: [plane][block][NPOSw rows][128 B]
+#pragma unroll 1
+      for (int p = 0; p < a.NPV; ++p) {
+#pragma unroll 1
+        for (int b = 0; b < a.nbV; ++b) {
+          const uint32_t reg = (uint32_t)a.v_off + (uint32_t)((p * a.nbV + b) * a.regV);
+          const int ch = b * 32 + c * 4;
+          for (int r = r0; r < a.NPOSw; r += WW_PROD / 8) {
+            const int src = s_tabV[p * a.NPOSw + r];
+            const uint32_t d = reg + r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));
+            if (vvec) {
+              if (ch < a.cv) cp_async16(sb + d, src >= 0 ? V + src + ch : V, src >= 0);
+            } else {
+              for (int e = 0; e < 4; ++e)
+                if (ch + e < a.cv) cp_async4(sb + d + e * 4, src >= 0 ? V + src + ch + e : V, src >= 0);
+            }
+            if (a.v_ones && a.cv >= ch && a.cv < ch + 4)
+              *reinterpret_cast<float*>(gb + d + (a.cv - ch) * 4) = src >= 0 ? 1.f : 0.f;
+          }
+        }
+      }
+      fence_proxy_async();  // the generic "ones" stores must be visible to the tensor core's async proxy
+      cp_async_arrive_noinc(full_bar(st));
+    }
+
+    // =============================== epilogue (warps 0-3) ===============================
+    if (warp < 4) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      float* __restrict__ part = a.partial + ((long long)(s * a.SPL + split) * a.rows) * a.cols;
+      const int m = warp * 32 + lane;  // accumulator row = U channel
+#pragma unroll 1
+      for (int e = 0; e < a.ncnt[tg]; ++e) {
+#pragma unroll 1
+        for (int n0 = 0; n0 < a.Nmma; n0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(e * a.Nmma + n0), v);
+          if (nst == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0u;  // this split had no positions: its tile is all zeros
+          }
+          const int blk = a.packed ? n0 >> 5 : 0;
+          const int tap = a.tapj[tg][e][blk];
+          const int brow = a.bias_row[tg][e][blk];
+          if (tap < 0) continue;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = a.packed ? ((n0 & 31) + j) : (n0 + j);  // V channel
+            const float val = __uint_as_float(v[j]);
+            if (a.u_is_input) {
+              // m = input channel (cin = ones), n = output channel
+              if (n >= a.cout) continue;
+              if (m < a.cin) {
+                part[(long long)(tap * a.Kc + m) * a.cols + n] = val;
+              } else if (m == a.cin) {
+                if (a.has_time) part[(long long)(tap * a.Kc + a.cin) * a.cols + n] = a.t * val;
+                if (brow >= 0) part[(long long)(a.Ktot + brow) * a.cols + n] = val;
+              }
+            } else {
+              // m = output channel, n = input channel (cin = ones)
+              if (m >= a.cout) continue;
+              if (n < a.cin) {
+                part[(long long)(tap * a.Kc + n) * a.cols + m] = val;
+              } else if (n == a.cin) {
+                if (a.has_time) part[(long long)(tap * a.Kc + a.cin) * a.cols + m] = a.t * val;
+                if (brow >= 0) part[(long long)(a.Ktot + brow) * a.cols + m] = val;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== MMA issuer ===============================
+    // whole warp, uniform operands, one elected lane issues
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(a.Nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t a_hi = desc_hi((uint32_t)a.regU, 512u, 1);
+    const uint64_t b_hi = desc_hi(a.lboB, 512u, 1);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int ncnt = a.ncnt[tg];
+#pragma unroll 1
+    for (int it = 0; it < nst; ++it) {
+      const int st = it % a.nstages;
+      mbar_wait(full_bar(st), (it / a.nstages) & 1);
+      fence_proxy_async();
+      tc_fence_after();
+      const uint32_t sb16 = (base + st * a.stage_bytes) >> 4;
+#pragma unroll 1
+      for (int ks = 0; ks < a.KS / 8; ++ks) {
+        const uint32_t kofs = (uint32_t)ks * 64u;  // 8 rows x 128 B
+        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+#pragma unroll 1
+        for (int e = 0; e < ncnt; ++e) {
+          const uint64_t ad = a_hi | (uint64_t)((sb16 + a.aoff[tg][e] + kofs) & 0x3FFFu);
+          const uint64_t bd = b_hi | (uint64_t)((sb16 + a.boff[tg][e] + kofs) & 0x3FFFu);
+          umma_tf32_elect(tm + (uint32_t)(e * a.Nmma), ad, bd, idesc, acc);
+        }
+      }
+      umma_commit_elect(empty_bar(st));
+    }
+    umma_commit_elect(done_bar);
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WW_MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+struct WwPlan {
+  bool ok;
+  WwArgs a;
+  size_t smem, part_floats;
+  int nbias;
+};
+
+static int ww_pow2_cols(int c) { int p = 32; while (p < c) p <<= 1; return p; }
+
+static bool ww_enabled() {
+  static const int on = [] { const char* e = getenv("BSDE_WGWIN"); return e ? atoi(e) : 1; }();
+  return on != 0;
+}
+
+static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
+  WwPlan p;
+  memset(&p, 0, sizeof(p));
+  WwArgs& a = p.a;
+  if (!ww_enabled() || !L || L->ksize != 3 || S < 1 || B < 1 || S > 74) return p;
+  int mode;
+  if (L->sd == 1 && L->sn == 1) mode = 1;
+  else if (L->sd == 1 && L->sn == 2) mode = 2;
+  else if (L->sd == 2 && L->sn == 1) mode = 3;
+  else return p;
+  if (mode == 1 && (L->hin != L->hout || L->win != L->wout)) return p;
+  if (mode == 2 && ((L->hin + 1) / 2 != L->hout || (L->win + 1) / 2 != L->wout)) return p;
+  if (mode == 3 && (L->hout != 2 * L->hin || L->wout != 2 * L->win)) return p;
+  if (mode == 2 && L->hout > 4) return p;  // measured slower than wgrad_tc.cu: 4 parity planes x 3 blocks leave only
+  if (mode == 3 && L->hin > 8) return p;   // 32-position stages, which cannot hide the load latency
+  a.Hq = mode == 3 ? L->hin : L->hout;
+  a.Wq = mode == 3 ? L->win : L->wout;
+  a.pitch = a.Wq + 1;
+  a.IP = (a.Hq + 1) * a.pitch;
+  a.S = S; a.B = B;
+  a.Q = B * a.IP;
+  if ((long long)B * a.IP + 4096 > (1LL << 24)) return p;
+  if ((long long)B * L->hin * L->win * L->cin > 0x7FFFFFFFLL || (long long)B * L->hout * L->wout * L->cout > 0x7FFFFFFFLL) return p;
+  a.cin = L->cin; a.cout = L->cout; a.has_time = L->has_time;
+  a.Kc = L->cin + (L->has_time ? 1 : 0);
+  a.Ktot = 9 * a.Kc;
+  a.cols = L->cout;
+
+  // taps: displacement in position space, operand planes
+  struct Tap { int tap, kh, kw, sy, sx, plane, cls; } taps[9];
+  int nt = 0;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      const int th = kh * L->kn + L->off, tw = kw * L->kn + L->off;
+      Tap& t = taps[nt];
+      t.tap = kh * 3 + kw; t.kh = kh; t.kw = kw; t.plane = 0; t.cls = 0;
+      if (mode == 1) { t.sy = th; t.sx = tw; }
+      else if (mode == 2) { const int py = th & 1, px = tw & 1; t.sy = (th - py) / 2; t.sx = (tw - px) / 2; t.plane = py * 2 + px; }
+      else {
+        // the (unique) output parity class of this tap: (po + t) even
+        const int poh = th & 1, pow_ = tw & 1;
+        t.cls = poh * 2 + pow_; t.sy = (poh + th) / 2; t.sx = (pow_ + tw) / 2;
+      }
+      if (abs(t.sy) > 1 || abs(t.sx) > 1) return p;
+      ++nt;
+    }
+
+  // operand roles
+  const bool v_is_input = mode == 1 && L->cin + 1 <= 32;  // packed input taps on the N side
+  a.u_is_input = !v_is_input;
+  if (a.u_is_input) {
+    a.cu = L->cin; a.u_ones = 1; a.cv = L->cout; a.v_ones = 0;
+    a.hU = L->hin; a.wU = L->win; a.hV = L->hout; a.wV = L->wout;
+    a.NPU = mode == 2 ? 4 : 1; a.NPV = mode == 3 ? 4 : 1;
+  } else {
+    a.cu = L->cout; a.u_ones = 0; a.cv = L->cin; a.v_ones = 1;
+    a.hU = L->hout; a.wU = L->wout; a.hV = L->hin; a.wV = L->win;
+    a.NPU = 1; a.NPV = 1;
+  }
+  if (a.cu + a.u_ones > 128) return p;
+  a.nbU = (a.cu + a.u_ones + 31) / 32;
+  a.nbV = (a.cv + a.v_ones + 31) / 32;
+  a.packed = (mode == 1 && a.cv + a.v_ones <= 32) ? 1 : 0;
+  a.Nmma = a.packed ? 96 : (a.cv + a.v_ones + 15) / 16 * 16;
+  if (a.Nmma > 256) return p;
+
+  // entries: (U plane, V plane, shift of V)
+  struct Ent { int up, vp, sh, tapj[3], brow[3]; } ents[9];
+  int ne = 0, mins = 0, maxs = 0;
+  p.nbias = mode == 3 ? 4 : 1;
+  bool have_bias[4] = {false, false, false, false};
+  if (a.packed) {
+    for (int kh = 0; kh < 3; ++kh) {
+      // the three taps of this kernel row: consecutive positions; the MMA's N-block j reads shift base + j
+      Ent& e = ents[ne];
+      e.up = 0; e.vp = 0;
+      int base_sh = 1 << 30;
+      for (int i = 0; i < 9; ++i)
+        if (taps[i].kh == kh) {
+          const int sh = (taps[i].sy * a.pitch + taps[i].sx) * (a.u_is_input ? -1 : 1);
+          base_sh = std::min(base_sh, sh);
+        }
+      e.sh = base_sh;
+      for (int j = 0; j < 3; ++j) { e.tapj[j] = -1; e.brow[j] = -1; }
+      for (int i = 0; i < 9; ++i)
+        if (taps[i].kh == kh) {
+          const int sh = (taps[i].sy * a.pitch + taps[i].sx) * (a.u_is_input ? -1 : 1);
+          const int j = sh - base_sh;
+          if (j < 0 || j > 2) return p;
+          e.tapj[j] = taps[i].tap;
+          if (taps[i].sy == 0 && taps[i].sx == 0) { e.brow[j] = 0; have_bias[0] = true; }
+        }
+      mins = std::min(mins, e.sh); maxs = std::max(maxs, e.sh + 2);
+      ++ne;
+    }
+  } else {
+    for (int i = 0; i < 9; ++i) {
+      Ent& e = ents[ne];
+      e.up = mode == 2 ? taps[i].plane : 0;
+      e.vp = mode == 3 ? taps[i].cls : 0;
+      e.sh = -(taps[i].sy * a.pitch + taps[i].sx);
+      e.tapj[0] = taps[i].tap; e.tapj[1] = e.tapj[2] = -1;
+      e.brow[0] = e.brow[1] = e.brow[2] = -1;
+      // bias = sum of dY over all positions: the zero-displacement tap of each class reads an always-valid source
+      const bool always = taps[i].sy == 0 && taps[i].sx == 0 && (mode != 2 || taps[i].plane == 0);
+      const int bc = mode == 3 ? taps[i].cls : 0;
+      if (always && !have_bias[bc]) { e.brow[0] = bc; have_bias[bc] = true; }
+      mins = std::min(mins, e.sh); maxs = std::max(maxs, e.sh);
+      ++ne;
+    }
+  }
+  for (int b = 0; b < p.nbias; ++b)
+    if (!have_bias[b]) return p;
+  a.rows = a.Ktot + p.nbias;
+  a.lead = -mins;
+  const int trail = maxs;
+
+  // tap groups: accumulators of one CTA must fit 512 TMEM columns
+  a.TG = (ne * a.Nmma + 511) / 512;
+  if (a.TG > 2) return p;
+  const int per = (ne + a.TG - 1) / a.TG;
+  a.tmem_cols = ww_pow2_cols(per * a.Nmma);
+  if (a.tmem_cols > 512) return p;
+
+  // stage size and ring depth: prefer >= 3 stages in flight (latency hiding), then the largest KS
+  const size_t cap = 227 * 1024 - 2048;
+  a.KS = 0;
+  for (int want = 3; want >= 2 && !a.KS; --want)
+    for (int ks : {128, 64, 32, 16}) {
+      const int nposw = (a.lead + ks + trail + 7) & ~7;
+      // an M=128 MMA always reads four 32-channel blocks `regU` apart: when U has fewer, the surplus blocks must
+      // still fall inside the stage (their accumulator rows are ignored), so the stage is padded if V is short
+      size_t st = (size_t)a.NPU * a.nbU * ks * 128 + (size_t)a.NPV * a.nbV * nposw * 128;
+      st = std::max(st, ((size_t)(a.NPU - 1) * a.nbU + 4) * ks * 128);
+      const size_t tabs = ((size_t)a.NPU * ks + (size_t)a.NPV * nposw) * 4;
+      if (want * st + tabs + 128 <= cap) {
+        a.KS = ks; a.NPOSw = nposw; a.stage_bytes = (int)st;
+        a.nstages = (int)std::min<size_t>(WW_MAXSTAGES, (cap - tabs - 128) / st);
+        break;
+      }
+    }
+  if (!a.KS) return p;
+  a.regU = a.KS * 128;
+  a.regV = a.NPOSw * 128;
+  a.v_off = a.NPU * a.nbU * a.regU;
+  a.lboB = a.packed ? 128u : (uint32_t)a.regV;
+  p.smem = 1024 + (size_t)a.nstages * a.stage_bytes + ((size_t)a.NPU * a.KS + (size_t)a.NPV * a.NPOSw) * 4 + 128;
+
+  a.SPL = std::max(1, 148 / (S * a.TG));
+  a.chunk = (a.Q + a.SPL - 1) / a.SPL;
+  a.chunk = (a.chunk + a.KS - 1) / a.KS * a.KS;
+  a.SPL = (a.Q + a.chunk - 1) / a.chunk;
+
+  for (int g = 0; g < 2; ++g) a.ncnt[g] = 0;
+  for (int i = 0; i < ne; ++i) {
+    const int g = i / per, k = a.ncnt[g]++;
+    a.aoff[g][k] = (uint32_t)(ents[i].up * a.nbU * a.regU) >> 4;
+    a.boff[g][k] = (uint32_t)(a.v_off + ents[i].vp * a.nbV * a.regV + (a.lead + ents[i].sh) * 128) >> 4;
+    for (int j = 0; j < 3; ++j) { a.tapj[g][k][j] = ents[i].tapj[j]; a.bias_row[g][k][j] = ents[i].brow[j]; }
+  }
+  p.part_floats = (size_t)S * a.SPL * a.rows * a.cols;
+  p.ok = true;
+  return p;
+}
+
+bool tconv_wgrad_win_supported(const bsde_conv_layer* L, int S, int B) { return ww_plan(L, S, B).ok; }
+
+size_t tconv_wgrad_ws_win(const bsde_conv_layer* L, int S, int B) {
+  WwPlan p = ww_plan(L, S, B);
+  return p.ok ? p.part_floats * sizeof(float) : 0;
+}
+
+int tconv_wgrad_win(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
+                    float* gw, long long gw_sample_stride, void* ws, size_t ws_bytes, cudaStream_t st) {
+  WwPlan p = ww_plan(L, S, B);
+  BSDE_CHECK_ARG(p.ok, "layer not supported by the window-staged weight gradient");
+  const size_t need = p.part_floats * sizeof(float);
+  if (!ws || ws_bytes < need) {
+    set_error("tconv_wgrad(win): workspace %zu < %zu bytes", ws_bytes, need);
+    return BSDE_ERR_WORKSPACE;
+  }
+  WwArgs& a = p.a;
+  a.U = a.u_is_input ? in : dy;
+  a.V = a.u_is_input ? dy : in;
+  a.partial = (float*)ws;
+  a.t = t;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  wgrad_win_kernel<<<S * a.TG * a.SPL, WW_THREADS, p.smem, st>>>(a);
+  BSDE_CUDA_OK(cudaGetLastError());
+  count_launch();
+
+  WreduceArgs r;
+  memset(&r, 0, sizeof(r));
+  r.partial = a.partial; r.bias_partial = nullptr; r.gw = gw; r.gw_sample_stride = gw_sample_stride;
+  r.S = S; r.splits = a.SPL; r.rows = a.rows; r.cols = a.cols; r.Kc = a.Kc; r.Ktot = a.Ktot;
+  r.has_time = L->has_time; r.time_row = L->time_first ? 0 : L->cin;
+  r.real_base = (L->has_time && L->time_first) ? 1 : 0; r.swapped = 0; r.cin = L->cin; r.cout = L->cout;
+  r.w_off = L->w_off; r.b_off = L->b_off; r.ts = L->w_tap_stride; r.ks = L->w_k_stride; r.ns = L->w_n_stride;
+  r.scale = scale; r.nbias = p.nbias;
+  const long long total = (long long)S * a.rows * a.cols;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  return launch_wgrad_reduce(r, blocks, st);
+}
+
+}  // namespace bsde
