@@ -40,16 +40,19 @@ constexpr int WW_THREADS = (WW_PROD_WARPS + 1) * 32;
 constexpr int WW_MAXENT = 9;
 constexpr int WW_MAXSTAGES = 4;
 
+__device__ float ww_one_dev = 1.0f;  // source of the ones channel (copied with cp.async like every other element)
+
 struct WwArgs {
   const float* U;
   const float* V;
+  const float* one;
   float* partial;
   int S, B, Hq, Wq, pitch, IP, Q;
   int cu, cv, u_ones, v_ones;     // real channels; append a ones channel at index cu / cv
   int nbU, nbV, NPU, NPV;         // 32-channel blocks, parity planes of each operand
   int hU, wU, hV, wV;             // spatial extent of the tensors behind U and V
   int KS, NPOSw, lead, regU, regV, stage_bytes, v_off, nstages;  // rows per stage, V window rows, region bytes
-  int SPL, TG, chunk;             // position splits, tap groups, positions per split (multiple of KS)
+  int SPL, TG, chunk, vgch;       // position splits, V channel groups, positions per split, V channels per group
   int Nmma;                       // N of every MMA
   uint32_t lboB;                  // LBO of the B descriptor: regV (channel blocks) or 128 (packed taps)
   int tmem_cols;
@@ -62,6 +65,7 @@ struct WwArgs {
   int packed, u_is_input;
   int cin, cout, Kc, Ktot, has_time, rows, cols;
   float t;
+  int dbg;  // tools/ only (BSDE_WW_DBG): 1 skip copies, 2 skip MMAs, 4 skip the source tables
 };
 
 // position -> source pixel offset (floats) inside one sample, or -1
@@ -80,12 +84,95 @@ __device__ __forceinline__ int ww_src(int q, int Q, int IP, int pitch, int Hq, i
   return ((img * h + y) * w + x) * c;
 }
 
+// Copy `rows` rows of one operand (np planes x nb 32-channel blocks) into its SWIZZLE_128B_BASE32B regions.
+// Channel counts that are a multiple of 4 move 16 bytes per lane, 8 lanes per row (whole 128-byte lines on both
+// sides); other counts (the 5-channel tensors) move 4 bytes per lane with (row, channel) flattened over ALL lanes.
+__device__ __forceinline__ void ww_copy_rows(const float* __restrict__ src, const float* one, uint32_t sb, const int* tab, int np,
+                                             int nb, int reg, int rows, int cch, int ones, int ch0, int tid) {
+  if ((cch & 3) == 0) {
+    const int c = tid & 7, r0 = tid >> 3;
+#pragma unroll 1
+    for (int p = 0; p < np; ++p) {
+#pragma unroll 1
+      for (int b = 0; b < nb; ++b) {
+        const uint32_t rg = sb + (uint32_t)((p * nb + b) * reg);
+        const int ch = ch0 + b * 32 + c * 4;
+        const bool is_one = ones && cch >= ch && cch < ch + 4;
+        if (ch >= cch && !is_one) continue;
+#pragma unroll 4
+        for (int r = r0; r < rows; r += WW_PROD / 8) {
+          const int so = tab[p * rows + r];
+          const uint32_t d = rg + r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));
+          if (ch < cch) cp_async16(d, so >= 0 ? src + so + ch : src, so >= 0);
+          else cp_async4(d, one, so >= 0);
+        }
+      }
+    }
+  } else {
+    // cch + ones <= 32 elements per row (one block): idx = row * ne + element
+    const int ne = cch + ones;
+#pragma unroll 1
+    for (int p = 0; p < np; ++p) {
+      const uint32_t rg = sb + (uint32_t)(p * nb * reg);
+#pragma unroll 2
+      for (int idx = tid; idx < rows * ne; idx += WW_PROD) {
+        const int r = idx / ne, e = idx - r * ne;
+        const int so = tab[p * rows + r];
+        const uint32_t d = rg + r * 128 + ((((e >> 3) ^ (r & 3)) << 5) | ((e & 7) << 2));
+        cp_async4(d, e < cch ? (so >= 0 ? src + so + e : src) : one, so >= 0);
+      }
+    }
+  }
+}
+
+// MMA issue loop of one CTA; NE > 0: entry count known at compile time (descriptor offsets stay in uniform registers)
+template <int NE>
+__device__ __forceinline__ void ww_issue(const WwArgs& a, int nst, uint32_t base, uint32_t bars, uint32_t tm) {
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                         ((uint32_t)(a.Nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t a_hi = desc_hi((uint32_t)a.regU, 512u, 1);
+  const uint64_t b_hi = desc_hi(a.lboB, 512u, 1);
+  const int ncnt = NE > 0 ? NE : a.ncnt[0];
+  uint32_t ao[NE > 0 ? NE : 1], bo[NE > 0 ? NE : 1];
+  if (NE > 0) {
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { ao[e] = a.aoff[0][e]; bo[e] = a.boff[0][e]; }
+  }
+  const uint32_t nm = (uint32_t)a.Nmma;
+#pragma unroll 1
+  for (int it = 0; it < nst; ++it) {
+    const int st = it % a.nstages;
+    mbar_wait(bars + 8u * st, (it / a.nstages) & 1);
+    fence_proxy_async();
+    tc_fence_after();
+    const uint32_t sb16 = (base + st * a.stage_bytes) >> 4;
+#pragma unroll 1
+    for (int ks = 0; ks < ((a.dbg & 2) ? 0 : a.KS / 8); ++ks) {
+      const uint32_t kofs = sb16 + (uint32_t)ks * 64u;  // 8 rows x 128 B
+      const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+      if (NE > 0) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+          umma_tf32_elect(tm + (uint32_t)e * nm, a_hi | (uint64_t)((kofs + ao[e]) & 0x3FFFu), b_hi | (uint64_t)((kofs + bo[e]) & 0x3FFFu), idesc, acc);
+      } else {
+#pragma unroll 1
+        for (int e = 0; e < ncnt; ++e)
+          umma_tf32_elect(tm + (uint32_t)e * nm, a_hi | (uint64_t)((kofs + a.aoff[0][e]) & 0x3FFFu),
+                          b_hi | (uint64_t)((kofs + a.boff[0][e]) & 0x3FFFu), idesc, acc);
+      }
+    }
+    umma_commit_elect(bars + 8u * (4 + st));
+  }
+  umma_commit_elect(bars + 8u * 8);
+}
+
 __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_constant__ WwArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s = blockIdx.x / (a.TG * a.SPL);
   const int rem = blockIdx.x - s * a.TG * a.SPL;
-  const int tg = rem / a.SPL, split = rem - tg * a.SPL;
+  const int vg = rem / a.SPL, split = rem - vg * a.SPL;  // this CTA's group of V channels (accumulator columns)
+  const int tg = 0;
   const int qbeg = split * a.chunk, qend = min(a.Q, qbeg + a.chunk);
   const int nst = qend > qbeg ? (qend - qbeg + a.KS - 1) / a.KS : 0;
 
@@ -123,19 +210,19 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
     const float* __restrict__ U = a.U + (long long)s * a.B * a.hU * a.wU * a.cu;
     const float* __restrict__ V = a.V + (long long)s * a.B * a.hV * a.wV * a.cv;
     const float rIP = 1.0f / (float)a.IP, rpitch = 1.0f / (float)a.pitch;
-    const int c = tid & 7, r0 = tid >> 3;  // chunk of the 128-byte row; rows r0 + 32 k
-    const bool uvec = (a.cu & 3) == 0, vvec = (a.cv & 3) == 0;
 #pragma unroll 1
     for (int it = 0; it < nst; ++it) {
       const int st = it % a.nstages;
       const int q0 = qbeg + it * a.KS;
       // source tables of this stage (shared by the producer threads)
       asm volatile("bar.sync 1, %0;" ::"n"(WW_PROD) : "memory");
+      if (!(a.dbg & 4))
       for (int i = tid; i < a.KS; i += WW_PROD) {
         const int q = q0 + i;
         for (int p = 0; p < a.NPU; ++p)
           s_tabU[p * a.KS + i] = q < qend ? ww_src(q, a.Q, a.IP, a.pitch, a.Hq, a.Wq, rIP, rpitch, a.NPU, p, a.hU, a.wU, a.cu) : -1;
       }
+      if (!(a.dbg & 4))
       for (int i = tid; i < a.NPOSw; i += WW_PROD) {
         const int q = q0 - a.lead + i;
         for (int p = 0; p < a.NPV; ++p)
@@ -144,50 +231,11 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
       asm volatile("bar.sync 1, %0;" ::"n"(WW_PROD) : "memory");
       if (it >= a.nstages) mbar_wait(empty_bar(st), ((it / a.nstages) & 1) ^ 1);
       const uint32_t sb = base + st * a.stage_bytes;
-      uint8_t* gb = gen + st * a.stage_bytes;
-      // ---- U rows: [plane][block][KS rows][128 B], granule g of row r at g ^ (r & 3)
-#pragma unroll 1
-      for (int p = 0; p < a.NPU; ++p) {
-#pragma unroll 1
-        for (int b = 0; b < a.nbU; ++b) {
-          const uint32_t reg = (uint32_t)((p * a.nbU + b) * a.regU);
-          const int ch = b * 32 + c * 4;
-          for (int r = r0; r < a.KS; r += WW_PROD / 8) {
-            const int src = s_tabU[p * a.KS + r];
-            const uint32_t d = reg + r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));
-            if (uvec) {
-              if (ch < a.cu) cp_async16(sb + d, src >= 0 ? U + src + ch : U, src >= 0);
-            } else {
-              for (int e = 0; e < 4; ++e)
-                if (ch + e < a.cu) cp_async4(sb + d + e * 4, src >= 0 ? U + src + ch + e : U, src >= 0);
-            }
-            if (a.u_ones && a.cu >= ch && a.cu < ch + 4)
-              *reinterpret_cast<float*>(gb + d + (a.cu - ch) * 4) = src >= 0 ? 1.f : 0.f;
-          }
-        }
+      // ---- U rows: [plane][block][KS rows][128 B], granule g of row r at g ^ (r & 3); then the V window rows
+      if (!(a.dbg & 1)) {
+        ww_copy_rows(U, a.one, sb, s_tabU, a.NPU, a.nbU, a.regU, a.KS, a.cu, a.u_ones, 0, tid);
+        ww_copy_rows(V, a.one, sb + (uint32_t)a.v_off, s_tabV, a.NPV, a.nbV, a.regV, a.NPOSw, a.cv, a.v_ones, vg * a.vgch, tid);
       }
-      // ---- V window rows: [plane][block][NPOSw rows][128 B]
-#pragma unroll 1
-      for (int p = 0; p < a.NPV; ++p) {
-#pragma unroll 1
-        for (int b = 0; b < a.nbV; ++b) {
-          const uint32_t reg = (uint32_t)a.v_off + (uint32_t)((p * a.nbV + b) * a.regV);
-          const int ch = b * 32 + c * 4;
-          for (int r = r0; r < a.NPOSw; r += WW_PROD / 8) {
-            const int src = s_tabV[p * a.NPOSw + r];
-            const uint32_t d = reg + r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));
-            if (vvec) {
-              if (ch < a.cv) cp_async16(sb + d, src >= 0 ? V + src + ch : V, src >= 0);
-            } else {
-              for (int e = 0; e < 4; ++e)
-                if (ch + e < a.cv) cp_async4(sb + d + e * 4, src >= 0 ? V + src + ch + e : V, src >= 0);
-            }
-            if (a.v_ones && a.cv >= ch && a.cv < ch + 4)
-              *reinterpret_cast<float*>(gb + d + (a.cv - ch) * 4) = src >= 0 ? 1.f : 0.f;
-          }
-        }
-      }
-      fence_proxy_async();  // the generic "ones" stores must be visible to the tensor core's async proxy
       cp_async_arrive_noinc(full_bar(st));
     }
 
@@ -213,7 +261,7 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
           if (tap < 0) continue;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int n = a.packed ? ((n0 & 31) + j) : (n0 + j);  // V channel
+            const int n = a.packed ? ((n0 & 31) + j) : (vg * a.vgch + n0 + j);  // V channel
             const float val = __uint_as_float(v[j]);
             if (a.u_is_input) {
               // m = input channel (cin = ones), n = output channel
@@ -241,33 +289,11 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
   } else {
     // =============================== MMA issuer ===============================
     // whole warp, uniform operands, one elected lane issues
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                           ((uint32_t)(a.Nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint64_t a_hi = desc_hi((uint32_t)a.regU, 512u, 1);
-    const uint64_t b_hi = desc_hi(a.lboB, 512u, 1);
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int ncnt = a.ncnt[tg];
-#pragma unroll 1
-    for (int it = 0; it < nst; ++it) {
-      const int st = it % a.nstages;
-      mbar_wait(full_bar(st), (it / a.nstages) & 1);
-      fence_proxy_async();
-      tc_fence_after();
-      const uint32_t sb16 = (base + st * a.stage_bytes) >> 4;
-#pragma unroll 1
-      for (int ks = 0; ks < a.KS / 8; ++ks) {
-        const uint32_t kofs = (uint32_t)ks * 64u;  // 8 rows x 128 B
-        const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-#pragma unroll 1
-        for (int e = 0; e < ncnt; ++e) {
-          const uint64_t ad = a_hi | (uint64_t)((sb16 + a.aoff[tg][e] + kofs) & 0x3FFFu);
-          const uint64_t bd = b_hi | (uint64_t)((sb16 + a.boff[tg][e] + kofs) & 0x3FFFu);
-          umma_tf32_elect(tm + (uint32_t)(e * a.Nmma), ad, bd, idesc, acc);
-        }
-      }
-      umma_commit_elect(empty_bar(st));
-    }
-    umma_commit_elect(done_bar);
+    if (ncnt == 9) ww_issue<9>(a, nst, base, bars, tm);
+    else if (ncnt == 3) ww_issue<3>(a, nst, base, bars, tm);
+    else ww_issue<0>(a, nst, base, bars, tm);
     __syncwarp();
   }
   tc_fence_before();
@@ -303,8 +329,9 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
   if (mode == 1 && (L->hin != L->hout || L->win != L->wout)) return p;
   if (mode == 2 && ((L->hin + 1) / 2 != L->hout || (L->win + 1) / 2 != L->wout)) return p;
   if (mode == 3 && (L->hout != 2 * L->hin || L->wout != 2 * L->win)) return p;
-  if (mode == 2 && L->hout > 4) return p;  // measured slower than wgrad_tc.cu: 4 parity planes x 3 blocks leave only
-  if (mode == 3 && L->hin > 8) return p;   // 32-position stages, which cannot hide the load latency
+  if (mode == 2 && L->hout > 4) return p;  // measured slower than wgrad_tc.cu: the big operand (4 parity planes x 3 blocks)
+                                           // sits on the U side, which every V-channel group reloads
+  if (mode == 3 && L->hin > 8) return p;   // 16x16 grids: measured on par / slower than wgrad_tc.cu (copy-issue bound)
   a.Hq = mode == 3 ? L->hin : L->hout;
   a.Wq = mode == 3 ? L->win : L->wout;
   a.pitch = a.Wq + 1;
@@ -350,6 +377,8 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
     a.NPU = 1; a.NPV = 1;
   }
   if (a.cu + a.u_ones > 128) return p;
+  // the 4-byte copy path handles one 32-channel block only
+  if (((a.cu & 3) && a.cu + a.u_ones > 32) || ((a.cv & 3) && a.cv + a.v_ones > 32)) return p;
   a.nbU = (a.cu + a.u_ones + 31) / 32;
   a.nbV = (a.cv + a.v_ones + 31) / 32;
   a.packed = (mode == 1 && a.cv + a.v_ones <= 32) ? 1 : 0;
@@ -407,10 +436,18 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
   a.lead = -mins;
   const int trail = maxs;
 
-  // tap groups: accumulators of one CTA must fit 512 TMEM columns
-  a.TG = (ne * a.Nmma + 511) / 512;
-  if (a.TG > 2) return p;
-  const int per = (ne + a.TG - 1) / a.TG;
+  // the nine accumulators of a CTA must fit the 512 TMEM columns: otherwise split the V channels into groups of one
+  // 32-channel block (each CTA then loads all of U but only its block of V)
+  a.TG = 1;
+  a.vgch = 32 * a.nbV;
+  if (ne * a.Nmma > 512) {
+    if (a.packed) return p;
+    a.TG = a.nbV;
+    a.nbV = 1;
+    a.vgch = 32;
+    a.Nmma = 32;
+  }
+  const int per = ne;
   a.tmem_cols = ww_pow2_cols(per * a.Nmma);
   if (a.tmem_cols > 512) return p;
 
@@ -445,7 +482,7 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
 
   for (int g = 0; g < 2; ++g) a.ncnt[g] = 0;
   for (int i = 0; i < ne; ++i) {
-    const int g = i / per, k = a.ncnt[g]++;
+    const int g = 0, k = a.ncnt[g]++;
     a.aoff[g][k] = (uint32_t)(ents[i].up * a.nbU * a.regU) >> 4;
     a.boff[g][k] = (uint32_t)(a.v_off + ents[i].vp * a.nbV * a.regV + (a.lead + ents[i].sh) * 128) >> 4;
     for (int j = 0; j < 3; ++j) { a.tapj[g][k][j] = ents[i].tapj[j]; a.bias_row[g][k][j] = ents[i].brow[j]; }
@@ -476,6 +513,10 @@ int tconv_wgrad_win(const bsde_conv_layer* L, int S, int B, const float* in, con
   a.V = a.u_is_input ? dy : in;
   a.partial = (float*)ws;
   a.t = t;
+  { static const int dbg = getenv("BSDE_WW_DBG") ? atoi(getenv("BSDE_WW_DBG")) : 0; a.dbg = dbg; }
+  static float* one_ptr = nullptr;
+  if (!one_ptr) BSDE_CUDA_OK(cudaGetSymbolAddress((void**)&one_ptr, ww_one_dev));
+  a.one = one_ptr;
   static bool attr_set = false;
   if (!attr_set) {
     BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
