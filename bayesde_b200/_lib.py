@@ -49,6 +49,11 @@ class XpathDesc(C.Structure):
                 ("layers", ConvLayer * MAX_LAYERS)]
 
 
+class ToyDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("nt", C.c_int32), ("h1", C.c_int32), ("h2", C.c_int32),
+                ("sigma", C.c_float), ("theta", C.c_float)]
+
+
 class BsdeError(RuntimeError):
     pass
 
@@ -58,7 +63,7 @@ _lib = None
 _EXPORTS = ["bsde_version", "bsde_last_error", "bsde_launch_count", "bsde_wsde_workspace_bytes", "bsde_wsde_fwd", "bsde_wsde_bwd",
             "bsde_tconv_fwd", "bsde_tconv_fwd_workspace_bytes", "bsde_tconv_wgrad_workspace_bytes", "bsde_tconv_wgrad",
             "bsde_xpath_workspace_bytes", "bsde_xpath_acts_bytes", "bsde_xpath_fwd", "bsde_xpath_bwd", "bsde_step_update",
-            "bsde_philox_increments"]
+            "bsde_philox_increments", "bsde_toy_em_fwd", "bsde_toy_em_bwd"]
 
 
 def lib():
@@ -97,10 +102,8 @@ def lib():
     L.bsde_xpath_acts_bytes.argtypes = [C.POINTER(XpathDesc)]
     L.bsde_step_update.argtypes = [C.c_int32, C.c_int64, C.c_float, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bsde_philox_increments.argtypes = [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_int64, vp, vp, vp]
-    for name in _EXPORTS:
-        f = getattr(L, name)
-        if f.restype is C.c_int and name != "bsde_version":
-            pass
+    L.bsde_toy_em_fwd.argtypes = [C.POINTER(ToyDesc), vp, vp, vp, C.c_uint64] + [vp] * 8 + [vp, vp, vp]
+    L.bsde_toy_em_bwd.argtypes = [C.POINTER(ToyDesc), vp, vp, vp, vp] + [vp] * 8 + [vp] * 8 + [vp]
     if L.bsde_version() != 100:
         raise BsdeError(f"libbsde.so version {L.bsde_version()} != 100: rebuild")
     _lib = L

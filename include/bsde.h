@@ -25,6 +25,9 @@
  *                            jaxsde/jaxsde/sdeint.py:103-110,135
  *   bsde_step_update         ito_euler_step / ito_milstein_step on a flat state for arbitrary
  *                            user f, g: jaxsde/jaxsde/sdeint.py:36-50 (+ euler_heun, :73-74 stub)
+ *   bsde_toy_em_fwd/bwd      em_solver + VariationalSDE drift/prior of the torch toy (config 2):
+ *                            examples/torch/sdebnn_toy1d.py:19-60, torchbnn/_impl/diffeq_layers.py:178-188,
+ *                            torchbnn/_impl/basic.py:298-312
  *   bsde_philox_increments   replaces make_brownian_motion / virtual_brownian_tree queries
  *                            bm(next_t)-bm(curr_t): jaxsde/jaxsde/brownian.py:26-95, sdeint.py:108
  */
@@ -218,6 +221,39 @@ int bsde_step_update(int32_t method, int64_t n, float dt, const float* d_y, cons
  * (p, k, s, stream_id): the stream bsde_wsde_fwd consumes when d_dW == NULL. */
 int bsde_philox_increments(uint64_t seed, uint32_t stream_id, int32_t S, int32_t nit, int64_t P,
                            const float* d_dtk, float* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * config 2 (torch toy): em_solver + VariationalSDE of examples/torch/sdebnn_toy1d.py:19-60
+ * ---------------------------------------------------------------------------------------- */
+
+/* f = construct_odenet([1, h1, h2, 1]) (sdebnn_toy1d.py:35-41): ConcatLinear / TimeDependentSwish,
+ * g = sigma, prior drift -theta * x.  torch nn.Linear layouts: W1 [h1][2], W2 [h2][h1+1], W3 [1][h2+1],
+ * column 0 = time channel (torchbnn/_impl/utils.py:201-203).  beta1 [nt-1][h1], beta2 [nt-1][h2] are the
+ * TimeDependentSwish gates beta(t_k) (torchbnn/_impl/basic.py:298-312), evaluated by the caller. */
+typedef struct {
+  int32_t n;      /* samples (independent scalar paths) */
+  int32_t nt;     /* time points; nt-1 Euler-Maruyama steps */
+  int32_t h1, h2; /* hidden widths, <= 128 */
+  float sigma;    /* diffusion */
+  float theta;    /* OU prior coefficient */
+} bsde_toy_desc;
+
+/* d_ts [nt]; d_z0 [n]; d_dW [nt-1][n] increments (already N(0,dt)) or NULL for Philox(seed).
+ * Outputs: d_zt [nt][n] (z_0 .. z_T), d_kl [n] = sum_k dt_k u_k^2 / 2 with u evaluated at the NEW state. */
+int bsde_toy_em_fwd(const bsde_toy_desc* d, const float* d_ts, const float* d_z0, const float* d_dW, uint64_t seed,
+                    const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                    const float* b3, const float* beta1, const float* beta2, float* d_zt, float* d_kl,
+                    void* stream);
+
+/* Reverse pass.  d_gzt [nt][n] = dL/dz_t (or NULL), d_gkl [n] = dL/dkl (or NULL).  Outputs: d_gz0 [n] and the
+ * per-(step, sample) layer gradients whose sums over (step, sample) are the parameter gradients:
+ * DA1 [nt-1][n][h1], DA2 [nt-1][n][h2] (pre-activation gradients), DF [nt-1][n] (output gradient),
+ * H1, H2 (hidden activations, same shapes), GB1, GB2 (dL/dbeta per step, sample, unit). */
+int bsde_toy_em_bwd(const bsde_toy_desc* d, const float* d_ts, const float* d_zt, const float* d_gzt,
+                    const float* d_gkl, const float* W1, const float* b1, const float* W2, const float* b2,
+                    const float* W3, const float* b3, const float* beta1, const float* beta2, float* d_gz0,
+                    float* d_DA1, float* d_DA2, float* d_DF, float* d_H1, float* d_H2, float* d_GB1,
+                    float* d_GB2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -587,3 +587,116 @@ def test_cuda_path_matches_committed_golden(built_lib, name):
     grads = torch.autograd.grad((xo * torch.from_numpy(z["cot"]).float().to(DEV)).sum() + 1e-3 * kl.sum(), leaves)
     for i, g_ in enumerate(grads):
         _gclose(g_, torch.from_numpy(z[f"grad{i}"]), 1e-3, f"grad {i}")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 2 (row a24): torch toy, fused em_solver kernels vs vectors produced by the REFERENCE's own code
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_torch_toy_matches_reference_run(built_lib, tag):
+    """bayesde_b200.torch_toy (csrc/toy_em.cu through the C ABI) against tests/golden/torch_toy.npz, which
+    holds the outputs of examples/torch/sdebnn_toy1d.py's em_solver / construct_odenet / loglik_fn run in the
+    build container with the same parameters, z0 and Brownian increments.  fp32 on both sides, 99 sequential
+    steps: z_t rtol 1e-4 / atol 1e-4, KL rtol 1e-3, objective 1e-4 abs, gradients rtol 2e-3 of the tensor max."""
+    import os
+    from bayesde_b200 import torch_toy as T
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "torch_toy.npz"))
+    f = T.construct_odenet([1, 64, 64, 1])
+    sd = {k[len(tag) + 3:]: torch.tensor(g[k]) for k in g.files if k.startswith(f"{tag}_p_")}
+    f.load_state_dict(sd)  # the reference's state_dict loads unchanged
+    q = T.VariationalSDE(f).to(DEV)
+    z0 = torch.tensor(g[f"{tag}_z0"]).to(DEV)
+    dW = torch.tensor(g[f"{tag}_dW"]).to(DEV)
+    z_t, kl = q(z0.shape[0], z0=z0, dW=dW)
+    _close(z_t, torch.tensor(g[f"{tag}_zt"]), 1e-4, 1e-4, "z_t")
+    _close(kl, torch.tensor(g[f"{tag}_kl"]), 1e-3, 1e-6, "kldiv")
+    elbo = T.elbo_fn(q, z_t, kl)
+    assert abs(elbo.item() - float(g[f"{tag}_elbo"])) < 1e-4
+    q.zero_grad()
+    elbo.mul(-1.0).backward()
+    for k, v in f.named_parameters():
+        _gclose(v.grad, torch.tensor(g[f"{tag}_g_{k}"]), 2e-3, k)
+
+
+def test_torch_toy_philox_and_edges(built_lib):
+    """In-kernel Philox increments: deterministic per seed, N(0, dt) law through the terminal variance of a
+    zero-drift net; bad arguments raise like the reference's Python would."""
+    from bayesde_b200 import torch_toy as T
+    f = T.construct_odenet([1, 8, 8, 1])
+    for p in f.parameters():
+        torch.nn.init.zeros_(p)
+    q = T.VariationalSDE(f, ou_drift_coef=0.0, diff_coef=1.0).to(DEV)
+    z0 = torch.zeros(4096, 1, device=DEV)
+    a, _ = q(4096, z0=z0, seed=11)
+    b, _ = q(4096, z0=z0, seed=11)
+    c, _ = q(4096, z0=z0, seed=12)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    # z_T = sum of increments ~ N(0, 3)
+    v = a[-1].var().item()
+    assert abs(v - 3.0) < 5 * 3.0 * math.sqrt(2.0 / 4096)
+    with pytest.raises(Exception):
+        T.em_solver(f, q.g_func, q.f_prior_func, torch.zeros(4, 1), torch.linspace(0, 3, 100))  # CPU tensor: no fallback
+    with pytest.raises(NotImplementedError):
+        T.em_solver(torch.nn.Linear(1, 1), q.g_func, q.f_prior_func, z0, torch.linspace(0, 3, 100))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 1 (row a20): the JAX toy's fixed-step solver brax/utils/sdeint.py with the [w, x, kl] toy dynamics
+# ---------------------------------------------------------------------------------------------------------
+def test_jax_toy_solver_vs_oracle(built_lib):
+    """bayesde_b200.brax_utils.sdeint against a line-by-line fp64 restatement of brax/utils/sdeint.py:30-60 with
+    the toy's augmented drift (brax/_impl/layers.py:54-118: state [w, x, kl], OU prior, KL integrand u^2/2 plus the
+    STL term sum(u_sg * eps) fed through the DRIFT, quirk Q5) on the same unit normals.  rtol 1e-5 states, 1e-3 grads."""
+    from bayesde_b200 import brax_utils as BU
+    g_ = torch.Generator().manual_seed(5)
+    P, Bx, Dx, H = 37, 6, 3, 8
+    W = (torch.randn(P, H, generator=g_, dtype=torch.float64) * 0.2).requires_grad_(True)
+    V = (torch.randn(H, P, generator=g_, dtype=torch.float64) * 0.2).requires_grad_(True)
+    A = torch.randn(Dx, Dx, generator=g_, dtype=torch.float64) * 0.3
+    sigma = 0.2
+    D = P + Bx * Dx + 1
+    s0 = torch.cat([torch.randn(P, generator=g_, dtype=torch.float64) * 0.1, torch.randn(Bx * Dx, generator=g_, dtype=torch.float64),
+                    torch.zeros(1, dtype=torch.float64)])
+    ts = torch.linspace(0.0, 1.0, 20)
+    bm = torch.randn(len(ts) - 1, D, generator=g_, dtype=torch.float64)
+
+    def make(Wm, Vm, Am):
+        def f(t, s, eps):
+            w, x = s[:P], s[P:P + Bx * Dx].reshape(Bx, Dx)
+            mlp = torch.tanh(w @ Wm + t) @ Vm
+            dw = -w + mlp                                  # Additive(-w, MLP) (layers.py:286-292)
+            u = (dw - (-w)) / sigma                        # posterior minus OU prior drift
+            dx = torch.tanh(x @ Am) * w[:Dx].sum()         # data path driven by the sampled weights
+            dkl = (u ** 2 / 2).sum() + (u.detach() * eps).sum()   # stop_grad STL term through the drift (Q5)
+            return torch.cat([dw, dx.reshape(-1), dkl.reshape(1)])
+
+        def g(t, s):
+            return torch.cat([torch.full((P,), sigma, dtype=s.dtype, device=s.device), torch.zeros(Bx * Dx + 1, dtype=s.dtype, device=s.device)])
+        return f, g
+
+    # oracle: brax/utils/sdeint.py:42-58 restated
+    f64, g64 = make(W, V, A)
+    st, ref = s0, []
+    for k in range(len(ts) - 1):
+        h = (ts[k + 1] - ts[k]).double()
+        st = st + h * f64(ts[k].double(), st, bm[k, :P]) + torch.sqrt(h) * bm[k] * g64(ts[k].double(), st)
+        ref.append(st)
+    ref = torch.stack(ref)
+    loss_r = ref[-1, -1] + ref[-1, P:P + 3].sum()
+    gW_r, gV_r = torch.autograd.grad(loss_r, (W, V))
+
+    Wd = W.detach().float().to(DEV).requires_grad_(True)
+    Vd = V.detach().float().to(DEV).requires_grad_(True)
+    fd, gd = make(Wd, Vd, A.float().to(DEV))
+    out = BU.sdeint(fd, gd, s0.float().to(DEV), P, ts, bm.float().to(DEV))
+    _close(out, ref, 1e-4, 1e-5, "states")
+    last = BU._sdeint(fd, gd, s0.float().to(DEV), P, ts, bm.float().to(DEV))
+    assert torch.equal(last, out[-1])
+    loss = out[-1, -1] + out[-1, P:P + 3].sum()
+    gW, gV = torch.autograd.grad(loss, (Wd, Vd))
+    _gclose(gW, gW_r, 1e-3, "dW")
+    _gclose(gV, gV_r, 1e-3, "dV")
+    # Philox route: deterministic per seed
+    a = BU._sdeint(fd, gd, s0.float().to(DEV), P, ts, 3)
+    b = BU._sdeint(fd, gd, s0.float().to(DEV), P, ts, 3)
+    assert torch.equal(a, b)

@@ -163,3 +163,26 @@ def test_oracle_reproduces_committed_golden(name):
         np.testing.assert_allclose(xo.numpy(), z["xT"][s], rtol=1e-10, atol=1e-12)
         np.testing.assert_allclose(kl.numpy(), z["kl"][s], rtol=1e-10)
         np.testing.assert_allclose(wt.numpy(), z["wtraj"][s], rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_torch_toy_oracle_matches_reference_run(tag):
+    """Config 2: the restatement in oracle/torch_toy.py against vectors produced by the REFERENCE's own code
+    (tests/golden/make_golden_torch_toy.py ran examples/torch/sdebnn_toy1d.py's em_solver in this container)."""
+    import os
+    import numpy as np
+    from oracle import torch_toy as tt
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "torch_toy.npz"))
+    p = {k[len(tag) + 3:].replace(".module", ""): torch.tensor(g[k]).requires_grad_(True) for k in g.files if k.startswith(f"{tag}_p_")}
+    z0, dW = torch.tensor(g[f"{tag}_z0"]), torch.tensor(g[f"{tag}_dW"])
+    t = torch.linspace(0.0, 3.0, 100)
+    zt, kl = tt.em_solver(p, z0, t, dW)
+    obj = tt.objective(zt[-1], kl)
+    assert torch.allclose(zt, torch.tensor(g[f"{tag}_zt"]), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(kl, torch.tensor(g[f"{tag}_kl"]), rtol=1e-4, atol=1e-6)
+    assert abs(obj.item() - float(g[f"{tag}_elbo"])) < 1e-5
+    (-obj).backward()
+    for k, v in p.items():
+        ref = torch.tensor(g[f"{tag}_g_" + k.replace("layers.0", "layers.0.module").replace("layers.1", "layers.1.module").replace(
+            "layers.2", "layers.2.module").replace("layers.3", "layers.3.module").replace("layers.4", "layers.4.module")])
+        assert torch.allclose(v.grad, ref, rtol=1e-3, atol=1e-6 + 1e-4 * ref.abs().max().item()), k
