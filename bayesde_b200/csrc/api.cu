@@ -41,7 +41,10 @@ bool tconv_win_supported(const bsde_conv_layer* L, int S, int B);
 size_t tconv_win_ws_bytes(const bsde_conv_layer* L, int S);
 int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const float* w, long long w_sample_stride,
                   float t, int act, int epi, float scale, const float* aux, float* out, void* ws, size_t ws_bytes,
-                  cudaStream_t st);
+                  cudaStream_t st, const float* prepacked);
+size_t tconv_win_img_floats(const bsde_conv_layer* L);
+int tconv_win_repack(const bsde_conv_layer* L, int S, int nit, const float* w, long long w_sample_stride, long long w_iter_stride,
+                     int epi, float* img, cudaStream_t st);
 
 bool tconv_wgrad_tc_supported(const bsde_conv_layer* L, int S, int B);
 size_t tconv_wgrad_ws_tc(const bsde_conv_layer* L, int S, int B);
@@ -72,9 +75,9 @@ static int conv_wgrad(const bsde_conv_layer* L, int S, int B, const float* in, c
 
 static int conv_fwd(const bsde_conv_layer* L, int S, int B, const float* in, const float* w,
                     long long wss, float t, int act, int epi, float scale, const float* aux, float* out,
-                    int math, void* tc_ws, size_t tc_ws_bytes, cudaStream_t st) {
+                    int math, void* tc_ws, size_t tc_ws_bytes, cudaStream_t st, const float* prepacked = nullptr) {
   if (math == BSDE_MATH_TC && tconv_win_supported(L, S, B))
-    return tconv_fwd_win(L, S, B, in, w, wss, t, act, epi, scale, aux, out, tc_ws, tc_ws_bytes, st);
+    return tconv_fwd_win(L, S, B, in, w, wss, t, act, epi, scale, aux, out, tc_ws, tc_ws_bytes, st, prepacked);
   if (math == BSDE_MATH_TC && tconv_tc_supported(L, epi))
     return tconv_fwd_tc(L, S, B, in, w, wss, t, act, epi, scale, aux, out, tc_ws, tc_ws_bytes, st);
   return tconv_fwd_simt(L, S, B, in, w, wss, t, act, epi, scale, aux, out, st);
@@ -181,6 +184,52 @@ static size_t xpath_tc_bytes(const bsde_xpath_desc* d, int backward) {
   return align_up(m);
 }
 
+// Weights of ALL scan iterations are repacked up front, one launch per layer form, into
+// [form][iteration][sample][image]: the per-iteration conv launches then follow each other directly.
+struct Prepack {
+  float* img[2 * BSDE_MAX_LAYERS];     // forward forms 0..n-1, data-gradient forms n..2n-1 (NULL: not prepacked)
+  size_t per_iter[2 * BSDE_MAX_LAYERS];  // floats per iteration (S * image)
+};
+
+static size_t prepack_floats(const bsde_xpath_desc* d, int backward, bool need_fwd_forms) {
+  if (d->math != BSDE_MATH_TC) return 0;
+  size_t tot = 0;
+  for (int l = 0; l < d->nlayers; ++l) {
+    if (need_fwd_forms && tconv_win_supported(&d->layers[l], d->S, d->B))
+      tot += (size_t)d->nit * d->S * tconv_win_img_floats(&d->layers[l]);
+    if (backward) {
+      bsde_conv_layer D = dgrad_layer(d->layers[l]);
+      if (tconv_win_supported(&D, d->S, d->B)) tot += (size_t)d->nit * d->S * tconv_win_img_floats(&D);
+    }
+  }
+  return tot;
+}
+
+static int prepack_all(const bsde_xpath_desc* d, int backward, bool need_fwd_forms, const float* d_wtraj, float* buf, Prepack& pp,
+                       cudaStream_t st) {
+  memset(&pp, 0, sizeof(pp));
+  if (d->math != BSDE_MATH_TC) return 0;
+  const int n = d->nlayers;
+  const long long wss = (long long)(d->nit + 1) * d->P;
+  for (int l = 0; l < n; ++l) {
+    if (need_fwd_forms && tconv_win_supported(&d->layers[l], d->S, d->B)) {
+      const int epi = l == n - 1 ? BSDE_EPI_EULER : BSDE_EPI_BIAS_ACT;
+      pp.img[l] = buf; pp.per_iter[l] = (size_t)d->S * tconv_win_img_floats(&d->layers[l]);
+      if (int e = tconv_win_repack(&d->layers[l], d->S, d->nit, d_wtraj, wss, d->P, epi, buf, st)) return e;
+      buf += (size_t)d->nit * pp.per_iter[l];
+    }
+    if (backward) {
+      bsde_conv_layer D = dgrad_layer(d->layers[l]);
+      if (tconv_win_supported(&D, d->S, d->B)) {
+        pp.img[n + l] = buf; pp.per_iter[n + l] = (size_t)d->S * tconv_win_img_floats(&D);
+        if (int e = tconv_win_repack(&D, d->S, d->nit, d_wtraj, wss, d->P, BSDE_EPI_DACT, buf, st)) return e;
+        buf += (size_t)d->nit * pp.per_iter[n + l];
+      }
+    }
+  }
+  return 0;
+}
+
 extern "C" size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t backward) {
   if (!d || d->nlayers < 2 || d->nlayers > BSDE_MAX_LAYERS) return 0;
   size_t tot = xpath_tc_bytes(d, backward);
@@ -193,6 +242,7 @@ extern "C" size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t b
     }
     tot += align_up(wg);
   }
+  tot += align_up(prepack_floats(d, backward, true) * sizeof(float));
   return tot;
 }
 
@@ -208,13 +258,13 @@ extern "C" size_t bsde_xpath_acts_bytes(const bsde_xpath_desc* d) {
 }
 
 static int xpath_recompute(const bsde_xpath_desc* d, const float* x, const float* wk, float t, float* const* a,
-                           void* tc_ws, size_t tc_bytes, cudaStream_t st) {
+                           void* tc_ws, size_t tc_bytes, cudaStream_t st, const Prepack& pp, int k) {
   const int n = d->nlayers;
   const long long wss = (long long)(d->nit + 1) * d->P;
   const float* in = x;
   for (int l = 0; l + 1 < n; ++l) {
     if (int e = conv_fwd(&d->layers[l], d->S, d->B, in, wk, wss, t, d->act, BSDE_EPI_BIAS_ACT, 1.f, nullptr,
-                         a[l], d->math, tc_ws, tc_bytes, st))
+                         a[l], d->math, tc_ws, tc_bytes, st, pp.img[l] ? pp.img[l] + (size_t)k * pp.per_iter[l] : nullptr))
       return e;
     in = a[l];
   }
@@ -241,6 +291,8 @@ extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const
   for (int l = 0; l + 1 < n; ++l) { a[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
   const long long wss = (long long)(d->nit + 1) * d->P;
   const size_t acts_step = xpath_acts_floats(d);
+  Prepack pp;
+  if (int e = prepack_all(d, 0, true, d_wtraj, (float*)ws, pp, st)) return e;
   for (int k = 0; k < d->nit; ++k) {
     if (d_acts) {  // keep this iteration's layer outputs for the reverse pass (remat = False)
       float* p = d_acts + (size_t)k * acts_step;
@@ -249,10 +301,11 @@ extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const
     const float* xk = d_xs + (size_t)k * d->x_numel;
     float* xn = d_xs + (size_t)(k + 1) * d->x_numel;
     const float* wk = d_wtraj + (size_t)k * d->P;
-    if (int e = xpath_recompute(d, xk, wk, h_tk[k], a, tc_ws, tc_bytes, st)) return e;
+    if (int e = xpath_recompute(d, xk, wk, h_tk[k], a, tc_ws, tc_bytes, st, pp, k)) return e;
     // last conv + Euler update: x_{k+1} = x_k + dt_k (conv(a_{n-2}) + b)   (sdeint.py:48-50, g_x = 0)
     if (int e = conv_fwd(&d->layers[n - 1], d->S, d->B, a[n - 2], wk, wss, h_tk[k], d->act, BSDE_EPI_EULER,
-                         h_dtk[k], xk, xn, d->math, tc_ws, tc_bytes, st))
+                         h_dtk[k], xk, xn, d->math, tc_ws, tc_bytes, st,
+                         pp.img[n - 1] ? pp.img[n - 1] + (size_t)k * pp.per_iter[n - 1] : nullptr))
       return e;
   }
   return 0;
@@ -279,7 +332,12 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
   for (int l = 0; l + 1 < n; ++l) { a[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
   for (int l = 0; l + 1 < n; ++l) { dz[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
   void* wg_ws = ws;
-  const size_t wg_bytes = workspace_bytes - (size_t)(ws - (char*)workspace);
+  size_t wgmax = 0;
+  for (int l = 0; l < n; ++l) wgmax = std::max(wgmax, wgrad_ws(&d->layers[l], d->S, d->B, d->math));
+  const size_t wg_bytes = align_up(wgmax);
+  ws += wg_bytes;
+  Prepack pp;
+  if (int e = prepack_all(d, 1, d_acts == nullptr, d_wtraj, (float*)ws, pp, st)) return e;
   const long long wss = (long long)(d->nit + 1) * d->P;
   const long long gss = (long long)d->nit * d->P;
 
@@ -294,7 +352,7 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
     if (d_acts) {
       float* p = const_cast<float*>(d_acts) + (size_t)k * xpath_acts_floats(d);
       for (int l = 0; l + 1 < n; ++l) { a[l] = p; p += align_up(act_elems(d, l) * sizeof(float)) / sizeof(float); }
-    } else if (int e = xpath_recompute(d, xk, wk, t, a, tc_ws, tc_bytes, st)) {
+    } else if (int e = xpath_recompute(d, xk, wk, t, a, tc_ws, tc_bytes, st, pp, k)) {
       return e;
     }
     // walk the stack backwards; `dy` is dL/d(conv output of layer l)
@@ -306,13 +364,13 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
       if (l > 0) {
         // dz_{l-1} = sc * dgrad(dy) * act'(a_{l-1})
         if (int e = conv_fwd(&D[l], d->S, d->B, dy, wk, wss, t, d->act, BSDE_EPI_DACT, sc, a[l - 1], dz[l - 1],
-                             d->math, tc_ws, tc_bytes, st))
+                             d->math, tc_ws, tc_bytes, st, pp.img[n + l] ? pp.img[n + l] + (size_t)k * pp.per_iter[n + l] : nullptr))
           return e;
         dy = dz[l - 1];
       } else {
         // gx_k = gx_{k+1} + dgrad_0(dz_0)   (identity path of the Euler update)
         if (int e = conv_fwd(&D[0], d->S, d->B, dy, wk, wss, t, d->act, BSDE_EPI_ACCUM, sc, d_gx, d_gx,
-                             d->math, tc_ws, tc_bytes, st))
+                             d->math, tc_ws, tc_bytes, st, pp.img[n] ? pp.img[n] + (size_t)k * pp.per_iter[n] : nullptr))
           return e;
       }
     }

@@ -83,7 +83,7 @@ __device__ __host__ __forceinline__ bool wn_map_axis(int o, int k, int sn, int k
 struct WinRepackArgs {
   const float* w;
   float* img;
-  long long w_sample_stride, img_sample_stride;
+  long long w_sample_stride, img_sample_stride, w_iter_stride, img_iter_stride;  // blockIdx.z = scan iteration
   int nent, nks, npad, cin, cout, ksize, NA, real_base, has_time, time_row, use_bias, w_floats, tb_rows;
   int mode, Hq, Wq, hin, win, sn, kn, off, sd;
   long long w_off, b_off, ts, ks, ns;
@@ -94,8 +94,8 @@ __device__ __forceinline__ int wn_class_rep(int f, int size) { return f == 0 ? 1
 
 __global__ void win_repack_kernel(WinRepackArgs a) {
   const int s = blockIdx.y;
-  const float* __restrict__ w = a.w + (long long)s * a.w_sample_stride;
-  float* __restrict__ img = a.img + (long long)s * a.img_sample_stride;
+  const float* __restrict__ w = a.w + (long long)s * a.w_sample_stride + (long long)blockIdx.z * a.w_iter_stride;
+  float* __restrict__ img = a.img + (long long)s * a.img_sample_stride + (long long)blockIdx.z * a.img_iter_stride;
   if ((int)blockIdx.x == a.nent * a.nks) {
     float* tb = img + a.w_floats;
     for (int idx = threadIdx.x; idx < a.tb_rows * a.npad; idx += blockDim.x) {
@@ -621,37 +621,54 @@ size_t tconv_win_ws_bytes(const bsde_conv_layer* L, int S) {
   return p.ok ? p.img_floats * sizeof(float) * S : 0;
 }
 
+// floats of one sample's resident image (weight tiles + tables)
+size_t tconv_win_img_floats(const bsde_conv_layer* L) {
+  WinPlan p = win_plan(L);
+  return p.ok ? p.img_floats : 0;
+}
+
+// Repack the weights of `nit` scan iterations in one launch: iteration z reads w + z*w_iter_stride and writes
+// img + z*S*img_floats ([iteration][sample][img_floats]).  `epi` only selects whether the bias row is kept.
+int tconv_win_repack(const bsde_conv_layer* L, int S, int nit, const float* w, long long w_sample_stride, long long w_iter_stride,
+                     int epi, float* img, cudaStream_t st) {
+  WinPlan p = win_plan(L);
+  BSDE_CHECK_ARG(p.ok, "layer not supported by the window-staged tensor-core path");
+  WinRepackArgs r;
+  memset(&r, 0, sizeof(r));
+  r.w = w; r.img = img; r.w_sample_stride = w_sample_stride; r.img_sample_stride = (long long)p.img_floats;
+  r.w_iter_stride = w_iter_stride; r.img_iter_stride = (long long)p.img_floats * S;
+  r.nent = p.nent; r.nks = p.nks; r.npad = p.npad; r.cin = L->cin; r.cout = L->cout; r.ksize = L->ksize; r.NA = p.NA;
+  r.real_base = (L->has_time && L->time_first) ? 1 : 0; r.has_time = L->has_time;
+  r.time_row = L->time_first ? 0 : L->cin; r.use_bias = epi <= BSDE_EPI_EULER; r.w_floats = p.w_bytes / 4;
+  r.w_off = L->w_off; r.b_off = L->b_off; r.ts = L->w_tap_stride; r.ks = L->w_k_stride; r.ns = L->w_n_stride;
+  r.tb_rows = p.tb_rows; r.mode = p.mode; r.Hq = p.Hq; r.Wq = p.Wq; r.hin = L->hin; r.win = L->win;
+  r.sn = L->sn; r.kn = L->kn; r.off = L->off; r.sd = L->sd;
+  for (int e = 0; e < p.nent; ++e) {
+    r.ent_tap[e] = p.ent_tap[e]; r.ent_acc[e] = p.ent[e].acc; r.ent_kh[e] = p.ent[e].kh; r.ent_kw[e] = p.ent[e].kw;
+  }
+  win_repack_kernel<<<dim3(p.nent * p.nks + 1, S, nit), 256, 0, st>>>(r);
+  BSDE_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const float* w, long long w_sample_stride,
                   float t, int act, int epi, float scale, const float* aux, float* out, void* ws, size_t ws_bytes,
-                  cudaStream_t st) {
+                  cudaStream_t st, const float* prepacked) {
   WinPlan p = win_plan(L);
   BSDE_CHECK_ARG(p.ok, "layer not supported by the window-staged tensor-core path");
   BSDE_CHECK_ARG(!(epi >= BSDE_EPI_EULER) || aux != nullptr, "epilogue %d needs aux", epi);
-  const size_t need = p.img_floats * sizeof(float) * S;
-  if (!ws || ws_bytes < need) {
-    set_error("tconv_fwd(win): workspace %zu < %zu bytes", ws_bytes, need);
-    return BSDE_ERR_WORKSPACE;
-  }
-  {
-    WinRepackArgs r;
-    memset(&r, 0, sizeof(r));
-    r.w = w; r.img = (float*)ws; r.w_sample_stride = w_sample_stride; r.img_sample_stride = (long long)p.img_floats;
-    r.nent = p.nent; r.nks = p.nks; r.npad = p.npad; r.cin = L->cin; r.cout = L->cout; r.ksize = L->ksize; r.NA = p.NA;
-    r.real_base = (L->has_time && L->time_first) ? 1 : 0; r.has_time = L->has_time;
-    r.time_row = L->time_first ? 0 : L->cin; r.use_bias = epi <= BSDE_EPI_EULER; r.w_floats = p.w_bytes / 4;
-    r.w_off = L->w_off; r.b_off = L->b_off; r.ts = L->w_tap_stride; r.ks = L->w_k_stride; r.ns = L->w_n_stride;
-    r.tb_rows = p.tb_rows; r.mode = p.mode; r.Hq = p.Hq; r.Wq = p.Wq; r.hin = L->hin; r.win = L->win;
-    r.sn = L->sn; r.kn = L->kn; r.off = L->off; r.sd = L->sd;
-    for (int e = 0; e < p.nent; ++e) {
-      r.ent_tap[e] = p.ent_tap[e]; r.ent_acc[e] = p.ent[e].acc; r.ent_kh[e] = p.ent[e].kh; r.ent_kw[e] = p.ent[e].kw;
+  if (!prepacked) {
+    const size_t need = p.img_floats * sizeof(float) * S;
+    if (!ws || ws_bytes < need) {
+      set_error("tconv_fwd(win): workspace %zu < %zu bytes", ws_bytes, need);
+      return BSDE_ERR_WORKSPACE;
     }
-    win_repack_kernel<<<dim3(p.nent * p.nks + 1, S), 256, 0, st>>>(r);
-    BSDE_CUDA_OK(cudaGetLastError());
-    count_launch();
+    if (int e = tconv_win_repack(L, S, 1, w, w_sample_stride, 0, epi, (float*)ws, st)) return e;
   }
   WinArgs a;
   memset(&a, 0, sizeof(a));
-  a.in = in; a.aux = aux; a.out = out; a.wimg = (const float*)ws; a.wimg_sample_stride = (long long)p.img_floats;
+  a.in = in; a.aux = aux; a.out = out; a.wimg = prepacked ? prepacked : (const float*)ws; a.wimg_sample_stride = (long long)p.img_floats;
   a.S = S; a.B = B;
   a.G = std::max(1, 148 / S);
   a.Q = B * p.IP;
