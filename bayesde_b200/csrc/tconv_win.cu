@@ -36,9 +36,9 @@ namespace bsde {
 using namespace um;
 
 constexpr int WN_EPI_WARPS = 8;   // warps 0-7 epilogue (TMEM lane quarter = warp & 3)
-constexpr int WN_PROD = 128;      // warps 8-11 producers
-constexpr int WN_MMA_WARP = 12;   // warp 12 MMA issuer + TMEM owner
-constexpr int WN_THREADS = 13 * 32;
+constexpr int WN_PROD = 256;      // warps 8-15 producers
+constexpr int WN_MMA_WARP = 16;   // warp 16 MMA issuer + TMEM owner
+constexpr int WN_THREADS = 17 * 32;
 constexpr int WN_MAXENT = 16;
 constexpr int WN_MAXRING = 6;
 
