@@ -58,6 +58,7 @@ struct WinArgs {
   int Hq, Wq, pitch, IP, Q, lead, NPOSw, NP, NA, nent;
   int ring, slab_bytes, w_bytes, tb_floats, nbuf, tmem_cols;
   int hslab, nslab, region;  // halves per slab, slabs per tile, bytes of one (plane, half) region
+  int gather;                // stride-2 layers: slabs are per-(tap, half) gathered tiles of 128 rows (no window, no pads)
   float t, scale;
   uint32_t aoff[WN_MAXENT];  // A start offset of each entry in 16-byte units (plane region + shifted row)
   uint32_t dcol[WN_MAXENT];  // accumulator column offset | (first tap of its accumulator) << 31
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
   const uint32_t s_w = base + soff;                             soff += a.w_bytes;
   float* s_tb = reinterpret_cast<float*>(gen + soff);           soff += a.tb_floats * 4;
   float* s_stage = reinterpret_cast<float*>(gen + soff);        soff += WN_EPI_WARPS * 32 * 16 * 4;
-  int* s_tab = reinterpret_cast<int*>(gen + soff);              soff += a.NP * a.NPOSw * 4;
+  int* s_tab = reinterpret_cast<int*>(gen + soff);              soff += (a.gather ? 2 : a.NP) * a.NPOSw * 4;
   int* s_pix = reinterpret_cast<int*>(gen + soff);              soff += WN_EPI_WARPS * 32 * 4;
   const uint32_t bars = base + soff;                            soff += 8 * (2 * WN_MAXRING + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + soff);
@@ -227,6 +228,56 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
     const int c = pt & 7;  // 16-byte chunk inside the 128-byte row: 8 lanes cover one row / one global line
     const float rIP = 1.0f / (float)a.IP, rpitch = 1.0f / (float)a.pitch;
     uint32_t cnt = 0;
+    if (a.gather) {
+      // ---- stride-2 layers: per-(tap, half) gathered slabs; one table entry per output position of the tile
+      const int r0 = pt >> 3;
+      const uint32_t swz = (uint32_t)((c ^ (r0 & 7)) << 4);
+#pragma unroll 1
+      for (int tile = g; tile < a.ntiles; tile += a.G) {
+        asm volatile("bar.sync 1, %0;" ::"n"(WN_PROD) : "memory");
+        if (pt < 128) {
+          const int q = tile * 128 + pt;
+          int base = -1, yx = 0;
+          if (q < a.Q) {
+            int img = (int)((float)q * rIP);
+            int r = q - img * a.IP;
+            if (r < 0) { --img; r += a.IP; } else if (r >= a.IP) { ++img; r -= a.IP; }
+            int y = (int)((float)r * rpitch);
+            int x = r - y * a.pitch;
+            if (x < 0) { --y; x += a.pitch; } else if (x >= a.pitch) { ++y; x -= a.pitch; }
+            base = ((img * a.hin + 2 * y) * a.win + 2 * x) * a.cin;
+            yx = (y << 16) | x;
+          }
+          s_tab[2 * pt] = base;
+          s_tab[2 * pt + 1] = yx;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(WN_PROD) : "memory");
+#pragma unroll 1
+        for (int e = 0; e < a.nent; ++e) {
+          const int th = a.ent[e].kh * a.kn + a.off, tw = a.ent[e].kw * a.kn + a.off;
+          const int toff = (th * a.win + tw) * a.cin;
+#pragma unroll 1
+          for (int h = 0; h < a.nhalf; ++h, ++cnt) {
+            const int slot = cnt % a.ring;
+            if (cnt >= (uint32_t)a.ring) mbar_wait(empty_bar(slot), ((cnt / a.ring) & 1) ^ 1);
+            const uint32_t sb = s_ring + slot * a.slab_bytes + swz;
+            const int ch = h * 32 + c * 4;
+            const bool cok = ch < a.cin;
+            if (!(a.dbg & 1)) {
+#pragma unroll
+              for (int k = 0; k < 128 / (WN_PROD / 8); ++k) {
+                const int r = r0 + k * (WN_PROD / 8);
+                const int base = s_tab[2 * r], yx = s_tab[2 * r + 1];
+                const int iy = 2 * (yx >> 16) + th, ix = 2 * (yx & 0xFFFF) + tw;
+                const bool ok = base >= 0 && cok && (unsigned)iy < (unsigned)a.hin && (unsigned)ix < (unsigned)a.win;
+                cp_async16(sb + r * 128, ok ? in + base + toff + ch : in, ok);
+              }
+            }
+            cp_async_arrive_noinc(full_bar(slot));
+          }
+        }
+      }
+    } else
 #pragma unroll 1
     for (int tile = g; tile < a.ntiles; tile += a.G) {
       const int q0 = tile * 128 - a.lead;
@@ -328,6 +379,33 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
           tc_fence_after();
         }
         const uint32_t dbase = tm + (uint32_t)(buf * a.NA * a.npad);
+        if (a.gather) {
+          // slabs arrive in (tap, half) order; each holds four k-steps of one tap: unshifted K-major SW128 tile
+#pragma unroll 1
+          for (int e = 0; e < a.nent; ++e) {
+#pragma unroll 1
+            for (int h = 0; h < a.nhalf; ++h, ++cnt) {
+              const int slot = cnt % a.ring;
+              mbar_wait(full_bar(slot), (cnt / a.ring) & 1);
+              fence_proxy_async();
+              tc_fence_after();
+              const uint32_t sb16 = (s_ring + slot * a.slab_bytes) >> 4;
+              const int kend = min(4, a.nks - h * 4);
+              if (!(a.dbg & 2)) {
+#pragma unroll 1
+                for (int kk = 0; kk < kend; ++kk) {
+                  const int ks = h * 4 + kk;
+                  const uint64_t ad = a_hi | (uint64_t)((sb16 + (uint32_t)kk * 2u) & 0x3FFFu);
+                  const uint64_t bd = b_hi | (uint64_t)((w16 + (uint32_t)(e * a.nks + ks) * bstep) & 0x3FFFu);
+                  umma_tf32_elect(dbase, ad, bd, idesc, (e > 0 || ks > 0) ? 1u : 0u);
+                }
+              }
+              umma_commit_elect(empty_bar(slot));
+            }
+          }
+          umma_commit_elect(accf_bar(buf));
+          continue;
+        }
 #pragma unroll 1
         for (int sl = 0; sl < a.nslab; ++sl, ++cnt) {
           const int slot = cnt % a.ring;
@@ -500,7 +578,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
 struct WinPlan {
   bool ok;
   int mode, NA, NP, nent, Hq, Wq, pitch, IP, lead, trail, NPOSw, nks, npad, ring, slab_bytes, w_bytes, tb_floats;
-  int tab_units, nbuf, tmem_cols, vec, nhalf, hslab, nslab, region, tb_rows;
+  int tab_units, nbuf, tmem_cols, vec, nhalf, hslab, nslab, region, tb_rows, gather;
   size_t smem, img_floats;
   WinEntry ent[WN_MAXENT];
   int ent_tap[WN_MAXENT];
@@ -590,7 +668,25 @@ static WinPlan win_plan(const bsde_conv_layer* L) {
     const size_t slab = (size_t)p.NP * k * p.region;
     if (fixed + 2 * slab <= cap) { p.hslab = k; p.slab_bytes = (int)slab; }
   }
-  if (!p.hslab) return p;
+  if (!p.hslab) {
+    // Stride-2 layer whose four parity-plane windows do not fit beside the resident weights: keep the persistent
+    // structure (resident weights, TMEM double buffering, uniform MMA issue) but fill the ring with per-(tap, half)
+    // gathered tiles of 128 rows x 128 B; positions are the plain output pixels (no pad column / row needed).
+    if (p.mode != 2 || !p.vec) return p;
+    p.gather = 1;
+    p.pitch = p.Wq; p.IP = p.Hq * p.Wq; p.lead = 0; p.trail = 0; p.NPOSw = 128; p.NP = 1;
+    p.region = 128 * 128; p.hslab = 1; p.slab_bytes = p.region;
+    const size_t old_tab = (size_t)p.tab_units * 4;
+    p.tab_units = 2 * 128;
+    const size_t fixed_g = fixed - old_tab + (size_t)p.tab_units * 4;
+    if (fixed_g + 3 * (size_t)p.slab_bytes > cap) return p;
+    p.nslab = p.nent * p.nhalf;
+    p.ring = (int)std::min<size_t>(WN_MAXRING, (cap - fixed_g) / p.slab_bytes);
+    p.smem = fixed_g + (size_t)p.ring * p.slab_bytes;
+    p.img_floats = ((size_t)p.w_bytes / 4 + p.tb_floats + 3) & ~(size_t)3;
+    p.ok = true;
+    return p;
+  }
   p.nslab = (p.nhalf + p.hslab - 1) / p.hslab;
   p.ring = (int)std::min<size_t>(WN_MAXRING, (cap - fixed) / p.slab_bytes);
   p.ring = std::min(p.ring, std::max(2, 3 * p.nslab));
@@ -680,7 +776,7 @@ int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const
   a.Hq = p.Hq; a.Wq = p.Wq; a.pitch = p.pitch; a.IP = p.IP; a.lead = p.lead; a.NPOSw = p.NPOSw; a.NP = p.NP; a.NA = p.NA;
   a.nent = p.nent; a.ring = p.ring; a.slab_bytes = p.slab_bytes; a.w_bytes = p.w_bytes; a.tb_floats = p.tb_floats;
   a.nbuf = p.nbuf; a.tmem_cols = p.tmem_cols;
-  a.hslab = p.hslab; a.nslab = p.nslab; a.region = p.region;
+  a.hslab = p.hslab; a.nslab = p.nslab; a.region = p.region; a.gather = p.gather;
   a.t = t; a.scale = scale;
   { static const int dbg = getenv("BSDE_WIN_DBG") ? atoi(getenv("BSDE_WIN_DBG")) : 0; a.dbg = dbg; }
   for (int e = 0; e < p.nent; ++e) {

@@ -331,7 +331,7 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
   if (mode == 3 && (L->hout != 2 * L->hin || L->wout != 2 * L->win)) return p;
   if (mode == 2 && L->hout > 4) return p;  // measured slower than wgrad_tc.cu: the big operand (4 parity planes x 3 blocks)
                                            // sits on the U side, which every V-channel group reloads
-  if (mode == 3 && L->hin > 8) return p;   // 16x16 grids: measured on par / slower than wgrad_tc.cu (copy-issue bound)
+  { static const int m3 = getenv("BSDE_WW_M3") ? atoi(getenv("BSDE_WW_M3")) : 0; if (mode == 3 && L->hin > 8 && !m3) return p; }  // 16x16 grids: measured on par / slower than wgrad_tc.cu
   a.Hq = mode == 3 ? L->hin : L->hout;
   a.Wq = mode == 3 ? L->win : L->wout;
   a.pitch = a.Wq + 1;
@@ -454,8 +454,10 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
   // stage size and ring depth: prefer >= 3 stages in flight (latency hiding), then the largest KS
   const size_t cap = 227 * 1024 - 2048;
   a.KS = 0;
+  static const int ks_min = getenv("BSDE_WW_KSMIN") ? atoi(getenv("BSDE_WW_KSMIN")) : 0;
   for (int want = 3; want >= 2 && !a.KS; --want)
     for (int ks : {128, 64, 32, 16}) {
+      if (want == 3 && ks < ks_min) continue;
       const int nposw = (a.lead + ks + trail + 7) & ~7;
       // an M=128 MMA always reads four 32-channel blocks `regU` apart: when U has fewer, the surplus blocks must
       // still fall inside the stage (their accumulator rows are ignored), so the stage is padded if V is short
