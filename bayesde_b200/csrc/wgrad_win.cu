@@ -68,6 +68,24 @@ struct WwArgs {
   int dbg;  // tools/ only (BSDE_WW_DBG): 1 skip copies, 2 skip MMAs, 4 skip the source tables
 };
 
+// position -> pixel coordinates on the position grid (returns false on pads / out of range)
+__device__ __forceinline__ bool ww_decode(int q, int Q, int IP, int pitch, int Hq, int Wq, float rIP, float rpitch, int& img, int& y, int& x) {
+  if (q < 0 || q >= Q) return false;
+  img = (int)((float)q * rIP);
+  int r = q - img * IP;
+  if (r < 0) { --img; r += IP; } else if (r >= IP) { ++img; r -= IP; }
+  y = (int)((float)r * rpitch);
+  x = r - y * pitch;
+  if (x < 0) { --y; x += pitch; } else if (x >= pitch) { ++y; x -= pitch; }
+  return y < Hq && x < Wq;
+}
+__device__ __forceinline__ int ww_plane_src(bool ok, int img, int y, int x, int np, int plane, int h, int w, int c) {
+  if (!ok) return -1;
+  if (np == 4) { y = 2 * y + (plane >> 1); x = 2 * x + (plane & 1); }
+  if (y >= h || x >= w) return -1;
+  return ((img * h + y) * w + x) * c;
+}
+
 // position -> source pixel offset (floats) inside one sample, or -1
 __device__ __forceinline__ int ww_src(int q, int Q, int IP, int pitch, int Hq, int Wq, float rIP, float rpitch, int np, int plane,
                                       int h, int w, int c) {
@@ -84,39 +102,62 @@ __device__ __forceinline__ int ww_src(int q, int Q, int IP, int pitch, int Hq, i
   return ((img * h + y) * w + x) * c;
 }
 
-// Copy `rows` rows of one operand (np planes x nb 32-channel blocks) into its SWIZZLE_128B_BASE32B regions.
-// Channel counts that are a multiple of 4 move 16 bytes per lane, 8 lanes per row (whole 128-byte lines on both
-// sides); other counts (the 5-channel tensors) move 4 bytes per lane with (row, channel) flattened over ALL lanes.
+// Copy `rows` rows of one operand (np planes x NB 32-channel blocks) into its SWIZZLE_128B_BASE32B regions, 16 bytes
+// per lane, 8 lanes per 128-byte row (whole lines on both sides).  Rows advance by 32 per pass, so the swizzled
+// granule slot ((c >> 1) ^ (r & 3)) is a per-thread constant; the table is read once per row for all blocks.
+template <int NB>
+__device__ __forceinline__ void ww_copy_vec(const float* __restrict__ src, const float* one, uint32_t sb, const int* tab, int np,
+                                            int reg, int rows, int cch, int ones, int ch0, int tid) {
+  const int c = tid & 7, r0 = tid >> 3;
+  const uint32_t swz = (uint32_t)((((c >> 1) ^ (r0 & 3)) << 5) | ((c & 1) << 4));
+  int kind[NB];  // 0: beyond the channels, 1: data chunk, 2: the ones channel starts this chunk
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int ch = ch0 + b * 32 + c * 4;
+    kind[b] = ch < cch ? 1 : ((ones && cch >= ch && cch < ch + 4) ? 2 : 0);
+  }
+  const float* __restrict__ sc = src + ch0 + c * 4;
+#pragma unroll 1
+  for (int p = 0; p < np; ++p) {
+    const int* tp = tab + p * rows;
+    const uint32_t rg = sb + (uint32_t)(p * NB * reg) + swz;
+#pragma unroll 4
+    for (int r = r0; r < rows; r += WW_PROD / 8) {
+      const int so = tp[r];
+      const bool ok = so >= 0;
+      const float* g = sc + (ok ? so : 0);
+      const uint32_t d = rg + r * 128;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        if (kind[b] == 1) cp_async16(d + b * reg, ok ? g + b * 32 : src, ok);
+        else if (kind[b] == 2) cp_async4(d + b * reg, one, ok);
+      }
+    }
+  }
+}
+
+// Channel counts that are not a multiple of 4 (the 5-channel tensors; one block): 4 bytes per lane with
+// (row, channel) flattened over ALL lanes.
 __device__ __forceinline__ void ww_copy_rows(const float* __restrict__ src, const float* one, uint32_t sb, const int* tab, int np,
                                              int nb, int reg, int rows, int cch, int ones, int ch0, int tid) {
   if ((cch & 3) == 0) {
-    const int c = tid & 7, r0 = tid >> 3;
-#pragma unroll 1
-    for (int p = 0; p < np; ++p) {
-#pragma unroll 1
-      for (int b = 0; b < nb; ++b) {
-        const uint32_t rg = sb + (uint32_t)((p * nb + b) * reg);
-        const int ch = ch0 + b * 32 + c * 4;
-        const bool is_one = ones && cch >= ch && cch < ch + 4;
-        if (ch >= cch && !is_one) continue;
-#pragma unroll 4
-        for (int r = r0; r < rows; r += WW_PROD / 8) {
-          const int so = tab[p * rows + r];
-          const uint32_t d = rg + r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));
-          if (ch < cch) cp_async16(d, so >= 0 ? src + so + ch : src, so >= 0);
-          else cp_async4(d, one, so >= 0);
-        }
-      }
+    switch (nb) {
+      case 1: ww_copy_vec<1>(src, one, sb, tab, np, reg, rows, cch, ones, ch0, tid); break;
+      case 2: ww_copy_vec<2>(src, one, sb, tab, np, reg, rows, cch, ones, ch0, tid); break;
+      case 3: ww_copy_vec<3>(src, one, sb, tab, np, reg, rows, cch, ones, ch0, tid); break;
+      default: ww_copy_vec<4>(src, one, sb, tab, np, reg, rows, cch, ones, ch0, tid); break;
     }
   } else {
-    // cch + ones <= 32 elements per row (one block): idx = row * ne + element
     const int ne = cch + ones;
+    const float rne = 1.0f / (float)ne;
 #pragma unroll 1
     for (int p = 0; p < np; ++p) {
       const uint32_t rg = sb + (uint32_t)(p * nb * reg);
 #pragma unroll 2
       for (int idx = tid; idx < rows * ne; idx += WW_PROD) {
-        const int r = idx / ne, e = idx - r * ne;
+        int r = (int)((float)idx * rne);
+        int e = idx - r * ne;
+        if (e < 0) { --r; e += ne; } else if (e >= ne) { ++r; e -= ne; }
         const int so = tab[p * rows + r];
         const uint32_t d = rg + r * 128 + ((((e >> 3) ^ (r & 3)) << 5) | ((e & 7) << 2));
         cp_async4(d, e < cch ? (so >= 0 ? src + so + e : src) : one, so >= 0);
@@ -180,10 +221,11 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw);
   const int ring_bytes = a.nstages * a.stage_bytes;
-  int* s_tabU = reinterpret_cast<int*>(gen + ring_bytes);                      // [NPU][KS]
-  int* s_tabV = s_tabU + a.NPU * a.KS;                                          // [NPV][NPOSw]
-  const uint32_t bars = base + ring_bytes + (a.NPU * a.KS + a.NPV * a.NPOSw) * 4;  // full[4], empty[4], done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + ring_bytes + (a.NPU * a.KS + a.NPV * a.NPOSw) * 4 + 8 * 9);
+  const int tab_stride = a.NPU * a.KS + a.NPV * a.NPOSw;
+  int* s_tabU = reinterpret_cast<int*>(gen + ring_bytes);                      // [2][NPU][KS]
+  int* s_tabV = s_tabU + a.NPU * a.KS;                                          // [2][NPV][NPOSw] (interleaved with U per buffer)
+  const uint32_t bars = base + ring_bytes + 2 * (a.NPU * a.KS + a.NPV * a.NPOSw) * 4;  // full[4], empty[4], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + ring_bytes + 2 * (a.NPU * a.KS + a.NPV * a.NPOSw) * 4 + 8 * 9);
   auto full_bar = [&](int st) { return bars + 8u * st; };
   auto empty_bar = [&](int st) { return bars + 8u * (4 + st); };
   const uint32_t done_bar = bars + 8u * 8;
@@ -214,27 +256,29 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
     for (int it = 0; it < nst; ++it) {
       const int st = it % a.nstages;
       const int q0 = qbeg + it * a.KS;
-      // source tables of this stage (shared by the producer threads)
-      asm volatile("bar.sync 1, %0;" ::"n"(WW_PROD) : "memory");
-      if (!(a.dbg & 4))
-      for (int i = tid; i < a.KS; i += WW_PROD) {
-        const int q = q0 + i;
-        for (int p = 0; p < a.NPU; ++p)
-          s_tabU[p * a.KS + i] = q < qend ? ww_src(q, a.Q, a.IP, a.pitch, a.Hq, a.Wq, rIP, rpitch, a.NPU, p, a.hU, a.wU, a.cu) : -1;
-      }
-      if (!(a.dbg & 4))
-      for (int i = tid; i < a.NPOSw; i += WW_PROD) {
-        const int q = q0 - a.lead + i;
-        for (int p = 0; p < a.NPV; ++p)
-          s_tabV[p * a.NPOSw + i] = ww_src(q, a.Q, a.IP, a.pitch, a.Hq, a.Wq, rIP, rpitch, a.NPV, p, a.hV, a.wV, a.cv);
+      // source tables of this stage (shared by the producer threads; double buffered -> one barrier per stage)
+      int* tU = s_tabU + (it & 1) * tab_stride;
+      int* tV = s_tabV + (it & 1) * tab_stride;
+      if (!(a.dbg & 4)) {
+        for (int i = tid; i < a.KS; i += WW_PROD) {
+          const int q = q0 + i;
+          int img = 0, y = 0, x = 0;
+          const bool ok = q < qend && ww_decode(q, a.Q, a.IP, a.pitch, a.Hq, a.Wq, rIP, rpitch, img, y, x);
+          for (int p = 0; p < a.NPU; ++p) tU[p * a.KS + i] = ww_plane_src(ok, img, y, x, a.NPU, p, a.hU, a.wU, a.cu);
+        }
+        for (int i = tid; i < a.NPOSw; i += WW_PROD) {
+          int img = 0, y = 0, x = 0;
+          const bool ok = ww_decode(q0 - a.lead + i, a.Q, a.IP, a.pitch, a.Hq, a.Wq, rIP, rpitch, img, y, x);
+          for (int p = 0; p < a.NPV; ++p) tV[p * a.NPOSw + i] = ww_plane_src(ok, img, y, x, a.NPV, p, a.hV, a.wV, a.cv);
+        }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(WW_PROD) : "memory");
       if (it >= a.nstages) mbar_wait(empty_bar(st), ((it / a.nstages) & 1) ^ 1);
       const uint32_t sb = base + st * a.stage_bytes;
       // ---- U rows: [plane][block][KS rows][128 B], granule g of row r at g ^ (r & 3); then the V window rows
       if (!(a.dbg & 1)) {
-        ww_copy_rows(U, a.one, sb, s_tabU, a.NPU, a.nbU, a.regU, a.KS, a.cu, a.u_ones, 0, tid);
-        ww_copy_rows(V, a.one, sb + (uint32_t)a.v_off, s_tabV, a.NPV, a.nbV, a.regV, a.NPOSw, a.cv, a.v_ones, vg * a.vgch, tid);
+        ww_copy_rows(U, a.one, sb, tU, a.NPU, a.nbU, a.regU, a.KS, a.cu, a.u_ones, 0, tid);
+        ww_copy_rows(V, a.one, sb + (uint32_t)a.v_off, tV, a.NPV, a.nbV, a.regV, a.NPOSw, a.cv, a.v_ones, vg * a.vgch, tid);
       }
       cp_async_arrive_noinc(full_bar(st));
     }
@@ -463,7 +507,7 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
       // still fall inside the stage (their accumulator rows are ignored), so the stage is padded if V is short
       size_t st = (size_t)a.NPU * a.nbU * ks * 128 + (size_t)a.NPV * a.nbV * nposw * 128;
       st = std::max(st, ((size_t)(a.NPU - 1) * a.nbU + 4) * ks * 128);
-      const size_t tabs = ((size_t)a.NPU * ks + (size_t)a.NPV * nposw) * 4;
+      const size_t tabs = 2 * ((size_t)a.NPU * ks + (size_t)a.NPV * nposw) * 4;
       if (want * st + tabs + 128 <= cap) {
         a.KS = ks; a.NPOSw = nposw; a.stage_bytes = (int)st;
         a.nstages = (int)std::min<size_t>(WW_MAXSTAGES, (cap - tabs - 128) / st);
@@ -475,7 +519,7 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
   a.regV = a.NPOSw * 128;
   a.v_off = a.NPU * a.nbU * a.regU;
   a.lboB = a.packed ? 128u : (uint32_t)a.regV;
-  p.smem = 1024 + (size_t)a.nstages * a.stage_bytes + ((size_t)a.NPU * a.KS + (size_t)a.NPV * a.NPOSw) * 4 + 128;
+  p.smem = 1024 + (size_t)a.nstages * a.stage_bytes + 2 * ((size_t)a.NPU * a.KS + (size_t)a.NPV * a.NPOSw) * 4 + 128;
 
   a.SPL = std::max(1, 148 / (S * a.TG));
   a.chunk = (a.Q + a.SPL - 1) / a.SPL;
