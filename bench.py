@@ -301,9 +301,14 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "K2/K3 time-dependent conv stack (conv_gather / conv_wgrad)",
+        "roofline": {"bound": "tensor", "kernel": "K2/K3 time-dependent conv stack (conv_win_kernel / wgrad_win_kernel + "
+                               "conv_tc / wgrad_tc fallbacks; tcgen05 kind::tf32)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "peak_source": peak_src, "traffic": None,
+                     "peak_source": peak_src + "; TF32 dense peak is half of the bf16 figure",
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one conv_win_kernel launch (64->5 data gradient,
+                     # 1024 images 32x32), ncu --set full capture summarised in profiles/r01_summary.md: equals the
+                     # algorithmic bytes (input read once 268.8 MB + output 19.0 MB)
+                     "traffic": 287.8e6,
                      "algorithmic_flops_per_step": alg_flops_step, "kernel_ms_per_step": conv_ms,
                      "share_of_step": conv_ms / (ms / args.steps)},
         "roofline_k1": {"bound": "hbm", "kernel": "K1 wsde_fwd/bwd (cooperative persistent)",

@@ -195,5 +195,48 @@ int main() {
         run(nm, img, ops, idesc_mn, N, R);
       }
   }
+  // ---------------- T_D: M = 64 (cta_group::1): which TMEM lanes hold accumulator rows 0..63? ----------------
+  {
+    const int P = 64, K = 32;
+    const int offB = 64 * 128;
+    std::vector<float> W(P * K), Bm(N * K);
+    for (auto& v : W) v = rv(8);
+    for (auto& v : Bm) v = rv(6);
+    std::vector<uint8_t> img(offB + N * 128, 0);
+    for (int p = 0; p < P; ++p) for (int k = 0; k < K; ++k) memcpy(&img[p * 128 + (((k >> 2) ^ (p & 7)) << 4) + (k & 3) * 4], &W[p * K + k], 4);
+    for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) memcpy(&img[offB + n * 128 + (((k >> 2) ^ (n & 7)) << 4) + (k & 3) * 4], &Bm[n * K + k], 4);
+    std::vector<float> R(64 * N, 0.f);
+    for (int m = 0; m < 64; ++m) for (int n = 0; n < N; ++n) { float s = 0; for (int k = 0; k < K; ++k) s += W[m * K + k] * Bm[n * K + k]; R[m * N + n] = s; }
+    std::vector<MmaOp> ops;
+    for (int ks = 0; ks < K / 8; ++ks) {
+      MmaOp o; memset(&o, 0, sizeof(o));
+      o.a_off = ks * 32; o.b_off = offB + ks * 32;
+      o.a_hi = desc_hi(16, 1024, 2, 0); o.b_hi = desc_hi(16, 1024, 2, 0);
+      o.acc = ks > 0;
+      ops.push_back(o);
+    }
+    const uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((64u >> 4) << 24);
+    uint8_t* dimg; MmaOp* dops; float* dD;
+    cudaMalloc(&dimg, img.size()); cudaMalloc(&dops, ops.size() * sizeof(MmaOp)); cudaMalloc(&dD, 128 * N * 4);
+    cudaMemcpy(dimg, img.data(), img.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(dops, ops.data(), ops.size() * sizeof(MmaOp), cudaMemcpyHostToDevice);
+    cudaMemset(dD, 0xFF, 128 * N * 4);
+    probe<<<1, 128, img.size() + 2048>>>(dimg, (int)img.size(), dops, (int)ops.size(), idesc64, dD, N);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<float> D(128 * N);
+    cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+    printf("T_D M=64: %s ; accumulator row -> TMEM lane:", cudaGetErrorString(e));
+    for (int m = 0; m < 64; ++m) {
+      int found = -1;
+      for (int l = 0; l < 128 && found < 0; ++l) {
+        bool ok = true;
+        for (int n = 0; n < N && ok; ++n) ok = fabsf(D[l * N + n] - R[m * N + n]) < 1e-3f;
+        if (ok) found = l;
+      }
+      if (m % 16 == 0) printf("\n   rows %2d..: ", m);
+      printf("%d ", found);
+    }
+    printf("\n");
+  }
   return 0;
 }
