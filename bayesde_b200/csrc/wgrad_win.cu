@@ -33,7 +33,7 @@ namespace bsde {
 
 using namespace um;
 
-constexpr int WW_PROD_WARPS = 8;
+constexpr int WW_PROD_WARPS = 16;
 constexpr int WW_PROD = WW_PROD_WARPS * 32;  // warps 0-7 producers (warps 0-3 also run the epilogue)
 constexpr int WW_MMA_WARP = WW_PROD_WARPS;
 constexpr int WW_THREADS = (WW_PROD_WARPS + 1) * 32;
