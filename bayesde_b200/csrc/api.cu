@@ -41,7 +41,7 @@ bool tconv_win_supported(const bsde_conv_layer* L, int S, int B);
 size_t tconv_win_ws_bytes(const bsde_conv_layer* L, int S);
 int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const float* w, long long w_sample_stride,
                   float t, int act, int epi, float scale, const float* aux, float* out, void* ws, size_t ws_bytes,
-                  cudaStream_t st, const float* prepacked);
+                  cudaStream_t st, const float* prepacked, int prepacked_safe);
 size_t tconv_win_img_floats(const bsde_conv_layer* L);
 int tconv_win_repack(const bsde_conv_layer* L, int S, int nit, const float* w, long long w_sample_stride, long long w_iter_stride,
                      int epi, float* img, cudaStream_t st);
@@ -75,9 +75,10 @@ static int conv_wgrad(const bsde_conv_layer* L, int S, int B, const float* in, c
 
 static int conv_fwd(const bsde_conv_layer* L, int S, int B, const float* in, const float* w,
                     long long wss, float t, int act, int epi, float scale, const float* aux, float* out,
-                    int math, void* tc_ws, size_t tc_ws_bytes, cudaStream_t st, const float* prepacked = nullptr) {
+                    int math, void* tc_ws, size_t tc_ws_bytes, cudaStream_t st, const float* prepacked = nullptr,
+                    int prepacked_safe = 0) {
   if (math == BSDE_MATH_TC && tconv_win_supported(L, S, B))
-    return tconv_fwd_win(L, S, B, in, w, wss, t, act, epi, scale, aux, out, tc_ws, tc_ws_bytes, st, prepacked);
+    return tconv_fwd_win(L, S, B, in, w, wss, t, act, epi, scale, aux, out, tc_ws, tc_ws_bytes, st, prepacked, prepacked_safe);
   if (math == BSDE_MATH_TC && tconv_tc_supported(L, epi))
     return tconv_fwd_tc(L, S, B, in, w, wss, t, act, epi, scale, aux, out, tc_ws, tc_ws_bytes, st);
   return tconv_fwd_simt(L, S, B, in, w, wss, t, act, epi, scale, aux, out, st);
@@ -258,13 +259,13 @@ extern "C" size_t bsde_xpath_acts_bytes(const bsde_xpath_desc* d) {
 }
 
 static int xpath_recompute(const bsde_xpath_desc* d, const float* x, const float* wk, float t, float* const* a,
-                           void* tc_ws, size_t tc_bytes, cudaStream_t st, const Prepack& pp, int k) {
+                           void* tc_ws, size_t tc_bytes, cudaStream_t st, const Prepack& pp, int k, int& nconv) {
   const int n = d->nlayers;
   const long long wss = (long long)(d->nit + 1) * d->P;
   const float* in = x;
   for (int l = 0; l + 1 < n; ++l) {
     if (int e = conv_fwd(&d->layers[l], d->S, d->B, in, wk, wss, t, d->act, BSDE_EPI_BIAS_ACT, 1.f, nullptr,
-                         a[l], d->math, tc_ws, tc_bytes, st, pp.img[l] ? pp.img[l] + (size_t)k * pp.per_iter[l] : nullptr))
+                         a[l], d->math, tc_ws, tc_bytes, st, pp.img[l] ? pp.img[l] + (size_t)k * pp.per_iter[l] : nullptr, nconv++ > 0))
       return e;
     in = a[l];
   }
@@ -293,6 +294,7 @@ extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const
   const size_t acts_step = xpath_acts_floats(d);
   Prepack pp;
   if (int e = prepack_all(d, 0, true, d_wtraj, (float*)ws, pp, st)) return e;
+  int nconv = 0;  // conv launches since the prepack: the first one must not read the images before its pdl_wait()
   for (int k = 0; k < d->nit; ++k) {
     if (d_acts) {  // keep this iteration's layer outputs for the reverse pass (remat = False)
       float* p = d_acts + (size_t)k * acts_step;
@@ -301,11 +303,11 @@ extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const
     const float* xk = d_xs + (size_t)k * d->x_numel;
     float* xn = d_xs + (size_t)(k + 1) * d->x_numel;
     const float* wk = d_wtraj + (size_t)k * d->P;
-    if (int e = xpath_recompute(d, xk, wk, h_tk[k], a, tc_ws, tc_bytes, st, pp, k)) return e;
+    if (int e = xpath_recompute(d, xk, wk, h_tk[k], a, tc_ws, tc_bytes, st, pp, k, nconv)) return e;
     // last conv + Euler update: x_{k+1} = x_k + dt_k (conv(a_{n-2}) + b)   (sdeint.py:48-50, g_x = 0)
     if (int e = conv_fwd(&d->layers[n - 1], d->S, d->B, a[n - 2], wk, wss, h_tk[k], d->act, BSDE_EPI_EULER,
                          h_dtk[k], xk, xn, d->math, tc_ws, tc_bytes, st,
-                         pp.img[n - 1] ? pp.img[n - 1] + (size_t)k * pp.per_iter[n - 1] : nullptr))
+                         pp.img[n - 1] ? pp.img[n - 1] + (size_t)k * pp.per_iter[n - 1] : nullptr, nconv++ > 0))
       return e;
   }
   return 0;
@@ -338,6 +340,7 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
   ws += wg_bytes;
   Prepack pp;
   if (int e = prepack_all(d, 1, d_acts == nullptr, d_wtraj, (float*)ws, pp, st)) return e;
+  int nconv = 0;
   const long long wss = (long long)(d->nit + 1) * d->P;
   const long long gss = (long long)d->nit * d->P;
 
@@ -352,7 +355,7 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
     if (d_acts) {
       float* p = const_cast<float*>(d_acts) + (size_t)k * xpath_acts_floats(d);
       for (int l = 0; l + 1 < n; ++l) { a[l] = p; p += align_up(act_elems(d, l) * sizeof(float)) / sizeof(float); }
-    } else if (int e = xpath_recompute(d, xk, wk, t, a, tc_ws, tc_bytes, st, pp, k)) {
+    } else if (int e = xpath_recompute(d, xk, wk, t, a, tc_ws, tc_bytes, st, pp, k, nconv)) {
       return e;
     }
     // walk the stack backwards; `dy` is dL/d(conv output of layer l)
@@ -364,13 +367,13 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
       if (l > 0) {
         // dz_{l-1} = sc * dgrad(dy) * act'(a_{l-1})
         if (int e = conv_fwd(&D[l], d->S, d->B, dy, wk, wss, t, d->act, BSDE_EPI_DACT, sc, a[l - 1], dz[l - 1],
-                             d->math, tc_ws, tc_bytes, st, pp.img[n + l] ? pp.img[n + l] + (size_t)k * pp.per_iter[n + l] : nullptr))
+                             d->math, tc_ws, tc_bytes, st, pp.img[n + l] ? pp.img[n + l] + (size_t)k * pp.per_iter[n + l] : nullptr, nconv++ > 0))
           return e;
         dy = dz[l - 1];
       } else {
         // gx_k = gx_{k+1} + dgrad_0(dz_0)   (identity path of the Euler update)
         if (int e = conv_fwd(&D[0], d->S, d->B, dy, wk, wss, t, d->act, BSDE_EPI_ACCUM, sc, d_gx, d_gx,
-                             d->math, tc_ws, tc_bytes, st, pp.img[n] ? pp.img[n] + (size_t)k * pp.per_iter[n] : nullptr))
+                             d->math, tc_ws, tc_bytes, st, pp.img[n] ? pp.img[n] + (size_t)k * pp.per_iter[n] : nullptr, nconv++ > 0))
           return e;
       }
     }

@@ -63,6 +63,7 @@ struct WinArgs {
   float t, scale;
   uint32_t aoff[WN_MAXENT];  // A start offset of each entry in 16-byte units (plane region + shifted row)
   uint32_t dcol[WN_MAXENT];  // accumulator column offset | (first tap of its accumulator) << 31
+  int wsafe;  // the weight image was written before the previous kernel in the stream started: load it before pdl_wait()
   int dbg;  // tools/ only (BSDE_WIN_DBG): 1 skip window copies, 2 skip MMAs, 4 skip epilogue stores
   WinEntry ent[WN_MAXENT];
 };
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
   auto acce_bar = [&](int b) { return bars + 8u * (2 * WN_MAXRING + WN_MAXBUF + b); };
 
   // resident weights + tables: one cooperative copy per CTA
+  if (!a.wsafe) pdl_wait();
   {
     const float* __restrict__ wsrc = a.wimg + (long long)s * a.wimg_sample_stride;
     const int n16 = (a.w_bytes + a.tb_floats * 4) >> 4;
@@ -229,6 +231,8 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (a.wsafe) pdl_wait();      // everything above overlapped the predecessor's tail
+  pdl_launch_dependents();
 
   if (warp >= WN_EPI_WARPS && warp < WN_MMA_WARP) {
     // =============================== producers ===============================
@@ -767,7 +771,7 @@ int tconv_win_repack(const bsde_conv_layer* L, int S, int nit, const float* w, l
 
 int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const float* w, long long w_sample_stride,
                   float t, int act, int epi, float scale, const float* aux, float* out, void* ws, size_t ws_bytes,
-                  cudaStream_t st, const float* prepacked) {
+                  cudaStream_t st, const float* prepacked, int prepacked_safe) {
   WinPlan p = win_plan(L);
   BSDE_CHECK_ARG(p.ok, "layer not supported by the window-staged tensor-core path");
   BSDE_CHECK_ARG(!(epi >= BSDE_EPI_EULER) || aux != nullptr, "epilogue %d needs aux", epi);
@@ -824,7 +828,16 @@ int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const
 #undef WN_PICK
   BSDE_CHECK_ARG(fn != nullptr, "epilogue %d / activation %d not instantiated", epi, act);
   BSDE_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  fn<<<S * a.G, WN_THREADS, p.smem, st>>>(a);
+  static const int pdl = getenv("BSDE_PDL") ? atoi(getenv("BSDE_PDL")) : 1;
+  a.wsafe = (prepacked && pdl) ? prepacked_safe : 0;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(S * a.G); cfg.blockDim = dim3(WN_THREADS); cfg.dynamicSmemBytes = p.smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  BSDE_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, a));
   BSDE_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -78,6 +78,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// programmatic dependent launch: a kernel launched with the stream-serialization attribute may start (and run its
+// prologue) while its predecessor drains; it must not touch the predecessor's outputs before pdl_wait()
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // descriptor bits other than the start address (cute::UMMA::SmemDescriptor, version 1):
 // layout 0 = no swizzle, 1 = SWIZZLE_128B_BASE32B, 2 = SWIZZLE_128B.  Swizzles are applied to absolute
 // shared-memory address bits (tools/umma_probe2.cu), so a start address shifted by whole rows / 16-byte
