@@ -491,9 +491,9 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
       mbar_wait(accf_bar(buf), (it / a.nbuf) & 1);
       tc_fence_after();
       int last_ac = -1;
-#pragma unroll 1
       int ac = 0, ch_i = half;  // item = ac * nchunk + ch_i, stepping by 2 without a division
       while (ch_i >= nchunk) { ch_i -= nchunk; ++ac; }
+#pragma unroll 1
       for (; ac < ((a.dbg & 8) ? 0 : a.NA);) {
         const int n0 = ch_i * 16;
         if (ac != last_ac) {

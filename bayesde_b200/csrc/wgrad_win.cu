@@ -40,6 +40,7 @@ constexpr int WW_THREADS = (WW_PROD_WARPS + 1) * 32;
 constexpr int WW_MAXENT = 9;
 constexpr int WW_MAXSTAGES = 4;
 
+__device__ long long* g_ww_dbg = nullptr;  // tools/stamp_wwin.py: accumulated clock64 phases of CTA 0
 __device__ float ww_one_dev = 1.0f;  // source of the ones channel (copied with cp.async like every other element)
 
 struct WwArgs {
@@ -67,6 +68,30 @@ struct WwArgs {
   float t;
   int dbg;  // tools/ only (BSDE_WW_DBG): 1 skip copies, 2 skip MMAs, 4 skip the source tables
 };
+
+// Per-thread position state of one staged row: every stage advances by KS positions, so (img, y, x) are updated
+// incrementally instead of being decoded (the decode cost ~1500 cycles per stage: tools/stamp_wwin.py).
+struct WwPos { int q, img, y, x; };
+struct WwGeo { int B, Hq, Wq, pitch, IP, adv_img, adv_y, adv_x; };
+__device__ __forceinline__ void ww_pos_init(WwPos& s, int q, const WwGeo& g) {
+  s.q = q;
+  int qq = q, img = 0;
+  if (qq < 0) { qq += g.IP; img = -1; }  // rows before the first position: |q| <= lead < IP
+  img += qq / g.IP;
+  const int r = qq % g.IP;
+  s.img = img; s.y = r / g.pitch; s.x = r % g.pitch;
+}
+__device__ __forceinline__ void ww_pos_advance(WwPos& s, int KS, const WwGeo& g) {
+  s.q += KS;
+  s.img += g.adv_img;
+  s.x += g.adv_x;
+  if (s.x >= g.pitch) { s.x -= g.pitch; ++s.y; }
+  s.y += g.adv_y;
+  if (s.y > g.Hq) { s.y -= g.Hq + 1; ++s.img; }
+}
+__device__ __forceinline__ bool ww_pos_valid(const WwPos& s, const WwGeo& g) {
+  return (unsigned)s.img < (unsigned)g.B && s.y < g.Hq && s.x < g.Wq;
+}
 
 // position -> pixel coordinates on the position grid (returns false on pads / out of range)
 __device__ __forceinline__ bool ww_decode(int q, int Q, int IP, int pitch, int Hq, int Wq, float rIP, float rpitch, int& img, int& y, int& x) {
@@ -180,10 +205,14 @@ __device__ __forceinline__ void ww_issue(const WwArgs& a, int nst, uint32_t base
     for (int e = 0; e < NE; ++e) { ao[e] = a.aoff[0][e]; bo[e] = a.boff[0][e]; }
   }
   const uint32_t nm = (uint32_t)a.Nmma;
+  const bool dbgm = g_ww_dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
+  long long mw = 0, mi = 0;
 #pragma unroll 1
   for (int it = 0; it < nst; ++it) {
+    long long m0 = dbgm ? clock64() : 0;
     const int st = it % a.nstages;
     mbar_wait(bars + 8u * st, (it / a.nstages) & 1);
+    long long m1 = dbgm ? clock64() : 0;
     fence_proxy_async();
     tc_fence_after();
     const uint32_t sb16 = (base + st * a.stage_bytes) >> 4;
@@ -203,7 +232,9 @@ __device__ __forceinline__ void ww_issue(const WwArgs& a, int nst, uint32_t base
       }
     }
     umma_commit_elect(bars + 8u * (4 + st));
+    if (dbgm) { mw += m1 - m0; mi += clock64() - m1; }
   }
+  if (dbgm) { g_ww_dbg[8] = mw; g_ww_dbg[9] = mi; }
   umma_commit_elect(bars + 8u * 8);
 }
 
@@ -252,36 +283,52 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
     const float* __restrict__ U = a.U + (long long)s * a.B * a.hU * a.wU * a.cu;
     const float* __restrict__ V = a.V + (long long)s * a.B * a.hV * a.wV * a.cv;
     const float rIP = 1.0f / (float)a.IP, rpitch = 1.0f / (float)a.pitch;
+    // thread t owns U row t (t < KS) and V window row t (t < NPOSw) of every stage
+    WwGeo geo;
+    geo.B = a.B; geo.Hq = a.Hq; geo.Wq = a.Wq; geo.pitch = a.pitch; geo.IP = a.IP;
+    geo.adv_img = a.KS / a.IP;
+    geo.adv_y = (a.KS % a.IP) / a.pitch;
+    geo.adv_x = (a.KS % a.IP) % a.pitch;
+    WwPos pu, pv;
+    ww_pos_init(pu, qbeg + tid, geo);
+    ww_pos_init(pv, qbeg - a.lead + tid, geo);
+    const bool dbgp = g_ww_dbg && blockIdx.x == 0 && tid == 0;
+    long long ph[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll 1
     for (int it = 0; it < nst; ++it) {
+      long long c0 = dbgp ? clock64() : 0;
       const int st = it % a.nstages;
-      const int q0 = qbeg + it * a.KS;
       // source tables of this stage (shared by the producer threads; double buffered -> one barrier per stage)
       int* tU = s_tabU + (it & 1) * tab_stride;
       int* tV = s_tabV + (it & 1) * tab_stride;
       if (!(a.dbg & 4)) {
-        for (int i = tid; i < a.KS; i += WW_PROD) {
-          const int q = q0 + i;
-          int img = 0, y = 0, x = 0;
-          const bool ok = q < qend && ww_decode(q, a.Q, a.IP, a.pitch, a.Hq, a.Wq, rIP, rpitch, img, y, x);
-          for (int p = 0; p < a.NPU; ++p) tU[p * a.KS + i] = ww_plane_src(ok, img, y, x, a.NPU, p, a.hU, a.wU, a.cu);
+        if (tid < a.KS) {
+          const bool ok = pu.q < qend && ww_pos_valid(pu, geo);
+          for (int p = 0; p < a.NPU; ++p) tU[p * a.KS + tid] = ww_plane_src(ok, pu.img, pu.y, pu.x, a.NPU, p, a.hU, a.wU, a.cu);
         }
-        for (int i = tid; i < a.NPOSw; i += WW_PROD) {
-          int img = 0, y = 0, x = 0;
-          const bool ok = ww_decode(q0 - a.lead + i, a.Q, a.IP, a.pitch, a.Hq, a.Wq, rIP, rpitch, img, y, x);
-          for (int p = 0; p < a.NPV; ++p) tV[p * a.NPOSw + i] = ww_plane_src(ok, img, y, x, a.NPV, p, a.hV, a.wV, a.cv);
+        if (tid < a.NPOSw) {
+          const bool ok = ww_pos_valid(pv, geo);
+          for (int p = 0; p < a.NPV; ++p) tV[p * a.NPOSw + tid] = ww_plane_src(ok, pv.img, pv.y, pv.x, a.NPV, p, a.hV, a.wV, a.cv);
         }
+        ww_pos_advance(pu, a.KS, geo);
+        ww_pos_advance(pv, a.KS, geo);
       }
+      long long c1 = dbgp ? clock64() : 0;
       asm volatile("bar.sync 1, %0;" ::"n"(WW_PROD) : "memory");
+      long long c2 = dbgp ? clock64() : 0;
       if (it >= a.nstages) mbar_wait(empty_bar(st), ((it / a.nstages) & 1) ^ 1);
+      long long c3 = dbgp ? clock64() : 0;
       const uint32_t sb = base + st * a.stage_bytes;
       // ---- U rows: [plane][block][KS rows][128 B], granule g of row r at g ^ (r & 3); then the V window rows
       if (!(a.dbg & 1)) {
         ww_copy_rows(U, a.one, sb, tU, a.NPU, a.nbU, a.regU, a.KS, a.cu, a.u_ones, 0, tid);
         ww_copy_rows(V, a.one, sb + (uint32_t)a.v_off, tV, a.NPV, a.nbV, a.regV, a.NPOSw, a.cv, a.v_ones, vg * a.vgch, tid);
       }
+      long long c4 = dbgp ? clock64() : 0;
       cp_async_arrive_noinc(full_bar(st));
+      if (dbgp) { ph[0] += c1 - c0; ph[1] += c2 - c1; ph[2] += c3 - c2; ph[3] += c4 - c3; ph[4] += clock64() - c4; ph[5] += 1; }
     }
+    if (dbgp) { for (int i = 0; i < 6; ++i) g_ww_dbg[i] = ph[i]; }
 
     // =============================== epilogue (warps 0-3) ===============================
     if (warp < 4) {
@@ -375,7 +422,7 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
   if (mode == 3 && (L->hout != 2 * L->hin || L->wout != 2 * L->win)) return p;
   if (mode == 2 && L->hout > 4) return p;  // measured slower than wgrad_tc.cu: the big operand (4 parity planes x 3 blocks)
                                            // sits on the U side, which every V-channel group reloads
-  { static const int m3 = getenv("BSDE_WW_M3") ? atoi(getenv("BSDE_WW_M3")) : 0; if (mode == 3 && L->hin > 8 && !m3) return p; }  // 16x16 grids: measured on par / slower than wgrad_tc.cu
+  { static const int m3 = getenv("BSDE_WW_M3") ? atoi(getenv("BSDE_WW_M3")) : 1; if (mode == 3 && L->hin > 8 && !m3) return p; }  // 16x16 grids: 234 us vs 256 us (wgrad_tc.cu)
   a.Hq = mode == 3 ? L->hin : L->hout;
   a.Wq = mode == 3 ? L->win : L->wout;
   a.pitch = a.Wq + 1;
@@ -587,3 +634,7 @@ int tconv_wgrad_win(const bsde_conv_layer* L, int S, int B, const float* in, con
 }
 
 }  // namespace bsde
+
+extern "C" int bsde_debug_set_ww_stamps(long long* d_buf) {
+  return cudaMemcpyToSymbol(bsde::g_ww_dbg, &d_buf, sizeof(d_buf)) == cudaSuccess ? 0 : -3;
+}
