@@ -24,6 +24,8 @@
 // swizzled smem transpose -> coalesced Euler / data-gradient combine and store.
 // The time channel never enters the GEMM (spatially constant): t * (sum of the time rows of the taps that
 // fall inside the image), looked up from a 16-entry border-class table per accumulator.
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -60,6 +62,7 @@ struct WinArgs {
   int ring, slab_bytes, w_bytes, tb_floats, nbuf, tmem_cols;
   int hslab, nslab, region;  // halves per slab, slabs per tile, bytes of one (plane, half) region
   int gather;                // stride-2 layers: slabs are per-(tap, half) gathered tiles of 128 rows (no window, no pads)
+  int tma, NR, box_bytes;    // TMA-fed window: NR row boxes {32 ch, Wq+1 px} per (tile, half), each box_bytes
   float t, scale;
   uint32_t aoff[WN_MAXENT];  // A start offset of each entry in 16-byte units (plane region + shifted row)
   uint32_t dcol[WN_MAXENT];  // accumulator column offset | (first tap of its accumulator) << 31
@@ -182,7 +185,7 @@ __device__ __forceinline__ float wn_combine(float q, float x, float scale) {
 }
 
 template <bool VEC, int EPI, int ACT>
-__global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_constant__ WinArgs a) {
+__global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_constant__ WinArgs a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s = blockIdx.x / a.G, g = blockIdx.x - s * a.G;
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
   }
   if (warp == WN_MMA_WARP) {
     if (lane == 0) {
-      for (int i = 0; i < a.ring; ++i) { mbar_init(full_bar(i), WN_PROD); mbar_init(empty_bar(i), 1); }
+      for (int i = 0; i < a.ring; ++i) { mbar_init(full_bar(i), a.tma ? 1 : WN_PROD); mbar_init(empty_bar(i), 1); }
       for (int b = 0; b < WN_MAXBUF; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), WN_EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -241,6 +244,47 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
     const int c = pt & 7;  // 16-byte chunk inside the 128-byte row: 8 lanes cover one row / one global line
     const float rIP = 1.0f / (float)a.IP, rpitch = 1.0f / (float)a.pitch;
     uint32_t cnt = 0;
+    if (a.tma) {
+      // ---- TMA-fed window: one elected thread issues NR row boxes {32 channels, Wq+1 pixels} per half.  The pixel
+      // past the row end, the row past the image end and images outside [0, S*B) are out of bounds -> zero filled:
+      // exactly the pad column / pad row of the flattened position grid.  Destinations are 128-byte aligned rows of
+      // the SWIZZLE_128B region (tools/tma_probe.cu: the TMA swizzle is a function of the absolute smem address).
+      if (pt < 32) {
+        // lane r issues the box of window row r (r < NR); lane 0 arms the barrier first
+        const int rows_img = a.Hq + 1;
+#pragma unroll 1
+        for (int tile = g; tile < a.ntiles; tile += a.G) {
+          const int n0 = tile * 128 - a.lead;
+          const int g0 = (n0 + 2 * a.pitch) / a.pitch - 2 + pt;  // floor(n0 / pitch) + r, n0 >= -(pitch + 1)
+          const int img = (g0 + rows_img) / rows_img - 1;         // floor(g0 / rows_img), g0 >= -2
+          const int y = g0 - img * rows_img;
+#pragma unroll 1
+          for (int sl = 0; sl < a.nslab; ++sl, ++cnt) {
+            const int slot = cnt % a.ring;
+            if (cnt >= (uint32_t)a.ring) mbar_wait(empty_bar(slot), ((cnt / a.ring) & 1) ^ 1);
+            const uint32_t sb = s_ring + slot * a.slab_bytes;
+            const int h0 = sl * a.hslab;
+            const int hend = min(a.hslab, a.nhalf - h0);
+            if (!(a.dbg & 1)) {
+              if (pt == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(slot)), "r"(hend * a.NR * a.box_bytes) : "memory");
+              __syncwarp();
+              if (pt < a.NR) {
+                for (int hs = 0; hs < hend; ++hs) {
+                  const uint32_t dst = sb + (uint32_t)hs * (uint32_t)a.region + (uint32_t)(pt * a.box_bytes);
+                  asm volatile(
+                      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                      "l"(&tmap), "r"(full_bar(slot)), "r"((h0 + hs) * 32), "r"(0), "r"(y), "r"(s * a.B + img)
+                      : "memory");
+                }
+              }
+            } else if (pt == 0) {
+              mbar_arrive(full_bar(slot));
+            }
+          }
+        }
+      }
+    } else
     if (a.gather) {
       // ---- stride-2 layers: per-(tap, half) gathered slabs; one table entry per output position of the tile
       const int r0 = pt >> 3;
@@ -382,6 +426,13 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
       const uint64_t b_hi = desc_hi((uint32_t)a.npad * 16u, 128u, 0);
       const uint32_t w16 = s_w >> 4, bstep = (uint32_t)(a.npad * 32) >> 4, region16 = (uint32_t)a.region >> 4;
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      // per-tap constants of the unrolled 3x3 issue path, loaded once (uniform registers)
+      uint32_t e_ao[9], e_bo[9], e_dc[9], e_fl[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) {
+        e_ao[e] = a.aoff[e]; e_bo[e] = (uint32_t)(e * a.nks) * bstep;
+        e_dc[e] = a.dcol[e] & 0xFFFFu; e_fl[e] = (a.dcol[e] >> 31) ^ 1u;
+      }
       uint32_t cnt = 0;
       int it = 0;
 #pragma unroll 1
@@ -392,6 +443,12 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
           tc_fence_after();
         }
         const uint32_t dbase = tm + (uint32_t)(buf * a.NA * a.npad);
+        uint32_t o0 = 0;  // TMA-fed window: positions of the first grid row before position q0 - lead, in 16-byte units
+        if (a.tma) {
+          const int n0 = tile * 128 - a.lead;
+          const int g0 = (n0 + 2 * a.pitch) / a.pitch - 2;
+          o0 = (uint32_t)(n0 - g0 * a.pitch) * 8u;
+        }
         if (a.gather) {
           // slabs arrive in (tap, half) order; each holds four k-steps of one tap: unshifted K-major SW128 tile
 #pragma unroll 1
@@ -432,7 +489,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
 #pragma unroll 1
             for (int kk = 0; kk < kend; ++kk) {
               // k-step kk of the slab: half kk >> 2 (region stride), 32-byte step kk & 3 inside the 128-byte row
-              const uint32_t ka = sb16 + (uint32_t)(kk >> 2) * region16 + (uint32_t)(kk & 3) * 2u;
+              const uint32_t ka = sb16 + o0 + (uint32_t)(kk >> 2) * region16 + (uint32_t)(kk & 3) * 2u;
               const uint32_t kb = w16 + (uint32_t)(ks0 + kk) * bstep;
               const uint32_t later = (ks0 + kk) > 0 ? 1u : 0u;
 #define WN_ISSUE(e)                                                                                         \
@@ -444,7 +501,9 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
   }
               if (a.nent == 9) {
 #pragma unroll
-                for (int e = 0; e < 9; ++e) WN_ISSUE(e)
+                for (int e = 0; e < 9; ++e)
+                  umma_tf32_elect(dbase + e_dc[e], a_hi | (uint64_t)((ka + e_ao[e]) & 0x3FFFu), b_hi | (uint64_t)((kb + e_bo[e]) & 0x3FFFu),
+                                  idesc, later | e_fl[e]);
               } else {
 #pragma unroll 1
                 for (int e = 0; e < a.nent; ++e) WN_ISSUE(e)
@@ -598,7 +657,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
 struct WinPlan {
   bool ok;
   int mode, NA, NP, nent, Hq, Wq, pitch, IP, lead, trail, NPOSw, nks, npad, ring, slab_bytes, w_bytes, tb_floats;
-  int tab_units, nbuf, tmem_cols, vec, nhalf, hslab, nslab, region, tb_rows, gather;
+  int tab_units, nbuf, tmem_cols, vec, nhalf, hslab, nslab, region, tb_rows, gather, tma, NR, box_bytes;
   size_t smem, img_floats;
   WinEntry ent[WN_MAXENT];
   int ent_tap[WN_MAXENT];
@@ -670,6 +729,14 @@ static WinPlan win_plan(const bsde_conv_layer* L) {
   p.npad = (L->cout + 15) / 16 * 16;
   p.nhalf = (L->cin + 31) / 32;
   p.region = p.NPOSw * 128;  // one (plane, 32-channel half) SWIZZLE_128B region; NPOSw % 8 == 0 keeps it 1024-byte aligned
+  // TMA-fed window (input channels a multiple of 32, single input plane): the window buffer holds NR whole grid rows
+  static const int tma_on = getenv("BSDE_TMA") ? atoi(getenv("BSDE_TMA")) : 1;
+  if (tma_on && p.vec && (L->cin % 32) == 0 && p.NP == 1 && p.Wq + 1 <= 256) {
+    p.tma = 1;
+    p.NR = (p.lead + 128 + p.trail + p.pitch - 2) / p.pitch + 1;   // grid rows any 128-position window (+ halo) can touch
+    p.box_bytes = p.pitch * 128;
+    p.region = (p.NR * p.box_bytes + 128 + 1023) & ~1023;          // + one slack row for the last shifted read
+  }
   p.w_bytes = p.nent * p.nks * p.npad * 32;
   p.tb_rows = L->has_time ? 1 + 16 * p.NA : 1;
   p.tb_floats = p.tb_rows * p.npad;
@@ -687,7 +754,7 @@ static WinPlan win_plan(const bsde_conv_layer* L) {
   for (int ci = 0; ci < 2 && !p.hslab; ++ci) {
     const int k = cands[ci];
     const size_t slab = (size_t)p.NP * k * p.region;
-    if (fixed + 2 * slab <= cap) { p.hslab = k; p.slab_bytes = (int)slab; }
+    if (fixed + (p.tma && k > 1 ? 3 : 2) * slab <= cap) { p.hslab = k; p.slab_bytes = (int)slab; }
   }
   if (!p.hslab) {
     // Stride-2 layer whose four parity-plane windows do not fit beside the resident weights: keep the persistent
@@ -798,6 +865,7 @@ int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const
   a.nent = p.nent; a.ring = p.ring; a.slab_bytes = p.slab_bytes; a.w_bytes = p.w_bytes; a.tb_floats = p.tb_floats;
   a.nbuf = p.nbuf; a.tmem_cols = p.tmem_cols;
   a.hslab = p.hslab; a.nslab = p.nslab; a.region = p.region; a.gather = p.gather;
+  a.tma = p.gather ? 0 : p.tma; a.NR = p.NR; a.box_bytes = p.box_bytes;
   a.t = t; a.scale = scale;
   { static const int dbg = getenv("BSDE_WIN_DBG") ? atoi(getenv("BSDE_WIN_DBG")) : 0; a.dbg = dbg; }
   for (int e = 0; e < p.nent; ++e) {
@@ -808,7 +876,7 @@ int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const
     a.dcol[e] = (uint32_t)(p.ent[e].acc * p.npad) | (first ? 0x80000000u : 0u);
   }
   // one instantiation per (producer path, epilogue, activation); activation only matters for BIAS_ACT / DACT
-  using KernelFn = void (*)(const WinArgs);
+  using KernelFn = void (*)(const WinArgs, const CUtensorMap);
   KernelFn fn = nullptr;
   const bool uses_act = epi == BSDE_EPI_BIAS_ACT || epi == BSDE_EPI_DACT;
   const int actk = uses_act ? act : BSDE_ACT_NONE;
@@ -837,7 +905,29 @@ int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  BSDE_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, a));
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (a.tma) {
+    // input tensor [S*B][hin][win][cin] fp32; box = one grid row of one 32-channel half (+ the out-of-bounds pad pixel)
+    using EncodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled enc = nullptr;
+    if (!enc) {
+      cudaDriverEntryPointQueryResult qres;
+      BSDE_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&enc, cudaEnableDefault, &qres));
+      if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return BSDE_ERR_CUDA; }
+    }
+    const cuuint64_t dims[4] = {(cuuint64_t)L->cin, (cuuint64_t)L->win, (cuuint64_t)L->hin, (cuuint64_t)S * B};
+    const cuuint64_t strides[3] = {(cuuint64_t)L->cin * 4, (cuuint64_t)L->win * L->cin * 4, (cuuint64_t)L->hin * L->win * L->cin * 4};
+    const cuuint32_t box[4] = {32, (cuuint32_t)p.pitch, 1, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return BSDE_ERR_CUDA; }
+  }
+  BSDE_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, a, tmap));
   BSDE_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
