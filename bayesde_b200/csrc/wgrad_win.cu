@@ -22,6 +22,8 @@
 // CTAs split the positions of a sample (and, when 9 accumulators exceed the 512 TMEM columns, the taps);
 // partial tiles go to the workspace in the layout of wgrad_reduce_kernel (tconv_simt.cu), which finishes
 // in a fixed order (no atomics: run-to-run deterministic).
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -53,6 +55,7 @@ struct WwArgs {
   int nbU, nbV, NPU, NPV;         // 32-channel blocks, parity planes of each operand
   int hU, wU, hV, wV;             // spatial extent of the tensors behind U and V
   int KS, NPOSw, lead, regU, regV, stage_bytes, v_off, nstages;  // rows per stage, V window rows, region bytes
+  int tmaU, tmaV, NRU, NRV, box_bytes;  // TMA-fed operands: NR grid-row boxes {32 ch, pitch px} per (plane, block), box_bytes each
   int SPL, TG, chunk, vgch;       // position splits, V channel groups, positions per split, V channels per group
   int Nmma;                       // N of every MMA
   uint32_t lboB;                  // LBO of the B descriptor: regV (channel blocks) or 128 (packed taps)
@@ -193,7 +196,7 @@ __device__ __forceinline__ void ww_copy_rows(const float* __restrict__ src, cons
 
 // MMA issue loop of one CTA; NE > 0: entry count known at compile time (descriptor offsets stay in uniform registers)
 template <int NE>
-__device__ __forceinline__ void ww_issue(const WwArgs& a, int nst, uint32_t base, uint32_t bars, uint32_t tm) {
+__device__ __forceinline__ void ww_issue(const WwArgs& a, int nst, int qbeg, uint32_t base, uint32_t bars, uint32_t tm) {
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                          ((uint32_t)(a.Nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint64_t a_hi = desc_hi((uint32_t)a.regU, 512u, 1);
@@ -216,6 +219,11 @@ __device__ __forceinline__ void ww_issue(const WwArgs& a, int nst, uint32_t base
     fence_proxy_async();
     tc_fence_after();
     const uint32_t sb16 = (base + st * a.stage_bytes) >> 4;
+    // TMA-fed regions start at a grid-row boundary: the stage's first position sits oU / oV rows into them
+    const int q0 = qbeg + it * a.KS;
+    const uint32_t oU = a.tmaU ? (uint32_t)(q0 % a.pitch) * 8u : 0u;
+    const int nv = q0 - a.lead;
+    const uint32_t oV = a.tmaV ? (uint32_t)(nv - ((nv + 2 * a.pitch) / a.pitch - 2) * a.pitch) * 8u : 0u;
 #pragma unroll 1
     for (int ks = 0; ks < ((a.dbg & 2) ? 0 : a.KS / 8); ++ks) {
       const uint32_t kofs = sb16 + (uint32_t)ks * 64u;  // 8 rows x 128 B
@@ -223,12 +231,12 @@ __device__ __forceinline__ void ww_issue(const WwArgs& a, int nst, uint32_t base
       if (NE > 0) {
 #pragma unroll
         for (int e = 0; e < NE; ++e)
-          umma_tf32_elect(tm + (uint32_t)e * nm, a_hi | (uint64_t)((kofs + ao[e]) & 0x3FFFu), b_hi | (uint64_t)((kofs + bo[e]) & 0x3FFFu), idesc, acc);
+          umma_tf32_elect(tm + (uint32_t)e * nm, a_hi | (uint64_t)((kofs + oU + ao[e]) & 0x3FFFu), b_hi | (uint64_t)((kofs + oV + bo[e]) & 0x3FFFu), idesc, acc);
       } else {
 #pragma unroll 1
         for (int e = 0; e < ncnt; ++e)
-          umma_tf32_elect(tm + (uint32_t)e * nm, a_hi | (uint64_t)((kofs + a.aoff[0][e]) & 0x3FFFu),
-                          b_hi | (uint64_t)((kofs + a.boff[0][e]) & 0x3FFFu), idesc, acc);
+          umma_tf32_elect(tm + (uint32_t)e * nm, a_hi | (uint64_t)((kofs + oU + a.aoff[0][e]) & 0x3FFFu),
+                          b_hi | (uint64_t)((kofs + oV + a.boff[0][e]) & 0x3FFFu), idesc, acc);
       }
     }
     umma_commit_elect(bars + 8u * (4 + st));
@@ -238,7 +246,8 @@ __device__ __forceinline__ void ww_issue(const WwArgs& a, int nst, uint32_t base
   umma_commit_elect(bars + 8u * 8);
 }
 
-__global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_constant__ WwArgs a) {
+__global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_constant__ WwArgs a, const __grid_constant__ CUtensorMap tmU,
+                                                                  const __grid_constant__ CUtensorMap tmV) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s = blockIdx.x / (a.TG * a.SPL);
@@ -265,7 +274,7 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
   for (int i = tid; i < ring_bytes >> 4; i += WW_THREADS) reinterpret_cast<uint4*>(gen)[i] = make_uint4(0, 0, 0, 0);
   if (warp == WW_MMA_WARP) {
     if (lane == 0) {
-      for (int i = 0; i < a.nstages; ++i) { mbar_init(full_bar(i), WW_PROD); mbar_init(empty_bar(i), 1); }
+      for (int i = 0; i < a.nstages; ++i) { mbar_init(full_bar(i), WW_PROD + ((a.tmaU | a.tmaV) ? 1 : 0)); mbar_init(empty_bar(i), 1); }
       mbar_init(done_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -302,11 +311,11 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
       int* tU = s_tabU + (it & 1) * tab_stride;
       int* tV = s_tabV + (it & 1) * tab_stride;
       if (!(a.dbg & 4)) {
-        if (tid < a.KS) {
+        if (!a.tmaU && tid < a.KS) {
           const bool ok = pu.q < qend && ww_pos_valid(pu, geo);
           for (int p = 0; p < a.NPU; ++p) tU[p * a.KS + tid] = ww_plane_src(ok, pu.img, pu.y, pu.x, a.NPU, p, a.hU, a.wU, a.cu);
         }
-        if (tid < a.NPOSw) {
+        if (!a.tmaV && tid < a.NPOSw) {
           const bool ok = ww_pos_valid(pv, geo);
           for (int p = 0; p < a.NPV; ++p) tV[p * a.NPOSw + tid] = ww_plane_src(ok, pv.img, pv.y, pv.x, a.NPV, p, a.hV, a.wV, a.cv);
         }
@@ -314,16 +323,70 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
         ww_pos_advance(pv, a.KS, geo);
       }
       long long c1 = dbgp ? clock64() : 0;
-      asm volatile("bar.sync 1, %0;" ::"n"(WW_PROD) : "memory");
+      if (!(a.tmaU && a.tmaV)) asm volatile("bar.sync 1, %0;" ::"n"(WW_PROD) : "memory");
       long long c2 = dbgp ? clock64() : 0;
       if (it >= a.nstages) mbar_wait(empty_bar(st), ((it / a.nstages) & 1) ^ 1);
       long long c3 = dbgp ? clock64() : 0;
       const uint32_t sb = base + st * a.stage_bytes;
       // ---- U rows: [plane][block][KS rows][128 B], granule g of row r at g ^ (r & 3); then the V window rows
       if (!(a.dbg & 1)) {
-        ww_copy_rows(U, a.one, sb, tU, a.NPU, a.nbU, a.regU, a.KS, a.cu, a.u_ones, 0, tid);
-        ww_copy_rows(V, a.one, sb + (uint32_t)a.v_off, tV, a.NPV, a.nbV, a.regV, a.NPOSw, a.cv, a.v_ones, vg * a.vgch, tid);
+        if (a.tmaU | a.tmaV) {
+          // ---- TMA-fed operands: one box {32 channels, pitch pixels} per (plane, block, grid row); the pixel past the
+          // row end / the row past the image end / images past the sample end are out of bounds -> zero fill = the pads.
+          // (tools/tma_probe.cu: SWIZZLE_128B_ATOM_32B == the BASE32B operand layout, absolute-address swizzle, and
+          // elementStrides = 2 yields the compact parity-plane rows.)
+          const int q0 = qbeg + it * a.KS;
+          const int rows_img = a.Hq + 1;
+          const int gU = q0 / a.pitch;
+          const int gV = (q0 - a.lead + 2 * a.pitch) / a.pitch - 2;   // floor((q0 - lead) / pitch), q0 - lead >= -(pitch + 1)
+          const int nbUr = a.cu >> 5;                                   // real 32-channel blocks of U (a ones block is not TMA-fed)
+          const int nbxU = a.tmaU ? a.NPU * nbUr * a.NRU : 0;
+          const int nbxV = a.tmaV ? a.NPV * a.nbV * a.NRV : 0;
+          if (warp == 0) {
+            if (lane == 0)
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_bar(st)), "r"((nbxU + nbxV) * a.box_bytes) : "memory");
+            __syncwarp();
+#pragma unroll 1
+            for (int idx = lane; idx < nbxU + nbxV; idx += 32) {
+              const bool isV = idx >= nbxU;
+              const int j = isV ? idx - nbxU : idx;
+              const int NR = isV ? a.NRV : a.NRU, nb = isV ? a.nbV : nbUr, np = isV ? a.NPV : a.NPU;
+              const int r = j % NR, tt = j / NR;
+              const int b = tt % nb, pl = tt / nb;
+              const int gg = (isV ? gV : gU) + r;
+              const int img = (gg + 2 * rows_img) / rows_img - 2;        // floor(gg / rows_img), gg >= -2
+              const int y = gg - img * rows_img;
+              const int yy = np == 4 ? 2 * y + (pl >> 1) : y, x0 = np == 4 ? (pl & 1) : 0;
+              const int c0 = (isV ? vg * a.vgch : 0) + b * 32;
+              const uint32_t dst = sb + (isV ? (uint32_t)a.v_off + (uint32_t)((pl * a.nbV + b) * a.regV) : (uint32_t)((pl * a.nbU + b) * a.regU)) +
+                                   (uint32_t)(r * a.box_bytes);
+              const CUtensorMap* tm = isV ? &tmV : &tmU;
+              asm volatile(
+                  "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+                  "l"(tm), "r"(full_bar(st)), "r"(c0), "r"(x0), "r"(yy), "r"(img), "r"(s)
+                  : "memory");
+            }
+          }
+          if (a.tmaU && a.u_ones && tid < a.NRU * a.pitch) {
+            // the ones channel of a TMA-fed U: one element per region row (region rows are whole grid rows)
+            const int ry = tid / a.pitch, x = tid - ry * a.pitch;
+            const int gg = gU + ry;
+            const int img = gg / rows_img, y = gg - img * rows_img;
+            const bool pv = img < a.B && y < a.Hq && x < a.Wq;
+            const int e = a.cu & 31;
+            for (int pl = 0; pl < a.NPU; ++pl) {
+              int yy = y, xx = x;
+              if (a.NPU == 4) { yy = 2 * y + (pl >> 1); xx = 2 * x + (pl & 1); }
+              const bool ok = pv && yy < a.hU && xx < a.wU;
+              const uint32_t d = sb + (uint32_t)((pl * a.nbU + (a.cu >> 5)) * a.regU) + tid * 128 + ((((e >> 3) ^ (tid & 3)) << 5) | ((e & 7) << 2));
+              cp_async4(d, a.one, ok);
+            }
+          }
+        }
+        if (!a.tmaU) ww_copy_rows(U, a.one, sb, tU, a.NPU, a.nbU, a.regU, a.KS, a.cu, a.u_ones, 0, tid);
+        if (!a.tmaV) ww_copy_rows(V, a.one, sb + (uint32_t)a.v_off, tV, a.NPV, a.nbV, a.regV, a.NPOSw, a.cv, a.v_ones, vg * a.vgch, tid);
       }
+      if ((a.dbg & 1) && (a.tmaU | a.tmaV) && tid == 0) mbar_arrive(full_bar(st));  // stands in for the expect_tx arrival
       long long c4 = dbgp ? clock64() : 0;
       cp_async_arrive_noinc(full_bar(st));
       if (dbgp) { ph[0] += c1 - c0; ph[1] += c2 - c1; ph[2] += c3 - c2; ph[3] += c4 - c3; ph[4] += clock64() - c4; ph[5] += 1; }
@@ -382,9 +445,9 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
     // whole warp, uniform operands, one elected lane issues
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int ncnt = a.ncnt[tg];
-    if (ncnt == 9) ww_issue<9>(a, nst, base, bars, tm);
-    else if (ncnt == 3) ww_issue<3>(a, nst, base, bars, tm);
-    else ww_issue<0>(a, nst, base, bars, tm);
+    if (ncnt == 9) ww_issue<9>(a, nst, qbeg, base, bars, tm);
+    else if (ncnt == 3) ww_issue<3>(a, nst, qbeg, base, bars, tm);
+    else ww_issue<0>(a, nst, qbeg, base, bars, tm);
     __syncwarp();
   }
   tc_fence_before();
@@ -545,25 +608,33 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
   // stage size and ring depth: prefer >= 3 stages in flight (latency hiding), then the largest KS
   const size_t cap = 227 * 1024 - 2048;
   a.KS = 0;
-  static const int ks_min = getenv("BSDE_WW_KSMIN") ? atoi(getenv("BSDE_WW_KSMIN")) : 0;
-  for (int want = 3; want >= 2 && !a.KS; --want)
-    for (int ks : {128, 64, 32, 16}) {
-      if (want == 3 && ks < ks_min) continue;
+  // TMA-fed operands are exact (GPU parity green) but measured 3-35 % slower than the LDGSTS producers on every layer
+  // (profiles/r01_summary.md): opt-in
+  static const int tma_on = getenv("BSDE_WW_TMA") ? atoi(getenv("BSDE_WW_TMA")) : 0;
+  a.tmaU = tma_on && (a.cu % 32) == 0 && 2 * a.pitch <= 256;
+  a.tmaV = tma_on && (a.cv % 32) == 0 && !a.v_ones && 2 * a.pitch <= 256;
+  a.box_bytes = a.pitch * 128;
+  auto rup = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  // larger stages first (the per-stage fixed cost is ~2-3 k cycles), then ring depth
+  for (int ks : {128, 64, 32, 16})
+    for (int want = 3; want >= 2 && !a.KS; --want) {
       const int nposw = (a.lead + ks + trail + 7) & ~7;
+      const int nru = (ks + a.pitch - 2) / a.pitch + 1, nrv = (a.lead + ks + trail + a.pitch - 2) / a.pitch + 1;
+      const size_t regU = a.tmaU ? rup((size_t)nru * a.pitch * 128) : (size_t)ks * 128;
+      const size_t regV = a.tmaV ? rup((size_t)nrv * a.pitch * 128 + 256) : (size_t)nposw * 128;
+      if ((a.tmaU && nru * a.pitch > WW_PROD) || regU > 0x3FFFFu || regV > 0x3FFFFu) continue;
       // an M=128 MMA always reads four 32-channel blocks `regU` apart: when U has fewer, the surplus blocks must
       // still fall inside the stage (their accumulator rows are ignored), so the stage is padded if V is short
-      size_t st = (size_t)a.NPU * a.nbU * ks * 128 + (size_t)a.NPV * a.nbV * nposw * 128;
-      st = std::max(st, ((size_t)(a.NPU - 1) * a.nbU + 4) * ks * 128);
+      size_t st = (size_t)a.NPU * a.nbU * regU + (size_t)a.NPV * a.nbV * regV;
+      st = std::max(st, ((size_t)(a.NPU - 1) * a.nbU + 4) * regU + 2048);
       const size_t tabs = 2 * ((size_t)a.NPU * ks + (size_t)a.NPV * nposw) * 4;
       if (want * st + tabs + 128 <= cap) {
-        a.KS = ks; a.NPOSw = nposw; a.stage_bytes = (int)st;
+        a.KS = ks; a.NPOSw = nposw; a.stage_bytes = (int)st; a.NRU = nru; a.NRV = nrv; a.regU = (int)regU; a.regV = (int)regV;
         a.nstages = (int)std::min<size_t>(WW_MAXSTAGES, (cap - tabs - 128) / st);
         break;
       }
     }
   if (!a.KS) return p;
-  a.regU = a.KS * 128;
-  a.regV = a.NPOSw * 128;
   a.v_off = a.NPU * a.nbU * a.regU;
   a.lboB = a.packed ? 128u : (uint32_t)a.regV;
   p.smem = 1024 + (size_t)a.nstages * a.stage_bytes + 2 * ((size_t)a.NPU * a.KS + (size_t)a.NPV * a.NPOSw) * 4 + 128;
@@ -615,7 +686,36 @@ int tconv_wgrad_win(const bsde_conv_layer* L, int S, int B, const float* in, con
     BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  wgrad_win_kernel<<<S * a.TG * a.SPL, WW_THREADS, p.smem, st>>>(a);
+  CUtensorMap tmU, tmV;
+  memset(&tmU, 0, sizeof(tmU));
+  memset(&tmV, 0, sizeof(tmV));
+  if (a.tmaU || a.tmaV) {
+    using EncodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled enc = nullptr;
+    if (!enc) {
+      cudaDriverEntryPointQueryResult qres;
+      BSDE_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&enc, cudaEnableDefault, &qres));
+      if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return BSDE_ERR_CUDA; }
+    }
+    // [S][B][h][w][c] fp32, rank 5 so that images past the end of a sample are out of bounds (zero filled)
+    auto make = [&](CUtensorMap* tm, const float* ptr, int c, int w, int h, int np) -> int {
+      const cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B, (cuuint64_t)S};
+      const cuuint64_t strides[4] = {(cuuint64_t)c * 4, (cuuint64_t)w * c * 4, (cuuint64_t)h * w * c * 4, (cuuint64_t)B * h * w * c * 4};
+      const cuuint32_t es1 = np == 4 ? 2u : 1u;
+      const cuuint32_t box[5] = {32, (cuuint32_t)a.pitch * es1, 1, 1, 1};
+      const cuuint32_t es[5] = {1, es1, 1, 1, 1};
+      const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(ptr), dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return BSDE_ERR_CUDA; }
+      return 0;
+    };
+    if (a.tmaU) { if (int e = make(&tmU, a.U, a.cu, a.wU, a.hU, a.NPU)) return e; }
+    if (a.tmaV) { if (int e = make(&tmV, a.V, a.cv, a.wV, a.hV, a.NPV)) return e; }
+  }
+  wgrad_win_kernel<<<S * a.TG * a.SPL, WW_THREADS, p.smem, st>>>(a, tmU, tmV);
   BSDE_CUDA_OK(cudaGetLastError());
   count_launch();
 

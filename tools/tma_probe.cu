@@ -92,5 +92,41 @@ int main() {
     printf("   absolute-address swizzle matches %d/%d, box-relative %d/%d, oob rows %d, sentinel before %d after %d\n", abs_ok, tot,
            rel_ok, tot, zero_rows, (int)before, (int)after);
   }
+  // ---------------- part 2: SWIZZLE_128B_ATOM_32B (the MN-major BASE32B operand layout) and elementStrides = 2 ----------------
+  {
+    CUtensorMap tm2;
+    cuuint32_t box2[4] = {32, 2 * 5, 1, 1};   // 5 pixels with traversal stride 2 -> boxDim = 10
+    cuuint32_t es2[4] = {1, 2, 1, 1};
+    CUresult r2 = enc(&tm2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dT, dims, strides, box2, es2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("encode ATOM_32B + stride 2: %d\n", (int)r2);
+    if (r2 == CUDA_SUCCESS) {
+      struct Case2 { int off, c0, x0, y0, n0; } cases2[] = {{0, 0, 0, 1, 1}, {128, 32, 1, 2, 0}, {384, 0, 1, 3, 1}, {640, 0, 0, 1, 1}};
+      for (auto cs : cases2) {
+        probe<<<1, 128, 16 * 1024>>>(tm2, cs.off, cs.c0, cs.x0, cs.y0, cs.n0, 5 * 128, dOut);
+        cudaError_t ee = cudaDeviceSynchronize();
+        std::vector<float> o(2048);
+        cudaMemcpy(o.data(), dOut, 8192, cudaMemcpyDeviceToHost);
+        printf("case2 off %d c0 %d x0 %d y %d n %d: %s\n", cs.off, cs.c0, cs.x0, cs.y0, cs.n0, cudaGetErrorString(ee));
+        if (ee != cudaSuccess) return 1;
+        int abs_ok = 0, rel_ok = 0, tot = 0;
+        for (int bx = 0; bx < 5; ++bx) {
+          const int x = cs.x0 + 2 * bx;   // strided traversal
+          const bool inb = x < W;
+          const int row_byte = cs.off + bx * 128;
+          for (int c = 0; c < 8; ++c) {   // 16-byte chunk c: granule c >> 1, half c & 1
+            const float want = inb ? (float)(((cs.n0 * H + cs.y0) * W + x) * C + cs.c0 + c * 4) : 0.f;
+            const int slot_abs = (((c >> 1) ^ ((row_byte >> 7) & 3)) << 1) | (c & 1);
+            const int slot_rel = (((c >> 1) ^ (bx & 3)) << 1) | (c & 1);
+            ++tot;
+            if (o[(row_byte + slot_abs * 16) / 4] == want) ++abs_ok;
+            if (o[(row_byte + slot_rel * 16) / 4] == want) ++rel_ok;
+          }
+        }
+        printf("   ATOM_32B, stride 2: absolute-address granule swizzle matches %d/%d, box-relative %d/%d, sentinel after %d\n", abs_ok, tot, rel_ok,
+               tot, (int)(o[(cs.off + 5 * 128) / 4] == -1.0f));
+      }
+    }
+  }
   return 0;
 }
