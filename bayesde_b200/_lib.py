@@ -25,13 +25,14 @@ class FwParams(C.Structure):
     _fields_ = ([("P", C.c_int32), ("nhid", C.c_int32), ("dims", C.c_int32 * (FW_MAX_MID + 2)), ("act", C.c_int32)]
                 + [(n, C.c_void_p) for n in ("W1", "b1", "wt1", "wtb1", "bt1")]
                 + [(n, C.c_void_p * FW_MAX_MID) for n in ("Wm", "bm", "wtm", "wtbm", "btm")]
-                + [(n, C.c_void_p) for n in ("W4", "b4", "wt4", "wtb4", "bt4")])
+                + [(n, C.c_void_p) for n in ("W4", "b4", "wt4", "wtb4", "bt4")] + [("plain", C.c_int32)])
 
 
 class WsdeDesc(C.Structure):
     _fields_ = [("S", C.c_int32), ("nit", C.c_int32), ("stl", C.c_int32), ("w0_per_sample", C.c_int32),
                 ("sigma", C.c_float), ("kl_weight", C.c_float), ("ou_coef", C.c_float),
-                ("seed", C.c_uint64), ("stream_id", C.c_uint32)]
+                ("seed", C.c_uint64), ("stream_id", C.c_uint32),
+                ("d_dtkl", C.c_void_p), ("d_nscale", C.c_void_p), ("d_nidx", C.c_void_p), ("d_back", C.c_void_p)]
 
 
 class ConvLayer(C.Structure):
@@ -63,7 +64,8 @@ _lib = None
 _EXPORTS = ["bsde_version", "bsde_last_error", "bsde_launch_count", "bsde_wsde_workspace_bytes", "bsde_wsde_fwd", "bsde_wsde_bwd",
             "bsde_tconv_fwd", "bsde_tconv_fwd_workspace_bytes", "bsde_tconv_wgrad_workspace_bytes", "bsde_tconv_wgrad",
             "bsde_xpath_workspace_bytes", "bsde_xpath_acts_bytes", "bsde_xpath_fwd", "bsde_xpath_bwd", "bsde_step_update",
-            "bsde_philox_increments", "bsde_toy_em_fwd", "bsde_toy_em_bwd"]
+            "bsde_philox_increments", "bsde_toy_em_fwd", "bsde_toy_em_bwd", "bsde_chain_workspace_bytes", "bsde_chain_acts_floats",
+            "bsde_chain_out_offset", "bsde_chain_fwd", "bsde_chain_bwd", "bsde_nchw_reinterp_axpy"]
 
 
 def lib():

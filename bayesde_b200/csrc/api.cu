@@ -382,6 +382,180 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
 }
 
 // ---------------------------------------------------------------------------------------------
+// Feed-forward drift net of the torch front end (make_y_net, torchbnn/_impl/models.py:25-54): ONE evaluation
+// f = y_net(t, x; w) of a chain of time-dependent convs, and its reverse pass (data gradients + per-layer weight
+// gradients).  The fixed-step solver (midpoint: two evaluations per step) drives these from the host side.
+// ---------------------------------------------------------------------------------------------
+static int chain_check(const bsde_chain_desc* d) {
+  BSDE_CHECK_ARG(d != nullptr, "NULL descriptor");
+  BSDE_CHECK_ARG(d->nlayers >= 1 && d->nlayers <= BSDE_CHAIN_MAX_LAYERS, "nlayers=%d unsupported", d->nlayers);
+  BSDE_CHECK_ARG(d->S >= 1 && d->B >= 1, "S, B must be positive");
+  BSDE_CHECK_ARG(d->act >= BSDE_ACT_SOFTPLUS && d->act <= BSDE_ACT_ELU, "activation %d unsupported", d->act);
+  for (int l = 0; l + 1 < d->nlayers; ++l)
+    BSDE_CHECK_ARG(d->layers[l].cout == d->layers[l + 1].cin && d->layers[l].hout == d->layers[l + 1].hin &&
+                       d->layers[l].wout == d->layers[l + 1].win,
+                   "layer %d output does not match layer %d input", l, l + 1);
+  if (d->act_after[d->nlayers - 1]) {
+    set_error("an activation after the last layer of the chain is not supported (models.py:35: last_activation=False there)");
+    return BSDE_ERR_UNSUPPORTED;
+  }
+  return 0;
+}
+
+static size_t chain_act_elems(const bsde_chain_desc* d, int l) {
+  const bsde_conv_layer& L = d->layers[l];
+  return (size_t)d->S * d->B * L.hout * L.wout * L.cout;
+}
+
+static size_t chain_act_offset(const bsde_chain_desc* d, int l) {  // floats
+  size_t off = 0;
+  for (int i = 0; i < l; ++i) off += align_up(chain_act_elems(d, i) * sizeof(float)) / sizeof(float);
+  return off;
+}
+
+static size_t chain_tc_bytes(const bsde_chain_desc* d, int backward) {
+  if (d->math != BSDE_MATH_TC) return 0;
+  size_t m = 0;
+  for (int l = 0; l < d->nlayers; ++l) {
+    m = std::max(m, conv_tc_ws(&d->layers[l], d->S));
+    if (backward) {
+      bsde_conv_layer D = dgrad_layer(d->layers[l]);
+      m = std::max(m, conv_tc_ws(&D, d->S));
+    }
+  }
+  return align_up(m);
+}
+
+static size_t chain_max_act_bytes(const bsde_chain_desc* d) {
+  size_t m = 0;
+  for (int l = 0; l < d->nlayers; ++l) m = std::max(m, align_up(chain_act_elems(d, l) * sizeof(float)));
+  return m;
+}
+
+static size_t chain_wgrad_bytes(const bsde_chain_desc* d) {
+  size_t m = 0;
+  for (int l = 0; l < d->nlayers; ++l) m = std::max(m, wgrad_ws(&d->layers[l], d->S, d->B, d->math));
+  return align_up(m);
+}
+
+extern "C" size_t bsde_chain_acts_floats(const bsde_chain_desc* d) {
+  if (!d || d->nlayers < 1 || d->nlayers > BSDE_CHAIN_MAX_LAYERS) return 0;
+  return chain_act_offset(d, d->nlayers);
+}
+
+extern "C" size_t bsde_chain_out_offset(const bsde_chain_desc* d) {
+  if (!d || d->nlayers < 1 || d->nlayers > BSDE_CHAIN_MAX_LAYERS) return 0;
+  return chain_act_offset(d, d->nlayers - 1);
+}
+
+extern "C" size_t bsde_chain_workspace_bytes(const bsde_chain_desc* d, int32_t backward) {
+  if (!d || d->nlayers < 1 || d->nlayers > BSDE_CHAIN_MAX_LAYERS) return 0;
+  size_t tot = chain_tc_bytes(d, backward);
+  if (backward) tot += 2 * chain_max_act_bytes(d) + chain_wgrad_bytes(d);
+  return tot + 256;
+}
+
+extern "C" int bsde_chain_fwd(const bsde_chain_desc* d, float t, const float* d_w, int64_t w_sample_stride, const float* d_x,
+                              float* d_acts, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = chain_check(d)) return e;
+  BSDE_CHECK_ARG(d_w && d_x && d_acts, "NULL pointer");
+  const size_t need = bsde_chain_workspace_bytes(d, 0);
+  if (!workspace || workspace_bytes < need) {
+    set_error("chain_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
+    return BSDE_ERR_WORKSPACE;
+  }
+  const size_t tc_bytes = chain_tc_bytes(d, 0);
+  const float* in = d_x;
+  size_t off = 0;
+  for (int l = 0; l < d->nlayers; ++l) {
+    float* out = d_acts + off;
+    if (int e = conv_fwd(&d->layers[l], d->S, d->B, in, d_w, w_sample_stride, t, d->act,
+                         d->act_after[l] ? BSDE_EPI_BIAS_ACT : BSDE_EPI_BIAS, 1.f, nullptr, out, d->math, workspace, tc_bytes,
+                         (cudaStream_t)stream))
+      return e;
+    in = out;
+    off += align_up(chain_act_elems(d, l) * sizeof(float)) / sizeof(float);
+  }
+  return 0;
+}
+
+extern "C" int bsde_chain_bwd(const bsde_chain_desc* d, float t, const float* d_w, int64_t w_sample_stride, const float* d_x,
+                              const float* d_acts, const float* d_gf, float* d_gx, int32_t accumulate_gx, float* d_gw,
+                              int64_t gw_sample_stride, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = chain_check(d)) return e;
+  BSDE_CHECK_ARG(d_w && d_x && d_acts && d_gf && d_gx && d_gw, "NULL pointer");
+  const size_t need = bsde_chain_workspace_bytes(d, 1);
+  if (!workspace || workspace_bytes < need) {
+    set_error("chain_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
+    return BSDE_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  void* tc_ws = ws;
+  const size_t tc_bytes = chain_tc_bytes(d, 1);
+  ws += tc_bytes;
+  const size_t mab = chain_max_act_bytes(d);
+  float* dz[2] = {(float*)ws, (float*)(ws + mab)};
+  ws += 2 * mab;
+  void* wg_ws = ws;
+  const size_t wg_bytes = chain_wgrad_bytes(d);
+  const int n = d->nlayers;
+  const float* dy = d_gf;  // dL/d(conv output of layer l)
+  for (int l = n - 1; l >= 0; --l) {
+    const float* lin = l == 0 ? d_x : d_acts + chain_act_offset(d, l - 1);
+    if (int e = conv_wgrad(&d->layers[l], d->S, d->B, lin, dy, t, 1.f, d_gw, gw_sample_stride, d->math, wg_ws, wg_bytes, st)) return e;
+    bsde_conv_layer D = dgrad_layer(d->layers[l]);
+    if (l > 0) {
+      float* out = dz[l & 1];
+      const int epi = d->act_after[l - 1] ? BSDE_EPI_DACT : BSDE_EPI_BIAS;  // D.b_off < 0: BIAS is the bare accumulator
+      if (int e = conv_fwd(&D, d->S, d->B, dy, d_w, w_sample_stride, t, d->act, epi, 1.f, lin, out, d->math, tc_ws, tc_bytes, st))
+        return e;
+      dy = out;
+    } else {
+      const int epi = accumulate_gx ? BSDE_EPI_ACCUM : BSDE_EPI_BIAS;
+      if (int e = conv_fwd(&D, d->S, d->B, dy, d_w, w_sample_stride, t, d->act, epi, 1.f, d_gx, d_gx, d->math, tc_ws, tc_bytes, st))
+        return e;
+    }
+  }
+  return 0;
+}
+
+// The torch front end adds the drift to the state in FLAT NCHW ORDER (models.py:163,168: `fy.reshape(-1)`): the
+// net's output (B, C2, H2, W2) is reinterpreted as the state's (B, C, H, W) per image.  Activations live in NHWC
+// storage here, so that reinterpretation is an index permutation:  out[n][h][w][c] = base + a * src[n][h2][w2][c2]
+// with  c*H*W + h*W + w  ==  c2*H2*W2 + h2*W2 + w2.   Swapping the two shapes gives the transpose (reverse pass).
+namespace bsde {
+__global__ void nchw_reinterp_axpy_kernel(long long total, int C, int H, int W, int C2, int H2, int W2, float a,
+                                          const float* __restrict__ base, const float* __restrict__ src, float* __restrict__ out) {
+  const int chw = C * H * W;
+  for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const long long n = o / chw;
+    const int r = (int)(o - n * chw);
+    const int c = r % C, pix = r / C;       // NHWC: r = (h*W + w)*C + c
+    const int i = c * (H * W) + pix;        // flat NCHW index inside the image
+    const int c2 = i / (H2 * W2), pix2 = i - c2 * (H2 * W2);
+    const float v = a * __ldg(src + n * chw + (long long)pix2 * C2 + c2);
+    out[o] = base ? base[o] + v : v;
+  }
+}
+}  // namespace bsde
+
+extern "C" int bsde_nchw_reinterp_axpy(int64_t nimg, int32_t C, int32_t H, int32_t W, int32_t C2, int32_t H2, int32_t W2, float a,
+                                       const float* d_base, const float* d_src, float* d_out, void* stream) {
+  BSDE_CHECK_ARG(nimg >= 0 && C >= 1 && H >= 1 && W >= 1 && C2 >= 1 && H2 >= 1 && W2 >= 1, "bad shape");
+  BSDE_CHECK_ARG((int64_t)C * H * W == (int64_t)C2 * H2 * W2, "the two shapes must have the same number of elements per image");
+  if (nimg == 0) return 0;
+  BSDE_CHECK_ARG(d_src && d_out, "NULL tensor pointer");
+  const long long total = (long long)nimg * C * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  nchw_reinterp_axpy_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(total, C, H, W, C2, H2, W2, a, d_base, d_src, d_out);
+  count_launch();
+  BSDE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic flat-state step (jaxsde/jaxsde/sdeint.py:36-50) and Philox increments
 // ---------------------------------------------------------------------------------------------
 namespace bsde {

@@ -61,6 +61,7 @@ struct WsdeArgs {
   float* klpart;    // [G][SC]
   float* stpart;    // [G][ME]
   float* glam;      // [S][P] (bwd)
+  float* ghold;     // [S][P] (bwd, stage tables with back = 1)
   float ou_coef;
   int s_base;  // global index of local sample 0 (Philox counter)
 };
@@ -115,8 +116,8 @@ __device__ __forceinline__ void tiny_forward(const WsdeArgs& A, const TinySmem& 
     for (int idx = threadIdx.x; idx < S * d1; idx += NTHREADS) {
       const int s = idx / d1, j = idx - s * d1;
       const float a = z1raw[s * ME + j] + __ldg(A.fw.b1 + j);
-      const float g = sigmoidf_(__ldg(A.fw.wt1 + j) * t + __ldg(A.fw.wtb1 + j));
-      const float y = a * g + __ldg(A.fw.bt1 + j) * t;
+      const float g = A.fw.plain ? 1.f : sigmoidf_(__ldg(A.fw.wt1 + j) * t + __ldg(A.fw.wtb1 + j));
+      const float y = A.fw.plain ? a : a * g + __ldg(A.fw.bt1 + j) * t;
       T.a[s * wsum + j] = a;
       if (s == 0) T.g[j] = g;
       T.y[s * wsum + j] = y;
@@ -132,8 +133,8 @@ __device__ __forceinline__ void tiny_forward(const WsdeArgs& A, const TinySmem& 
       const int s = idx / dout, j = idx - s * dout;
       float a = __ldg(A.fw.bm[l] + j);
       for (int q = 0; q < din; ++q) a = fmaf(T.h[s * wsum + oi + q], __ldg(W + q * dout + j), a);
-      const float g = sigmoidf_(__ldg(A.fw.wtm[l] + j) * t + __ldg(A.fw.wtbm[l] + j));
-      const float y = a * g + __ldg(A.fw.btm[l] + j) * t;
+      const float g = A.fw.plain ? 1.f : sigmoidf_(__ldg(A.fw.wtm[l] + j) * t + __ldg(A.fw.wtbm[l] + j));
+      const float y = A.fw.plain ? a : a * g + __ldg(A.fw.btm[l] + j) * t;
       T.a[s * wsum + oo + j] = a;
       if (s == 0) T.g[oo + j] = g;
       T.y[s * wsum + oo + j] = y;
@@ -209,7 +210,11 @@ __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
 
   for (int k = 0; k < nit; ++k) {
     const float t = __ldg(A.tk + k), dt = __ldg(A.dtk + k);
-    const float sq = sqrtf(fmaxf(dt, 0.f));
+    // stage tables (bsde.h): KL step, noise scale / Philox step index, base slot of the update
+    const float dtkl = A.d.d_dtkl ? __ldg(A.d.d_dtkl + k) : dt;
+    const float sq = A.d.d_nscale ? __ldg(A.d.d_nscale + k) : sqrtf(fmaxf(dt, 0.f));
+    const uint32_t nidx = A.d.d_nidx ? (uint32_t)__ldg(A.d.d_nidx + k) : (uint32_t)k;
+    const int back = A.d.d_back ? __ldg(A.d.d_back + k) : 0;
     const float* pin = A.partials + (long long)(k & 1) * G * SC * ME;
     float* pout = A.partials + (long long)((k + 1) & 1) * G * SC * ME;
     gather_partials(pin, G, SC * ME, SC * ME, sh_z1);
@@ -234,8 +239,8 @@ __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
         w1[j] = j < d1 ? __ldg(A.fw.W1 + p * d1 + j) : 0.f;
         w4[j] = j < dL ? __ldg(A.fw.W4 + (long long)j * P + p) : 0.f;
       }
-      const float b4 = __ldg(A.fw.b4 + p), bt4 = __ldg(A.fw.bt4 + p);
-      const float s4 = sigmoidf_(__ldg(A.fw.wt4 + p) * t + __ldg(A.fw.wtb4 + p));
+      const float b4 = __ldg(A.fw.b4 + p), bt4 = A.fw.plain ? 0.f : __ldg(A.fw.bt4 + p);
+      const float s4 = A.fw.plain ? 1.f : sigmoidf_(__ldg(A.fw.wt4 + p) * t + __ldg(A.fw.wtb4 + p));
       float ust = 0.f;
       if (A.d.stl) {
         float pre = b4;
@@ -255,9 +260,10 @@ __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
           const float dw = mlp + A.ou_coef * w;
           const float u = (mlp + (A.ou_coef + 1.f) * w) * inv_sigma;
           const float dWv = A.dW ? __ldg(A.dW + ((long long)s * nit + k) * P + p)
-                                 : sq * philox_normal(A.d.seed, (uint32_t)p, (uint32_t)k, (uint32_t)(s + A.s_base), A.d.stream_id);
-          klacc[s] += dt * A.d.kl_weight * u * u + ust * dWv;
-          const float wn = w + dt * dw + sigma * dWv;
+                                 : sq * philox_normal(A.d.seed, (uint32_t)p, nidx, (uint32_t)(s + A.s_base), A.d.stream_id);
+          klacc[s] += dtkl * A.d.kl_weight * u * u + ust * dWv;
+          const float wb = back ? A.wtraj[s * wstride + (long long)(k - back) * P + p] : w;
+          const float wn = wb + dt * dw + sigma * dWv;
           A.wtraj[s * wstride + (long long)(k + 1) * P + p] = wn;
 #pragma unroll
           for (int j = 0; j < ME; ++j) acc[s * ME + j] = fmaf(wn, w1[j], acc[s * ME + j]);
@@ -312,16 +318,23 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
     if (!acc_in) {
       for (int j = 0; j < d1; ++j) A.gfw.W1[p * d1 + j] = 0.f;
       for (int j = 0; j < dL; ++j) A.gfw.W4[(long long)j * P + p] = 0.f;
-      A.gfw.b4[p] = 0.f; A.gfw.wt4[p] = 0.f; A.gfw.wtb4[p] = 0.f; A.gfw.bt4[p] = 0.f;
+      A.gfw.b4[p] = 0.f;
+      if (!A.fw.plain) { A.gfw.wt4[p] = 0.f; A.gfw.wtb4[p] = 0.f; A.gfw.bt4[p] = 0.f; }
     }
     for (int s = 0; s < S; ++s) A.glam[(long long)s * P + p] = A.gwT ? __ldg(A.gwT + (long long)s * P + p) : 0.f;
   }
   if (blockIdx.x == 0 && !acc_in) {
-    for (int j = threadIdx.x; j < d1; j += NTHREADS) { A.gfw.b1[j] = 0.f; A.gfw.wt1[j] = 0.f; A.gfw.wtb1[j] = 0.f; A.gfw.bt1[j] = 0.f; }
+    for (int j = threadIdx.x; j < d1; j += NTHREADS) {
+      A.gfw.b1[j] = 0.f;
+      if (!A.fw.plain) { A.gfw.wt1[j] = 0.f; A.gfw.wtb1[j] = 0.f; A.gfw.bt1[j] = 0.f; }
+    }
     for (int l = 0; l + 1 < td.nhid; ++l) {
       const int din = td.dims[l], dout = td.dims[l + 1];
       for (int i = threadIdx.x; i < din * dout; i += NTHREADS) A.gfw.Wm[l][i] = 0.f;
-      for (int j = threadIdx.x; j < dout; j += NTHREADS) { A.gfw.bm[l][j] = 0.f; A.gfw.wtm[l][j] = 0.f; A.gfw.wtbm[l][j] = 0.f; A.gfw.btm[l][j] = 0.f; }
+      for (int j = threadIdx.x; j < dout; j += NTHREADS) {
+        A.gfw.bm[l][j] = 0.f;
+        if (!A.fw.plain) { A.gfw.wtm[l][j] = 0.f; A.gfw.wtbm[l][j] = 0.f; A.gfw.btm[l][j] = 0.f; }
+      }
     }
   }
   for (int i = threadIdx.x; i < SC * ME; i += NTHREADS) sh_dz1[i] = 0.f;
@@ -330,6 +343,9 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
   bool pending = false;
   for (int k = nit - 1; k >= 0; --k) {
     const float t = __ldg(A.tk + k), dt = __ldg(A.dtk + k);
+    const float dtkl = A.d.d_dtkl ? __ldg(A.d.d_dtkl + k) : dt;
+    const int back = A.d.d_back ? __ldg(A.d.d_back + k) : 0;                        // w_{k+1} starts from w_{k-back}
+    const int hold_in = (A.d.d_back && k + 1 < nit) ? __ldg(A.d.d_back + k + 1) : 0;  // iteration k+1 started from w_k
     // tiny forward of iteration k from the stored first-layer dots
     for (int idx = threadIdx.x; idx < SC * ME; idx += NTHREADS) {
       const int s = idx / ME, j = idx - s * ME;
@@ -349,8 +365,8 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
         w4[j] = j < dL ? __ldg(A.fw.W4 + (long long)j * P + p) : 0.f;
         gw1[j] = 0.f; gw4[j] = 0.f;
       }
-      const float b4 = __ldg(A.fw.b4 + p), bt4 = __ldg(A.fw.bt4 + p);
-      const float s4 = sigmoidf_(__ldg(A.fw.wt4 + p) * t + __ldg(A.fw.wtb4 + p));
+      const float b4 = __ldg(A.fw.b4 + p), bt4 = A.fw.plain ? 0.f : __ldg(A.fw.bt4 + p);
+      const float s4 = A.fw.plain ? 1.f : sigmoidf_(__ldg(A.fw.wt4 + p) * t + __ldg(A.fw.wtb4 + p));
       float gb4 = 0.f, gwt4 = 0.f, gwtb4 = 0.f, gbt4 = 0.f;
 #pragma unroll
       for (int s = 0; s < SC; ++s) {
@@ -370,11 +386,15 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
           for (int j = 0; j < ME; ++j) pre = fmaf(T.h[s * wsum + offL + (j < dL ? j : 0)], w4[j], pre);
           const float mlp = pre * s4 + bt4 * t;
           const float u = (mlp + (A.ou_coef + 1.f) * w) * inv_sigma;
-          const float gu = __ldg(A.gkl + s) * dt * A.d.kl_weight * 2.f * u * inv_sigma;  // dL/d(mlp) via kl
+          const float gu = __ldg(A.gkl + s) * dtkl * A.d.kl_weight * 2.f * u * inv_sigma;  // dL/d(mlp) via kl
           const float q = dt * lam + gu;  // dL/d mlp
           const float gwk = A.gw_traj ? __ldg(A.gw_traj + ((long long)s * nit + k) * P + p) : 0.f;
           // dL/dw_k without the first-layer term (added next iteration / epilogue)
-          A.glam[(long long)s * P + p] = lam + dt * A.ou_coef * lam + (A.ou_coef + 1.f) * gu + gwk;
+          float gl = dt * A.ou_coef * lam + (A.ou_coef + 1.f) * gu + gwk;
+          if (back) A.ghold[(long long)s * P + p] = lam;   // the identity path of this update ends at w_{k-1}
+          else gl += lam;
+          if (hold_in) gl += A.ghold[(long long)s * P + p];
+          A.glam[(long long)s * P + p] = gl;
           const float qs = q * s4;
 #pragma unroll
           for (int j = 0; j < ME; ++j) {
@@ -390,7 +410,8 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
       }
       for (int j = 0; j < d1; ++j) if (pending) A.gfw.W1[p * d1 + j] += gw1[j];
       for (int j = 0; j < dL; ++j) A.gfw.W4[(long long)j * P + p] += gw4[j];
-      A.gfw.b4[p] += gb4; A.gfw.wt4[p] += gwt4; A.gfw.wtb4[p] += gwtb4; A.gfw.bt4[p] += gbt4;
+      A.gfw.b4[p] += gb4;
+      if (!A.fw.plain) { A.gfw.wt4[p] += gwt4; A.gfw.wtb4[p] += gwtb4; A.gfw.bt4[p] += gbt4; }
     }
     float* pout = A.partials + (long long)(k & 1) * G * SC * ME;
     block_reduce_store<SC * ME>(part, sh_red, pout + (long long)blockIdx.x * SC * ME, SC * ME);
@@ -428,7 +449,8 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
             se += gy * T.a[s * wsum + oo + j] * g * (1.f - g);
             sy += gy;
           }
-          gb[j] += sb; gwt[j] += se * t; gwtb[j] += se; gbt[j] += sy * t;
+          gb[j] += sb;
+          if (!A.fw.plain) { gwt[j] += se * t; gwtb[j] += se; gbt[j] += sy * t; }
         }
         if (l > 0) {
           const int din = td.dims[l - 1], oi = td.off[l - 1];
@@ -538,7 +560,7 @@ constexpr int MAXG = 148 * 2 * 2;  // workspace is sized for at most this many C
 
 static size_t ws_floats(int S, int P, bool bwd) {
   size_t f = (size_t)2 * MAXG * SC * ME + (size_t)MAXG * SC + (size_t)MAXG * ME;
-  if (bwd) f += (size_t)(S < SC ? S : SC) * P;
+  if (bwd) f += (size_t)2 * (S < SC ? S : SC) * P;  // lambda + the held identity path of back = 1 stages
   return f;
 }
 
@@ -637,7 +659,8 @@ extern "C" int bsde_wsde_bwd(const bsde_wsde_desc* d, const bsde_fw_params* fw, 
     A.partials = ws; ws += (size_t)2 * MAXG * SC * ME;
     A.klpart = ws; ws += (size_t)MAXG * SC;
     A.stpart = ws; ws += (size_t)MAXG * ME;
-    A.glam = ws;
+    A.glam = ws; ws += (size_t)sc * P;
+    A.ghold = ws;
     void* args[] = {&A};
     BSDE_CUDA_OK(cudaLaunchCooperativeKernel((void*)wsde_bwd_kernel, dim3(G), dim3(NTHREADS), args, smem,
                                              (cudaStream_t)stream));

@@ -1,0 +1,505 @@
+"""torch front end: `SDENet`, `make_y_net`, `make_w_net` of
+torchbnn/_impl/models.py:25-80,105-204 on the kernels of libbsde.so.
+
+The reference integrates ONE Stratonovich SDE over the flat state `[y (B*C*H*W), w (P), logqp (1)]` with torchsde's
+fixed-step solvers (models.py:184-197).  The `[w, logqp]` rows never read `y`, so they are integrated first for all
+solver stages in one cooperative launch (`bsde_wsde_fwd` with stage tables: plain-Linear w-net, `fw = nn - w`,
+`fl = |nn|^2 / sigma^2`), then the `y` rows consume `w` stage by stage through `bsde_chain_fwd` (the whole `y_net`:
+every group plus the `ConvDownsample` layers, time channel FIRST, OIHW / IOHW kernels read in place from the flat vector
+through strides) and `bsde_nchw_reinterp_axpy` (the flat-NCHW-order state update).  The reverse pass is hand written
+(`bsde_chain_bwd` per evaluation in reverse order, then `bsde_wsde_bwd`): backprop through the solver, like
+`loss.backward()` through `torchsde.sdeint` (examples/torch/sdebnn_classification.py:34-46).
+
+Semantics follow the INTENDED flat-state reading of `SDENet` (the class as shipped raises in `split`/`cat`: SURVEY
+quirk Q7).  `adjoint=True` / `adaptive=True` raise NotImplementedError.  There is no CPU path.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+
+CHAIN_MAX_LAYERS = 40
+
+
+class ChainDesc(C.Structure):
+    _fields_ = [("S", C.c_int32), ("B", C.c_int32), ("nlayers", C.c_int32), ("act", C.c_int32), ("math", C.c_int32),
+                ("act_after", C.c_int32 * CHAIN_MAX_LAYERS), ("layers", _lib.ConvLayer * CHAIN_MAX_LAYERS)]
+
+
+_bound = False
+
+
+def _L():
+    global _bound
+    L = _lib.lib()
+    if not _bound:
+        vp = C.c_void_p
+        for name in ("bsde_chain_workspace_bytes", "bsde_chain_acts_floats", "bsde_chain_out_offset", "bsde_chain_fwd", "bsde_chain_bwd",
+                     "bsde_nchw_reinterp_axpy"):
+            if not hasattr(L, name):
+                raise _lib.BsdeError(f"libbsde.so does not export {name}")
+        L.bsde_chain_workspace_bytes.restype = C.c_size_t
+        L.bsde_chain_workspace_bytes.argtypes = [C.POINTER(ChainDesc), C.c_int32]
+        L.bsde_chain_acts_floats.restype = C.c_size_t
+        L.bsde_chain_acts_floats.argtypes = [C.POINTER(ChainDesc)]
+        L.bsde_chain_out_offset.restype = C.c_size_t
+        L.bsde_chain_out_offset.argtypes = [C.POINTER(ChainDesc)]
+        L.bsde_chain_fwd.argtypes = [C.POINTER(ChainDesc), C.c_float, vp, C.c_int64, vp, vp, vp, C.c_size_t, vp]
+        L.bsde_chain_bwd.argtypes = [C.POINTER(ChainDesc), C.c_float, vp, C.c_int64, vp, vp, vp, vp, C.c_int32, vp, C.c_int64, vp,
+                                     C.c_size_t, vp]
+        L.bsde_nchw_reinterp_axpy.argtypes = [C.c_int64] + [C.c_int32] * 6 + [C.c_float, vp, vp, vp, vp]
+        _bound = True
+    return L
+
+
+# ------------------------------------------------------------------------------------------------
+# pytree helpers (torchbnn/_impl/utils.py:165-193)
+# ------------------------------------------------------------------------------------------------
+def ravel_pytree(tree):
+    """Flatten a nested list of tensors depth first; returns (flat, unravel)."""
+    if torch.is_tensor(tree):
+        shape = tree.shape
+        return tree.reshape(-1), (lambda v: v.reshape(shape))
+    parts = [ravel_pytree(e) for e in tree]
+    sizes = [f.numel() for f, _ in parts]
+
+    def unravel(v):
+        return [un(piece) for piece, (_, un) in zip(v.split(sizes), parts)]
+
+    flat = torch.cat([f for f, _ in parts]) if parts else torch.tensor([])
+    return flat, unravel
+
+
+# ------------------------------------------------------------------------------------------------
+# y_net: models.py:25-54, diffeq_layers.py:280-311 (mode 0), ConvDownsample :230-239
+# ------------------------------------------------------------------------------------------------
+class YNet:
+    """Layout + evaluation handle of the hidden-state drift net.  Parameters are NOT owned here (`explicit_params=True`,
+    diffeq_layers.py:46): every call takes the flat vector (or its unravelled pytree)."""
+
+    def __init__(self, input_size, blocks=(2, 2, 2), activation="softplus", hidden_width=128, aug_dim=0):
+        if activation not in ("softplus", "tanh", "elu"):
+            raise NotImplementedError(f"y_net activation {activation!r} is not available in the fused path")
+        self.activation = activation
+        c, h, w = input_size[0] + aug_dim, input_size[1], input_size[2]
+        self.input_size = (c, h, w)
+        self.layers, off = [], 0
+
+        def conv(cin, cout, hin, win, stride=1, padding=0, transpose=False, output_padding=0, act_after=True):
+            nonlocal off
+            if transpose:  # o = i*stride - padding + k  (F.conv_transpose2d), weight (cin+1, cout, 3, 3)
+                hout, wout = (hin - 1) * stride - 2 * padding + 3 + output_padding, (win - 1) * stride - 2 * padding + 3 + output_padding
+                sn, kn, o, sd = 1, -1, padding, stride
+                ks, ns = cout * 9, 9
+                fan_in = cout * 9
+            else:          # i = o*stride + k - padding   (F.conv2d), weight (cout, cin+1, 3, 3)
+                hout, wout = (hin + 2 * padding - 3) // stride + 1, (win + 2 * padding - 3) // stride + 1
+                sn, kn, o, sd = stride, 1, -padding, 1
+                ks, ns = 9, (cin + 1) * 9
+                fan_in = (cin + 1) * 9
+            nw = (cin + 1) * cout * 9
+            self.layers.append(dict(cin=cin, cout=cout, hin=hin, win=win, hout=hout, wout=wout, sn=sn, kn=kn, off=o, sd=sd,
+                                    w_off=off, b_off=off + nw, ks=ks, ns=ns, act_after=act_after, transpose=transpose,
+                                    shape=(cin + 1, cout, 3, 3) if transpose else (cout, cin + 1, 3, 3), fan_in=fan_in))
+            off += nw + cout
+            return hout, wout
+
+        for i, nb in enumerate(blocks, 1):
+            for j in range(1, nb + 1):
+                h1, w1 = conv(c, hidden_width, h, w, padding=1)
+                h2, w2 = conv(hidden_width, hidden_width, h1, w1, stride=2, padding=1)
+                h3, w3 = conv(hidden_width, hidden_width, h2, w2, stride=2, transpose=True, output_padding=1)
+                h4, w4 = conv(hidden_width, c, h3, w3, act_after=(i < len(blocks) or j < nb))
+                if (h4, w4) != (h, w):
+                    raise AssertionError(f"block output {(h4, w4)} != input {(h, w)}. Check nblocks for dataset divisibility.")
+            if i < len(blocks):
+                h, w = conv(c, 4 * c, h, w, stride=2, padding=1, act_after=False)
+                c = 4 * c
+        self.P = off
+        self.output_size = (c, h, w)
+        if len(self.layers) > CHAIN_MAX_LAYERS:
+            raise NotImplementedError(f"{len(self.layers)} conv layers > {CHAIN_MAX_LAYERS}")
+        if c * h * w != self.input_size[0] * self.input_size[1] * self.input_size[2]:
+            raise AssertionError("Check nblocks for dataset divisibility.")   # models.py:167
+
+    # -- reference surface ---------------------------------------------------------------------
+    def make_initial_params(self, generator=None):
+        """[[weight, bias] per conv, [] per activation] with nn.Conv2d / nn.ConvTranspose2d default initialisation
+        (DiffEqSequential.make_initial_params, diffeq_layers.py:58-59)."""
+        tree = []
+        for d in self.layers:
+            bound = 1.0 / math.sqrt(d["fan_in"])
+            W = (torch.rand(d["shape"], generator=generator) * 2 - 1) * bound
+            b = (torch.rand(d["cout"], generator=generator) * 2 - 1) * bound
+            tree.append([W, b])
+            if d["act_after"]:
+                tree.append([])
+        return tree
+
+    def chain_desc(self, S, B, math_mode):
+        d = ChainDesc()
+        d.S, d.B, d.nlayers = S, B, len(self.layers)
+        d.act, d.math = _lib.ACT[self.activation], _lib.MATH[math_mode]
+        for i, lay in enumerate(self.layers):
+            c = d.layers[i]
+            c.cin, c.cout, c.ksize = lay["cin"], lay["cout"], 3
+            c.hin, c.win, c.hout, c.wout = lay["hin"], lay["win"], lay["hout"], lay["wout"]
+            c.sn, c.kn, c.off, c.sd = lay["sn"], lay["kn"], lay["off"], lay["sd"]
+            c.has_time, c.time_first = 1, 1          # utils.channel_cat: time channel first
+            c.w_off, c.b_off = lay["w_off"], lay["b_off"]
+            c.w_tap_stride, c.w_k_stride, c.w_n_stride = 1, lay["ks"], lay["ns"]
+            d.act_after[i] = int(lay["act_after"])
+        return d
+
+    def __call__(self, t, y, params, math_mode="fp32"):
+        """y_net(t, y, params): y (B, C, H, W) CUDA, params = flat vector or the pytree.  Forward only (the differentiable
+        route is SDENet.forward)."""
+        flat = params if torch.is_tensor(params) else ravel_pytree(params)[0]
+        flat = flat.detach().float().contiguous()
+        B = y.shape[0]
+        x = y.detach().float().permute(0, 2, 3, 1).contiguous()
+        desc = self.chain_desc(1, B, math_mode)
+        acts = chain_forward(desc, float(t), flat, self.P, x)
+        c, h, w = self.output_size
+        out = acts[_L().bsde_chain_out_offset(C.byref(desc)):][:B * c * h * w].reshape(B, h, w, c)
+        return out.permute(0, 3, 1, 2).contiguous()
+
+
+def make_y_net(input_size, blocks=(2, 2, 2), activation="softplus", verbose=False, explicit_params=True, hidden_width=128,
+               aug_dim=0):
+    """models.py:25-54 -> (y_net, output_size)."""
+    if not explicit_params:
+        raise NotImplementedError("explicit_params=False (BaselineYNet) is outside the SDE-BNN hot path")
+    net = YNet(input_size, blocks, activation, hidden_width, aug_dim)
+    return net, net.output_size
+
+
+# ------------------------------------------------------------------------------------------------
+# w_net: models.py:57-80
+# ------------------------------------------------------------------------------------------------
+class _WNet(nn.Module):
+    """Parameter container with the reference's state_dict keys (`layers.{0,2,..}.weight/bias` for inhomogeneous=True,
+    `module.{0,2,..}` otherwise).  Both variants ignore t (diffeq_layers.py:65-72,169-175)."""
+
+    def __init__(self, sizes, activation, inhomogeneous):
+        super().__init__()
+        acts = {"tanh": nn.Tanh, "softplus": nn.Softplus, "elu": nn.ELU}
+        if activation not in acts:
+            raise NotImplementedError(f"w_net activation {activation!r} is not available in the fused path")
+        mods = []
+        for i, (din, dout) in enumerate(zip(sizes[:-1], sizes[1:]), 1):
+            mods.append(nn.Linear(din, dout))
+            if i + 1 < len(sizes):
+                mods.append(acts[activation]())
+            else:  # last layer needs zero initialisation (models.py:67-69)
+                nn.init.zeros_(mods[-1].weight)
+                nn.init.zeros_(mods[-1].bias)
+        if inhomogeneous:
+            self.layers = nn.ModuleList(mods)
+        else:
+            self.module = nn.Sequential(*mods)
+        self.activation = activation
+        self.hidden_sizes = tuple(sizes[1:-1])
+
+    def linears(self):
+        mods = self.layers if hasattr(self, "layers") else self.module
+        return [m for m in mods if isinstance(m, nn.Linear)]
+
+    def forward(self, t, w):
+        raise NotImplementedError("w_net is evaluated inside libbsde.so (bsde_wsde_fwd); use SDENet.forward")
+
+
+def make_w_net(in_features, hidden_sizes=(1, 64, 1), activation="softplus", inhomogeneous=True):
+    sizes = (in_features,) + tuple(hidden_sizes) + (in_features,)
+    if len(hidden_sizes) < 1 or hidden_sizes[0] > _lib.FW_MAX_EDGE or hidden_sizes[-1] > _lib.FW_MAX_EDGE:
+        raise NotImplementedError(f"first / last hidden widths must be <= {_lib.FW_MAX_EDGE}, got {hidden_sizes}")
+    return _WNet(sizes, activation, inhomogeneous)
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel wrappers
+# ------------------------------------------------------------------------------------------------
+def chain_forward(desc, t, w, w_sample_stride, x, acts=None):
+    L = _L()
+    n = L.bsde_chain_acts_floats(C.byref(desc))
+    if acts is None:
+        acts = torch.empty(n, device=x.device, dtype=torch.float32)
+    nbytes = L.bsde_chain_workspace_bytes(C.byref(desc), 0)
+    ws = _lib.workspace(nbytes, x.device, "chain")
+    st = L.bsde_chain_fwd(C.byref(desc), t, _lib.ptr(w), w_sample_stride, _lib.ptr(x), _lib.ptr(acts), C.c_void_p(ws.data_ptr()),
+                          ws.numel(), _lib.stream_ptr())
+    _lib.check(st, "bsde_chain_fwd")
+    return acts
+
+
+def chain_backward(desc, t, w, w_sample_stride, x, acts, gf, gx, accumulate, gw, gw_sample_stride):
+    L = _L()
+    nbytes = L.bsde_chain_workspace_bytes(C.byref(desc), 1)
+    ws = _lib.workspace(nbytes, x.device, "chain")
+    st = L.bsde_chain_bwd(C.byref(desc), t, _lib.ptr(w), w_sample_stride, _lib.ptr(x), _lib.ptr(acts), _lib.ptr(gf), _lib.ptr(gx),
+                          int(accumulate), _lib.ptr(gw), gw_sample_stride, C.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr())
+    _lib.check(st, "bsde_chain_bwd")
+
+
+def reinterp_axpy(out, out_chw, base, a, src, src_chw):
+    """out[NHWC of out_chw] = base + a * (src viewed in flat NCHW order as out_chw)."""
+    nimg = out.numel() // (out_chw[0] * out_chw[1] * out_chw[2])
+    st = _L().bsde_nchw_reinterp_axpy(nimg, *out_chw, *src_chw, a, _lib.ptr(base), _lib.ptr(src), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(st, "bsde_nchw_reinterp_axpy")
+
+
+def _plain_fw_struct(klayers, P, hidden, actfn):
+    """bsde_fw_params for a plain-Linear w-net; klayers in kernel layout: (W1 [P,d1], b1), (Wm [din,dout], bm).., (W4 [dL,P], b4)."""
+    fp = _lib.FwParams()
+    fp.P, fp.nhid, fp.act, fp.plain = P, len(hidden), _lib.ACT[actfn], 1
+    for i, d in enumerate(hidden):
+        fp.dims[i] = d
+    fp.W1, fp.b1 = _lib.ptr(klayers[0][0]).value, _lib.ptr(klayers[0][1]).value
+    for i, (W, b) in enumerate(klayers[1:-1]):
+        fp.Wm[i], fp.bm[i] = _lib.ptr(W).value, _lib.ptr(b).value
+    fp.W4, fp.b4 = _lib.ptr(klayers[-1][0]).value, _lib.ptr(klayers[-1][1]).value
+    return fp
+
+
+class SolveConfig:
+    """Static description of one SDENet solve: stage tables of the fixed-step scheme (include/bsde.h)."""
+
+    def __init__(self, ynet, S, B, nsteps, h, method, sigma, hidden, w_act, math_mode, remat, t0=0.0):
+        if method not in ("midpoint", "euler_heun", "milstein"):
+            raise ValueError(f"Unknown method: {method}")
+        self.ynet, self.S, self.B, self.n, self.h, self.method = ynet, S, B, nsteps, float(h), method
+        self.sigma, self.hidden, self.w_act, self.math, self.remat = float(sigma), tuple(hidden), w_act, math_mode, remat
+        f32 = np.float32
+        hh = f32(h)
+        tk = [f32(t0) + f32(k) * hh for k in range(nsteps)]
+        if method == "midpoint":   # torchsde midpoint: f at (t, y) and (t + h/2, y'), the same increment I in both stages
+            self.nit = 2 * nsteps
+            self.tk = np.asarray([v for t in tk for v in (t, t + f32(0.5) * hh)], dtype=f32)
+            self.dtk = np.asarray([f32(0.5) * hh, hh] * nsteps, dtype=f32)
+            self.dtkl = np.asarray([0.0, hh] * nsteps, dtype=f32)
+            self.nscale = np.asarray([0.5 * math.sqrt(h), math.sqrt(h)] * nsteps, dtype=f32)
+            self.nidx = np.asarray([k for k in range(nsteps) for _ in (0, 1)], dtype=np.int32)
+            self.back = np.asarray([0, 1] * nsteps, dtype=np.int32)
+        else:                      # constant diagonal g: euler_heun / milstein reduce to y + h f + g I
+            self.nit = nsteps
+            self.tk = np.asarray(tk, dtype=f32)
+            self.dtk = np.full(nsteps, hh, dtype=f32)
+            self.dtkl = self.nscale = self.nidx = self.back = None
+        self._dev = {}
+
+    def on(self, device):
+        key = str(device)
+        if key not in self._dev:
+            t = lambda a: None if a is None else torch.from_numpy(a).to(device)
+            self._dev[key] = tuple(t(a) for a in (self.tk, self.dtk, self.dtkl, self.nscale, self.nidx, self.back))
+        return self._dev[key]
+
+    def wdesc(self, device, seed, stream_id):
+        d = _lib.WsdeDesc()
+        d.S, d.nit, d.stl, d.w0_per_sample = self.S, self.nit, 0, 0
+        # fw = nn - w (models.py:165), fl = |nn|^2 / sigma^2 (:166): ou_coef -1 => u = nn / sigma, integrand u^2
+        d.sigma, d.kl_weight, d.ou_coef = self.sigma, 1.0, -1.0
+        d.seed, d.stream_id = int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_id) & 0xFFFFFFFF
+        _, _, dtkl, nscale, nidx, back = self.on(device)
+        if dtkl is not None:
+            d.d_dtkl, d.d_nscale, d.d_nidx, d.d_back = dtkl.data_ptr(), nscale.data_ptr(), nidx.data_ptr(), back.data_ptr()
+        return d
+
+    def stage_increments(self, I):
+        """Per-stage noise [S, nit, P] from per-step increments I [S, nsteps, P]."""
+        if self.method != "midpoint":
+            return I.contiguous()
+        return torch.stack((0.5 * I, I), dim=2).reshape(I.shape[0], 2 * I.shape[1], I.shape[2]).contiguous()
+
+
+class SDENetSolve(torch.autograd.Function):
+    """(y_T, logqp_state [S], wtraj) of sdeint(SDENet, [y, w0, 0], ts=[0,1], bm, method, dt) for S weight samples.
+
+    forward(cfg, increments or None, seed, stream_id, x [S,B,H,W,C] (NHWC storage), w0 [P], W1,b1, Wm,bm.., W4,b4 (kernel layout))"""
+
+    @staticmethod
+    def forward(ctx, cfg, I, seed, stream_id, x, w0, *flat):
+        L = _L()
+        dev = x.device
+        klayers = [(flat[i].contiguous(), flat[i + 1].contiguous()) for i in range(0, len(flat), 2)]
+        S, B, P, nit, n = cfg.S, cfg.B, cfg.ynet.P, cfg.nit, cfg.n
+        tk, dtk, *_ = cfg.on(dev)
+        # ---- K1: the [w, logqp] rows for every stage
+        d = cfg.wdesc(dev, seed, stream_id)
+        fp = _plain_fw_struct(klayers, P, cfg.hidden, cfg.w_act)
+        wtraj = torch.empty(S, nit + 1, P, device=dev, dtype=torch.float32)
+        z1 = torch.empty(nit * S * cfg.hidden[0], device=dev, dtype=torch.float32)
+        kl = torch.empty(S, device=dev, dtype=torch.float32)
+        ws = _lib.workspace(L.bsde_wsde_workspace_bytes(C.byref(d), C.byref(fp)), dev, "wsde")
+        dW = None
+        if I is not None:
+            if tuple(I.shape) != (S, n, P):
+                raise ValueError(f"increments must have shape {(S, n, P)}, got {tuple(I.shape)}")
+            dW = cfg.stage_increments(I.float())
+        st = L.bsde_wsde_fwd(C.byref(d), C.byref(fp), _lib.ptr(w0.contiguous()), _lib.ptr(tk), _lib.ptr(dtk), _lib.ptr(dW), None,
+                             _lib.ptr(wtraj), _lib.ptr(z1), _lib.ptr(kl), C.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr())
+        _lib.check(st, "bsde_wsde_fwd")
+        # ---- y rows
+        x = x.contiguous()
+        desc = cfg.ynet.chain_desc(S, B, cfg.math)
+        nacts, ooff = L.bsde_chain_acts_floats(C.byref(desc)), L.bsde_chain_out_offset(C.byref(desc))
+        keep = (not cfg.remat) and any(ctx.needs_input_grad)
+        store = torch.empty(nit if keep else 1, nacts, device=dev, dtype=torch.float32)
+        ys = torch.empty((n + 1,) + tuple(x.shape), device=dev, dtype=torch.float32)
+        ys[0].copy_(x)
+        mid = cfg.method == "midpoint"
+        ymid = torch.empty((n,) + tuple(x.shape), device=dev, dtype=torch.float32) if mid else None
+        chw_in, chw_out = cfg.ynet.input_size, cfg.ynet.output_size
+        wss = (nit + 1) * P
+        tkh = cfg.tk
+        for k in range(n):
+            j = 2 * k if mid else k
+            a0 = store[j if keep else 0]
+            chain_forward(desc, float(tkh[j]), wtraj[0, j], wss, ys[k], a0)
+            if mid:
+                reinterp_axpy(ymid[k], chw_in, ys[k], 0.5 * cfg.h, a0[ooff:], chw_out)
+                a1 = store[j + 1 if keep else 0]
+                chain_forward(desc, float(tkh[j + 1]), wtraj[0, j + 1], wss, ymid[k], a1)
+                reinterp_axpy(ys[k + 1], chw_in, ys[k], cfg.h, a1[ooff:], chw_out)
+            else:
+                reinterp_axpy(ys[k + 1], chw_in, ys[k], cfg.h, a0[ooff:], chw_out)
+        ctx.cfg, ctx.klayers, ctx.desc = cfg, klayers, desc
+        ctx.store = store if keep else None
+        ctx.save_for_backward(wtraj, z1, ys, ymid if mid else ys)
+        ctx.mark_non_differentiable(wtraj)
+        return ys[n].clone(), kl, wtraj
+
+    @staticmethod
+    def backward(ctx, gy, gkl, _gw):
+        L = _L()
+        cfg, desc, klayers = ctx.cfg, ctx.desc, ctx.klayers
+        wtraj, z1, ys, ymid = ctx.saved_tensors
+        dev = ys.device
+        S, P, nit, n = cfg.S, cfg.ynet.P, cfg.nit, cfg.n
+        mid = cfg.method == "midpoint"
+        gy = torch.zeros_like(ys[0]) if gy is None else gy.float().contiguous().clone()
+        gkl = torch.zeros(S, device=dev) if gkl is None else gkl.float().contiguous()
+        nacts, ooff = L.bsde_chain_acts_floats(C.byref(desc)), L.bsde_chain_out_offset(C.byref(desc))
+        chw_in, chw_out = cfg.ynet.input_size, cfg.ynet.output_size
+        nf = S * cfg.B * chw_out[0] * chw_out[1] * chw_out[2]
+        gf = torch.empty(nf, device=dev, dtype=torch.float32)
+        gyp = torch.empty_like(gy)
+        gw_traj = torch.empty(S, nit, P, device=dev, dtype=torch.float32)
+        scratch = None if ctx.store is not None else torch.empty(nacts, device=dev, dtype=torch.float32)
+        wss, gss = (nit + 1) * P, nit * P
+        tkh = cfg.tk
+
+        def acts_of(j, x):
+            if ctx.store is not None:
+                return ctx.store[j]
+            return chain_forward(desc, float(tkh[j]), wtraj[0, j], wss, x, scratch)   # recompute (remat)
+
+        for k in range(n - 1, -1, -1):
+            if mid:
+                j = 2 * k
+                # y_{k+1} = y_k + h R(f(t + h/2, y', w'))
+                reinterp_axpy(gf, chw_out, None, cfg.h, gy, chw_in)
+                chain_backward(desc, float(tkh[j + 1]), wtraj[0, j + 1], wss, ymid[k], acts_of(j + 1, ymid[k]), gf, gyp, False,
+                               gw_traj[0, j + 1], gss)
+                # y' = y_k + h/2 R(f(t, y_k, w_k))
+                reinterp_axpy(gf, chw_out, None, 0.5 * cfg.h, gyp, chw_in)
+                gy.add_(gyp)
+                chain_backward(desc, float(tkh[j]), wtraj[0, j], wss, ys[k], acts_of(j, ys[k]), gf, gy, True, gw_traj[0, j], gss)
+            else:
+                reinterp_axpy(gf, chw_out, None, cfg.h, gy, chw_in)
+                chain_backward(desc, float(tkh[k]), wtraj[0, k], wss, ys[k], acts_of(k, ys[k]), gf, gy, True, gw_traj[0, k], gss)
+        ctx.store = None
+        # ---- K1 reverse
+        d = cfg.wdesc(dev, 0, 0)
+        fp = _plain_fw_struct(klayers, P, cfg.hidden, cfg.w_act)
+        gl = [(torch.empty_like(W), torch.empty_like(b)) for W, b in klayers]
+        gfp = _plain_fw_struct(gl, P, cfg.hidden, cfg.w_act)
+        gw0 = torch.empty(P, device=dev, dtype=torch.float32)
+        tk, dtk, *_ = cfg.on(dev)
+        ws = _lib.workspace(L.bsde_wsde_workspace_bytes(C.byref(d), C.byref(fp)), dev, "wsde")
+        st = L.bsde_wsde_bwd(C.byref(d), C.byref(fp), _lib.ptr(tk), _lib.ptr(dtk), _lib.ptr(wtraj), _lib.ptr(z1), _lib.ptr(gw_traj),
+                             _lib.ptr(gkl), None, _lib.ptr(gw0), C.byref(gfp), C.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr())
+        _lib.check(st, "bsde_wsde_bwd")
+        return (None, None, None, None, gy, gw0, *[t for pair in gl for t in pair])
+
+
+def sdenet_solve(cfg, x_nhwc, w0, linears, increments=None, seed=0, stream_id=0):
+    """Differentiable solve.  x_nhwc [S,B,H,W,C]; linears = [(weight [out,in], bias)] in torch nn.Linear layout."""
+    kl = []
+    for W, b in linears:
+        kl += [W.t().contiguous(), b]      # kernel layout: W1 [P,d1], Wm [din,dout], W4 [dL,P]
+    return SDENetSolve.apply(cfg, increments, seed, stream_id, x_nhwc, w0, *kl)
+
+
+# ------------------------------------------------------------------------------------------------
+# SDENet: models.py:105-204
+# ------------------------------------------------------------------------------------------------
+class SDENet(nn.Module):
+    def __init__(self, input_size=(3, 32, 32), blocks=(2, 2, 2), weight_network_sizes=(1, 64, 1), num_classes=10,
+                 activation="softplus", verbose=False, inhomogeneous=True, sigma=0.1, hidden_width=128, aug_dim=0,
+                 math="tc", remat=False):
+        super().__init__()
+        self.input_size = tuple(input_size)
+        self.aug_input_size = (aug_dim + input_size[0], *input_size[1:])
+        self.aug_zeros_size = (aug_dim, *input_size[1:])
+        self.register_buffer("aug_zeros", torch.zeros(size=(1, *self.aug_zeros_size)))
+        self.y_net, self.output_size = make_y_net(input_size=input_size, blocks=blocks, activation=activation, verbose=verbose,
+                                                  hidden_width=hidden_width, aug_dim=aug_dim)
+        flat, self.unravel_params = ravel_pytree(self.y_net.make_initial_params())
+        self.flat_initial_params = nn.Parameter(flat, requires_grad=True)
+        self.params_size = flat.numel()
+        self.w_net = make_w_net(in_features=self.params_size, hidden_sizes=weight_network_sizes, activation="tanh",
+                                inhomogeneous=inhomogeneous)
+        self.projection = nn.Sequential(nn.Flatten(), nn.Linear(int(np.prod(self.output_size)), 1024), nn.ReLU(inplace=True),
+                                        nn.Linear(1024, num_classes))
+        self.register_buffer("ts", torch.tensor([0., 1.]))
+        self.sigma = sigma
+        self.nfe = 0
+        self.math, self.remat = math, remat
+        self.seed, self._calls = 0, 0
+        self._cfg = {}
+
+    def make_initial_params(self):
+        return self.y_net.make_initial_params()
+
+    def _config(self, B, nsteps, h, method):
+        key = (B, nsteps, h, method, self.math, self.remat)
+        if key not in self._cfg:
+            self._cfg[key] = SolveConfig(self.y_net, 1, B, nsteps, h, method, self.sigma, self.w_net.hidden_sizes,
+                                         self.w_net.activation, self.math, self.remat, t0=float(self.ts[0]))
+        return self._cfg[key]
+
+    def forward(self, y, adjoint=False, dt=0.02, adaptive=False, adjoint_adaptive=False, method="midpoint", rtol=1e-4, atol=1e-3,
+                increments=None):
+        """-> (logits, logqp).  `increments` [nsteps, P]: W(t_{k+1}) - W(t_k) to replay (else in-kernel Philox keyed by
+        (self.seed, call counter), the stand-in for torchsde.BrownianInterval, models.py:190-193)."""
+        if adjoint or adjoint_adaptive:
+            raise NotImplementedError("sdeint_adjoint is out of scope (SURVEY 8.2 / 8.6 N4)")
+        if adaptive:
+            raise NotImplementedError("adaptive stepping is out of scope (SURVEY 8.2 / 8.6 N4)")
+        if not y.is_cuda:
+            raise _lib.BsdeError("bayesde_b200 kernels need CUDA tensors (there is no CPU fallback)")
+        t0, t1 = float(self.ts[0]), float(self.ts[-1])
+        nsteps = int(round((t1 - t0) / dt))
+        if self.aug_zeros.numel() > 0:  # add zero channels (models.py:185-187)
+            y = torch.cat((y, self.aug_zeros.expand(y.shape[0], *self.aug_zeros_size)), dim=1)
+        cfg = self._config(y.shape[0], nsteps, dt, method)
+        x = y.float().permute(0, 2, 3, 1).contiguous()[None]               # NHWC storage, S = 1
+        lin = [(m.weight, m.bias) for m in self.w_net.linears()]
+        I = None if increments is None else increments[None]
+        self._calls += 1
+        y1, lq, _ = sdenet_solve(cfg, x, self.flat_initial_params, lin, I, seed=self.seed, stream_id=self._calls)
+        # f and g are each evaluated once per stage (models.py:161,172): 2 stages for midpoint; euler_heun evaluates g twice
+        self.nfe = nsteps * {"midpoint": 4, "euler_heun": 3, "milstein": 2}[method]
+        y1 = y1[0].permute(0, 3, 1, 2)                                       # back to (B, C, H, W) order for Flatten
+        logits = self.projection(y1.reshape(y1.shape[0], -1))
+        logqp = .5 * lq[0]
+        return logits, logqp
+
+    def zero_grad(self, set_to_none=True) -> None:
+        for p in self.parameters():
+            p.grad = None

@@ -28,6 +28,9 @@
  *   bsde_toy_em_fwd/bwd      em_solver + VariationalSDE drift/prior of the torch toy (config 2):
  *                            examples/torch/sdebnn_toy1d.py:19-60, torchbnn/_impl/diffeq_layers.py:178-188,
  *                            torchbnn/_impl/basic.py:298-312
+ *   bsde_chain_fwd/bwd       one evaluation of SDENet's y_net drift (all groups + ConvDownsample) and its reverse:
+ *                            torchbnn/_impl/models.py:25-54,159-169, torchbnn/_impl/diffeq_layers.py:40-62,75-166,230-311
+ *   bsde_nchw_reinterp_axpy  the flat-state update y + a * fy.reshape(-1) of the torch front end: models.py:163,168
  *   bsde_philox_increments   replaces make_brownian_motion / virtual_brownian_tree queries
  *                            bm(next_t)-bm(curr_t): jaxsde/jaxsde/brownian.py:26-95, sdeint.py:108
  */
@@ -87,6 +90,8 @@ typedef struct {
   float* wtbm[BSDE_FW_MAX_MID]; float* btm[BSDE_FW_MAX_MID];
   /* last layer  dL -> P :  W4 [dL][P] row-major, b,w_t,w_tb,b_t [P] each */
   float* W4; float* b4; float* wt4; float* wtb4; float* bt4;
+  int32_t plain;   /* 1: every layer is a plain Linear (torchbnn `Linear`, time ignored: torchbnn/_impl/diffeq_layers.py:169-175,
+                      make_w_net models.py:57-80): gate = 1, shift = 0; the w_t / w_tb / b_t pointers are not touched */
 } bsde_fw_params;
 
 typedef struct {
@@ -100,6 +105,14 @@ typedef struct {
                          torchbnn (models.py:165); u = (f_w + (ou_coef+1) w)/sigma (prior drift -w) */
   uint64_t seed;      /* Philox key when d_dW == NULL */
   uint32_t stream_id; /* Philox sub-stream (block index in the network) */
+  /* Optional stage tables, device arrays [nit] (all NULL = the Euler scan above).  They express fixed-step schemes whose
+   * stages are Euler-like updates that start from the previous slot, e.g. torchsde's midpoint (call site
+   * torchbnn/_impl/models.py:184-197;  y' = y + dt/2 f(t,y) + g I/2,  y1 = y + dt f(t + dt/2, y') + g I):
+   *     w_{j+1} = w_{j - back_j} + dt_j f_w(w_j, t_j) + sigma * noise_j ,   kl += dtkl_j * kl_weight * u(w_j)^2
+   *     noise_j = d_dW[s][j][p]   or   nscale_j * N(0,1)[Philox counter (p, nidx_j, s, stream_id)]
+   * back_j in {0, 1}, back_0 = 0 and no two consecutive ones.  midpoint: dt = (h/2, h), dtkl = (0, h), nscale = (sqrt(h)/2, sqrt(h)),
+   * nidx = (k, k), back = (0, 1) for step k; the trajectory then holds w_k in slot 2k and the midpoint state in slot 2k+1. */
+  const float* d_dtkl; const float* d_nscale; const int32_t* d_nidx; const int32_t* d_back;
 } bsde_wsde_desc;
 
 size_t bsde_wsde_workspace_bytes(const bsde_wsde_desc* d, const bsde_fw_params* fw);
@@ -206,6 +219,46 @@ int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const float* h_d
 int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const float* h_dtk,
                    const float* d_wtraj, const float* d_xs, const float* d_acts, float* d_gx,
                    float* d_gw_traj, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * torch front end: the feed-forward drift net on the hidden state (make_y_net, torchbnn/_impl/models.py:25-54,
+ * blocks of torchbnn/_impl/diffeq_layers.py:280-311 + ConvDownsample :230-239) -- one evaluation and its reverse
+ * ---------------------------------------------------------------------------------------- */
+
+#define BSDE_CHAIN_MAX_LAYERS 40
+
+typedef struct {
+  int32_t S, B;            /* weight samples, images per sample */
+  int32_t nlayers;
+  int32_t act;             /* bsde_act applied after the layers flagged in act_after */
+  int32_t math;            /* bsde_math */
+  int32_t act_after[BSDE_CHAIN_MAX_LAYERS];      /* 1: DiffEqWrapper(activation) follows conv l; must be 0 for the last */
+  bsde_conv_layer layers[BSDE_CHAIN_MAX_LAYERS]; /* layer l's output shape is layer l+1's input shape */
+} bsde_chain_desc;
+
+size_t bsde_chain_workspace_bytes(const bsde_chain_desc* d, int32_t backward);
+/* floats of the buffer that receives every layer's output (256-byte aligned slots), and the offset (floats) of the
+ * last layer's output f inside it */
+size_t bsde_chain_acts_floats(const bsde_chain_desc* d);
+size_t bsde_chain_out_offset(const bsde_chain_desc* d);
+
+/* f = y_net(t, x; w) (DiffEqSequential.forward with explicit params, diffeq_layers.py:49-56).  d_x: [S*B] NHWC images;
+ * image n uses the flat weight vector d_w + (n / B) * w_sample_stride.  d_acts receives all layer outputs. */
+int bsde_chain_fwd(const bsde_chain_desc* d, float t, const float* d_w, int64_t w_sample_stride, const float* d_x,
+                   float* d_acts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Reverse of one evaluation.  d_gf = dL/df (shape of the last layer's output).  d_gx receives dL/dx (added to its
+ * content when accumulate_gx != 0); d_gw + s * gw_sample_stride receives dL/dw of sample s (every element that belongs
+ * to a layer of the chain is written). */
+int bsde_chain_bwd(const bsde_chain_desc* d, float t, const float* d_w, int64_t w_sample_stride, const float* d_x,
+                   const float* d_acts, const float* d_gf, float* d_gx, int32_t accumulate_gx, float* d_gw,
+                   int64_t gw_sample_stride, void* workspace, size_t workspace_bytes, void* stream);
+
+/* SDENet.f adds the drift to the state in flat NCHW order (models.py:163,168 `fy.reshape(-1)`): with NHWC storage
+ *     out[n][h][w][c] = (d_base ? d_base[n][h][w][c] : 0) + a * src[n][h2][w2][c2],   c*H*W + h*W + w == c2*H2*W2 + h2*W2 + w2
+ * out/base: [nimg][H][W][C], src: [nimg][H2][W2][C2].  Swapping the shapes gives the transpose (reverse pass). */
+int bsde_nchw_reinterp_axpy(int64_t nimg, int32_t C, int32_t H, int32_t W, int32_t C2, int32_t H2, int32_t W2, float a,
+                            const float* d_base, const float* d_src, float* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * generic flat-state step and Brownian increments

@@ -1,0 +1,190 @@
+"""CPU oracle for the torch front end.  TEST INFRASTRUCTURE ONLY.
+
+Restates, with plain torch CPU ops (fp64 or fp32, autograd for the gradients):
+  * the drift network on the hidden state, `make_y_net` (torchbnn/_impl/models.py:25-54) built from
+    `make_ode_k3_block_layers` (torchbnn/_impl/diffeq_layers.py:280-311), `ConcatConv2d` (:75-119),
+    `ConcatConvTranspose2d` (:122-166), `ConvDownsample` (:230-239), `channel_cat` (torchbnn/_impl/utils.py:201-203),
+    with the parameters taken from ONE flat vector in `ravel_pytree` order (utils.py:172-193; per conv layer
+    `[weight.ravel(), bias]`, models.py:131-133);
+  * the weight drift network `make_w_net` (models.py:57-80): `Linear` layers (time is ignored, diffeq_layers.py:169-175)
+    with tanh between them (models.py:136-141);
+  * `SDENet.f` / `SDENet.g` / `SDENet.forward` (models.py:159-201) with the INTENDED semantics of SURVEY quirk Q7: a flat
+    1-D state `[y, w, logqp]` (the class as shipped raises in `split` / `cat`): `fw = nn - w`, `fl = sum(nn^2)/sigma^2`,
+    `g = [0, sigma, 0]`, `logqp = 0.5 * state[-1]`;
+  * torchsde's fixed-step Stratonovich solvers for diagonal noise (third-party, un-pinned git dependency, requirements.txt:5;
+    absent here - restated from the published algorithm, torchsde/_core/methods/{midpoint,euler_heun,milstein}.py):
+        midpoint    y' = y + dt/2 f(t,y) + g(t,y) I/2 ;  y1 = y + dt f(t+dt/2, y') + g(t+dt/2, y') I
+        euler_heun  y' = y + g(t,y) I ;                  y1 = y + dt f(t,y) + (g(t,y) + g(t1,y')) I / 2
+    with I = W(t1) - W(t0) supplied by the caller (`BrownianInterval` is replaced by explicit increments).  With the constant
+    diagonal g of SDENet every noise term is sigma * I.
+
+PARITY STATUS: the conv stack and the w-net are PINNED against the reference's own `make_y_net` / `make_w_net`, which run in
+this container (tests/golden/make_golden_torch_sdenet.py -> tests/golden/torch_sdenet.npz); the solver loop is unpinned
+(torchsde is not installable; `SDENet.forward` is not runnable as shipped, Q7).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def act(name, x):
+    if name == "softplus":
+        return F.softplus(x)
+    if name == "tanh":
+        return torch.tanh(x)
+    if name == "elu":
+        return F.elu(x)
+    if name == "relu":
+        return torch.relu(x)
+    raise ValueError(name)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# y_net layout: list of ("conv", dict) / ("act", None) in evaluation order, offsets into the flat vector
+# ---------------------------------------------------------------------------------------------------------------
+def y_net_layout(input_size, blocks=(2, 2, 2), hidden_width=128, aug_dim=0):
+    """models.py:25-54 + diffeq_layers.py:280-311 (mode 0).  Returns (ops, P, output_size)."""
+    c, h, w = input_size[0] + aug_dim, input_size[1], input_size[2]
+    ops, off = [], 0
+
+    def conv(cin, cout, stride=1, padding=0, transpose=False, output_padding=0):
+        nonlocal off
+        # nn.Conv2d weight (cout, cin+1, 3, 3); nn.ConvTranspose2d weight (cin+1, cout, 3, 3)
+        shape = (cin + 1, cout, 3, 3) if transpose else (cout, cin + 1, 3, 3)
+        nw = (cin + 1) * cout * 9
+        d = dict(cin=cin, cout=cout, stride=stride, padding=padding, transpose=transpose, output_padding=output_padding,
+                 w_off=off, b_off=off + nw, shape=shape)
+        off += nw + cout
+        ops.append(("conv", d))
+
+    for i, nb in enumerate(blocks, 1):
+        for j in range(1, nb + 1):
+            conv(c, hidden_width, padding=1)
+            ops.append(("act", None))
+            conv(hidden_width, hidden_width, stride=2, padding=1)
+            ops.append(("act", None))
+            conv(hidden_width, hidden_width, stride=2, transpose=True, output_padding=1)
+            ops.append(("act", None))
+            conv(hidden_width, c)
+            if i < len(blocks) or j < nb:   # last_activation
+                ops.append(("act", None))
+        if i < len(blocks):
+            conv(c, 4 * c, stride=2, padding=1)   # ConvDownsample
+            c, h, w = 4 * c, h // 2, w // 2
+    return ops, off, (c, h, w)
+
+
+def y_net_apply(ops, flat_w, t, y, activation="softplus"):
+    """DiffEqSequential.forward with explicit params (diffeq_layers.py:49-56).  y: (B, C, H, W)."""
+    for kind, d in ops:
+        if kind == "act":
+            y = act(activation, y)
+            continue
+        W = flat_w[d["w_off"]:d["b_off"]].reshape(d["shape"])
+        b = flat_w[d["b_off"]:d["b_off"] + d["cout"]]
+        tt = torch.as_tensor(t, dtype=y.dtype).reshape(1, 1, 1, 1).expand(y.shape[0], 1, y.shape[2], y.shape[3])
+        ty = torch.cat((tt, y), dim=1)      # utils.channel_cat: time channel FIRST
+        if d["transpose"]:
+            y = F.conv_transpose2d(ty, W, b, d["stride"], d["padding"], d["output_padding"])
+        else:
+            y = F.conv2d(ty, W, b, d["stride"], d["padding"])
+    return y
+
+
+def init_y_params(ops, P, gen, dtype=torch.float32):
+    """nn.Conv2d / nn.ConvTranspose2d default init (kaiming_uniform(a=sqrt 5) => U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for
+    weight and bias; fan_in = shape[1] * 9 as torch computes it)."""
+    w = torch.zeros(P, dtype=dtype)
+    for kind, d in ops:
+        if kind != "conv":
+            continue
+        bound = 1.0 / math.sqrt(d["shape"][1] * 9)
+        n = d["b_off"] - d["w_off"]
+        w[d["w_off"]:d["b_off"]] = (torch.rand(n, generator=gen, dtype=dtype) * 2 - 1) * bound
+        w[d["b_off"]:d["b_off"] + d["cout"]] = (torch.rand(d["cout"], generator=gen, dtype=dtype) * 2 - 1) * bound
+    return w
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# w_net
+# ---------------------------------------------------------------------------------------------------------------
+def init_w_net(P, hidden_sizes, gen, dtype=torch.float32, last_std=0.0):
+    """models.py:57-80: nn.Linear default init, last layer zeros (:67-69); `last_std` > 0 perturbs it."""
+    sizes = (P,) + tuple(hidden_sizes) + (P,)
+    layers = []
+    for i, (din, dout) in enumerate(zip(sizes[:-1], sizes[1:]), 1):
+        bound = 1.0 / math.sqrt(din)
+        W = (torch.rand(dout, din, generator=gen, dtype=dtype) * 2 - 1) * bound
+        b = (torch.rand(dout, generator=gen, dtype=dtype) * 2 - 1) * bound
+        if i + 1 == len(sizes):
+            W = torch.randn(dout, din, generator=gen, dtype=dtype) * last_std
+            b = torch.randn(dout, generator=gen, dtype=dtype) * last_std
+        layers.append((W, b))
+    return layers
+
+
+def w_net_apply(layers, w, activation="tanh"):
+    """models.py:62-71: Linear -> act -> ... -> Linear (time ignored)."""
+    h = w
+    for i, (W, b) in enumerate(layers):
+        h = F.linear(h, W, b)
+        if i + 1 < len(layers):
+            h = act(activation, h)
+    return h
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SDENet drift / diffusion on the flat state, fixed-step solvers
+# ---------------------------------------------------------------------------------------------------------------
+class SDENetOracle:
+    def __init__(self, input_size=(3, 32, 32), blocks=(2, 2, 2), weight_network_sizes=(1, 64, 1), activation="softplus",
+                 sigma=0.1, hidden_width=128, aug_dim=0):
+        self.input_size = tuple(input_size)
+        self.aug_dim = aug_dim
+        self.aug_input_size = (aug_dim + input_size[0],) + tuple(input_size[1:])
+        self.ops, self.P, self.output_size = y_net_layout(input_size, blocks, hidden_width, aug_dim)
+        self.activation, self.sigma = activation, sigma
+        self.hidden_sizes = tuple(weight_network_sizes)
+
+    def f_parts(self, t, y, w, w_layers):
+        """models.py:159-169 on the split state.  y: (B, C, H, W) -> fy reshaped back to y's shape (flat NCHW order)."""
+        fy = y_net_apply(self.ops, w, t, y, self.activation).reshape(y.shape[0], -1)
+        assert fy.shape[1] == y[0].numel(), "Check nblocks for dataset divisibility."   # models.py:167
+        nn_ = w_net_apply(w_layers, w)
+        return fy.reshape(y.shape), nn_ - w, (nn_ ** 2).sum() / self.sigma ** 2, nn_
+
+    def solve(self, y, w0, w_layers, increments, dt=0.05, method="midpoint", t0=0.0, t1=1.0, return_path=False):
+        """sdeint(self, aug_y, ts=[0,1], bm, method, dt) (models.py:184-197).  increments: (nsteps, P) = W(t_{k+1}) - W(t_k)."""
+        n = int(round((t1 - t0) / dt))
+        assert increments.shape[0] == n
+        w, lq = w0, torch.zeros((), dtype=y.dtype)
+        path = [w0]
+        for k in range(n):
+            tk = t0 + k * dt
+            I = increments[k]
+            fy, fw, fl, _ = self.f_parts(tk, y, w, w_layers)
+            if method == "midpoint":
+                y_p = y + 0.5 * dt * fy
+                w_p = w + 0.5 * dt * fw + 0.5 * self.sigma * I
+                fy2, fw2, fl2, _ = self.f_parts(tk + 0.5 * dt, y_p, w_p, w_layers)
+                y, w, lq = y + dt * fy2, w + dt * fw2 + self.sigma * I, lq + dt * fl2
+                path += [w_p, w]
+            elif method in ("euler_heun", "milstein"):
+                # constant diagonal g: g(t1, y') = g(t, y) and g dg = 0, so both reduce to the Euler update
+                y, w, lq = y + dt * fy, w + dt * fw + self.sigma * I, lq + dt * fl
+                path += [w]
+            else:
+                raise ValueError(f"Unknown method: {method}")
+        if return_path:
+            return y, w, lq, torch.stack(path)
+        return y, w, lq
+
+    def forward(self, x, w0, w_layers, proj, increments, dt=0.05, method="midpoint"):
+        """SDENet.forward (models.py:180-201): zero channels, solve, projection head, logqp = state[-1] / 2."""
+        if self.aug_dim > 0:
+            x = torch.cat((x, x.new_zeros(x.shape[0], self.aug_dim, *x.shape[2:])), dim=1)
+        y1, _, lq = self.solve(x, w0, w_layers, increments, dt, method)
+        (W1, b1), (W2, b2) = proj
+        logits = F.linear(torch.relu(F.linear(y1.reshape(y1.shape[0], -1), W1, b1)), W2, b2)
+        return logits, 0.5 * lq

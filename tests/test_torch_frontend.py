@@ -1,0 +1,245 @@
+"""torch front end.
+
+CPU: the oracle restatement (oracle/torch_path.py) against golden vectors produced by the REFERENCE's own `make_y_net` /
+`make_w_net` (tests/golden/make_golden_torch_sdenet.py), fp64 finite differences of the oracle's solve, host logic.
+GPU: `bayesde_b200.torch_models` (through libbsde.so) against the oracle on the same inputs and Brownian increments.
+
+Tolerances: fp32 conv path -- drift net vs reference golden 2e-5 * max|ref|; y_T, w trajectory, logqp vs fp64 oracle
+rtol 1e-4; gradients 1e-3 * max|ref|.  Tensor-core path (TF32 operands, 10-bit mantissa) -- y_T 5e-3 * max|ref|,
+gradients 3e-2 * max|ref|.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_path as tp
+
+GOLD = np.load(__file__.rsplit("/", 1)[0] + "/golden/torch_sdenet.npz")
+DEV = "cuda:0"
+
+
+def _case(tag):
+    cfg = [int(v) for v in GOLD[f"{tag}_cfg"]]
+    c, h, w, nb = cfg[:4]
+    blocks = tuple(cfg[4:4 + nb])
+    hw, aug, B = cfg[4 + nb:]
+    return (c, h, w), blocks, hw, aug, B, tuple(int(v) for v in GOLD[f"{tag}_wsizes"])
+
+
+# ------------------------------------------------------------------------------------------------ CPU
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_oracle_matches_reference_y_net_and_w_net(tag):
+    """PIN: the oracle reproduces the reference's own make_y_net / make_w_net outputs bit for bit (same torch ops)."""
+    insz, blocks, hw, aug, B, wsizes = _case(tag)
+    ops, P, osz = tp.y_net_layout(insz, blocks, hw, aug)
+    flat = torch.from_numpy(GOLD[f"{tag}_flat"])
+    assert P == flat.numel() and tuple(osz) == tuple(GOLD[f"{tag}_out_size"])
+    fy = tp.y_net_apply(ops, flat, float(GOLD[f"{tag}_t"]), torch.from_numpy(GOLD[f"{tag}_y"]))
+    assert torch.equal(fy, torch.from_numpy(GOLD[f"{tag}_fy"]))
+    layers = [(torch.from_numpy(GOLD[f"{tag}_wnet_W{i}"]), torch.from_numpy(GOLD[f"{tag}_wnet_b{i}"])) for i in range(len(wsizes) + 1)]
+    nn_ = tp.w_net_apply(layers, flat)
+    assert torch.equal(nn_, torch.from_numpy(GOLD[f"{tag}_nn"]))
+    net = tp.SDENetOracle((insz[0] - 0, insz[1], insz[2]), blocks, wsizes, sigma=0.1, hidden_width=hw, aug_dim=aug)
+    _, fw, fl, _ = net.f_parts(float(GOLD[f"{tag}_t"]), torch.from_numpy(GOLD[f"{tag}_y"]), flat, layers)
+    assert torch.allclose(fw, torch.from_numpy(GOLD[f"{tag}_fw"]), rtol=0, atol=0)
+    assert torch.allclose(fl, torch.from_numpy(GOLD[f"{tag}_fl"])[0], rtol=1e-6)
+
+
+def _small_problem(dtype=torch.float64, seed=0, method="midpoint", nsteps=3, aug=1):
+    g = torch.Generator().manual_seed(seed)
+    net = tp.SDENetOracle((2, 8, 8), (1, 1), (1, 8, 1), sigma=0.3, hidden_width=4, aug_dim=aug)
+    w0 = tp.init_y_params(net.ops, net.P, g, dtype)
+    wl = tp.init_w_net(net.P, net.hidden_sizes, g, dtype, last_std=0.05)
+    x = torch.randn(2, 2 + aug, 8, 8, generator=g, dtype=dtype)
+    h = 1.0 / nsteps
+    I = torch.randn(nsteps, net.P, generator=g, dtype=dtype) * h ** 0.5
+    return net, w0, wl, x, I, h
+
+
+def test_oracle_midpoint_properties():
+    """sigma -> 0 with a zero w-net: w follows dw = -w exactly as the midpoint rule prescribes, logqp = 0; midpoint and the
+    Euler-type schemes agree to O(h)."""
+    net, w0, wl, x, I, h = _small_problem(nsteps=4)
+    wl0 = [(W * 0, b * 0) for W, b in wl]
+    y, w, lq = net.solve(x, w0, wl0, I * 0, dt=h, method="midpoint")
+    assert torch.allclose(w, w0 * (1 - h + h * h / 2) ** 4, rtol=1e-12)
+    assert lq.item() == 0.0
+    with pytest.raises(ValueError, match="Unknown method"):
+        net.solve(x, w0, wl, I, dt=h, method="srk")
+    n = 64
+    g = torch.Generator().manual_seed(1)
+    If = torch.randn(n, net.P, generator=g, dtype=torch.float64) * (1.0 / n) ** 0.5
+    ya, wa, la = net.solve(x, w0, wl, If, dt=1.0 / n, method="midpoint")
+    yb, wb, lb = net.solve(x, w0, wl, If, dt=1.0 / n, method="euler_heun")
+    assert (wa - wb).abs().max() < 5e-2 * wa.abs().max() and abs(la - lb) < 5e-2 * abs(la)
+
+
+def test_oracle_gradient_finite_differences():
+    """fp64 central differences of the oracle's loss along random directions (the analogue of jaxsde/tests/test_vjp.py:88-114)."""
+    net, w0, wl, x, I, h = _small_problem()
+    w0 = w0.clone().requires_grad_(True)
+
+    def loss(w0_):
+        y, _, lq = net.solve(x, w0_, wl, I, dt=h)
+        return (y ** 2).sum() + 1e-3 * lq
+
+    (g,) = torch.autograd.grad(loss(w0), w0)
+    gen = torch.Generator().manual_seed(5)
+    for _ in range(3):
+        v = torch.randn(net.P, generator=gen, dtype=torch.float64)
+        eps = 1e-6
+        fd = (loss(w0.detach() + eps * v) - loss(w0.detach() - eps * v)) / (2 * eps)
+        assert abs(fd - (g * v).sum()) <= 1e-5 * abs(fd) + 1e-8
+
+
+def test_host_layout_matches_oracle_and_reference_pytree():
+    from bayesde_b200 import torch_models as tm
+    for insz, blocks, hw, aug in [((3, 32, 32), (2, 2, 2), 32, 0), ((2, 16, 16), (2, 2, 2), 6, 1), ((1, 8, 8), (1,), 4, 2)]:
+        net, osz = tm.make_y_net(insz, blocks, hidden_width=hw, aug_dim=aug)
+        ops, P, osz2 = tp.y_net_layout(insz, blocks, hw, aug)
+        assert net.P == P and tuple(osz) == tuple(osz2)
+        convs = [d for k, d in ops if k == "conv"]
+        assert [(l["w_off"], l["b_off"], l["shape"]) for l in net.layers] == [(d["w_off"], d["b_off"], d["shape"]) for d in convs]
+        flat, unravel = tm.ravel_pytree(net.make_initial_params(torch.Generator().manual_seed(0)))
+        assert flat.numel() == P
+        tree = unravel(flat)
+        assert [tuple(e[0].shape) for e in tree if len(e)] == [d["shape"] for d in convs]
+    assert tm.make_y_net((3, 32, 32), hidden_width=32)[0].P == 196296
+    with pytest.raises(AssertionError, match="divisibility"):
+        tm.make_y_net((1, 28, 28), (2, 2, 2), hidden_width=4)                    # 7x7 third group (quirk Q10 analogue)
+    cfg = tm.SolveConfig(net, 1, 2, 20, 0.05, "midpoint", 0.1, (1, 8, 1), "tanh", "fp32", False)
+    assert cfg.nit == 40 and cfg.back.tolist()[:4] == [0, 1, 0, 1] and abs(cfg.tk[3] - 0.075) < 1e-7 and cfg.dtkl[0] == 0
+    with pytest.raises(ValueError, match="Unknown method"):
+        tm.SolveConfig(net, 1, 2, 20, 0.05, "srk", 0.1, (1, 8, 1), "tanh", "fp32", False)
+
+
+def test_sdenet_module_surface(built_lib):
+    from bayesde_b200 import _lib, torch_models as tm
+    m = tm.SDENet(input_size=(2, 8, 8), blocks=(1, 1), weight_network_sizes=(1, 8, 1), hidden_width=4, aug_dim=1)
+    keys = set(m.state_dict().keys())
+    assert {"flat_initial_params", "w_net.layers.0.weight", "w_net.layers.4.bias", "projection.1.weight", "projection.3.bias",
+            "ts", "aug_zeros"} <= keys
+    assert m.params_size == m.y_net.P and float(m.w_net.linears()[-1].weight.abs().max()) == 0.0
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 2, 8, 8), adjoint=True)
+    with pytest.raises(_lib.BsdeError):
+        m(torch.zeros(1, 2, 8, 8))     # CPU tensor: no fallback
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _close(a, b, tol, what):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item()
+    assert err <= tol * ref + 1e-12, f"{what}: max err {err:.3e} vs ref max {ref:.3e} (tol {tol:g})"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("math_mode,tol", [("fp32", 2e-5), ("tc", 5e-3)])
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_gpu_y_net_matches_reference_golden(built_lib, tag, math_mode, tol):
+    """bsde_chain_fwd (all groups + ConvDownsample, OIHW / IOHW weights read in place, time channel first) against the
+    REFERENCE's own make_y_net output."""
+    from bayesde_b200 import torch_models as tm
+    insz, blocks, hw, aug, B, _ = _case(tag)
+    net, _ = tm.make_y_net(insz, blocks, hidden_width=hw, aug_dim=aug)
+    fy = net(float(GOLD[f"{tag}_t"]), torch.from_numpy(GOLD[f"{tag}_y"]).to(DEV), torch.from_numpy(GOLD[f"{tag}_flat"]).to(DEV), math_mode)
+    _close(fy, torch.from_numpy(GOLD[f"{tag}_fy"]), tol, f"y_net {tag} {math_mode}")
+
+
+def _run_gpu(net, w0, wl, x, I, h, method, math_mode, remat, seed_loss=3):
+    from bayesde_b200 import torch_models as tm
+    ynet, _ = tm.make_y_net(net.input_size, _run_gpu.blocks, activation=net.activation, hidden_width=_run_gpu.hw, aug_dim=net.aug_dim)
+    assert ynet.P == net.P
+    B = x.shape[0]
+    cfg = tm.SolveConfig(ynet, 1, B, I.shape[0], h, method, net.sigma, net.hidden_sizes, "tanh", math_mode, remat)
+    xd = x.float().permute(0, 2, 3, 1).contiguous()[None].to(DEV).requires_grad_(True)
+    w0d = w0.float().to(DEV).requires_grad_(True)
+    lin = [(W.float().to(DEV).requires_grad_(True), b.float().to(DEV).requires_grad_(True)) for W, b in wl]
+    y1, lq, wtraj = tm.sdenet_solve(cfg, xd, w0d, lin, I.float().to(DEV)[None])
+    y1n = y1[0].permute(0, 3, 1, 2)
+    g = torch.Generator().manual_seed(seed_loss)
+    cot = torch.randn(y1n.shape, generator=g).to(DEV)
+    loss = (y1n * cot).sum() + 0.7 * lq[0]
+    grads = torch.autograd.grad(loss, [xd, w0d] + [t for p in lin for t in p])
+    return y1n, lq[0], wtraj[0], grads, cot
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,math_mode,remat", [("midpoint", "fp32", False), ("midpoint", "fp32", True), ("euler_heun", "fp32", False),
+                                                   ("midpoint", "tc", False), ("milstein", "tc", True)])
+def test_gpu_sdenet_solve_matches_oracle(built_lib, method, math_mode, remat):
+    """State, w trajectory (all stages), logqp and every gradient of the fixed-step solve against the fp64 oracle with the
+    same increments: two groups (ConvDownsample in the drift), aug channel, P -> 2 -> 8 -> 3 -> P w-net."""
+    g = torch.Generator().manual_seed(11)
+    blocks, hw = (1, 1), 8
+    net = tp.SDENetOracle((2, 8, 8), blocks, (2, 8, 3), sigma=0.3, hidden_width=hw, aug_dim=1)
+    _run_gpu.blocks, _run_gpu.hw = blocks, hw
+    dt64 = torch.float64
+    w0 = tp.init_y_params(net.ops, net.P, g, dt64).requires_grad_(True)
+    wl = [(W.requires_grad_(True), b.requires_grad_(True)) for W, b in tp.init_w_net(net.P, net.hidden_sizes, g, dt64, last_std=0.05)]
+    x = torch.randn(3, 3, 8, 8, generator=g, dtype=dt64).requires_grad_(True)
+    n = 4
+    h = 1.0 / n
+    I = torch.randn(n, net.P, generator=g, dtype=dt64) * h ** 0.5
+    y1n, lq, wtraj, grads, cot = _run_gpu(net, w0.detach(), [(W.detach(), b.detach()) for W, b in wl], x.detach(), I, h, method, math_mode, remat)
+    yr, wr, lr, path = net.solve(x, w0, wl, I, dt=h, method=method, return_path=True)
+    loss = (yr * cot.double().cpu()).sum() + 0.7 * lr
+    gr = torch.autograd.grad(loss, [x, w0] + [t for p in wl for t in p])
+    ty, tg = (1e-4, 1e-3) if math_mode == "fp32" else (5e-3, 3e-2)
+    _close(wtraj, path, 1e-5, "w trajectory (all stages)")
+    _close(lq, lr, 1e-4, "logqp state")
+    _close(y1n, yr, ty, "y_T")
+    _close(grads[0][0].permute(0, 3, 1, 2), gr[0], tg, "dL/dx")
+    names = ["w0"] + [f"w_net[{i // 2}].{'weight' if i % 2 == 0 else 'bias'}" for i in range(2 * len(wl))]
+    for nme, a, b in zip(names, grads[1:], gr[1:]):
+        _close(a, b, tg, f"dL/d{nme}")
+
+
+@pytest.mark.gpu
+def test_gpu_sdenet_module_forward_backward(built_lib):
+    """The nn.Module surface: forward(y, dt, method) -> (logits, logqp) with replayed increments against the oracle's forward,
+    Philox path determinism, nfe bookkeeping, gradients reach every parameter."""
+    from bayesde_b200 import torch_models as tm
+    torch.manual_seed(0)
+    m = tm.SDENet(input_size=(2, 8, 8), blocks=(1, 1), weight_network_sizes=(1, 8, 1), hidden_width=4, aug_dim=1, sigma=0.2, math="fp32").to(DEV)
+    with torch.no_grad():
+        last = m.w_net.linears()[-1]
+        last.weight.normal_(0, 0.05), last.bias.normal_(0, 0.05)
+    x = torch.randn(3, 2, 8, 8, device=DEV)
+    n = 5
+    I = torch.randn(n, m.params_size, device=DEV) * (1.0 / n) ** 0.5
+    logits, logqp = m(x, dt=1.0 / n, method="midpoint", increments=I)
+    assert m.nfe == 4 * n and logits.shape == (3, 10)
+    net = tp.SDENetOracle((2, 8, 8), (1, 1), (1, 8, 1), sigma=0.2, hidden_width=4, aug_dim=1)
+    dd = lambda t: t.detach().double().cpu()
+    proj = [(dd(m.projection[1].weight), dd(m.projection[1].bias)), (dd(m.projection[3].weight), dd(m.projection[3].bias))]
+    lo, lq = net.forward(dd(x), dd(m.flat_initial_params), [(dd(l.weight), dd(l.bias)) for l in m.w_net.linears()], proj, dd(I), dt=1.0 / n)
+    _close(logits, lo, 1e-4, "logits")
+    _close(logqp, lq, 1e-4, "logqp")
+    (logits.logsumexp(1).mean() + 1e-3 * logqp).backward()
+    for nme, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().max() > 0, nme
+    # in-kernel Philox: same (seed, call) -> same result; next call -> fresh noise
+    m._calls = 0
+    a1, q1 = m(x, dt=0.25)
+    m._calls = 0
+    a2, q2 = m(x, dt=0.25)
+    a3, q3 = m(x, dt=0.25)
+    assert torch.equal(a1, a2) and torch.equal(q1, q2) and not torch.equal(q1, q3)
+
+
+@pytest.mark.gpu
+def test_gpu_nchw_reinterp_roundtrip(built_lib):
+    """bsde_nchw_reinterp_axpy against torch's reshape on NCHW tensors, and <R x, y> == <x, R^T y>."""
+    from bayesde_b200 import torch_models as tm
+    B, chw, chw2 = 3, (3, 8, 8), (12, 4, 4)
+    f = torch.randn(B, *chw2, device=DEV)
+    y = torch.randn(B, *chw, device=DEV)
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    out = torch.empty(B, 8, 8, 3, device=DEV)
+    tm.reinterp_axpy(out, chw, nhwc(y), 0.5, nhwc(f), chw2)
+    assert torch.equal(out.permute(0, 3, 1, 2), y + 0.5 * f.reshape(B, *chw))
+    back = torch.empty(B, 4, 4, 12, device=DEV)
+    tm.reinterp_axpy(back, chw2, None, 1.0, nhwc(y), chw)
+    assert torch.equal(back.permute(0, 3, 1, 2), y.reshape(B, *chw2))
