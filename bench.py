@@ -66,6 +66,51 @@ def conv_flops_per_image_eval():
     return total
 
 
+def conv_bytes_per_image_eval():
+    """Algorithmic HBM bytes of the conv stacks for one image and one drift evaluation with fp32 NHWC activations and no
+    cross-layer fusion: every layer reads its input once and writes its output once.  Returns (fwd, bwd): bwd = data
+    gradients (dy read, act'(.) operand read, dz written) + weight gradients (layer input and dy read)."""
+    from bayesde_b200.arch import FxSpec
+    fwd = bwd = 0
+    shape = (1, 32, 32, 5)
+    for gi, nb in enumerate(MODEL_KW["nblocks"]):
+        fx = FxSpec(0, shape, MODEL_KW["fx_dim"], "softplus")
+        f = b = 0
+        n = len(fx.layers)
+        for li, L in enumerate(fx.layers):
+            vin, vout = L["hin"] * L["win"] * L["cin"], L["hout"] * L["wout"] * L["cout"]
+            f += vin + vout + (vout if li == n - 1 else 0)      # Euler epilogue reads x_k
+            b += vout + vin + vin                               # dgrad: dy, aux (act output / gx), dz
+            b += vin + vout                                     # wgrad: layer input, dy
+        fwd += nb * f * 4
+        bwd += nb * b * 4
+        shape = (1, shape[1] // 2, shape[2] // 2, shape[3] * 4)
+    return fwd, bwd
+
+
+def measure_tf32_peak(dev):
+    """Dense TF32 tensor-core throughput measured live the way MEASURED_PEAKS.json's bf16 figure was (cuBLAS 8192^3)."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        return 10 * 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -284,6 +329,8 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
     peak_hbm = peaks.get("hbm_gbs", 6650.0)
     fl_eval = conv_flops_per_image_eval()
+    tf32_peak = measure_tf32_peak(dev) if args.math == "tc" else None
+    by_fwd, by_bwd = conv_bytes_per_image_eval()
     nit = MODEL_KW["nsteps"] - 1
     alg_flops_step = 3.0 * fl_eval * nit * B * args.nsamples  # fwd + dgrad + wgrad (recompute not counted)
     conv_ms = (ktime.get("k2_fwd", 0.0) + ktime.get("k3_bwd", 0.0)) / args.steps
@@ -303,14 +350,27 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "K2/K3 time-dependent conv stack (conv_win_kernel / wgrad_win_kernel + "
                                "conv_tc / wgrad_tc fallbacks; tcgen05 kind::tf32)",
-                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "peak_source": peak_src + "; TF32 dense peak is half of the bf16 figure",
+                     "achieved": achieved, "peak": tf32_peak or peak_tf, "unit": "TFLOP/s", "frac": achieved / (tf32_peak or peak_tf),
+                     "peak_source": ("measured live in this run: cuBLAS 8192^3 TF32 matmul (the kernels issue tcgen05 kind::tf32; "
+                                     "MEASURED_PEAKS.json holds no TF32 figure, SURVEY 8.4)" if tf32_peak else peak_src),
+                     "peak_bf16_sustained": peak_tf, "frac_of_bf16_peak": achieved / peak_tf,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one conv_win_kernel launch (64->5 data gradient,
                      # 1024 images 32x32), ncu --set full capture summarised in profiles/r01_summary.md: equals the
                      # algorithmic bytes (input read once 268.8 MB + output 19.0 MB)
                      "traffic": 287.8e6,
                      "algorithmic_flops_per_step": alg_flops_step, "kernel_ms_per_step": conv_ms,
                      "share_of_step": conv_ms / (ms / args.steps)},
+        # the same conv launches against HBM: with fp32 NHWC activations and one launch per layer the byte floor
+        # (bytes / hbm_gbs) is ABOVE the flop floor (flops / tensor peak), i.e. this decomposition is HBM-bound
+        "roofline_hbm": {"bound": "hbm", "kernel": "the same K2/K3 conv launches",
+                         "achieved": (by_fwd + by_bwd) * nit * B * args.nsamples / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0,
+                         "peak": peak_hbm, "unit": "GB/s",
+                         "frac": ((by_fwd + by_bwd) * nit * B * args.nsamples / (conv_ms * 1e-3) / 1e9 / peak_hbm) if conv_ms > 0 else 0.0,
+                         "algorithmic_bytes_per_step": (by_fwd + by_bwd) * nit * B * args.nsamples,
+                         "byte_floor_ms": (by_fwd + by_bwd) * nit * B * args.nsamples / (peak_hbm * 1e9) * 1e3,
+                         "flop_floor_ms": alg_flops_step / ((tf32_peak or peak_tf) * 1e12) * 1e3,
+                         "note": "every layer reads its fp32 NHWC input once and writes its output once; dgrad also reads the "
+                                 "activation it differentiates; wgrad reads layer input + dy"},
         "roofline_k1": {"bound": "hbm", "kernel": "K1 wsde_fwd/bwd (cooperative persistent)",
                         "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0, "peak": peak_hbm,
                         "unit": "GB/s", "frac": (k1_bytes / (k1_ms * 1e-3) / 1e9 / peak_hbm) if k1_ms > 0 else 0.0,
