@@ -6,7 +6,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libbsde.so")
+# BSDE_LIB_PATH: tools-only override (A/B timing of two builds on the same box); the default is the in-tree library
+_LIB_PATH = os.environ.get("BSDE_LIB_PATH") or os.path.join(_HERE, "libbsde.so")
 
 FW_MAX_MID = 4
 FW_MAX_EDGE = 4
