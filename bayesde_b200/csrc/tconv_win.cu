@@ -57,6 +57,7 @@ struct WinArgs {
   long long wimg_sample_stride;  // floats
   int S, B, G, ntiles;
   int cin, cout, npad, nks, nhalf;
+  int opitch;  // floats per output pixel in `out` / `aux` (> cout when this launch produces a channel slice of the layer)
   int hin, win, hout, wout, sn, kn, off, sd, has_time, mode;
   int Hq, Wq, pitch, IP, Q, lead, NPOSw, NP, NA, nent;
   int ring, slab_bytes, w_bytes, tb_floats, nbuf, tmem_cols;
@@ -523,9 +524,9 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
     const int quarter = warp & 3, half = warp >> 2;
     float* stage = s_stage + warp * 32 * 16;
     int* w_pix = s_pix + warp * 32;
-    float* __restrict__ out = a.out + (long long)s * a.B * a.hout * a.wout * a.cout;
-    const float* __restrict__ aux = a.aux ? a.aux + (long long)s * a.B * a.hout * a.wout * a.cout : nullptr;
-    const bool vec_out = (a.cout & 3) == 0;
+    float* __restrict__ out = a.out + (long long)s * a.B * a.hout * a.wout * a.opitch;
+    const float* __restrict__ aux = a.aux ? a.aux + (long long)s * a.B * a.hout * a.wout * a.opitch : nullptr;
+    const bool vec_out = ((a.cout | a.opitch) & 3) == 0;
     const int nchunk = (a.cout + 15) >> 4;
     const int c4 = lane & 3, r8 = lane >> 2;
     const float e_rIP = 1.0f / (float)a.IP, e_rpitch = 1.0f / (float)a.pitch;
@@ -611,7 +612,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
           if (EPI >= BSDE_EPI_EULER) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              xv[j] = pp[j] >= 0 ? *reinterpret_cast<const float4*>(aux + (long long)pp[j] * a.cout + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+              xv[j] = pp[j] >= 0 ? *reinterpret_cast<const float4*>(aux + (long long)pp[j] * a.opitch + n) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
               qq.x = wn_combine<EPI, ACT>(qq.x, xv[j].x, a.scale); qq.y = wn_combine<EPI, ACT>(qq.y, xv[j].y, a.scale);
               qq.z = wn_combine<EPI, ACT>(qq.z, xv[j].z, a.scale); qq.w = wn_combine<EPI, ACT>(qq.w, xv[j].w, a.scale);
             }
-            *reinterpret_cast<float4*>(out + (long long)pp[j] * a.cout + n) = qq;
+            *reinterpret_cast<float4*>(out + (long long)pp[j] * a.opitch + n) = qq;
           }
         } else {
           // partial chunk / cout not a multiple of 4: rows r8 + 8 j, columns c4 + 4 i
@@ -633,7 +634,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
 #pragma unroll 1
             for (int cc = c4; cc < ncol; cc += 4) {
               const float qq = stage[rr * 16 + ((((cc >> 2) ^ ((rr >> 1) & 3)) << 2) | (cc & 3))];
-              const long long o = (long long)pq * a.cout + n0 + cc;
+              const long long o = (long long)pq * a.opitch + n0 + cc;
               const float xx = EPI >= BSDE_EPI_EULER ? aux[o] : 0.f;
               out[o] = wn_combine<EPI, ACT>(qq, xx, a.scale);
             }
@@ -789,10 +790,52 @@ static bool win_enabled() {
   return on != 0;
 }
 
+// A layer whose resident weight image does not fit beside the window ring (e.g. 80 -> 64 and 64 -> 80 channels: 184 KB) is
+// served as TWO launches over output-channel slices [0, c0) and [c0, cout): each slice is an ordinary layer whose kernel
+// and bias offsets are shifted by c0 output channels and whose rows are written with the full layer's pixel pitch.
+struct WinSplit {
+  int n;                     // 0: unsupported, 1: whole layer, 2: two channel slices
+  bsde_conv_layer sub[2];
+  int n0[2];                 // first output channel of each slice
+  size_t img_off[2];         // float offset of each slice's image inside a sample's image
+  size_t img_floats;         // floats of one sample's image (all slices)
+};
+
+static WinSplit win_split(const bsde_conv_layer* L) {
+  WinSplit sp;
+  memset(&sp, 0, sizeof(sp));
+  if (!L) return sp;
+  WinPlan p = win_plan(L);
+  if (p.ok) {
+    sp.n = 1; sp.sub[0] = *L; sp.img_floats = p.img_floats;
+    return sp;
+  }
+  static const int on = getenv("BSDE_WIN_NSPLIT") ? atoi(getenv("BSDE_WIN_NSPLIT")) : 1;
+  if (!on || L->cout < 32 || (L->cout & 3)) return sp;
+  const int c0 = ((L->cout / 2 + 15) / 16) * 16;   // 64 -> 32 + 32, 80 -> 48 + 32
+  if (c0 >= L->cout) return sp;
+  size_t off = 0;
+  for (int i = 0; i < 2; ++i) {
+    bsde_conv_layer& q = sp.sub[i];
+    q = *L;
+    sp.n0[i] = i == 0 ? 0 : c0;
+    q.cout = i == 0 ? c0 : L->cout - c0;
+    q.w_off = L->w_off + (long long)sp.n0[i] * L->w_n_stride;
+    if (L->b_off >= 0) q.b_off = L->b_off + sp.n0[i];
+    WinPlan ps = win_plan(&q);
+    if (!ps.ok) return sp;
+    sp.img_off[i] = off;
+    off += ps.img_floats;
+  }
+  sp.n = 2; sp.img_floats = off;
+  return sp;
+}
+
 bool tconv_win_supported(const bsde_conv_layer* L, int S, int B) {
   if (!win_enabled() || !L || S < 1 || S > 148 || B < 1) return false;
-  WinPlan p = win_plan(L);
-  if (!p.ok) return false;
+  WinSplit sp = win_split(L);
+  if (!sp.n) return false;
+  WinPlan p = win_plan(&sp.sub[0]);
   // 32-bit position / offset arithmetic inside the kernel
   if ((long long)B * p.IP + 1024 > (1LL << 24)) return false;  // fp32-reciprocal position decode is exact below 2^24
   if ((long long)B * L->hin * L->win * L->cin > 0x7FFFFFFFLL) return false;
@@ -801,26 +844,26 @@ bool tconv_win_supported(const bsde_conv_layer* L, int S, int B) {
 }
 
 size_t tconv_win_ws_bytes(const bsde_conv_layer* L, int S) {
-  WinPlan p = win_plan(L);
-  return p.ok ? p.img_floats * sizeof(float) * S : 0;
+  WinSplit sp = win_split(L);
+  return sp.n ? sp.img_floats * sizeof(float) * S : 0;
 }
 
-// floats of one sample's resident image (weight tiles + tables)
+// floats of one sample's resident image (weight tiles + tables; all channel slices)
 size_t tconv_win_img_floats(const bsde_conv_layer* L) {
-  WinPlan p = win_plan(L);
-  return p.ok ? p.img_floats : 0;
+  WinSplit sp = win_split(L);
+  return sp.n ? sp.img_floats : 0;
 }
 
 // Repack the weights of `nit` scan iterations in one launch: iteration z reads w + z*w_iter_stride and writes
 // img + z*S*img_floats ([iteration][sample][img_floats]).  `epi` only selects whether the bias row is kept.
-int tconv_win_repack(const bsde_conv_layer* L, int S, int nit, const float* w, long long w_sample_stride, long long w_iter_stride,
-                     int epi, float* img, cudaStream_t st) {
+static int win_repack_one(const bsde_conv_layer* L, int S, int nit, const float* w, long long w_sample_stride, long long w_iter_stride,
+                          int epi, float* img, long long img_sample_stride, cudaStream_t st) {
   WinPlan p = win_plan(L);
   BSDE_CHECK_ARG(p.ok, "layer not supported by the window-staged tensor-core path");
   WinRepackArgs r;
   memset(&r, 0, sizeof(r));
-  r.w = w; r.img = img; r.w_sample_stride = w_sample_stride; r.img_sample_stride = (long long)p.img_floats;
-  r.w_iter_stride = w_iter_stride; r.img_iter_stride = (long long)p.img_floats * S;
+  r.w = w; r.img = img; r.w_sample_stride = w_sample_stride; r.img_sample_stride = img_sample_stride;
+  r.w_iter_stride = w_iter_stride; r.img_iter_stride = img_sample_stride * S;
   r.nent = p.nent; r.nks = p.nks; r.npad = p.npad; r.cin = L->cin; r.cout = L->cout; r.ksize = L->ksize; r.NA = p.NA;
   r.real_base = (L->has_time && L->time_first) ? 1 : 0; r.has_time = L->has_time;
   r.time_row = L->time_first ? 0 : L->cin; r.use_bias = epi <= BSDE_EPI_EULER; r.w_floats = p.w_bytes / 4;
@@ -836,23 +879,53 @@ int tconv_win_repack(const bsde_conv_layer* L, int S, int nit, const float* w, l
   return 0;
 }
 
+int tconv_win_repack(const bsde_conv_layer* L, int S, int nit, const float* w, long long w_sample_stride, long long w_iter_stride,
+                     int epi, float* img, cudaStream_t st) {
+  WinSplit sp = win_split(L);
+  BSDE_CHECK_ARG(sp.n > 0, "layer not supported by the window-staged tensor-core path");
+  for (int i = 0; i < sp.n; ++i)
+    if (int e = win_repack_one(&sp.sub[i], S, nit, w, w_sample_stride, w_iter_stride, epi, img + sp.img_off[i], (long long)sp.img_floats, st))
+      return e;
+  return 0;
+}
+
+static int win_launch_one(const bsde_conv_layer* L, int S, int B, const float* in, float t, int act, int epi, float scale,
+                          const float* aux, float* out, int opitch, const float* wimg, long long wimg_sample_stride, int wsafe,
+                          cudaStream_t st);
+
 int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const float* w, long long w_sample_stride,
                   float t, int act, int epi, float scale, const float* aux, float* out, void* ws, size_t ws_bytes,
                   cudaStream_t st, const float* prepacked, int prepacked_safe) {
-  WinPlan p = win_plan(L);
-  BSDE_CHECK_ARG(p.ok, "layer not supported by the window-staged tensor-core path");
+  WinSplit sp = win_split(L);
+  BSDE_CHECK_ARG(sp.n > 0, "layer not supported by the window-staged tensor-core path");
   BSDE_CHECK_ARG(!(epi >= BSDE_EPI_EULER) || aux != nullptr, "epilogue %d needs aux", epi);
   if (!prepacked) {
-    const size_t need = p.img_floats * sizeof(float) * S;
+    const size_t need = sp.img_floats * sizeof(float) * S;
     if (!ws || ws_bytes < need) {
       set_error("tconv_fwd(win): workspace %zu < %zu bytes", ws_bytes, need);
       return BSDE_ERR_WORKSPACE;
     }
     if (int e = tconv_win_repack(L, S, 1, w, w_sample_stride, 0, epi, (float*)ws, st)) return e;
   }
+  const float* wimg = prepacked ? prepacked : (const float*)ws;
+  for (int i = 0; i < sp.n; ++i) {
+    // slice i > 0 follows slice i-1 in the stream: its image was written before that kernel started
+    const int wsafe = prepacked ? (i > 0 ? 1 : prepacked_safe) : 0;
+    if (int e = win_launch_one(&sp.sub[i], S, B, in, t, act, epi, scale, aux ? aux + sp.n0[i] : nullptr, out + sp.n0[i], L->cout,
+                               wimg + sp.img_off[i], (long long)sp.img_floats, wsafe, st))
+      return e;
+  }
+  return 0;
+}
+
+static int win_launch_one(const bsde_conv_layer* L, int S, int B, const float* in, float t, int act, int epi, float scale,
+                          const float* aux, float* out, int opitch, const float* wimg, long long wimg_sample_stride, int wsafe,
+                          cudaStream_t st) {
+  WinPlan p = win_plan(L);
+  BSDE_CHECK_ARG(p.ok, "layer not supported by the window-staged tensor-core path");
   WinArgs a;
   memset(&a, 0, sizeof(a));
-  a.in = in; a.aux = aux; a.out = out; a.wimg = prepacked ? prepacked : (const float*)ws; a.wimg_sample_stride = (long long)p.img_floats;
+  a.in = in; a.aux = aux; a.out = out; a.wimg = wimg; a.wimg_sample_stride = wimg_sample_stride; a.opitch = opitch;
   a.S = S; a.B = B;
   a.G = std::max(1, 148 / S);
   a.Q = B * p.IP;
@@ -897,7 +970,7 @@ int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const
   BSDE_CHECK_ARG(fn != nullptr, "epilogue %d / activation %d not instantiated", epi, act);
   BSDE_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   static const int pdl = getenv("BSDE_PDL") ? atoi(getenv("BSDE_PDL")) : 1;
-  a.wsafe = (prepacked && pdl) ? prepacked_safe : 0;
+  a.wsafe = pdl ? wsafe : 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(S * a.G); cfg.blockDim = dim3(WN_THREADS); cfg.dynamicSmemBytes = p.smem; cfg.stream = st;
