@@ -700,3 +700,38 @@ def test_jax_toy_solver_vs_oracle(built_lib):
     a = BU._sdeint(fd, gd, s0.float().to(DEV), P, ts, 3)
     b = BU._sdeint(fd, gd, s0.float().to(DEV), P, ts, 3)
     assert torch.equal(a, b)
+
+
+def test_config3_mnist_shape_and_q10(built_lib):
+    """Config 3 (28x28x1 MNIST shape, aug 2): nblocks 2-2 matches the oracle (loss, every gradient); nblocks 2-2-2 hits the
+    reference's shape assertion (quirk Q10: 7x7 third group, stride-2 conv -> 4, SAME transpose -> 8 != 7; brax.py:40)."""
+    from bayesde_b200.classification import SDEBNNClassifier
+    S, B = 2, 2
+    kw = dict(input_size=(28, 28, 1), aug=2, nblocks=(1, 1), fx_dim=8, fw_dims=(2, 8, 2), diff_coef=0.2, nsteps=4)
+    net_r = jp.SDEBNNClassifier(batch=B, **kw)
+    params_r, head_r = net_r.init(0, torch.float64, fw_last_std=0.05)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, 28, 28, 1, generator=g, dtype=torch.float64)
+    labels = torch.tensor([4, 0])
+    onehot = torch.nn.functional.one_hot(labels, 10).double()
+    dWs = [torch.stack([jp.sample_increments(b.P, 4, g, torch.float64) for _ in range(S)]) for b in net_r.blocks()]
+    eps = torch.randn(S, net_r.feat * 10 + 10, generator=g, dtype=torch.float64)
+    pr, leaves_r = [], []
+    for (w0, fw) in params_r:
+        w0 = w0.clone().requires_grad_(True)
+        fw = [tuple(t.clone().requires_grad_(True) for t in lay) for lay in fw]
+        pr.append((w0, fw))
+        leaves_r += [w0] + [t for lay in fw for t in lay]
+    hr = tuple(tuple(t.clone().requires_grad_(True) for t in pair) for pair in head_r)
+    leaves_r += [hr[0][0], hr[0][1], hr[1][0], hr[1][1]]
+    loss_r = torch.stack([net_r.loss(pr, hr, x, onehot, [d[s] for d in dWs], eps[s], 1e-5)[0] for s in range(S)]).mean()
+    grads_r = torch.autograd.grad(loss_r, leaves_r)
+    net = SDEBNNClassifier(nsamples=S, device=DEV, **kw)
+    net.load_oracle_params(params_r, head_r)
+    loss, _, _ = net.loss(x.float().to(DEV), labels.to(DEV), 1e-5, rng=net.explicit_rng([d.float().to(DEV) for d in dWs], eps.float().to(DEV)))
+    _close(loss, loss_r, 1e-4, 1e-6, "loss")
+    loss.backward()
+    for i, (p, gr) in enumerate(zip(net.oracle_ordered_parameters(), grads_r)):
+        _gclose(p.grad, gr, 2e-3, f"param {i} grad")
+    with pytest.raises(AssertionError, match="same input and output shapes"):
+        SDEBNNClassifier(nsamples=1, device=DEV, input_size=(28, 28, 1), aug=2, nblocks=(2, 2, 2), fx_dim=8, fw_dims=(2, 8, 2), nsteps=4)

@@ -243,3 +243,45 @@ def test_gpu_nchw_reinterp_roundtrip(built_lib):
     back = torch.empty(B, 4, 4, 12, device=DEV)
     tm.reinterp_axpy(back, chw2, None, 1.0, nhwc(y), chw)
     assert torch.equal(back.permute(0, 3, 1, 2), y.reshape(B, *chw2))
+
+
+@pytest.mark.gpu
+def test_gpu_config5_full_size_properties(built_lib):
+    """Config 5 at full size (3x32x32, blocks 2-2-2, hidden 32, P = 196 296, w-net 1-128-1, midpoint dt 0.05) through properties
+    that do not need the oracle at that size: determinism of the Philox path, tensor-core vs fp32 conv agreement (TF32 tolerance),
+    remat == stored activations bit for bit, batch independence (images [0:B/2] of a B solve equal a B/2 solve on them), and the
+    w / logqp rows do not depend on y."""
+    from bayesde_b200 import torch_models as tm
+    torch.manual_seed(0)
+    B = 16
+    m = tm.SDENet(input_size=(3, 32, 32), blocks=(2, 2, 2), weight_network_sizes=(1, 128, 1), hidden_width=32, sigma=0.1, math="tc").to(DEV)
+    assert m.params_size == 196296
+    with torch.no_grad():
+        last = m.w_net.linears()[-1]
+        last.weight.normal_(0, 1e-2), last.bias.normal_(0, 1e-2)
+    x = torch.randn(B, 3, 32, 32, device=DEV)
+
+    def run(xx, math_mode="tc", remat=False):
+        m.math, m.remat, m._calls = math_mode, remat, 0
+        m.zero_grad()
+        logits, logqp = m(xx, dt=0.05, method="midpoint")
+        (logits.square().mean() + 1e-6 * logqp).backward()
+        return logits.detach(), logqp.detach(), m.flat_initial_params.grad.clone(), m.w_net.linears()[0].weight.grad.clone()
+
+    a = run(x)
+    b = run(x)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v), "not deterministic"
+    assert all(torch.isfinite(t).all() for t in a) and m.nfe == 80
+    r = run(x, remat=True)
+    for u, v in zip(a, r):
+        assert torch.equal(u, v), "remat differs from stored activations"
+    f = run(x, math_mode="fp32")
+    _close(a[0], f[0], 5e-3, "logits tc vs fp32")
+    assert torch.equal(a[1], f[1])                      # the [w, logqp] rows never touch the convs
+    _close(a[2], f[2], 3e-2, "dL/dw0 tc vs fp32")
+    h = run(x[:B // 2].contiguous())
+    # the projection head is a cuBLAS GEMM whose reduction order depends on the batch: allclose, not equal
+    assert torch.allclose(h[0], a[0][:B // 2], rtol=1e-5, atol=1e-6) and torch.equal(h[1], a[1])
+    z = run(torch.zeros_like(x))
+    assert torch.equal(z[1], a[1])
