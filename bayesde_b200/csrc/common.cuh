@@ -105,6 +105,21 @@ struct WreduceArgs {
 };
 int launch_wgrad_reduce(const WreduceArgs& a, int blocks, cudaStream_t st);
 
+// Launch with programmatic dependent launch allowed: the kernel may be scheduled while its stream predecessor drains (after the
+// predecessor's griddepcontrol.launch_dependents) and MUST execute griddepcontrol.wait before touching global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const int pdl = getenv("BSDE_PDL") ? atoi(getenv("BSDE_PDL")) : 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, fn, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

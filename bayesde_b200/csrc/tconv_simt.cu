@@ -367,6 +367,9 @@ __global__ void colsum_partial_kernel(const float* __restrict__ dy, float* __res
 
 
 __global__ void wgrad_reduce_kernel(WreduceArgs a) {
+  // launched with programmatic dependent launch from the tensor-core weight-gradient paths: wait for the partial tiles
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const long long per = (long long)a.rows * a.cols;
   const long long total = per * a.S;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -412,7 +415,7 @@ __global__ void wgrad_reduce_kernel(WreduceArgs a) {
 }
 
 int launch_wgrad_reduce(const WreduceArgs& a, int blocks, cudaStream_t st) {
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(a);
+  BSDE_CUDA_OK(launch_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, a));
   BSDE_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -286,6 +286,9 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (smem zeroing, barriers, TMEM) overlapped the predecessor's tail
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp < WW_PROD_WARPS) {
     // =============================== producers ===============================
@@ -715,7 +718,7 @@ int tconv_wgrad_win(const bsde_conv_layer* L, int S, int B, const float* in, con
     if (a.tmaU) { if (int e = make(&tmU, a.U, a.cu, a.wU, a.hU, a.NPU)) return e; }
     if (a.tmaV) { if (int e = make(&tmV, a.V, a.cv, a.wV, a.hV, a.NPV)) return e; }
   }
-  wgrad_win_kernel<<<S * a.TG * a.SPL, WW_THREADS, p.smem, st>>>(a, tmU, tmV);
+  BSDE_CUDA_OK(launch_pdl(wgrad_win_kernel, dim3(S * a.TG * a.SPL), dim3(WW_THREADS), p.smem, st, a, tmU, tmV));
   BSDE_CUDA_OK(cudaGetLastError());
   count_launch();
 
