@@ -130,6 +130,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(WgTcArgs a) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: the prologue above overlapped the predecessor's tail
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < WG_PROD / 32) {
     // =============================== producers ===============================
@@ -334,6 +337,8 @@ __global__ void __launch_bounds__(1024) tap_colsum_kernel(TapSumArgs a) {
     }
     if (isrow) s_rowmask[o] = mk; else s_colmask[o] = mk;
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched with programmatic dependent launch
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __syncthreads();
   const unsigned fullmask = (1u << a.ksize) - 1u;
   const int ngrp = (a.cout + VW - 1) / VW;      // column groups
@@ -516,7 +521,7 @@ int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, cons
     BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
-#define WG_LAUNCH(VA_, VB_) wgrad_tc_kernel<VA_, VB_><<<S * p.splits, WG_THREADS, p.smem, st>>>(a)
+#define WG_LAUNCH(VA_, VB_) BSDE_CUDA_OK(launch_pdl(wgrad_tc_kernel<VA_, VB_>, dim3(S * p.splits), dim3(WG_THREADS), p.smem, st, a))
   if (va && vb) WG_LAUNCH(true, true);
   else if (va) WG_LAUNCH(true, false);
   else if (vb) WG_LAUNCH(false, true);
@@ -534,8 +539,8 @@ int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, cons
   ta.rows = p.rows; ta.cols = p.cols; ta.swapped = p.swapped; ta.has_time = L->has_time; ta.Kc = Kc; ta.Ktot = Ktot;
   ta.cin = L->cin; ta.t = t;
   if (!(wg_dbg & 1))
-  if (L->cout % 4 == 0) tap_colsum_kernel<4><<<dim3(p.splits, S), 1024, 0, st>>>(ta);
-  else tap_colsum_kernel<1><<<dim3(p.splits, S), 1024, 0, st>>>(ta);
+  if (L->cout % 4 == 0) BSDE_CUDA_OK(launch_pdl(tap_colsum_kernel<4>, dim3(p.splits, S), dim3(1024), 0, st, ta));
+  else BSDE_CUDA_OK(launch_pdl(tap_colsum_kernel<1>, dim3(p.splits, S), dim3(1024), 0, st, ta));
   BSDE_CUDA_OK(cudaGetLastError());
   count_launch();
 
