@@ -354,10 +354,11 @@ def run_ours(args):
                      "peak_source": ("measured live in this run: cuBLAS 8192^3 TF32 matmul (the kernels issue tcgen05 kind::tf32; "
                                      "MEASURED_PEAKS.json holds no TF32 figure, SURVEY 8.4)" if tf32_peak else peak_src),
                      "peak_bf16_sustained": peak_tf, "frac_of_bf16_peak": achieved / peak_tf,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one conv_win_kernel launch (64->5 data gradient,
-                     # 1024 images 32x32), ncu --set full capture summarised in profiles/r01_summary.md: equals the
-                     # algorithmic bytes (input read once 268.8 MB + output 19.0 MB)
-                     "traffic": 287.8e6,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel with the largest share of the
+                     # step (wgrad_win_kernel, 29 %: 5->64 weight gradient, 1024 images 32x32), ncu --set full capture
+                     # profiles/r01j_wgrad_win_full_summary.csv: 289.8 MB read + 3.9 MB written = the algorithmic bytes
+                     # (dY 268.4 MB + input 21.0 MB read once, partial tiles 3.5 MB)
+                     "traffic": 293.7e6,
                      "algorithmic_flops_per_step": alg_flops_step, "kernel_ms_per_step": conv_ms,
                      "share_of_step": conv_ms / (ms / args.steps)},
         # the same conv launches against HBM: with fp32 NHWC activations and one launch per layer the byte floor
