@@ -585,6 +585,74 @@ __global__ void philox_increments_kernel(uint64_t seed, uint32_t stream_id, int 
 }
 }  // namespace bsde
 
+// ---------------------------------------------------------------------------------------------
+// Virtual Brownian tree (jaxsde/jaxsde/brownian.py:19-95) and the product-form step of the stochastic adjoint
+// (jaxsde/jaxsde/sdeint.py:36-50 with g_prod / gdg_prod given as vectors, sde_vjp.py:13-47)
+// ---------------------------------------------------------------------------------------------
+namespace bsde {
+__global__ void brownian_tree_kernel(uint64_t seed, uint32_t stream_id, long long n, int rep, int depth, float t0, float t1,
+                                     float t, float* __restrict__ out) {
+  const float span = t1 - t0;
+  const float s = (t - t0) / span;  // scaled_brownian_motion, brownian.py:12-17
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    // sample_with_rep (brownian.py:69-74): the last `rep` entries reuse the normals of the `rep` entries before them
+    const uint32_t e = (uint32_t)((rep > 0 && i >= n - rep) ? i - rep : i);
+    float tl = 0.f, xl = 0.f, tr = 1.f;
+    float xr = philox_normal(seed, e, 0u, 0u, stream_id);  // B(1): make_standard_brownian_motion, brownian.py:77-88
+    uint32_t node = 1u;                                     // heap index <-> the left / right key of random.split
+    for (int lvl = 0; lvl < depth; ++lvl) {                 // virtual_brownian_tree, brownian.py:26-51
+      const float tm = (tl + tr) * 0.5f;
+      const float z = philox_normal(seed, e, node, 1u, stream_id);
+      const float xm = (xl * (tr - tm) + xr * (tm - tl)) / (tr - tl) + sqrtf((tr - tm) * (tm - tl) / (tr - tl)) * z;  // :19-23
+      if (s < tm) { tr = tm; xr = xm; node = 2u * node; }
+      else { tl = tm; xl = xm; node = 2u * node + 1u; }
+    }
+    const float z = philox_normal(seed, e, node, 1u, stream_id);
+    const float mean = (xl * (tr - s) + xr * (s - tl)) / (tr - tl);
+    const float sd = sqrtf(fmaxf((tr - s) * (s - tl), 0.f) / (tr - tl));
+    out[i] = sqrtf(span) * (mean + sd * z);
+  }
+}
+
+__global__ void step_update_prod_kernel(long long n, float dt, const float* __restrict__ y, const float* __restrict__ f,
+                                        const float* __restrict__ gp, const float* __restrict__ mp, float* __restrict__ y1) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = y[i] + dt * f[i] + gp[i];
+    if (mp) v += 0.5f * mp[i];
+    y1[i] = v;
+  }
+}
+}  // namespace bsde
+
+extern "C" int bsde_brownian_tree(uint64_t seed, uint32_t stream_id, int64_t n, int32_t rep, int32_t depth, float t0, float t1,
+                                  float t, float* d_out, void* stream) {
+  BSDE_CHECK_ARG(n >= 0 && rep >= 0 && 2 * (int64_t)rep <= n, "need 0 <= 2*rep <= n (n=%lld, rep=%d)", (long long)n, rep);
+  BSDE_CHECK_ARG(depth >= 0 && depth <= 30, "depth must be in [0, 30], got %d", depth);
+  BSDE_CHECK_ARG(t1 > t0, "need t1 > t0");
+  BSDE_CHECK_ARG(n < (1LL << 32), "n must be < 2^32");
+  if (n == 0) return 0;
+  BSDE_CHECK_ARG(d_out != nullptr, "NULL tensor pointer");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  brownian_tree_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(seed, stream_id, n, rep, depth, t0, t1, t, d_out);
+  count_launch();
+  BSDE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bsde_step_update_prod(int64_t n, float dt, const float* d_y, const float* d_f, const float* d_gprod,
+                                     const float* d_gdgprod, float* d_y1, void* stream) {
+  BSDE_CHECK_ARG(n >= 0, "n must be >= 0");
+  if (n == 0) return 0;
+  BSDE_CHECK_ARG(d_y && d_f && d_gprod && d_y1, "NULL tensor pointer");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  step_update_prod_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n, dt, d_y, d_f, d_gprod, d_gdgprod, d_y1);
+  count_launch();
+  BSDE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int bsde_step_update(int32_t method, int64_t n, float dt, const float* d_y, const float* d_f,
                                 const float* d_g, const float* d_dW, const float* d_gdg, const float* d_g2,
                                 float* d_y1, void* stream) {

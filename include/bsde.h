@@ -31,6 +31,8 @@
  *   bsde_chain_fwd/bwd       one evaluation of SDENet's y_net drift (all groups + ConvDownsample) and its reverse:
  *                            torchbnn/_impl/models.py:25-54,159-169, torchbnn/_impl/diffeq_layers.py:40-62,75-166,230-311
  *   bsde_nchw_reinterp_axpy  the flat-state update y + a * fy.reshape(-1) of the torch front end: models.py:163,168
+ *   bsde_brownian_tree       a queryable Brownian path for sdeint_ito (stochastic adjoint): jaxsde/jaxsde/brownian.py:19-95
+ *   bsde_step_update_prod    the product-form step of the adjoint system: jaxsde/jaxsde/sde_vjp.py:13-47, sdeint.py:36-50
  *   bsde_philox_increments   replaces make_brownian_motion / virtual_brownian_tree queries
  *                            bm(next_t)-bm(curr_t): jaxsde/jaxsde/brownian.py:26-95, sdeint.py:108
  */
@@ -274,6 +276,21 @@ int bsde_step_update(int32_t method, int64_t n, float dt, const float* d_y, cons
  * (p, k, s, stream_id): the stream bsde_wsde_fwd consumes when d_dW == NULL. */
 int bsde_philox_increments(uint64_t seed, uint32_t stream_id, int32_t S, int32_t nit, int64_t P,
                            const float* d_dtk, float* d_out, void* stream);
+
+/* Virtual Brownian tree (jaxsde/jaxsde/brownian.py:19-95, make_brownian_motion :92-95): W(t) on [t0, t1] for n state entries,
+ * O(1) memory, queryable at any t in any order.  Standard motion B on [0, 1] with B(1) ~ N(0, 1); `depth` bisection levels,
+ * every midpoint a Brownian-bridge draw (:19-23); a final bridge point at s = (t - t0)/(t1 - t0) inside the leaf;
+ * W(t) = sqrt(t1 - t0) * B(s).  The normals come from Philox4x32-10 keyed (seed) with counter (element, heap index of the tree
+ * node, ., stream_id) in place of threefry key splitting (NOT bit-compatible with a JAX run); `rep` ties the last rep entries
+ * to the rep entries before them (sample_with_rep, :69-74). */
+int bsde_brownian_tree(uint64_t seed, uint32_t stream_id, int64_t n, int32_t rep, int32_t depth, float t0, float t1, float t,
+                       float* d_out, void* stream);
+
+/* y1 = y + dt*f + gprod [+ 0.5*gdgprod]: ito_euler_step / ito_milstein_step (jaxsde/jaxsde/sdeint.py:36-50) when the
+ * diffusion enters as the products g_prod(y,t,args,dW) and gdg_prod(y,t,args,dW^2 - dt) -- the form the augmented adjoint
+ * system of sdeint_ito's reverse pass takes (jaxsde/jaxsde/sde_vjp.py:13-47,137-199). */
+int bsde_step_update_prod(int64_t n, float dt, const float* d_y, const float* d_f, const float* d_gprod,
+                          const float* d_gdgprod, float* d_y1, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * config 2 (torch toy): em_solver + VariationalSDE of examples/torch/sdebnn_toy1d.py:19-60
