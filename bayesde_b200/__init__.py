@@ -2,6 +2,7 @@
 
 Public surface (same names / call shapes as the reference):
     sdeint_ito_fixed_grid(f, g, y0, ts, rng, args=(), dt=1e-6, method='milstein', rep=0)
+    sdeint_ito(f, g, y0, ts, rng, args=(), dt=1e-6, method='milstein', rep=0)   (stochastic adjoint, Philox Brownian tree)
     brax.SDEBNN(...), brax.MeanField, brax.bnn_serial, arch.MLP, arch.build_fx, arch.Augment, ...
     brax_utils.sdeint / _sdeint          (JAX toy solver, brax/utils/sdeint.py)
     torch_toy.em_solver / VariationalSDE (torch toy, examples/torch/sdebnn_toy1d.py)
@@ -11,6 +12,6 @@ All arithmetic on the hot path runs in libbsde.so (hand-written CUDA, C ABI in i
 there is no CPU / eager fallback.
 """
 from . import arch, brax, brax_utils, evaluation, torch_models, torch_toy  # noqa: F401
-from .sdeint import sdeint_ito_fixed_grid  # noqa: F401
+from .sdeint import sdeint_ito_fixed_grid, sdeint_ito, make_brownian_motion  # noqa: F401
 
-__all__ = ["sdeint_ito_fixed_grid", "arch", "brax", "brax_utils", "torch_toy", "torch_models", "evaluation"]
+__all__ = ["sdeint_ito_fixed_grid", "sdeint_ito", "make_brownian_motion", "arch", "brax", "brax_utils", "torch_toy", "torch_models", "evaluation"]

@@ -1,0 +1,367 @@
+"""Row N1: `sdeint_ito` with the stochastic-adjoint reverse pass and the Philox virtual Brownian tree.
+
+The reference's own tests for this path (jaxsde/tests/test_vjp.py, test_brownian.py, test_sdeint.py) need JAX 0.1.77 and hold no
+stored vectors, so parity here is "unpinned"; the tests below are the analogues of those property tests:
+  * CPU: Brownian-tree laws (test_brownian.py:17-47), adjoint gradient vs. differentiation through the solve as dt -> 0 and the
+    reconstructed y0 (test_vjp.py:88-114, same SDE, same tolerances 1e-2), explicit sigma / Milstein term of the augmented system
+    (test_vjp.py:49-74), closed-form geometric Brownian motion, the host-side assembly of bayesde_b200.sdeint._SdeintIto with the two
+    device launches replaced by their oracle restatements (fp64, 1e-9);
+  * GPU: bsde_brownian_tree / bsde_step_update_prod through the C ABI against the oracle (1e-5 / bit-exact), sdeint_ito values
+    (1e-4) and gradients (2e-3 of max) against the oracle on the same tree.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import jax_adjoint as ja
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the SDE of jaxsde/tests/test_vjp.py:16-30 on torch tensors
+# --------------------------------------------------------------------------------------------------------------
+def make_sde(dtype=torch.float64, device="cpu"):
+    D = 3
+    ts = [0.1, 0.5]
+    y0 = torch.linspace(0.1, 0.9, D, dtype=dtype, device=device)
+    args = (torch.linspace(0.1, 0.2, 2, dtype=dtype, device=device), torch.linspace(0.8, 0.9, 3, dtype=dtype, device=device))
+
+    def f(y, t, args):
+        f_args, g_args = args
+        t = torch.as_tensor(t, dtype=y.dtype, device=y.device)
+        return -torch.sqrt(t) - y + 0.1 - f_args[0] * torch.mean((y + 0.2) ** 2) + f_args[1]
+
+    def g(y, t, args):
+        f_args, g_args = args
+        t = torch.as_tensor(t, dtype=y.dtype, device=y.device)
+        return g_args[0] * (y ** 2 + torch.sin(0.1 * y)) + g_args[1] * torch.cos(t) + g_args[2]
+
+    return D, ts, y0, args, f, g
+
+
+def _unravel2(fa):
+    return (fa[:2], fa[2:])
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU: the oracle itself
+# --------------------------------------------------------------------------------------------------------------
+def test_tree_end_points_and_determinism():
+    bm = ja.BrownianTree(seed=3, stream_id=1, n=64, t0=0.25, t1=2.0)
+    assert float(bm(0.25).abs().max()) == 0.0
+    w1 = bm(2.0)
+    z = ja.philox_normal(3, np.arange(64), 0, 0, 1)
+    assert torch.allclose(w1, torch.from_numpy(z).double() * math.sqrt(1.75), rtol=1e-6, atol=1e-6)
+    assert torch.equal(bm(1.3), bm(1.3))                      # queryable in any order, O(1) memory
+    a = bm(0.7)
+    bm(1.9)
+    assert torch.equal(a, bm(0.7))
+
+
+def test_tree_rep_ties_the_tail():
+    n, rep = 40, 12
+    bm = ja.BrownianTree(seed=5, stream_id=0, n=n, t0=0.0, t1=1.0, rep=rep)
+    w = bm(0.61)
+    assert torch.equal(w[n - rep:], w[n - 2 * rep:n - rep])   # sample_with_rep, brownian.py:69-74
+    assert not torch.equal(w[:rep], w[n - rep:])
+
+
+def test_tree_mean_and_var():
+    """test_brownian.py:17-47 with the samples taken across elements (every element has its own Philox counter)."""
+    n, t1 = 20000, 3.0
+    bm = ja.BrownianTree(seed=11, stream_id=0, n=n, t0=0.0, t1=t1)
+    for t in (t1, t1 / 2.0, 0.3):
+        v = bm(t).numpy()
+        assert abs(v.mean()) < 0.05 and abs(v.var() - t) < 0.05 * max(t, 1.0), (t, v.mean(), v.var())
+
+
+def test_tree_increments_are_independent_and_gaussian():
+    n = 40000
+    bm = ja.BrownianTree(seed=2, stream_id=7, n=n, t0=0.0, t1=1.0)
+    a, b, c = bm(0.2).numpy(), bm(0.55).numpy(), bm(0.9).numpy()
+    d1, d2 = b - a, c - b
+    assert abs(d1.var() - 0.35) < 0.01 and abs(d2.var() - 0.35) < 0.01
+    assert abs(np.mean(d1 * d2)) < 0.01 and abs(np.mean(a * d1)) < 0.01
+    assert abs(np.mean(d1 ** 4) / d1.var() ** 2 - 3.0) < 0.15                                  # Gaussian kurtosis
+    # different streams / seeds give unrelated paths
+    other = ja.BrownianTree(seed=2, stream_id=8, n=n, t0=0.0, t1=1.0)(0.55).numpy()
+    assert abs(np.mean(other * b)) < 0.01
+
+
+def test_gbm_closed_form():
+    """dy = a y dt + b y dW has y_T = y0 exp((a - b^2/2) T + b W_T); Milstein is strongly first order."""
+    a, b = 0.3, 0.5
+    n = 16
+    bm = ja.BrownianTree(seed=9, stream_id=0, n=n, t0=0.0, t1=1.0, depth=12)
+    y0 = torch.linspace(0.5, 1.5, n, dtype=torch.float64)
+    f = lambda y, t, args: a * y
+    g = lambda y, t, args: b * y
+    exact = y0 * torch.exp((a - 0.5 * b * b) * 1.0 + b * bm(1.0))
+    errs = []
+    for dt in (1.0 / 64, 1.0 / 256):
+        ys = ja.ito_integrate(f, g, y0, [0.0, 1.0], bm, dt, method="milstein")
+        errs.append(float((ys[-1] - exact).abs().max()))
+    assert errs[1] < 0.02 and errs[1] < 0.45 * errs[0], errs
+
+
+def test_oracle_unknown_method():
+    D, ts, y0, args, f, g = make_sde()
+    bm = ja.BrownianTree(0, 0, D, ts[0], ts[-1])
+    with pytest.raises(ValueError, match="Unknown method"):
+        ja.ito_integrate(f, g, y0, ts, bm, 1e-2, args, method="heun")
+
+
+def test_oracle_adjoint_explicit_sigma_and_milstein():
+    """test_vjp.py:49-74: the products aug_g_prod / aug_gdg of the augmented system equal the explicit diffusion matrix
+    sigma_ij and its Milstein term m_ij = sum_l dsigma_ij/dy_l sigma_lj (sde_vjp.py:49-88,124-134), built here by autograd."""
+    D, ts, y0, args, f, g = make_sde()
+    fa = torch.cat(args)
+    A = fa.numel()
+    flat_g = lambda y, t, a: g(y, t, _unravel2(a))
+    aug = torch.cat([y0, y0, torch.zeros(A, dtype=y0.dtype)])
+    t = ts[0]
+
+    def sigma(aug_):          # (2D + A) x D, column j = response to noise channel j
+        y, adj = aug_[:D], aug_[D:2 * D]
+        gy = flat_g(y, t, fa_leaf)
+        cols = []
+        for j in range(D):
+            e = torch.zeros(D, dtype=y.dtype)
+            e[j] = 1.0
+            va, vargs = torch.autograd.grad(gy, (y_leaf, fa_leaf), -adj * e, retain_graph=True, create_graph=True)
+            cols.append(torch.cat([gy * e, va, vargs]))
+        return torch.stack(cols, dim=1)
+
+    # explicit matrices by autograd on leaves
+    y_leaf = y0.clone().requires_grad_(True)
+    fa_leaf = fa.clone().requires_grad_(True)
+    aug_leaf = torch.cat([y_leaf, y0, torch.zeros(A, dtype=y0.dtype)])
+    sig = sigma(aug_leaf)
+    # Milstein term: m_ij = sum_l dsigma_ij/daug_l sigma_lj; only the y-rows of aug carry noise and sigma depends on
+    # aug through y (leaf) and linearly through adj
+    adj_leaf = y0.clone().requires_grad_(True)
+
+    def sigma_full(yv, adjv):
+        gy = flat_g(yv, t, fa_leaf)
+        cols = []
+        for j in range(D):
+            e = torch.zeros(D, dtype=yv.dtype)
+            e[j] = 1.0
+            va, vargs = torch.autograd.grad(gy, (yv, fa_leaf), -adjv * e, retain_graph=True, create_graph=True)
+            cols.append(torch.cat([gy * e, va, vargs]))
+        return torch.stack(cols, dim=1)
+
+    jac_y, jac_adj = torch.autograd.functional.jacobian(sigma_full, (y0.clone(), y0.clone()), create_graph=False)
+    sig_val = sigma_full(y_leaf, adj_leaf).detach()
+    n_aug = 2 * D + A
+    m = torch.zeros(n_aug, D, dtype=y0.dtype)
+    for j in range(D):
+        m[:, j] = jac_y[:, j, :] @ sig_val[:D, j] + jac_adj[:, j, :] @ sig_val[D:2 * D, j]
+
+    # implicit products from the oracle's adjoint dynamics, probed with unit vectors (they are linear in v)
+    captured = {}
+    orig = ja.ito_integrate
+
+    def grab(aug_f, g_, aug0, rts, rb, dt, flat_args, gdg=None, g_prod=None, method="milstein"):
+        captured.update(f=aug_f, gp=g_prod, gdg=gdg)
+        return aug0[None]
+    ja.ito_integrate = grab
+    try:
+        # the reflected system evaluates g at -t: reflect the probe time so that rg(y, -t) = g(y, t)
+        ja.stochastic_adjoint(f, g, y0, y0, ts, lambda tt: torch.zeros(D, dtype=y0.dtype), 1e-2, fa, _unravel2)
+    finally:
+        ja.ito_integrate = orig
+    for j in range(D):
+        e = torch.zeros(D, dtype=y0.dtype)
+        e[j] = 1.0
+        gp = captured["gp"](aug, -t, fa, e)
+        mm = captured["gdg"](aug, -t, fa, e)
+        assert torch.allclose(gp, sig_val[:, j], rtol=1e-10, atol=1e-12), j
+        assert torch.allclose(mm, m[:, j], rtol=1e-9, atol=1e-11), (j, mm, m[:, j])
+
+
+@pytest.mark.parametrize("method", ["milstein", "euler_maruyama"])
+def test_oracle_adjoint_matches_backprop_through_the_solve(method):
+    """test_vjp.py:88-114: same SDE, dt = 1e-3 here (1e-4 there, with rtol = atol = 1e-2)."""
+    D, ts, y0, args, f, g = make_sde()
+    bm = ja.BrownianTree(seed=0, stream_id=0, n=D, t0=ts[0], t1=ts[-1], depth=12)
+    dt = 1e-3
+    y0_ = y0.clone().requires_grad_(True)
+    fa = torch.cat(args).requires_grad_(True)
+    ys = ja.ito_integrate(f, g, y0_, ts, bm, dt, _unravel2(fa), method=method)
+    gy, ga = torch.autograd.grad(ys[-1].sum(), (y0_, fa))
+    y0_rec, y_adj, a_adj = ja.stochastic_adjoint(f, g, ys[-1].detach(), torch.ones(D, dtype=y0.dtype), ts, bm, dt, fa.detach(),
+                                                 _unravel2, method=method)
+    # Milstein is strongly first order (measured 0.038 / 0.013 / 0.0024 at dt = 4e-3 / 1e-3 / 2.5e-4 for y0_rec), Euler-Maruyama
+    # of order 1/2 (0.31 / 0.12 / 0.06): the reference's 1e-2 holds for its dt = 1e-4 Milstein case; bounds scaled to dt = 1e-3
+    tol_y, tol_g = (2e-2, 1e-2) if method == "milstein" else (0.2, 0.2)
+    assert torch.allclose(y0_rec, y0, rtol=tol_y, atol=tol_y)
+    assert torch.allclose(y_adj, gy, rtol=tol_g, atol=tol_g), (y_adj, gy)
+    assert torch.allclose(a_adj, ga, rtol=tol_g, atol=tol_g), (a_adj, ga)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU: host-side assembly of the product (bayesde_b200.sdeint._SdeintIto) with the two launches restated by the oracle
+# --------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def cpu_launches(monkeypatch):
+    """Replaces the two device launches (bsde_brownian_tree, bsde_step_update_prod) and the CUDA-only guard by their oracle
+    restatements so that the Python assembly of the adjoint system can be compared with the oracle on the CPU.  Test-only."""
+    from bayesde_b200 import sdeint as sd
+
+    def tree_call(self, t):
+        return ja.BrownianTree(self.seed, self.sid, self.n, self.t0, self.t1, self.depth, self.rep, dtype=torch.float64)(t)
+
+    def prod_step(dt, y, fy, gp, mp):
+        out = y + float(dt) * fy + gp
+        return out if mp is None else out + 0.5 * mp
+
+    monkeypatch.setattr(sd.BrownianTree, "__call__", tree_call)
+    monkeypatch.setattr(sd, "_prod_step", prod_step)
+    monkeypatch.setattr(sd, "_require_cuda", lambda y0: None)
+    monkeypatch.setattr(sd, "_state_dtype", torch.float64)
+    return sd
+
+
+@pytest.mark.parametrize("method", ["milstein", "euler_maruyama"])
+@pytest.mark.parametrize("rep", [0, 1])
+def test_host_assembly_matches_oracle(cpu_launches, method, rep):
+    sd = cpu_launches
+    D, ts, y0, args, f, g = make_sde()
+    dt = 0.01
+    y0_ = y0.clone().requires_grad_(True)
+    args_ = tuple(a.clone().requires_grad_(True) for a in args)
+    ys = sd.sdeint_ito(f, g, y0_, ts, (4, 2), args_, dt=dt, method=method, rep=rep)
+    cot = torch.linspace(-1.0, 2.0, D, dtype=y0.dtype)
+    (ys[-1] * cot).sum().backward()
+
+    bm = ja.BrownianTree(4, 2, D, ts[0], ts[-1], depth=10, rep=rep)
+    ref = ja.ito_integrate(f, g, y0, ts, bm, dt, args, method=method)
+    assert torch.allclose(ys.detach(), ref, rtol=1e-12, atol=1e-12)
+    fa = torch.cat(args)
+    _, y_adj, a_adj = ja.stochastic_adjoint(f, g, ref[-1], cot, ts, bm, dt, fa, _unravel2, method=method)
+    assert torch.allclose(y0_.grad, y_adj, rtol=1e-9, atol=1e-11), (y0_.grad, y_adj)
+    assert torch.allclose(torch.cat([a.grad for a in args_]), a_adj, rtol=1e-9, atol=1e-11)
+
+
+def test_host_intermediate_outputs_and_zero_ts_grad(cpu_launches):
+    """Three output times (interior targets may be overshot, sdeint.py:114-128); only the last row's cotangent is used (sde_vjp.py:186)."""
+    sd = cpu_launches
+    D, _, y0, args, f, g = make_sde()
+    ts = [0.1, 0.33, 0.5]
+    y0_ = y0.clone().requires_grad_(True)
+    ys = sd.sdeint_ito(f, g, y0_, ts, 3, args, dt=0.01, method="milstein")
+    bm = ja.BrownianTree(3, 0, D, ts[0], ts[-1])
+    ref = ja.ito_integrate(f, g, y0, ts, bm, 0.01, args, method="milstein")
+    assert ys.shape == (3, D) and torch.allclose(ys.detach(), ref, rtol=1e-12, atol=1e-12)
+    g_all = torch.autograd.grad(ys.sum(), y0_, retain_graph=True)[0]
+    g_last = torch.autograd.grad(ys[-1].sum(), y0_)[0]
+    assert torch.isfinite(g_last).all() and torch.equal(g_all, g_last)
+
+
+def test_host_errors():
+    from bayesde_b200 import sdeint as sd
+    from bayesde_b200 import _lib
+    D, ts, y0, args, f, g = make_sde(torch.float32)
+    with pytest.raises(ValueError, match="Unknown method"):
+        sd.sdeint_ito(f, g, y0, ts, 0, args, method="euler_heun")
+    with pytest.raises(_lib.BsdeError):
+        sd.sdeint_ito(f, g, y0, ts, 0, args)                  # CPU tensors: no fallback
+    with pytest.raises(ValueError):
+        sd.BrownianTree(0.0, 4, 1.0, torch.zeros(3, 4))       # a tree cannot be built from supplied increments
+
+
+# --------------------------------------------------------------------------------------------------------------
+# GPU: through the C ABI / the public API
+# --------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,rep,depth", [(1, 0, 10), (1000, 0, 10), (4099, 1024, 10), (300, 150, 0), (257, 0, 17)])
+def test_gpu_brownian_tree_matches_oracle(built_lib, n, rep, depth):
+    from bayesde_b200.sdeint import BrownianTree
+    t0, t1 = -0.5, 1.25
+    dev = BrownianTree(t0, n, t1, (123456789012345, 3), depth=depth, rep=rep, device="cuda:0")
+    ref = ja.BrownianTree(123456789012345, 3, n, t0, t1, depth=depth, rep=rep, dtype=torch.float32)
+    for t in (t0, t1, 0.0, 0.3333, 1.2499, -0.4999, 0.375):
+        a, b = dev(t).cpu(), ref(t)
+        assert float((a - b).abs().max()) <= 1e-5, (t, float((a - b).abs().max()))
+    assert float(dev(t0).abs().max()) == 0.0
+    assert torch.equal(dev(0.77), dev(0.77))
+
+
+@pytest.mark.gpu
+def test_gpu_brownian_tree_full_size_laws(built_lib):
+    """Config-4 sized state (D = 655 360 + 2 * 81 458, rep = P): laws instead of an element-wise oracle."""
+    from bayesde_b200.sdeint import BrownianTree
+    P, X = 81458, 655360
+    n = X + 2 * P
+    bm = BrownianTree(0.0, n, 1.0, 1, rep=P, device="cuda:0")
+    a, b = bm(0.25), bm(0.75)
+    d = b - a
+    assert torch.equal(b[n - P:], b[n - 2 * P:n - P])
+    assert abs(float(d[:n - P].var()) - 0.5) < 5e-3 and abs(float(d[:n - P].mean())) < 5e-3
+    assert abs(float((a[:n - P] * d[:n - P]).mean())) < 5e-3
+    assert abs(float(bm(1.0)[:n - P].var()) - 1.0) < 1e-2
+
+
+@pytest.mark.gpu
+def test_gpu_step_update_prod_exact(built_lib):
+    from bayesde_b200 import sdeint as sd
+    gen = torch.Generator().manual_seed(0)
+    for n in (1, 255, 100003):
+        y, f, gp, mp = (torch.randn(n, generator=gen) for _ in range(4))
+        dt = np.float32(0.0137)
+        for m in (None, mp):
+            out = sd._prod_step(dt, y.cuda(), f.cuda(), gp.cuda(), None if m is None else m.cuda()).cpu().numpy()
+            ref = y.numpy() + dt * f.numpy() + gp.numpy()            # same order in fp32; the device contracts to FMAs
+            if m is not None:
+                ref = ref + np.float32(0.5) * m.numpy()
+            assert np.allclose(out, ref, rtol=3e-7, atol=2e-6)        # atol: cancellation between terms of size ~4
+    with pytest.raises(Exception):
+        sd._prod_step(0.1, torch.zeros(3), torch.zeros(3), torch.zeros(3), None)   # CPU tensors are refused
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["milstein", "euler_maruyama"])
+def test_gpu_sdeint_ito_matches_oracle(built_lib, method):
+    """Values 1e-4, adjoint gradients 2e-3 of the largest entry, against the fp64 oracle on the same Philox tree."""
+    import bayesde_b200 as bs
+    D, ts, y0, args, f, g = make_sde(torch.float32, "cuda:0")
+    dt = 0.01
+    y0_ = y0.clone().requires_grad_(True)
+    args_ = tuple(a.clone().requires_grad_(True) for a in args)
+    ys = bs.sdeint_ito(f, g, y0_, ts, (21, 5), args_, dt=dt, method=method)
+    cot = torch.tensor([1.0, -0.5, 2.0], device="cuda:0")
+    (ys[-1] * cot).sum().backward()
+
+    _, _, y0c, argsc, fc, gc = make_sde()
+    bm = ja.BrownianTree(21, 5, D, ts[0], ts[-1])
+    ref = ja.ito_integrate(fc, gc, y0c, ts, bm, dt, argsc, method=method)
+    assert torch.allclose(ys.detach().cpu().double(), ref, rtol=1e-4, atol=1e-4)
+    _, y_adj, a_adj = ja.stochastic_adjoint(fc, gc, ref[-1], cot.cpu().double(), ts, bm, dt, torch.cat(argsc), _unravel2, method=method)
+    got_a = torch.cat([a.grad for a in args_]).cpu().double()
+    assert float((y0_.grad.cpu().double() - y_adj).abs().max()) <= 2e-3 * float(y_adj.abs().max())
+    assert float((got_a - a_adj).abs().max()) <= 2e-3 * float(a_adj.abs().max())
+
+
+@pytest.mark.gpu
+def test_gpu_sdeint_ito_adjoint_vs_backprop_small_dt(built_lib):
+    """test_vjp.py:88-114 on the device: the O(1)-memory adjoint against backprop through sdeint_ito_fixed_grid's generic route
+    is not available on the same tree, so the check is against the fp64 oracle's backprop through the solve (3e-2 at dt = 2e-3:
+    the adjoint and backprop-through-the-solve differ by O(dt) for Milstein -- the oracle's own gap here is 0.016; the reference
+    asserts 1e-2 at dt = 1e-4)."""
+    import bayesde_b200 as bs
+    D, ts, y0, args, f, g = make_sde(torch.float32, "cuda:0")
+    dt = 2e-3
+    y0_ = y0.clone().requires_grad_(True)
+    args_ = tuple(a.clone().requires_grad_(True) for a in args)
+    ys = bs.sdeint_ito(f, g, y0_, ts, 0, args_, dt=dt)
+    ys[-1].sum().backward()
+    _, _, y0c, argsc, fc, gc = make_sde()
+    bm = ja.BrownianTree(0, 0, D, ts[0], ts[-1])
+    y0r = y0c.clone().requires_grad_(True)
+    fa = torch.cat(argsc).requires_grad_(True)
+    ref = ja.ito_integrate(fc, gc, y0r, ts, bm, dt, _unravel2(fa))
+    gy, ga = torch.autograd.grad(ref[-1].sum(), (y0r, fa))
+    assert torch.allclose(y0_.grad.cpu().double(), gy, rtol=3e-2, atol=3e-2)
+    assert torch.allclose(torch.cat([a.grad for a in args_]).cpu().double(), ga, rtol=3e-2, atol=3e-2)
