@@ -74,6 +74,11 @@ class BlockConfig:
         self.x_numel = S * B * fx_spec.H * fx_spec.W * fx_spec.C
         self._dev = {}
 
+    def set_step(self, t, h):
+        """One-iteration grid (t_k, dt_k) = (t, h) for the step-at-a-time callers (the stochastic-adjoint route)."""
+        self.tk, self.dtk = np.asarray([t], dtype=np.float32), np.asarray([h], dtype=np.float32)
+        self._dev = {}
+
     def grid_on(self, device):
         key = str(device)
         if key not in self._dev:
@@ -238,6 +243,112 @@ class SDEBNNSolve(torch.autograd.Function):
                                          ctx.w0_per_sample)
         flat = [t for lay in glayers for t in lay]
         return (None, None, None, None, None, gx0, gw0, *flat)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fixed_grid=False: `sdeint_ito` for SDEBNN dynamics (brax/_impl/brax.py:114-116) -- variable-step forward solve on a
+# queryable Brownian path and the stochastic-adjoint reverse pass (jaxsde/jaxsde/sde_vjp.py:13-47,137-192), O(1) memory
+# ------------------------------------------------------------------------------------------------------------------
+def ito_step_schedule(ts, dt, max_steps=1 << 22):
+    """The steps the `while _t < target_t` loop of `_stochastic_integrate` takes (jaxsde/jaxsde/sdeint.py:114-128), in fp32:
+    `next_t = min(_t + dt, ts[-1])`, so interior output times may be overshot.  Returns (t_k, h_k, t_{k+1}) per step and, for
+    every output time after the first, how many steps have been taken when its row is emitted."""
+    f32 = np.float32
+    ts = [f32(v) for v in ts]
+    dt = f32(dt)
+    if not dt > 0:
+        raise ValueError(f"dt must be > 0, got {dt}")
+    steps, marks, _t = [], [], ts[0]
+    for target in ts[1:]:
+        while _t < target:
+            nxt = min(f32(_t + dt), ts[-1])
+            if not nxt > _t:
+                raise ValueError(f"dt={dt} does not advance t={_t} in fp32")
+            steps.append((_t, f32(nxt - _t), nxt))
+            if len(steps) > max_steps:
+                raise ValueError(f"more than {max_steps} steps of dt={dt} between {ts[0]} and {ts[-1]}")
+            _t = nxt
+        marks.append(len(steps))
+    return steps, marks
+
+
+LAST_RECONSTRUCTION = None
+
+
+class SDEBNNAdjointSolve(torch.autograd.Function):
+    """`sdeint_ito(f_aug, g_aug, [x, w0, 0], ts, rng, fw_params, method="euler_maruyama", rep)` for S samples at once
+    (brax.py:114-116), one step per K1 / K2 call.  g_aug is state-independent (quirk Q2), so Milstein == Euler-Maruyama, the
+    reflected drift of `time_reflect_ito` (sde_utils.py:30-37) is -f(y, -t), and one step of the augmented adjoint system
+    (sde_vjp.py:17-43) at the reconstructed state Y and forward time tau is
+        Y      <- Y - h f(Y, tau) + g (W(tau - h) - W(tau))            K1 / K2 step with dt = -h and the tree's increment
+        a      <- a + h (df/dy)(Y, tau)^T a                             K3 / K1' of that step with dt = +h
+        a_args <- a_args + h (df/dargs)(Y, tau)^T a
+    i.e. the existing single-iteration launches; nothing but the final state is kept from the forward pass.
+
+    forward(x [S,B,H,W,C], w0 [P] or [S,P], *fw tensors) -> (x_T, kl [S], w at the output times [S, len(ts), P])"""
+
+    @staticmethod
+    def forward(ctx, cfg, ts, dt, bm, w_stale, x, w0, *fw_flat):
+        layers = [tuple(t.contiguous() for t in fw_flat[i:i + 5]) for i in range(0, len(fw_flat), 5)]
+        S, P = cfg.S, cfg.P
+        steps, marks = ito_step_schedule(ts, dt)
+        Yx = x.contiguous()
+        Yw = (w0 if w0.dim() == 2 else w0.expand(S, P)).contiguous()
+        kl = torch.zeros(S, device=x.device, dtype=torch.float32)
+        rows, done = [Yw], 0
+        W_t = bm(ts[0]) if steps else None
+        with _Timed("adj_fwd"):
+            for j, upto in enumerate(marks):
+                for (t, h, tn) in steps[done:upto]:
+                    W_n = bm(tn)
+                    cfg.set_step(t, h)
+                    wtraj, _, klk = wsde_forward(cfg, Yw, layers, (W_n - W_t).view(S, 1, P), 0, 0, w_stale)
+                    xs, _ = xpath_forward(cfg, Yx, wtraj, keep_acts=False)
+                    Yx, Yw, W_t = xs[1], wtraj[:, 1].contiguous(), W_n
+                    kl = kl + klk
+                done = upto
+                rows.append(Yw)
+        ctx.cfg, ctx.ts, ctx.dt, ctx.bm, ctx.w_stale, ctx.layers = cfg, ts, dt, bm, w_stale, layers
+        ctx.w0_per_sample = w0.dim() == 2
+        ctx.save_for_backward(Yx, Yw)
+        wout = torch.stack(rows, dim=1)
+        ctx.mark_non_differentiable(wout)
+        return Yx.clone(), kl, wout
+
+    @staticmethod
+    def backward(ctx, gx, gkl, _gw):
+        cfg, layers, bm = ctx.cfg, ctx.layers, ctx.bm
+        Yx, Yw = ctx.saved_tensors
+        S, P = cfg.S, cfg.P
+        dev = Yx.device
+        a_x = (torch.zeros_like(Yx) if gx is None else gx.to(torch.float32)).contiguous()
+        gkl = (torch.zeros(S, device=dev) if gkl is None else gkl.to(torch.float32)).contiguous()
+        a_w = torch.zeros(S, P, device=dev, dtype=torch.float32)
+        gacc = None
+        rts = [-np.float32(v) for v in list(ctx.ts)[::-1]]  # time_reflect_ito, sde_utils.py:37
+        steps, _ = ito_step_schedule(rts, ctx.dt)
+        W_t = bm(-steps[0][0]) if steps else None
+        with _Timed("adj_bwd"):
+            for (r, h, rn) in steps:
+                tau, W_n = -r, bm(-rn)
+                cfg.set_step(tau, -h)
+                wtraj, z1, _ = wsde_forward(cfg, Yw, layers, (W_n - W_t).view(S, 1, P), 0, 0, ctx.w_stale)
+                xs, acts = xpath_forward(cfg, Yx, wtraj, keep_acts=True)
+                cfg.set_step(tau, h)
+                a_x, gw_traj = xpath_backward(cfg, xs, wtraj, a_x, acts)
+                a_w, gl = wsde_backward(cfg, layers, wtraj, z1, gw_traj, gkl, a_w, True)
+                gl = [t for lay in gl for t in lay]
+                if gacc is None:
+                    gacc = gl
+                else:
+                    torch._foreach_add_(gacc, gl)
+                Yx, Yw, W_t = xs[1], wtraj[:, 1].contiguous(), W_n
+        if gacc is None:
+            gacc = [torch.zeros_like(t) for lay in layers for t in lay]
+        global LAST_RECONSTRUCTION
+        LAST_RECONSTRUCTION = (Yx, Yw)  # y0 as the reverse solve reconstructs it (`y0_rec` of sde_vjp.py:162; diagnostics / tests)
+        gw0 = a_w if ctx.w0_per_sample else a_w.sum(0)
+        return (None, None, None, None, None, a_x, gw0, *gacc)
 
 
 def zero_fw_layers(P, device):

@@ -18,7 +18,7 @@ import torch
 
 from . import _fused, _lib
 from .arch import FxSpec, Layer, _gen, fw_layers, split
-from .sdeint import sdeint_ito_fixed_grid
+from .sdeint import sdeint_ito, sdeint_ito_fixed_grid
 
 
 class _AugDynamics:
@@ -42,10 +42,7 @@ class _AugDynamics:
     def g_aug(self, y, t, args):
         raise NotImplementedError("g_aug is evaluated by the fused kernels; pass it to sdeint_ito_fixed_grid")
 
-    def _solve(self, y0, ts, rng, args, method, rep, time_grid):
-        """y0: (S, x_dim + 2P) flat states (brax.py:110) or (x_dim + 2P,).  Returns ys[-1]-style
-        output packed as (T=2 rows: y0, y_T) is not needed by the layer, so the full tuple
-        (x_T, kl, wtraj) is returned for `SDEBNN.apply_fun`; `ys` is assembled there on demand."""
+    def _unpack(self, y0, rep):
         S, B, H, W, Cc = self.x_shape
         P, x_dim = self.P, self.x_dim
         y0 = y0.reshape(S, x_dim + 2 * P)
@@ -55,17 +52,30 @@ class _AugDynamics:
             w0 = w0[0]
         if rep not in (0, P):
             raise ValueError(f"rep must be 0 or w_dim={P} for SDEBNN dynamics, got {rep}")
-        # method: g_aug is state-independent as shipped (quirk Q2), so the Milstein correction
-        # (sdeint.py:36-39) and the Heun average are identically zero / equal: all three coincide.
-        nsteps = len(ts)
-        ts_np = ts.detach().cpu().numpy() if isinstance(ts, torch.Tensor) else np.asarray(ts, dtype=np.float32)
+        return x, w0
+
+    def _config(self, nsteps, ts_np, rep, time_grid, args, device):
+        S, B = self.x_shape[:2]
         cfg = _fused.BlockConfig(self.fx, self.fw, S, B, nsteps, self.diff_coef, bool(rep), time_grid, self.math,
                                  ts=ts_np, remat=self.remat)
         if self.w_drift:
             layers = fw_layers(args)
         else:
-            layers = _fused.zero_fw_layers(P, y0.device)
+            layers = _fused.zero_fw_layers(self.P, device)
             cfg.fw = dict(hidden_dims=(1,), actfn="softplus", ou_dw=False)
+        return cfg, layers
+
+    def _solve(self, y0, ts, rng, args, method, rep, time_grid):
+        """y0: (S, x_dim + 2P) flat states (brax.py:110) or (x_dim + 2P,).  Returns ys[-1]-style
+        output packed as (T=2 rows: y0, y_T) is not needed by the layer, so the full tuple
+        (x_T, kl, wtraj) is returned for `SDEBNN.apply_fun`; `ys` is assembled there on demand."""
+        S, P = self.x_shape[0], self.P
+        x, w0 = self._unpack(y0, rep)
+        # method: g_aug is state-independent as shipped (quirk Q2), so the Milstein correction
+        # (sdeint.py:36-39) and the Heun average are identically zero / equal: all three coincide.
+        nsteps = len(ts)
+        ts_np = ts.detach().cpu().numpy() if isinstance(ts, torch.Tensor) else np.asarray(ts, dtype=np.float32)
+        cfg, layers = self._config(nsteps, ts_np, rep, time_grid, args, y0.device)
         if isinstance(rng, torch.Tensor):
             dW, seed, sid = rng.to(torch.float32).reshape(S, cfg.nit, P).contiguous(), 0, 0
         elif isinstance(rng, (tuple, list)):
@@ -74,6 +84,22 @@ class _AugDynamics:
             dW, seed, sid = None, int(rng), self.stream_id
         flat = [t for lay in layers for t in lay]
         return _fused.SDEBNNSolve.apply(cfg, dW, seed, sid, self.w_stale, x, w0, *flat)
+
+    def _solve_adjoint(self, y0, ts, rng, args, dt, method, rep):
+        """`sdeint_ito` (jaxsde/jaxsde/sdeint.py:11-13) for these dynamics: steps of `dt` on a Philox Brownian tree over the
+        S*P weight rows (the x rows have g = 0; with rep = P the kl rows reuse the w rows' path, brownian.py:69-74), reverse
+        pass by the stochastic adjoint.  Returns (x_T, kl [S], w at the output times [S, len(ts), P])."""
+        from .sdeint import BrownianTree
+        S, P = self.x_shape[0], self.P
+        x, w0 = self._unpack(y0, rep)
+        if isinstance(rng, torch.Tensor):
+            raise ValueError("sdeint_ito needs a seed or a (seed, stream_id) pair: its Brownian path is queried at arbitrary times")
+        seed, sid = (int(rng[0]), int(rng[1])) if isinstance(rng, (tuple, list)) else (int(rng), self.stream_id)
+        tsl = [float(v) for v in (ts.detach().cpu().tolist() if isinstance(ts, torch.Tensor) else ts)]
+        cfg, layers = self._config(2, np.asarray([0.0, 1.0], dtype=np.float32), rep, "uniform", args, y0.device)
+        bm = BrownianTree(tsl[0], S * P, tsl[-1], (seed, sid), depth=10, rep=0, device=y0.device)
+        flat = [t for lay in layers for t in lay]
+        return _fused.SDEBNNAdjointSolve.apply(cfg, tsl, float(dt), bm, self.w_stale, x, w0, *flat)
 
 
 def SDEBNN(fx_block_type, fx_dim, fx_actfn, fw, diff_coef=1e-4, name="sdebnn", stl=False, xt=False, nsteps=20,
@@ -113,8 +139,6 @@ def SDEBNN(fx_block_type, fx_dim, fx_actfn, fw, diff_coef=1e-4, name="sdebnn", s
         return tuple(input_shape), (init_w0, logstd_w0, fw_params)
 
     def apply_fun(params, inputs, rng, full_output=False, fixed_grid=True, **kwargs):
-        if not fixed_grid:
-            raise NotImplementedError("stochastic adjoint (sdeint_ito) is out of scope: README.md:25")
         init_w0, logstd_w0, fw_params = params
         x = inputs
         squeeze_s = x.dim() == 4
@@ -141,8 +165,12 @@ def SDEBNN(fx_block_type, fx_dim, fx_actfn, fw, diff_coef=1e-4, name="sdebnn", s
             w0 = init_w0.expand(S, P)
         y0 = torch.cat([x.reshape(S, -1), w0, x.new_zeros(S, P)], dim=1)  # brax.py:110
         rep = P if stl else 0  # brax.py:111
-        xo, kl_sde, wtraj = sdeint_ito_fixed_grid(dyn.f_aug, dyn.g_aug, y0, ts, rng, fw_params, method=method,
-                                                  rep=rep, time_grid=time_grid)
+        if fixed_grid:
+            xo, kl_sde, wtraj = sdeint_ito_fixed_grid(dyn.f_aug, dyn.g_aug, y0, ts, rng, fw_params, method=method,
+                                                      rep=rep, time_grid=time_grid)
+        else:  # brax.py:114-116 ("using stochastic adjoint"); `dt` (keyword) is sdeint_ito's step, default 1e-6 as there
+            xo, kl_sde, wtraj = sdeint_ito(dyn.f_aug, dyn.g_aug, y0, ts, rng, fw_params, dt=kwargs.get("dt", 1e-6),
+                                           method="euler_maruyama", rep=rep)
         kl = kl + kl_sde  # brax.py:119
         if squeeze_s:
             xo, kl = xo[0], kl[0]

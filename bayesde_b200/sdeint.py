@@ -325,6 +325,9 @@ def sdeint_ito(f, g, y0, ts, rng, args=(), dt=1e-6, method="milstein", rep=0):
     `rng` is an int seed or a (seed, stream_id) pair; gradients w.r.t. `ts` are zero as in the reference (sde_vjp.py:192)."""
     if method not in ("milstein", "euler_maruyama"):
         raise ValueError("Unknown method: {}".format(method))  # sdeint.py:62
+    owner = getattr(f, "__self__", None)
+    if owner is not None and getattr(owner, "_bsde_structured", False) and getattr(g, "__self__", None) is owner:
+        return owner._solve_adjoint(y0, ts, rng, args, dt, method, rep)  # SDEBNN dynamics: fused K1/K2/K3 steps
     _require_cuda(y0)
     tsl = [float(v) for v in (ts.detach().cpu().tolist() if isinstance(ts, torch.Tensor) else ts)]
     return _SdeintIto.apply(f, g, float(dt), method, rng, int(rep), tsl, args, y0, *_leaves(args))

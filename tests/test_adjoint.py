@@ -365,3 +365,140 @@ def test_gpu_sdeint_ito_adjoint_vs_backprop_small_dt(built_lib):
     gy, ga = torch.autograd.grad(ref[-1].sum(), (y0r, fa))
     assert torch.allclose(y0_.grad.cpu().double(), gy, rtol=3e-2, atol=3e-2)
     assert torch.allclose(torch.cat([a.grad for a in args_]).cpu().double(), ga, rtol=3e-2, atol=3e-2)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# SDEBNN blocks with fixed_grid=False (brax/_impl/brax.py:114-116): fused K1 / K2 / K3 steps + stochastic adjoint
+# --------------------------------------------------------------------------------------------------------------
+def test_step_schedule_follows_the_while_loop():
+    from bayesde_b200._fused import ito_step_schedule
+    f32 = np.float32
+    ts = np.linspace(0.0, 1.0, 6, dtype=f32)
+    steps, marks = ito_step_schedule(ts, 0.15)
+    assert marks == [2, 3, 4, 6, 7]                                    # interior targets are overshot, sdeint.py:114-128
+    assert steps[0] == (f32(0.0), f32(0.15), f32(0.15))
+    assert steps[-1][2] == f32(1.0) and abs(float(steps[-1][1]) - 0.1) < 1e-6   # clipped at ts[-1] only
+    assert all(s[2] == n[0] for s, n in zip(steps, steps[1:]))
+    rsteps, _ = ito_step_schedule([-f32(v) for v in ts[::-1]], 0.15)   # the reflected grid is not the mirror image
+    assert rsteps[0][0] == f32(-1.0) and rsteps[-1][2] == f32(-0.0) and len(rsteps) == 7
+    with pytest.raises(ValueError):
+        ito_step_schedule(ts, 0.0)
+    with pytest.raises(ValueError):
+        ito_step_schedule([0.0, 1.0], 1e-3, max_steps=10)
+    assert ito_step_schedule([0.5], 0.1) == ([], [])
+
+
+def _oracle_block_adjoint(blk, w0, fw, x, seed, sid, dt, cot, kl_w, method="euler_maruyama"):
+    """Per-sample oracle: ito_integrate on the sample's slice of the S*P-row tree, then the reference's stochastic adjoint."""
+    S, P, x_dim = x.shape[0], blk.P, blk.x_dim
+    ts = np.linspace(0.0, 1.0, blk.nsteps, dtype=np.float32)
+    tree = ja.BrownianTree(seed, sid, S * P, float(ts[0]), float(ts[-1]))
+    sizes = [t.numel() for lay in fw for t in lay]
+    shapes = [t.shape for lay in fw for t in lay]
+    fa = torch.cat([t.reshape(-1) for lay in fw for t in lay])
+
+    def unravel(v):
+        parts = [p.reshape(sh) for p, sh in zip(torch.split(v, sizes), shapes)]
+        return [tuple(parts[i:i + 5]) for i in range(0, len(parts), 5)]
+
+    out = []
+    for s in range(S):
+        def bm(t, s=s):
+            w = tree(t)[s * P:(s + 1) * P]
+            return torch.cat([w.new_zeros(x_dim), w, w])
+        y0 = torch.cat([x[s].reshape(-1), w0, torch.zeros_like(w0)])
+        ys = ja.ito_integrate(blk.f_aug, blk.g_aug, y0, ts, bm, dt, unravel(fa), method=method)
+        v = torch.cat([cot[s].reshape(-1), torch.zeros_like(w0), kl_w * torch.ones_like(w0)])
+        y0_rec, y_adj, a_adj = ja.stochastic_adjoint(blk.f_aug, blk.g_aug, ys[-1].detach(), v, ts, bm, dt, fa, unravel, method=method)
+        out.append((ys.detach(), y0_rec, y_adj, a_adj))
+    return out, unravel
+
+
+def _adjoint_case(stl, S=2, B=2, H=8, C_in=5, fx_dim=8, nsteps=4, fw_dims=(2, 8, 2), seed=0):
+    from oracle import jax_path as jp
+    g = torch.Generator().manual_seed(seed)
+    blk = jp.SDEBNNBlock((B, H, H, C_in), 0, fx_dim, "softplus", "softplus", 0.2, stl, nsteps)
+    w0 = jp.init_fx(blk.layout, blk.P, g, torch.float64)
+    fw = jp.init_fw(blk.P, fw_dims, g, torch.float64, last_std=0.05)
+    x = torch.randn(S, B, H, H, C_in, generator=g, dtype=torch.float64)
+    cot = torch.randn(S, B, H, H, C_in, generator=g, dtype=torch.float64)
+    return blk, w0, fw, x, cot
+
+
+def test_oracle_block_adjoint_close_to_backprop():
+    """The oracle's stochastic adjoint of an SDEBNN block against backprop through the same variable-step solve: they differ by the
+    discretisation of the reverse solve only, first order in dt here (additive noise): measured 0.088 / 0.20 / 0.12 at dt = 0.02 and
+    0.022 / 0.051 / 0.031 at dt = 0.005 for y0_rec / dL/dy0 (max 7.9) / dL/dargs (max 2.3)."""
+    blk, w0, fw, x, cot = _adjoint_case(False, S=1, B=1, H=4, fx_dim=4, nsteps=3)
+    blk.w_stale = torch.zeros(blk.P, dtype=torch.float64)
+    kl_w = 1e-3
+    P, x_dim = blk.P, blk.x_dim
+    ts = np.linspace(0.0, 1.0, blk.nsteps, dtype=np.float32)
+    tree = ja.BrownianTree(5, 1, P, 0.0, 1.0)
+    bm = lambda t: torch.cat([torch.zeros(x_dim, dtype=torch.float64), tree(t), tree(t)])
+    v = torch.cat([cot[0].reshape(-1), torch.zeros_like(w0), kl_w * torch.ones_like(w0)])
+    errs = []
+    for dt in (0.02, 0.005):
+        (res,), unravel = _oracle_block_adjoint(blk, w0, fw, x, 5, 1, dt, cot, kl_w)
+        ys, y0_rec, y_adj, a_adj = res
+        y0 = torch.cat([x[0].reshape(-1), w0, torch.zeros_like(w0)]).requires_grad_(True)
+        fa = torch.cat([t.reshape(-1) for lay in fw for t in lay]).requires_grad_(True)
+        ys2 = ja.ito_integrate(blk.f_aug, blk.g_aug, y0, ts, bm, dt, unravel(fa), method="euler_maruyama")
+        assert torch.allclose(ys2.detach(), ys, rtol=1e-12, atol=1e-12)
+        gy, ga = torch.autograd.grad((ys2[-1] * v).sum(), (y0, fa))
+        errs.append((float((y0_rec[:x_dim + P] - y0.detach()[:x_dim + P]).abs().max()),
+                     float((y_adj - gy).abs().max()) / float(gy.abs().max()),
+                     float((a_adj - ga).abs().max()) / float(ga.abs().max())))
+    assert errs[1][0] < 0.03 and errs[1][1] < 0.01 and errs[1][2] < 0.02, errs
+    assert all(3.0 < a / b < 5.0 for a, b in zip(errs[0], errs[1])), errs     # first order in dt
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stl", [False, True])
+def test_gpu_sdebnn_block_stochastic_adjoint(built_lib, stl):
+    """`apply_fun(..., fixed_grid=False, dt=...)` through the reference-shaped layer API against the oracle's sdeint_ito + stochastic
+    adjoint on the same Philox tree: x_T / w(t) 1e-4, KL 1e-4 relative, reconstructed y0 and every gradient 2e-3 of the largest entry."""
+    from bayesde_b200 import _fused, arch, brax
+    blk, w0, fw, x, cot = _adjoint_case(stl)
+    dt, kl_w, seed, sid = 0.07, 1e-3, 11, 3
+    fw_layer = arch.MLP((2, 8, 2), actfn="softplus", xt=True, ou_dw=True)
+    layer = brax.SDEBNN(0, 8, "softplus", fw_layer, diff_coef=0.2, stl=stl, xt=True, nsteps=blk.nsteps, stream_id=sid)
+    _, (w_stale_like, _, _) = layer.init(0, tuple(x.shape[1:]))
+    blk.w_stale = w_stale_like.double()
+    res, unravel = _oracle_block_adjoint(blk, w0, fw, x, seed, sid, dt, cot, kl_w)
+
+    dev = "cuda:0"
+    w0d = w0.float().to(dev).requires_grad_(True)
+    tree = []
+    for i, lay in enumerate(fw):
+        tree.append(tuple(t.float().to(dev).contiguous().requires_grad_(True) for t in lay))
+        if i < len(fw) - 1:
+            tree.append(())
+    fwd = ((), tree)
+    xd = x.float().to(dev).requires_grad_(True)
+    xo, kl, info = layer.apply((w0d, (), fwd), xd, seed, full_output=True, fixed_grid=False, dt=dt)
+    P, x_dim = blk.P, blk.x_dim
+    for s, (ys, y0_rec, y_adj, a_adj) in enumerate(res):
+        assert torch.allclose(xo[s].detach().cpu().double().reshape(-1), ys[-1][:x_dim], rtol=1e-4, atol=1e-4), "x_T"
+        assert torch.allclose(info["sdebnn_w"][s].detach().cpu().double(), ys[:, x_dim:x_dim + P], rtol=1e-4, atol=1e-5), "w(t)"
+        klr = float(ys[-1][x_dim + P:].sum())
+        assert abs(float(kl[s].detach()) - klr) <= 1e-4 * abs(klr) + 1e-5, ("kl", float(kl[s].detach()), klr)
+    obj = (xo * cot.float().to(dev)).sum() + kl_w * kl.sum()
+    leaves = [xd, w0d] + [t for lay in arch.fw_layers(fwd) for t in lay]
+    grads = torch.autograd.grad(obj, leaves)
+
+    def close(a, b, what):
+        a, b = a.detach().cpu().double(), b.double()
+        assert float((a - b).abs().max()) <= 2e-3 * float(b.abs().max()) + 1e-9, (what, float((a - b).abs().max()), float(b.abs().max()))
+
+    x0r, w0r = _fused.LAST_RECONSTRUCTION
+    for s, (ys, y0_rec, y_adj, a_adj) in enumerate(res):
+        close(x0r[s].reshape(-1), y0_rec[:x_dim], "reconstructed x0")
+        close(w0r[s], y0_rec[x_dim:x_dim + P], "reconstructed w0")
+        close(grads[0][s].reshape(-1), y_adj[:x_dim], "grad x")
+    close(grads[1], sum(r[2][x_dim:x_dim + P] for r in res), "grad w0")
+    a_sum = sum(r[3] for r in res)
+    flat = torch.cat([g.reshape(-1) for g in grads[2:]])
+    for (n, a, b) in zip(range(len(grads) - 2), grads[2:], [t for lay in unravel(a_sum) for t in lay]):
+        close(a, b, f"grad fw tensor {n}")
+    assert flat.isfinite().all()
