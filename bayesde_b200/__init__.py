@@ -12,6 +12,6 @@ All arithmetic on the hot path runs in libbsde.so (hand-written CUDA, C ABI in i
 there is no CPU / eager fallback.
 """
 from . import arch, brax, brax_utils, evaluation, torch_models, torch_toy  # noqa: F401
-from .sdeint import sdeint_ito_fixed_grid, sdeint_ito, make_brownian_motion  # noqa: F401
+from .sdeint import sdeint_ito_fixed_grid, sdeint_ito, make_brownian_motion, PRNGKey, split  # noqa: F401
 
-__all__ = ["sdeint_ito_fixed_grid", "sdeint_ito", "make_brownian_motion", "arch", "brax", "brax_utils", "torch_toy", "torch_models", "evaluation"]
+__all__ = ["sdeint_ito_fixed_grid", "sdeint_ito", "make_brownian_motion", "PRNGKey", "split", "arch", "brax", "brax_utils", "torch_toy", "torch_models", "evaluation"]

@@ -67,7 +67,7 @@ _EXPORTS = ["bsde_version", "bsde_last_error", "bsde_launch_count", "bsde_wsde_w
             "bsde_xpath_workspace_bytes", "bsde_xpath_acts_bytes", "bsde_xpath_fwd", "bsde_xpath_bwd", "bsde_step_update",
             "bsde_philox_increments", "bsde_toy_em_fwd", "bsde_toy_em_bwd", "bsde_chain_workspace_bytes", "bsde_chain_acts_floats",
             "bsde_chain_out_offset", "bsde_chain_fwd", "bsde_chain_bwd", "bsde_nchw_reinterp_axpy", "bsde_brownian_tree",
-            "bsde_step_update_prod"]
+            "bsde_step_update_prod", "bsde_brownian_tree_threefry", "bsde_threefry_split"]
 
 
 def lib():
@@ -107,6 +107,9 @@ def lib():
     L.bsde_step_update.argtypes = [C.c_int32, C.c_int64, C.c_float, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bsde_philox_increments.argtypes = [C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_int64, vp, vp, vp]
     L.bsde_brownian_tree.argtypes = [C.c_uint64, C.c_uint32, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, vp, vp]
+    L.bsde_brownian_tree_threefry.argtypes = [C.c_uint32, C.c_uint32, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float,
+                                              C.c_int64, C.c_int64, vp, vp]
+    L.bsde_threefry_split.argtypes = [C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(C.c_uint32)]
     L.bsde_step_update_prod.argtypes = [C.c_int64, C.c_float, vp, vp, vp, vp, vp, vp]
     L.bsde_toy_em_fwd.argtypes = [C.POINTER(ToyDesc), vp, vp, vp, C.c_uint64] + [vp] * 8 + [vp, vp, vp]
     L.bsde_toy_em_bwd.argtypes = [C.POINTER(ToyDesc), vp, vp, vp, vp] + [vp] * 8 + [vp] * 8 + [vp]

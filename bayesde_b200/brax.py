@@ -65,6 +65,16 @@ class _AugDynamics:
             cfg.fw = dict(hidden_dims=(1,), actfn="softplus", ou_dw=False)
         return cfg, layers
 
+    def _jax_trees(self, keys, tsl, rep, device):
+        """One reference-layout tree per sample for JAX keys (`vmap` over rngs, examples/jax/sdebnn_classification.py:218): the state
+        of a sample is [x (x_dim), w (P), kl (P)] with rep tying (brax.py:110-111); only the w rows [x_dim, x_dim + P) are drawn."""
+        from .sdeint import BrownianTree
+        keys = np.asarray(keys, dtype=np.uint32).reshape(-1, 2)
+        S, P = self.x_shape[0], self.P
+        if keys.shape[0] != S:
+            raise ValueError(f"need one PRNGKey per sample: {S} samples, {keys.shape[0]} keys")
+        return [BrownianTree(tsl[0], self.x_dim + 2 * P, tsl[-1], k, depth=10, rep=rep, device=device) for k in keys]
+
     def _solve(self, y0, ts, rng, args, method, rep, time_grid):
         """y0: (S, x_dim + 2P) flat states (brax.py:110) or (x_dim + 2P,).  Returns ys[-1]-style
         output packed as (T=2 rows: y0, y_T) is not needed by the layer, so the full tuple
@@ -76,6 +86,11 @@ class _AugDynamics:
         nsteps = len(ts)
         ts_np = ts.detach().cpu().numpy() if isinstance(ts, torch.Tensor) else np.asarray(ts, dtype=np.float32)
         cfg, layers = self._config(nsteps, ts_np, rep, time_grid, args, y0.device)
+        if _is_jax_keys(rng):  # replay of a JAX run: increments of the reference's own threefry tree
+            from .sdeint import tree_increments
+            tsl = [float(v) for v in ts_np]
+            rng = torch.stack([tree_increments(tr, tsl, time_grid, self.x_dim, P)
+                               for tr in self._jax_trees(rng, tsl, rep, y0.device)])
         if isinstance(rng, torch.Tensor):
             dW, seed, sid = rng.to(torch.float32).reshape(S, cfg.nit, P).contiguous(), 0, 0
         elif isinstance(rng, (tuple, list)):
@@ -93,13 +108,21 @@ class _AugDynamics:
         S, P = self.x_shape[0], self.P
         x, w0 = self._unpack(y0, rep)
         if isinstance(rng, torch.Tensor):
-            raise ValueError("sdeint_ito needs a seed or a (seed, stream_id) pair: its Brownian path is queried at arbitrary times")
-        seed, sid = (int(rng[0]), int(rng[1])) if isinstance(rng, (tuple, list)) else (int(rng), self.stream_id)
+            raise ValueError("sdeint_ito needs a seed, a (seed, stream_id) pair or PRNGKeys: its Brownian path is queried at arbitrary times")
         tsl = [float(v) for v in (ts.detach().cpu().tolist() if isinstance(ts, torch.Tensor) else ts)]
         cfg, layers = self._config(2, np.asarray([0.0, 1.0], dtype=np.float32), rep, "uniform", args, y0.device)
-        bm = BrownianTree(tsl[0], S * P, tsl[-1], (seed, sid), depth=10, rep=0, device=y0.device)
+        if _is_jax_keys(rng):
+            trees, x_dim = self._jax_trees(rng, tsl, rep, y0.device), self.x_dim
+            bm = lambda t: torch.cat([tr.query(t, x_dim, P) for tr in trees])
+        else:
+            seed, sid = (int(rng[0]), int(rng[1])) if isinstance(rng, (tuple, list)) else (int(rng), self.stream_id)
+            bm = BrownianTree(tsl[0], S * P, tsl[-1], (seed, sid), depth=10, rep=0, device=y0.device)
         flat = [t for lay in layers for t in lay]
         return _fused.SDEBNNAdjointSolve.apply(cfg, tsl, float(dt), bm, self.w_stale, x, w0, *flat)
+
+
+def _is_jax_keys(rng):
+    return isinstance(rng, np.ndarray) and rng.dtype == np.uint32 and rng.shape[-1] == 2
 
 
 def SDEBNN(fx_block_type, fx_dim, fx_actfn, fw, diff_coef=1e-4, name="sdebnn", stl=False, xt=False, nsteps=20,

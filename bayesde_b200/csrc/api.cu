@@ -640,6 +640,134 @@ extern "C" int bsde_brownian_tree(uint64_t seed, uint32_t stream_id, int64_t n, 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same tree on JAX's threefry PRNG: jaxsde/jaxsde/brownian.py:19-95 with jax.random.{split,normal}
+// (jax==0.1.77, requirements.txt:1; Threefry-2x32-20, uniform from the top 23 bits, XLA's float32 erf_inv) so that the path a JAX
+// run saw can be queried here.  The keys along the root-to-leaf walk are the same for every element: the host derives them
+// (22 Threefry blocks), the kernel draws one normal per element and level.
+// ---------------------------------------------------------------------------------------------
+namespace bsde {
+#define BSDE_TF_MAX_DEPTH 30
+struct TfPath {
+  uint32_t end_key[2];
+  uint32_t lvl_key[BSDE_TF_MAX_DEPTH + 1][2];  // key of the bridge draw at level l; [depth] = the final bridge point
+};
+
+__host__ __device__ __forceinline__ uint32_t tf_rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+__host__ __device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  const uint32_t ks[3] = {k0, k1, k0 ^ k1 ^ 0x1BD11BDAu};
+  x0 += ks[0]; x1 += ks[1];
+#define TF_R(r) x0 += x1; x1 = tf_rotl(x1, r) ^ x0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    if (i % 2 == 0) { TF_R(13) TF_R(15) TF_R(26) TF_R(6) } else { TF_R(17) TF_R(29) TF_R(16) TF_R(24) }
+    x0 += ks[(i + 1) % 3];
+    x1 += ks[(i + 2) % 3] + (uint32_t)(i + 1);
+  }
+#undef TF_R
+}
+
+// jax.random.split(key): threefry over iota(4) = lanes (0, 2) and (1, 3); left = lane-0 outputs, right = lane-1 outputs
+static void tf_split(const uint32_t key[2], uint32_t left[2], uint32_t right[2]) {
+  uint32_t a0 = 0, a1 = 2, b0 = 1, b1 = 3;
+  threefry2x32(key[0], key[1], a0, a1);
+  threefry2x32(key[0], key[1], b0, b1);
+  left[0] = a0; left[1] = b0; right[0] = a1; right[1] = b1;
+}
+
+// element e of jax.random.normal(key, (n,)) in float32: _random_bits puts counts [0, half) on lane 0 and [half, 2 half) on lane 1
+// (one zero appended when n is odd); uniform on [nextafter(-1, 0), 1) from the top 23 bits; sqrt(2) * erf_inv (XLA / Giles 2010)
+__device__ __forceinline__ float tf_normal(uint32_t k0, uint32_t k1, long long n, long long e) {
+  const long long half = (n + 1) >> 1;
+  uint32_t x0, x1;
+  const bool lane1 = e >= half;
+  if (!lane1) { x0 = (uint32_t)e; x1 = (e + half < n) ? (uint32_t)(e + half) : 0u; }
+  else { x0 = (uint32_t)(e - half); x1 = (uint32_t)e; }
+  threefry2x32(k0, k1, x0, x1);
+  const uint32_t bits = lane1 ? x1 : x0;
+  const float lo = -0.99999994f;                                              // nextafter(-1, 0)
+  const float fl = __fsub_rn(__uint_as_float((bits >> 9) | 0x3F800000u), 1.0f);
+  const float u = fmaxf(lo, __fadd_rn(__fmul_rn(fl, __fsub_rn(1.0f, lo)), lo));
+  float w = -log1pf(__fmul_rn(-u, u));
+  const bool lt = w < 5.0f;
+  w = lt ? __fsub_rn(w, 2.5f) : __fsub_rn(sqrtf(w), 3.0f);
+  float p = lt ? 2.81022636e-08f : -0.000200214257f;
+#define TF_C(a, b) p = __fadd_rn(lt ? a : b, __fmul_rn(p, w));
+  TF_C(3.43273939e-07f, 0.000100950558f) TF_C(-3.5233877e-06f, 0.00134934322f) TF_C(-4.39150654e-06f, -0.00367342844f)
+  TF_C(0.00021858087f, 0.00573950773f) TF_C(-0.00125372503f, -0.0076224613f) TF_C(-0.00417768164f, 0.00943887047f)
+  TF_C(0.246640727f, 1.00167406f) TF_C(1.50140941f, 2.83297682f)
+#undef TF_C
+  const float r = fabsf(u) == 1.0f ? u * INFINITY : __fmul_rn(p, u);
+  return __fmul_rn(1.41421354f, r);
+}
+
+__global__ void brownian_tree_threefry_kernel(TfPath path, long long n, int rep, int depth, float t0, float t1, float t,
+                                              long long first, long long count, float* __restrict__ out) {
+  const float span = __fsub_rn(t1, t0);
+  const float s = __fdiv_rn(__fsub_rn(t, t0), span);
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < count; j += (long long)gridDim.x * blockDim.x) {
+    const long long i = first + j;
+    const long long e = (rep > 0 && i >= n - rep) ? i - rep : i;               // sample_with_rep, brownian.py:69-74
+    float tl = 0.f, xl = 0.f, tr = 1.f;
+    float xr = tf_normal(path.end_key[0], path.end_key[1], n, e);            // w_end, brownian.py:81-82
+    for (int lvl = 0; lvl < depth; ++lvl) {                                   // virtual_brownian_tree, brownian.py:26-51
+      const float tm = __fdiv_rn(__fadd_rn(tl, tr), 2.0f);
+      const float z = tf_normal(path.lvl_key[lvl][0], path.lvl_key[lvl][1], n, e);
+      const float xm = (xl * (tr - tm) + xr * (tm - tl)) / (tr - tl) + sqrtf((tr - tm) * (tm - tl) / (tr - tl)) * z;
+      if (s < tm) { tr = tm; xr = xm; } else { tl = tm; xl = xm; }
+    }
+    const float z = tf_normal(path.lvl_key[depth][0], path.lvl_key[depth][1], n, e);
+    const float mean = (xl * (tr - s) + xr * (s - tl)) / (tr - tl);
+    const float sd = sqrtf((tr - s) * (s - tl) / (tr - tl));
+    out[j] = sqrtf(span) * (mean + sd * z);
+  }
+}
+}  // namespace bsde
+
+extern "C" int bsde_threefry_split(uint32_t key0, uint32_t key1, int32_t num, uint32_t* h_out) {
+  BSDE_CHECK_ARG(num >= 1 && h_out, "need num >= 1 and a host output array of 2*num words");
+  // jax.random.split(key, num): threefry of iota(2 num), first half on lane 0, second half on lane 1, reshaped (num, 2)
+  for (int32_t i = 0; i < num; ++i) {
+    uint32_t x0 = (uint32_t)i, x1 = (uint32_t)(i + num);
+    bsde::threefry2x32(key0, key1, x0, x1);
+    h_out[i] = x0;
+    h_out[num + i] = x1;
+  }
+  return 0;
+}
+
+extern "C" int bsde_brownian_tree_threefry(uint32_t key0, uint32_t key1, int64_t n, int32_t rep, int32_t depth, float t0, float t1,
+                                           float t, int64_t first, int64_t count, float* d_out, void* stream) {
+  BSDE_CHECK_ARG(n >= 0 && rep >= 0 && 2 * (int64_t)rep <= n, "need 0 <= 2*rep <= n (n=%lld, rep=%d)", (long long)n, rep);
+  BSDE_CHECK_ARG(depth >= 0 && depth <= BSDE_TF_MAX_DEPTH, "depth must be in [0, %d], got %d", BSDE_TF_MAX_DEPTH, depth);
+  BSDE_CHECK_ARG(t1 > t0, "need t1 > t0");
+  BSDE_CHECK_ARG(n < (1LL << 32), "n must be < 2^32");
+  BSDE_CHECK_ARG(first >= 0 && count >= 0 && first + count <= n, "slice [first, first+count) must lie inside [0, n)");
+  if (count == 0) return 0;
+  BSDE_CHECK_ARG(d_out != nullptr, "NULL tensor pointer");
+  bsde::TfPath path;
+  const uint32_t root[2] = {key0, key1};
+  uint32_t cur[2], l[2], r[2];
+  bsde::tf_split(root, path.end_key, cur);                     // end_rng, path_rng = random.split(rng), brownian.py:81
+  const float s = (t - t0) / (t1 - t0);
+  float tl = 0.f, tr = 1.f;
+  for (int lvl = 0; lvl < depth; ++lvl) {
+    path.lvl_key[lvl][0] = cur[0]; path.lvl_key[lvl][1] = cur[1];
+    const float tm = (tl + tr) / 2.0f;
+    bsde::tf_split(cur, l, r);
+    if (s < tm) { tr = tm; cur[0] = l[0]; cur[1] = l[1]; } else { tl = tm; cur[0] = r[0]; cur[1] = r[1]; }
+  }
+  path.lvl_key[depth][0] = cur[0]; path.lvl_key[depth][1] = cur[1];
+  long long blocks = (count + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bsde::brownian_tree_threefry_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(path, n, rep, depth, t0, t1, t, first, count,
+                                                                                     d_out);
+  count_launch();
+  BSDE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int bsde_step_update_prod(int64_t n, float dt, const float* d_y, const float* d_f, const float* d_gprod,
                                      const float* d_gdgprod, float* d_y1, void* stream) {
   BSDE_CHECK_ARG(n >= 0, "n must be >= 0");

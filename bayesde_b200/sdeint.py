@@ -9,8 +9,9 @@ Two routes, both on libbsde.so kernels (no CPU fallback):
     as torch ops on the GPU, the step itself (ito_euler_step / ito_milstein_step, sdeint.py:36-50,
     plus euler_heun) is one fused elementwise kernel, increments come from the Philox kernel.
 
-`rng` is an int seed, a `(seed, stream_id)` pair, or a tensor of explicit increments
-(len(ts)-1, D) -- the "supplied increments" mode used for exact comparison with the reference.
+`rng` is an int seed, a `(seed, stream_id)` pair (Philox), a tensor of explicit increments (len(ts)-1, D) -- the "supplied
+increments" mode used for exact comparison with the reference -- or a `PRNGKey` (uint32 pair): the increments then come from the
+reference's own virtual Brownian tree on JAX's threefry stream (jaxsde/jaxsde/brownian.py).
 """
 import ctypes as C
 
@@ -93,6 +94,9 @@ def sdeint_ito_fixed_grid(f, g, y0, ts, rng, args=(), dt=1e-6, method="milstein"
         raise _lib.BsdeError("sdeint_ito_fixed_grid needs CUDA tensors (there is no CPU fallback)")
     tk, dtk = reference_time_grid(ts.detach().cpu().numpy() if isinstance(ts, torch.Tensor) else ts, time_grid)
     D = y0.numel()
+    if is_jax_key(rng):  # the reference's own path: make_brownian_motion(ts[0], zeros(D), ts[-1], rng, rep=rep), sdeint.py:17
+        tsl = [float(v) for v in (ts.detach().cpu().tolist() if isinstance(ts, torch.Tensor) else ts)]
+        rng = tree_increments(BrownianTree(tsl[0], D, tsl[-1], rng, depth=10, rep=rep, device=y0.device), tsl, time_grid)
     seed, sid, inc = _parse_rng(rng)
     if inc is None:
         inc = philox_increments(seed, sid, 1, dtk, D, y0.device)[0]
@@ -123,25 +127,78 @@ def sdeint_ito_fixed_grid(f, g, y0, ts, rng, args=(), dt=1e-6, method="milstein"
 # ------------------------------------------------------------------------------------------------------------------
 # sdeint_ito: variable-step solve with the stochastic-adjoint reverse pass
 # ------------------------------------------------------------------------------------------------------------------
+def PRNGKey(seed):
+    """jax.random.PRNGKey(seed): the uint32 pair [seed >> 32, seed & 0xFFFFFFFF] (numpy, host)."""
+    seed = int(seed)
+    return np.array([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], dtype=np.uint32)
+
+
+def is_jax_key(rng):
+    return isinstance(rng, np.ndarray) and rng.dtype == np.uint32 and rng.shape == (2,)
+
+
+def split(key, num=2):
+    """jax.random.split(key, num) on the host (bsde_threefry_split): (num, 2) uint32."""
+    if not is_jax_key(key):
+        raise ValueError("split needs a PRNGKey (numpy uint32 array of shape (2,))")
+    out = (C.c_uint32 * (2 * int(num)))()
+    _lib.check(_lib.lib().bsde_threefry_split(int(key[0]), int(key[1]), int(num), out), "bsde_threefry_split")
+    return np.frombuffer(out, dtype=np.uint32).reshape(int(num), 2).copy()
+
+
 class BrownianTree:
     """`make_brownian_motion(t0, zeros(n), t1, rng, depth, rep)` (jaxsde/jaxsde/brownian.py:92-95) as a callable
-    t -> W(t) [n] on the device: every query is one `bsde_brownian_tree` launch (O(1) memory, any order of queries).
-    The normals are Philox4x32-10 draws keyed by (seed, stream_id, element, tree node), not threefry splits."""
+    t -> W(t) [n] on the device: every query is one launch (O(1) memory, any order of queries).
+      * rng = int seed or (seed, stream_id): Philox4x32-10 draws keyed by (seed, stream_id, element, tree node) (bsde_brownian_tree);
+      * rng = PRNGKey(...) (uint32 pair): the reference's own stream -- jax.random.split / jax.random.normal on threefry keys
+        (bsde_brownian_tree_threefry), i.e. the path a JAX run of the reference saw.
+    `query(t, first, count)` returns the slice W(t)[first:first+count] without drawing the rest (the x rows of an SDEBNN state
+    have g = 0: quirk Q13)."""
 
     def __init__(self, t0, n, t1, rng, depth=10, rep=0, device="cuda"):
-        seed, sid, inc = _parse_rng(rng)
-        if inc is not None:
-            raise ValueError("a Brownian tree needs an integer seed or a (seed, stream_id) pair")
-        self.seed, self.sid, self.n, self.depth, self.rep = seed, sid, int(n), int(depth), int(rep)
+        self.key = None
+        if is_jax_key(rng):
+            self.key, self.seed, self.sid = (int(rng[0]), int(rng[1])), None, None
+        else:
+            seed, sid, inc = _parse_rng(rng)
+            if inc is not None:
+                raise ValueError("a Brownian tree needs an integer seed, a (seed, stream_id) pair or a PRNGKey")
+            self.seed, self.sid = seed, sid
+        self.n, self.depth, self.rep = int(n), int(depth), int(rep)
         self.t0, self.t1, self.device = float(np.float32(t0)), float(np.float32(t1)), torch.device(device)
 
-    def __call__(self, t):
-        out = torch.empty(self.n, device=self.device, dtype=torch.float32)
-        st = _lib.lib().bsde_brownian_tree(C.c_uint64(self.seed & 0xFFFFFFFFFFFFFFFF), C.c_uint32(self.sid & 0xFFFFFFFF), self.n,
-                                           self.rep, self.depth, self.t0, self.t1, float(np.float32(t)), _lib.ptr(out),
-                                           _lib.stream_ptr())
+    def query(self, t, first=0, count=None):
+        count = self.n - first if count is None else int(count)
+        out = torch.empty(count, device=self.device, dtype=torch.float32)
+        L = _lib.lib()
+        if self.key is not None:
+            st = L.bsde_brownian_tree_threefry(self.key[0], self.key[1], self.n, self.rep, self.depth, self.t0, self.t1,
+                                               float(np.float32(t)), int(first), count, _lib.ptr(out), _lib.stream_ptr())
+            _lib.check(st, "bsde_brownian_tree_threefry")
+            return out
+        if first != 0 or count != self.n:
+            full = self.query(t)
+            return full[first:first + count].contiguous()
+        st = L.bsde_brownian_tree(C.c_uint64(self.seed & 0xFFFFFFFFFFFFFFFF), C.c_uint32(self.sid & 0xFFFFFFFF), self.n,
+                                  self.rep, self.depth, self.t0, self.t1, float(np.float32(t)), _lib.ptr(out), _lib.stream_ptr())
         _lib.check(st, "bsde_brownian_tree")
         return out
+
+    def __call__(self, t):
+        return self.query(t)
+
+
+def tree_increments(bm, ts, time_grid="reference", first=0, count=None):
+    """The increments `bm(next_t) - bm(curr_t)` the fixed-grid scan draws (jaxsde/jaxsde/sdeint.py:103-110), one row per scan
+    iteration, with the scan's own time bookkeeping (quirk Q1) or on the uniform grid: (len(ts)-1, count)."""
+    f32 = np.float32
+    ts = [f32(v) for v in (ts.detach().cpu().tolist() if isinstance(ts, torch.Tensor) else ts)]
+    rows, curr = [], ts[0]
+    for k in range(1, len(ts)):
+        nxt = f32(ts[k] - curr) if time_grid == "reference" else ts[k]
+        rows.append(bm.query(nxt, first, count) - bm.query(curr, first, count))
+        curr = nxt
+    return torch.stack(rows)
 
 
 def make_brownian_motion(t0, x0, t1, rng, depth=10, rep=0):

@@ -32,6 +32,8 @@
  *                            torchbnn/_impl/models.py:25-54,159-169, torchbnn/_impl/diffeq_layers.py:40-62,75-166,230-311
  *   bsde_nchw_reinterp_axpy  the flat-state update y + a * fy.reshape(-1) of the torch front end: models.py:163,168
  *   bsde_brownian_tree       a queryable Brownian path for sdeint_ito (stochastic adjoint): jaxsde/jaxsde/brownian.py:19-95
+ *   bsde_brownian_tree_threefry / bsde_threefry_split   the same tree on jax.random's threefry keys (replay of a JAX run's path):
+ *                            jaxsde/jaxsde/brownian.py:69-95 + jax.random.{split,normal} (jax==0.1.77, requirements.txt:1)
  *   bsde_step_update_prod    the product-form step of the adjoint system: jaxsde/jaxsde/sde_vjp.py:13-47, sdeint.py:36-50
  *   bsde_philox_increments   replaces make_brownian_motion / virtual_brownian_tree queries
  *                            bm(next_t)-bm(curr_t): jaxsde/jaxsde/brownian.py:26-95, sdeint.py:108
@@ -285,6 +287,18 @@ int bsde_philox_increments(uint64_t seed, uint32_t stream_id, int32_t S, int32_t
  * to the rep entries before them (sample_with_rep, :69-74). */
 int bsde_brownian_tree(uint64_t seed, uint32_t stream_id, int64_t n, int32_t rep, int32_t depth, float t0, float t1, float t,
                        float* d_out, void* stream);
+
+/* The same tree driven by JAX's threefry PRNG, so that the Brownian path of a JAX run of the reference can be
+ * queried here: `make_brownian_motion(t0, zeros(n), t1, rng, depth, rep)` (jaxsde/jaxsde/brownian.py:77-95) with rng = (key0, key1),
+ * every draw `jax.random.normal(key, (n,))` in float32 and every descent `jax.random.split(key)` (jax==0.1.77: Threefry-2x32-20,
+ * uniform from the top 23 bits on [nextafter(-1,0), 1), sqrt(2)*erf_inv with XLA's float32 polynomial).  The integer stream is
+ * exact; the float transform follows the same operation order (log1p / sqrt to within 1-2 ulp of XLA's).  Writes the entries
+ * [first, first+count) of the n-vector W(t) to d_out[0..count). */
+int bsde_brownian_tree_threefry(uint32_t key0, uint32_t key1, int64_t n, int32_t rep, int32_t depth, float t0, float t1, float t,
+                                int64_t first, int64_t count, float* d_out, void* stream);
+
+/* jax.random.split(key, num) on the host: h_out receives num keys as [num][2] words (threefry over iota(2*num)). */
+int bsde_threefry_split(uint32_t key0, uint32_t key1, int32_t num, uint32_t* h_out);
 
 /* y1 = y + dt*f + gprod [+ 0.5*gdgprod]: ito_euler_step / ito_milstein_step (jaxsde/jaxsde/sdeint.py:36-50) when the
  * diffusion enters as the products g_prod(y,t,args,dW) and gdg_prod(y,t,args,dW^2 - dt) -- the form the augmented adjoint
