@@ -11,7 +11,8 @@ through strides) and `bsde_nchw_reinterp_axpy` (the flat-NCHW-order state update
 `loss.backward()` through `torchsde.sdeint` (examples/torch/sdebnn_classification.py:34-46).
 
 Semantics follow the INTENDED flat-state reading of `SDENet` (the class as shipped raises in `split`/`cat`: SURVEY
-quirk Q7).  `adjoint=True` / `adaptive=True` raise NotImplementedError.  There is no CPU path.
+quirk Q7).  `adjoint=True` selects the O(1)-memory reverse pass of `sdeint_adjoint` (SDENetAdjointSolve); `adaptive=True` /
+`adjoint_adaptive=True` raise NotImplementedError.  There is no CPU path.
 """
 import ctypes as C
 import math
@@ -427,6 +428,117 @@ class SDENetSolve(torch.autograd.Function):
         return (None, None, None, None, gy, gw0, *[t for pair in gl for t in pair])
 
 
+class SDENetAdjointSolve(torch.autograd.Function):
+    """`sdeint_adjoint(SDENet, [y, w0, 0], ts=[0,1], bm, method, dt)` (models.py:184-197 with `adjoint=True`): the forward solve keeps
+    nothing but its final state; the reverse pass integrates the augmented system [y, w | a_y, a_w, a_logqp | a_params] from t1 back to
+    t0 with the same fixed-step scheme on the same Brownian path run backwards (Li et al. 2020, Alg. 2; torchsde itself is absent).
+    g = [0, sigma, 0] is constant, so per reverse step (forward time tau, step h, reverse increment dW~ = -I_k), midpoint:
+        stage A at (tau, Z):            Z' = Z - h/2 f(tau, Z) + g dW~/2      a' = a + h/2 J(tau, Z)^T a
+        stage B at (tau - h/2, Z'):     Z1 = Z - h   f(.., Z') + g dW~        a1 = a + h   J(.., Z')^T a'    a_par += h (df/dpar)(.., Z')^T a'
+    Every stage is the existing single-iteration launches: bsde_wsde_fwd / bsde_chain_fwd with dt < 0 (reconstruction) and
+    bsde_chain_bwd / bsde_wsde_bwd with dt > 0 at the reconstructed state (an Euler-like reverse step seeded with a or a')."""
+
+    @staticmethod
+    def forward(ctx, cfg, I, seed, stream_id, x, w0, *flat):
+        from .sdeint import philox_increments
+        S, P, n = cfg.S, cfg.ynet.P, cfg.n
+        if S != 1:
+            raise NotImplementedError("sdeint_adjoint route: one weight sample per call (SDENet.forward always has S = 1)")
+        if I is None:  # the same path the in-kernel stream of the plain route draws: N(0, h) at Philox counter (p, k, s, stream)
+            I = philox_increments(seed, stream_id, S, np.full(n, np.float32(cfg.h), dtype=np.float32), P, x.device)
+        elif tuple(I.shape) != (S, n, P):
+            raise ValueError(f"increments must have shape {(S, n, P)}, got {tuple(I.shape)}")
+        I = I.float().contiguous()
+        with torch.no_grad():
+            yT, kl, wtraj = SDENetSolve.apply(cfg, I, 0, 0, x.detach(), w0.detach(), *[t.detach() for t in flat])
+        ctx.cfg = cfg
+        ctx.klayers = [(flat[i].detach().contiguous(), flat[i + 1].detach().contiguous()) for i in range(0, len(flat), 2)]
+        ctx.save_for_backward(yT, wtraj[0, cfg.nit].contiguous(), I)
+        ctx.mark_non_differentiable(wtraj)
+        return yT.clone(), kl, wtraj
+
+    @staticmethod
+    def backward(ctx, gy, gkl, _gw):
+        L = _L()
+        cfg, klayers = ctx.cfg, ctx.klayers
+        Zy, Zw, I = ctx.saved_tensors
+        dev = Zy.device
+        P, n, h = cfg.ynet.P, cfg.n, float(np.float32(cfg.h))
+        mid = cfg.method == "midpoint"
+        desc = cfg.ynet.chain_desc(1, cfg.B, cfg.math)
+        nacts, ooff = L.bsde_chain_acts_floats(C.byref(desc)), L.bsde_chain_out_offset(C.byref(desc))
+        chw_in, chw_out = cfg.ynet.input_size, cfg.ynet.output_size
+        nf = cfg.B * chw_out[0] * chw_out[1] * chw_out[2]
+        a_y = (torch.zeros_like(Zy) if gy is None else gy.float()).contiguous().clone()
+        a_l = (torch.zeros(1, device=dev) if gkl is None else gkl.float()).contiguous()
+        a_w = torch.zeros(P, device=dev, dtype=torch.float32)
+        gacc = [torch.zeros_like(t) for pair in klayers for t in pair]
+        acts = torch.empty(nacts, device=dev, dtype=torch.float32)
+        gf = torch.empty(nf, device=dev, dtype=torch.float32)
+        d = _lib.WsdeDesc()
+        d.S, d.nit, d.stl, d.w0_per_sample = 1, 1, 0, 0
+        d.sigma, d.kl_weight, d.ou_coef = cfg.sigma, 1.0, -1.0
+        fp = _plain_fw_struct(klayers, P, cfg.hidden, cfg.w_act)
+        ws = _lib.workspace(L.bsde_wsde_workspace_bytes(C.byref(d), C.byref(fp)), dev, "wsde")
+        kl_scratch = torch.empty(1, device=dev, dtype=torch.float32)
+        f32t = lambda v: torch.tensor([v], device=dev, dtype=torch.float32)
+
+        def stage(t, dt, Zy_base, Zy_at, Zw_base, Zw_at, noise, ay_base, ay_at, aw_base, aw_at, want_params):
+            """One Euler-like stage evaluated at (Zy_at, Zw_at): returns Z_base - dt f + sigma noise and a_base + dt J^T a_at."""
+            tt, tneg, tpos = f32t(t), f32t(-dt), f32t(dt)
+            wtraj2 = torch.empty(1, 2, P, device=dev, dtype=torch.float32)
+            z1 = torch.empty(cfg.hidden[0], device=dev, dtype=torch.float32)
+            st = L.bsde_wsde_fwd(C.byref(d), C.byref(fp), _lib.ptr(Zw_at), _lib.ptr(tt), _lib.ptr(tneg), _lib.ptr(noise), None,
+                                 _lib.ptr(wtraj2), _lib.ptr(z1), _lib.ptr(kl_scratch), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                 _lib.stream_ptr())
+            _lib.check(st, "bsde_wsde_fwd")
+            Zw_new = wtraj2[0, 1] if Zw_base is Zw_at else wtraj2[0, 1] - Zw_at + Zw_base
+            chain_forward(desc, t, Zw_at, 2 * P, Zy_at, acts)
+            Zy_new = torch.empty_like(Zy_base)
+            reinterp_axpy(Zy_new, chw_in, Zy_base, -dt, acts[ooff:], chw_out)
+            # adjoint rows: a_base + dt J(Z_at)^T a_at
+            reinterp_axpy(gf, chw_out, None, dt, ay_at, chw_in)
+            gyp, gwy = torch.empty_like(ay_at), torch.empty(1, 1, P, device=dev, dtype=torch.float32)
+            chain_backward(desc, t, Zw_at, 2 * P, Zy_at, acts, gf, gyp, False, gwy, P)
+            ay_new = ay_base + gyp
+            gl = [(torch.empty_like(W), torch.empty_like(b)) for W, b in klayers]
+            gfp = _plain_fw_struct(gl, P, cfg.hidden, cfg.w_act)
+            r = torch.empty(P, device=dev, dtype=torch.float32)
+            st = L.bsde_wsde_bwd(C.byref(d), C.byref(fp), _lib.ptr(tt), _lib.ptr(tpos), _lib.ptr(wtraj2), _lib.ptr(z1), _lib.ptr(gwy),
+                                 _lib.ptr(a_l), _lib.ptr(aw_at), _lib.ptr(r), C.byref(gfp), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                 _lib.stream_ptr())
+            _lib.check(st, "bsde_wsde_bwd")
+            aw_new = r if aw_base is aw_at else r - aw_at + aw_base
+            if want_params:
+                torch._foreach_add_(gacc, [t for pair in gl for t in pair])
+            return Zy_new, Zw_new.contiguous(), ay_new, aw_new
+
+        t0 = float(cfg.tk[0])
+        for k in range(n - 1, -1, -1):
+            tau = float(np.float32(t0) + np.float32(k + 1) * np.float32(h))
+            dWr = (-I[0, k]).contiguous()
+            if mid:
+                Zy_p, Zw_p, ay_p, aw_p = stage(tau, 0.5 * h, Zy, Zy, Zw, Zw, 0.5 * dWr, a_y, a_y, a_w, a_w, False)
+                tm = float(np.float32(t0) + np.float32(k) * np.float32(h) + np.float32(0.5) * np.float32(h))
+                Zy, Zw, a_y, a_w = stage(tm, h, Zy, Zy_p, Zw, Zw_p, dWr, a_y, ay_p, a_w, aw_p, True)
+            else:
+                Zy, Zw, a_y, a_w = stage(tau, h, Zy, Zy, Zw, Zw, dWr, a_y, a_y, a_w, a_w, True)
+        global LAST_RECONSTRUCTION
+        LAST_RECONSTRUCTION = (Zy, Zw)
+        return (None, None, None, None, a_y, a_w, *gacc)
+
+
+LAST_RECONSTRUCTION = None
+
+
+def sdenet_solve_adjoint(cfg, x_nhwc, w0, linears, increments=None, seed=0, stream_id=0):
+    """As `sdenet_solve`, with the O(1)-memory reverse pass of `sdeint_adjoint`."""
+    kl = []
+    for W, b in linears:
+        kl += [W.t().contiguous(), b]
+    return SDENetAdjointSolve.apply(cfg, increments, seed, stream_id, x_nhwc, w0, *kl)
+
+
 def sdenet_solve(cfg, x_nhwc, w0, linears, increments=None, seed=0, stream_id=0):
     """Differentiable solve.  x_nhwc [S,B,H,W,C]; linears = [(weight [out,in], bias)] in torch nn.Linear layout."""
     kl = []
@@ -477,9 +589,7 @@ class SDENet(nn.Module):
                 increments=None):
         """-> (logits, logqp).  `increments` [nsteps, P]: W(t_{k+1}) - W(t_k) to replay (else in-kernel Philox keyed by
         (self.seed, call counter), the stand-in for torchsde.BrownianInterval, models.py:190-193)."""
-        if adjoint or adjoint_adaptive:
-            raise NotImplementedError("sdeint_adjoint is out of scope (SURVEY 8.2 / 8.6 N4)")
-        if adaptive:
+        if adaptive or adjoint_adaptive:
             raise NotImplementedError("adaptive stepping is out of scope (SURVEY 8.2 / 8.6 N4)")
         if not y.is_cuda:
             raise _lib.BsdeError("bayesde_b200 kernels need CUDA tensors (there is no CPU fallback)")
@@ -492,7 +602,8 @@ class SDENet(nn.Module):
         lin = [(m.weight, m.bias) for m in self.w_net.linears()]
         I = None if increments is None else increments[None]
         self._calls += 1
-        y1, lq, _ = sdenet_solve(cfg, x, self.flat_initial_params, lin, I, seed=self.seed, stream_id=self._calls)
+        solve = sdenet_solve_adjoint if adjoint else sdenet_solve  # models.py:194: sdeint_adjoint / sdeint
+        y1, lq, _ = solve(cfg, x, self.flat_initial_params, lin, I, seed=self.seed, stream_id=self._calls)
         # f and g are each evaluated once per stage (models.py:161,172): 2 stages for midpoint; euler_heun evaluates g twice
         self.nfe = nsteps * {"midpoint": 4, "euler_heun": 3, "milstein": 2}[method]
         y1 = y1[0].permute(0, 3, 1, 2)                                       # back to (B, C, H, W) order for Flatten

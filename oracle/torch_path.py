@@ -180,6 +180,52 @@ class SDENetOracle:
             return y, w, lq, torch.stack(path)
         return y, w, lq
 
+    def adjoint(self, yT, wT, cot_y, cot_w, cot_lq, w_layers, increments, dt=0.05, method="midpoint", t0=0.0, t1=1.0):
+        """The reverse pass of `torchsde.sdeint_adjoint` (call site models.py:184-197 with `adjoint=True`; torchsde is an un-pinned git
+        dependency that is absent here, so this restates the published scheme: Li et al., "Scalable gradients for stochastic
+        differential equations", AISTATS 2020, Alg. 2).  The augmented state [y, w | a_y, a_w, a_lq | a_params] is integrated from t1 back
+        to t0 with the SAME fixed-step scheme and step as the forward solve on the same Brownian path run backwards
+        (W~(s) = W(-s): the increment of reverse step k is -increments[k]):
+            d[y, w]   = -f(tau, y, w) ds + g dW~          (Stratonovich, g = [0, sigma, 0] constant: no correction term)
+            d a       = +(df/d[y, w])^T a ds              (g does not depend on the state or the parameters)
+            d a_par   = +(df/dparams)^T a ds
+        a_lq stays cot_lq (no drift reads logqp).  Returns (y0_rec, w0_rec, dL/dy0, dL/dw0, [dL/d(W, b) per w_net layer])."""
+        n = int(round((t1 - t0) / dt))
+        assert increments.shape[0] == n
+        params = [t for lay in w_layers for t in lay]
+        y, w, ay, aw = yT.detach(), wT.detach(), cot_y.detach(), cot_w.detach()
+        ap = [torch.zeros_like(p) for p in params]
+
+        def F(tau, y, w, ay, aw):
+            with torch.enable_grad():
+                y_, w_ = y.detach().requires_grad_(True), w.detach().requires_grad_(True)
+                ps = [p.detach().requires_grad_(True) for p in params]
+                lay = [tuple(ps[i:i + 2]) for i in range(0, len(ps), 2)]
+                fy, fw, fl, _ = self.f_parts(tau, y_, w_, lay)
+                obj = (fy * ay).sum() + (fw * aw).sum() + fl * cot_lq
+                gs = torch.autograd.grad(obj, [y_, w_] + ps, allow_unused=True)
+            gs = [torch.zeros_like(q) if g is None else g for g, q in zip(gs, [y_, w_] + ps)]
+            return fy.detach(), fw.detach(), gs[0], gs[1], gs[2:]
+
+        for k in range(n - 1, -1, -1):
+            tau = t0 + (k + 1) * dt
+            dWr = -increments[k]
+            fy, fw, vy, vw, vp = F(tau, y, w, ay, aw)
+            if method == "midpoint":
+                y_p, w_p = y - 0.5 * dt * fy, w - 0.5 * dt * fw + 0.5 * self.sigma * dWr
+                ay_p, aw_p = ay + 0.5 * dt * vy, aw + 0.5 * dt * vw
+                fy2, fw2, vy2, vw2, vp2 = F(tau - 0.5 * dt, y_p, w_p, ay_p, aw_p)
+                y, w = y - dt * fy2, w - dt * fw2 + self.sigma * dWr
+                ay, aw = ay + dt * vy2, aw + dt * vw2
+                ap = [a + dt * v for a, v in zip(ap, vp2)]
+            elif method in ("euler_heun", "milstein"):
+                y, w = y - dt * fy, w - dt * fw + self.sigma * dWr
+                ay, aw = ay + dt * vy, aw + dt * vw
+                ap = [a + dt * v for a, v in zip(ap, vp)]
+            else:
+                raise ValueError(f"Unknown method: {method}")
+        return y, w, ay, aw, ap
+
     def forward(self, x, w0, w_layers, proj, increments, dt=0.05, method="midpoint"):
         """SDENet.forward (models.py:180-201): zero channels, solve, projection head, logqp = state[-1] / 2."""
         if self.aug_dim > 0:

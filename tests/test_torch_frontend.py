@@ -121,9 +121,11 @@ def test_sdenet_module_surface(built_lib):
             "ts", "aug_zeros"} <= keys
     assert m.params_size == m.y_net.P and float(m.w_net.linears()[-1].weight.abs().max()) == 0.0
     with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 2, 8, 8), adjoint=True)
+        m(torch.zeros(1, 2, 8, 8), adaptive=True)
     with pytest.raises(_lib.BsdeError):
         m(torch.zeros(1, 2, 8, 8))     # CPU tensor: no fallback
+    with pytest.raises(_lib.BsdeError):
+        m(torch.zeros(1, 2, 8, 8), adjoint=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU
@@ -285,3 +287,105 @@ def test_gpu_config5_full_size_properties(built_lib):
     assert torch.allclose(h[0], a[0][:B // 2], rtol=1e-5, atol=1e-6) and torch.equal(h[1], a[1])
     z = run(torch.zeros_like(x))
     assert torch.equal(z[1], a[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# `adjoint=True` (torchsde.sdeint_adjoint, models.py:194) -- O(1)-memory reverse pass
+# ---------------------------------------------------------------------------------------------------------------
+def _adjoint_case(seed=11):
+    g = torch.Generator().manual_seed(seed)
+    net = tp.SDENetOracle((2, 8, 8), (1, 1), (2, 8, 3), sigma=0.3, hidden_width=8, aug_dim=1)
+    dt64 = torch.float64
+    w0 = tp.init_y_params(net.ops, net.P, g, dt64)
+    wl = tp.init_w_net(net.P, net.hidden_sizes, g, dt64, last_std=0.05)
+    x = torch.randn(3, 3, 8, 8, generator=g, dtype=dt64)
+    cot = torch.randn(3, 3, 8, 8, generator=g, dtype=dt64)
+    fine = torch.randn(32, net.P, generator=g, dtype=dt64) * (1.0 / 32) ** 0.5      # one Brownian path, coarsened per step count
+    return net, w0, wl, x, cot, fine
+
+
+def test_oracle_sdenet_adjoint_converges_to_backprop():
+    """The restated `sdeint_adjoint` reverse pass against autograd through the oracle's own forward solve on one Brownian path:
+    midpoint reconstructs the initial state to third order and the gradients to second order in h, the Euler-type schemes to first
+    order (measured: y0_rec 2.7e-2 / 3.5e-3 / 4.3e-4 and dL/dw0 5.4e-2 / 1.1e-2 / 2.4e-3 relative at n = 4 / 8 / 16, midpoint)."""
+    net, w0, wl, x, cot, fine = _adjoint_case()
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    for method, order_rec, order_g in (("midpoint", 3, 2), ("euler_heun", 1, 1)):
+        errs = []
+        for n in (8, 16):
+            h = 1.0 / n
+            I = fine.reshape(n, 32 // n, net.P).sum(1)
+            xr, w0r = x.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+            wlr = [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in wl]
+            yr, wr, lr = net.solve(xr, w0r, wlr, I, dt=h, method=method)
+            gr = torch.autograd.grad((yr * cot).sum() + 0.7 * lr, [xr, w0r] + [t for p in wlr for t in p])
+            y0, w0_, ay, aw, ap = net.adjoint(yr.detach(), wr.detach(), cot, torch.zeros_like(w0), torch.tensor(0.7, dtype=x.dtype),
+                                              wl, I, dt=h, method=method)
+            errs.append((float((y0 - x).abs().max()), rel(aw, gr[1]), max(rel(a, b) for a, b in zip(ap, gr[2:]))))
+        (r0, g0, p0), (r1, g1, p1) = errs
+        assert r0 / r1 > 0.7 * 2 ** order_rec and g0 / g1 > 0.7 * 2 ** order_g and p0 / p1 > 0.7 * 2 ** order_g, (method, errs)
+        if method == "midpoint":
+            assert r1 < 1e-3 and g1 < 5e-3 and p1 < 5e-3, errs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,math_mode", [("midpoint", "fp32"), ("euler_heun", "fp32"), ("midpoint", "tc")])
+def test_gpu_sdenet_adjoint_matches_oracle(built_lib, method, math_mode):
+    """sdenet_solve_adjoint against the oracle's restated reverse pass with the same increments: forward values equal the plain route,
+    reconstructed initial state and every adjoint gradient 1e-3 (fp32) / 3e-2 (TF32) of the largest entry."""
+    from bayesde_b200 import torch_models as tm
+    net, w0, wl, x, cot, fine = _adjoint_case()
+    n = 8
+    h = 1.0 / n
+    I = fine.reshape(n, 32 // n, net.P).sum(1)
+    ynet, _ = tm.make_y_net(net.input_size, (1, 1), activation=net.activation, hidden_width=8, aug_dim=net.aug_dim)
+    cfg = tm.SolveConfig(ynet, 1, x.shape[0], n, h, method, net.sigma, net.hidden_sizes, "tanh", math_mode, False)
+    xd = x.float().permute(0, 2, 3, 1).contiguous()[None].to(DEV).requires_grad_(True)
+    w0d = w0.float().to(DEV).requires_grad_(True)
+    lin = [(W.float().to(DEV).requires_grad_(True), b.float().to(DEV).requires_grad_(True)) for W, b in wl]
+    y1, lq, wtraj = tm.sdenet_solve_adjoint(cfg, xd, w0d, lin, I.float().to(DEV)[None])
+    with torch.no_grad():
+        y1p, lqp, _ = tm.sdenet_solve(cfg, xd, w0d, lin, I.float().to(DEV)[None])
+    assert torch.equal(y1, y1p) and torch.equal(lq, lqp)
+    y1n = y1[0].permute(0, 3, 1, 2)
+    loss = (y1n * cot.float().to(DEV)).sum() + 0.7 * lq[0]
+    grads = torch.autograd.grad(loss, [xd, w0d] + [t for p in lin for t in p])
+    yr, wr, lr = net.solve(x, w0, wl, I, dt=h, method=method)
+    y0, w0r, ay, aw, ap = net.adjoint(yr, wr, cot, torch.zeros_like(w0), torch.tensor(0.7, dtype=x.dtype), wl, I, dt=h, method=method)
+    tol = 1e-3 if math_mode == "fp32" else 3e-2
+    Zy, Zw = tm.LAST_RECONSTRUCTION
+    _close(Zy[0].permute(0, 3, 1, 2), y0, tol, "reconstructed y0")
+    _close(Zw, w0r, tol, "reconstructed w0")
+    _close(grads[0][0].permute(0, 3, 1, 2), ay, tol, "dL/dx")
+    _close(grads[1], aw, tol, "dL/dw0")
+    for i, (a, b) in enumerate(zip(grads[2:], ap)):
+        _close(a, b, tol, f"dL/d w_net tensor {i}")
+
+
+@pytest.mark.gpu
+def test_gpu_sdenet_module_adjoint_flag(built_lib):
+    """SDENet.forward(adjoint=True): same logits / logqp as the plain route on the same path (replayed and in-kernel Philox), gradients
+    within the O(h^2) gap of the two reverse passes; the adaptive options still raise."""
+    from bayesde_b200 import torch_models as tm
+    torch.manual_seed(0)
+    m = tm.SDENet(input_size=(2, 8, 8), blocks=(1, 1), weight_network_sizes=(1, 8, 1), hidden_width=4, aug_dim=1, sigma=0.2, math="fp32").to(DEV)
+    with torch.no_grad():
+        last = m.w_net.linears()[-1]
+        last.weight.normal_(0, 0.05), last.bias.normal_(0, 0.05)
+    x = torch.randn(3, 2, 8, 8, device=DEV)
+    n = 16
+    outs = []
+    for adjoint in (False, True):
+        m.zero_grad()
+        m._calls = 0
+        logits, logqp = m(x, dt=1.0 / n, method="midpoint", adjoint=adjoint)      # in-kernel Philox path of call 1 in both
+        (logits.logsumexp(1).mean() + 1e-3 * logqp).backward()
+        outs.append((logits.detach(), logqp.detach(), {k: p.grad.clone() for k, p in m.named_parameters()}))
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-5) and torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-6)
+    for k in outs[0][2]:
+        a, b = outs[1][2][k], outs[0][2][k]
+        assert float((a - b).abs().max()) <= 2e-2 * float(b.abs().max()) + 1e-8, (k, float((a - b).abs().max()), float(b.abs().max()))
+    with pytest.raises(NotImplementedError):
+        m(x, adaptive=True)
+    with pytest.raises(NotImplementedError):
+        m(x, adjoint=True, adjoint_adaptive=True)
