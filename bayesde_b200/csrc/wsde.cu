@@ -262,7 +262,9 @@ __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
           const float dWv = A.dW ? __ldg(A.dW + ((long long)s * nit + k) * P + p)
                                  : sq * philox_normal(A.d.seed, (uint32_t)p, nidx, (uint32_t)(s + A.s_base), A.d.stream_id);
           klacc[s] += dtkl * A.d.kl_weight * u * u + ust * dWv;
-          const float wb = back ? A.wtraj[s * wstride + (long long)(k - back) * P + p] : w;
+          // base of the update: w_k, w_{k-1} (back = 1) or their average (back = 2: the corrector of a trapezoidal step)
+          const float wb = back == 1 ? A.wtraj[s * wstride + (long long)(k - 1) * P + p]
+                         : back == 2 ? 0.5f * (A.wtraj[s * wstride + (long long)(k - 1) * P + p] + w) : w;
           const float wn = wb + dt * dw + sigma * dWv;
           A.wtraj[s * wstride + (long long)(k + 1) * P + p] = wn;
 #pragma unroll
@@ -391,7 +393,8 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
           const float gwk = A.gw_traj ? __ldg(A.gw_traj + ((long long)s * nit + k) * P + p) : 0.f;
           // dL/dw_k without the first-layer term (added next iteration / epilogue)
           float gl = dt * A.ou_coef * lam + (A.ou_coef + 1.f) * gu + gwk;
-          if (back) A.ghold[(long long)s * P + p] = lam;   // the identity path of this update ends at w_{k-1}
+          if (back == 1) A.ghold[(long long)s * P + p] = lam;   // the identity path of this update ends at w_{k-1}
+          else if (back == 2) { A.ghold[(long long)s * P + p] = 0.5f * lam; gl += 0.5f * lam; }  // ... at (w_{k-1} + w_k)/2
           else gl += lam;
           if (hold_in) gl += A.ghold[(long long)s * P + p];
           A.glam[(long long)s * P + p] = gl;

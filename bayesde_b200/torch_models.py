@@ -270,7 +270,7 @@ class SolveConfig:
     """Static description of one SDENet solve: stage tables of the fixed-step scheme (include/bsde.h)."""
 
     def __init__(self, ynet, S, B, nsteps, h, method, sigma, hidden, w_act, math_mode, remat, t0=0.0):
-        if method not in ("midpoint", "euler_heun", "milstein"):
+        if method not in ("midpoint", "heun", "euler_heun", "milstein"):
             raise ValueError(f"Unknown method: {method}")
         self.ynet, self.S, self.B, self.n, self.h, self.method = ynet, S, B, nsteps, float(h), method
         self.sigma, self.hidden, self.w_act, self.math, self.remat = float(sigma), tuple(hidden), w_act, math_mode, remat
@@ -285,6 +285,14 @@ class SolveConfig:
             self.nscale = np.asarray([0.5 * math.sqrt(h), math.sqrt(h)] * nsteps, dtype=f32)
             self.nidx = np.asarray([k for k in range(nsteps) for _ in (0, 1)], dtype=np.int32)
             self.back = np.asarray([0, 1] * nsteps, dtype=np.int32)
+        elif method == "heun":     # torchsde heun (trapezoidal): y' = y + h f(t, y) + g I; y1 = y + h/2 (f(t, y) + f(t + h, y')) + g I
+            self.nit = 2 * nsteps      # = (y + y')/2 + h/2 f(t + h, y') + g I/2: the corrector starts from the average (back = 2)
+            self.tk = np.asarray([v for t in tk for v in (t, t + hh)], dtype=f32)
+            self.dtk = np.asarray([hh, f32(0.5) * hh] * nsteps, dtype=f32)
+            self.dtkl = np.asarray([f32(0.5) * hh, f32(0.5) * hh] * nsteps, dtype=f32)
+            self.nscale = np.asarray([math.sqrt(h), 0.5 * math.sqrt(h)] * nsteps, dtype=f32)
+            self.nidx = np.asarray([k for k in range(nsteps) for _ in (0, 1)], dtype=np.int32)
+            self.back = np.asarray([0, 2] * nsteps, dtype=np.int32)
         else:                      # constant diagonal g: euler_heun / milstein reduce to y + h f + g I
             self.nit = nsteps
             self.tk = np.asarray(tk, dtype=f32)
@@ -312,9 +320,13 @@ class SolveConfig:
 
     def stage_increments(self, I):
         """Per-stage noise [S, nit, P] from per-step increments I [S, nsteps, P]."""
-        if self.method != "midpoint":
+        if self.method == "midpoint":
+            pair = (0.5 * I, I)
+        elif self.method == "heun":
+            pair = (I, 0.5 * I)
+        else:
             return I.contiguous()
-        return torch.stack((0.5 * I, I), dim=2).reshape(I.shape[0], 2 * I.shape[1], I.shape[2]).contiguous()
+        return torch.stack(pair, dim=2).reshape(I.shape[0], 2 * I.shape[1], I.shape[2]).contiguous()
 
 
 class SDENetSolve(torch.autograd.Function):
@@ -352,16 +364,25 @@ class SDENetSolve(torch.autograd.Function):
         store = torch.empty(nit if keep else 1, nacts, device=dev, dtype=torch.float32)
         ys = torch.empty((n + 1,) + tuple(x.shape), device=dev, dtype=torch.float32)
         ys[0].copy_(x)
-        mid = cfg.method == "midpoint"
-        ymid = torch.empty((n,) + tuple(x.shape), device=dev, dtype=torch.float32) if mid else None
+        mid, heun = cfg.method == "midpoint", cfg.method == "heun"
+        two = mid or heun
+        ymid = torch.empty((n,) + tuple(x.shape), device=dev, dtype=torch.float32) if two else None   # y' of every step
         chw_in, chw_out = cfg.ynet.input_size, cfg.ynet.output_size
         wss = (nit + 1) * P
         tkh = cfg.tk
         for k in range(n):
-            j = 2 * k if mid else k
+            j = 2 * k if two else k
             a0 = store[j if keep else 0]
             chain_forward(desc, float(tkh[j]), wtraj[0, j], wss, ys[k], a0)
-            if mid:
+            if heun:
+                reinterp_axpy(ymid[k], chw_in, ys[k], cfg.h, a0[ooff:], chw_out)                   # y' = y + h f(t, y)
+                if k == 0:
+                    yavg = torch.empty_like(ys[0])
+                reinterp_axpy(yavg, chw_in, ys[k], 0.5 * cfg.h, a0[ooff:], chw_out)               # (y + y')/2 = y + h/2 f(t, y)
+                a1 = store[j + 1 if keep else 0]
+                chain_forward(desc, float(tkh[j + 1]), wtraj[0, j + 1], wss, ymid[k], a1)
+                reinterp_axpy(ys[k + 1], chw_in, yavg, 0.5 * cfg.h, a1[ooff:], chw_out)           # + h/2 f(t + h, y')
+            elif mid:
                 reinterp_axpy(ymid[k], chw_in, ys[k], 0.5 * cfg.h, a0[ooff:], chw_out)
                 a1 = store[j + 1 if keep else 0]
                 chain_forward(desc, float(tkh[j + 1]), wtraj[0, j + 1], wss, ymid[k], a1)
@@ -370,7 +391,7 @@ class SDENetSolve(torch.autograd.Function):
                 reinterp_axpy(ys[k + 1], chw_in, ys[k], cfg.h, a0[ooff:], chw_out)
         ctx.cfg, ctx.klayers, ctx.desc = cfg, klayers, desc
         ctx.store = store if keep else None
-        ctx.save_for_backward(wtraj, z1, ys, ymid if mid else ys)
+        ctx.save_for_backward(wtraj, z1, ys, ymid if two else ys)
         ctx.mark_non_differentiable(wtraj)
         return ys[n].clone(), kl, wtraj
 
@@ -399,8 +420,20 @@ class SDENetSolve(torch.autograd.Function):
                 return ctx.store[j]
             return chain_forward(desc, float(tkh[j]), wtraj[0, j], wss, x, scratch)   # recompute (remat)
 
+        heun = cfg.method == "heun"
         for k in range(n - 1, -1, -1):
-            if mid:
+            if heun:
+                j = 2 * k
+                # y_{k+1} = y_k + h/2 R(f(t, y_k, w_k)) + h/2 R(f(t + h, y', w'))
+                reinterp_axpy(gf, chw_out, None, 0.5 * cfg.h, gy, chw_in)
+                chain_backward(desc, float(tkh[j + 1]), wtraj[0, j + 1], wss, ymid[k], acts_of(j + 1, ymid[k]), gf, gyp, False,
+                               gw_traj[0, j + 1], gss)
+                # y' = y_k + h R(f(t, y_k, w_k)): f(t, y_k) receives h * dL/dy' + h/2 * dL/dy_{k+1}
+                gf2 = torch.empty_like(gf)
+                reinterp_axpy(gf2, chw_out, gf, cfg.h, gyp, chw_in)
+                gy.add_(gyp)
+                chain_backward(desc, float(tkh[j]), wtraj[0, j], wss, ys[k], acts_of(j, ys[k]), gf2, gy, True, gw_traj[0, j], gss)
+            elif mid:
                 j = 2 * k
                 # y_{k+1} = y_k + h R(f(t + h/2, y', w'))
                 reinterp_axpy(gf, chw_out, None, cfg.h, gy, chw_in)
@@ -509,15 +542,20 @@ class SDENetAdjointSolve(torch.autograd.Function):
                                  _lib.stream_ptr())
             _lib.check(st, "bsde_wsde_bwd")
             aw_new = r if aw_base is aw_at else r - aw_at + aw_base
-            if want_params:
-                torch._foreach_add_(gacc, [t for pair in gl for t in pair])
+            if want_params:  # weight of this stage's dt (df/dparams)^T a_at in the parameter adjoint (True = 1)
+                torch._foreach_add_(gacc, [t for pair in gl for t in pair], alpha=float(want_params))
             return Zy_new, Zw_new.contiguous(), ay_new, aw_new
 
         t0 = float(cfg.tk[0])
         for k in range(n - 1, -1, -1):
             tau = float(np.float32(t0) + np.float32(k + 1) * np.float32(h))
             dWr = (-I[0, k]).contiguous()
-            if mid:
+            if cfg.method == "heun":   # Z' = Z - h f(tau, Z) + g dW~;  Z1 = (Z + Z')/2 - h/2 f(tau - h, Z') + g dW~/2;  a likewise
+                Zy_p, Zw_p, ay_p, aw_p = stage(tau, h, Zy, Zy, Zw, Zw, dWr, a_y, a_y, a_w, a_w, 0.5)
+                tl = float(np.float32(t0) + np.float32(k) * np.float32(h))
+                Zy, Zw, a_y, a_w = stage(tl, 0.5 * h, 0.5 * (Zy + Zy_p), Zy_p, 0.5 * (Zw + Zw_p), Zw_p, 0.5 * dWr,
+                                         0.5 * (a_y + ay_p), ay_p, 0.5 * (a_w + aw_p), aw_p, 1.0)
+            elif mid:
                 Zy_p, Zw_p, ay_p, aw_p = stage(tau, 0.5 * h, Zy, Zy, Zw, Zw, 0.5 * dWr, a_y, a_y, a_w, a_w, False)
                 tm = float(np.float32(t0) + np.float32(k) * np.float32(h) + np.float32(0.5) * np.float32(h))
                 Zy, Zw, a_y, a_w = stage(tm, h, Zy, Zy_p, Zw, Zw_p, dWr, a_y, ay_p, a_w, aw_p, True)
@@ -605,7 +643,7 @@ class SDENet(nn.Module):
         solve = sdenet_solve_adjoint if adjoint else sdenet_solve  # models.py:194: sdeint_adjoint / sdeint
         y1, lq, _ = solve(cfg, x, self.flat_initial_params, lin, I, seed=self.seed, stream_id=self._calls)
         # f and g are each evaluated once per stage (models.py:161,172): 2 stages for midpoint; euler_heun evaluates g twice
-        self.nfe = nsteps * {"midpoint": 4, "euler_heun": 3, "milstein": 2}[method]
+        self.nfe = nsteps * {"midpoint": 4, "heun": 4, "euler_heun": 3, "milstein": 2}[method]
         y1 = y1[0].permute(0, 3, 1, 2)                                       # back to (B, C, H, W) order for Flatten
         logits = self.projection(y1.reshape(y1.shape[0], -1))
         logqp = .5 * lq[0]

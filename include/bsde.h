@@ -114,7 +114,9 @@ typedef struct {
    * torchbnn/_impl/models.py:184-197;  y' = y + dt/2 f(t,y) + g I/2,  y1 = y + dt f(t + dt/2, y') + g I):
    *     w_{j+1} = w_{j - back_j} + dt_j f_w(w_j, t_j) + sigma * noise_j ,   kl += dtkl_j * kl_weight * u(w_j)^2
    *     noise_j = d_dW[s][j][p]   or   nscale_j * N(0,1)[Philox counter (p, nidx_j, s, stream_id)]
-   * back_j in {0, 1}, back_0 = 0 and no two consecutive ones.  midpoint: dt = (h/2, h), dtkl = (0, h), nscale = (sqrt(h)/2, sqrt(h)),
+   * back_j in {0, 1, 2}, back_0 = 0 and no two consecutive non-zeros; back_j = 2 starts the update from the average
+   * (w_{j-1} + w_j)/2 -- the corrector of torchsde's trapezoidal `heun` (y' = y + h f(t,y) + g I, y1 = y + h/2 (f(t,y) + f(t+h,y')) + g I):
+   * dt = (h, h/2), dtkl = (h/2, h/2), nscale = (sqrt(h), sqrt(h)/2), nidx = (k, k), back = (0, 2).  midpoint: dt = (h/2, h), dtkl = (0, h), nscale = (sqrt(h)/2, sqrt(h)),
    * nidx = (k, k), back = (0, 1) for step k; the trajectory then holds w_k in slot 2k and the midpoint state in slot 2k+1. */
   const float* d_dtkl; const float* d_nscale; const int32_t* d_nidx; const int32_t* d_back;
 } bsde_wsde_desc;

@@ -170,6 +170,12 @@ class SDENetOracle:
                 fy2, fw2, fl2, _ = self.f_parts(tk + 0.5 * dt, y_p, w_p, w_layers)
                 y, w, lq = y + dt * fy2, w + dt * fw2 + self.sigma * I, lq + dt * fl2
                 path += [w_p, w]
+            elif method == "heun":
+                # torchsde heun (Stratonovich trapezoidal rule): y' = y + dt f(t, y) + g I; y1 = y + dt/2 (f(t, y) + f(t + dt, y')) + g I
+                y_p, w_p = y + dt * fy, w + dt * fw + self.sigma * I
+                fy2, fw2, fl2, _ = self.f_parts(tk + dt, y_p, w_p, w_layers)
+                y, w, lq = y + 0.5 * dt * (fy + fy2), w + 0.5 * dt * (fw + fw2) + self.sigma * I, lq + 0.5 * dt * (fl + fl2)
+                path += [w_p, w]
             elif method in ("euler_heun", "milstein"):
                 # constant diagonal g: g(t1, y') = g(t, y) and g dg = 0, so both reduce to the Euler update
                 y, w, lq = y + dt * fy, w + dt * fw + self.sigma * I, lq + dt * fl
@@ -218,6 +224,13 @@ class SDENetOracle:
                 y, w = y - dt * fy2, w - dt * fw2 + self.sigma * dWr
                 ay, aw = ay + dt * vy2, aw + dt * vw2
                 ap = [a + dt * v for a, v in zip(ap, vp2)]
+            elif method == "heun":
+                y_p, w_p = y - dt * fy, w - dt * fw + self.sigma * dWr
+                ay_p, aw_p = ay + dt * vy, aw + dt * vw
+                fy2, fw2, vy2, vw2, vp2 = F(tau - dt, y_p, w_p, ay_p, aw_p)
+                y, w = y - 0.5 * dt * (fy + fy2), w - 0.5 * dt * (fw + fw2) + self.sigma * dWr
+                ay, aw = ay + 0.5 * dt * (vy + vy2), aw + 0.5 * dt * (vw + vw2)
+                ap = [a + 0.5 * dt * (v + v2) for a, v, v2 in zip(ap, vp, vp2)]
             elif method in ("euler_heun", "milstein"):
                 y, w = y - dt * fy, w - dt * fw + self.sigma * dWr
                 ay, aw = ay + dt * vy, aw + dt * vw

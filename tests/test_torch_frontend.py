@@ -72,6 +72,12 @@ def test_oracle_midpoint_properties():
     ya, wa, la = net.solve(x, w0, wl, If, dt=1.0 / n, method="midpoint")
     yb, wb, lb = net.solve(x, w0, wl, If, dt=1.0 / n, method="euler_heun")
     assert (wa - wb).abs().max() < 5e-2 * wa.abs().max() and abs(la - lb) < 5e-2 * abs(la)
+    # heun (trapezoidal): on dw = -w it has the same stability polynomial as midpoint; on the full problem the two second-order
+    # schemes agree much more closely with each other than with the Euler-type ones
+    yh, wh, lh = net.solve(x, w0, wl0, I * 0, dt=h, method="heun")
+    assert torch.allclose(wh, w0 * (1 - h + h * h / 2) ** 4, rtol=1e-12) and lh.item() == 0.0
+    yc, wc, lc = net.solve(x, w0, wl, If, dt=1.0 / n, method="heun")
+    assert (wa - wc).abs().max() < 0.2 * (wa - wb).abs().max() and abs(la - lc) < 0.2 * abs(la - lb)
 
 
 def test_oracle_gradient_finite_differences():
@@ -169,7 +175,8 @@ def _run_gpu(net, w0, wl, x, I, h, method, math_mode, remat, seed_loss=3):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("method,math_mode,remat", [("midpoint", "fp32", False), ("midpoint", "fp32", True), ("euler_heun", "fp32", False),
-                                                   ("midpoint", "tc", False), ("milstein", "tc", True)])
+                                                   ("midpoint", "tc", False), ("milstein", "tc", True),
+                                                   ("heun", "fp32", False), ("heun", "fp32", True), ("heun", "tc", False)])
 def test_gpu_sdenet_solve_matches_oracle(built_lib, method, math_mode, remat):
     """State, w trajectory (all stages), logqp and every gradient of the fixed-step solve against the fp64 oracle with the
     same increments: two groups (ConvDownsample in the drift), aug channel, P -> 2 -> 8 -> 3 -> P w-net."""
@@ -310,7 +317,7 @@ def test_oracle_sdenet_adjoint_converges_to_backprop():
     order (measured: y0_rec 2.7e-2 / 3.5e-3 / 4.3e-4 and dL/dw0 5.4e-2 / 1.1e-2 / 2.4e-3 relative at n = 4 / 8 / 16, midpoint)."""
     net, w0, wl, x, cot, fine = _adjoint_case()
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
-    for method, order_rec, order_g in (("midpoint", 3, 2), ("euler_heun", 1, 1)):
+    for method, order_rec, order_g in (("midpoint", 3, 2), ("heun", 2, 2), ("euler_heun", 1, 1)):
         errs = []
         for n in (8, 16):
             h = 1.0 / n
@@ -329,7 +336,7 @@ def test_oracle_sdenet_adjoint_converges_to_backprop():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("method,math_mode", [("midpoint", "fp32"), ("euler_heun", "fp32"), ("midpoint", "tc")])
+@pytest.mark.parametrize("method,math_mode", [("midpoint", "fp32"), ("euler_heun", "fp32"), ("midpoint", "tc"), ("heun", "fp32")])
 def test_gpu_sdenet_adjoint_matches_oracle(built_lib, method, math_mode):
     """sdenet_solve_adjoint against the oracle's restated reverse pass with the same increments: forward values equal the plain route,
     reconstructed initial state and every adjoint gradient 1e-3 (fp32) / 3e-2 (TF32) of the largest entry."""
