@@ -14,7 +14,7 @@ FW_MAX_EDGE = 4
 FW_MAX_HID = 256
 MAX_LAYERS = 4
 
-ACT = {"softplus": 0, "tanh": 1, "elu": 2, "none": 3}
+ACT = {"softplus": 0, "tanh": 1, "elu": 2, "none": 3, "rbf": 4}
 METHOD = {"euler_maruyama": 0, "milstein": 1, "euler_heun": 2}
 MATH = {"fp32": 0, "tc": 1}
 EPI_BIAS, EPI_BIAS_ACT, EPI_EULER, EPI_DACT, EPI_ACCUM = range(5)

@@ -47,6 +47,8 @@ def _act(name, x):
         return torch.tanh(x)
     if name == "elu":
         return F.elu(x)
+    if name == "rbf":
+        return torch.exp(-x ** 2)
     raise NotImplementedError(f"activation {name!r} is not available in the fused B200 path")
 
 
@@ -71,7 +73,7 @@ def MLP(hidden_dims=(1, 64, 1), actfn="softplus", xt=False, ou_dw=False, p_scale
         raise NotImplementedError("MLP(xt=False): the fused path implements the time-dependent f_w only")
     if p_scale != -1.0:
         raise NotImplementedError("p_scale: arch.Exp is undefined in the reference (arch.py:65)")
-    if actfn not in ("softplus", "tanh", "elu"):
+    if actfn not in ("softplus", "tanh", "elu", "rbf"):
         raise NotImplementedError(f"fw_actfn={actfn!r} is not available in the fused B200 path")
     if len(hidden_dims) < 1 or len(hidden_dims) > _lib.FW_MAX_MID + 1:
         raise ValueError(f"len(hidden_dims) must be in 1..{_lib.FW_MAX_MID + 1}")
@@ -133,7 +135,7 @@ class FxSpec:
     """Conv stack of one SDEBNN block for a fixed NHWC input shape."""
 
     def __init__(self, block_type, input_shape, fx_dim, fx_actfn):
-        if fx_actfn not in ("softplus", "tanh", "elu"):
+        if fx_actfn not in ("softplus", "tanh", "elu", "rbf"):
             raise NotImplementedError(f"fx_actfn={fx_actfn!r} is not available in the fused B200 path")
         _, H, W, C = input_shape
         self.block_type, self.fx_dim, self.actfn = block_type, fx_dim, fx_actfn

@@ -159,7 +159,7 @@ static int xpath_check(const bsde_xpath_desc* d) {
   BSDE_CHECK_ARG(d != nullptr, "NULL descriptor");
   BSDE_CHECK_ARG(d->nlayers >= 2 && d->nlayers <= BSDE_MAX_LAYERS, "nlayers=%d unsupported", d->nlayers);
   BSDE_CHECK_ARG(d->S >= 1 && d->B >= 1 && d->nit >= 1, "S, B, nit must be positive");
-  BSDE_CHECK_ARG(d->act >= BSDE_ACT_SOFTPLUS && d->act <= BSDE_ACT_ELU, "fx activation %d unsupported", d->act);
+  BSDE_CHECK_ARG((d->act >= BSDE_ACT_SOFTPLUS && d->act <= BSDE_ACT_ELU) || d->act == BSDE_ACT_RBF, "fx activation %d unsupported", d->act);
   const bsde_conv_layer& L0 = d->layers[0];
   const bsde_conv_layer& Ln = d->layers[d->nlayers - 1];
   BSDE_CHECK_ARG(L0.cin == Ln.cout && L0.hin == Ln.hout && L0.win == Ln.wout,

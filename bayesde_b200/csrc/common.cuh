@@ -30,8 +30,19 @@ void count_launch(int n = 1);  // bookkeeping for bsde_launch_count()
 
 // ---- activations (brax/_impl/arch.py:31-32; torch.nn.Softplus threshold 20 is also what
 // jax.nn.softplus = logaddexp(x,0) evaluates to in fp32 for x > 20) -------------------------------
+// rbf (exp(-x^2), arch.py:31) as the conv epilogues store it: the sign of the pre-activation rides in the last mantissa bit
+__device__ __forceinline__ float rbf_fwd_tagged(float x) {
+  const uint32_t b = (__float_as_uint(expf(-x * x)) & ~1u) | (x < 0.f ? 1u : 0u);
+  return __uint_as_float(b);
+}
+// d/dx exp(-x^2) = -2 x a from the tagged output a
+__device__ __forceinline__ float rbf_grad_from_tagged(float a) {
+  const float ax = sqrtf(fmaxf(-logf(a), 0.f));
+  return (__float_as_uint(a) & 1u) ? 2.f * ax * a : -2.f * ax * a;
+}
 __device__ __forceinline__ float act_fwd(int act, float x) {
   switch (act) {
+    case BSDE_ACT_RBF: return expf(-x * x);
     case BSDE_ACT_SOFTPLUS: return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
     case BSDE_ACT_TANH: return tanhf(x);
     case BSDE_ACT_ELU: return x > 0.f ? x : expm1f(x);
@@ -44,6 +55,7 @@ __device__ __forceinline__ float act_grad_from_out(int act, float a) {
     case BSDE_ACT_SOFTPLUS: return -expm1f(-a);  // sigmoid(x) = 1 - exp(-softplus(x))
     case BSDE_ACT_TANH: return 1.f - a * a;
     case BSDE_ACT_ELU: return a > 0.f ? 1.f : a + 1.f;
+    case BSDE_ACT_RBF: return rbf_grad_from_tagged(a);
     default: return 1.f;
   }
 }
@@ -53,6 +65,7 @@ __device__ __forceinline__ float act_grad(int act, float x) {
     case BSDE_ACT_SOFTPLUS: return 1.f / (1.f + expf(-x));
     case BSDE_ACT_TANH: { float a = tanhf(x); return 1.f - a * a; }
     case BSDE_ACT_ELU: return x > 0.f ? 1.f : expf(x);
+    case BSDE_ACT_RBF: return -2.f * x * expf(-x * x);
     default: return 1.f;
   }
 }

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) conv_gather_kernel(ConvArgs a) {
       const float b = (a.b_off >= 0 && a.epi <= BSDE_EPI_EULER) ? __ldg(w + a.b_off + n) : 0.f;
       switch (a.epi) {
         case BSDE_EPI_BIAS: v = v + b; break;
-        case BSDE_EPI_BIAS_ACT: v = act_fwd(a.act, v + b); break;
+        case BSDE_EPI_BIAS_ACT: v = a.act == BSDE_ACT_RBF ? rbf_fwd_tagged(v + b) : act_fwd(a.act, v + b); break;
         case BSDE_EPI_EULER: v = aux[o] + a.scale * (v + b); break;
         case BSDE_EPI_DACT: v = a.scale * v * act_grad_from_out(a.act, aux[o]); break;
         case BSDE_EPI_ACCUM: v = aux[o] + a.scale * v; break;

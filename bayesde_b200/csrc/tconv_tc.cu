@@ -248,6 +248,7 @@ __device__ __forceinline__ float tc_act_fwd(int act, float x) {
     case BSDE_ACT_SOFTPLUS: return x > 15.f ? x : __logf(1.f + __expf(x));
     case BSDE_ACT_TANH: return tanhf(x);
     case BSDE_ACT_ELU: return x > 0.f ? x : __expf(x) - 1.f;
+    case BSDE_ACT_RBF: return rbf_fwd_tagged(x);
     default: return x;
   }
 }
@@ -256,6 +257,7 @@ __device__ __forceinline__ float tc_act_grad_out(int act, float a) {
     case BSDE_ACT_SOFTPLUS: return 1.f - __expf(-a);
     case BSDE_ACT_TANH: return 1.f - a * a;
     case BSDE_ACT_ELU: return a > 0.f ? 1.f : a + 1.f;
+    case BSDE_ACT_RBF: return rbf_grad_from_tagged(a);
     default: return 1.f;
   }
 }

@@ -168,6 +168,7 @@ __device__ __forceinline__ float wn_act_fwd(float x) {
   }
   if (ACT == BSDE_ACT_TANH) return tanhf(x);
   if (ACT == BSDE_ACT_ELU) return x > 0.f ? x : wn_ex2(1.44269504f * x) - 1.f;
+  if (ACT == BSDE_ACT_RBF) return rbf_fwd_tagged(x);
   return x;
 }
 template <int ACT>
@@ -175,6 +176,7 @@ __device__ __forceinline__ float wn_act_grad_out(float a) {
   if (ACT == BSDE_ACT_SOFTPLUS) return 1.f - wn_ex2(-1.44269504f * a);
   if (ACT == BSDE_ACT_TANH) return 1.f - a * a;
   if (ACT == BSDE_ACT_ELU) return a > 0.f ? 1.f : a + 1.f;
+  if (ACT == BSDE_ACT_RBF) return rbf_grad_from_tagged(a);
   return 1.f;
 }
 // second half of the epilogue (needs the value already stored at the output position)
@@ -961,10 +963,12 @@ static int win_launch_one(const bsde_conv_layer* L, int S, int B, const float* i
   WN_PICK(BSDE_EPI_BIAS_ACT, BSDE_ACT_SOFTPLUS)
   WN_PICK(BSDE_EPI_BIAS_ACT, BSDE_ACT_TANH)
   WN_PICK(BSDE_EPI_BIAS_ACT, BSDE_ACT_ELU)
+  WN_PICK(BSDE_EPI_BIAS_ACT, BSDE_ACT_RBF)
   WN_PICK(BSDE_EPI_BIAS_ACT, BSDE_ACT_NONE)
   WN_PICK(BSDE_EPI_DACT, BSDE_ACT_SOFTPLUS)
   WN_PICK(BSDE_EPI_DACT, BSDE_ACT_TANH)
   WN_PICK(BSDE_EPI_DACT, BSDE_ACT_ELU)
+  WN_PICK(BSDE_EPI_DACT, BSDE_ACT_RBF)
   WN_PICK(BSDE_EPI_DACT, BSDE_ACT_NONE)
 #undef WN_PICK
   BSDE_CHECK_ARG(fn != nullptr, "epilogue %d / activation %d not instantiated", epi, act);

@@ -530,7 +530,7 @@ static int fill_tiny(const bsde_fw_params* fw, TinyDims& td) {
   td.wsum = off;
   BSDE_CHECK_ARG(fw->dims[0] <= ME && fw->dims[fw->nhid - 1] <= ME,
                  "first/last hidden widths must be <= %d (got %d, %d)", ME, fw->dims[0], fw->dims[fw->nhid - 1]);
-  BSDE_CHECK_ARG(fw->act >= BSDE_ACT_SOFTPLUS && fw->act <= BSDE_ACT_NONE, "bad fw activation %d", fw->act);
+  BSDE_CHECK_ARG(fw->act >= BSDE_ACT_SOFTPLUS && fw->act <= BSDE_ACT_RBF, "bad fw activation %d", fw->act);
   return 0;
 }
 

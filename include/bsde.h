@@ -59,7 +59,10 @@ typedef enum {
 } bsde_status;
 
 /* activations: brax/_impl/arch.py:31-32 ACTFNS (swish carries trainable state: unsupported here) */
-typedef enum { BSDE_ACT_SOFTPLUS = 0, BSDE_ACT_TANH = 1, BSDE_ACT_ELU = 2, BSDE_ACT_NONE = 3 } bsde_act;
+/* BSDE_ACT_RBF = exp(-x^2) (brax/_impl/arch.py:31).  Its derivative -2 x a needs the sign of the pre-activation, which the output
+ * a = exp(-x^2) does not determine: the conv epilogues store a with the sign of x in the LAST MANTISSA BIT (a perturbation of at most
+ * one ulp of the stored activation) and the data-gradient epilogues read it back: x = (bit ? -1 : 1) * sqrt(-ln a). */
+typedef enum { BSDE_ACT_SOFTPLUS = 0, BSDE_ACT_TANH = 1, BSDE_ACT_ELU = 2, BSDE_ACT_NONE = 3, BSDE_ACT_RBF = 4 } bsde_act;
 
 typedef enum { BSDE_EULER_MARUYAMA = 0, BSDE_MILSTEIN = 1, BSDE_EULER_HEUN = 2 } bsde_method;
 
