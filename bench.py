@@ -206,6 +206,40 @@ def cpu_reference_images_per_s(args, steps, warmup):
     return value, cores, sample, t_step
 
 
+def cpu_torch_reference_images_per_s(batch):
+    """The torch-CPU leg of the north star: one training step of config 5 (torchbnn SDENet, 3x32x32, blocks 2-2-2, hidden 32, w-net
+    1-128-1, midpoint dt 0.05) through the oracle's restatement of the torch path (SDENet as shipped raises: quirk Q7; torchsde is
+    absent), all host threads, bounded sample: 1 warm-up + 1 timed step at `batch` images."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import torch_path as tp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    net = tp.SDENetOracle((3, 32, 32), (2, 2, 2), (1, 128, 1), sigma=0.1, hidden_width=32)
+    gg = torch.Generator().manual_seed(0)
+    w0 = tp.init_y_params(net.ops, net.P, gg).requires_grad_(True)
+    wl = [(W.requires_grad_(True), b.requires_grad_(True)) for W, b in tp.init_w_net(net.P, net.hidden_sizes, gg, last_std=1e-2)]
+    feat = int(net.output_size[0] * net.output_size[1] * net.output_size[2])
+    proj = [((torch.randn(1024, feat, generator=gg) * 0.01).requires_grad_(True), torch.zeros(1024, requires_grad=True)),
+            ((torch.randn(10, 1024, generator=gg) * 0.01).requires_grad_(True), torch.zeros(10, requires_grad=True))]
+    leaves = [w0] + [t for pr in wl for t in pr] + [t for pr in proj for t in pr]
+    opt = torch.optim.Adam(leaves, lr=1e-3)
+    xc = torch.randn(batch, 3, 32, 32, generator=gg)
+    yc = torch.randint(0, 10, (batch,), generator=gg)
+    ts = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        I = torch.randn(20, net.P, generator=gg) * 0.05 ** 0.5
+        opt.zero_grad()
+        lo, lq = net.forward(xc, w0, wl, proj, I, dt=0.05)
+        (F.cross_entropy(lo, yc) + 1e-4 * lq).backward()
+        opt.step()
+        ts.append(time.perf_counter() - t0)
+    sample = (f"1 warm-up + 1 timed train step (fwd+bwd+Adam, 40 drift evaluations) of oracle/torch_path.py at {batch} images, "
+              f"{ts[-1]:.2f} s/step")
+    return batch / ts[-1], cores, sample
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -383,6 +417,12 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample, _ = cpu_reference_images_per_s(args, 2, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        try:  # the second CPU leg the north star names (torch front end, config 5); reported beside, not a ratio input
+            v5, cores5, sample5 = cpu_torch_reference_images_per_s(args.cpu_batch)
+            line["cpu_baseline_torch"] = {"value": v5, "unit": "images/s (config 5: torchbnn SDENet, midpoint dt 0.05, 1 weight sample)",
+                                          "cores": cores5, "kind": "port", "sample": sample5}
+        except Exception as e:  # noqa: BLE001 -- a reporting extra must not cost the bench line
+            line["cpu_baseline_torch"] = {"unavailable": repr(e)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
