@@ -368,6 +368,8 @@ def run_ours(args):
     nit = MODEL_KW["nsteps"] - 1
     alg_flops_step = 3.0 * fl_eval * nit * B * args.nsamples  # fwd + dgrad + wgrad (recompute not counted)
     conv_ms = (ktime.get("k2_fwd", 0.0) + ktime.get("k3_bwd", 0.0)) / args.steps
+    hbm_bytes_step = (by_fwd + by_bwd) * nit * B * args.nsamples
+    hbm_achieved = hbm_bytes_step / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
     achieved = alg_flops_step / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     # K1 (weight-SDE) against the 48*P HBM model of SURVEY.md 8.4 (fwd) and 2x for the reverse pass
     sumP = sum(blk[0].numel() for blk in model.block_params())
@@ -382,30 +384,34 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "K2/K3 time-dependent conv stack (conv_win_kernel / wgrad_win_kernel + "
-                               "conv_tc / wgrad_tc fallbacks; tcgen05 kind::tf32)",
-                     "achieved": achieved, "peak": tf32_peak or peak_tf, "unit": "TFLOP/s", "frac": achieved / (tf32_peak or peak_tf),
-                     "peak_source": ("measured live in this run: cuBLAS 8192^3 TF32 matmul (the kernels issue tcgen05 kind::tf32; "
-                                     "MEASURED_PEAKS.json holds no TF32 figure, SURVEY 8.4)" if tf32_peak else peak_src),
-                     "peak_bf16_sustained": peak_tf, "frac_of_bf16_peak": achieved / peak_tf,
+        # The conv stack sits on the MEMORY side of the ridge: 10.2 PFLOP / 230 GB per step = 44 FLOP/B against a ridge of
+        # (TF32 peak 748 TFLOP/s) / (6.55 TB/s) = 114 FLOP/B (byte floor 35 ms > flop floor 13.7 ms), so the bounding roofline of the
+        # dominant kernels (conv_win / wgrad_win, 79 % of the step in the ncu launch list) is HBM; the tensor-pipe view is kept beside it.
+        "roofline": {"bound": "hbm", "kernel": "K2/K3 time-dependent conv stack (conv_win_kernel / wgrad_win_kernel + conv_tc / wgrad_tc "
+                                                "fallbacks), all launches of a step",
+                     "achieved": hbm_achieved, "peak": peak_hbm, "unit": "GB/s", "frac": hbm_achieved / peak_hbm,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel with the largest share of the
                      # step (wgrad_win_kernel, 29 %: 5->64 weight gradient, 1024 images 32x32), ncu --set full capture
                      # profiles/r01j_wgrad_win_full_summary.csv: 289.8 MB read + 3.9 MB written = the algorithmic bytes
-                     # (dY 268.4 MB + input 21.0 MB read once, partial tiles 3.5 MB)
+                     # (dY 268.4 MB + input 21.0 MB read once, partial tiles 3.5 MB); the eight group-0 conv_win launches
+                     # likewise move exactly their algorithmic bytes (profiles/r01k_conv_win_full_summary.csv)
                      "traffic": 293.7e6,
-                     "algorithmic_flops_per_step": alg_flops_step, "kernel_ms_per_step": conv_ms,
-                     "share_of_step": conv_ms / (ms / args.steps)},
-        # the same conv launches against HBM: with fp32 NHWC activations and one launch per layer the byte floor
-        # (bytes / hbm_gbs) is ABOVE the flop floor (flops / tensor peak), i.e. this decomposition is HBM-bound
-        "roofline_hbm": {"bound": "hbm", "kernel": "the same K2/K3 conv launches",
-                         "achieved": (by_fwd + by_bwd) * nit * B * args.nsamples / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0,
-                         "peak": peak_hbm, "unit": "GB/s",
-                         "frac": ((by_fwd + by_bwd) * nit * B * args.nsamples / (conv_ms * 1e-3) / 1e9 / peak_hbm) if conv_ms > 0 else 0.0,
-                         "algorithmic_bytes_per_step": (by_fwd + by_bwd) * nit * B * args.nsamples,
-                         "byte_floor_ms": (by_fwd + by_bwd) * nit * B * args.nsamples / (peak_hbm * 1e9) * 1e3,
-                         "flop_floor_ms": alg_flops_step / ((tf32_peak or peak_tf) * 1e12) * 1e3,
-                         "note": "every layer reads its fp32 NHWC input once and writes its output once; dgrad also reads the "
-                                 "activation it differentiates; wgrad reads layer input + dy"},
+                     "algorithmic_bytes_per_step": hbm_bytes_step, "kernel_ms_per_step": conv_ms,
+                     "share_of_step": conv_ms / (ms / args.steps),
+                     "byte_floor_ms": hbm_bytes_step / (peak_hbm * 1e9) * 1e3,
+                     "flop_floor_ms": alg_flops_step / ((tf32_peak or peak_tf) * 1e12) * 1e3,
+                     "arithmetic_intensity_flop_per_byte": alg_flops_step / hbm_bytes_step,
+                     "ridge_flop_per_byte": (tf32_peak or peak_tf) * 1e12 / (peak_hbm * 1e9),
+                     "note": "algorithmic bytes: every layer reads its fp32 NHWC input once and writes its output once; dgrad also "
+                             "reads the activation it differentiates; wgrad reads layer input + dy.  achieved = those bytes / "
+                             "CUDA-event time of the x-path calls (K2 forward + K3 reverse) on the launching stream"},
+        "roofline_tensor": {"bound": "tensor", "kernel": "the same K2/K3 conv launches (tcgen05 kind::tf32)",
+                            "achieved": achieved, "peak": tf32_peak or peak_tf, "unit": "TFLOP/s", "frac": achieved / (tf32_peak or peak_tf),
+                            "peak_source": ("measured live in this run: cuBLAS 8192^3 TF32 matmul (the kernels issue tcgen05 kind::tf32; "
+                                            "MEASURED_PEAKS.json holds no TF32 figure, SURVEY 8.4)" if tf32_peak else peak_src),
+                            "peak_bf16_sustained": peak_tf, "frac_of_bf16_peak": achieved / peak_tf,
+                            "algorithmic_flops_per_step": alg_flops_step},
         "roofline_k1": {"bound": "hbm", "kernel": "K1 wsde_fwd/bwd (cooperative persistent)",
                         "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0, "peak": peak_hbm,
                         "unit": "GB/s", "frac": (k1_bytes / (k1_ms * 1e-3) / 1e9 / peak_hbm) if k1_ms > 0 else 0.0,
