@@ -574,3 +574,33 @@ def test_gpu_block_adjoint_full_size_vs_backprop(built_lib):
             bad.append((name, cos, float(a.norm() / b.norm())))
     assert not bad, bad
     assert mem_a < 0.35 * mem_b, (mem_a, mem_b)
+
+
+@pytest.mark.gpu
+def test_gpu_classifier_with_stochastic_adjoint(built_lib):
+    """The whole network (Augment -> SDEBNN blocks -> SqueezeDownsample -> mean-field head, examples/jax/sdebnn_classification.py)
+    with `fixed_grid=False` passed through `bnn_serial` to every block, as the reference's apply_fun accepts it (brax.py:97,112-116):
+    deterministic for a given seed, finite loss, gradients reach every parameter; a small step gives nearly the fixed-grid KL scale."""
+    from bayesde_b200.classification import SDEBNNClassifier
+    dev = "cuda:0"
+    model = SDEBNNClassifier(input_size=(8, 8, 3), aug=1, nblocks=(1, 1), fx_dim=8, fw_dims=(2, 8, 2), diff_coef=1e-2, nsteps=5,
+                             nsamples=2, w_init=1e-2, b_init=1e-2, math="fp32", seed=0, device=dev)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4, 8, 8, 3, generator=g).to(dev)
+    labels = torch.randint(0, 10, (4,), generator=g).to(dev)
+    xs = x.unsqueeze(0).expand(2, *x.shape).contiguous()
+
+    def run(seed):
+        logp, kl, _ = model._predict(model.params(), xs, rng=seed, mc_samples=2, fixed_grid=False, dt=0.05)
+        nll = -logp.gather(-1, labels.view(1, -1, 1).expand(2, -1, 1)).squeeze(-1).mean(dim=1)
+        return logp, kl, (nll + 1e-6 * kl).mean()
+
+    logp, kl, loss = run(3)
+    assert logp.shape == (2, 4, 10) and torch.isfinite(loss) and torch.isfinite(kl).all() and (kl > 0).all()
+    loss.backward()
+    for i, p in enumerate(model.parameters()):
+        assert p.grad is not None and torch.isfinite(p.grad).all(), i
+    assert sum(float(p.grad.abs().max()) > 0 for p in model.parameters()) >= len(list(model.parameters())) - 2
+    logp2, kl2, _ = run(3)
+    logp3, _, _ = run(4)
+    assert torch.equal(logp, logp2) and torch.equal(kl, kl2) and not torch.equal(logp, logp3)
