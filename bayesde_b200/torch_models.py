@@ -11,8 +11,9 @@ through strides) and `bsde_nchw_reinterp_axpy` (the flat-NCHW-order state update
 `loss.backward()` through `torchsde.sdeint` (examples/torch/sdebnn_classification.py:34-46).
 
 Semantics follow the INTENDED flat-state reading of `SDENet` (the class as shipped raises in `split`/`cat`: SURVEY
-quirk Q7).  `adjoint=True` selects the O(1)-memory reverse pass of `sdeint_adjoint` (SDENetAdjointSolve); `adaptive=True` /
-`adjoint_adaptive=True` raise NotImplementedError.  There is no CPU path.
+quirk Q7).  `adjoint=True` selects the O(1)-memory reverse pass of `sdeint_adjoint` (SDENetAdjointSolve); `adaptive=True` runs torchsde's
+step-doubling controller and replays the accepted grid; `adjoint_adaptive=True` (and adaptive + adjoint together) raise
+NotImplementedError.  There is no CPU path.
 """
 import ctypes as C
 import math
@@ -267,36 +268,46 @@ def _plain_fw_struct(klayers, P, hidden, actfn):
 
 
 class SolveConfig:
-    """Static description of one SDENet solve: stage tables of the fixed-step scheme (include/bsde.h)."""
+    """Static description of one SDENet solve: stage tables of the fixed-step scheme (include/bsde.h).  `grid` = (t_k, h_k) lists
+    replaces the uniform grid t0 + k h (the accepted steps of an adaptive solve)."""
 
-    def __init__(self, ynet, S, B, nsteps, h, method, sigma, hidden, w_act, math_mode, remat, t0=0.0):
+    def __init__(self, ynet, S, B, nsteps, h, method, sigma, hidden, w_act, math_mode, remat, t0=0.0, grid=None):
         if method not in ("midpoint", "heun", "euler_heun", "milstein"):
             raise ValueError(f"Unknown method: {method}")
-        self.ynet, self.S, self.B, self.n, self.h, self.method = ynet, S, B, nsteps, float(h), method
-        self.sigma, self.hidden, self.w_act, self.math, self.remat = float(sigma), tuple(hidden), w_act, math_mode, remat
         f32 = np.float32
-        hh = f32(h)
-        tk = [f32(t0) + f32(k) * hh for k in range(nsteps)]
+        if grid is not None:
+            tk, hs = [f32(t) for t in grid[0]], [f32(v) for v in grid[1]]
+            nsteps, h = len(tk), float(hs[0]) if len(hs) else 0.0
+        else:
+            hh = f32(h)
+            tk, hs = [f32(t0) + f32(k) * hh for k in range(nsteps)], [hh] * nsteps
+        self.ynet, self.S, self.B, self.n, self.h, self.method = ynet, S, B, nsteps, float(h), method
+        self.hs = [float(v) for v in hs]
+        self.uniform = grid is None
+        self.sigma, self.hidden, self.w_act, self.math, self.remat = float(sigma), tuple(hidden), w_act, math_mode, remat
+        half = f32(0.5)
+        sq = [math.sqrt(float(v)) for v in hs]
+        pairs = lambda a, b: np.asarray([v for k in range(nsteps) for v in (a(k), b(k))], dtype=f32)
         if method == "midpoint":   # torchsde midpoint: f at (t, y) and (t + h/2, y'), the same increment I in both stages
             self.nit = 2 * nsteps
-            self.tk = np.asarray([v for t in tk for v in (t, t + f32(0.5) * hh)], dtype=f32)
-            self.dtk = np.asarray([f32(0.5) * hh, hh] * nsteps, dtype=f32)
-            self.dtkl = np.asarray([0.0, hh] * nsteps, dtype=f32)
-            self.nscale = np.asarray([0.5 * math.sqrt(h), math.sqrt(h)] * nsteps, dtype=f32)
+            self.tk = pairs(lambda k: tk[k], lambda k: tk[k] + half * hs[k])
+            self.dtk = pairs(lambda k: half * hs[k], lambda k: hs[k])
+            self.dtkl = pairs(lambda k: 0.0, lambda k: hs[k])
+            self.nscale = pairs(lambda k: 0.5 * sq[k], lambda k: sq[k])
             self.nidx = np.asarray([k for k in range(nsteps) for _ in (0, 1)], dtype=np.int32)
             self.back = np.asarray([0, 1] * nsteps, dtype=np.int32)
         elif method == "heun":     # torchsde heun (trapezoidal): y' = y + h f(t, y) + g I; y1 = y + h/2 (f(t, y) + f(t + h, y')) + g I
             self.nit = 2 * nsteps      # = (y + y')/2 + h/2 f(t + h, y') + g I/2: the corrector starts from the average (back = 2)
-            self.tk = np.asarray([v for t in tk for v in (t, t + hh)], dtype=f32)
-            self.dtk = np.asarray([hh, f32(0.5) * hh] * nsteps, dtype=f32)
-            self.dtkl = np.asarray([f32(0.5) * hh, f32(0.5) * hh] * nsteps, dtype=f32)
-            self.nscale = np.asarray([math.sqrt(h), 0.5 * math.sqrt(h)] * nsteps, dtype=f32)
+            self.tk = pairs(lambda k: tk[k], lambda k: tk[k] + hs[k])
+            self.dtk = pairs(lambda k: hs[k], lambda k: half * hs[k])
+            self.dtkl = pairs(lambda k: half * hs[k], lambda k: half * hs[k])
+            self.nscale = pairs(lambda k: sq[k], lambda k: 0.5 * sq[k])
             self.nidx = np.asarray([k for k in range(nsteps) for _ in (0, 1)], dtype=np.int32)
             self.back = np.asarray([0, 2] * nsteps, dtype=np.int32)
         else:                      # constant diagonal g: euler_heun / milstein reduce to y + h f + g I
             self.nit = nsteps
             self.tk = np.asarray(tk, dtype=f32)
-            self.dtk = np.full(nsteps, hh, dtype=f32)
+            self.dtk = np.asarray(hs, dtype=f32)
             self.dtkl = self.nscale = self.nidx = self.back = None
         self._dev = {}
 
@@ -371,24 +382,25 @@ class SDENetSolve(torch.autograd.Function):
         wss = (nit + 1) * P
         tkh = cfg.tk
         for k in range(n):
+            hk = cfg.hs[k]
             j = 2 * k if two else k
             a0 = store[j if keep else 0]
             chain_forward(desc, float(tkh[j]), wtraj[0, j], wss, ys[k], a0)
             if heun:
-                reinterp_axpy(ymid[k], chw_in, ys[k], cfg.h, a0[ooff:], chw_out)                   # y' = y + h f(t, y)
+                reinterp_axpy(ymid[k], chw_in, ys[k], hk, a0[ooff:], chw_out)                      # y' = y + h f(t, y)
                 if k == 0:
                     yavg = torch.empty_like(ys[0])
-                reinterp_axpy(yavg, chw_in, ys[k], 0.5 * cfg.h, a0[ooff:], chw_out)               # (y + y')/2 = y + h/2 f(t, y)
+                reinterp_axpy(yavg, chw_in, ys[k], 0.5 * hk, a0[ooff:], chw_out)                  # (y + y')/2 = y + h/2 f(t, y)
                 a1 = store[j + 1 if keep else 0]
                 chain_forward(desc, float(tkh[j + 1]), wtraj[0, j + 1], wss, ymid[k], a1)
-                reinterp_axpy(ys[k + 1], chw_in, yavg, 0.5 * cfg.h, a1[ooff:], chw_out)           # + h/2 f(t + h, y')
+                reinterp_axpy(ys[k + 1], chw_in, yavg, 0.5 * hk, a1[ooff:], chw_out)              # + h/2 f(t + h, y')
             elif mid:
-                reinterp_axpy(ymid[k], chw_in, ys[k], 0.5 * cfg.h, a0[ooff:], chw_out)
+                reinterp_axpy(ymid[k], chw_in, ys[k], 0.5 * hk, a0[ooff:], chw_out)
                 a1 = store[j + 1 if keep else 0]
                 chain_forward(desc, float(tkh[j + 1]), wtraj[0, j + 1], wss, ymid[k], a1)
-                reinterp_axpy(ys[k + 1], chw_in, ys[k], cfg.h, a1[ooff:], chw_out)
+                reinterp_axpy(ys[k + 1], chw_in, ys[k], hk, a1[ooff:], chw_out)
             else:
-                reinterp_axpy(ys[k + 1], chw_in, ys[k], cfg.h, a0[ooff:], chw_out)
+                reinterp_axpy(ys[k + 1], chw_in, ys[k], hk, a0[ooff:], chw_out)
         ctx.cfg, ctx.klayers, ctx.desc = cfg, klayers, desc
         ctx.store = store if keep else None
         ctx.save_for_backward(wtraj, z1, ys, ymid if two else ys)
@@ -422,29 +434,30 @@ class SDENetSolve(torch.autograd.Function):
 
         heun = cfg.method == "heun"
         for k in range(n - 1, -1, -1):
+            hk = cfg.hs[k]
             if heun:
                 j = 2 * k
                 # y_{k+1} = y_k + h/2 R(f(t, y_k, w_k)) + h/2 R(f(t + h, y', w'))
-                reinterp_axpy(gf, chw_out, None, 0.5 * cfg.h, gy, chw_in)
+                reinterp_axpy(gf, chw_out, None, 0.5 * hk, gy, chw_in)
                 chain_backward(desc, float(tkh[j + 1]), wtraj[0, j + 1], wss, ymid[k], acts_of(j + 1, ymid[k]), gf, gyp, False,
                                gw_traj[0, j + 1], gss)
                 # y' = y_k + h R(f(t, y_k, w_k)): f(t, y_k) receives h * dL/dy' + h/2 * dL/dy_{k+1}
                 gf2 = torch.empty_like(gf)
-                reinterp_axpy(gf2, chw_out, gf, cfg.h, gyp, chw_in)
+                reinterp_axpy(gf2, chw_out, gf, hk, gyp, chw_in)
                 gy.add_(gyp)
                 chain_backward(desc, float(tkh[j]), wtraj[0, j], wss, ys[k], acts_of(j, ys[k]), gf2, gy, True, gw_traj[0, j], gss)
             elif mid:
                 j = 2 * k
                 # y_{k+1} = y_k + h R(f(t + h/2, y', w'))
-                reinterp_axpy(gf, chw_out, None, cfg.h, gy, chw_in)
+                reinterp_axpy(gf, chw_out, None, hk, gy, chw_in)
                 chain_backward(desc, float(tkh[j + 1]), wtraj[0, j + 1], wss, ymid[k], acts_of(j + 1, ymid[k]), gf, gyp, False,
                                gw_traj[0, j + 1], gss)
                 # y' = y_k + h/2 R(f(t, y_k, w_k))
-                reinterp_axpy(gf, chw_out, None, 0.5 * cfg.h, gyp, chw_in)
+                reinterp_axpy(gf, chw_out, None, 0.5 * hk, gyp, chw_in)
                 gy.add_(gyp)
                 chain_backward(desc, float(tkh[j]), wtraj[0, j], wss, ys[k], acts_of(j, ys[k]), gf, gy, True, gw_traj[0, j], gss)
             else:
-                reinterp_axpy(gf, chw_out, None, cfg.h, gy, chw_in)
+                reinterp_axpy(gf, chw_out, None, hk, gy, chw_in)
                 chain_backward(desc, float(tkh[k]), wtraj[0, k], wss, ys[k], acts_of(k, ys[k]), gf, gy, True, gw_traj[0, k], gss)
         ctx.store = None
         # ---- K1 reverse
@@ -477,6 +490,8 @@ class SDENetAdjointSolve(torch.autograd.Function):
         S, P, n = cfg.S, cfg.ynet.P, cfg.n
         if S != 1:
             raise NotImplementedError("sdeint_adjoint route: one weight sample per call (SDENet.forward always has S = 1)")
+        if not cfg.uniform:
+            raise NotImplementedError("sdeint_adjoint route: uniform step grids only")
         if I is None:  # the same path the in-kernel stream of the plain route draws: N(0, h) at Philox counter (p, k, s, stream)
             I = philox_increments(seed, stream_id, S, np.full(n, np.float32(cfg.h), dtype=np.float32), P, x.device)
         elif tuple(I.shape) != (S, n, P):
@@ -586,6 +601,66 @@ def sdenet_solve(cfg, x_nhwc, w0, linears, increments=None, seed=0, stream_id=0)
 
 
 # ------------------------------------------------------------------------------------------------
+# adaptive stepping (`adaptive=True`, models.py:194-197 -> torchsde's step-doubling controller)
+# ------------------------------------------------------------------------------------------------
+def update_step_size(error_estimate, prev_step_size, safety=0.9, facmin=0.2, facmax=1.4, prev_error_ratio=None):
+    """torchsde/_core/adaptive_stepping.py (restated from the published controller: PI step-size control, Burrage & Burrage 2004 /
+    Ilie, Jackson & Enright 2015): returns (new_step_size, prev_error_ratio)."""
+    if error_estimate > 1:
+        pfactor, ifactor = 0.0, 1.0 / 1.5
+    else:
+        pfactor, ifactor = 0.13, 1.0 / 4.5
+    error_ratio = safety / error_estimate
+    if prev_error_ratio is None:
+        prev_error_ratio = error_ratio
+    factor = error_ratio ** ifactor * (error_ratio / prev_error_ratio) ** pfactor
+    if error_estimate <= 1:
+        prev_error_ratio = error_ratio
+        facmin = 1.0
+    factor = min(facmax, max(facmin, factor))
+    return prev_step_size * factor, prev_error_ratio
+
+
+def compute_error(full, halves, rtol, atol, eps=1e-7):
+    """RMS over the WHOLE augmented state [y, w, logqp] of (one full step - two half steps) / (rtol max(|.|, |.|) + atol + eps)."""
+    num, cnt = 0.0, 0
+    for a, b in zip(full, halves):
+        tol = rtol * torch.maximum(a.abs(), b.abs()) + atol
+        num = num + (((a - b) / (tol + eps)) ** 2).sum()
+        cnt += a.numel()
+    return max(float(torch.sqrt(num / cnt)), eps)
+
+
+def sdenet_adaptive_grid(one_step, t0, t1, dt, rtol, atol, state, dt_min=1e-5, max_trials=100000):
+    """torchsde's adaptive loop for ts = [t0, t1] (BaseSDESolver.integrate, adaptive branch): every trial takes one full step and two
+    half steps from the current state, accepts the half-step result when the error estimate is <= 1 (or the step hit dt_min) and
+    updates the step with `update_step_size` either way.  `one_step(ta, h, state) -> state`.  Returns the accepted (t, h) half steps,
+    the final state and the number of single steps taken (accepted or not)."""
+    f32 = np.float32
+    curr_t, step, prev_ratio = f32(t0), f32(dt), None
+    ts, hs, nsingle = [], [], 0
+    for _ in range(max_trials):
+        if not curr_t < f32(t1):
+            return ts, hs, state, nsingle
+        next_t = min(f32(curr_t + step), f32(t1))
+        mid_t = f32(f32(0.5) * f32(curr_t + next_t))
+        full = one_step(curr_t, f32(next_t - curr_t), state)
+        mid = one_step(curr_t, f32(mid_t - curr_t), state)
+        nxt = one_step(mid_t, f32(next_t - mid_t), mid)
+        nsingle += 3
+        err = compute_error(full, nxt, rtol, atol)
+        new_step, prev_ratio = update_step_size(err, float(step), prev_error_ratio=prev_ratio)
+        step = f32(new_step)
+        if step < dt_min:
+            step, prev_ratio = f32(dt_min), None
+        if err <= 1 or step <= dt_min:
+            ts += [curr_t, mid_t]
+            hs += [f32(mid_t - curr_t), f32(next_t - mid_t)]
+            curr_t, state = next_t, nxt
+    raise RuntimeError(f"adaptive solve did not reach t1 = {t1} in {max_trials} trials")
+
+
+# ------------------------------------------------------------------------------------------------
 # SDENet: models.py:105-204
 # ------------------------------------------------------------------------------------------------
 class SDENet(nn.Module):
@@ -627,19 +702,21 @@ class SDENet(nn.Module):
                 increments=None):
         """-> (logits, logqp).  `increments` [nsteps, P]: W(t_{k+1}) - W(t_k) to replay (else in-kernel Philox keyed by
         (self.seed, call counter), the stand-in for torchsde.BrownianInterval, models.py:190-193)."""
-        if adaptive or adjoint_adaptive:
-            raise NotImplementedError("adaptive stepping is out of scope (SURVEY 8.2 / 8.6 N4)")
+        if adjoint_adaptive or (adaptive and adjoint):
+            raise NotImplementedError("adaptive stepping inside sdeint_adjoint is not built (SURVEY 8.6 N4)")
         if not y.is_cuda:
             raise _lib.BsdeError("bayesde_b200 kernels need CUDA tensors (there is no CPU fallback)")
         t0, t1 = float(self.ts[0]), float(self.ts[-1])
         nsteps = int(round((t1 - t0) / dt))
         if self.aug_zeros.numel() > 0:  # add zero channels (models.py:185-187)
             y = torch.cat((y, self.aug_zeros.expand(y.shape[0], *self.aug_zeros_size)), dim=1)
-        cfg = self._config(y.shape[0], nsteps, dt, method)
         x = y.float().permute(0, 2, 3, 1).contiguous()[None]               # NHWC storage, S = 1
         lin = [(m.weight, m.bias) for m in self.w_net.linears()]
-        I = None if increments is None else increments[None]
         self._calls += 1
+        if adaptive:
+            return self._forward_adaptive(x, lin, t0, t1, dt, method, rtol, atol)
+        cfg = self._config(y.shape[0], nsteps, dt, method)
+        I = None if increments is None else increments[None]
         solve = sdenet_solve_adjoint if adjoint else sdenet_solve  # models.py:194: sdeint_adjoint / sdeint
         y1, lq, _ = solve(cfg, x, self.flat_initial_params, lin, I, seed=self.seed, stream_id=self._calls)
         # f and g are each evaluated once per stage (models.py:161,172): 2 stages for midpoint; euler_heun evaluates g twice
@@ -648,6 +725,34 @@ class SDENet(nn.Module):
         logits = self.projection(y1.reshape(y1.shape[0], -1))
         logqp = .5 * lq[0]
         return logits, logqp
+
+    def _forward_adaptive(self, x, lin, t0, t1, dt, method, rtol, atol):
+        """`adaptive=True`: the accepted step grid is found by torchsde's step-doubling loop on a queryable Philox Brownian tree over
+        the P weight rows (the stand-in for BrownianInterval: any interval's increment is W(tb) - W(ta)), without autograd; the
+        solve is then replayed on that grid through `sdenet_solve` so that `loss.backward()` differentiates the accepted steps."""
+        from .sdeint import BrownianTree
+        P, B = self.params_size, x.shape[1]
+        tree = BrownianTree(t0, P, t1, (self.seed, self._calls), device=x.device)
+        mk = lambda ts, hs: SolveConfig(self.y_net, 1, B, len(ts), 0.0, method, self.sigma, self.w_net.hidden_sizes,
+                                        self.w_net.activation, self.math, True, grid=(ts, hs))
+        inc = lambda ts, hs: torch.stack([tree(float(np.float32(t + h))) - tree(float(t)) for t, h in zip(ts, hs)])[None]
+
+        def one_step(ta, h, state):
+            yy, ww, lq = state
+            cfg1 = mk([ta], [h])
+            y1, kl, wtraj = sdenet_solve(cfg1, yy, ww, lin, inc([ta], [h]))
+            return y1, wtraj[0, cfg1.nit].contiguous(), lq + kl[0]
+
+        with torch.no_grad():
+            state0 = (x, self.flat_initial_params.detach().float().contiguous(), torch.zeros((), device=x.device))
+            ts, hs, _, nsingle = sdenet_adaptive_grid(one_step, t0, t1, dt, rtol, atol, state0)
+        self.adaptive_grid = (ts, hs)
+        cfg = mk(ts, hs)
+        y1, lq, _ = sdenet_solve(cfg, x, self.flat_initial_params, lin, inc(ts, hs))
+        self.nfe = nsingle * {"midpoint": 4, "heun": 4, "euler_heun": 3, "milstein": 2}[method]
+        y1 = y1[0].permute(0, 3, 1, 2)
+        logits = self.projection(y1.reshape(y1.shape[0], -1))
+        return logits, .5 * lq[0]
 
     def zero_grad(self, set_to_none=True) -> None:
         for p in self.parameters():

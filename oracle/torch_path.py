@@ -239,6 +239,76 @@ class SDENetOracle:
                 raise ValueError(f"Unknown method: {method}")
         return y, w, ay, aw, ap
 
+    # ---- adaptive stepping: torchsde's step-doubling controller (un-pinned git dependency, absent here; restated from the published
+    # scheme: BaseSDESolver.integrate with adaptive=True + adaptive_stepping.{update_step_size, compute_error}) ----------------------
+    @staticmethod
+    def update_step_size(error_estimate, prev_step_size, safety=0.9, facmin=0.2, facmax=1.4, prev_error_ratio=None):
+        if error_estimate > 1:
+            pfactor, ifactor = 0.0, 1.0 / 1.5
+        else:
+            pfactor, ifactor = 0.13, 1.0 / 4.5
+        error_ratio = safety / error_estimate
+        if prev_error_ratio is None:
+            prev_error_ratio = error_ratio
+        factor = error_ratio ** ifactor * (error_ratio / prev_error_ratio) ** pfactor
+        if error_estimate <= 1:
+            prev_error_ratio = error_ratio
+            facmin = 1.0
+        factor = min(facmax, max(facmin, factor))
+        return prev_step_size * factor, prev_error_ratio
+
+    @staticmethod
+    def compute_error(full, halves, rtol, atol, eps=1e-7):
+        num, cnt = 0.0, 0
+        for a, b in zip(full, halves):
+            tol = rtol * torch.maximum(a.abs(), b.abs()) + atol
+            num = num + (((a - b) / (tol + eps)) ** 2).sum()
+            cnt += a.numel()
+        return max(float(torch.sqrt(num / cnt)), eps)
+
+    def solve_adaptive(self, y, w0, w_layers, bm, dt, rtol, atol, method="midpoint", t0=0.0, t1=1.0, dt_min=1e-5):
+        """ts = [t0, t1]; `bm(t)` -> W(t) over the P weight rows.  Returns (accepted t list, accepted h list, trials' error estimates,
+        (y, w, logqp) at t1).  Time arithmetic in float32 as on the product side."""
+        import numpy as np
+        f32 = np.float32
+
+        def one(ta, h, state):
+            yy, ww, lq = state
+            I = (bm(float(f32(ta + h))) - bm(float(ta)))[None]
+            y1, w1, l1 = self.solve(yy, ww, w_layers, I, dt=float(h), method=method, t0=float(ta), t1=float(ta) + float(h))
+            return y1, w1, lq + l1
+
+        state = (y, w0, torch.zeros((), dtype=y.dtype))
+        curr, step, prev = f32(t0), f32(dt), None
+        ts, hs, errs = [], [], []
+        while curr < f32(t1):
+            nxt_t = min(f32(curr + step), f32(t1))
+            mid_t = f32(f32(0.5) * f32(curr + nxt_t))
+            full = one(curr, f32(nxt_t - curr), state)
+            mid = one(curr, f32(mid_t - curr), state)
+            nxt = one(mid_t, f32(nxt_t - mid_t), mid)
+            err = self.compute_error(full, nxt, rtol, atol)
+            errs.append(err)
+            new_step, prev = self.update_step_size(err, float(step), prev_error_ratio=prev)
+            step = f32(new_step)
+            if step < dt_min:
+                step, prev = f32(dt_min), None
+            if err <= 1 or step <= dt_min:
+                ts += [curr, mid_t]
+                hs += [f32(mid_t - curr), f32(nxt_t - mid_t)]
+                curr, state = nxt_t, nxt
+        return ts, hs, errs, state
+
+    def solve_on_grid(self, y, w0, w_layers, bm, ts, hs, method="midpoint"):
+        """The fixed-step schemes on an arbitrary step grid (the replay of an adaptive solve's accepted steps)."""
+        import numpy as np
+        w, lq = w0, torch.zeros((), dtype=y.dtype)
+        for ta, h in zip(ts, hs):
+            I = (bm(float(np.float32(ta + h))) - bm(float(ta)))[None]
+            y, w, l1 = self.solve(y, w, w_layers, I, dt=float(h), method=method, t0=float(ta), t1=float(ta) + float(h))
+            lq = lq + l1
+        return y, w, lq
+
     def forward(self, x, w0, w_layers, proj, increments, dt=0.05, method="midpoint"):
         """SDENet.forward (models.py:180-201): zero channels, solve, projection head, logqp = state[-1] / 2."""
         if self.aug_dim > 0:

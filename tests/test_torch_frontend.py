@@ -8,6 +8,8 @@ Tolerances: fp32 conv path -- drift net vs reference golden 2e-5 * max|ref|; y_T
 rtol 1e-4; gradients 1e-3 * max|ref|.  Tensor-core path (TF32 operands, 10-bit mantissa) -- y_T 5e-3 * max|ref|,
 gradients 3e-2 * max|ref|.
 """
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -127,6 +129,8 @@ def test_sdenet_module_surface(built_lib):
             "ts", "aug_zeros"} <= keys
     assert m.params_size == m.y_net.P and float(m.w_net.linears()[-1].weight.abs().max()) == 0.0
     with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 2, 8, 8), adjoint_adaptive=True)
+    with pytest.raises(_lib.BsdeError):
         m(torch.zeros(1, 2, 8, 8), adaptive=True)
     with pytest.raises(_lib.BsdeError):
         m(torch.zeros(1, 2, 8, 8))     # CPU tensor: no fallback
@@ -393,6 +397,115 @@ def test_gpu_sdenet_module_adjoint_flag(built_lib):
         a, b = outs[1][2][k], outs[0][2][k]
         assert float((a - b).abs().max()) <= 2e-2 * float(b.abs().max()) + 1e-8, (k, float((a - b).abs().max()), float(b.abs().max()))
     with pytest.raises(NotImplementedError):
-        m(x, adaptive=True)
-    with pytest.raises(NotImplementedError):
         m(x, adjoint=True, adjoint_adaptive=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# `adaptive=True` -- torchsde's step-doubling controller, accepted grid replayed for the gradients
+# ---------------------------------------------------------------------------------------------------------------
+def test_step_size_controller_known_values():
+    """Hand-evaluated values of the PI controller (safety 0.9, I exponent 1/4.5 on acceptance and 1/1.5 on rejection, P exponent 0.13,
+    factor clamped to [0.2 or 1, 1.4]); product and oracle restatements agree."""
+    from bayesde_b200 import torch_models as tm
+    for fn in (tm.update_step_size, tp.SDENetOracle.update_step_size):
+        s, r = fn(0.5, 0.1)
+        assert abs(s - 0.1 * 1.8 ** (1 / 4.5)) < 1e-15 and r == 1.8
+        s, r = fn(2.0, 0.1, prev_error_ratio=1.8)
+        assert abs(s - 0.1 * 0.45 ** (1 / 1.5)) < 1e-15 and r == 1.8                  # rejected: prev ratio kept, no P term
+        assert abs(fn(1000.0, 0.1)[0] - 0.02) < 1e-15 and abs(fn(1e-3, 0.1)[0] - 0.14) < 1e-15      # clamps 0.2 and 1.4
+        s, r = fn(0.9, 0.1, prev_error_ratio=2.0)
+        assert abs(s - 0.1 * max(1.0, 1.0 ** (1 / 4.5) * (1.0 / 2.0) ** 0.13)) < 1e-15 and r == 1.0    # accepted: factor floor 1
+    g = torch.Generator().manual_seed(0)
+    a = [torch.randn(5, 7, generator=g), torch.randn(11, generator=g), torch.randn((), generator=g)]
+    b = [t + 1e-3 * torch.randn(t.shape, generator=g) for t in a]
+    assert abs(tm.compute_error(a, b, 1e-3, 1e-4) - tp.SDENetOracle.compute_error(a, b, 1e-3, 1e-4)) < 1e-9
+    assert tm.compute_error(a, a, 1e-3, 1e-4) == 1e-7
+
+
+def test_adaptive_loop_host_logic():
+    """The product's loop on a scalar test problem (explicit midpoint on y' = -3 y): reaches t1 exactly, the accepted half steps tile
+    [t0, t1], rejections occur when the first step is too large, tighter tolerances take more steps and land closer to exp(-3)."""
+    from bayesde_b200 import torch_models as tm
+
+    def one_step(ta, h, state):
+        (y,) = state
+        h = float(h)
+        return (y + h * (-3.0) * (y + 0.5 * h * (-3.0) * y),)
+
+    res = []
+    for tol in (1e-2, 1e-4):
+        ts, hs, (y,), nsingle = tm.sdenet_adaptive_grid(one_step, 0.0, 1.0, 0.5, tol, tol, (torch.ones(3, dtype=torch.float64),))
+        assert len(ts) == len(hs) and len(ts) % 2 == 0 and nsingle >= 3 * len(ts) // 2
+        assert ts[0] == 0.0 and all(abs(float(ts[i] + hs[i]) - float(ts[i + 1])) < 1e-6 for i in range(len(ts) - 1))
+        assert abs(float(ts[-1] + hs[-1]) - 1.0) < 1e-6
+        res.append((len(ts), nsingle, abs(float(y[0]) - math.exp(-3.0))))
+    assert res[1][0] > res[0][0] and res[1][2] < res[0][2] and res[1][2] < 1e-3
+    assert res[1][1] > 3 * res[1][0] // 2                     # some trials were rejected
+    with pytest.raises(RuntimeError):
+        tm.sdenet_adaptive_grid(one_step, 0.0, 1.0, 0.5, 1e-4, 1e-4, (torch.ones(1),), max_trials=2)
+
+
+def test_oracle_adaptive_converges_and_replays():
+    from oracle import jax_adjoint as ja
+    net, w0, wl, x, cot, fine = _adjoint_case()
+    tree = ja.BrownianTree(7, 1, net.P, 0.0, 1.0)
+    bm = lambda t: tree(t)
+    outs = []
+    for tol in (1e-2, 1e-3):
+        ts, hs, errs, (y, w, lq) = net.solve_adaptive(x, w0, wl, bm, 0.25, tol, tol)
+        yr, wr, lr = net.solve_on_grid(x, w0, wl, bm, ts, hs)
+        assert torch.equal(y, yr) and torch.equal(w, wr) and torch.equal(lq, lr)          # the replay IS the accepted solve
+        assert abs(float(sum(float(h) for h in hs)) - 1.0) < 1e-5 and max(errs) > 1.0 > min(errs)
+        outs.append((len(ts), y, lq))
+    n = 256
+    I = torch.stack([bm((k + 1) / n) - bm(k / n) for k in range(n)])
+    yf, wf, lf = net.solve(x, w0, wl, I, dt=1.0 / n, method="midpoint")
+    e = [float((o[1] - yf).abs().max()) for o in outs]
+    assert outs[1][0] > outs[0][0] and e[1] < e[0] and abs(float(outs[1][2] - lf)) < abs(float(outs[0][2] - lf)) + 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["midpoint", "heun"])
+def test_gpu_sdenet_adaptive(built_lib, method):
+    """SDENet.forward(adaptive=True): valid accepted grid; logits / logqp and every gradient against the oracle's fixed-step solve ON THE
+    PRODUCT'S accepted grid with the same Philox tree (1e-4 / 1e-3); the oracle's own adaptive loop takes a comparable number of steps
+    (accept / reject decisions sit near error = 1 by construction, so fp32 and fp64 grids need not coincide); deterministic per call."""
+    from bayesde_b200 import torch_models as tm
+    from oracle import jax_adjoint as ja
+    torch.manual_seed(0)
+    m = tm.SDENet(input_size=(2, 8, 8), blocks=(1, 1), weight_network_sizes=(1, 8, 1), hidden_width=4, aug_dim=1, sigma=0.2, math="fp32").to(DEV)
+    with torch.no_grad():
+        last = m.w_net.linears()[-1]
+        last.weight.normal_(0, 0.05), last.bias.normal_(0, 0.05)
+    x = torch.randn(3, 2, 8, 8, device=DEV)
+    m._calls = 0
+    logits, logqp = m(x, dt=0.25, method=method, adaptive=True, rtol=1e-3, atol=1e-3)
+    ts, hs = m.adaptive_grid
+    assert len(ts) >= 4 and abs(sum(float(h) for h in hs) - 1.0) < 1e-5 and m.nfe >= 4 * len(ts)
+    (logits.logsumexp(1).mean() + 1e-3 * logqp).backward()
+    grads = {k: p.grad.clone() for k, p in m.named_parameters()}
+
+    net = tp.SDENetOracle((2, 8, 8), (1, 1), (1, 8, 1), sigma=0.2, hidden_width=4, aug_dim=1)
+    dd = lambda t: t.detach().double().cpu()
+    tree = ja.BrownianTree(m.seed, 1, net.P, 0.0, 1.0)
+    bm = lambda t: tree(t)
+    w0 = dd(m.flat_initial_params).requires_grad_(True)
+    wl = [(dd(l.weight).requires_grad_(True), dd(l.bias).requires_grad_(True)) for l in m.w_net.linears()]
+    xa = torch.cat((dd(x), torch.zeros(3, 1, 8, 8, dtype=torch.float64)), dim=1)
+    yr, wr, lr = net.solve_on_grid(xa, w0, wl, bm, ts, hs, method=method)
+    (W1, b1), (W2, b2) = (dd(m.projection[1].weight), dd(m.projection[1].bias)), (dd(m.projection[3].weight), dd(m.projection[3].bias))
+    lo = torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(yr.reshape(3, -1), W1, b1)), W2, b2)
+    _close(logits, lo, 1e-4, "logits on the accepted grid")
+    _close(logqp, 0.5 * lr, 1e-4, "logqp on the accepted grid")
+    gr = torch.autograd.grad(lo.logsumexp(1).mean() + 1e-3 * 0.5 * lr, [w0] + [t for p in wl for t in p])
+    _close(grads["flat_initial_params"], gr[0], 1e-3, "dL/dw0")
+    for i, l in enumerate(m.w_net.linears()):
+        name = [k for k, p in m.named_parameters() if p is l.weight][0]
+        _close(grads[name], gr[1 + 2 * i], 1e-3, f"dL/d w_net[{i}].weight")
+    ts_o, hs_o, errs_o, _ = net.solve_adaptive(xa, w0.detach(), [(W.detach(), b.detach()) for W, b in wl], bm, 0.25, 1e-3, 1e-3, method=method)
+    assert 0.6 * len(ts_o) <= len(ts) <= 1.6 * len(ts_o), (len(ts), len(ts_o))
+    m._calls = 0
+    l2, q2 = m(x, dt=0.25, method=method, adaptive=True, rtol=1e-3, atol=1e-3)
+    assert torch.equal(l2, logits) and torch.equal(q2, logqp)
+    with pytest.raises(NotImplementedError):
+        m(x, adaptive=True, adjoint=True)
