@@ -12,8 +12,8 @@ through strides) and `bsde_nchw_reinterp_axpy` (the flat-NCHW-order state update
 
 Semantics follow the INTENDED flat-state reading of `SDENet` (the class as shipped raises in `split`/`cat`: SURVEY
 quirk Q7).  `adjoint=True` selects the O(1)-memory reverse pass of `sdeint_adjoint` (SDENetAdjointSolve); `adaptive=True` runs torchsde's
-step-doubling controller and replays the accepted grid; `adjoint_adaptive=True` (and adaptive + adjoint together) raise
-NotImplementedError.  There is no CPU path.
+step-doubling controller and replays the accepted grid (with `adjoint=True`: fixed-step reverse solve from the adaptive solve's
+final state); `adjoint_adaptive=True` raises NotImplementedError.  There is no CPU path.
 """
 import ctypes as C
 import math
@@ -485,7 +485,9 @@ class SDENetAdjointSolve(torch.autograd.Function):
     bsde_chain_bwd / bsde_wsde_bwd with dt > 0 at the reconstructed state (an Euler-like reverse step seeded with a or a')."""
 
     @staticmethod
-    def forward(ctx, cfg, I, seed, stream_id, x, w0, *flat):
+    def forward(ctx, cfg, I, seed, stream_id, final, x, w0, *flat):
+        """`final` = (y_T, logqp state [S], w_T) of a forward solve made elsewhere on the same Brownian path (the adaptive loop), or
+        None to run the fixed-step forward solve of `cfg` here."""
         from .sdeint import philox_increments
         S, P, n = cfg.S, cfg.ynet.P, cfg.n
         if S != 1:
@@ -497,11 +499,17 @@ class SDENetAdjointSolve(torch.autograd.Function):
         elif tuple(I.shape) != (S, n, P):
             raise ValueError(f"increments must have shape {(S, n, P)}, got {tuple(I.shape)}")
         I = I.float().contiguous()
-        with torch.no_grad():
-            yT, kl, wtraj = SDENetSolve.apply(cfg, I, 0, 0, x.detach(), w0.detach(), *[t.detach() for t in flat])
+        if final is None:
+            with torch.no_grad():
+                yT, kl, wtraj = SDENetSolve.apply(cfg, I, 0, 0, x.detach(), w0.detach(), *[t.detach() for t in flat])
+            wT = wtraj[0, cfg.nit].contiguous()
+        else:
+            yT, kl, wT = (t.detach() for t in final)
+            yT, kl, wT = yT.contiguous(), kl.clone(), wT.contiguous()
+            wtraj = wT[None, None]
         ctx.cfg = cfg
         ctx.klayers = [(flat[i].detach().contiguous(), flat[i + 1].detach().contiguous()) for i in range(0, len(flat), 2)]
-        ctx.save_for_backward(yT, wtraj[0, cfg.nit].contiguous(), I)
+        ctx.save_for_backward(yT, wT, I)
         ctx.mark_non_differentiable(wtraj)
         return yT.clone(), kl, wtraj
 
@@ -578,18 +586,18 @@ class SDENetAdjointSolve(torch.autograd.Function):
                 Zy, Zw, a_y, a_w = stage(tau, h, Zy, Zy, Zw, Zw, dWr, a_y, a_y, a_w, a_w, True)
         global LAST_RECONSTRUCTION
         LAST_RECONSTRUCTION = (Zy, Zw)
-        return (None, None, None, None, a_y, a_w, *gacc)
+        return (None, None, None, None, None, a_y, a_w, *gacc)
 
 
 LAST_RECONSTRUCTION = None
 
 
-def sdenet_solve_adjoint(cfg, x_nhwc, w0, linears, increments=None, seed=0, stream_id=0):
+def sdenet_solve_adjoint(cfg, x_nhwc, w0, linears, increments=None, seed=0, stream_id=0, final=None):
     """As `sdenet_solve`, with the O(1)-memory reverse pass of `sdeint_adjoint`."""
     kl = []
     for W, b in linears:
         kl += [W.t().contiguous(), b]
-    return SDENetAdjointSolve.apply(cfg, increments, seed, stream_id, x_nhwc, w0, *kl)
+    return SDENetAdjointSolve.apply(cfg, increments, seed, stream_id, final, x_nhwc, w0, *kl)
 
 
 def sdenet_solve(cfg, x_nhwc, w0, linears, increments=None, seed=0, stream_id=0):
@@ -702,8 +710,8 @@ class SDENet(nn.Module):
                 increments=None):
         """-> (logits, logqp).  `increments` [nsteps, P]: W(t_{k+1}) - W(t_k) to replay (else in-kernel Philox keyed by
         (self.seed, call counter), the stand-in for torchsde.BrownianInterval, models.py:190-193)."""
-        if adjoint_adaptive or (adaptive and adjoint):
-            raise NotImplementedError("adaptive stepping inside sdeint_adjoint is not built (SURVEY 8.6 N4)")
+        if adjoint_adaptive:
+            raise NotImplementedError("adaptive stepping of the reverse solve (adjoint_adaptive) is not built (SURVEY 8.6 N4)")
         if not y.is_cuda:
             raise _lib.BsdeError("bayesde_b200 kernels need CUDA tensors (there is no CPU fallback)")
         t0, t1 = float(self.ts[0]), float(self.ts[-1])
@@ -714,7 +722,7 @@ class SDENet(nn.Module):
         lin = [(m.weight, m.bias) for m in self.w_net.linears()]
         self._calls += 1
         if adaptive:
-            return self._forward_adaptive(x, lin, t0, t1, dt, method, rtol, atol)
+            return self._forward_adaptive(x, lin, t0, t1, dt, method, rtol, atol, adjoint, nsteps)
         cfg = self._config(y.shape[0], nsteps, dt, method)
         I = None if increments is None else increments[None]
         solve = sdenet_solve_adjoint if adjoint else sdenet_solve  # models.py:194: sdeint_adjoint / sdeint
@@ -726,7 +734,7 @@ class SDENet(nn.Module):
         logqp = .5 * lq[0]
         return logits, logqp
 
-    def _forward_adaptive(self, x, lin, t0, t1, dt, method, rtol, atol):
+    def _forward_adaptive(self, x, lin, t0, t1, dt, method, rtol, atol, adjoint=False, nsteps=0):
         """`adaptive=True`: the accepted step grid is found by torchsde's step-doubling loop on a queryable Philox Brownian tree over
         the P weight rows (the stand-in for BrownianInterval: any interval's increment is W(tb) - W(ta)), without autograd; the
         solve is then replayed on that grid through `sdenet_solve` so that `loss.backward()` differentiates the accepted steps."""
@@ -745,10 +753,18 @@ class SDENet(nn.Module):
 
         with torch.no_grad():
             state0 = (x, self.flat_initial_params.detach().float().contiguous(), torch.zeros((), device=x.device))
-            ts, hs, _, nsingle = sdenet_adaptive_grid(one_step, t0, t1, dt, rtol, atol, state0)
+            ts, hs, final, nsingle = sdenet_adaptive_grid(one_step, t0, t1, dt, rtol, atol, state0)
         self.adaptive_grid = (ts, hs)
-        cfg = mk(ts, hs)
-        y1, lq, _ = sdenet_solve(cfg, x, self.flat_initial_params, lin, inc(ts, hs))
+        if adjoint:
+            # sdeint_adjoint(adaptive=True, adjoint_adaptive=False): adaptive forward solve, reverse solve with fixed steps `dt` on
+            # the same path (the tree's increments over the uniform grid), started from the adaptive solve's final state
+            cfg = self._config(x.shape[1], nsteps, dt, method)
+            tu = [np.float32(t0) + np.float32(k) * np.float32(dt) for k in range(nsteps)]
+            y1, lq, _ = sdenet_solve_adjoint(cfg, x, self.flat_initial_params, lin, inc(tu, [np.float32(dt)] * nsteps),
+                                             final=(final[0], final[2].reshape(1), final[1]))
+        else:
+            cfg = mk(ts, hs)
+            y1, lq, _ = sdenet_solve(cfg, x, self.flat_initial_params, lin, inc(ts, hs))
         self.nfe = nsingle * {"midpoint": 4, "heun": 4, "euler_heun": 3, "milstein": 2}[method]
         y1 = y1[0].permute(0, 3, 1, 2)
         logits = self.projection(y1.reshape(y1.shape[0], -1))

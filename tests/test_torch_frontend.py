@@ -507,5 +507,26 @@ def test_gpu_sdenet_adaptive(built_lib, method):
     m._calls = 0
     l2, q2 = m(x, dt=0.25, method=method, adaptive=True, rtol=1e-3, atol=1e-3)
     assert torch.equal(l2, logits) and torch.equal(q2, logqp)
+    # adaptive forward + sdeint_adjoint's fixed-step reverse solve (adjoint_adaptive=False) from the adaptive solve's final state
+    m.zero_grad()
+    m._calls = 0
+    dt = 0.125
+    l3, q3 = m(x, dt=dt, method=method, adaptive=True, adjoint=True, rtol=1e-3, atol=1e-3)
+    ts3, hs3 = m.adaptive_grid
+    (l3.logsumexp(1).mean() + 1e-3 * q3).backward()
+    y3, w3, lr3 = net.solve_on_grid(xa, w0.detach(), [(W.detach(), b.detach()) for W, b in wl], bm, ts3, hs3, method=method)
+    yl = y3.clone().requires_grad_(True)
+    lo3 = torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(yl.reshape(3, -1), W1, b1)), W2, b2)
+    _close(l3, lo3, 1e-4, "logits (adaptive + adjoint)")
+    (cot_y,) = torch.autograd.grad(lo3.logsumexp(1).mean(), yl)
+    f32 = np.float32
+    tu = [f32(0.0) + f32(k) * f32(dt) for k in range(8)]
+    Iu = torch.stack([bm(float(f32(t + f32(dt)))) - bm(float(t)) for t in tu])
+    _, _, ay, aw, ap = net.adjoint(y3, w3, cot_y, torch.zeros_like(w3), torch.tensor(0.5e-3, dtype=torch.float64),
+                                   [(W.detach(), b.detach()) for W, b in wl], Iu, dt=dt, method=method)
+    _close(m.flat_initial_params.grad, aw, 1e-3, "dL/dw0 (adaptive + adjoint)")
+    for i, l in enumerate(m.w_net.linears()):
+        _close(l.weight.grad, ap[2 * i], 1e-3, f"dL/d w_net[{i}].weight (adaptive + adjoint)")
+        _close(l.bias.grad, ap[2 * i + 1], 1e-3, f"dL/d w_net[{i}].bias (adaptive + adjoint)")
     with pytest.raises(NotImplementedError):
-        m(x, adaptive=True, adjoint=True)
+        m(x, adaptive=True, adjoint=True, adjoint_adaptive=True)
