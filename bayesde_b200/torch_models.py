@@ -13,7 +13,7 @@ through strides) and `bsde_nchw_reinterp_axpy` (the flat-NCHW-order state update
 Semantics follow the INTENDED flat-state reading of `SDENet` (the class as shipped raises in `split`/`cat`: SURVEY
 quirk Q7).  `adjoint=True` selects the O(1)-memory reverse pass of `sdeint_adjoint` (SDENetAdjointSolve); `adaptive=True` runs torchsde's
 step-doubling controller and replays the accepted grid (with `adjoint=True`: fixed-step reverse solve from the adaptive solve's
-final state); `adjoint_adaptive=True` raises NotImplementedError.  There is no CPU path.
+final state; `adjoint_adaptive=True`: the controller also drives the reverse solve).  There is no CPU path.
 """
 import ctypes as C
 import math
@@ -485,9 +485,10 @@ class SDENetAdjointSolve(torch.autograd.Function):
     bsde_chain_bwd / bsde_wsde_bwd with dt > 0 at the reconstructed state (an Euler-like reverse step seeded with a or a')."""
 
     @staticmethod
-    def forward(ctx, cfg, I, seed, stream_id, final, x, w0, *flat):
+    def forward(ctx, cfg, I, seed, stream_id, final, rev, x, w0, *flat):
         """`final` = (y_T, logqp state [S], w_T) of a forward solve made elsewhere on the same Brownian path (the adaptive loop), or
-        None to run the fixed-step forward solve of `cfg` here."""
+        None to run the fixed-step forward solve of `cfg` here.  `rev` = (tree, rtol, atol, dt, t1) makes the reverse solve
+        adaptive (`adjoint_adaptive=True`) on that tree instead of stepping over `I`."""
         from .sdeint import philox_increments
         S, P, n = cfg.S, cfg.ynet.P, cfg.n
         if S != 1:
@@ -507,7 +508,7 @@ class SDENetAdjointSolve(torch.autograd.Function):
             yT, kl, wT = (t.detach() for t in final)
             yT, kl, wT = yT.contiguous(), kl.clone(), wT.contiguous()
             wtraj = wT[None, None]
-        ctx.cfg = cfg
+        ctx.cfg, ctx.rev = cfg, rev
         ctx.klayers = [(flat[i].detach().contiguous(), flat[i + 1].detach().contiguous()) for i in range(0, len(flat), 2)]
         ctx.save_for_backward(yT, wT, I)
         ctx.mark_non_differentiable(wtraj)
@@ -565,39 +566,65 @@ class SDENetAdjointSolve(torch.autograd.Function):
                                  _lib.stream_ptr())
             _lib.check(st, "bsde_wsde_bwd")
             aw_new = r if aw_base is aw_at else r - aw_at + aw_base
-            if want_params:  # weight of this stage's dt (df/dparams)^T a_at in the parameter adjoint (True = 1)
-                torch._foreach_add_(gacc, [t for pair in gl for t in pair], alpha=float(want_params))
-            return Zy_new, Zw_new.contiguous(), ay_new, aw_new
+            # this stage's dt (df/dparams)^T a_at, weighted by `want_params` in the parameter adjoint (True = 1, False = unused)
+            gp = [t * float(want_params) for pair in gl for t in pair] if want_params else None
+            return Zy_new, Zw_new.contiguous(), ay_new, aw_new, gp
+
+        def rev_step(tau, h, dWr, state):
+            """One reverse step of the scheme from forward time tau to tau - h: state = (Zy, Zw, a_y, a_w, *a_params) -> new state."""
+            Zy, Zw, a_y, a_w = state[:4]
+            gacc = list(state[4:])
+            if cfg.method == "heun":   # Z' = Z - h f(tau, Z) + g dW~;  Z1 = (Z + Z')/2 - h/2 f(tau - h, Z') + g dW~/2;  a likewise
+                Zy_p, Zw_p, ay_p, aw_p, g1 = stage(tau, h, Zy, Zy, Zw, Zw, dWr, a_y, a_y, a_w, a_w, 0.5)
+                Zy, Zw, a_y, a_w, g2 = stage(float(np.float32(tau) - np.float32(h)), 0.5 * h, 0.5 * (Zy + Zy_p), Zy_p, 0.5 * (Zw + Zw_p),
+                                             Zw_p, 0.5 * dWr, 0.5 * (a_y + ay_p), ay_p, 0.5 * (a_w + aw_p), aw_p, 1.0)
+                gacc = [a + b + c for a, b, c in zip(gacc, g1, g2)]
+            elif mid:
+                Zy_p, Zw_p, ay_p, aw_p, _ = stage(tau, 0.5 * h, Zy, Zy, Zw, Zw, 0.5 * dWr, a_y, a_y, a_w, a_w, False)
+                Zy, Zw, a_y, a_w, g2 = stage(float(np.float32(tau) - np.float32(0.5) * np.float32(h)), h, Zy, Zy_p, Zw, Zw_p, dWr,
+                                             a_y, ay_p, a_w, aw_p, True)
+                gacc = [a + b for a, b in zip(gacc, g2)]
+            else:
+                Zy, Zw, a_y, a_w, g1 = stage(tau, h, Zy, Zy, Zw, Zw, dWr, a_y, a_y, a_w, a_w, True)
+                gacc = [a + b for a, b in zip(gacc, g1)]
+            return (Zy, Zw, a_y, a_w, *gacc)
 
         t0 = float(cfg.tk[0])
-        for k in range(n - 1, -1, -1):
-            tau = float(np.float32(t0) + np.float32(k + 1) * np.float32(h))
-            dWr = (-I[0, k]).contiguous()
-            if cfg.method == "heun":   # Z' = Z - h f(tau, Z) + g dW~;  Z1 = (Z + Z')/2 - h/2 f(tau - h, Z') + g dW~/2;  a likewise
-                Zy_p, Zw_p, ay_p, aw_p = stage(tau, h, Zy, Zy, Zw, Zw, dWr, a_y, a_y, a_w, a_w, 0.5)
-                tl = float(np.float32(t0) + np.float32(k) * np.float32(h))
-                Zy, Zw, a_y, a_w = stage(tl, 0.5 * h, 0.5 * (Zy + Zy_p), Zy_p, 0.5 * (Zw + Zw_p), Zw_p, 0.5 * dWr,
-                                         0.5 * (a_y + ay_p), ay_p, 0.5 * (a_w + aw_p), aw_p, 1.0)
-            elif mid:
-                Zy_p, Zw_p, ay_p, aw_p = stage(tau, 0.5 * h, Zy, Zy, Zw, Zw, 0.5 * dWr, a_y, a_y, a_w, a_w, False)
-                tm = float(np.float32(t0) + np.float32(k) * np.float32(h) + np.float32(0.5) * np.float32(h))
-                Zy, Zw, a_y, a_w = stage(tm, h, Zy, Zy_p, Zw, Zw_p, dWr, a_y, ay_p, a_w, aw_p, True)
-            else:
-                Zy, Zw, a_y, a_w = stage(tau, h, Zy, Zy, Zw, Zw, dWr, a_y, a_y, a_w, a_w, True)
+        state = (Zy, Zw, a_y, a_w, *gacc)
+        if ctx.rev is None:
+            for k in range(n - 1, -1, -1):
+                tau = float(np.float32(t0) + np.float32(k + 1) * np.float32(h))
+                state = rev_step(tau, h, (-I[0, k]).contiguous(), state)
+        else:
+            # adjoint_adaptive=True: the step-doubling controller on the reverse solve (reverse time s = -t runs from -t1 to -t0;
+            # the error norm covers [Z_y, Z_w, a_y, a_w, a_params]), increments W(tau - h) - W(tau) from the queryable tree
+            tree, rtol, atol, dt0, t1 = ctx.rev
+
+            def one_step(sa, hh, st):
+                tau, hh = float(np.float32(-sa)), float(hh)
+                dWr = (tree(float(np.float32(tau) - np.float32(hh))) - tree(tau)).contiguous()
+                return rev_step(tau, hh, dWr, st)
+
+            ts_r, hs_r, state, _ = sdenet_adaptive_grid(one_step, -t1, -t0, dt0, rtol, atol, state)
+            global LAST_REVERSE_GRID
+            LAST_REVERSE_GRID = (ts_r, hs_r)
+        Zy, Zw, a_y, a_w = state[:4]
+        gacc = list(state[4:])
         global LAST_RECONSTRUCTION
         LAST_RECONSTRUCTION = (Zy, Zw)
-        return (None, None, None, None, None, a_y, a_w, *gacc)
+        return (None, None, None, None, None, None, a_y, a_w, *gacc)
 
 
 LAST_RECONSTRUCTION = None
+LAST_REVERSE_GRID = None
 
 
-def sdenet_solve_adjoint(cfg, x_nhwc, w0, linears, increments=None, seed=0, stream_id=0, final=None):
+def sdenet_solve_adjoint(cfg, x_nhwc, w0, linears, increments=None, seed=0, stream_id=0, final=None, rev=None):
     """As `sdenet_solve`, with the O(1)-memory reverse pass of `sdeint_adjoint`."""
     kl = []
     for W, b in linears:
         kl += [W.t().contiguous(), b]
-    return SDENetAdjointSolve.apply(cfg, increments, seed, stream_id, final, x_nhwc, w0, *kl)
+    return SDENetAdjointSolve.apply(cfg, increments, seed, stream_id, final, rev, x_nhwc, w0, *kl)
 
 
 def sdenet_solve(cfg, x_nhwc, w0, linears, increments=None, seed=0, stream_id=0):
@@ -710,8 +737,8 @@ class SDENet(nn.Module):
                 increments=None):
         """-> (logits, logqp).  `increments` [nsteps, P]: W(t_{k+1}) - W(t_k) to replay (else in-kernel Philox keyed by
         (self.seed, call counter), the stand-in for torchsde.BrownianInterval, models.py:190-193)."""
-        if adjoint_adaptive:
-            raise NotImplementedError("adaptive stepping of the reverse solve (adjoint_adaptive) is not built (SURVEY 8.6 N4)")
+        if adjoint_adaptive and not adjoint:
+            raise ValueError("adjoint_adaptive=True needs adjoint=True")
         if not y.is_cuda:
             raise _lib.BsdeError("bayesde_b200 kernels need CUDA tensors (there is no CPU fallback)")
         t0, t1 = float(self.ts[0]), float(self.ts[-1])
@@ -721,8 +748,8 @@ class SDENet(nn.Module):
         x = y.float().permute(0, 2, 3, 1).contiguous()[None]               # NHWC storage, S = 1
         lin = [(m.weight, m.bias) for m in self.w_net.linears()]
         self._calls += 1
-        if adaptive:
-            return self._forward_adaptive(x, lin, t0, t1, dt, method, rtol, atol, adjoint, nsteps)
+        if adaptive or adjoint_adaptive:
+            return self._forward_adaptive(x, lin, t0, t1, dt, method, rtol, atol, adjoint, nsteps, adaptive, adjoint_adaptive)
         cfg = self._config(y.shape[0], nsteps, dt, method)
         I = None if increments is None else increments[None]
         solve = sdenet_solve_adjoint if adjoint else sdenet_solve  # models.py:194: sdeint_adjoint / sdeint
@@ -734,7 +761,7 @@ class SDENet(nn.Module):
         logqp = .5 * lq[0]
         return logits, logqp
 
-    def _forward_adaptive(self, x, lin, t0, t1, dt, method, rtol, atol, adjoint=False, nsteps=0):
+    def _forward_adaptive(self, x, lin, t0, t1, dt, method, rtol, atol, adjoint=False, nsteps=0, adaptive=True, adjoint_adaptive=False):
         """`adaptive=True`: the accepted step grid is found by torchsde's step-doubling loop on a queryable Philox Brownian tree over
         the P weight rows (the stand-in for BrownianInterval: any interval's increment is W(tb) - W(ta)), without autograd; the
         solve is then replayed on that grid through `sdenet_solve` so that `loss.backward()` differentiates the accepted steps."""
@@ -751,17 +778,21 @@ class SDENet(nn.Module):
             y1, kl, wtraj = sdenet_solve(cfg1, yy, ww, lin, inc([ta], [h]))
             return y1, wtraj[0, cfg1.nit].contiguous(), lq + kl[0]
 
-        with torch.no_grad():
-            state0 = (x, self.flat_initial_params.detach().float().contiguous(), torch.zeros((), device=x.device))
-            ts, hs, final, nsingle = sdenet_adaptive_grid(one_step, t0, t1, dt, rtol, atol, state0)
-        self.adaptive_grid = (ts, hs)
+        final, nsingle = None, nsteps
+        if adaptive:
+            with torch.no_grad():
+                state0 = (x, self.flat_initial_params.detach().float().contiguous(), torch.zeros((), device=x.device))
+                ts, hs, final, nsingle = sdenet_adaptive_grid(one_step, t0, t1, dt, rtol, atol, state0)
+            self.adaptive_grid = (ts, hs)
+            final = (final[0], final[2].reshape(1), final[1])
         if adjoint:
             # sdeint_adjoint(adaptive=True, adjoint_adaptive=False): adaptive forward solve, reverse solve with fixed steps `dt` on
             # the same path (the tree's increments over the uniform grid), started from the adaptive solve's final state
             cfg = self._config(x.shape[1], nsteps, dt, method)
             tu = [np.float32(t0) + np.float32(k) * np.float32(dt) for k in range(nsteps)]
+            rev = (tree, rtol, atol, dt, t1) if adjoint_adaptive else None
             y1, lq, _ = sdenet_solve_adjoint(cfg, x, self.flat_initial_params, lin, inc(tu, [np.float32(dt)] * nsteps),
-                                             final=(final[0], final[2].reshape(1), final[1]))
+                                             final=final, rev=rev)
         else:
             cfg = mk(ts, hs)
             y1, lq, _ = sdenet_solve(cfg, x, self.flat_initial_params, lin, inc(ts, hs))

@@ -186,7 +186,8 @@ class SDENetOracle:
             return y, w, lq, torch.stack(path)
         return y, w, lq
 
-    def adjoint(self, yT, wT, cot_y, cot_w, cot_lq, w_layers, increments, dt=0.05, method="midpoint", t0=0.0, t1=1.0):
+    def adjoint(self, yT, wT, cot_y, cot_w, cot_lq, w_layers, increments, dt=0.05, method="midpoint", t0=0.0, t1=1.0,
+                reverse_grid=None):
         """The reverse pass of `torchsde.sdeint_adjoint` (call site models.py:184-197 with `adjoint=True`; torchsde is an un-pinned git
         dependency that is absent here, so this restates the published scheme: Li et al., "Scalable gradients for stochastic
         differential equations", AISTATS 2020, Alg. 2).  The augmented state [y, w | a_y, a_w, a_lq | a_params] is integrated from t1 back
@@ -197,7 +198,7 @@ class SDENetOracle:
             d a_par   = +(df/dparams)^T a ds
         a_lq stays cot_lq (no drift reads logqp).  Returns (y0_rec, w0_rec, dL/dy0, dL/dw0, [dL/d(W, b) per w_net layer])."""
         n = int(round((t1 - t0) / dt))
-        assert increments.shape[0] == n
+        assert reverse_grid is not None or increments.shape[0] == n
         params = [t for lay in w_layers for t in lay]
         y, w, ay, aw = yT.detach(), wT.detach(), cot_y.detach(), cot_w.detach()
         ap = [torch.zeros_like(p) for p in params]
@@ -213,9 +214,7 @@ class SDENetOracle:
             gs = [torch.zeros_like(q) if g is None else g for g, q in zip(gs, [y_, w_] + ps)]
             return fy.detach(), fw.detach(), gs[0], gs[1], gs[2:]
 
-        for k in range(n - 1, -1, -1):
-            tau = t0 + (k + 1) * dt
-            dWr = -increments[k]
+        def rev_step(tau, dt, dWr, y, w, ay, aw, ap):
             fy, fw, vy, vw, vp = F(tau, y, w, ay, aw)
             if method == "midpoint":
                 y_p, w_p = y - 0.5 * dt * fy, w - 0.5 * dt * fw + 0.5 * self.sigma * dWr
@@ -237,6 +236,18 @@ class SDENetOracle:
                 ap = [a + dt * v for a, v in zip(ap, vp)]
             else:
                 raise ValueError(f"Unknown method: {method}")
+            return y, w, ay, aw, ap
+
+        if reverse_grid is not None:   # (s_k, h_k) of an adaptive reverse solve, s = -t; bm(t) -> W(t)
+            import numpy as np
+            bm, ts_r, hs_r = reverse_grid
+            for sa, h in zip(ts_r, hs_r):
+                tau = float(np.float32(-sa))
+                dWr = bm(float(np.float32(tau) - np.float32(h))) - bm(tau)
+                y, w, ay, aw, ap = rev_step(tau, float(h), dWr, y, w, ay, aw, ap)
+            return y, w, ay, aw, ap
+        for k in range(n - 1, -1, -1):
+            y, w, ay, aw, ap = rev_step(t0 + (k + 1) * dt, dt, -increments[k], y, w, ay, aw, ap)
         return y, w, ay, aw, ap
 
     # ---- adaptive stepping: torchsde's step-doubling controller (un-pinned git dependency, absent here; restated from the published

@@ -128,8 +128,8 @@ def test_sdenet_module_surface(built_lib):
     assert {"flat_initial_params", "w_net.layers.0.weight", "w_net.layers.4.bias", "projection.1.weight", "projection.3.bias",
             "ts", "aug_zeros"} <= keys
     assert m.params_size == m.y_net.P and float(m.w_net.linears()[-1].weight.abs().max()) == 0.0
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 2, 8, 8), adjoint_adaptive=True)
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 2, 8, 8), adjoint_adaptive=True)      # needs adjoint=True
     with pytest.raises(_lib.BsdeError):
         m(torch.zeros(1, 2, 8, 8), adaptive=True)
     with pytest.raises(_lib.BsdeError):
@@ -376,7 +376,7 @@ def test_gpu_sdenet_adjoint_matches_oracle(built_lib, method, math_mode):
 @pytest.mark.gpu
 def test_gpu_sdenet_module_adjoint_flag(built_lib):
     """SDENet.forward(adjoint=True): same logits / logqp as the plain route on the same path (replayed and in-kernel Philox), gradients
-    within the O(h^2) gap of the two reverse passes; the adaptive options still raise."""
+    within the O(h^2) gap of the two reverse passes."""
     from bayesde_b200 import torch_models as tm
     torch.manual_seed(0)
     m = tm.SDENet(input_size=(2, 8, 8), blocks=(1, 1), weight_network_sizes=(1, 8, 1), hidden_width=4, aug_dim=1, sigma=0.2, math="fp32").to(DEV)
@@ -396,8 +396,8 @@ def test_gpu_sdenet_module_adjoint_flag(built_lib):
     for k in outs[0][2]:
         a, b = outs[1][2][k], outs[0][2][k]
         assert float((a - b).abs().max()) <= 2e-2 * float(b.abs().max()) + 1e-8, (k, float((a - b).abs().max()), float(b.abs().max()))
-    with pytest.raises(NotImplementedError):
-        m(x, adjoint=True, adjoint_adaptive=True)
+    with pytest.raises(ValueError):
+        m(x, adjoint_adaptive=True)                                                # needs adjoint=True
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -528,5 +528,22 @@ def test_gpu_sdenet_adaptive(built_lib, method):
     for i, l in enumerate(m.w_net.linears()):
         _close(l.weight.grad, ap[2 * i], 1e-3, f"dL/d w_net[{i}].weight (adaptive + adjoint)")
         _close(l.bias.grad, ap[2 * i + 1], 1e-3, f"dL/d w_net[{i}].bias (adaptive + adjoint)")
-    with pytest.raises(NotImplementedError):
-        m(x, adaptive=True, adjoint=True, adjoint_adaptive=True)
+    # adjoint_adaptive=True: the controller also drives the reverse solve; oracle reverse pass ON THE PRODUCT'S accepted reverse grid
+    m.zero_grad()
+    m._calls = 0
+    l4, q4 = m(x, dt=dt, method=method, adaptive=True, adjoint=True, adjoint_adaptive=True, rtol=1e-3, atol=1e-3)
+    assert torch.equal(l4, l3) and torch.equal(q4, q3)
+    (l4.logsumexp(1).mean() + 1e-3 * q4).backward()
+    ts_r, hs_r = tm.LAST_REVERSE_GRID
+    assert len(ts_r) >= 4 and abs(float(ts_r[0]) + 1.0) < 1e-6 and abs(sum(float(h) for h in hs_r) - 1.0) < 1e-5
+    y0r, w0r, ay, aw, ap = net.adjoint(y3, w3, cot_y, torch.zeros_like(w3), torch.tensor(0.5e-3, dtype=torch.float64),
+                                       [(W.detach(), b.detach()) for W, b in wl], None, dt=dt, method=method, reverse_grid=(bm, ts_r, hs_r))
+    _close(m.flat_initial_params.grad, aw, 1e-3, "dL/dw0 (adjoint_adaptive)")
+    for i, l in enumerate(m.w_net.linears()):
+        _close(l.weight.grad, ap[2 * i], 1e-3, f"dL/d w_net[{i}].weight (adjoint_adaptive)")
+    Zy, Zw = tm.LAST_RECONSTRUCTION
+    _close(Zw, w0r, 1e-3, "reconstructed w0 (adjoint_adaptive)")
+    # the reverse solve reconstructs w0 only up to the discretisation of both adaptive solves (different grids, sigma = 0.2)
+    assert float((Zw.double().cpu() - dd(m.flat_initial_params)).abs().max()) < 0.15 * float(dd(m.flat_initial_params).abs().max())
+    with pytest.raises(ValueError):
+        m(x, adjoint_adaptive=True)
