@@ -416,8 +416,13 @@ def run_ours(args):
                         "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0, "peak": peak_hbm,
                         "unit": "GB/s", "frac": (k1_bytes / (k1_ms * 1e-3) / 1e9 / peak_hbm) if k1_ms > 0 else 0.0,
                         "algorithmic_bytes_per_step": k1_bytes, "kernel_ms_per_step": k1_ms,
-                        "note": "48*P B per (sample, block, iteration) fwd, 2x bwd; state is L2-resident so "
-                                "frac may exceed 1"},
+                        # ncu --set full of wsde_fwd_kernel (profiles/r01m_wsde_full_summary.csv, group-0 block, S = 8, 19 iterations):
+                        # 3.0 MB read + 3.0-3.8 MB written per launch against 594 MB algorithmic -- the state and the f_w parameters
+                        # stay in the 126 MB L2, so this kernel is NOT HBM-bound: issue active 18 %, 8 warps per SM, one grid barrier
+                        # per iteration (29 us per iteration, of which ~1.4 us per sample is arithmetic)
+                        "traffic": 6.0e6,
+                        "note": "48*P B per (sample, block, iteration) fwd, 2x bwd (SURVEY 8.4 model); measured DRAM traffic is 1 % of it "
+                                "(L2-resident), the kernel is latency / barrier bound, so this fraction is a model figure, not a bound"},
         "kernel_ms_per_step": {k: v / args.steps for k, v in ktime.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
