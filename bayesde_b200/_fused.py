@@ -217,7 +217,9 @@ class SDEBNNSolve(torch.autograd.Function):
         with _Timed("k1_fwd"):
             wtraj, z1, kl = wsde_forward(cfg, w0c, layers, dW, seed, stream_id, w_stale)
         with _Timed("k2_fwd"):
-            xs, acts = xpath_forward(cfg, x, wtraj, keep_acts=(not cfg.remat) and any(ctx.needs_input_grad))
+            # under torch.no_grad() (evaluation) nothing will be differentiated, but needs_input_grad only reflects requires_grad and
+            # grad mode is always off inside forward(): the caller records it in cfg.track before apply()
+            xs, acts = xpath_forward(cfg, x, wtraj, keep_acts=(not cfg.remat) and getattr(cfg, "track", True) and any(ctx.needs_input_grad))
         ctx.cfg = cfg
         ctx.layers = layers
         ctx.w0_per_sample = w0.dim() == 2
@@ -333,7 +335,7 @@ class SDEBNNAdjointSolve(torch.autograd.Function):
                 tau, W_n = -r, bm(-rn)
                 cfg.set_step(tau, -h)
                 wtraj, z1, _ = wsde_forward(cfg, Yw, layers, (W_n - W_t).view(S, 1, P), 0, 0, ctx.w_stale)
-                xs, acts = xpath_forward(cfg, Yx, wtraj, keep_acts=True)
+                xs, acts = xpath_forward(cfg, Yx, wtraj, keep_acts=not cfg.remat)   # remat: K3 recomputes them from Y
                 cfg.set_step(tau, h)
                 a_x, gw_traj = xpath_backward(cfg, xs, wtraj, a_x, acts)
                 a_w, gl = wsde_backward(cfg, layers, wtraj, z1, gw_traj, gkl, a_w, True)

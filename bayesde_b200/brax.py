@@ -98,6 +98,7 @@ class _AugDynamics:
         else:
             dW, seed, sid = None, int(rng), self.stream_id
         flat = [t for lay in layers for t in lay]
+        cfg.track = torch.is_grad_enabled()
         return _fused.SDEBNNSolve.apply(cfg, dW, seed, sid, self.w_stale, x, w0, *flat)
 
     def _solve_adjoint(self, y0, ts, rng, args, dt, method, rep):

@@ -371,7 +371,7 @@ class SDENetSolve(torch.autograd.Function):
         x = x.contiguous()
         desc = cfg.ynet.chain_desc(S, B, cfg.math)
         nacts, ooff = L.bsde_chain_acts_floats(C.byref(desc)), L.bsde_chain_out_offset(C.byref(desc))
-        keep = (not cfg.remat) and any(ctx.needs_input_grad)
+        keep = (not cfg.remat) and getattr(cfg, "track", True) and any(ctx.needs_input_grad)   # cfg.track: grad mode at the call site
         store = torch.empty(nit if keep else 1, nacts, device=dev, dtype=torch.float32)
         ys = torch.empty((n + 1,) + tuple(x.shape), device=dev, dtype=torch.float32)
         ys[0].copy_(x)
@@ -501,6 +501,7 @@ class SDENetAdjointSolve(torch.autograd.Function):
             raise ValueError(f"increments must have shape {(S, n, P)}, got {tuple(I.shape)}")
         I = I.float().contiguous()
         if final is None:
+            cfg.track = False
             with torch.no_grad():
                 yT, kl, wtraj = SDENetSolve.apply(cfg, I, 0, 0, x.detach(), w0.detach(), *[t.detach() for t in flat])
             wT = wtraj[0, cfg.nit].contiguous()
@@ -632,6 +633,7 @@ def sdenet_solve(cfg, x_nhwc, w0, linears, increments=None, seed=0, stream_id=0)
     kl = []
     for W, b in linears:
         kl += [W.t().contiguous(), b]      # kernel layout: W1 [P,d1], Wm [din,dout], W4 [dL,P]
+    cfg.track = torch.is_grad_enabled()
     return SDENetSolve.apply(cfg, increments, seed, stream_id, x_nhwc, w0, *kl)
 
 
