@@ -279,6 +279,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is VERSION / INFO
+        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
