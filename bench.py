@@ -278,9 +278,11 @@ def run_ours(args):
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # keep stdout to the one JSON line: NCCL writes its version banner to fd 1 from C, so fd 1 points at stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG is VERSION / INFO
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
@@ -356,6 +358,9 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
 
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
