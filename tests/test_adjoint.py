@@ -454,15 +454,15 @@ def test_oracle_block_adjoint_close_to_backprop():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("stl", [False, True])
-def test_gpu_sdebnn_block_stochastic_adjoint(built_lib, stl):
+@pytest.mark.parametrize("stl,remat", [(False, False), (True, False), (False, True)])
+def test_gpu_sdebnn_block_stochastic_adjoint(built_lib, stl, remat):
     """`apply_fun(..., fixed_grid=False, dt=...)` through the reference-shaped layer API against the oracle's sdeint_ito + stochastic
     adjoint on the same Philox tree: x_T / w(t) 1e-4, KL 1e-4 relative, reconstructed y0 and every gradient 2e-3 of the largest entry."""
     from bayesde_b200 import _fused, arch, brax
     blk, w0, fw, x, cot = _adjoint_case(stl)
     dt, kl_w, seed, sid = 0.07, 1e-3, 11, 3
     fw_layer = arch.MLP((2, 8, 2), actfn="softplus", xt=True, ou_dw=True)
-    layer = brax.SDEBNN(0, 8, "softplus", fw_layer, diff_coef=0.2, stl=stl, xt=True, nsteps=blk.nsteps, stream_id=sid)
+    layer = brax.SDEBNN(0, 8, "softplus", fw_layer, diff_coef=0.2, stl=stl, xt=True, nsteps=blk.nsteps, stream_id=sid, remat=remat)
     _, (w_stale_like, _, _) = layer.init(0, tuple(x.shape[1:]))
     blk.w_stale = w_stale_like.double()
     res, unravel = _oracle_block_adjoint(blk, w0, fw, x, seed, sid, dt, cot, kl_w)
