@@ -173,3 +173,35 @@ def test_gpu_sdebnn_block_with_jax_keys(built_lib):
     xo2, kl2, info2 = layer.apply(params, x, dW, full_output=True)
     assert torch.allclose(xo, xo2, rtol=1e-4, atol=1e-5) and torch.allclose(kl, kl2, rtol=1e-4, atol=1e-4)
     assert torch.allclose(info["sdebnn_w"], info2["sdebnn_w"], rtol=1e-5, atol=2e-6)
+
+
+def test_tree_increments_follow_the_scan_bookkeeping():
+    """Host logic of `tree_increments`: with time_grid="reference" the queries are bm(next_t) - bm(curr_t) with next_t = target - curr
+    (quirk Q1: the scan's own bookkeeping, jaxsde/jaxsde/sdeint.py:103-110), with "uniform" the intended ts[k] - ts[k-1] pairs."""
+    from bayesde_b200.sdeint import tree_increments
+
+    class FakeTree:
+        def __init__(self):
+            self.calls = []
+
+        def query(self, t, first=0, count=None):
+            self.calls.append((float(np.float32(t)), first, count))
+            return torch.full((3,), float(t))
+
+    ts = np.linspace(0.0, 1.0, 5, dtype=np.float32)
+    bm = FakeTree()
+    inc = tree_increments(bm, ts, "reference", 2, 3)
+    f32 = np.float32
+    want, curr = [], ts[0]
+    for k in range(1, 5):
+        nxt = f32(ts[k] - curr)
+        want.append((float(nxt), float(curr)))
+        curr = nxt
+    got = [(bm.calls[2 * i][0], bm.calls[2 * i + 1][0]) for i in range(4)]
+    assert got == want and all(c[1:] == (2, 3) for c in bm.calls)
+    assert inc.shape == (4, 3) and torch.allclose(inc[:, 0], torch.tensor([a - b for a, b in want]))
+    assert [w[0] for w in want] == [0.25, 0.25, 0.5, 0.5]            # dt = 0.25, 0, 0.25, 0: the zero steps of quirk Q1
+    bm2 = FakeTree()
+    inc2 = tree_increments(bm2, torch.from_numpy(ts), "uniform")
+    assert [(bm2.calls[2 * i][0], bm2.calls[2 * i + 1][0]) for i in range(4)] == [(0.25, 0.0), (0.5, 0.25), (0.75, 0.5), (1.0, 0.75)]
+    assert torch.allclose(inc2, torch.full((4, 3), 0.25))

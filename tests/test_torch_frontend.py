@@ -547,3 +547,35 @@ def test_gpu_sdenet_adaptive(built_lib, method):
     assert float((Zw.double().cpu() - dd(m.flat_initial_params)).abs().max()) < 0.15 * float(dd(m.flat_initial_params).abs().max())
     with pytest.raises(ValueError):
         m(x, adjoint_adaptive=True)
+
+
+def test_solve_config_tables_for_explicit_grids(built_lib):
+    """Host logic: `SolveConfig(grid=(t_k, h_k))` gives the same stage tables as the uniform constructor when the grid is uniform, and the
+    per-step entries follow each scheme's definition on a non-uniform grid (midpoint: (t, t + h/2), dt (h/2, h), KL step (0, h), noise
+    (sqrt(h)/2, sqrt(h)), back (0, 1); heun: (t, t + h), (h, h/2), (h/2, h/2), (sqrt(h), sqrt(h)/2), back (0, 2); Euler-type: no tables)."""
+    from bayesde_b200 import torch_models as tm
+    ynet, _ = tm.make_y_net((2, 8, 8), (1, 1), hidden_width=4, aug_dim=1)
+    f32 = np.float32
+    for method in ("midpoint", "heun", "milstein"):
+        u = tm.SolveConfig(ynet, 1, 3, 4, 0.25, method, 0.1, (1, 8, 1), "tanh", "fp32", False)
+        g = tm.SolveConfig(ynet, 1, 3, 0, 0.0, method, 0.1, (1, 8, 1), "tanh", "fp32", False,
+                           grid=([f32(0.25) * f32(k) for k in range(4)], [f32(0.25)] * 4))
+        assert u.uniform and not g.uniform and u.n == g.n == 4 and u.nit == g.nit
+        for name in ("tk", "dtk", "dtkl", "nscale", "nidx", "back"):
+            a, b = getattr(u, name), getattr(g, name)
+            assert (a is None and b is None) or np.array_equal(a, b), (method, name)
+    ts, hs = [0.0, 0.1, 0.4], [0.1, 0.3, 0.6]
+    m = tm.SolveConfig(ynet, 1, 3, 0, 0.0, "midpoint", 0.1, (1, 8, 1), "tanh", "fp32", False, grid=(ts, hs))
+    assert np.allclose(m.tk, [0.0, 0.05, 0.1, 0.25, 0.4, 0.7]) and np.allclose(m.dtk, [0.05, 0.1, 0.15, 0.3, 0.3, 0.6])
+    assert np.allclose(m.dtkl, [0, 0.1, 0, 0.3, 0, 0.6]) and m.back.tolist() == [0, 1] * 3 and m.nidx.tolist() == [0, 0, 1, 1, 2, 2]
+    assert np.allclose(m.nscale, [0.5 * 0.1 ** 0.5, 0.1 ** 0.5, 0.5 * 0.3 ** 0.5, 0.3 ** 0.5, 0.5 * 0.6 ** 0.5, 0.6 ** 0.5])
+    h = tm.SolveConfig(ynet, 1, 3, 0, 0.0, "heun", 0.1, (1, 8, 1), "tanh", "fp32", False, grid=(ts, hs))
+    assert np.allclose(h.tk, [0.0, 0.1, 0.1, 0.4, 0.4, 1.0]) and np.allclose(h.dtk, [0.1, 0.05, 0.3, 0.15, 0.6, 0.3])
+    assert np.allclose(h.dtkl, [0.05, 0.05, 0.15, 0.15, 0.3, 0.3]) and h.back.tolist() == [0, 2] * 3
+    I = torch.arange(6.0).reshape(1, 3, 2)
+    assert torch.equal(m.stage_increments(I)[0, :, 0], torch.tensor([0.0, 0.0, 1.0, 2.0, 2.0, 4.0]))
+    assert torch.equal(h.stage_increments(I)[0, :, 0], torch.tensor([0.0, 0.0, 2.0, 1.0, 4.0, 2.0]))
+    e = tm.SolveConfig(ynet, 1, 3, 0, 0.0, "euler_heun", 0.1, (1, 8, 1), "tanh", "fp32", False, grid=(ts, hs))
+    assert e.nit == 3 and e.back is None and np.allclose(e.dtk, hs) and e.hs == [float(f32(v)) for v in hs]
+    with pytest.raises(ValueError, match="Unknown method"):
+        tm.SolveConfig(ynet, 1, 3, 4, 0.25, "srk", 0.1, (1, 8, 1), "tanh", "fp32", False)
