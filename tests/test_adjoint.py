@@ -604,3 +604,22 @@ def test_gpu_classifier_with_stochastic_adjoint(built_lib):
     logp2, kl2, _ = run(3)
     logp3, _, _ = run(4)
     assert torch.equal(logp, logp2) and torch.equal(kl, kl2) and not torch.equal(logp, logp3)
+
+
+def test_oracle_noise_only_integration_is_the_brownian_path():
+    """jaxsde/tests/test_sdeint.py:39-53 for the variable-step path: with f = 0, g = 1 the solve telescopes to W(t) - W(t0) at the time
+    the loop has reached when it emits each row (interior targets are overshot: the product's `ito_step_schedule` gives those times)."""
+    from bayesde_b200._fused import ito_step_schedule
+    n = 5
+    ts = [0.0, 0.3, 0.55, 1.0]
+    dt = 0.1
+    bm = ja.BrownianTree(3, 0, n, ts[0], ts[-1])
+    zero = lambda y, t, a: torch.zeros_like(y)
+    one = lambda y, t, a: torch.ones_like(y)
+    for method in ("euler_maruyama", "milstein"):
+        ys = ja.ito_integrate(zero, one, torch.zeros(n, dtype=torch.float64), ts, bm, dt, method=method)
+        steps, marks = ito_step_schedule(ts, dt)
+        reached = [ts[0]] + [float(steps[m - 1][2]) for m in marks]
+        assert reached[1] > ts[1] - 1e-6 and abs(reached[-1] - 1.0) < 1e-6
+        for row, t in zip(ys, reached):
+            assert torch.allclose(row, bm(t) - bm(ts[0]), rtol=0, atol=1e-6)
