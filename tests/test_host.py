@@ -162,3 +162,21 @@ def test_gradient_allreduce_gloo_world2(tmp_path):
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_sass_carries_the_blackwell_instructions(built_lib):
+    """Static evidence that the hot kernels are the sm_100a tensor-core / TMA code and not a recompiled legacy path: the library's SASS
+    holds tcgen05.mma (UTCHMMA), tcgen05.ld (LDTM), tcgen05.commit (UTCBAR), TMA tensor loads (UTMALDG) and mbarrier waits (SYNCS), and
+    the conv / wgrad kernels are compiled for sm_100a (profiles/r01_summary.md section 3)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", built_lib], capture_output=True, text=True, check=True).stdout
+    assert "arch = sm_100a" in sass
+    for mnemonic, least in (("UTCHMMA", 50), ("LDTM", 10), ("UTCBAR", 20), ("UTMALDG", 20), ("SYNCS", 100)):
+        assert sass.count(mnemonic) >= least, (mnemonic, sass.count(mnemonic))
+    for kernel in ("conv_win_kernel", "wgrad_win_kernel", "wsde_fwd_kernel", "wsde_bwd_kernel", "brownian_tree_threefry_kernel"):
+        assert kernel in sass, kernel
+    assert "HMMA.16816" not in sass and "HGMMA" not in sass        # no mma.sync / wgmma tensor-core path in the library
