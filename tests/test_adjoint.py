@@ -623,3 +623,68 @@ def test_oracle_noise_only_integration_is_the_brownian_path():
         assert reached[1] > ts[1] - 1e-6 and abs(reached[-1] - 1.0) < 1e-6
         for row, t in zip(ys, reached):
             assert torch.allclose(row, bm(t) - bm(ts[0]), rtol=0, atol=1e-6)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# committed golden fixture of the block adjoint (tests/golden/make_golden_adjoint.py)
+# --------------------------------------------------------------------------------------------------------------
+def _load_adjoint_golden():
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "jax_block_adjoint.npz"))
+    S, B, H, Cc, fx_dim, nsteps, seed, sid = [int(v) for v in z["meta"]]
+    nfw = len(z["fw_dims"])
+    fw = [tuple(torch.from_numpy(z[f"fw{i}_{n}"]) for n in ("W", "b", "wt", "wtb", "bt")) for i in range(nfw + 1)]
+    return z, (S, B, H, Cc, fx_dim, nsteps, seed, sid), fw
+
+
+def test_oracle_reproduces_adjoint_golden():
+    from oracle import jax_path as jp
+    z, (S, B, H, Cc, fx_dim, nsteps, seed, sid), fw = _load_adjoint_golden()
+    blk = jp.SDEBNNBlock((B, H, H, Cc), 0, fx_dim, "softplus", "softplus", float(z["sigma"]), False, nsteps)
+    blk.w_stale = torch.zeros(blk.P, dtype=torch.float64)
+    x, w0, cot = (torch.from_numpy(z[k]) for k in ("x", "w0", "cot"))
+    res, unravel = _oracle_block_adjoint(blk, w0, fw, x, seed, sid, float(z["dt"]), cot, float(z["kl_w"]))
+    P, x_dim = blk.P, blk.x_dim
+    for s, (ys, y0_rec, y_adj, a_adj) in enumerate(res):
+        np.testing.assert_allclose(ys[-1][:x_dim].numpy(), z["xT"][s], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(ys[:, x_dim:x_dim + P].numpy(), z["wrows"][s], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(float(ys[-1][x_dim + P:].sum()), z["kl"][s], rtol=1e-10)
+        np.testing.assert_allclose(y_adj[:x_dim].numpy(), z["grad_x"][s], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(sum(r[2][x_dim:x_dim + P] for r in res).numpy(), z["grad_w0"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_block_adjoint_matches_committed_golden(built_lib):
+    """The CUDA route (`apply_fun(fixed_grid=False)`) against the committed fixture: values 1e-4, reconstruction and gradients 2e-3 of max."""
+    from bayesde_b200 import _fused, arch, brax
+    z, (S, B, H, Cc, fx_dim, nsteps, seed, sid), fw = _load_adjoint_golden()
+    dev = "cuda:0"
+    layer = brax.SDEBNN(0, fx_dim, "softplus", arch.MLP(tuple(int(v) for v in z["fw_dims"]), actfn="softplus", xt=True, ou_dw=True),
+                        diff_coef=float(z["sigma"]), stl=False, xt=True, nsteps=nsteps, stream_id=sid)
+    w0d = torch.from_numpy(z["w0"]).float().to(dev).requires_grad_(True)
+    tree = []
+    for i, lay in enumerate(fw):
+        tree.append(tuple(t.float().to(dev).contiguous().requires_grad_(True) for t in lay))
+        if i < len(fw) - 1:
+            tree.append(())
+    fwd = ((), tree)
+    xd = torch.from_numpy(z["x"]).float().to(dev).requires_grad_(True)
+    xo, kl, info = layer.apply((w0d, (), fwd), xd, seed, full_output=True, fixed_grid=False, dt=float(z["dt"]))
+    assert torch.allclose(xo.detach().cpu().double().reshape(S, -1), torch.from_numpy(z["xT"]), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(info["sdebnn_w"].detach().cpu().double(), torch.from_numpy(z["wrows"]), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(kl.detach().cpu().double(), torch.from_numpy(z["kl"]), rtol=1e-4)
+    obj = (xo * torch.from_numpy(z["cot"]).float().to(dev)).sum() + float(z["kl_w"]) * kl.sum()
+    leaves = [xd, w0d] + [t for lay in arch.fw_layers(fwd) for t in lay]
+    grads = torch.autograd.grad(obj, leaves)
+
+    def close(a, b, what):
+        a, b = a.detach().cpu().double(), torch.from_numpy(np.asarray(b)).double()
+        assert float((a - b).abs().max()) <= 2e-3 * float(b.abs().max()) + 1e-9, (what, float((a - b).abs().max()), float(b.abs().max()))
+
+    x0r, w0r = _fused.LAST_RECONSTRUCTION
+    close(x0r.reshape(S, -1), z["x0_rec"], "reconstructed x0")
+    close(w0r, z["w0_rec"], "reconstructed w0")
+    close(grads[0].reshape(S, -1), z["grad_x"], "grad x")
+    close(grads[1], z["grad_w0"], "grad w0")
+    for i, g_ in enumerate(grads[2:]):
+        close(g_, z[f"grad_fw{i}"], f"grad fw tensor {i}")
