@@ -136,13 +136,19 @@ def ptr(t):
         return None
     if not t.is_cuda:
         raise BsdeError("bayesde_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        # libbsde.so launches on the CUDA current device and on torch's current stream of that device; a tensor living on
+        # another GPU would be dereferenced by the wrong context
+        raise BsdeError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: wrap the call in "
+                        f"`with torch.cuda.device({t.device.index}):` (one process per GPU is the supported layout)")
     if t.dtype != torch.float32 or not t.is_contiguous():
         raise ValueError(f"expected a contiguous float32 tensor, got {t.dtype} contiguous={t.is_contiguous()}")
     return C.c_void_p(t.data_ptr())
 
 
 def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """torch's current stream on the current device (ptr() guarantees that the tensors of the call live there)."""
+    return C.c_void_p(torch.cuda.current_stream(torch.cuda.current_device()).cuda_stream)
 
 
 _ws_cache = {}

@@ -144,7 +144,10 @@ class FxSpec:
             convs = [(C, fx_dim, 3, 1, False), (fx_dim, fx_dim, 3, 2, False), (fx_dim, fx_dim, 3, 2, True),
                      (fx_dim, C, 3, 1, False)]
         elif block_type == 1:
-            convs = [(C, fx_dim, 3, 1, False), (fx_dim, fx_dim, 1, 1, False), (fx_dim, C, 3, 1, False)]
+            # arch.py:193 writes ConcatConv2D(fx_dim, (1, 1), padding="SAME"), but the tuple binds to the unused `W_init`
+            # positional (diffeq_layers.py:124: ConcatConv2D(out_dim, W_init, b_init, kernel=3, ...)), so the middle
+            # convolution of block type 1 is 3x3 as shipped (same mechanism as quirk Q12); kept for parity
+            convs = [(C, fx_dim, 3, 1, False), (fx_dim, fx_dim, 3, 1, False), (fx_dim, C, 3, 1, False)]
         elif block_type == 2:
             convs = [(C, fx_dim, 3, 1, False), (fx_dim, C, 3, 1, False)]
         else:

@@ -273,17 +273,21 @@ def MeanField(layer, prior_std=0.1, disable=False):
         leaves = tree_leaves(params_mean)
         sampled = kwargs.pop("mc_samples", None)
         S = sampled if sampled is not None else None
+        # brax.py:150,165: the key is split and the wrapped layer receives `rng=next_rng` (a stochastic wrapped layer, e.g.
+        # MeanField(SDEBNN(..., stax_api=True)) of --meanfield_sdebnn, draws its Brownian path from it)
+        explicit = isinstance(rng, (tuple, list)) and len(rng) == 2 and isinstance(rng[1], torch.Tensor)
+        base = rng[0] if explicit else rng
+        rng_eps, rng_next = split(base, 2) if base is not None else (None, None)
         if not leaves:  # parameter-free layer: kl = sum over an empty vector
-            out = apply_fun(params_mean, input, **kwargs)
+            out = apply_fun(params_mean, input, rng=rng_next, **kwargs)
             return out, input.new_zeros(S) if S else input.new_zeros(())
         flat_mean = torch.cat([t.reshape(-1) for t in leaves])
         flat_logstd = torch.cat([t.reshape(-1) for t in tree_leaves(params_logstd)])
-        if isinstance(rng, (tuple, list)) and len(rng) == 2 and isinstance(rng[1], torch.Tensor):
+        if explicit:
             eps = rng[1]
         else:
-            rng, _next = split(rng, 2)
             shape = (S, flat_mean.numel()) if S else (flat_mean.numel(),)
-            eps = torch.randn(shape, generator=_gen(rng, flat_mean.device), device=flat_mean.device)
+            eps = torch.randn(shape, generator=_gen(rng_eps, flat_mean.device), device=flat_mean.device)
         if disable:
             flat_params = flat_mean.expand_as(eps) if S else flat_mean
             kl = flat_params.new_zeros(flat_params.shape)
@@ -292,7 +296,7 @@ def MeanField(layer, prior_std=0.1, disable=False):
             kl = normal_logprob(flat_params, flat_mean, flat_logstd) - normal_logprob(
                 flat_params, 0.0, math.log(prior_std))
         p = _unflatten_like(flat_params, params_mean, lead=1 if S else 0)
-        output = apply_fun(p, input, **kwargs)
+        output = apply_fun(p, input, rng=rng_next, **kwargs)
         return output, kl.sum(-1)
 
     return Layer(wrapped_init_fun, wrapped_apply_fun)

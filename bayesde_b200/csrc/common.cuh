@@ -4,11 +4,25 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/bsde.h"
 
 namespace bsde {
 
 void set_error(const char* fmt, ...);
+
+// One-time per-DEVICE initialisation (function attributes, symbol addresses are per device / context: a process that drives
+// several GPUs must repeat them on each).  `first()` is true the first time it is called while device d is current.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done[4];
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long m = 1ull << (d & 63);
+    return (done[(d >> 6) & 3].fetch_or(m) & m) == 0;
+  }
+};
 void count_launch(int n = 1);  // bookkeeping for bsde_launch_count()
 
 #define BSDE_CHECK_ARG(cond, ...)        \
@@ -37,6 +51,8 @@ __device__ __forceinline__ float rbf_fwd_tagged(float x) {
 }
 // d/dx exp(-x^2) = -2 x a from the tagged output a
 __device__ __forceinline__ float rbf_grad_from_tagged(float a) {
+  // a == 0 (|x| > ~10.2: expf underflows) would give -log(0) = inf and inf * 0 = NaN; the true derivative is 0 there
+  if (!(fabsf(a) >= 1.17549435e-38f)) return 0.f;
   const float ax = sqrtf(fmaxf(-logf(a), 0.f));
   return (__float_as_uint(a) & 1u) ? 2.f * ax * a : -2.f * ax * a;
 }

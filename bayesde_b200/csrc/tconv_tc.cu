@@ -671,12 +671,11 @@ int tconv_fwd_tc(const bsde_conv_layer* L, int S, int B, const float* in, const 
                       (size_t)maxkb * (L->cin % 4 == 0 ? 8 : 32) * 8;
   const int Mcls = L->sd == 2 ? B * ((L->hout + 1) / 2) * ((L->wout + 1) / 2) : a.Mper;
   dim3 grid((Mcls + TC_BM - 1) / TC_BM, ncls, S);
-  // opt in to the large dynamic shared memory once per kernel (the attribute is sticky per device context)
-  static bool attr_set = false;
-  if (!attr_set) {
+  // opt in to the large dynamic shared memory once per kernel (the attribute is per device)
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     BSDE_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BSDE_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   if (L->cin % 4 == 0) conv_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(a);
   else conv_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a);

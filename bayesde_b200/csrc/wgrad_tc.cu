@@ -513,13 +513,12 @@ int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, cons
   static const int wg_dbg = getenv("BSDE_WG_DBG") ? atoi(getenv("BSDE_WG_DBG")) : 0;
   a.dbg = wg_dbg;
   const bool va = p.CA % 4 == 0, vb = p.CB % 4 == 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
   }
 #define WG_LAUNCH(VA_, VB_) BSDE_CUDA_OK(launch_pdl(wgrad_tc_kernel<VA_, VB_>, dim3(S * p.splits), dim3(WG_THREADS), p.smem, st, a))
   if (va && vb) WG_LAUNCH(true, true);

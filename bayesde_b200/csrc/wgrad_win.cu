@@ -681,14 +681,18 @@ int tconv_wgrad_win(const bsde_conv_layer* L, int S, int B, const float* in, con
   a.partial = (float*)ws;
   a.t = t;
   { static const int dbg = getenv("BSDE_WW_DBG") ? atoi(getenv("BSDE_WW_DBG")) : 0; a.dbg = dbg; }
-  static float* one_ptr = nullptr;
-  if (!one_ptr) BSDE_CUDA_OK(cudaGetSymbolAddress((void**)&one_ptr, ww_one_dev));
-  a.one = one_ptr;
-  static bool attr_set = false;
-  if (!attr_set) {
-    BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  {
+    // the __device__ symbol has one address per device
+    static float* one_ptr[64] = {nullptr};
+    int dev = 0;
+    BSDE_CUDA_OK(cudaGetDevice(&dev));
+    float*& op = one_ptr[dev & 63];
+    if (!op) BSDE_CUDA_OK(cudaGetSymbolAddress((void**)&op, ww_one_dev));
+    a.one = op;
   }
+  static PerDeviceOnce attr_once;
+  if (attr_once.first())
+    BSDE_CUDA_OK(cudaFuncSetAttribute(wgrad_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CUtensorMap tmU, tmV;
   memset(&tmU, 0, sizeof(tmU));
   memset(&tmV, 0, sizeof(tmV));

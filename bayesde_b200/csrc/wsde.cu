@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
 // host side
 // =============================================================================================
 static std::mutex g_mu;
-static int g_num_sms = 0;
+static int g_num_sms[64] = {0};  // per device
 
 static int fill_tiny(const bsde_fw_params* fw, TinyDims& td) {
   BSDE_CHECK_ARG(fw->nhid >= 1 && fw->nhid <= BSDE_FW_MAX_MID + 1, "len(fw_dims)=%d unsupported", fw->nhid);
@@ -542,18 +542,17 @@ static size_t smem_bytes(const TinyDims& td, bool bwd) {
 
 static int grid_for(int P, bool bwd, size_t smem, int& G) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_num_sms == 0) {
-    int dev = 0;
-    BSDE_CUDA_OK(cudaGetDevice(&dev));
-    BSDE_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int dev = 0;
+  BSDE_CUDA_OK(cudaGetDevice(&dev));
+  int& num_sms = g_num_sms[dev & 63];
+  if (num_sms == 0) BSDE_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   int occ = 0;
   if (bwd) BSDE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsde_bwd_kernel, NTHREADS, smem));
   else BSDE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsde_fwd_kernel, NTHREADS, smem));
   if (occ < 1) { set_error("wsde kernel does not fit on an SM (smem %zu)", smem); return BSDE_ERR_UNSUPPORTED; }
   if (occ > 2) occ = 2;
   int want = (P + NTHREADS - 1) / NTHREADS;
-  G = g_num_sms * occ;
+  G = num_sms * occ;
   if (G > want) G = want;
   if (G < 1) G = 1;
   return 0;

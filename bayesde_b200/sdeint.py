@@ -67,14 +67,22 @@ class _StepUpdate(torch.autograd.Function):
 
 
 def _gdg(g, y, t, args):
-    """J_g(y) applied to g(y) for an elementwise (diagonal) g: jaxsde/jaxsde/sde_utils.py:55-61."""
+    """J_g(y) applied to g(y) for an elementwise (diagonal) g: jaxsde/jaxsde/sde_utils.py:55-61.
+
+    The reference differentiates THROUGH this jvp (reverse mode over `make_gdg_prod`), so when gradients are being
+    recorded the product stays attached to the graph of `y` and of g's parameters (second-order terms included);
+    otherwise it is evaluated on a detached copy."""
+    track = torch.is_grad_enabled()
     with torch.enable_grad():
-        y_ = y.detach().requires_grad_(True)
+        y_ = y if (track and y.requires_grad) else y.detach().requires_grad_(True)
         gy = g(y_, t, args)
-        if not gy.requires_grad:
+        if not gy.requires_grad or gy.grad_fn is None:
             return None  # state-independent diffusion: the Milstein correction vanishes
-        (diag,) = torch.autograd.grad(gy.sum(), y_, create_graph=torch.is_grad_enabled() and y.requires_grad)
-    return diag * gy.detach()
+        (diag,) = torch.autograd.grad(gy.sum(), y_, create_graph=track, allow_unused=True)
+        if diag is None:
+            return None
+        out = diag * gy
+    return out if track else out.detach()
 
 
 def sdeint_ito_fixed_grid(f, g, y0, ts, rng, args=(), dt=1e-6, method="milstein", rep=0, time_grid="reference"):

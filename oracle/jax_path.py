@@ -72,15 +72,19 @@ def time_grid(ts, mode="reference"):
 
 
 def _gdg_prod(g, y, t, args, v):
-    """sde_utils.py:55-61 make_gdg_prod: jvp(g(.,t,args), y, v*g(y)) for elementwise g."""
-    y_ = y.detach().clone().requires_grad_(True)
+    """sde_utils.py:55-61 make_gdg_prod: jvp(g(.,t,args), y, v*g(y)) for elementwise g.
+
+    Differentiable like the reference's jvp (the scan is reverse-differentiated through it): for an elementwise g
+    the Jacobian is diagonal, J @ tangent = d(sum g)/dy * tangent, built with create_graph so that gradients flow
+    through g(y), through the diagonal and through g's parameters."""
+    y_ = y if y.requires_grad else y.detach().clone().requires_grad_(True)
     gy = g(y_, t, args)
-    if not gy.requires_grad:  # state-independent diffusion => zero Jacobian
+    if not gy.requires_grad or gy.grad_fn is None:  # state-independent diffusion => zero Jacobian
         return torch.zeros_like(y)
-    tangent = (v * gy).detach()
-    # elementwise g: J is diagonal, so J @ tangent = d(sum g)/dy * tangent
-    (diag,) = torch.autograd.grad(gy.sum(), y_, create_graph=False)
-    return diag * tangent
+    (diag,) = torch.autograd.grad(gy.sum(), y_, create_graph=True, allow_unused=True)
+    if diag is None:
+        return torch.zeros_like(y)
+    return diag * (v * gy)
 
 
 def sdeint_ito_fixed_grid(f, g, y0, ts, increments, args=(), dt=1e-6, method="milstein", rep=0,
@@ -190,7 +194,8 @@ def fx_layout(block_type, in_ch, fx_dim, actfn="softplus"):
         convs = [(in_ch, fx_dim, 3, 1, False), (fx_dim, fx_dim, 3, 2, False),
                  (fx_dim, fx_dim, 3, 2, True), (fx_dim, in_ch, 3, 1, False)]
     elif block_type == 1:
-        convs = [(in_ch, fx_dim, 3, 1, False), (fx_dim, fx_dim, 1, 1, False), (fx_dim, in_ch, 3, 1, False)]
+        # arch.py:193 passes (1, 1) into ConcatConv2D's unused W_init slot (diffeq_layers.py:124): kernel stays 3
+        convs = [(in_ch, fx_dim, 3, 1, False), (fx_dim, fx_dim, 3, 1, False), (fx_dim, in_ch, 3, 1, False)]
     elif block_type == 2:
         convs = [(in_ch, fx_dim, 3, 1, False), (fx_dim, in_ch, 3, 1, False)]
     else:

@@ -174,8 +174,12 @@ def test_sdebnn_block_forward_backward(built_lib, kw):
 
 
 def test_block_types_1_and_2(built_lib):
-    """arch.py:189-205: block_type 1 (3x3, 1x1, 3x3) and 2 (3x3, 3x3)."""
+    """arch.py:189-205: block_type 1 (3x3, 3x3, 3x3 as shipped: the `(1, 1)` of arch.py:193 lands in ConcatConv2D's unused W_init
+    slot, diffeq_layers.py:124, so kernel stays 3) and 2 (3x3, 3x3)."""
     from bayesde_b200 import arch, brax
+    # P of block type 1 with a 3x3 middle conv: 9*(C+1)*F + F + 9*(F+1)*F + F + 9*(F+1)*C + C
+    assert arch.FxSpec(1, (1, 6, 6, 4), 8, "softplus").P == 9 * 5 * 8 + 8 + 9 * 9 * 8 + 8 + 9 * 9 * 4 + 4
+    assert jp.fx_layout(1, 4, 8)[1] == arch.FxSpec(1, (1, 6, 6, 4), 8, "softplus").P
     for bt in (1, 2):
         g = torch.Generator().manual_seed(3)
         S, B, H, Cc, nsteps = 1, 2, 6, 4, 4
