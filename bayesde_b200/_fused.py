@@ -72,6 +72,7 @@ class BlockConfig:
         self.tk, self.dtk = reference_time_grid(ts, time_grid)
         self.P = fx_spec.P
         self.x_numel = S * B * fx_spec.H * fx_spec.W * fx_spec.C
+        self.sample_offset = 0   # global index of local sample 0 (ranks sharding the MC samples)
         self._dev = {}
 
     def set_step(self, t, h):
@@ -105,6 +106,7 @@ class BlockConfig:
         d.sigma, d.kl_weight, d.ou_coef = self.sigma, self.kl_weight, self.ou_coef
         d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         d.stream_id = int(stream_id) & 0xFFFFFFFF
+        d.sample_offset = int(self.sample_offset) & 0xFFFFFFFF
         return d
 
 

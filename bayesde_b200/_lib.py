@@ -32,7 +32,7 @@ class FwParams(C.Structure):
 class WsdeDesc(C.Structure):
     _fields_ = [("S", C.c_int32), ("nit", C.c_int32), ("stl", C.c_int32), ("w0_per_sample", C.c_int32),
                 ("sigma", C.c_float), ("kl_weight", C.c_float), ("ou_coef", C.c_float),
-                ("seed", C.c_uint64), ("stream_id", C.c_uint32),
+                ("seed", C.c_uint64), ("stream_id", C.c_uint32), ("sample_offset", C.c_uint32),
                 ("d_dtkl", C.c_void_p), ("d_nscale", C.c_void_p), ("d_nidx", C.c_void_p), ("d_back", C.c_void_p)]
 
 
@@ -113,8 +113,8 @@ def lib():
     L.bsde_step_update_prod.argtypes = [C.c_int64, C.c_float, vp, vp, vp, vp, vp, vp]
     L.bsde_toy_em_fwd.argtypes = [C.POINTER(ToyDesc), vp, vp, vp, C.c_uint64] + [vp] * 8 + [vp, vp, vp]
     L.bsde_toy_em_bwd.argtypes = [C.POINTER(ToyDesc), vp, vp, vp, vp] + [vp] * 8 + [vp] * 8 + [vp]
-    if L.bsde_version() != 100:
-        raise BsdeError(f"libbsde.so version {L.bsde_version()} != 100: rebuild")
+    if L.bsde_version() != 200:
+        raise BsdeError(f"libbsde.so version {L.bsde_version()} != 200: rebuild")
     _lib = L
     return L
 

@@ -35,6 +35,7 @@ class _AugDynamics:
         self.x_dim = int(np.prod(self.x_shape[1:]))  # per sample, as brax.py:45
         self.P = fx_spec.P
         self.w0_per_sample = False
+        self.sample_offset = 0
 
     def f_aug(self, y, t, args):  # placeholders: the arithmetic lives in libbsde.so
         raise NotImplementedError("f_aug is evaluated by the fused kernels; pass it to sdeint_ito_fixed_grid")
@@ -58,6 +59,7 @@ class _AugDynamics:
         S, B = self.x_shape[:2]
         cfg = _fused.BlockConfig(self.fx, self.fw, S, B, nsteps, self.diff_coef, bool(rep), time_grid, self.math,
                                  ts=ts_np, remat=self.remat)
+        cfg.sample_offset = self.sample_offset
         if self.w_drift:
             layers = fw_layers(args)
         else:
@@ -173,13 +175,17 @@ def SDEBNN(fx_block_type, fx_dim, fx_actfn, fw, diff_coef=1e-4, name="sdebnn", s
         P = fx.P
         dyn = _AugDynamics(fx, fw.spec, x.shape, diff_coef, stl, w_drift, math, w_stale.to(x.device), stream_id,
                            remat=remat)
+        # ranks that shard the MC samples: local sample s is global sample mc_offset + s of mc_total (Philox sample counter)
+        dyn.sample_offset = int(kwargs.get("mc_offset", 0))
+        S_total = int(kwargs.get("mc_total", 0)) or S
         kl = x.new_zeros(S)
         if infer_initial_state:  # brax.py:100-106
             if isinstance(rng, (tuple, list)) and len(rng) == 2 and isinstance(rng[1], torch.Tensor):
                 eps, rng = rng[1], rng[0]
             else:
                 w0_rng, rng = split(rng, 2)
-                eps = torch.randn(S, P, generator=_gen(w0_rng, x.device), device=x.device)
+                eps = torch.randn(S_total, P, generator=_gen(w0_rng, x.device), device=x.device)
+                eps = eps[dyn.sample_offset:dyn.sample_offset + S]
             mean_w0 = init_w0
             w0 = eps * torch.exp(logstd_w0) + mean_w0
             kl = (normal_logprob(w0, mean_w0, logstd_w0)
@@ -273,6 +279,8 @@ def MeanField(layer, prior_std=0.1, disable=False):
         leaves = tree_leaves(params_mean)
         sampled = kwargs.pop("mc_samples", None)
         S = sampled if sampled is not None else None
+        # sample-sharded ranks draw the GLOBAL (mc_total, n) noise and keep their rows [mc_offset, mc_offset + S)
+        mc_off, mc_tot = int(kwargs.get("mc_offset", 0)), int(kwargs.get("mc_total", 0)) or S
         # brax.py:150,165: the key is split and the wrapped layer receives `rng=next_rng` (a stochastic wrapped layer, e.g.
         # MeanField(SDEBNN(..., stax_api=True)) of --meanfield_sdebnn, draws its Brownian path from it)
         explicit = isinstance(rng, (tuple, list)) and len(rng) == 2 and isinstance(rng[1], torch.Tensor)
@@ -286,8 +294,10 @@ def MeanField(layer, prior_std=0.1, disable=False):
         if explicit:
             eps = rng[1]
         else:
-            shape = (S, flat_mean.numel()) if S else (flat_mean.numel(),)
+            shape = (mc_tot, flat_mean.numel()) if S else (flat_mean.numel(),)
             eps = torch.randn(shape, generator=_gen(rng_eps, flat_mean.device), device=flat_mean.device)
+            if S:
+                eps = eps[mc_off:mc_off + S]
         if disable:
             flat_params = flat_mean.expand_as(eps) if S else flat_mean
             kl = flat_params.new_zeros(flat_params.shape)

@@ -605,7 +605,7 @@ extern "C" int bsde_wsde_fwd(const bsde_wsde_desc* d, const bsde_fw_params* fw, 
   const int S = d->S, P = fw->P, nit = d->nit, d1 = fw->dims[0];
   for (int s0 = 0; s0 < S; s0 += SC) {
     const int sc = S - s0 < SC ? S - s0 : SC;
-    A.d = *d; A.d.S = sc; A.fw = *fw; A.ou_coef = d->ou_coef; A.s_base = s0;
+    A.d = *d; A.d.S = sc; A.fw = *fw; A.ou_coef = d->ou_coef; A.s_base = s0 + (int)d->sample_offset;
     A.w0 = d_w0 + (d->w0_per_sample ? (size_t)s0 * P : 0);
     A.tk = d_tk; A.dtk = d_dtk;
     A.dW = d_dW ? d_dW + (size_t)s0 * nit * P : nullptr;
@@ -648,7 +648,7 @@ extern "C" int bsde_wsde_bwd(const bsde_wsde_desc* d, const bsde_fw_params* fw, 
   const int S = d->S, P = fw->P, nit = d->nit, d1 = fw->dims[0];
   for (int s0 = 0; s0 < S; s0 += SC) {
     const int sc = S - s0 < SC ? S - s0 : SC;
-    A.d = *d; A.d.S = sc; A.fw = *fw; A.gfw = *gfw; A.ou_coef = d->ou_coef; A.s_base = s0;
+    A.d = *d; A.d.S = sc; A.fw = *fw; A.gfw = *gfw; A.ou_coef = d->ou_coef; A.s_base = s0 + (int)d->sample_offset;
     A.tk = d_tk; A.dtk = d_dtk;
     A.wtraj = const_cast<float*>(d_wtraj) + (size_t)s0 * (nit + 1) * P;
     A.z1 = const_cast<float*>(d_z1) + (size_t)s0 * nit * d1;

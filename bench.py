@@ -36,11 +36,17 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=128, help="images per GPU per step")
     p.add_argument("--nsamples", type=int, default=8)
-    p.add_argument("--math", default=os.environ.get("BSDE_MATH", "tc"), choices=["fp32", "tc"])
+    p.add_argument("--math", default=os.environ.get("BSDE_MATH", "tc"), choices=["fp32", "tc", "bf16"])
+    p.add_argument("--shard", default="batch", choices=["batch", "samples"],
+                   help="batch: B images x S samples per rank (weak scaling, default); samples: the S x B work of one step on a "
+                        "samples x batch grid of ranks (strong scaling, SURVEY 8.5)")
+    p.add_argument("--no_overlap", action="store_true", help="serial gradient all-reduce after backward (default: per-block buckets "
+                                                             "launched on a side stream during the reverse pass)")
     p.add_argument("--remat", action="store_true", help="recompute conv intermediates in the reverse pass")
     p.add_argument("--time_grid", default="reference", choices=["reference", "uniform"])
     p.add_argument("--diff_coef", type=float, default=0.2)
-    p.add_argument("--cpu_batch", type=int, default=8, help="images in the bounded CPU sample")
+    p.add_argument("--cpu_batch", type=int, default=32, help="images in the bounded CPU sample (SURVEY 8.4: B = 32)")
+    p.add_argument("--no_fp32_leg", action="store_true", help="skip the fp32-class (CUDA-core conv) throughput leg")
     p.add_argument("--no_cpu_baseline", action="store_true")
     return p.parse_args()
 
@@ -161,9 +167,11 @@ class ClockSampler:
 
 
 def cpu_reference_images_per_s(args, steps, warmup):
-    """The oracle's torch-CPU fp32 restatement of the JAX path (the reference itself needs JAX 0.1.77,
-    which cannot be installed here), all host threads, bounded sample: `cpu_batch` images x 1 MC
-    sample per step, scaled to the metric's unit (images/s at nsamples samples per image)."""
+    """The oracle's torch-CPU fp32 restatement of the JAX path (the reference itself needs JAX 0.1.77, which cannot be
+    installed here), all host threads, bounded sample per SURVEY 8.4: `cpu_batch` (32) images x 1 MC sample per train step
+    (forward + backward + Adam), `warmup` untimed + `steps` timed steps.  The metric counts images/s with every image integrated
+    under `nsamples` weight paths, and the samples are independent repeats of the same work (script :218 vmaps over rngs), so
+    value = cpu_batch / (s_per_step * nsamples): extrapolated in S, stated in `ran`."""
     import torch
     from oracle import jax_path as jp
     cores = os.cpu_count() or 1
@@ -203,7 +211,9 @@ def cpu_reference_images_per_s(args, steps, warmup):
     value = B / (t_step * args.nsamples)
     sample = (f"{steps} timed + {warmup} warm-up train steps (fwd+bwd+Adam) of the oracle port at "
               f"{B} images x 1 MC sample, {t_step:.2f} s/step; value = {B}/(s_per_step*{args.nsamples} samples)")
-    return value, cores, sample, t_step
+    ran = {"batch": B, "nsamples": 1, "steps": steps, "warmup": warmup, "extrapolated": True,
+           "extrapolation": f"x 1/{args.nsamples} in the MC-sample count (independent repeats of the measured work)"}
+    return value, cores, sample, t_step, ran
 
 
 def cpu_torch_reference_images_per_s(batch):
@@ -244,31 +254,56 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warmup = 1 if args.warmup > 0 else 0
-    v, cores, sample, t_step = cpu_reference_images_per_s(args, steps, warmup)
+    steps = max(5, min(args.steps, 8))   # >= 5 timed steps; bounded so the arm ends within a few minutes
+    warmup = 3 if args.warmup >= 3 else max(1, args.warmup)
+    v, cores, sample, t_step, ran = cpu_reference_images_per_s(args, steps, warmup)
+    cfg = workload_config(args)
+    # what this arm actually ran (the GPU arm's batch_per_gpu / nsamples are the metric's definition, not this arm's sample)
+    cfg.update({"conv_math": "fp32 (torch CPU)", "parallelism": f"host threads x{cores}", "reference_arm_ran": ran,
+                "l2_policy": "n/a (CPU)"})
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args),
+            "config": cfg,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(args):
+    shard = getattr(args, "shard", "batch")
+    par = (f"dp{args.gpus} (batch sharded: {args.batch} images x {args.nsamples} samples per rank)" if shard == "batch" else
+           f"samples x batch grid over {args.gpus} ranks (SURVEY 8.5): {args.nsamples} samples and {args.batch} images in total")
     return {"workload": "config4: SDEBNN 32x32x3 CIFAR-10-shape synthetic, aug 2, nblocks 2-2-2, fx_dim 64, "
                         "fw_dims 2-64-2, softplus, nsteps 20 (19 drift evaluations/block), euler_maruyama",
             "batch_per_gpu": args.batch, "nsamples": args.nsamples, "diff_coef": args.diff_coef,
-            "time_grid": args.time_grid, "conv_math": args.math, "remat": bool(getattr(args, "remat", False)), "parallelism": f"dp{args.gpus} (batch sharded)",
+            "time_grid": args.time_grid, "conv_math": args.math, "remat": bool(getattr(args, "remat", False)), "parallelism": par,
+            "shard": shard,
             "l2_policy": "per-step working set (checkpoints+activations, >2 GB) exceeds the 126 MB L2; no flush"}
+
+
+def fused_floor_bytes_per_image_eval():
+    """HBM byte floor of a block evaluation if conv1->conv2 and convT->conv4 were fused pairs: per block
+    the state x is read and written once (fp32) and only the half-resolution 64-channel tensor crosses HBM (written, read);
+    reverse pass with recompute: x read, gx read + written, half-resolution activation and its gradient written + read."""
+    from bayesde_b200.arch import FxSpec
+    fwd = bwd = 0
+    shape = (1, 32, 32, 5)
+    for gi, nb in enumerate(MODEL_KW["nblocks"]):
+        fx = FxSpec(0, shape, MODEL_KW["fx_dim"], "softplus")
+        vx = fx.H * fx.W * fx.C
+        vmid = fx.layers[1]["hout"] * fx.layers[1]["wout"] * fx.layers[1]["cout"]
+        fwd += nb * 4 * (2 * vx + 2 * vmid)
+        bwd += nb * 4 * (3 * vx + 4 * vmid)
+        shape = (1, shape[1] // 2, shape[2] // 2, shape[3] * 4)
+    return fwd, bwd
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from bayesde_b200 import _fused, _lib
-    from bayesde_b200.classification import SDEBNNClassifier, Trainer
+    from bayesde_b200.classification import SDEBNNClassifier, Trainer, sample_shard
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -286,14 +321,27 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
-    model = SDEBNNClassifier(nsamples=args.nsamples, diff_coef=args.diff_coef, time_grid=args.time_grid,
-                             math=args.math, remat=args.remat, w_init=1e-2, b_init=1e-2, seed=0, device=dev, **MODEL_KW)
-    trainer = Trainer(model, lr=1e-3, kl_coef=1e-3, train_size=45000)
+    # ---- decomposition.  batch (default, weak scaling): every rank integrates all S weight paths on its own B images.
+    # samples (strong scaling): the S x B work of ONE step is laid on a samples x batch grid -- S/G samples per rank
+    # on the whole batch while G <= S, beyond that ranks of a sample group split the batch; every sample's KL is counted once.
     B = args.batch
-    g = torch.Generator().manual_seed(1234 + rank)
+    if args.shard == "samples":
+        s_off, s_loc, b_grp, grp = sample_shard(args.nsamples, world, rank)
+        if B % grp:
+            raise SystemExit(f"--batch {B} is not divisible by the {grp} ranks of a sample group")
+        B_loc = B // grp
+    else:
+        s_off, s_loc, b_grp, grp, B_loc = 0, args.nsamples, rank, 1, B
+    mk = dict(nsamples=s_loc, sample_offset=s_off, total_samples=args.nsamples, diff_coef=args.diff_coef,
+              time_grid=args.time_grid, remat=args.remat, w_init=1e-2, b_init=1e-2, seed=0, device=dev, **MODEL_KW)
+    model = SDEBNNClassifier(math=args.math, **mk)
+    trainer = Trainer(model, lr=1e-3, kl_coef=1e-3, train_size=45000, overlap=not args.no_overlap)
+    # batch mode: different images per rank; samples mode: the SAME global batch on every rank, a group's ranks take slices of it
+    g = torch.Generator().manual_seed(1234 + (rank if args.shard == "batch" else 0))
     n_host = 4
-    host_x = [torch.randn(B, 32, 32, 3, generator=g).pin_memory() for _ in range(n_host)]
-    host_y = [torch.randint(0, 10, (B,), generator=g).pin_memory() for _ in range(n_host)]
+    lo = b_grp * B_loc if args.shard == "samples" else 0
+    host_x = [torch.randn(B, 32, 32, 3, generator=g)[lo:lo + B_loc].contiguous().pin_memory() for _ in range(n_host)]
+    host_y = [torch.randint(0, 10, (B,), generator=g)[lo:lo + B_loc].contiguous().pin_memory() for _ in range(n_host)]
     dev_x = [t.to(dev) for t in host_x]
     dev_y = [t.to(dev) for t in host_y]
 
@@ -318,18 +366,21 @@ def run_ours(args):
         return ms
 
     seed_base = [0]
-
-    def step_resident(i):
-        trainer.step(dev_x[i % n_host], dev_y[i % n_host], seed=seed_base[0] + i)
-
     last = {}
 
-    def step_e2e(i):
-        x = host_x[i % n_host].to(dev, non_blocking=True)
-        y = host_y[i % n_host].to(dev, non_blocking=True)
-        loss, _, _ = trainer.step(x, y, seed=seed_base[0] + i)
-        last["loss"] = loss.item()  # device -> host read of the step's result
+    def make_steps(tr):
+        def step_resident(i):
+            out = tr.step(dev_x[i % n_host], dev_y[i % n_host], seed=seed_base[0] + i)
+            last["dev"] = out
 
+        def step_e2e(i):
+            x = host_x[i % n_host].to(dev, non_blocking=True)
+            y = host_y[i % n_host].to(dev, non_blocking=True)
+            loss, _, _ = tr.step(x, y, seed=seed_base[0] + i)
+            last["loss"] = loss.item()  # device -> host read of the step's result
+        return step_resident, step_e2e
+
+    step_resident, step_e2e = make_steps(trainer)
     for i in range(args.warmup):
         step_resident(i)
     seed_base[0] = 1000
@@ -346,13 +397,37 @@ def run_ours(args):
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     ktime = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in prof.items()}
+    loss_last = [float(v) for v in last["dev"]]   # (loss, nll, kl) of the last timed step (read after the timed region)
 
     seed_base[0] = 2000
     ms_e2e = timed(step_e2e, args.steps)
 
-    images = B * world * args.steps
+    imgs_step = B * world if args.shard == "batch" else B
+    images = imgs_step * args.steps
     value = images / (ms * 1e-3)
     e2e_value = images / (ms_e2e * 1e-3)
+
+    # ---- fp32-class leg (CUDA-core fp32 convolutions, the arithmetic of the reference) on the same workload, and the same-seed
+    # loss of the two arithmetics on one un-timed step from identical parameters: the benchmarked step is a sane computation
+    fp32_leg = None
+    if args.math != "fp32" and not args.no_fp32_leg:
+        seed_cmp = 4242
+        with torch.no_grad():
+            loss_fast = float(model.loss(dev_x[0], dev_y[0], trainer.kl_scale, rng=seed_cmp)[0])
+        m32 = SDEBNNClassifier(math="fp32", **mk)
+        m32.load_state_dict(model.state_dict())
+        with torch.no_grad():
+            loss_32 = float(m32.loss(dev_x[0], dev_y[0], trainer.kl_scale, rng=seed_cmp)[0])
+        t32 = Trainer(m32, lr=1e-3, kl_coef=1e-3, train_size=45000, overlap=not args.no_overlap)
+        st32, _ = make_steps(t32)
+        st32(0)
+        n32 = max(1, min(2, args.steps))
+        ms32 = timed(st32, n32)
+        fp32_leg = {"value": imgs_step * n32 / (ms32 * 1e-3), "unit": UNIT, "steps": n32, "warmup": 1, "ms_per_step": ms32 / n32,
+                    "conv_math": "fp32 (CUDA-core FMA, csrc/tconv_simt.cu)",
+                    "same_seed_loss": {"fast": loss_fast, "fp32": loss_32,
+                                       "rel_diff": abs(loss_fast - loss_32) / max(abs(loss_32), 1e-30)}}
+        del m32, t32
 
     if rank != 0:
         if world > 1:
@@ -366,77 +441,90 @@ def run_ours(args):
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
-    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    peak_bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     peak_hbm = peaks.get("hbm_gbs", 6650.0)
     fl_eval = conv_flops_per_image_eval()
     tf32_peak = measure_tf32_peak(dev) if args.math == "tc" else None
     by_fwd, by_bwd = conv_bytes_per_image_eval()
+    ff_fwd, ff_bwd = fused_floor_bytes_per_image_eval()
     nit = MODEL_KW["nsteps"] - 1
-    alg_flops_step = 3.0 * fl_eval * nit * B * args.nsamples  # fwd + dgrad + wgrad (recompute not counted)
+    units = B_loc * s_loc                                      # image-samples one rank integrates per step
+    alg_flops_step = 3.0 * fl_eval * nit * units               # fwd + dgrad + wgrad (recompute not counted): 9.98 GFLOP/image-sample
     conv_ms = (ktime.get("k2_fwd", 0.0) + ktime.get("k3_bwd", 0.0)) / args.steps
-    hbm_bytes_step = (by_fwd + by_bwd) * nit * B * args.nsamples
+    hbm_bytes_step = (by_fwd + by_bwd) * nit * units
+    floor_bytes_step = (ff_fwd + ff_bwd) * nit * units
     hbm_achieved = hbm_bytes_step / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
     achieved = alg_flops_step / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    if args.math == "tc":
+        t_peak, t_src = tf32_peak, ("measured live in this run: cuBLAS 8192^3 TF32 matmul (the kernels issue tcgen05 kind::tf32; "
+                                    "MEASURED_PEAKS.json holds no TF32 figure, SURVEY 8.4)")
+    else:
+        t_peak, t_src = peak_bf16, peak_src
+    # ncu DRAM traffic of the dominant kernel: read from the committed summary of the capture, never typed in
+    traffic, traffic_src = None, None
+    tj = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tj):
+        try:
+            tjd = json.load(open(tj)).get(args.math)
+            if tjd:
+                traffic, traffic_src = tjd.get("dram_bytes_per_launch"), tjd.get("source")
+        except Exception:  # noqa: BLE001
+            pass
     # K1 (weight-SDE) against the 48*P HBM model of SURVEY.md 8.4 (fwd) and 2x for the reverse pass
     sumP = sum(blk[0].numel() for blk in model.block_params())
-    k1_bytes = 3 * 48.0 * sumP * nit * args.nsamples
+    k1_bytes = 3 * 48.0 * sumP * nit * s_loc
     k1_ms = (ktime.get("k1_fwd", 0.0) + ktime.get("k1_bwd", 0.0)) / args.steps
+    dtype = {"fp32": "f32", "tc": "tf32 (tcgen05 kind::tf32 operands, f32 accumulate)",
+             "bf16": "bf16 (tcgen05 kind::f16 operands and bf16 storage of the 64-channel intermediates; x, dx, accumulators, "
+                     "all parameter gradients f32)"}[args.math]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.math == "fp32" else "tf32 (tcgen05 kind::tf32 operands, f32 accumulate)", "data": "synthetic",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if args.shard == "batch" else "strong",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": workload_config(args),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (32 * 32 * 3 * 4 + 8),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B_loc * (32 * 32 * 3 * 4 + 8),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        # The conv stack sits on the MEMORY side of the ridge: 10.2 PFLOP / 230 GB per step = 44 FLOP/B against a ridge of
-        # (TF32 peak 748 TFLOP/s) / (6.55 TB/s) = 114 FLOP/B (byte floor 35 ms > flop floor 13.7 ms), so the bounding roofline of the
-        # dominant kernels (conv_win / wgrad_win, 79 % of the step in the ncu launch list) is HBM; the tensor-pipe view is kept beside it.
-        "roofline": {"bound": "hbm", "kernel": "K2/K3 time-dependent conv stack (conv_win_kernel / wgrad_win_kernel + conv_tc / wgrad_tc "
-                                                "fallbacks), all launches of a step",
-                     "achieved": hbm_achieved, "peak": peak_hbm, "unit": "GB/s", "frac": hbm_achieved / peak_hbm,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel with the largest share of the
-                     # step (wgrad_win_kernel, 29 %: 5->64 weight gradient, 1024 images 32x32), ncu --set full capture
-                     # profiles/r01j_wgrad_win_full_summary.csv: 289.8 MB read + 3.9 MB written = the algorithmic bytes
-                     # (dY 268.4 MB + input 21.0 MB read once, partial tiles 3.5 MB); the eight group-0 conv_win launches
-                     # likewise move exactly their algorithmic bytes (profiles/r01k_conv_win_full_summary.csv)
-                     "traffic": 293.7e6,
-                     "algorithmic_bytes_per_step": hbm_bytes_step, "kernel_ms_per_step": conv_ms,
-                     "share_of_step": conv_ms / (ms / args.steps),
-                     "byte_floor_ms": hbm_bytes_step / (peak_hbm * 1e9) * 1e3,
-                     "flop_floor_ms": alg_flops_step / ((tf32_peak or peak_tf) * 1e12) * 1e3,
-                     "arithmetic_intensity_flop_per_byte": alg_flops_step / hbm_bytes_step,
-                     "ridge_flop_per_byte": (tf32_peak or peak_tf) * 1e12 / (peak_hbm * 1e9),
-                     "note": "algorithmic bytes: every layer reads its fp32 NHWC input once and writes its output once; dgrad also "
-                             "reads the activation it differentiates; wgrad reads layer input + dy.  achieved = those bytes / "
-                             "CUDA-event time of the x-path calls (K2 forward + K3 reverse) on the launching stream"},
-        "roofline_tensor": {"bound": "tensor", "kernel": "the same K2/K3 conv launches (tcgen05 kind::tf32)",
-                            "achieved": achieved, "peak": tf32_peak or peak_tf, "unit": "TFLOP/s", "frac": achieved / (tf32_peak or peak_tf),
-                            "peak_source": ("measured live in this run: cuBLAS 8192^3 TF32 matmul (the kernels issue tcgen05 kind::tf32; "
-                                            "MEASURED_PEAKS.json holds no TF32 figure, SURVEY 8.4)" if tf32_peak else peak_src),
-                            "peak_bf16_sustained": peak_tf, "frac_of_bf16_peak": achieved / peak_tf,
-                            "algorithmic_flops_per_step": alg_flops_step},
+        "loss": {"last_timed_step": loss_last[0], "nll": loss_last[1], "kl": loss_last[2], "last_e2e_step": last.get("loss"),
+                 "finite": bool(all(map(lambda v: v == v and abs(v) != float("inf"), loss_last + [last.get("loss", 0.0)])))},
+        "value_fp32": fp32_leg["value"] if fp32_leg else (value if args.math == "fp32" else None),
+        "fp32_leg": fp32_leg,
+        # the per-step conv is a dense contraction => tensor-core bound; achieved = algorithmic FLOPs (9.98 GFLOP per
+        # image-sample and training step = 3 x 175.1 MFLOP x 19 iterations) / CUDA-event time of the K2 + K3 calls on the launching stream
+        "roofline": {"bound": "tensor", "kernel": "K2/K3 time-dependent conv stack (conv_win_kernel / wgrad_win_kernel + fallbacks), all "
+                                                  "launches of a step",
+                     "achieved": achieved, "peak": t_peak, "unit": "TFLOP/s", "frac": achieved / t_peak,
+                     "peak_source": t_src, "peak_bf16_sustained": peak_bf16, "frac_of_bf16_peak": achieved / peak_bf16,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_flops_per_step": alg_flops_step, "flops_per_image_sample": 3.0 * fl_eval * nit,
+                     "image_samples_per_step": units, "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / (ms / args.steps),
+                     "flop_floor_ms": alg_flops_step / (t_peak * 1e12) * 1e3},
+        # the explanation beside it: with fp32 NHWC activations and one launch per layer the stack sits on the memory side of the ridge
+        "roofline_hbm": {"bound": "hbm", "kernel": "the same K2/K3 launches", "achieved": hbm_achieved, "peak": peak_hbm, "unit": "GB/s",
+                         "frac": hbm_achieved / peak_hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "per_layer_bytes_per_step": hbm_bytes_step, "per_layer_byte_floor_ms": hbm_bytes_step / (peak_hbm * 1e9) * 1e3,
+                         "fused_block_floor_bytes_per_step": floor_bytes_step,
+                         "fused_block_floor_ms": floor_bytes_step / (peak_hbm * 1e9) * 1e3,
+                         "note": "per_layer: every layer reads its input once and writes its output once at the storage width of this "
+                                 "run's arithmetic (fp32 here unless conv_math = bf16); dgrad also reads the activation it differentiates; "
+                                 "wgrad reads layer input + dy.  fused_block_floor: conv1->conv2 and convT->conv4 as fused pairs -- only x, "
+                                 "gx and the half-resolution 64-channel tensor cross HBM (VERDICT r1 item 5)"},
         "roofline_k1": {"bound": "hbm", "kernel": "K1 wsde_fwd/bwd (cooperative persistent)",
                         "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0, "peak": peak_hbm,
                         "unit": "GB/s", "frac": (k1_bytes / (k1_ms * 1e-3) / 1e9 / peak_hbm) if k1_ms > 0 else 0.0,
-                        "algorithmic_bytes_per_step": k1_bytes, "kernel_ms_per_step": k1_ms,
-                        # ncu --set full of wsde_fwd_kernel (profiles/r01m_wsde_full_summary.csv, group-0 block, S = 8, 19 iterations):
-                        # 3.0 MB read + 3.0-3.8 MB written per launch against 594 MB algorithmic -- the state and the f_w parameters
-                        # stay in the 126 MB L2, so this kernel is NOT HBM-bound: issue active 18 %, 8 warps per SM, one grid barrier
-                        # per iteration (29 us per iteration, of which ~1.4 us per sample is arithmetic)
-                        "traffic": 6.0e6,
-                        "note": "48*P B per (sample, block, iteration) fwd, 2x bwd (SURVEY 8.4 model); measured DRAM traffic is 1 % of it "
-                                "(L2-resident), the kernel is latency / barrier bound, so this fraction is a model figure, not a bound"},
+                        "algorithmic_bytes_per_step": k1_bytes, "kernel_ms_per_step": k1_ms, "traffic": None,
+                        "note": "48*P B per (sample, block, iteration) fwd, 2x bwd (SURVEY 8.4 model); the state and the f_w parameters stay "
+                                "in L2 (ncu: profiles/r01m_wsde_full_summary.csv, ~1 % of the model bytes reach DRAM), so this fraction is a "
+                                "model figure, not a bound"},
         "kernel_ms_per_step": {k: v / args.steps for k, v in ktime.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, sample, _ = cpu_reference_images_per_s(args, 2, 1)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        v, cores, sample, _, ran = cpu_reference_images_per_s(args, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ran": ran}
         try:  # the second CPU leg the north star names (torch front end, config 5); reported beside, not a ratio input
-            v5, cores5, sample5 = cpu_torch_reference_images_per_s(args.cpu_batch)
+            v5, cores5, sample5 = cpu_torch_reference_images_per_s(8)
             line["cpu_baseline_torch"] = {"value": v5, "unit": "images/s (config 5: torchbnn SDENet, midpoint dt 0.05, 1 weight sample)",
                                           "cores": cores5, "kind": "port", "sample": sample5}
         except Exception as e:  # noqa: BLE001 -- a reporting extra must not cost the bench line

@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define BSDE_VERSION 100
+#define BSDE_VERSION 200
 
 typedef enum {
   BSDE_OK = 0,
@@ -112,6 +112,9 @@ typedef struct {
                          torchbnn (models.py:165); u = (f_w + (ou_coef+1) w)/sigma (prior drift -w) */
   uint64_t seed;      /* Philox key when d_dW == NULL */
   uint32_t stream_id; /* Philox sub-stream (block index in the network) */
+  uint32_t sample_offset; /* global index of local sample 0 in the Philox counter: ranks that shard the MC samples
+                             (examples/jax/sdebnn_classification.py:218 vmaps over per-sample rngs) draw the same paths as one rank
+                             integrating all of them */
   /* Optional stage tables, device arrays [nit] (all NULL = the Euler scan above).  They express fixed-step schemes whose
    * stages are Euler-like updates that start from the previous slot, e.g. torchsde's midpoint (call site
    * torchbnn/_impl/models.py:184-197;  y' = y + dt/2 f(t,y) + g I/2,  y1 = y + dt f(t + dt/2, y') + g I):

@@ -1,0 +1,124 @@
+"""Parity of the BENCHMARKED model on the BENCHMARKED arithmetic ("What's missing" 1).
+
+The exact `MODEL_KW` of bench.py (config 4: 32x32x3, aug 2, nblocks 2-2-2, fx_dim 64, fw_dims 2-64-2, nsteps 20 =>
+19 drift evaluations per block, softplus), B = 8 images x S = 2 Monte-Carlo samples, supplied Brownian increments and
+supplied head noise, sigma in {1e-4 (script default, examples/jax/sdebnn_classification.py:126), 0.2 (README / bench)},
+through the public API (`classification.SDEBNNClassifier.loss`) in every conv arithmetic the library ships
+(`math` = "fp32" CUDA cores, "tc" tcgen05 kind::tf32, "bf16" tcgen05 kind::f16 with bf16 storage of the 64-channel
+intermediates) against `oracle.jax_path.SDEBNNClassifier` in fp64: loss, nll, sum-KL, log-probabilities and the gradient
+of EVERY parameter (examples/jax/sdebnn_classification.py:27-51,173-213).
+
+Tolerances are stated PER ELEMENT as |a - b| <= atol + rtol * |b| with atol tied to the tensor's RMS (not its maximum),
+so small entries are checked too; the table below is the contract.  The sigma = 0.2 case is an expanding flow with random
+weights (|logit| ~ 3e4): rounding differences are amplified ~1e3 x per block, hence its own row.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import jax_path as jp
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+MODEL_KW = dict(input_size=(32, 32, 3), aug=2, nblocks=(2, 2, 2), fx_dim=64, fw_dims=(2, 64, 2), nsteps=20,
+                fx_actfn="softplus", fw_actfn="softplus")
+B, S = 8, 2
+KL_SCALE = 1e-3 / 45000
+
+# (rtol, atol as a fraction of the reference tensor's RMS) per quantity; scalar quantities use rtol only
+TOL = {
+    # math     sigma   loss    kl      logp(rtol, atol_rms)   grads(rtol, atol_rms)
+    ("fp32", 1e-4): dict(loss=1e-5, kl=1e-5, logp=(1e-4, 1e-4), grad=(2e-3, 2e-3)),
+    ("fp32", 0.2): dict(loss=2e-3, kl=1e-5, logp=(5e-3, 5e-3), grad=(2e-2, 2e-2)),
+    ("tc", 1e-4): dict(loss=1e-3, kl=1e-5, logp=(1e-2, 1e-2), grad=(5e-2, 5e-2)),
+    ("tc", 0.2): dict(loss=5e-2, kl=1e-5, logp=(1e-1, 1e-1), grad=(3e-1, 3e-1)),
+}
+
+_REF = {}
+
+
+def _reference(sigma):
+    if sigma in _REF:
+        return _REF[sigma]
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = jp.SDEBNNClassifier(batch=B, diff_coef=sigma, **MODEL_KW)
+    params, head = net.init(0, torch.float64, fw_last_std=1e-2)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, 32, 32, 3, generator=g, dtype=torch.float64)
+    labels = torch.randint(0, 10, (B,), generator=g)
+    onehot = torch.nn.functional.one_hot(labels, 10).double()
+    dWs = [torch.stack([jp.sample_increments(b.P, 20, g, torch.float64) for _ in range(S)]) for b in net.blocks()]
+    eps = torch.randn(S, net.feat * 10 + 10, generator=g, dtype=torch.float64)
+    pr, leaves = [], []
+    for (w0, fw) in params:
+        w0 = w0.clone().requires_grad_(True)
+        fw = [tuple(t.clone().requires_grad_(True) for t in lay) for lay in fw]
+        pr.append((w0, fw))
+        leaves += [w0] + [t for lay in fw for t in lay]
+    hr = tuple(tuple(t.clone().requires_grad_(True) for t in pair) for pair in head)
+    leaves += [hr[0][0], hr[0][1], hr[1][0], hr[1][1]]
+    losses, nlls, kls, logps = [], [], [], []
+    for s in range(S):
+        lo, nll, kl, logp = net.loss(pr, hr, x, onehot, [d[s] for d in dWs], eps[s], KL_SCALE)
+        losses.append(lo), nlls.append(nll.detach()), kls.append(kl.detach()), logps.append(logp.detach())
+    loss = torch.stack(losses).mean()  # mean over samples of the per-sample losses (script :231: mean of per-sample grads)
+    grads = torch.autograd.grad(loss, leaves)
+    _REF[sigma] = dict(params=params, head=head, x=x, labels=labels, dWs=dWs, eps=eps, loss=loss.detach(),
+                       nll=torch.stack(nlls), kl=torch.stack(kls), logp=torch.stack(logps), grads=grads)
+    return _REF[sigma]
+
+
+def _elem_check(a, b, rtol, atol_rms, what, stats):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    rms = float(b.pow(2).mean().sqrt())
+    err = (a - b).abs()
+    tol = atol_rms * rms + rtol * b.abs()
+    worst = float((err / tol.clamp_min(1e-300)).max())
+    stats[what] = dict(max_abs_err=float(err.max()), ref_rms=rms, ref_max=float(b.abs().max()), worst_over_tol=worst,
+                       rel_l2=float((a - b).norm() / b.norm().clamp_min(1e-300)))
+    return worst
+
+
+@pytest.mark.parametrize("sigma", [1e-4, 0.2])
+@pytest.mark.parametrize("math_mode", ["fp32", "tc"])
+def test_gpu_config4_full_model_vs_oracle(built_lib, math_mode, sigma):
+    from bayesde_b200.classification import SDEBNNClassifier
+    ref = _reference(sigma)
+    tol = TOL[(math_mode, sigma)]
+    net = SDEBNNClassifier(nsamples=S, diff_coef=sigma, math=math_mode, device=DEV, **MODEL_KW)
+    net.load_oracle_params(ref["params"], ref["head"])
+    rng = net.explicit_rng([d.float().to(DEV) for d in ref["dWs"]], ref["eps"].float().to(DEV))
+    x, labels = ref["x"].float().to(DEV), ref["labels"].to(DEV)
+    logp, kl = net.forward(x, rng)
+    loss, nll, klm = net.loss(x, labels, KL_SCALE, rng=rng)
+    loss.backward()
+    torch.cuda.synchronize()
+    stats, fails = {}, []
+    assert torch.isfinite(loss) and torch.isfinite(logp).all()
+    rel = lambda a, b: abs(float(a) - float(b)) / max(abs(float(b)), 1e-300)
+    stats["loss"] = dict(value=float(loss), ref=float(ref["loss"]), rel_err=rel(loss, ref["loss"]))
+    stats["kl"] = dict(rel_err=max(rel(kl[s], ref["kl"][s]) for s in range(S)))
+    if stats["loss"]["rel_err"] > tol["loss"]:
+        fails.append(f"loss rel err {stats['loss']['rel_err']:.2e} > {tol['loss']:.0e}")
+    if stats["kl"]["rel_err"] > tol["kl"]:
+        fails.append(f"KL rel err {stats['kl']['rel_err']:.2e} > {tol['kl']:.0e}")
+    if _elem_check(logp, ref["logp"], *tol["logp"], "logp", stats) > 1:
+        fails.append(f"logp {stats['logp']}")
+    leaves = net.oracle_ordered_parameters()
+    assert len(leaves) == len(ref["grads"])
+    worst_g = 0.0
+    for i, (p, gr) in enumerate(zip(leaves, ref["grads"])):
+        assert p.grad is not None and torch.isfinite(p.grad).all(), f"param {i}: missing / non-finite gradient"
+        w = _elem_check(p.grad, gr, *tol["grad"], f"grad{i}", stats)
+        worst_g = max(worst_g, w)
+        if w > 1:
+            fails.append(f"grad of param {i} {tuple(p.shape)}: {stats[f'grad{i}']}")
+    stats["worst_grad_over_tol"] = worst_g
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, f"parity_config4_{math_mode}_{sigma:g}.json"), "w") as f:
+            json.dump(dict(math=math_mode, sigma=sigma, tol={k: v for k, v in tol.items()}, stats=stats), f, indent=1)
+    assert not fails, "\n".join(fails)

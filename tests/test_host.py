@@ -28,7 +28,7 @@ def test_abi_exports_every_declared_symbol(built_lib):
     exported = set(re.findall(r" T (bsde_[a-z0-9_]+)", nm))
     assert declared <= exported
     lib.bsde_version.restype = C.c_int
-    assert lib.bsde_version() == 100
+    assert lib.bsde_version() == 200
 
 
 def test_struct_sizes_match_c(built_lib, tmp_path):
@@ -160,6 +160,66 @@ def test_gradient_allreduce_gloo_world2(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29617", str(script), ROOT],
                        capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
+
+
+_GLOO_SAMPLE_SHARD_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from bayesde_b200.classification import SDEBNNClassifier, Trainer, sample_shard
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+S = 4
+kw = dict(input_size=(4, 4, 3), aug=1, nblocks=(), device="cpu", seed=3)   # Augment -> mean-field Dense head: runs on CPU
+g = torch.Generator().manual_seed(0)
+x, y = torch.randn(6, 4, 4, 3, generator=g), torch.randint(0, 10, (6,), generator=g)
+# one process integrating all S samples
+full = SDEBNNClassifier(nsamples=S, **kw)
+tf = Trainer(full, lr=0.0, kl_coef=1.0, train_size=10)
+lf, nf, kf = tf.step(x, y, seed=11)
+ref = [p.grad.clone() for p in full.parameters()]
+# this rank's shard of the samples, same batch; gradients meet in ONE all-reduce (mean): overlap on and off
+off, per, bgrp, grp = sample_shard(S, world, rank)
+assert (per, grp) == (S // world, 1)
+for overlap in (False, True):
+    m = SDEBNNClassifier(nsamples=per, sample_offset=off, total_samples=S, **kw)
+    t = Trainer(m, lr=0.0, kl_coef=1.0, train_size=10, overlap=overlap)
+    lo, nl, kl = t.step(x, y, seed=11)
+    for p, r in zip(m.parameters(), ref):
+        assert torch.allclose(p.grad, r, rtol=1e-5, atol=1e-7), (rank, overlap, (p.grad - r).abs().max())
+    vals = torch.stack([lo, nl, kl])
+    dist.all_reduce(vals)
+    vals /= world                                   # every sample's KL is counted once: mean over ranks of the local means
+    assert torch.allclose(vals, torch.stack([lf, nf, kf]), rtol=1e-5), (vals, lf, nf, kf)
+# --acc_grad (script :220-240): chunk 0 twice, last chunk never, equal weights -- and the intended walk
+m = SDEBNNClassifier(nsamples=S, **kw)
+t = Trainer(m, lr=0.0, kl_coef=1.0, train_size=10, acc_grad=3)
+assert [(c.start, c.stop) for c in t._chunks(6)] == [(0, 2), (0, 2), (2, 4)]
+t.step(x, y, seed=11)
+g_ref = [p.grad.clone() for p in m.parameters()]
+acc = None
+for sl in (slice(0, 2), slice(0, 2), slice(2, 4)):
+    m.zero_grad()
+    m.loss(x[sl], y[sl], 0.1, rng=11)[0].backward()
+    acc = [p.grad / 3 for p in m.parameters()] if acc is None else [a + p.grad / 3 for a, p in zip(acc, m.parameters())]
+for a, r in zip(acc, g_ref):
+    assert torch.allclose(a, r, rtol=1e-5, atol=1e-6 * float(r.abs().max()))
+assert [(c.start, c.stop) for c in Trainer(m, acc_grad=3, acc_grad_mode="intended")._chunks(6)] == [(0, 2), (2, 4), (4, 6)]
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_sample_sharding_and_acc_grad_gloo_world2(tmp_path):
+    """SURVEY 8.5 samples x batch grid: two ranks with S/2 samples each (global Philox sample counters, global head-noise rows)
+    reproduce one rank with S samples after the single gradient all-reduce (serial and overlapped per-bucket launches); the
+    KL of every sample is counted once.  Also the `--acc_grad` loop of the script (:220-240) with its chunk quirk."""
+    script = tmp_path / "w2.py"
+    script.write_text(_GLOO_SAMPLE_SHARD_WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29618", str(script), ROOT],
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
 
