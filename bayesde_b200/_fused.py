@@ -121,6 +121,10 @@ def wsde_forward(cfg, w0, layers, dW, seed, stream_id, w_stale):
     wtraj = torch.empty(S, nit + 1, P, device=dev, dtype=torch.float32)
     z1 = torch.empty(nit * S * cfg.fw["hidden_dims"][0], device=dev, dtype=torch.float32)
     kl = torch.empty(S, device=dev, dtype=torch.float32)
+    cfg.kltraj = None
+    if getattr(cfg, "want_kltraj", False):   # the kl rows of `ys` (sdeint.py:138) for callers of the bare solver
+        cfg.kltraj = torch.empty(S, nit + 1, P, device=dev, dtype=torch.float32)
+        d.d_kltraj = cfg.kltraj.data_ptr()
     nbytes = L.bsde_wsde_workspace_bytes(C.byref(d), C.byref(fp))
     ws = _lib.workspace(nbytes, dev, "wsde")
     tk, dtk = cfg.grid_on(dev)
@@ -228,6 +232,8 @@ class SDEBNNSolve(torch.autograd.Function):
         ctx.acts = acts
         ctx.save_for_backward(wtraj, z1, xs)
         ctx.mark_non_differentiable(wtraj)
+        if getattr(cfg, "want_kltraj", False):
+            cfg.xs = xs   # every x_k (the scan's checkpoints): the x rows of `ys`
         return xs[cfg.nit].clone(), kl, wtraj
 
     @staticmethod

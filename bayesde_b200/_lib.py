@@ -33,7 +33,8 @@ class WsdeDesc(C.Structure):
     _fields_ = [("S", C.c_int32), ("nit", C.c_int32), ("stl", C.c_int32), ("w0_per_sample", C.c_int32),
                 ("sigma", C.c_float), ("kl_weight", C.c_float), ("ou_coef", C.c_float),
                 ("seed", C.c_uint64), ("stream_id", C.c_uint32), ("sample_offset", C.c_uint32),
-                ("d_dtkl", C.c_void_p), ("d_nscale", C.c_void_p), ("d_nidx", C.c_void_p), ("d_back", C.c_void_p)]
+                ("d_dtkl", C.c_void_p), ("d_nscale", C.c_void_p), ("d_nidx", C.c_void_p), ("d_back", C.c_void_p),
+                ("d_kltraj", C.c_void_p)]
 
 
 class ConvLayer(C.Structure):

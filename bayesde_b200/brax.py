@@ -37,11 +37,41 @@ class _AugDynamics:
         self.w0_per_sample = False
         self.sample_offset = 0
 
-    def f_aug(self, y, t, args):  # placeholders: the arithmetic lives in libbsde.so
-        raise NotImplementedError("f_aug is evaluated by the fused kernels; pass it to sdeint_ito_fixed_grid")
+    # f_aug / g_aug (brax.py:49-78) as plain callables: VALUES only (no autograd), evaluated by the same kernels as the fused
+    # solve -- one Euler iteration of K1 / K2 with dt = 1 and zero noise gives y + f(y), so f = (y + f) - y (exact to the fp32
+    # rounding of that sum).  Passing the bound methods to `sdeint_ito_fixed_grid` selects the fused solve instead.
+    def _one_step(self, y, t, args, sigma_noise):
+        S, P, x_dim = self.x_shape[0], self.P, self.x_dim
+        yy = y.reshape(S, x_dim + 2 * P).to(torch.float32)
+        x = yy[:, :x_dim].reshape(self.x_shape).contiguous()
+        w = yy[:, x_dim:x_dim + P].contiguous()
+        cfg, layers = self._config(2, np.asarray([0.0, 1.0], dtype=np.float32), P if self.stl else 0, "uniform", args, y.device)
+        cfg.set_step(float(t), 1.0)
+        cfg.want_kltraj = True
+        dW = sigma_noise.reshape(S, 1, P).to(torch.float32).contiguous() if sigma_noise is not None else torch.zeros(S, 1, P, device=y.device)
+        with torch.no_grad():
+            wtraj, _, _ = _fused.wsde_forward(cfg, w, layers, dW, 0, 0, self.w_stale)
+            xs, _ = _fused.xpath_forward(cfg, x, wtraj, keep_acts=False)
+        return yy, xs[1].reshape(S, x_dim), wtraj[:, 1], cfg.kltraj[:, 1]
+
+    def f_aug(self, y, t, args):
+        """brax.py:49-62: [dx, dw, dkl] at (y, t).  Values only; use `sdeint_ito_fixed_grid(f_aug, g_aug, ...)` for the solve."""
+        yy, x1, w1, kl1 = self._one_step(y, t, args, None)
+        x_dim, P = self.x_dim, self.P
+        out = torch.cat([x1 - yy[:, :x_dim], w1 - yy[:, x_dim:x_dim + P], kl1], dim=1)
+        return out.reshape(y.shape)
 
     def g_aug(self, y, t, args):
-        raise NotImplementedError("g_aug is evaluated by the fused kernels; pass it to sdeint_ito_fixed_grid")
+        """brax.py:64-78: [0_x, sigma 1_P, stl ? u(w_stale, t; stop_gradient(params)) : 0_P]  (quirk Q2: the stale vector)."""
+        S, P, x_dim = self.x_shape[0], self.P, self.x_dim
+        out = torch.zeros(S, x_dim + 2 * P, device=y.device, dtype=torch.float32)
+        out[:, x_dim:x_dim + P] = self.diff_coef
+        if self.stl:
+            # the kl row's noise coefficient: a unit increment on every w row adds exactly u_stale to the kl rows
+            _, _, _, kl_a = self._one_step(y, t, args, torch.ones(S, P, device=y.device))
+            _, _, _, kl_b = self._one_step(y, t, args, None)
+            out[:, x_dim + P:] = kl_a - kl_b
+        return out.reshape(y.shape)
 
     def _unpack(self, y0, rep):
         S, B, H, W, Cc = self.x_shape
@@ -77,10 +107,10 @@ class _AugDynamics:
             raise ValueError(f"need one PRNGKey per sample: {S} samples, {keys.shape[0]} keys")
         return [BrownianTree(tsl[0], self.x_dim + 2 * P, tsl[-1], k, depth=10, rep=rep, device=device) for k in keys]
 
-    def _solve(self, y0, ts, rng, args, method, rep, time_grid):
-        """y0: (S, x_dim + 2P) flat states (brax.py:110) or (x_dim + 2P,).  Returns ys[-1]-style
-        output packed as (T=2 rows: y0, y_T) is not needed by the layer, so the full tuple
-        (x_T, kl, wtraj) is returned for `SDEBNN.apply_fun`; `ys` is assembled there on demand."""
+    def _solve(self, y0, ts, rng, args, method, rep, time_grid, want_ys=False):
+        """y0: (S, x_dim + 2P) flat states (brax.py:110) or (x_dim + 2P,).  Returns the layer's view of the solution,
+        (x_T, kl [S], wtraj [S, T, P]) -- and, with `want_ys`, the reference's `ys` (T, D) (sdeint.py:138) assembled from the
+        scan's x checkpoints, the w trajectory and the kl-row trajectory."""
         S, P = self.x_shape[0], self.P
         x, w0 = self._unpack(y0, rep)
         # method: g_aug is state-independent as shipped (quirk Q2), so the Milstein correction
@@ -101,7 +131,19 @@ class _AugDynamics:
             dW, seed, sid = None, int(rng), self.stream_id
         flat = [t for lay in layers for t in lay]
         cfg.track = torch.is_grad_enabled()
-        return _fused.SDEBNNSolve.apply(cfg, dW, seed, sid, self.w_stale, x, w0, *flat)
+        cfg.want_kltraj = bool(want_ys)
+        xT, kl, wtraj = _fused.SDEBNNSolve.apply(cfg, dW, seed, sid, self.w_stale, x, w0, *flat)
+        if not want_ys:
+            return xT, kl, wtraj
+        # ys[k] = [x_k, w_k, kl_k] per sample.  Differentiable where the reference's own consumer differentiates it
+        # (brax.py:117-119): the x rows and the SUM of the kl rows of ys[-1]; the other rows are values.
+        T = cfg.nit + 1
+        ys = torch.cat([cfg.xs.reshape(T, S, -1), wtraj.transpose(0, 1), cfg.kltraj.transpose(0, 1)], dim=2)
+        last = torch.cat([xT.reshape(S, -1), wtraj[:, -1],
+                          cfg.kltraj[:, -1] + ((kl - kl.detach()) / P).unsqueeze(1)], dim=1)
+        ys = torch.cat([ys[:-1], last.unsqueeze(0)], dim=0)
+        cfg.xs = cfg.kltraj = None
+        return ys.reshape(T, -1) if y0.dim() == 1 else ys
 
     def _solve_adjoint(self, y0, ts, rng, args, dt, method, rep):
         """`sdeint_ito` (jaxsde/jaxsde/sdeint.py:11-13) for these dynamics: steps of `dt` on a Philox Brownian tree over the
@@ -197,7 +239,7 @@ def SDEBNN(fx_block_type, fx_dim, fx_actfn, fw, diff_coef=1e-4, name="sdebnn", s
         rep = P if stl else 0  # brax.py:111
         if fixed_grid:
             xo, kl_sde, wtraj = sdeint_ito_fixed_grid(dyn.f_aug, dyn.g_aug, y0, ts, rng, fw_params, method=method,
-                                                      rep=rep, time_grid=time_grid)
+                                                      rep=rep, time_grid=time_grid, _layer_view=True)
         else:  # brax.py:114-116 ("using stochastic adjoint"); `dt` (keyword) is sdeint_ito's step, default 1e-6 as there
             xo, kl_sde, wtraj = sdeint_ito(dyn.f_aug, dyn.g_aug, y0, ts, rng, fw_params, dt=kwargs.get("dt", 1e-6),
                                            method="euler_maruyama", rep=rep)

@@ -261,7 +261,13 @@ __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
           const float u = (mlp + (A.ou_coef + 1.f) * w) * inv_sigma;
           const float dWv = A.dW ? __ldg(A.dW + ((long long)s * nit + k) * P + p)
                                  : sq * philox_normal(A.d.seed, (uint32_t)p, nidx, (uint32_t)(s + A.s_base), A.d.stream_id);
-          klacc[s] += dtkl * A.d.kl_weight * u * u + ust * dWv;
+          const float klinc = dtkl * A.d.kl_weight * u * u + ust * dWv;
+          klacc[s] += klinc;
+          if (A.d.d_kltraj) {   // optional: the kl rows of ys (sdeint.py:138), read-modify-write by the element's owner thread
+            float* kt = A.d.d_kltraj + s * wstride + (long long)k * P + p;
+            kt[P] = (k == 0 ? 0.f : kt[0]) + klinc;
+            if (k == 0) kt[0] = 0.f;
+          }
           // base of the update: w_k, w_{k-1} (back = 1) or their average (back = 2: the corrector of a trapezoidal step)
           const float wb = back == 1 ? A.wtraj[s * wstride + (long long)(k - 1) * P + p]
                          : back == 2 ? 0.5f * (A.wtraj[s * wstride + (long long)(k - 1) * P + p] + w) : w;
@@ -611,6 +617,7 @@ extern "C" int bsde_wsde_fwd(const bsde_wsde_desc* d, const bsde_fw_params* fw, 
     A.dW = d_dW ? d_dW + (size_t)s0 * nit * P : nullptr;
     A.wstale = d_w_stale;
     A.wtraj = d_wtraj + (size_t)s0 * (nit + 1) * P;
+    if (d->d_kltraj) A.d.d_kltraj = d->d_kltraj + (size_t)s0 * (nit + 1) * P;
     A.kl = d_kl + s0;
     float* ws = (float*)workspace;
     A.partials = ws; ws += (size_t)2 * MAXG * SC * ME;

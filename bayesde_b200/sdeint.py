@@ -85,8 +85,12 @@ def _gdg(g, y, t, args):
     return out if track else out.detach()
 
 
-def sdeint_ito_fixed_grid(f, g, y0, ts, rng, args=(), dt=1e-6, method="milstein", rep=0, time_grid="reference"):
-    """Fixed-grid Ito solve; returns ys of shape (len(ts), D) including y0 (sdeint.py:138).
+def sdeint_ito_fixed_grid(f, g, y0, ts, rng, args=(), dt=1e-6, method="milstein", rep=0, time_grid="reference", *,
+                          _layer_view=False):
+    """Fixed-grid Ito solve; returns ys of shape (len(ts), D) including y0 (sdeint.py:138) -- also on the structured route
+    (`f`, `g` = the `f_aug` / `g_aug` of an SDEBNN block: D = x_dim + 2P per sample, a leading sample axis is kept when y0 has
+    one), so `ys[-1][:x_dim]`, `ys[:, x_dim:x_dim+P]` and `ys[-1][x_dim+P:].sum()` read as in brax.py:117-127.  `_layer_view`
+    is the SDEBNN layer's private short cut to (x_T, kl, w trajectory) without materialising `ys`.
 
     `dt` is ignored on the fixed grid, as in the reference.  `rep` ties the noise of the last `rep`
     state entries to the `rep` entries before them (jaxsde/jaxsde/brownian.py:69-74).
@@ -96,7 +100,7 @@ def sdeint_ito_fixed_grid(f, g, y0, ts, rng, args=(), dt=1e-6, method="milstein"
         raise ValueError("Unknown method: {}".format(method))  # sdeint.py:62
     owner = getattr(f, "__self__", None)
     if owner is not None and getattr(owner, "_bsde_structured", False) and getattr(g, "__self__", None) is owner:
-        return owner._solve(y0, ts, rng, args, method, rep, time_grid)
+        return owner._solve(y0, ts, rng, args, method, rep, time_grid, want_ys=not _layer_view)
 
     if not y0.is_cuda:
         raise _lib.BsdeError("sdeint_ito_fixed_grid needs CUDA tensors (there is no CPU fallback)")

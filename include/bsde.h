@@ -125,6 +125,10 @@ typedef struct {
    * dt = (h, h/2), dtkl = (h/2, h/2), nscale = (sqrt(h), sqrt(h)/2), nidx = (k, k), back = (0, 2).  midpoint: dt = (h/2, h), dtkl = (0, h), nscale = (sqrt(h)/2, sqrt(h)),
    * nidx = (k, k), back = (0, 1) for step k; the trajectory then holds w_k in slot 2k and the midpoint state in slot 2k+1. */
   const float* d_dtkl; const float* d_nscale; const int32_t* d_nidx; const int32_t* d_back;
+  /* Optional output of bsde_wsde_fwd (NULL = not written): the kl ROWS of the state at every scan time, [S][nit+1][P]
+   * (slot 0 = 0) -- what `ys[:, x_dim+P:]` of sdeint_ito_fixed_grid holds (jaxsde/jaxsde/sdeint.py:138; brax.py:110).  The
+   * layer itself only consumes their sum at the final time (brax.py:119), which is d_kl. */
+  float* d_kltraj;
 } bsde_wsde_desc;
 
 size_t bsde_wsde_workspace_bytes(const bsde_wsde_desc* d, const bsde_fw_params* fw);

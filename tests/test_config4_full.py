@@ -28,13 +28,21 @@ MODEL_KW = dict(input_size=(32, 32, 3), aug=2, nblocks=(2, 2, 2), fx_dim=64, fw_
 B, S = 8, 2
 KL_SCALE = 1e-3 / 45000
 
-# (rtol, atol as a fraction of the reference tensor's RMS) per quantity; scalar quantities use rtol only
+# (rtol, atol as a fraction of the reference tensor's RMS) per quantity; scalar quantities use rtol only; `l2` bounds the
+# relative L2 error of every gradient tensor.  Measured on a B200 (gpurun_out/parity_config4_*.json of round 2, worst case over
+# all 126 parameter tensors), which is what the bounds are set from (~4x head-room):
+#   fp32  sigma 1e-4: loss 3e-8, log-probabilities 6e-7 rel-L2, gradients 7e-7 rel-L2
+#   fp32  sigma 0.2 : loss 7e-7, log-probabilities 2e-6,        gradients 7e-5      <- 100x the sigma = 1e-4 error: the
+#         flow with random weights and sigma = 0.2 EXPANDS (|logit| ~ 3e4), so rounding differences are amplified
+#   tc    sigma 1e-4: loss 1e-7, log-probabilities 4e-4,        gradients 8e-4      (TF32 operands: unit round-off 2^-11)
+#   tc    sigma 0.2 : loss 2.4e-2, log-probabilities 2.5e-2,    gradients 3e-2 .. 1.6e-1 rel-L2 -- the same ~100-1000x
+#         amplification applied to TF32's round-off (2^13 x fp32's): conditioning of the benchmark's sigma, not a kernel
+#         defect; the well-conditioned row above is the arithmetic check, this row bounds the drift in the chaotic regime
 TOL = {
-    # math     sigma   loss    kl      logp(rtol, atol_rms)   grads(rtol, atol_rms)
-    ("fp32", 1e-4): dict(loss=1e-5, kl=1e-5, logp=(1e-4, 1e-4), grad=(2e-3, 2e-3)),
-    ("fp32", 0.2): dict(loss=2e-3, kl=1e-5, logp=(5e-3, 5e-3), grad=(2e-2, 2e-2)),
-    ("tc", 1e-4): dict(loss=1e-3, kl=1e-5, logp=(1e-2, 1e-2), grad=(5e-2, 5e-2)),
-    ("tc", 0.2): dict(loss=5e-2, kl=1e-5, logp=(1e-1, 1e-1), grad=(3e-1, 3e-1)),
+    ("fp32", 1e-4): dict(loss=1e-6, kl=1e-6, logp=(1e-5, 1e-5), grad=(1e-4, 1e-4), l2=1e-5),
+    ("fp32", 0.2): dict(loss=1e-5, kl=1e-6, logp=(1e-4, 1e-4), grad=(5e-3, 5e-3), l2=5e-4),
+    ("tc", 1e-4): dict(loss=1e-5, kl=1e-6, logp=(5e-3, 5e-3), grad=(2e-2, 2e-2), l2=4e-3),
+    ("tc", 0.2): dict(loss=8e-2, kl=1e-6, logp=(1e-1, 1e-1), grad=(1.0, 1.0), l2=0.4),
 }
 
 _REF = {}
@@ -99,7 +107,7 @@ def test_gpu_config4_full_model_vs_oracle(built_lib, math_mode, sigma):
     stats, fails = {}, []
     assert torch.isfinite(loss) and torch.isfinite(logp).all()
     rel = lambda a, b: abs(float(a) - float(b)) / max(abs(float(b)), 1e-300)
-    stats["loss"] = dict(value=float(loss), ref=float(ref["loss"]), rel_err=rel(loss, ref["loss"]))
+    stats["loss"] = dict(value=float(loss.detach()), ref=float(ref["loss"]), rel_err=rel(loss.detach(), ref["loss"]))
     stats["kl"] = dict(rel_err=max(rel(kl[s], ref["kl"][s]) for s in range(S)))
     if stats["loss"]["rel_err"] > tol["loss"]:
         fails.append(f"loss rel err {stats['loss']['rel_err']:.2e} > {tol['loss']:.0e}")
@@ -114,7 +122,7 @@ def test_gpu_config4_full_model_vs_oracle(built_lib, math_mode, sigma):
         assert p.grad is not None and torch.isfinite(p.grad).all(), f"param {i}: missing / non-finite gradient"
         w = _elem_check(p.grad, gr, *tol["grad"], f"grad{i}", stats)
         worst_g = max(worst_g, w)
-        if w > 1:
+        if w > 1 or stats[f"grad{i}"]["rel_l2"] > tol["l2"]:
             fails.append(f"grad of param {i} {tuple(p.shape)}: {stats[f'grad{i}']}")
     stats["worst_grad_over_tol"] = worst_g
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")

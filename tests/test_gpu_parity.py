@@ -173,6 +173,68 @@ def test_sdebnn_block_forward_backward(built_lib, kw):
         _gclose(a, b, gt, f"grad {n}")
 
 
+@pytest.mark.parametrize("stl", [False, True])
+def test_structured_route_returns_ys_and_callable_dynamics(built_lib, stl):
+    """Drop-in boundary (jaxsde/jaxsde/sdeint.py:138): `sdeint_ito_fixed_grid(dyn.f_aug, dyn.g_aug, y0, ts, rng, fw_params)`
+    returns ys (T, D) also on the fused route -- x rows, w rows and kl rows of EVERY scan time against the oracle's generic
+    solve of the flat state, `ys[-1][:x_dim]` / `ys[-1][x_dim+P:].sum()` differentiable as brax.py:117-119 consumes them --
+    and `f_aug` / `g_aug` are callable (values) like the reference's closures (brax.py:49-78)."""
+    from bayesde_b200 import arch, brax, sdeint_ito_fixed_grid
+    blk, w0, fw, x, dW = _block_case(S=1, B=2, H=6, C_in=4, fx_dim=8, nsteps=5, stl=stl)
+    fw_layer = arch.MLP((2, 16, 2), xt=True, ou_dw=True)
+    layer = brax.SDEBNN(0, 8, "softplus", fw_layer, diff_coef=blk.diff_coef, stl=stl, xt=True, nsteps=blk.nsteps)
+    _, (w_stale_like, _, _) = layer.init(0, tuple(x.shape[1:]))
+    blk.w_stale = w_stale_like.double()
+    P, x_dim = blk.P, blk.x_dim
+    # oracle: the generic solver on the flat state [x, w, kl] (brax.py:110-113)
+    w0r = w0.clone().requires_grad_(True)
+    y0_r = torch.cat([x[0].reshape(-1), w0r, torch.zeros(P, dtype=torch.float64)])
+    inc = torch.cat([dW[0].new_zeros(dW.shape[1], x_dim), dW[0], dW[0]], dim=1)
+    ts = torch.linspace(0.0, 1.0, blk.nsteps)
+    ys_r = jp.sdeint_ito_fixed_grid(blk.f_aug, blk.g_aug, y0_r, ts.double(), inc, fw, method="euler_maruyama", rep=P if stl else 0)
+    obj_r = ys_r[-1][:x_dim].pow(2).sum() + 1e-3 * ys_r[-1][x_dim + P:].sum()
+    (g_r,) = torch.autograd.grad(obj_r, w0r)
+
+    dyn = brax._AugDynamics(arch.FxSpec(0, (1,) + tuple(x.shape[2:]), 8, "softplus"), fw_layer.spec, x.shape, blk.diff_coef, stl,
+                            True, "fp32", w_stale_like.to(DEV), 0)
+    w0d = w0.float().to(DEV).requires_grad_(True)
+    y0 = torch.cat([x[0].reshape(-1).float().to(DEV), w0d, torch.zeros(P, device=DEV)])
+    fwd = _product_fw_params(fw, DEV)
+    ys = sdeint_ito_fixed_grid(dyn.f_aug, dyn.g_aug, y0, ts, dW.float().to(DEV), fwd, method="euler_maruyama", rep=P if stl else 0)
+    assert ys.shape == ys_r.shape == (blk.nsteps, x_dim + 2 * P)
+    _close(ys[:, :x_dim], ys_r[:, :x_dim], 1e-4, 1e-5, "ys x rows")
+    _close(ys[:, x_dim:x_dim + P], ys_r[:, x_dim:x_dim + P], 1e-5, 1e-6, "ys w rows")
+    _close(ys[:, x_dim + P:], ys_r[:, x_dim + P:], 1e-4, 1e-4 * float(ys_r[:, x_dim + P:].abs().max()), "ys kl rows")
+    obj = ys[-1][:x_dim].pow(2).sum() + 1e-3 * ys[-1][x_dim + P:].sum()
+    (g_d,) = torch.autograd.grad(obj, w0d)
+    _gclose(g_d, g_r, 1e-3, "d/dw0 through ys[-1]")
+    # the closures themselves, at an interior state and time
+    yk, t = ys_r[2].detach(), 0.37
+    f_r, g_ref = blk.f_aug(yk, torch.tensor(t, dtype=torch.float64), fw), blk.g_aug(yk, torch.tensor(t, dtype=torch.float64), fw)
+    f_d = dyn.f_aug(yk.float().to(DEV), t, fwd)
+    g_d2 = dyn.g_aug(yk.float().to(DEV), t, fwd)
+    for name, sl in (("dx", slice(0, x_dim)), ("dw", slice(x_dim, x_dim + P)), ("dkl", slice(x_dim + P, None))):
+        _tc_close(f_d[sl], f_r[sl], 2e-5, f"f_aug {name}")
+        _tc_close(g_d2[sl], g_ref[sl], 2e-5, f"g_aug {name}")
+
+
+def test_meanfield_wraps_a_stochastic_layer(built_lib):
+    """`--meanfield_sdebnn` (examples/jax/sdebnn_classification.py:180-194): MeanField(SDEBNN(..., stax_api=True)).  The wrapper
+    must hand the wrapped layer `rng=next_rng` (brax.py:150,165) -- SDEBNN.apply_fun needs it for its Brownian path."""
+    from bayesde_b200 import arch, brax
+    inner = brax.SDEBNN(0, 8, "softplus", arch.MLP((2, 8, 2), xt=True, ou_dw=True), diff_coef=0.1, xt=True, nsteps=4,
+                        stax_api=True)
+    init, apply = brax.MeanField(inner)
+    _, params = init(3, (2, 6, 6, 4))
+    params = brax.tree_map(lambda t: t.to(DEV), params)
+    x = torch.randn(2, 6, 6, 4, device=DEV)
+    out1, kl1 = apply(params, x, rng=5)
+    out2, kl2 = apply(params, x, rng=5)
+    out3, _ = apply(params, x, rng=6)
+    assert out1.shape == x.shape and torch.isfinite(out1).all() and kl1.dim() == 0 and float(kl1) > 0
+    assert torch.equal(out1, out2) and torch.equal(kl1, kl2) and not torch.equal(out1, out3)
+
+
 def test_block_types_1_and_2(built_lib):
     """arch.py:189-205: block_type 1 (3x3, 3x3, 3x3 as shipped: the `(1, 1)` of arch.py:193 lands in ConcatConv2D's unused W_init
     slot, diffeq_layers.py:124, so kernel stays 3) and 2 (3x3, 3x3)."""
