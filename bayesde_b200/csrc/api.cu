@@ -580,7 +580,10 @@ __global__ void philox_increments_kernel(uint64_t seed, uint32_t stream_id, int 
     const long long p = i % P;
     const long long r = i / P;
     const int k = (int)(r % nit), s = (int)(r / nit);
-    out[i] = sqrtf(fmaxf(dtk[k], 0.f)) * philox_normal(seed, (uint32_t)p, (uint32_t)k, (uint32_t)s, stream_id);
+    float z4[4];   // the K1 increments stream: one Philox call per four samples (common.cuh: philox_normal4)
+    philox_normal4(seed, (uint32_t)p, (uint32_t)k, (uint32_t)s >> 2, stream_id, z4);
+    const int zc = s & 3;
+    out[i] = sqrtf(fmaxf(dtk[k], 0.f)) * (zc == 0 ? z4[0] : zc == 1 ? z4[1] : zc == 2 ? z4[2] : z4[3]);
   }
 }
 }  // namespace bsde

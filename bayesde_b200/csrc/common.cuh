@@ -121,6 +121,27 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t p, uint32
   return r * cs;
 }
 
+// four standard normals of the increments stream from ONE Philox call: counter (element, iteration, sample / 4, stream);
+// sample s takes component s & 3 (two Box-Muller pairs).  Shared by the K1 kernels and bsde_philox_increments, which must agree
+// bit for bit, so both use this one function.  lg2 / sin / cos are the MUFU approximations (absolute error ~1e-6 on the normal,
+// far below the fp32 rounding of sigma * dW in the update; the law tests bound mean / variance / kurtosis): the K1 pass over P
+// is bound by this arithmetic once its state is resident.
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t p, uint32_t k, uint32_t sgroup, uint32_t stream_id,
+                                               float (&z)[4]) {
+  uint32_t c[4] = {p, k, sgroup, stream_id};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = ((float)c[2 * h] + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+    const float u2 = (float)c[2 * h + 1] * 2.3283064365386963e-10f;       // [0,1)
+    const float r = sqrtf(-1.3862943611198906f * __log2f(fmaxf(u1, 1e-37f)));   // sqrt(-2 ln u1)
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    z[2 * h] = r * cs;
+    z[2 * h + 1] = r * sn;
+  }
+}
+
 // arguments of the fixed-order split reduction of weight-gradient partial tiles (tconv_simt.cu)
 struct WreduceArgs {
   const float* partial;

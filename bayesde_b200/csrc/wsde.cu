@@ -17,6 +17,8 @@
 // fewer DRAM bytes than the 48*P algorithmic figure of SURVEY.md 8.4.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -64,6 +66,9 @@ struct WsdeArgs {
   float* ghold;     // [S][P] (bwd, stage tables with back = 1)
   float ou_coef;
   int s_base;  // global index of local sample 0 (Philox counter)
+  int ept;     // RES kernels: resident elements per thread (ceil(P / (G * NTHREADS)))
+  int stamp;   // tools only
+  int tp_floats;  // > 0: the tiny MLP's parameters are staged in shared memory (that many floats)
 };
 
 // ---- block-level reduction of NV per-thread values; result (sum over the CTA) to dst[v] -------
@@ -85,14 +90,29 @@ __device__ __forceinline__ void block_reduce_store(float (&v)[NV], float* sh_red
   __syncthreads();
 }
 
-// sum partials over CTAs in a fixed order: out[v] = sum_g part[g*stride + v], v < nv
-__device__ __forceinline__ void gather_partials(const float* part, int G, int stride, int nv, float* out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int v = warp; v < nv; v += NWARPS) {
-    float r = 0.f;
-    for (int g = lane; g < G; g += 32) r += __ldcg(part + (long long)g * stride + v);
-    r = warp_sum(r);
-    if (lane == 0) out[v] = r;
+// sum partials over CTAs in a fixed order: out[v] = sum_g part[g*stride + v], v < nv <= 32.  Thread (v = tid & 31, c = tid >> 5)
+// adds the partials of CTAs c, c + NWARPS, ... (independent, coalesced loads: one L2 round trip), then NWARPS chunk sums are added
+// in order -- identical on every CTA.  `scratch` = NWARPS * 32 floats of shared memory.
+__device__ __forceinline__ void gather_partials(const float* part, int G, int stride, int nv, float* out, float* scratch) {
+  const int v = threadIdx.x & 31, c = threadIdx.x >> 5;
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+  if (v < nv) {
+    const float* q = part + v;
+    int g = c;
+    for (; g + 3 * NWARPS < G; g += 4 * NWARPS) {
+      const float a0 = __ldcg(q + (long long)g * stride), a1 = __ldcg(q + (long long)(g + NWARPS) * stride);
+      const float a2 = __ldcg(q + (long long)(g + 2 * NWARPS) * stride), a3 = __ldcg(q + (long long)(g + 3 * NWARPS) * stride);
+      r0 += a0; r1 += a1; r2 += a2; r3 += a3;
+    }
+    for (; g < G; g += NWARPS) r0 += __ldcg(q + (long long)g * stride);
+  }
+  scratch[c * 32 + v] = (r0 + r1) + (r2 + r3);
+  __syncthreads();
+  if (threadIdx.x < nv) {
+    float t = 0.f;
+#pragma unroll
+    for (int c2 = 0; c2 < NWARPS; ++c2) t += scratch[c2 * 32 + threadIdx.x];
+    out[threadIdx.x] = t;
   }
   __syncthreads();
 }
@@ -100,14 +120,70 @@ __device__ __forceinline__ void gather_partials(const float* part, int G, int st
 // ---- the tiny middle of f_w, per sample row.  Stores a (pre-gate), g (gate), y (pre-activation)
 // and h (activation) for every hidden layer so the reverse pass can reuse them. ----------------
 struct TinySmem {
-  float* a;  // [SC][wsum]
-  float* g;  // [wsum]   (gate is sample-independent)
-  float* y;  // [SC][wsum]
-  float* h;  // [SC][wsum]
+  float* a;    // [SC+1][wsum]
+  float* g;    // [wsum]   gate sigmoid(w_t t + w_tb) (sample-independent)
+  float* y;    // [SC+1][wsum]
+  float* h;    // [SC+1][wsum]
+  float* btt;  // [wsum]   shift b_t * t
 };
 
-__device__ __forceinline__ void tiny_forward(const WsdeArgs& A, const TinySmem& T, const float* z1raw /*[S][d1] smem*/,
-                                             int S, float t) {
+constexpr int TL = BSDE_FW_MAX_MID + 1;   // hidden layers of the tiny MLP
+constexpr int TP_MAX = 6144;              // floats of tiny parameters staged in shared memory once per launch (else: global)
+// b, w_t, w_tb, b_t of hidden layer l (dims[l] each) and, for l >= 1, W [dims[l-1]][dims[l]]: shared-memory copies or the originals
+struct TinyPar {
+  const float* b[TL]; const float* wt[TL]; const float* wtb[TL]; const float* bt[TL]; const float* W[TL];
+};
+struct TinyGrad {
+  float* b[TL]; float* wt[TL]; float* wtb[TL]; float* bt[TL]; float* W[TL];
+};
+__host__ __device__ inline int tiny_par_floats(const TinyDims& td) {
+  int f = 0;
+  for (int l = 0; l < td.nhid; ++l) f += 4 * td.dims[l] + (l > 0 ? td.dims[l - 1] * td.dims[l] : 0);
+  return f;
+}
+__device__ __forceinline__ void tiny_par_init(const bsde_fw_params& fw, const TinyDims& td, float* stage, TinyPar& TP) {
+  for (int l = 0; l < td.nhid; ++l) {
+    TP.b[l] = l == 0 ? fw.b1 : fw.bm[l - 1];
+    TP.wt[l] = l == 0 ? fw.wt1 : fw.wtm[l - 1];
+    TP.wtb[l] = l == 0 ? fw.wtb1 : fw.wtbm[l - 1];
+    TP.bt[l] = l == 0 ? fw.bt1 : fw.btm[l - 1];
+    TP.W[l] = l == 0 ? nullptr : fw.Wm[l - 1];
+  }
+  if (!stage) return;
+  float* q = stage;
+  for (int l = 0; l < td.nhid; ++l) {
+    const int d = td.dims[l];
+    const float* src[4] = {TP.b[l], TP.wt[l], TP.wtb[l], TP.bt[l]};
+    for (int f = 0; f < 4; ++f) {
+      if (f == 0 || !fw.plain)
+        for (int j = threadIdx.x; j < d; j += NTHREADS) q[j] = __ldg(src[f] + j);
+      if (f == 0) TP.b[l] = q; else if (f == 1) TP.wt[l] = q; else if (f == 2) TP.wtb[l] = q; else TP.bt[l] = q;
+      q += d;
+    }
+    if (l > 0) {
+      const int n = td.dims[l - 1] * d;
+      for (int j = threadIdx.x; j < n; j += NTHREADS) q[j] = __ldg(TP.W[l] + j);
+      TP.W[l] = q;
+      q += n;
+    }
+  }
+  __syncthreads();
+}
+
+// gates and shifts of every hidden unit at time t (sample-independent; no dependence on the state): callers run it BEFORE
+// the partials gather so that it overlaps that round trip; a later __syncthreads publishes it
+__device__ __forceinline__ void tiny_gates(const bsde_fw_params& fw, const TinyDims& td, const TinyPar& TP, const TinySmem& T, float t) {
+  for (int idx = threadIdx.x; idx < td.wsum; idx += NTHREADS) {
+    int l = 0;
+    while (l + 1 < td.nhid && idx >= td.off[l + 1]) ++l;
+    const int j = idx - td.off[l];
+    T.g[idx] = fw.plain ? 1.f : sigmoidf_(TP.wt[l][j] * t + TP.wtb[l][j]);
+    T.btt[idx] = fw.plain ? 0.f : TP.bt[l][j] * t;
+  }
+}
+
+__device__ __forceinline__ void tiny_forward(const WsdeArgs& A, const TinyPar& TP, const TinySmem& T, const float* z1raw /*[S][d1] smem*/,
+                                             int S) {
   const TinyDims& td = A.td;
   const int wsum = td.wsum;
   // layer 0 (first hidden): a = z1 + b1
@@ -115,11 +191,9 @@ __device__ __forceinline__ void tiny_forward(const WsdeArgs& A, const TinySmem& 
     const int d1 = td.dims[0];
     for (int idx = threadIdx.x; idx < S * d1; idx += NTHREADS) {
       const int s = idx / d1, j = idx - s * d1;
-      const float a = z1raw[s * ME + j] + __ldg(A.fw.b1 + j);
-      const float g = A.fw.plain ? 1.f : sigmoidf_(__ldg(A.fw.wt1 + j) * t + __ldg(A.fw.wtb1 + j));
-      const float y = A.fw.plain ? a : a * g + __ldg(A.fw.bt1 + j) * t;
+      const float a = z1raw[s * ME + j] + TP.b[0][j];
+      const float y = a * T.g[j] + T.btt[j];
       T.a[s * wsum + j] = a;
-      if (s == 0) T.g[j] = g;
       T.y[s * wsum + j] = y;
       T.h[s * wsum + j] = act_fwd(A.fw.act, y);
     }
@@ -128,15 +202,19 @@ __device__ __forceinline__ void tiny_forward(const WsdeArgs& A, const TinySmem& 
   for (int l = 0; l + 1 < td.nhid; ++l) {
     const int din = td.dims[l], dout = td.dims[l + 1];
     const int oi = td.off[l], oo = td.off[l + 1];
-    const float* __restrict__ W = A.fw.Wm[l];
+    const float* W = TP.W[l + 1];
     for (int idx = threadIdx.x; idx < S * dout; idx += NTHREADS) {
       const int s = idx / dout, j = idx - s * dout;
-      float a = __ldg(A.fw.bm[l] + j);
-      for (int q = 0; q < din; ++q) a = fmaf(T.h[s * wsum + oi + q], __ldg(W + q * dout + j), a);
-      const float g = A.fw.plain ? 1.f : sigmoidf_(__ldg(A.fw.wtm[l] + j) * t + __ldg(A.fw.wtbm[l] + j));
-      const float y = A.fw.plain ? a : a * g + __ldg(A.fw.btm[l] + j) * t;
+      float a0 = TP.b[l + 1][j], a1 = 0.f;
+      int q = 0;
+      for (; q + 1 < din; q += 2) {
+        a0 = fmaf(T.h[s * wsum + oi + q], W[q * dout + j], a0);
+        a1 = fmaf(T.h[s * wsum + oi + q + 1], W[(q + 1) * dout + j], a1);
+      }
+      if (q < din) a0 = fmaf(T.h[s * wsum + oi + q], W[q * dout + j], a0);
+      const float a = a0 + a1;
+      const float y = a * T.g[oo + j] + T.btt[oo + j];
       T.a[s * wsum + oo + j] = a;
-      if (s == 0) T.g[oo + j] = g;
       T.y[s * wsum + oo + j] = y;
       T.h[s * wsum + oo + j] = act_fwd(A.fw.act, y);
     }
@@ -149,6 +227,35 @@ __device__ __forceinline__ float inv_or_zero(float s) { return s != 0.f ? 1.f / 
 // =============================================================================================
 // forward
 // =============================================================================================
+// Per-thread resident storage in shared memory (RES kernels): slot (field f, element e) of thread tid lives at
+// base[(f * ept + e) * NTHREADS + tid] -- consecutive threads hit consecutive banks.  A thread owns the elements
+// p = gtid + e * NT, e < ept, for the whole launch, so its w state, the f_w parameter vectors of its elements and (reverse
+// pass) its adjoint and gradient accumulators stay on chip across all scan iterations (north star (a)).
+// tools-only phase stamps (BSDE_K1_STAMP=1; read back with bsde_debug_k1_stamps): %globaltimer of CTA 0 / thread 0 at the
+// phase boundaries of every forward / reverse iteration
+constexpr int STAMP_PH = 8, STAMP_IT = 64;
+__device__ unsigned long long g_k1_stamps[2][STAMP_IT][STAMP_PH];
+__device__ __forceinline__ void k1_stamp(int on, int which, int k, int ph) {
+  if (on && blockIdx.x == 0 && threadIdx.x == 0 && k < STAMP_IT) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_k1_stamps[which][k][ph] = t;
+  }
+}
+
+struct Slots {
+  float* base;  // already offset by threadIdx.x
+  int ept;
+  __device__ __forceinline__ float& operator()(int f, int e) const { return base[(f * ept + e) * NTHREADS]; }
+};
+// field indices
+constexpr int F_W1 = 0, F_W4 = ME, F_B4 = 2 * ME, F_WT4 = 2 * ME + 1, F_WTB4 = 2 * ME + 2, F_BT4 = 2 * ME + 3;
+constexpr int F_NPAR = 2 * ME + 4;
+constexpr int FF_STALE = F_NPAR, FF_W = F_NPAR + 1, FF_N = FF_W + SC;                              // forward
+constexpr int FB_GW1 = F_NPAR, FB_GW4 = FB_GW1 + ME, FB_GB4 = FB_GW4 + ME, FB_LAM = FB_GB4 + 4, FB_N = FB_LAM + SC;  // reverse
+constexpr int MAXE = 6;   // resident elements per thread; larger P runs the streaming instantiation
+
+template <bool RES>
 __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ float smem[];
@@ -164,14 +271,22 @@ __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
   T.g = T.a + (SC + 1) * wsum;
   T.y = T.g + wsum;
   T.h = T.y + (SC + 1) * wsum;
-  float* sh_z1 = T.h + (SC + 1) * wsum;  // [(SC+1)][ME]  (row SC = stale vector)
+  T.btt = T.h + (SC + 1) * wsum;
+  float* sh_z1 = T.btt + wsum;            // [(SC+1)][ME]  (row SC = stale vector)
   float* sh_red = sh_z1 + (SC + 1) * ME;  // [NWARPS][SC*ME]
   float* sh_hst = sh_red + NWARPS * SC * ME;  // [ME] hL of the stale vector
+  float* sh_stage = sh_hst + ME;          // [tp_floats] staged tiny parameters
+  Slots R;
+  R.base = sh_stage + A.tp_floats + threadIdx.x;
+  R.ept = A.ept;
+  TinyPar TP;
+  tiny_par_init(A.fw, A.td, A.tp_floats ? sh_stage : nullptr, TP);
 
   const float sigma = A.d.sigma, inv_sigma = inv_or_zero(sigma);
   const long long wstride = (long long)(nit + 1) * P;
+  const uint32_t sg0 = (uint32_t)A.s_base >> 2, sph = (uint32_t)A.s_base & 3u;  // sample group / phase of local sample 0
 
-  // ---- phase 0: w_0 -> trajectory slot 0, partial dots of w_0 (and of w_stale)
+  // ---- phase 0: w_0 -> trajectory slot 0, partial dots of w_0 (and of w_stale); RES: parameters and state -> slots
   {
     float acc[SC * ME];
 #pragma unroll
@@ -179,15 +294,29 @@ __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
     float accst[ME];
 #pragma unroll
     for (int j = 0; j < ME; ++j) accst[j] = 0.f;
-    for (long long p = gtid; p < P; p += NT) {
+    int e = 0;
+    for (long long p = gtid; p < P; p += NT, ++e) {
       float w1[ME];
 #pragma unroll
       for (int j = 0; j < ME; ++j) w1[j] = j < d1 ? __ldg(A.fw.W1 + p * d1 + j) : 0.f;
+      if (RES) {
+#pragma unroll
+        for (int j = 0; j < ME; ++j) {
+          R(F_W1 + j, e) = w1[j];
+          R(F_W4 + j, e) = j < dL ? __ldg(A.fw.W4 + (long long)j * P + p) : 0.f;
+        }
+        R(F_B4, e) = __ldg(A.fw.b4 + p);
+        R(F_WT4, e) = A.fw.plain ? 0.f : __ldg(A.fw.wt4 + p);
+        R(F_WTB4, e) = A.fw.plain ? 0.f : __ldg(A.fw.wtb4 + p);
+        R(F_BT4, e) = A.fw.plain ? 0.f : __ldg(A.fw.bt4 + p);
+        R(FF_STALE, e) = A.d.stl ? __ldg(A.wstale + p) : 0.f;
+      }
 #pragma unroll
       for (int s = 0; s < SC; ++s) {
         if (s < S) {
           const float w = __ldg(A.w0 + (A.d.w0_per_sample ? (long long)s * P : 0) + p);
           A.wtraj[s * wstride + p] = w;
+          if (RES) R(FF_W + s, e) = w;
 #pragma unroll
           for (int j = 0; j < ME; ++j) acc[s * ME + j] = fmaf(w, w1[j], acc[s * ME + j]);
         }
@@ -202,7 +331,7 @@ __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
     if (A.d.stl) block_reduce_store<ME>(accst, sh_red, A.stpart + (long long)blockIdx.x * ME, ME);
   }
   grid.sync();
-  if (A.d.stl) gather_partials(A.stpart, G, ME, ME, sh_z1 + SC * ME);
+  if (A.d.stl) gather_partials(A.stpart, G, ME, ME, sh_z1 + SC * ME, sh_red);
 
   float klacc[SC];
 #pragma unroll
@@ -217,7 +346,10 @@ __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
     const int back = A.d.d_back ? __ldg(A.d.d_back + k) : 0;
     const float* pin = A.partials + (long long)(k & 1) * G * SC * ME;
     float* pout = A.partials + (long long)((k + 1) & 1) * G * SC * ME;
-    gather_partials(pin, G, SC * ME, SC * ME, sh_z1);
+    k1_stamp(A.stamp, 0, k, 0);
+    tiny_gates(A.fw, A.td, TP, T, t);   // independent of the partials: overlaps their round trip
+    gather_partials(pin, G, SC * ME, SC * ME, sh_z1, sh_red);
+    k1_stamp(A.stamp, 0, k, 1);
     if (blockIdx.x == 0) {
       for (int idx = threadIdx.x; idx < S * d1; idx += NTHREADS) {
         const int s = idx / d1, j = idx - s * d1;
@@ -225,42 +357,66 @@ __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
       }
     }
     // tiny MLP for the S samples (+ the stale vector as row SC when stl)
-    tiny_forward(A, T, sh_z1, A.d.stl ? SC + 1 : S, t);
+    tiny_forward(A, TP, T, sh_z1, A.d.stl ? SC + 1 : S);
     if (A.d.stl && threadIdx.x < ME) sh_hst[threadIdx.x] = threadIdx.x < dL ? T.h[SC * wsum + offL + threadIdx.x] : 0.f;
     __syncthreads();
+    k1_stamp(A.stamp, 0, k, 2);
 
     float acc[SC * ME];
 #pragma unroll
     for (int i = 0; i < SC * ME; ++i) acc[i] = 0.f;
-    for (long long p = gtid; p < P; p += NT) {
-      float w1[ME], w4[ME];
+    // last hidden activations of the samples: registers for the whole pass over P
+    float hL[SC][ME];
 #pragma unroll
-      for (int j = 0; j < ME; ++j) {
-        w1[j] = j < d1 ? __ldg(A.fw.W1 + p * d1 + j) : 0.f;
-        w4[j] = j < dL ? __ldg(A.fw.W4 + (long long)j * P + p) : 0.f;
+    for (int s = 0; s < SC; ++s)
+#pragma unroll
+      for (int j = 0; j < ME; ++j) hL[s][j] = (s < S && j < dL) ? T.h[s * wsum + offL + j] : 0.f;
+    int e = 0;
+    for (long long p = gtid; p < P; p += NT, ++e) {
+      float w1[ME], w4[ME], b4, bt4, s4, wsv = 0.f;
+      if (RES) {
+#pragma unroll
+        for (int j = 0; j < ME; ++j) { w1[j] = R(F_W1 + j, e); w4[j] = R(F_W4 + j, e); }
+        b4 = R(F_B4, e); bt4 = R(F_BT4, e);
+        s4 = A.fw.plain ? 1.f : sigmoidf_(R(F_WT4, e) * t + R(F_WTB4, e));
+        if (A.d.stl) wsv = R(FF_STALE, e);
+      } else {
+#pragma unroll
+        for (int j = 0; j < ME; ++j) {
+          w1[j] = j < d1 ? __ldg(A.fw.W1 + p * d1 + j) : 0.f;
+          w4[j] = j < dL ? __ldg(A.fw.W4 + (long long)j * P + p) : 0.f;
+        }
+        b4 = __ldg(A.fw.b4 + p); bt4 = A.fw.plain ? 0.f : __ldg(A.fw.bt4 + p);
+        s4 = A.fw.plain ? 1.f : sigmoidf_(__ldg(A.fw.wt4 + p) * t + __ldg(A.fw.wtb4 + p));
+        if (A.d.stl) wsv = __ldg(A.wstale + p);
       }
-      const float b4 = __ldg(A.fw.b4 + p), bt4 = A.fw.plain ? 0.f : __ldg(A.fw.bt4 + p);
-      const float s4 = A.fw.plain ? 1.f : sigmoidf_(__ldg(A.fw.wt4 + p) * t + __ldg(A.fw.wtb4 + p));
       float ust = 0.f;
       if (A.d.stl) {
         float pre = b4;
 #pragma unroll
         for (int j = 0; j < ME; ++j) pre = fmaf(sh_hst[j], w4[j], pre);
-        const float ws = __ldg(A.wstale + p);
-        ust = (pre * s4 + bt4 * t + (A.ou_coef + 1.f) * ws) * inv_sigma;
+        ust = (pre * s4 + bt4 * t + (A.ou_coef + 1.f) * wsv) * inv_sigma;
       }
+      float z4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int s = 0; s < SC; ++s) {
         if (s < S) {
-          const float w = A.wtraj[s * wstride + (long long)k * P + p];
+          const float w = RES ? R(FF_W + s, e) : A.wtraj[s * wstride + (long long)k * P + p];
           float pre = b4;
 #pragma unroll
-          for (int j = 0; j < ME; ++j) pre = fmaf(T.h[s * wsum + offL + (j < dL ? j : 0)], w4[j], pre);
+          for (int j = 0; j < ME; ++j) pre = fmaf(hL[s][j], w4[j], pre);
           const float mlp = pre * s4 + bt4 * t;
           const float dw = mlp + A.ou_coef * w;
           const float u = (mlp + (A.ou_coef + 1.f) * w) * inv_sigma;
-          const float dWv = A.dW ? __ldg(A.dW + ((long long)s * nit + k) * P + p)
-                                 : sq * philox_normal(A.d.seed, (uint32_t)p, nidx, (uint32_t)(s + A.s_base), A.d.stream_id);
+          float dWv;
+          if (A.dW) {
+            dWv = __ldg(A.dW + ((long long)s * nit + k) * P + p);
+          } else {
+            const uint32_t sl = (uint32_t)s + sph;   // position inside the global groups of four samples
+            if (s == 0 || (sl & 3u) == 0u) philox_normal4(A.d.seed, (uint32_t)p, nidx, sg0 + (sl >> 2), A.d.stream_id, z4);
+            const uint32_t zc = sl & 3u;
+            dWv = sq * (zc == 0u ? z4[0] : zc == 1u ? z4[1] : zc == 2u ? z4[2] : z4[3]);
+          }
           const float klinc = dtkl * A.d.kl_weight * u * u + ust * dWv;
           klacc[s] += klinc;
           if (A.d.d_kltraj) {   // optional: the kl rows of ys (sdeint.py:138), read-modify-write by the element's owner thread
@@ -273,21 +429,25 @@ __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
                          : back == 2 ? 0.5f * (A.wtraj[s * wstride + (long long)(k - 1) * P + p] + w) : w;
           const float wn = wb + dt * dw + sigma * dWv;
           A.wtraj[s * wstride + (long long)(k + 1) * P + p] = wn;
+          if (RES) R(FF_W + s, e) = wn;
 #pragma unroll
           for (int j = 0; j < ME; ++j) acc[s * ME + j] = fmaf(wn, w1[j], acc[s * ME + j]);
         }
       }
     }
+    k1_stamp(A.stamp, 0, k, 3);
     if (k + 1 < nit) {
       block_reduce_store<SC * ME>(acc, sh_red, pout + (long long)blockIdx.x * SC * ME, SC * ME);
+      k1_stamp(A.stamp, 0, k, 4);
       grid.sync();
+      k1_stamp(A.stamp, 0, k, 5);
     }
   }
   // ---- kl: block partials, then CTA 0 sums in order
   block_reduce_store<SC>(klacc, sh_red, A.klpart + (long long)blockIdx.x * SC, SC);
   grid.sync();
   if (blockIdx.x == 0) {
-    gather_partials(A.klpart, G, SC, SC, sh_z1);
+    gather_partials(A.klpart, G, SC, SC, sh_z1, sh_red);
     if (threadIdx.x < S) A.kl[threadIdx.x] = sh_z1[threadIdx.x];
   }
 }
@@ -295,6 +455,7 @@ __global__ void __launch_bounds__(NTHREADS) wsde_fwd_kernel(WsdeArgs A) {
 // =============================================================================================
 // reverse pass
 // =============================================================================================
+template <bool RES>
 __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ float smem[];
@@ -311,27 +472,79 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
   T.g = T.a + (SC + 1) * wsum;
   T.y = T.g + wsum;
   T.h = T.y + (SC + 1) * wsum;
-  float* sh_z1 = T.h + (SC + 1) * wsum;       // [(SC+1)][ME]
+  T.btt = T.h + (SC + 1) * wsum;
+  float* sh_z1 = T.btt + wsum;                // [(SC+1)][ME]
   float* sh_red = sh_z1 + (SC + 1) * ME;      // [NWARPS][SC*ME]
   float* sh_gh = sh_red + NWARPS * SC * ME;   // [SC][wsum]  dL/dh (then reused as dL/da)
   float* sh_dz1 = sh_gh + SC * wsum;          // [SC][ME]    pending dL/dz1 of iteration k+1
   float* sh_ghL = sh_dz1 + SC * ME;           // [SC][ME]
+  float* sh_stage = sh_ghL + SC * ME;         // [2 * tp_floats] staged tiny parameters, then CTA 0's tiny gradient accumulators
+  Slots R;
+  R.base = sh_stage + 2 * A.tp_floats + threadIdx.x;
+  R.ept = A.ept;
+  TinyPar TP;
+  tiny_par_init(A.fw, A.td, A.tp_floats ? sh_stage : nullptr, TP);
+  // tiny parameter gradients: only CTA 0 accumulates them (every CTA computes the same tiny reverse pass); staged: in shared
+  // memory across all iterations, written once in the epilogue -- else read-modify-write in global memory every iteration
+  TinyGrad TG;
+  {
+    float* q = sh_stage + A.tp_floats;
+    for (int l = 0; l < td.nhid; ++l) {
+      const int dd = td.dims[l];
+      float* gsrc[5] = {l == 0 ? A.gfw.b1 : A.gfw.bm[l - 1], l == 0 ? A.gfw.wt1 : A.gfw.wtm[l - 1], l == 0 ? A.gfw.wtb1 : A.gfw.wtbm[l - 1],
+                        l == 0 ? A.gfw.bt1 : A.gfw.btm[l - 1], l == 0 ? nullptr : A.gfw.Wm[l - 1]};
+      const int nW = l > 0 ? td.dims[l - 1] * dd : 0;
+      if (A.tp_floats) {
+        const bool acc0 = A.accumulate != 0;
+        for (int f = 0; f < 4; ++f)
+          for (int j = threadIdx.x; j < dd; j += NTHREADS) q[f * dd + j] = (acc0 && (f == 0 || !A.fw.plain)) ? gsrc[f][j] : 0.f;
+        for (int j = threadIdx.x; j < nW; j += NTHREADS) q[4 * dd + j] = acc0 ? gsrc[4][j] : 0.f;
+        TG.b[l] = q; TG.wt[l] = q + dd; TG.wtb[l] = q + 2 * dd; TG.bt[l] = q + 3 * dd; TG.W[l] = q + 4 * dd;
+        q += 4 * dd + nW;
+      } else {
+        TG.b[l] = gsrc[0]; TG.wt[l] = gsrc[1]; TG.wtb[l] = gsrc[2]; TG.bt[l] = gsrc[3]; TG.W[l] = gsrc[4];
+      }
+    }
+    __syncthreads();
+  }
 
   const float sigma = A.d.sigma, inv_sigma = inv_or_zero(sigma);
   const long long wstride = (long long)(nit + 1) * P;
   const bool acc_in = A.accumulate != 0;
 
-  // ---- prologue: zero the per-element gradient accumulators, seed lambda
-  for (long long p = gtid; p < P; p += NT) {
-    if (!acc_in) {
-      for (int j = 0; j < d1; ++j) A.gfw.W1[p * d1 + j] = 0.f;
-      for (int j = 0; j < dL; ++j) A.gfw.W4[(long long)j * P + p] = 0.f;
-      A.gfw.b4[p] = 0.f;
-      if (!A.fw.plain) { A.gfw.wt4[p] = 0.f; A.gfw.wtb4[p] = 0.f; A.gfw.bt4[p] = 0.f; }
+  // ---- prologue: zero the per-element gradient accumulators, seed lambda; RES: parameters / accumulators / lambda -> slots
+  {
+    int e = 0;
+    for (long long p = gtid; p < P; p += NT, ++e) {
+      if (RES) {
+#pragma unroll
+        for (int j = 0; j < ME; ++j) {
+          R(F_W1 + j, e) = j < d1 ? __ldg(A.fw.W1 + p * d1 + j) : 0.f;
+          R(F_W4 + j, e) = j < dL ? __ldg(A.fw.W4 + (long long)j * P + p) : 0.f;
+          R(FB_GW1 + j, e) = (acc_in && j < d1) ? A.gfw.W1[p * d1 + j] : 0.f;
+          R(FB_GW4 + j, e) = (acc_in && j < dL) ? A.gfw.W4[(long long)j * P + p] : 0.f;
+        }
+        R(F_B4, e) = __ldg(A.fw.b4 + p);
+        R(F_WT4, e) = A.fw.plain ? 0.f : __ldg(A.fw.wt4 + p);
+        R(F_WTB4, e) = A.fw.plain ? 0.f : __ldg(A.fw.wtb4 + p);
+        R(F_BT4, e) = A.fw.plain ? 0.f : __ldg(A.fw.bt4 + p);
+        R(FB_GB4 + 0, e) = acc_in ? A.gfw.b4[p] : 0.f;
+        R(FB_GB4 + 1, e) = (acc_in && !A.fw.plain) ? A.gfw.wt4[p] : 0.f;
+        R(FB_GB4 + 2, e) = (acc_in && !A.fw.plain) ? A.gfw.wtb4[p] : 0.f;
+        R(FB_GB4 + 3, e) = (acc_in && !A.fw.plain) ? A.gfw.bt4[p] : 0.f;
+        for (int s = 0; s < S; ++s) R(FB_LAM + s, e) = A.gwT ? __ldg(A.gwT + (long long)s * P + p) : 0.f;
+      } else {
+        if (!acc_in) {
+          for (int j = 0; j < d1; ++j) A.gfw.W1[p * d1 + j] = 0.f;
+          for (int j = 0; j < dL; ++j) A.gfw.W4[(long long)j * P + p] = 0.f;
+          A.gfw.b4[p] = 0.f;
+          if (!A.fw.plain) { A.gfw.wt4[p] = 0.f; A.gfw.wtb4[p] = 0.f; A.gfw.bt4[p] = 0.f; }
+        }
+        for (int s = 0; s < S; ++s) A.glam[(long long)s * P + p] = A.gwT ? __ldg(A.gwT + (long long)s * P + p) : 0.f;
+      }
     }
-    for (int s = 0; s < S; ++s) A.glam[(long long)s * P + p] = A.gwT ? __ldg(A.gwT + (long long)s * P + p) : 0.f;
   }
-  if (blockIdx.x == 0 && !acc_in) {
+  if (blockIdx.x == 0 && !acc_in && !A.tp_floats) {
     for (int j = threadIdx.x; j < d1; j += NTHREADS) {
       A.gfw.b1[j] = 0.f;
       if (!A.fw.plain) { A.gfw.wt1[j] = 0.f; A.gfw.wtb1[j] = 0.f; A.gfw.bt1[j] = 0.f; }
@@ -354,32 +567,59 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
     const float dtkl = A.d.d_dtkl ? __ldg(A.d.d_dtkl + k) : dt;
     const int back = A.d.d_back ? __ldg(A.d.d_back + k) : 0;                        // w_{k+1} starts from w_{k-back}
     const int hold_in = (A.d.d_back && k + 1 < nit) ? __ldg(A.d.d_back + k + 1) : 0;  // iteration k+1 started from w_k
+    k1_stamp(A.stamp, 1, k, 0);
+    // the next iteration's streamed operands (w_{k-1}, the x rows' dL/dw_{k-1}) -> L2 while this iteration computes: the pass over
+    // P is otherwise bound by the DRAM latency of these loads (8 warps per SM cannot hide it)
+    if (k > 0 && ((threadIdx.x & 31) == 0 || (threadIdx.x & 31) == 31)) {   // a warp's 32 consecutive floats span <= 2 lines
+      for (long long p = gtid; p < P; p += NT) {
+        for (int s2 = 0; s2 < S; ++s2) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(A.wtraj + s2 * wstride + (long long)(k - 1) * P + p));
+          if (A.gw_traj) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.gw_traj + ((long long)s2 * nit + (k - 1)) * P + p));
+        }
+      }
+    }
     // tiny forward of iteration k from the stored first-layer dots
     for (int idx = threadIdx.x; idx < SC * ME; idx += NTHREADS) {
       const int s = idx / ME, j = idx - s * ME;
       sh_z1[idx] = (s < S && j < d1) ? __ldg(A.z1 + ((long long)k * S + s) * d1 + j) : 0.f;
     }
+    tiny_gates(A.fw, A.td, TP, T, t);
     __syncthreads();
-    tiny_forward(A, T, sh_z1, S, t);
+    tiny_forward(A, TP, T, sh_z1, S);
+    k1_stamp(A.stamp, 1, k, 1);
 
     float part[SC * ME];
 #pragma unroll
     for (int i = 0; i < SC * ME; ++i) part[i] = 0.f;
-    for (long long p = gtid; p < P; p += NT) {
-      float w1[ME], w4[ME], gw1[ME], gw4[ME];
+    float hL[SC][ME];
 #pragma unroll
-      for (int j = 0; j < ME; ++j) {
-        w1[j] = j < d1 ? __ldg(A.fw.W1 + p * d1 + j) : 0.f;
-        w4[j] = j < dL ? __ldg(A.fw.W4 + (long long)j * P + p) : 0.f;
-        gw1[j] = 0.f; gw4[j] = 0.f;
+    for (int s = 0; s < SC; ++s)
+#pragma unroll
+      for (int j = 0; j < ME; ++j) hL[s][j] = (s < S && j < dL) ? T.h[s * wsum + offL + j] : 0.f;
+    int e = 0;
+    for (long long p = gtid; p < P; p += NT, ++e) {
+      float w1[ME], w4[ME], gw1[ME], gw4[ME];
+      float b4, bt4, s4;
+      if (RES) {
+#pragma unroll
+        for (int j = 0; j < ME; ++j) { w1[j] = R(F_W1 + j, e); w4[j] = R(F_W4 + j, e); gw1[j] = 0.f; gw4[j] = 0.f; }
+        b4 = R(F_B4, e); bt4 = R(F_BT4, e);
+        s4 = A.fw.plain ? 1.f : sigmoidf_(R(F_WT4, e) * t + R(F_WTB4, e));
+      } else {
+#pragma unroll
+        for (int j = 0; j < ME; ++j) {
+          w1[j] = j < d1 ? __ldg(A.fw.W1 + p * d1 + j) : 0.f;
+          w4[j] = j < dL ? __ldg(A.fw.W4 + (long long)j * P + p) : 0.f;
+          gw1[j] = 0.f; gw4[j] = 0.f;
+        }
+        b4 = __ldg(A.fw.b4 + p); bt4 = A.fw.plain ? 0.f : __ldg(A.fw.bt4 + p);
+        s4 = A.fw.plain ? 1.f : sigmoidf_(__ldg(A.fw.wt4 + p) * t + __ldg(A.fw.wtb4 + p));
       }
-      const float b4 = __ldg(A.fw.b4 + p), bt4 = A.fw.plain ? 0.f : __ldg(A.fw.bt4 + p);
-      const float s4 = A.fw.plain ? 1.f : sigmoidf_(__ldg(A.fw.wt4 + p) * t + __ldg(A.fw.wtb4 + p));
       float gb4 = 0.f, gwt4 = 0.f, gwtb4 = 0.f, gbt4 = 0.f;
 #pragma unroll
       for (int s = 0; s < SC; ++s) {
         if (s < S) {
-          float lam = A.glam[(long long)s * P + p];
+          float lam = RES ? R(FB_LAM + s, e) : A.glam[(long long)s * P + p];
           if (pending) {
             const float wn = __ldg(A.wtraj + s * wstride + (long long)(k + 1) * P + p);
 #pragma unroll
@@ -391,7 +631,7 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
           const float w = __ldg(A.wtraj + s * wstride + (long long)k * P + p);
           float pre = b4;
 #pragma unroll
-          for (int j = 0; j < ME; ++j) pre = fmaf(T.h[s * wsum + offL + (j < dL ? j : 0)], w4[j], pre);
+          for (int j = 0; j < ME; ++j) pre = fmaf(hL[s][j], w4[j], pre);
           const float mlp = pre * s4 + bt4 * t;
           const float u = (mlp + (A.ou_coef + 1.f) * w) * inv_sigma;
           const float gu = __ldg(A.gkl + s) * dtkl * A.d.kl_weight * 2.f * u * inv_sigma;  // dL/d(mlp) via kl
@@ -403,29 +643,39 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
           else if (back == 2) { A.ghold[(long long)s * P + p] = 0.5f * lam; gl += 0.5f * lam; }  // ... at (w_{k-1} + w_k)/2
           else gl += lam;
           if (hold_in) gl += A.ghold[(long long)s * P + p];
-          A.glam[(long long)s * P + p] = gl;
+          if (RES) R(FB_LAM + s, e) = gl; else A.glam[(long long)s * P + p] = gl;
           const float qs = q * s4;
 #pragma unroll
           for (int j = 0; j < ME; ++j) {
             part[s * ME + j] = fmaf(w4[j], qs, part[s * ME + j]);
-            gw4[j] = fmaf(T.h[s * wsum + offL + (j < dL ? j : 0)], qs, gw4[j]);
+            gw4[j] = fmaf(hL[s][j], qs, gw4[j]);
           }
           gb4 += qs;
-          const float e = q * pre * s4 * (1.f - s4);
-          gwt4 = fmaf(e, t, gwt4);
-          gwtb4 += e;
+          const float ee = q * pre * s4 * (1.f - s4);
+          gwt4 = fmaf(ee, t, gwt4);
+          gwtb4 += ee;
           gbt4 = fmaf(q, t, gbt4);
         }
       }
-      for (int j = 0; j < d1; ++j) if (pending) A.gfw.W1[p * d1 + j] += gw1[j];
-      for (int j = 0; j < dL; ++j) A.gfw.W4[(long long)j * P + p] += gw4[j];
-      A.gfw.b4[p] += gb4;
-      if (!A.fw.plain) { A.gfw.wt4[p] += gwt4; A.gfw.wtb4[p] += gwtb4; A.gfw.bt4[p] += gbt4; }
+      if (RES) {
+#pragma unroll
+        for (int j = 0; j < ME; ++j) { if (pending) R(FB_GW1 + j, e) += gw1[j]; R(FB_GW4 + j, e) += gw4[j]; }
+        R(FB_GB4 + 0, e) += gb4; R(FB_GB4 + 1, e) += gwt4; R(FB_GB4 + 2, e) += gwtb4; R(FB_GB4 + 3, e) += gbt4;
+      } else {
+        for (int j = 0; j < d1; ++j) if (pending) A.gfw.W1[p * d1 + j] += gw1[j];
+        for (int j = 0; j < dL; ++j) A.gfw.W4[(long long)j * P + p] += gw4[j];
+        A.gfw.b4[p] += gb4;
+        if (!A.fw.plain) { A.gfw.wt4[p] += gwt4; A.gfw.wtb4[p] += gwtb4; A.gfw.bt4[p] += gbt4; }
+      }
     }
+    k1_stamp(A.stamp, 1, k, 2);
     float* pout = A.partials + (long long)(k & 1) * G * SC * ME;
     block_reduce_store<SC * ME>(part, sh_red, pout + (long long)blockIdx.x * SC * ME, SC * ME);
+    k1_stamp(A.stamp, 1, k, 3);
     grid.sync();
-    gather_partials(pout, G, SC * ME, SC * ME, sh_ghL);
+    k1_stamp(A.stamp, 1, k, 4);
+    gather_partials(pout, G, SC * ME, SC * ME, sh_ghL, sh_red);
+    k1_stamp(A.stamp, 1, k, 5);
 
     // ---- tiny reverse: dL/dhL -> ... -> dL/dz1 ; CTA 0 accumulates the tiny parameter grads
     for (int idx = threadIdx.x; idx < SC * wsum; idx += NTHREADS) sh_gh[idx] = 0.f;
@@ -445,10 +695,10 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
       }
       __syncthreads();
       if (blockIdx.x == 0) {
-        float* gb = l == 0 ? A.gfw.b1 : A.gfw.bm[l - 1];
-        float* gwt = l == 0 ? A.gfw.wt1 : A.gfw.wtm[l - 1];
-        float* gwtb = l == 0 ? A.gfw.wtb1 : A.gfw.wtbm[l - 1];
-        float* gbt = l == 0 ? A.gfw.bt1 : A.gfw.btm[l - 1];
+        float* gb = TG.b[l];
+        float* gwt = TG.wt[l];
+        float* gwtb = TG.wtb[l];
+        float* gbt = TG.bt[l];
         for (int j = threadIdx.x; j < dout; j += NTHREADS) {
           const float g = T.g[oo + j];
           float sb = 0.f, se = 0.f, sy = 0.f;
@@ -463,7 +713,7 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
         }
         if (l > 0) {
           const int din = td.dims[l - 1], oi = td.off[l - 1];
-          float* gW = A.gfw.Wm[l - 1];
+          float* gW = TG.W[l];
           for (int idx = threadIdx.x; idx < din * dout; idx += NTHREADS) {
             const int qi = idx / dout, j = idx - qi * dout;
             float sw = 0.f;
@@ -474,12 +724,17 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
       }
       if (l > 0) {
         const int din = td.dims[l - 1], oi = td.off[l - 1];
-        const float* __restrict__ W = A.fw.Wm[l - 1];
+        const float* W = TP.W[l];
         for (int idx = threadIdx.x; idx < S * din; idx += NTHREADS) {
           const int s = idx / din, qi = idx - s * din;
-          float r = 0.f;
-          for (int j = 0; j < dout; ++j) r = fmaf(__ldg(W + qi * dout + j), sh_gh[s * wsum + oo + j] * T.g[oo + j], r);
-          sh_gh[s * wsum + oi + qi] = r;
+          float r0 = 0.f, r1 = 0.f;
+          int j = 0;
+          for (; j + 1 < dout; j += 2) {
+            r0 = fmaf(W[qi * dout + j], sh_gh[s * wsum + oo + j] * T.g[oo + j], r0);
+            r1 = fmaf(W[qi * dout + j + 1], sh_gh[s * wsum + oo + j + 1] * T.g[oo + j + 1], r1);
+          }
+          if (j < dout) r0 = fmaf(W[qi * dout + j], sh_gh[s * wsum + oo + j] * T.g[oo + j], r0);
+          sh_gh[s * wsum + oi + qi] = r0 + r1;
         }
       } else {
         for (int idx = threadIdx.x; idx < SC * ME; idx += NTHREADS) {
@@ -490,30 +745,55 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
       __syncthreads();
     }
     pending = true;
+    k1_stamp(A.stamp, 1, k, 6);
   }
 
-  // ---- epilogue: close lambda_0 with the first-layer term of iteration 0
-  for (long long p = gtid; p < P; p += NT) {
-    float w1[ME], gw1[ME];
+  // ---- epilogue: close lambda_0 with the first-layer term of iteration 0; RES: accumulators -> global, once
+  {
+    int e = 0;
+    for (long long p = gtid; p < P; p += NT, ++e) {
+      float w1[ME], gw1[ME];
 #pragma unroll
-    for (int j = 0; j < ME; ++j) { w1[j] = j < d1 ? __ldg(A.fw.W1 + p * d1 + j) : 0.f; gw1[j] = 0.f; }
-    float tot = 0.f;
+      for (int j = 0; j < ME; ++j) { w1[j] = j < d1 ? __ldg(A.fw.W1 + p * d1 + j) : 0.f; gw1[j] = 0.f; }
+      float tot = 0.f;
 #pragma unroll
-    for (int s = 0; s < SC; ++s) {
-      if (s < S) {
-        float lam = A.glam[(long long)s * P + p];
-        const float w = __ldg(A.wtraj + s * wstride + p);
+      for (int s = 0; s < SC; ++s) {
+        if (s < S) {
+          float lam = RES ? R(FB_LAM + s, e) : A.glam[(long long)s * P + p];
+          const float w = __ldg(A.wtraj + s * wstride + p);
 #pragma unroll
-        for (int j = 0; j < ME; ++j) {
-          lam = fmaf(w1[j], sh_dz1[s * ME + j], lam);
-          gw1[j] = fmaf(w, sh_dz1[s * ME + j], gw1[j]);
+          for (int j = 0; j < ME; ++j) {
+            lam = fmaf(w1[j], sh_dz1[s * ME + j], lam);
+            gw1[j] = fmaf(w, sh_dz1[s * ME + j], gw1[j]);
+          }
+          if (A.d.w0_per_sample) A.gw0[(long long)s * P + p] = lam;
+          tot += lam;
         }
-        if (A.d.w0_per_sample) A.gw0[(long long)s * P + p] = lam;
-        tot += lam;
       }
+      if (RES) {
+        for (int j = 0; j < d1; ++j) A.gfw.W1[p * d1 + j] = R(FB_GW1 + j, e) + gw1[j];
+        for (int j = 0; j < dL; ++j) A.gfw.W4[(long long)j * P + p] = R(FB_GW4 + j, e);
+        A.gfw.b4[p] = R(FB_GB4 + 0, e);
+        if (!A.fw.plain) { A.gfw.wt4[p] = R(FB_GB4 + 1, e); A.gfw.wtb4[p] = R(FB_GB4 + 2, e); A.gfw.bt4[p] = R(FB_GB4 + 3, e); }
+      } else {
+        for (int j = 0; j < d1; ++j) A.gfw.W1[p * d1 + j] += gw1[j];
+      }
+      if (!A.d.w0_per_sample) A.gw0[p] = acc_in ? A.gw0[p] + tot : tot;
     }
-    for (int j = 0; j < d1; ++j) A.gfw.W1[p * d1 + j] += gw1[j];
-    if (!A.d.w0_per_sample) A.gw0[p] = acc_in ? A.gw0[p] + tot : tot;
+  }
+  if (A.tp_floats && blockIdx.x == 0) {   // staged tiny gradient accumulators -> global, once
+    __syncthreads();
+    for (int l = 0; l < td.nhid; ++l) {
+      const int dd = td.dims[l];
+      float* gdst[5] = {l == 0 ? A.gfw.b1 : A.gfw.bm[l - 1], l == 0 ? A.gfw.wt1 : A.gfw.wtm[l - 1], l == 0 ? A.gfw.wtb1 : A.gfw.wtbm[l - 1],
+                        l == 0 ? A.gfw.bt1 : A.gfw.btm[l - 1], l == 0 ? nullptr : A.gfw.Wm[l - 1]};
+      for (int j = threadIdx.x; j < dd; j += NTHREADS) {
+        gdst[0][j] = TG.b[l][j];
+        if (!A.fw.plain) { gdst[1][j] = TG.wt[l][j]; gdst[2][j] = TG.wtb[l][j]; gdst[3][j] = TG.bt[l][j]; }
+      }
+      if (l > 0)
+        for (int j = threadIdx.x; j < td.dims[l - 1] * dd; j += NTHREADS) gdst[4][j] = TG.W[l][j];
+    }
   }
 }
 
@@ -540,24 +820,52 @@ static int fill_tiny(const bsde_fw_params* fw, TinyDims& td) {
   return 0;
 }
 
-static size_t smem_bytes(const TinyDims& td, bool bwd) {
-  size_t f = (size_t)(3 * (SC + 1) + 1) * td.wsum + (SC + 1) * ME + NWARPS * SC * ME + ME;
+static int staged_floats(const TinyDims& td) {
+  const int f = tiny_par_floats(td);
+  return f <= TP_MAX ? f : 0;
+}
+
+static size_t smem_bytes(const TinyDims& td, bool bwd, int ept = 0) {
+  size_t f = (size_t)(3 * (SC + 1) + 2) * td.wsum + (SC + 1) * ME + NWARPS * SC * ME + ME;
   if (bwd) f += (size_t)SC * td.wsum + 2 * SC * ME;
+  f += (size_t)(bwd ? 2 : 1) * staged_floats(td);
+  f += (size_t)(bwd ? FB_N : FF_N) * ept * NTHREADS;   // resident slots (RES instantiations)
   return f * sizeof(float);
 }
 
-static int grid_for(int P, bool bwd, size_t smem, int& G) {
+// Grid and resident-slot plan: the RES instantiation (one CTA per SM, ept = ceil(P / (G * NTHREADS)) <= MAXE elements per
+// thread held in shared memory for the whole launch) unless P is too large for that, then the streaming instantiation.
+static int grid_for(int P, bool bwd, const TinyDims& td, int& G, int& ept, size_t& smem) {
   std::lock_guard<std::mutex> lk(g_mu);
   int dev = 0;
   BSDE_CUDA_OK(cudaGetDevice(&dev));
   int& num_sms = g_num_sms[dev & 63];
   if (num_sms == 0) BSDE_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  static const int res_on = getenv("BSDE_K1_RES") ? atoi(getenv("BSDE_K1_RES")) : 1;
+  const int want = (P + NTHREADS - 1) / NTHREADS;
+  {
+    const int g = std::min(num_sms, want);
+    const int e = (int)(((long long)P + (long long)g * NTHREADS - 1) / ((long long)g * NTHREADS));
+    const size_t sm = smem_bytes(td, bwd, e);
+    if (res_on && e <= MAXE && sm <= 227 * 1024) {
+      static PerDeviceOnce once_f, once_b;
+      if (bwd ? once_b.first() : once_f.first()) {
+        if (bwd) BSDE_CUDA_OK(cudaFuncSetAttribute(wsde_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        else BSDE_CUDA_OK(cudaFuncSetAttribute(wsde_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      }
+      int occ = 0;
+      if (bwd) BSDE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsde_bwd_kernel<true>, NTHREADS, sm));
+      else BSDE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsde_fwd_kernel<true>, NTHREADS, sm));
+      if (occ >= 1) { G = g; ept = e; smem = sm; return 0; }
+    }
+  }
+  ept = 0;
+  smem = smem_bytes(td, bwd, 0);
   int occ = 0;
-  if (bwd) BSDE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsde_bwd_kernel, NTHREADS, smem));
-  else BSDE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsde_fwd_kernel, NTHREADS, smem));
+  if (bwd) BSDE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsde_bwd_kernel<false>, NTHREADS, smem));
+  else BSDE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wsde_fwd_kernel<false>, NTHREADS, smem));
   if (occ < 1) { set_error("wsde kernel does not fit on an SM (smem %zu)", smem); return BSDE_ERR_UNSUPPORTED; }
   if (occ > 2) occ = 2;
-  int want = (P + NTHREADS - 1) / NTHREADS;
   G = num_sms * occ;
   if (G > want) G = want;
   if (G < 1) G = 1;
@@ -604,10 +912,13 @@ extern "C" int bsde_wsde_fwd(const bsde_wsde_desc* d, const bsde_fw_params* fw, 
     set_error("wsde_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
     return BSDE_ERR_WORKSPACE;
   }
-  const size_t smem = smem_bytes(A.td, false);
-  int G = 0;
-  if (int e = grid_for(fw->P, false, smem, G)) return e;
+  size_t smem = 0;
+  int G = 0, ept = 0;
+  if (int e = grid_for(fw->P, false, A.td, G, ept, smem)) return e;
   if (G > MAXG) G = MAXG;
+  A.ept = ept;
+  A.tp_floats = staged_floats(A.td);
+  { static const int st_on = getenv("BSDE_K1_STAMP") ? atoi(getenv("BSDE_K1_STAMP")) : 0; A.stamp = st_on; }
   const int S = d->S, P = fw->P, nit = d->nit, d1 = fw->dims[0];
   for (int s0 = 0; s0 < S; s0 += SC) {
     const int sc = S - s0 < SC ? S - s0 : SC;
@@ -626,8 +937,8 @@ extern "C" int bsde_wsde_fwd(const bsde_wsde_desc* d, const bsde_fw_params* fw, 
     // z1 layout for chunked launches: chunk c occupies [nit][sc][d1] at offset s0*nit*d1
     A.z1 = d_z1 + (size_t)s0 * nit * d1;
     void* args[] = {&A};
-    BSDE_CUDA_OK(cudaLaunchCooperativeKernel((void*)wsde_fwd_kernel, dim3(G), dim3(NTHREADS), args, smem,
-                                             (cudaStream_t)stream));
+    BSDE_CUDA_OK(cudaLaunchCooperativeKernel(ept ? (void*)wsde_fwd_kernel<true> : (void*)wsde_fwd_kernel<false>, dim3(G), dim3(NTHREADS),
+                                             args, smem, (cudaStream_t)stream));
     count_launch();
   }
   return 0;
@@ -648,10 +959,13 @@ extern "C" int bsde_wsde_bwd(const bsde_wsde_desc* d, const bsde_fw_params* fw, 
     set_error("wsde_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
     return BSDE_ERR_WORKSPACE;
   }
-  const size_t smem = smem_bytes(A.td, true);
-  int G = 0;
-  if (int e = grid_for(fw->P, true, smem, G)) return e;
+  size_t smem = 0;
+  int G = 0, ept = 0;
+  if (int e = grid_for(fw->P, true, A.td, G, ept, smem)) return e;
   if (G > MAXG) G = MAXG;
+  A.ept = ept;
+  A.tp_floats = staged_floats(A.td);
+  { static const int st_on = getenv("BSDE_K1_STAMP") ? atoi(getenv("BSDE_K1_STAMP")) : 0; A.stamp = st_on; }
   const int S = d->S, P = fw->P, nit = d->nit, d1 = fw->dims[0];
   for (int s0 = 0; s0 < S; s0 += SC) {
     const int sc = S - s0 < SC ? S - s0 : SC;
@@ -671,10 +985,15 @@ extern "C" int bsde_wsde_bwd(const bsde_wsde_desc* d, const bsde_fw_params* fw, 
     A.glam = ws; ws += (size_t)sc * P;
     A.ghold = ws;
     void* args[] = {&A};
-    BSDE_CUDA_OK(cudaLaunchCooperativeKernel((void*)wsde_bwd_kernel, dim3(G), dim3(NTHREADS), args, smem,
-                                             (cudaStream_t)stream));
+    BSDE_CUDA_OK(cudaLaunchCooperativeKernel(ept ? (void*)wsde_bwd_kernel<true> : (void*)wsde_bwd_kernel<false>, dim3(G), dim3(NTHREADS),
+                                             args, smem, (cudaStream_t)stream));
     count_launch();
   }
   return 0;
 }
 
+// tools only: copy the phase stamps of the last stamped K1 launches to the host ([2][64][8] uint64, ns)
+extern "C" int bsde_debug_k1_stamps(unsigned long long* h_out) {
+  BSDE_CUDA_OK(cudaMemcpyFromSymbol(h_out, g_k1_stamps, sizeof(unsigned long long) * 2 * STAMP_IT * STAMP_PH));
+  return 0;
+}

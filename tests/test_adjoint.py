@@ -558,7 +558,7 @@ def test_gpu_block_adjoint_full_size_vs_backprop(built_lib):
     inc = torch.stack([tree(tn) - tree(t) for (t, h, tn) in steps]).reshape(len(steps), S, P).permute(1, 0, 2).contiguous()
     ts_sched = torch.tensor([float(steps[0][0])] + [float(s[2]) for s in steps])
     xo_b, kl_b, g_b, mem_b = run(lambda y0: sdeint_ito_fixed_grid(dyn.f_aug, dyn.g_aug, y0, ts_sched, inc, fw_params,
-                                                                 method="euler_maruyama", rep=0, time_grid="uniform"))
+                                                                 method="euler_maruyama", rep=0, time_grid="uniform", _layer_view=True))
     assert float((xo_a - xo_b).abs().max()) <= 1e-4 * float(xo_b.abs().max())
     assert torch.allclose(kl_a, kl_b, rtol=1e-4)
     bad = []

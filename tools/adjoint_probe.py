@@ -40,7 +40,7 @@ for sub in (1, 4):
     inc = torch.stack([tree(tn) - tree(t) for (t, h, tn) in steps]).reshape(len(steps), S, P).permute(1, 0, 2).contiguous()
     ts_sched = torch.tensor([float(steps[0][0])] + [float(s[2]) for s in steps])
     dynB = brax._AugDynamics(fx, fw.spec, x.shape, SIG, False, True, math, fx.init(0).to(dev), 0, remat=True)
-    xo_b, kl_b, g_b = run(lambda y0: sdeint_ito_fixed_grid(dynB.f_aug, dynB.g_aug, y0, ts_sched, inc, fw_params, method="euler_maruyama", rep=0, time_grid="uniform"), dynB)
+    xo_b, kl_b, g_b = run(lambda y0: sdeint_ito_fixed_grid(dynB.f_aug, dynB.g_aug, y0, ts_sched, inc, fw_params, method="euler_maruyama", rep=0, time_grid="uniform", _layer_view=True), dynB)
     rel = lambda a, b: float((a - b).norm() / b.norm())
     cos = lambda a, b: float(torch.dot(a.flatten().double(), b.flatten().double()) / (a.double().norm() * b.double().norm()))
     print(f"sub={sub} steps={len(steps)} fwd rel {rel(xo_a, xo_b):.2e} | x_T norm {float(xo_a.norm()):.3e} x0 norm {float(x.norm()):.3e} | rec x rel {rel(x0r, x.detach()):.3e} rec w rel {rel(w0r, w0.detach().expand(S, P)):.3e} | "

@@ -91,7 +91,7 @@ if "N1" in rows:
     for name, remat in (("checkpointing (activations kept)", False), ("checkpointing (remat: x_k kept, activations recomputed)", True)):
         dyn = brax._AugDynamics(fx, fw.spec, x.shape, 1e-3, False, True, "tc", fx.init(0).to(dev), 0, remat=remat)
         ms, mem = timed(lambda: run(lambda y0: sdeint_ito_fixed_grid(dyn.f_aug, dyn.g_aug, y0, ts_sched, inc, fw_params,
-                                                                     method="euler_maruyama", rep=0, time_grid="uniform")), a.reps)
+                                                                     method="euler_maruyama", rep=0, time_grid="uniform", _layer_view=True)), a.reps)
         print(json.dumps({"row": "N1", "what": f"config-4 group-0 block, {len(steps)} steps, fwd + reverse, {name}", "ms": ms,
                           "images_per_s": B / (ms * 1e-3), "peak_MiB": mem}), flush=True)
     dyn = brax._AugDynamics(fx, fw.spec, x.shape, 1e-3, False, True, "tc", fx.init(0).to(dev), 0)
