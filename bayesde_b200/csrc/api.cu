@@ -46,6 +46,14 @@ size_t tconv_win_img_floats(const bsde_conv_layer* L);
 int tconv_win_repack(const bsde_conv_layer* L, int S, int nit, const float* w, long long w_sample_stride, long long w_iter_stride,
                      int epi, float* img, cudaStream_t st);
 
+// taps-on-N path for small-cout stride-1 layers (csrc/tconv_tapn.cu)
+bool tconv_tapn_supported(const bsde_conv_layer* L, int S, int B, int epi);
+size_t tconv_tapn_img_floats(const bsde_conv_layer* L);
+int tconv_tapn_repack(const bsde_conv_layer* L, int S, int nit, const float* w, long long w_sample_stride, long long w_iter_stride,
+                      int epi, float* img, cudaStream_t st);
+int tconv_fwd_tapn(const bsde_conv_layer* L, int S, int B, const float* in, const float* w, long long w_sample_stride,
+                   float t, int act, int epi, float scale, const float* aux, float* out, void* ws, size_t ws_bytes,
+                   cudaStream_t st, const float* prepacked);
 bool tconv_wgrad_tc_supported(const bsde_conv_layer* L, int S, int B);
 size_t tconv_wgrad_ws_tc(const bsde_conv_layer* L, int S, int B);
 int tconv_wgrad_tc(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
@@ -77,6 +85,8 @@ static int conv_fwd(const bsde_conv_layer* L, int S, int B, const float* in, con
                     long long wss, float t, int act, int epi, float scale, const float* aux, float* out,
                     int math, void* tc_ws, size_t tc_ws_bytes, cudaStream_t st, const float* prepacked = nullptr,
                     int prepacked_safe = 0) {
+  if (math == BSDE_MATH_TC && tconv_tapn_supported(L, S, B, epi))
+    return tconv_fwd_tapn(L, S, B, in, w, wss, t, act, epi, scale, aux, out, tc_ws, tc_ws_bytes, st, prepacked);
   if (math == BSDE_MATH_TC && tconv_win_supported(L, S, B))
     return tconv_fwd_win(L, S, B, in, w, wss, t, act, epi, scale, aux, out, tc_ws, tc_ws_bytes, st, prepacked, prepacked_safe);
   if (math == BSDE_MATH_TC && tconv_tc_supported(L, epi))
@@ -106,6 +116,7 @@ static size_t conv_tc_ws(const bsde_conv_layer* L, int S) {
   size_t m = 0;
   if (tconv_tc_supported(L, 0)) m = std::max(m, tconv_tc_ws_bytes(L, S));
   m = std::max(m, tconv_win_ws_bytes(L, S));
+  m = std::max(m, tconv_tapn_img_floats(L) * sizeof(float) * S);
   return m;
 }
 
@@ -192,15 +203,31 @@ struct Prepack {
   size_t per_iter[2 * BSDE_MAX_LAYERS];  // floats per iteration (S * image)
 };
 
+// resident-image forms: the taps-on-N kernel where it applies (epilogue-dependent), else the window kernel
+static bool fast_form(const bsde_conv_layer* L, int S, int B, int epi) {
+  return tconv_tapn_supported(L, S, B, epi) || tconv_win_supported(L, S, B);
+}
+static size_t fast_img_floats(const bsde_conv_layer* L, int S, int B, int epi) {
+  return tconv_tapn_supported(L, S, B, epi) ? tconv_tapn_img_floats(L) : tconv_win_img_floats(L);
+}
+static int fast_repack(const bsde_conv_layer* L, int S, int B, int nit, const float* w, long long wss, long long wis, int epi, float* img,
+                       cudaStream_t st) {
+  if (tconv_tapn_supported(L, S, B, epi)) return tconv_tapn_repack(L, S, nit, w, wss, wis, epi, img, st);
+  return tconv_win_repack(L, S, nit, w, wss, wis, epi, img, st);
+}
+
 static size_t prepack_floats(const bsde_xpath_desc* d, int backward, bool need_fwd_forms) {
   if (d->math != BSDE_MATH_TC) return 0;
   size_t tot = 0;
-  for (int l = 0; l < d->nlayers; ++l) {
-    if (need_fwd_forms && tconv_win_supported(&d->layers[l], d->S, d->B))
-      tot += (size_t)d->nit * d->S * tconv_win_img_floats(&d->layers[l]);
+  const int n = d->nlayers;
+  for (int l = 0; l < n; ++l) {
+    const int epi_f = l == n - 1 ? BSDE_EPI_EULER : BSDE_EPI_BIAS_ACT;
+    if (need_fwd_forms && fast_form(&d->layers[l], d->S, d->B, epi_f))
+      tot += (size_t)d->nit * d->S * fast_img_floats(&d->layers[l], d->S, d->B, epi_f);
     if (backward) {
       bsde_conv_layer D = dgrad_layer(d->layers[l]);
-      if (tconv_win_supported(&D, d->S, d->B)) tot += (size_t)d->nit * d->S * tconv_win_img_floats(&D);
+      const int epi_b = l == 0 ? BSDE_EPI_ACCUM : BSDE_EPI_DACT;
+      if (fast_form(&D, d->S, d->B, epi_b)) tot += (size_t)d->nit * d->S * fast_img_floats(&D, d->S, d->B, epi_b);
     }
   }
   return tot;
@@ -213,17 +240,18 @@ static int prepack_all(const bsde_xpath_desc* d, int backward, bool need_fwd_for
   const int n = d->nlayers;
   const long long wss = (long long)(d->nit + 1) * d->P;
   for (int l = 0; l < n; ++l) {
-    if (need_fwd_forms && tconv_win_supported(&d->layers[l], d->S, d->B)) {
-      const int epi = l == n - 1 ? BSDE_EPI_EULER : BSDE_EPI_BIAS_ACT;
-      pp.img[l] = buf; pp.per_iter[l] = (size_t)d->S * tconv_win_img_floats(&d->layers[l]);
-      if (int e = tconv_win_repack(&d->layers[l], d->S, d->nit, d_wtraj, wss, d->P, epi, buf, st)) return e;
+    const int epi_f = l == n - 1 ? BSDE_EPI_EULER : BSDE_EPI_BIAS_ACT;
+    if (need_fwd_forms && fast_form(&d->layers[l], d->S, d->B, epi_f)) {
+      pp.img[l] = buf; pp.per_iter[l] = (size_t)d->S * fast_img_floats(&d->layers[l], d->S, d->B, epi_f);
+      if (int e = fast_repack(&d->layers[l], d->S, d->B, d->nit, d_wtraj, wss, d->P, epi_f, buf, st)) return e;
       buf += (size_t)d->nit * pp.per_iter[l];
     }
     if (backward) {
       bsde_conv_layer D = dgrad_layer(d->layers[l]);
-      if (tconv_win_supported(&D, d->S, d->B)) {
-        pp.img[n + l] = buf; pp.per_iter[n + l] = (size_t)d->S * tconv_win_img_floats(&D);
-        if (int e = tconv_win_repack(&D, d->S, d->nit, d_wtraj, wss, d->P, BSDE_EPI_DACT, buf, st)) return e;
+      const int epi_b = l == 0 ? BSDE_EPI_ACCUM : BSDE_EPI_DACT;
+      if (fast_form(&D, d->S, d->B, epi_b)) {
+        pp.img[n + l] = buf; pp.per_iter[n + l] = (size_t)d->S * fast_img_floats(&D, d->S, d->B, epi_b);
+        if (int e = fast_repack(&D, d->S, d->B, d->nit, d_wtraj, wss, d->P, epi_b, buf, st)) return e;
         buf += (size_t)d->nit * pp.per_iter[n + l];
       }
     }

@@ -19,6 +19,8 @@ p.add_argument("--groups", default="0,1,2")
 p.add_argument("--reps", type=int, default=10)
 p.add_argument("--warm", type=int, default=3)
 p.add_argument("--no_wgrad", action="store_true")
+p.add_argument("--epi_bias", action="store_true", help="EPI_BIAS for the forward geometry too (the taps-on-N path serves BIAS / EULER / ACCUM)")
+p.add_argument("--layers", default="", help="comma list of layer indices (default all)")
 a = p.parse_args()
 L = _lib.lib()
 dev = "cuda:0"
@@ -43,12 +45,14 @@ for g in [int(v) for v in a.groups.split(",")]:
     fx = FxSpec(0, (1, H, H, Cc), 64, "softplus")
     w = torch.randn(a.S, fx.P, device=dev) * 0.05
     for li, cs in enumerate(fx.conv_layer_structs()):
+        if a.layers and str(li) not in a.layers.split(","):
+            continue
         for kind, lay in (("fwd", cs), ("dgrad", dgrad_of(cs))):
             x = torch.randn(a.S, a.B, lay.hin, lay.win, lay.cin, device=dev)
             out = torch.empty(a.S, a.B, lay.hout, lay.wout, lay.cout, device=dev)
             nb = L.bsde_tconv_fwd_workspace_bytes(C.byref(lay), a.S, math)
             ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
-            epi = _lib.EPI_BIAS_ACT if kind == "fwd" else _lib.EPI_BIAS
+            epi = _lib.EPI_BIAS_ACT if (kind == "fwd" and not a.epi_bias) else _lib.EPI_BIAS
 
             def run():
                 st = L.bsde_tconv_fwd(C.byref(lay), a.S, a.B, _lib.ptr(x), _lib.ptr(w), fx.P, 0.3, 0, epi, 1.0, None,
