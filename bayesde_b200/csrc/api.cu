@@ -65,8 +65,15 @@ size_t tconv_wgrad_ws_win(const bsde_conv_layer* L, int S, int B);
 int tconv_wgrad_win(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
                     float* gw, long long gw_sample_stride, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// thin layers (64 <-> <= 7 channels, stride-1 3x3): taps on the N side (csrc/wgrad_thin.cu)
+bool tconv_wgrad_thin_supported(const bsde_conv_layer* L, int S, int B);
+size_t tconv_wgrad_ws_thin(const bsde_conv_layer* L, int S, int B);
+int tconv_wgrad_thin(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
+                     float* gw, long long gw_sample_stride, void* ws, size_t ws_bytes, cudaStream_t st);
+
 static size_t wgrad_ws(const bsde_conv_layer* L, int S, int B, int math) {
   size_t b = tconv_wgrad_ws_simt(L, S, B);
+  if (math == BSDE_MATH_TC && tconv_wgrad_thin_supported(L, S, B)) b = std::max(b, tconv_wgrad_ws_thin(L, S, B));
   if (math == BSDE_MATH_TC) b = std::max(b, tconv_wgrad_ws_win(L, S, B));
   if (math == BSDE_MATH_TC && tconv_wgrad_tc_supported(L, S, B)) b = std::max(b, tconv_wgrad_ws_tc(L, S, B));
   return b;
@@ -74,6 +81,8 @@ static size_t wgrad_ws(const bsde_conv_layer* L, int S, int B, int math) {
 
 static int conv_wgrad(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
                       float* gw, long long gss, int math, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (math == BSDE_MATH_TC && tconv_wgrad_thin_supported(L, S, B))
+    return tconv_wgrad_thin(L, S, B, in, dy, t, scale, gw, gss, ws, ws_bytes, st);
   if (math == BSDE_MATH_TC && tconv_wgrad_win_supported(L, S, B))
     return tconv_wgrad_win(L, S, B, in, dy, t, scale, gw, gss, ws, ws_bytes, st);
   if (math == BSDE_MATH_TC && tconv_wgrad_tc_supported(L, S, B))
