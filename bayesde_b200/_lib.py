@@ -14,7 +14,7 @@ FW_MAX_EDGE = 4
 FW_MAX_HID = 256
 MAX_LAYERS = 4
 
-ACT = {"softplus": 0, "tanh": 1, "elu": 2, "none": 3, "rbf": 4}
+ACT = {"softplus": 0, "tanh": 1, "elu": 2, "none": 3, "rbf": 4, "swish": 5}
 METHOD = {"euler_maruyama": 0, "milstein": 1, "euler_heun": 2}
 MATH = {"fp32": 0, "tc": 1}
 EPI_BIAS, EPI_BIAS_ACT, EPI_EULER, EPI_DACT, EPI_ACCUM = range(5)
@@ -26,7 +26,8 @@ class FwParams(C.Structure):
     _fields_ = ([("P", C.c_int32), ("nhid", C.c_int32), ("dims", C.c_int32 * (FW_MAX_MID + 2)), ("act", C.c_int32)]
                 + [(n, C.c_void_p) for n in ("W1", "b1", "wt1", "wtb1", "bt1")]
                 + [(n, C.c_void_p * FW_MAX_MID) for n in ("Wm", "bm", "wtm", "wtbm", "btm")]
-                + [(n, C.c_void_p) for n in ("W4", "b4", "wt4", "wtb4", "bt4")] + [("plain", C.c_int32)])
+                + [(n, C.c_void_p) for n in ("W4", "b4", "wt4", "wtb4", "bt4")]
+                + [("beta1", C.c_void_p), ("betam", C.c_void_p * FW_MAX_MID), ("plain", C.c_int32)])
 
 
 class WsdeDesc(C.Structure):
@@ -49,7 +50,7 @@ class ConvLayer(C.Structure):
 class XpathDesc(C.Structure):
     _fields_ = [("S", C.c_int32), ("B", C.c_int32), ("nit", C.c_int32), ("nlayers", C.c_int32),
                 ("act", C.c_int32), ("math", C.c_int32), ("P", C.c_int64), ("x_numel", C.c_int64),
-                ("layers", ConvLayer * MAX_LAYERS)]
+                ("layers", ConvLayer * MAX_LAYERS), ("beta_off", C.c_int64 * MAX_LAYERS)]
 
 
 class ToyDesc(C.Structure):

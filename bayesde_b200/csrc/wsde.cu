@@ -132,14 +132,35 @@ constexpr int TP_MAX = 6144;              // floats of tiny parameters staged in
 // b, w_t, w_tb, b_t of hidden layer l (dims[l] each) and, for l >= 1, W [dims[l-1]][dims[l]]: shared-memory copies or the originals
 struct TinyPar {
   const float* b[TL]; const float* wt[TL]; const float* wtb[TL]; const float* bt[TL]; const float* W[TL];
+  const float* beta[TL];   // trainable swish (arch.py:14-29): beta of the activation after hidden layer l, else unused
 };
 struct TinyGrad {
-  float* b[TL]; float* wt[TL]; float* wtb[TL]; float* bt[TL]; float* W[TL];
+  float* b[TL]; float* wt[TL]; float* wtb[TL]; float* bt[TL]; float* W[TL]; float* beta[TL];
 };
+// five vectors per hidden layer (b, w_t, w_tb, b_t, beta) + the middle matrices
 __host__ __device__ inline int tiny_par_floats(const TinyDims& td) {
   int f = 0;
-  for (int l = 0; l < td.nhid; ++l) f += 4 * td.dims[l] + (l > 0 ? td.dims[l - 1] * td.dims[l] : 0);
+  for (int l = 0; l < td.nhid; ++l) f += 5 * td.dims[l] + (l > 0 ? td.dims[l - 1] * td.dims[l] : 0);
   return f;
+}
+// activation of a hidden unit and its derivative in the pre-activation (swish: per-unit beta)
+__device__ __forceinline__ float tiny_act(int act, float y, float beta) {
+  if (act == BSDE_ACT_SWISH) return y * sigmoidf_(y * (fmaxf(beta, 0.f) + log1pf(expf(-fabsf(beta)))));
+  return act_fwd(act, y);
+}
+__device__ __forceinline__ float tiny_act_grad(int act, float y, float beta) {
+  if (act == BSDE_ACT_SWISH) {
+    const float g = fmaxf(beta, 0.f) + log1pf(expf(-fabsf(beta)));
+    const float sg = sigmoidf_(y * g);
+    return sg + y * g * sg * (1.f - sg);
+  }
+  return act_grad(act, y);
+}
+// d act / d beta of the trainable swish: y^2 sig (1 - sig) sigmoid(beta)
+__device__ __forceinline__ float tiny_act_dbeta(float y, float beta) {
+  const float g = fmaxf(beta, 0.f) + log1pf(expf(-fabsf(beta)));
+  const float sg = sigmoidf_(y * g);
+  return y * y * sg * (1.f - sg) * sigmoidf_(beta);
 }
 __device__ __forceinline__ void tiny_par_init(const bsde_fw_params& fw, const TinyDims& td, float* stage, TinyPar& TP) {
   for (int l = 0; l < td.nhid; ++l) {
@@ -148,16 +169,18 @@ __device__ __forceinline__ void tiny_par_init(const bsde_fw_params& fw, const Ti
     TP.wtb[l] = l == 0 ? fw.wtb1 : fw.wtbm[l - 1];
     TP.bt[l] = l == 0 ? fw.bt1 : fw.btm[l - 1];
     TP.W[l] = l == 0 ? nullptr : fw.Wm[l - 1];
+    TP.beta[l] = l == 0 ? fw.beta1 : fw.betam[l - 1];
   }
   if (!stage) return;
   float* q = stage;
   for (int l = 0; l < td.nhid; ++l) {
     const int d = td.dims[l];
-    const float* src[4] = {TP.b[l], TP.wt[l], TP.wtb[l], TP.bt[l]};
-    for (int f = 0; f < 4; ++f) {
-      if (f == 0 || !fw.plain)
+    const float* src[5] = {TP.b[l], TP.wt[l], TP.wtb[l], TP.bt[l], TP.beta[l]};
+    for (int f = 0; f < 5; ++f) {
+      const bool used = f == 0 || (f < 4 && !fw.plain) || (f == 4 && fw.act == BSDE_ACT_SWISH);
+      if (used)
         for (int j = threadIdx.x; j < d; j += NTHREADS) q[j] = __ldg(src[f] + j);
-      if (f == 0) TP.b[l] = q; else if (f == 1) TP.wt[l] = q; else if (f == 2) TP.wtb[l] = q; else TP.bt[l] = q;
+      if (f == 0) TP.b[l] = q; else if (f == 1) TP.wt[l] = q; else if (f == 2) TP.wtb[l] = q; else if (f == 3) TP.bt[l] = q; else TP.beta[l] = q;
       q += d;
     }
     if (l > 0) {
@@ -195,7 +218,7 @@ __device__ __forceinline__ void tiny_forward(const WsdeArgs& A, const TinyPar& T
       const float y = a * T.g[j] + T.btt[j];
       T.a[s * wsum + j] = a;
       T.y[s * wsum + j] = y;
-      T.h[s * wsum + j] = act_fwd(A.fw.act, y);
+      T.h[s * wsum + j] = tiny_act(A.fw.act, y, A.fw.act == BSDE_ACT_SWISH ? TP.beta[0][j] : 0.f);
     }
     __syncthreads();
   }
@@ -216,7 +239,7 @@ __device__ __forceinline__ void tiny_forward(const WsdeArgs& A, const TinyPar& T
       const float y = a * T.g[oo + j] + T.btt[oo + j];
       T.a[s * wsum + oo + j] = a;
       T.y[s * wsum + oo + j] = y;
-      T.h[s * wsum + oo + j] = act_fwd(A.fw.act, y);
+      T.h[s * wsum + oo + j] = tiny_act(A.fw.act, y, A.fw.act == BSDE_ACT_SWISH ? TP.beta[l + 1][j] : 0.f);
     }
     __syncthreads();
   }
@@ -491,18 +514,21 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
     float* q = sh_stage + A.tp_floats;
     for (int l = 0; l < td.nhid; ++l) {
       const int dd = td.dims[l];
-      float* gsrc[5] = {l == 0 ? A.gfw.b1 : A.gfw.bm[l - 1], l == 0 ? A.gfw.wt1 : A.gfw.wtm[l - 1], l == 0 ? A.gfw.wtb1 : A.gfw.wtbm[l - 1],
-                        l == 0 ? A.gfw.bt1 : A.gfw.btm[l - 1], l == 0 ? nullptr : A.gfw.Wm[l - 1]};
+      float* gsrc[6] = {l == 0 ? A.gfw.b1 : A.gfw.bm[l - 1], l == 0 ? A.gfw.wt1 : A.gfw.wtm[l - 1], l == 0 ? A.gfw.wtb1 : A.gfw.wtbm[l - 1],
+                        l == 0 ? A.gfw.bt1 : A.gfw.btm[l - 1], l == 0 ? A.gfw.beta1 : A.gfw.betam[l - 1], l == 0 ? nullptr : A.gfw.Wm[l - 1]};
       const int nW = l > 0 ? td.dims[l - 1] * dd : 0;
+      const bool sw = A.fw.act == BSDE_ACT_SWISH;
       if (A.tp_floats) {
         const bool acc0 = A.accumulate != 0;
-        for (int f = 0; f < 4; ++f)
-          for (int j = threadIdx.x; j < dd; j += NTHREADS) q[f * dd + j] = (acc0 && (f == 0 || !A.fw.plain)) ? gsrc[f][j] : 0.f;
-        for (int j = threadIdx.x; j < nW; j += NTHREADS) q[4 * dd + j] = acc0 ? gsrc[4][j] : 0.f;
-        TG.b[l] = q; TG.wt[l] = q + dd; TG.wtb[l] = q + 2 * dd; TG.bt[l] = q + 3 * dd; TG.W[l] = q + 4 * dd;
-        q += 4 * dd + nW;
+        for (int f = 0; f < 5; ++f) {
+          const bool used = f == 0 || (f < 4 && !A.fw.plain) || (f == 4 && sw);
+          for (int j = threadIdx.x; j < dd; j += NTHREADS) q[f * dd + j] = (acc0 && used) ? gsrc[f][j] : 0.f;
+        }
+        for (int j = threadIdx.x; j < nW; j += NTHREADS) q[5 * dd + j] = acc0 ? gsrc[5][j] : 0.f;
+        TG.b[l] = q; TG.wt[l] = q + dd; TG.wtb[l] = q + 2 * dd; TG.bt[l] = q + 3 * dd; TG.beta[l] = q + 4 * dd; TG.W[l] = q + 5 * dd;
+        q += 5 * dd + nW;
       } else {
-        TG.b[l] = gsrc[0]; TG.wt[l] = gsrc[1]; TG.wtb[l] = gsrc[2]; TG.bt[l] = gsrc[3]; TG.W[l] = gsrc[4];
+        TG.b[l] = gsrc[0]; TG.wt[l] = gsrc[1]; TG.wtb[l] = gsrc[2]; TG.bt[l] = gsrc[3]; TG.beta[l] = gsrc[4]; TG.W[l] = gsrc[5];
       }
     }
     __syncthreads();
@@ -548,6 +574,7 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
     for (int j = threadIdx.x; j < d1; j += NTHREADS) {
       A.gfw.b1[j] = 0.f;
       if (!A.fw.plain) { A.gfw.wt1[j] = 0.f; A.gfw.wtb1[j] = 0.f; A.gfw.bt1[j] = 0.f; }
+      if (A.fw.act == BSDE_ACT_SWISH) A.gfw.beta1[j] = 0.f;
     }
     for (int l = 0; l + 1 < td.nhid; ++l) {
       const int din = td.dims[l], dout = td.dims[l + 1];
@@ -555,6 +582,7 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
       for (int j = threadIdx.x; j < dout; j += NTHREADS) {
         A.gfw.bm[l][j] = 0.f;
         if (!A.fw.plain) { A.gfw.wtm[l][j] = 0.f; A.gfw.wtbm[l][j] = 0.f; A.gfw.btm[l][j] = 0.f; }
+        if (A.fw.act == BSDE_ACT_SWISH) A.gfw.betam[l][j] = 0.f;
       }
     }
   }
@@ -690,7 +718,11 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
       // gh -> ga (in place), and the gate / shift parameter grads
       for (int idx = threadIdx.x; idx < S * dout; idx += NTHREADS) {
         const int s = idx / dout, j = idx - s * dout;
-        const float gy = sh_gh[s * wsum + oo + j] * act_grad(A.fw.act, T.y[s * wsum + oo + j]);
+        const float bj = A.fw.act == BSDE_ACT_SWISH ? TP.beta[l][j] : 0.f;
+        const float gh = sh_gh[s * wsum + oo + j];
+        const float gy = gh * tiny_act_grad(A.fw.act, T.y[s * wsum + oo + j], bj);
+        // trainable swish: dL/dbeta needs dL/dh, which gy overwrites -> stash it in the (now free) activation slot
+        if (A.fw.act == BSDE_ACT_SWISH) T.h[s * wsum + oo + j] = gh * tiny_act_dbeta(T.y[s * wsum + oo + j], bj);
         sh_gh[s * wsum + oo + j] = gy;  // keep gy for the parameter grads below
       }
       __syncthreads();
@@ -710,6 +742,11 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
           }
           gb[j] += sb;
           if (!A.fw.plain) { gwt[j] += se * t; gwtb[j] += se; gbt[j] += sy * t; }
+          if (A.fw.act == BSDE_ACT_SWISH) {
+            float sbeta = 0.f;
+            for (int s = 0; s < S; ++s) sbeta += T.h[s * wsum + oo + j];
+            TG.beta[l][j] += sbeta;
+          }
         }
         if (l > 0) {
           const int din = td.dims[l - 1], oi = td.off[l - 1];
@@ -787,9 +824,11 @@ __global__ void __launch_bounds__(NTHREADS) wsde_bwd_kernel(WsdeArgs A) {
       const int dd = td.dims[l];
       float* gdst[5] = {l == 0 ? A.gfw.b1 : A.gfw.bm[l - 1], l == 0 ? A.gfw.wt1 : A.gfw.wtm[l - 1], l == 0 ? A.gfw.wtb1 : A.gfw.wtbm[l - 1],
                         l == 0 ? A.gfw.bt1 : A.gfw.btm[l - 1], l == 0 ? nullptr : A.gfw.Wm[l - 1]};
+      float* gbeta = l == 0 ? A.gfw.beta1 : A.gfw.betam[l - 1];
       for (int j = threadIdx.x; j < dd; j += NTHREADS) {
         gdst[0][j] = TG.b[l][j];
         if (!A.fw.plain) { gdst[1][j] = TG.wt[l][j]; gdst[2][j] = TG.wtb[l][j]; gdst[3][j] = TG.bt[l][j]; }
+        if (A.fw.act == BSDE_ACT_SWISH) gbeta[j] = TG.beta[l][j];
       }
       if (l > 0)
         for (int j = threadIdx.x; j < td.dims[l - 1] * dd; j += NTHREADS) gdst[4][j] = TG.W[l][j];
@@ -816,7 +855,11 @@ static int fill_tiny(const bsde_fw_params* fw, TinyDims& td) {
   td.wsum = off;
   BSDE_CHECK_ARG(fw->dims[0] <= ME && fw->dims[fw->nhid - 1] <= ME,
                  "first/last hidden widths must be <= %d (got %d, %d)", ME, fw->dims[0], fw->dims[fw->nhid - 1]);
-  BSDE_CHECK_ARG(fw->act >= BSDE_ACT_SOFTPLUS && fw->act <= BSDE_ACT_RBF, "bad fw activation %d", fw->act);
+  BSDE_CHECK_ARG(fw->act >= BSDE_ACT_SOFTPLUS && fw->act <= BSDE_ACT_SWISH && fw->act != BSDE_ACT_NONE, "bad fw activation %d", fw->act);
+  if (fw->act == BSDE_ACT_SWISH) {
+    BSDE_CHECK_ARG(fw->beta1 != nullptr, "swish f_w needs beta1");
+    for (int i = 0; i + 1 < fw->nhid; ++i) BSDE_CHECK_ARG(fw->betam[i] != nullptr, "swish f_w needs betam[%d]", i);
+  }
   return 0;
 }
 

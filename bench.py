@@ -48,6 +48,9 @@ def parse():
     p.add_argument("--cpu_batch", type=int, default=32, help="images in the bounded CPU sample (SURVEY 8.4: B = 32)")
     p.add_argument("--no_fp32_leg", action="store_true", help="skip the fp32-class (CUDA-core conv) throughput leg")
     p.add_argument("--no_cpu_baseline", action="store_true")
+    p.add_argument("--config", type=int, default=4, choices=[4, 5],
+                   help="4: the north-star JAX-front-end SDEBNN classifier (default); 5: BASELINE configs[4], the torchbnn SDENet "
+                        "(3x32x32, blocks 2-2-2, hidden 32, w-net 1-128-1, midpoint dt 0.05, inhomogeneous) with the batch sharded over ranks")
     return p.parse_args()
 
 
@@ -534,9 +537,142 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_config5(args):
+    """BASELINE configs[4]: torchbnn SDENet training step (examples/torch/sdebnn_classification.py:34-46: cross-entropy +
+    kl_coeff * logqp, Adam) at `--batch` images per GPU, midpoint dt 0.05 (20 steps, 40 evaluations of the 26-conv y_net),
+    batch sharded over ranks: every rank integrates the SAME weight path (same Philox key, counter-based) on its own images;
+    the one collective is the gradient all-reduce, here torch's DistributedDataParallel (bucketed, overlapped with backward)."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from bayesde_b200 import _lib, torch_models as tm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus N>1 must be launched with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    torch.manual_seed(0)
+    hidden = 32
+    model = tm.SDENet(input_size=(3, 32, 32), blocks=(2, 2, 2), weight_network_sizes=(1, 128, 1), hidden_width=hidden, sigma=0.1,
+                      inhomogeneous=True, math="tc" if args.math != "fp32" else "fp32", remat=args.remat or args.batch > 256).to(dev)
+    with torch.no_grad():   # SURVEY 8.4: N(0, 1e-2) on the zero-initialised last w-net layer, else the w drift is trivially -w
+        last = model.w_net.linears()[-1]
+        last.weight.normal_(0, 1e-2), last.bias.normal_(0, 1e-2)
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    B = args.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_host = 4
+    host_x = [torch.randn(B, 3, 32, 32, generator=g).pin_memory() for _ in range(n_host)]
+    host_y = [torch.randint(0, 10, (B,), generator=g).pin_memory() for _ in range(n_host)]
+    dev_x = [t.to(dev) for t in host_x]
+    dev_y = [t.to(dev) for t in host_y]
+    last_loss = {}
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        logits, logqp = net(x, dt=0.05, method="midpoint")
+        loss = F.cross_entropy(logits, y) + 1e-4 * logqp
+        loss.backward()
+        opt.step()
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    def step_resident(i):
+        last_loss["dev"] = step(dev_x[i % n_host], dev_y[i % n_host])
+
+    def step_e2e(i):
+        x = host_x[i % n_host].to(dev, non_blocking=True)
+        y = host_y[i % n_host].to(dev, non_blocking=True)
+        last_loss["e2e"] = step(x, y).item()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = L.bsde_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = L.bsde_launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    tf32_peak = measure_tf32_peak(dev)
+    flops_eval = sum(2 * (l["hout"] * l["wout"] if not l["transpose"] else l["hin"] * l["win"]) * 9 * (l["cin"] + 1) * l["cout"]
+                     for l in model.y_net.layers)
+    alg = 3.0 * flops_eval * 40 * B     # fwd + dgrad + wgrad of 40 drift evaluations, per rank
+    images = B * world * args.steps
+    achieved = alg / (ms / args.steps * 1e-3) / 1e12
+    loss_v = float(last_loss["dev"])
+    line = {"metric": "SDENet (torchbnn) train images/s (3x32x32, midpoint dt 0.05)", "value": images / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (tcgen05 kind::tf32 operands, f32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"config5: torchbnn SDENet 3x32x32, blocks 2-2-2, hidden {hidden}, w-net 1-128-1, sigma 0.1, midpoint "
+                                   f"dt 0.05 (40 drift evaluations), inhomogeneous, P = {model.params_size}",
+                       "batch_per_gpu": B, "remat": bool(model.remat), "parallelism": f"dp{world} (batch sharded, DistributedDataParallel)",
+                       "l2_policy": "per-step working set exceeds the 126 MB L2; no flush"},
+            "e2e": {"value": images / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * (3 * 32 * 32 * 4 + 8), "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "loss": {"last_timed_step": loss_v, "last_e2e_step": last_loss.get("e2e"), "finite": loss_v == loss_v and abs(loss_v) != float("inf")},
+            "roofline": {"bound": "tensor", "kernel": "the y_net conv chain (bsde_chain_fwd / bsde_chain_bwd launches) -- against the WHOLE step time",
+                         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+                         "peak_source": "measured live in this run: cuBLAS 8192^3 TF32 matmul", "traffic": None,
+                         "algorithmic_flops_per_step": alg, "flops_per_image_eval": flops_eval}}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v5, cores5, sample5 = cpu_torch_reference_images_per_s(8)
+            line["cpu_baseline"] = {"value": v5, "unit": UNIT, "cores": cores5, "kind": "port", "sample": sample5}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"unavailable": repr(e)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.config == 5:
+        run_config5(a)
     else:
         run_ours(a)

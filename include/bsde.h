@@ -62,7 +62,10 @@ typedef enum {
 /* BSDE_ACT_RBF = exp(-x^2) (brax/_impl/arch.py:31).  Its derivative -2 x a needs the sign of the pre-activation, which the output
  * a = exp(-x^2) does not determine: the conv epilogues store a with the sign of x in the LAST MANTISSA BIT (a perturbation of at most
  * one ulp of the stored activation) and the data-gradient epilogues read it back: x = (bit ? -1 : 1) * sqrt(-ln a). */
-typedef enum { BSDE_ACT_SOFTPLUS = 0, BSDE_ACT_TANH = 1, BSDE_ACT_ELU = 2, BSDE_ACT_NONE = 3, BSDE_ACT_RBF = 4 } bsde_act;
+/* BSDE_ACT_SWISH = x * sigmoid(x * softplus(beta)) with a TRAINABLE beta per channel / hidden unit (brax/_impl/arch.py:14-29): for
+ * f_x beta lives in the flat weight vector w(t) after the conv it follows (bsde_xpath_desc.beta_off), for f_w it is a parameter
+ * vector of the hidden layer (bsde_fw_params.beta1 / betam). */
+typedef enum { BSDE_ACT_SOFTPLUS = 0, BSDE_ACT_TANH = 1, BSDE_ACT_ELU = 2, BSDE_ACT_NONE = 3, BSDE_ACT_RBF = 4, BSDE_ACT_SWISH = 5 } bsde_act;
 
 typedef enum { BSDE_EULER_MARUYAMA = 0, BSDE_MILSTEIN = 1, BSDE_EULER_HEUN = 2 } bsde_method;
 
@@ -97,6 +100,9 @@ typedef struct {
   float* wtbm[BSDE_FW_MAX_MID]; float* btm[BSDE_FW_MAX_MID];
   /* last layer  dL -> P :  W4 [dL][P] row-major, b,w_t,w_tb,b_t [P] each */
   float* W4; float* b4; float* wt4; float* wtb4; float* bt4;
+  /* act == BSDE_ACT_SWISH: trainable beta of the activation after the first hidden layer ([dims[0]]) and after middle layer i
+   * ([dims[i+1]]); NULL otherwise */
+  float* beta1; float* betam[BSDE_FW_MAX_MID];
   int32_t plain;   /* 1: every layer is a plain Linear (torchbnn `Linear`, time ignored: torchbnn/_impl/diffeq_layers.py:169-175,
                       make_w_net models.py:57-80): gate = 1, shift = 0; the w_t / w_tb / b_t pointers are not touched */
 } bsde_fw_params;
@@ -215,6 +221,8 @@ typedef struct {
   int64_t P;               /* w_dim: stride between w_k and w_{k+1} in d_wtraj */
   int64_t x_numel;         /* S*B*H*W*C */
   bsde_conv_layer layers[BSDE_MAX_LAYERS];
+  int64_t beta_off[BSDE_MAX_LAYERS]; /* act == BSDE_ACT_SWISH: offset inside w of the beta vector (layers[l].cout entries) of the
+                                        activation that follows conv l (arch.py:172-174; l < nlayers - 1); ignored otherwise */
 } bsde_xpath_desc;
 
 size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t backward);

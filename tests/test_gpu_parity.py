@@ -404,7 +404,12 @@ def _tc_close(a, b, rel, what):
     _close(a, b, 0.0, rel * float(b64.abs().max()) + 1e-12, what)
 
 
-@pytest.mark.parametrize("C_in,fx_dim,H,B", [(5, 64, 8, 3), (20, 64, 16, 2), (80, 64, 8, 5), (4, 16, 6, 3)])
+@pytest.mark.parametrize("C_in,fx_dim,H,B", [(5, 64, 8, 3), (20, 64, 16, 2), (80, 64, 8, 5), (4, 16, 6, 3),
+                                             # the taps-on-N conv kernel (64 / 32 -> <= 7 channels, BIAS and ACCUM epilogues) and the thin
+                                             # weight-gradient kernel (64 <-> <= 7 channels): every channel count they serve, one-tile and
+                                             # many-tile position grids, a full-size 32x32 image, and the counts just outside (fallbacks)
+                                             (1, 64, 12, 2), (2, 64, 4, 1), (6, 64, 32, 1), (7, 64, 6, 3), (8, 64, 4, 2), (5, 32, 8, 2),
+                                             (3, 64, 16, 9)])
 def test_tconv_tc_layers_forward_and_dgrad(built_lib, C_in, fx_dim, H, B):
     """Every forward geometry and every data gradient on the tcgen05 path vs the fp64 oracle."""
     from bayesde_b200 import _lib

@@ -51,6 +51,38 @@ def test_xla_padding_rules():
     assert y.shape[1] == 4 and z.shape[1] == 8
 
 
+def test_xla_geometry_pinned_on_independent_statements():
+    """The north-star (JAX) path cannot be run here (jax 0.1.77 is not installable), so the two third-party geometry rules the
+    oracle restates are pinned on statements that do not come from the oracle's author:
+
+    (i) SAME padding of `lax.conv_general_dilated` = TensorFlow's rule.  The TensorFlow guide's illustrated example ("Notes on
+        padding": 13 inputs, filter width 6, stride 5 -> "pad| |1 2 ... 13| |pad pad", i.e. one zero before and two after) and
+        its sentence "the bottom and right sides always get the one additional padded pixel" are the known answers.
+    (ii) `lax.conv_transpose(padding="SAME")`: JAX documents its padding as the one that makes the op the TRANSPOSE (gradient)
+        of `conv_general_dilated` with the same padding string when `transpose_kernel=True`; the reference calls it with the
+        default `transpose_kernel=False` (stax.GeneralConvTranspose), i.e. the same geometry with the kernel neither flipped
+        nor its I/O axes swapped.  So the oracle's transposed conv, fed a spatially flipped, I/O-swapped kernel, must equal
+        torch autograd's data gradient of the oracle's stride-2 SAME conv -- pads (2, 1) pass, (1, 2) / (1, 1) / (2, 2) do not."""
+    assert jp.xla_same_pads(13, 6, 5) == (1, 2)
+    for n in (7, 8, 16, 28, 32):
+        lo, hi = jp.xla_same_pads(n, 3, 2)
+        assert hi - lo in (0, 1) and lo + hi == max((-(-n // 2) - 1) * 2 + 3 - n, 0)   # the extra pixel goes to the end
+    g = torch.Generator().manual_seed(0)
+    for n in (8, 16):
+        x = torch.randn(2, n, n, 3, generator=g, dtype=torch.float64, requires_grad=True)
+        w = torch.randn(3, 3, 3, 4, generator=g, dtype=torch.float64)             # HWIO
+        y = jp.conv_general_dilated_nhwc(x, w, 2, (jp.xla_same_pads(n, 3, 2),) * 2)
+        dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+        (gx,) = torch.autograd.grad((y * dy).sum(), x)                            # the transpose of the SAME stride-2 conv
+        wt = w.flip(0, 1).permute(0, 1, 3, 2)                                     # transpose_kernel=True: flip space, swap I/O
+        p = jp.conv_transpose_same_pads(3, 2)
+        got = jp.conv_general_dilated_nhwc(dy, wt, 1, (p, p), lhs_dilation=2)
+        assert got.shape == gx.shape and torch.allclose(got, gx, rtol=1e-12, atol=1e-12)
+        for bad in ((1, 2), (1, 1), (2, 2)):
+            alt = jp.conv_general_dilated_nhwc(dy, wt, 1, (bad, bad), lhs_dilation=2)
+            assert alt.shape != gx.shape or not torch.allclose(alt, gx, rtol=1e-6, atol=1e-6)
+
+
 def test_layout_sizes_match_survey():
     assert [jp.fx_layout(0, c, 64)[1] for c in (5, 20, 80)] == [81458, 98888, 168608]
     assert jp.fx_layout(0, 3, 64)[1] == 79134 - 0 or True
