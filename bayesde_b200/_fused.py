@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .arch import fw_layers
+from .arch import fw_betas, fw_layers  # noqa: F401
 
 
 def reference_time_grid(ts, mode="reference"):
@@ -37,8 +37,8 @@ def reference_time_grid(ts, mode="reference"):
     return np.asarray(tk, dtype=np.float32), np.asarray(dtk, dtype=np.float32)
 
 
-def _fw_struct(layers, P, hidden_dims, actfn):
-    """Fill a bsde_fw_params with the device pointers of the (W,b,w_t,w_tb,b_t) tensors."""
+def _fw_struct(layers, P, hidden_dims, actfn, betas=()):
+    """Fill a bsde_fw_params with the device pointers of the (W,b,w_t,w_tb,b_t) tensors (and the swish beta vectors)."""
     fp = _lib.FwParams()
     fp.P = P
     fp.nhid = len(hidden_dims)
@@ -53,7 +53,21 @@ def _fw_struct(layers, P, hidden_dims, actfn):
             getattr(fp, name)[i] = _lib.ptr(t).value
     for name, t in zip(("W4", "b4", "wt4", "wtb4", "bt4"), layers[-1]):
         setattr(fp, name, _lib.ptr(t).value)
+    if actfn == "swish":
+        if len(betas) != len(hidden_dims):
+            raise ValueError(f"swish f_w needs one beta vector per hidden layer ({len(hidden_dims)}), got {len(betas)}")
+        fp.beta1 = _lib.ptr(betas[0]).value
+        for i, t in enumerate(betas[1:]):
+            fp.betam[i] = _lib.ptr(t).value
     return fp
+
+
+def split_fw_flat(cfg, fw_flat):
+    """The flat f_w tensor list of the autograd functions: five tensors per layer, then (swish only) one beta per hidden layer."""
+    nl = len(cfg.fw["hidden_dims"]) + 1
+    layers = [tuple(t.contiguous() for t in fw_flat[5 * i:5 * i + 5]) for i in range(nl)]
+    betas = [t.contiguous() for t in fw_flat[5 * nl:]]
+    return layers, betas
 
 
 class BlockConfig:
@@ -97,6 +111,7 @@ class BlockConfig:
         d.x_numel = self.x_numel
         for i, L in enumerate(layers):
             d.layers[i] = L
+            d.beta_off[i] = self.fx.layers[i].get("beta_off", -1)
         return d
 
     def wdesc(self, seed, stream_id, w0_per_sample):
@@ -110,14 +125,14 @@ class BlockConfig:
         return d
 
 
-def wsde_forward(cfg, w0, layers, dW, seed, stream_id, w_stale):
+def wsde_forward(cfg, w0, layers, dW, seed, stream_id, w_stale, betas=()):
     """K1 forward.  Returns (wtraj [S,nit+1,P], z1 (opaque), kl [S])."""
     L = _lib.lib()
     dev = w0.device
     S, nit, P = cfg.S, cfg.nit, cfg.P
     w0_per_sample = w0.dim() == 2
     d = cfg.wdesc(seed, stream_id, w0_per_sample)
-    fp = _fw_struct(layers, P, cfg.fw["hidden_dims"], cfg.fw["actfn"])
+    fp = _fw_struct(layers, P, cfg.fw["hidden_dims"], cfg.fw["actfn"], betas)
     wtraj = torch.empty(S, nit + 1, P, device=dev, dtype=torch.float32)
     z1 = torch.empty(nit * S * cfg.fw["hidden_dims"][0], device=dev, dtype=torch.float32)
     kl = torch.empty(S, device=dev, dtype=torch.float32)
@@ -137,14 +152,16 @@ def wsde_forward(cfg, w0, layers, dW, seed, stream_id, w_stale):
     return wtraj, z1, kl
 
 
-def wsde_backward(cfg, layers, wtraj, z1, gw_traj, gkl, gwT, w0_per_sample):
+def wsde_backward(cfg, layers, wtraj, z1, gw_traj, gkl, gwT, w0_per_sample, betas=()):
+    """K1 reverse pass.  Returns (gw0, gradients of the layer tensors [+ the swish beta gradients as a last list entry])."""
     L = _lib.lib()
     dev = wtraj.device
     S, P = cfg.S, cfg.P
     d = cfg.wdesc(0, 0, w0_per_sample)
-    fp = _fw_struct(layers, P, cfg.fw["hidden_dims"], cfg.fw["actfn"])
+    fp = _fw_struct(layers, P, cfg.fw["hidden_dims"], cfg.fw["actfn"], betas)
     glayers = [tuple(torch.empty_like(t) for t in lay) for lay in layers]
-    gfp = _fw_struct(glayers, P, cfg.fw["hidden_dims"], cfg.fw["actfn"])
+    gbetas = [torch.empty_like(t) for t in betas]
+    gfp = _fw_struct(glayers, P, cfg.fw["hidden_dims"], cfg.fw["actfn"], gbetas)
     gw0 = torch.empty((S, P) if w0_per_sample else (P,), device=dev, dtype=torch.float32)
     nbytes = L.bsde_wsde_workspace_bytes(C.byref(d), C.byref(fp))
     ws = _lib.workspace(nbytes, dev, "wsde")
@@ -153,6 +170,8 @@ def wsde_backward(cfg, layers, wtraj, z1, gw_traj, gkl, gwT, w0_per_sample):
                          _lib.ptr(gw_traj), _lib.ptr(gkl), _lib.ptr(gwT), _lib.ptr(gw0), C.byref(gfp),
                          C.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr())
     _lib.check(st, "bsde_wsde_bwd")
+    if gbetas:
+        glayers = glayers + [tuple(gbetas)]   # flattened by the callers in the order of split_fw_flat
     return gw0, glayers
 
 
@@ -216,18 +235,17 @@ class SDEBNNSolve(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, dW, seed, stream_id, w_stale, x, w0, *fw_flat):
-        layers = [tuple(fw_flat[i:i + 5]) for i in range(0, len(fw_flat), 5)]
+        layers, betas = split_fw_flat(cfg, fw_flat)
         x = x.contiguous()
         w0c = w0.contiguous()
-        layers = [tuple(t.contiguous() for t in lay) for lay in layers]
         with _Timed("k1_fwd"):
-            wtraj, z1, kl = wsde_forward(cfg, w0c, layers, dW, seed, stream_id, w_stale)
+            wtraj, z1, kl = wsde_forward(cfg, w0c, layers, dW, seed, stream_id, w_stale, betas)
         with _Timed("k2_fwd"):
             # under torch.no_grad() (evaluation) nothing will be differentiated, but needs_input_grad only reflects requires_grad and
             # grad mode is always off inside forward(): the caller records it in cfg.track before apply()
             xs, acts = xpath_forward(cfg, x, wtraj, keep_acts=(not cfg.remat) and getattr(cfg, "track", True) and any(ctx.needs_input_grad))
         ctx.cfg = cfg
-        ctx.layers = layers
+        ctx.layers, ctx.betas = layers, betas
         ctx.w0_per_sample = w0.dim() == 2
         ctx.acts = acts
         ctx.save_for_backward(wtraj, z1, xs)
@@ -250,7 +268,7 @@ class SDEBNNSolve(torch.autograd.Function):
             ctx.acts = None
         with _Timed("k1_bwd"):
             gw0, glayers = wsde_backward(cfg, ctx.layers, wtraj, z1, gw_traj, gkl.contiguous().float(), None,
-                                         ctx.w0_per_sample)
+                                         ctx.w0_per_sample, ctx.betas)
         flat = [t for lay in glayers for t in lay]
         return (None, None, None, None, None, gx0, gw0, *flat)
 
@@ -299,7 +317,7 @@ class SDEBNNAdjointSolve(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, ts, dt, bm, w_stale, x, w0, *fw_flat):
-        layers = [tuple(t.contiguous() for t in fw_flat[i:i + 5]) for i in range(0, len(fw_flat), 5)]
+        layers, betas = split_fw_flat(cfg, fw_flat)
         S, P = cfg.S, cfg.P
         steps, marks = ito_step_schedule(ts, dt)
         Yx = x.contiguous()
@@ -312,13 +330,13 @@ class SDEBNNAdjointSolve(torch.autograd.Function):
                 for (t, h, tn) in steps[done:upto]:
                     W_n = bm(tn)
                     cfg.set_step(t, h)
-                    wtraj, _, klk = wsde_forward(cfg, Yw, layers, (W_n - W_t).view(S, 1, P), 0, 0, w_stale)
+                    wtraj, _, klk = wsde_forward(cfg, Yw, layers, (W_n - W_t).view(S, 1, P), 0, 0, w_stale, betas)
                     xs, _ = xpath_forward(cfg, Yx, wtraj, keep_acts=False)
                     Yx, Yw, W_t = xs[1], wtraj[:, 1].contiguous(), W_n
                     kl = kl + klk
                 done = upto
                 rows.append(Yw)
-        ctx.cfg, ctx.ts, ctx.dt, ctx.bm, ctx.w_stale, ctx.layers = cfg, ts, dt, bm, w_stale, layers
+        ctx.cfg, ctx.ts, ctx.dt, ctx.bm, ctx.w_stale, ctx.layers, ctx.betas = cfg, ts, dt, bm, w_stale, layers, betas
         ctx.w0_per_sample = w0.dim() == 2
         ctx.save_for_backward(Yx, Yw)
         wout = torch.stack(rows, dim=1)
@@ -342,11 +360,11 @@ class SDEBNNAdjointSolve(torch.autograd.Function):
             for (r, h, rn) in steps:
                 tau, W_n = -r, bm(-rn)
                 cfg.set_step(tau, -h)
-                wtraj, z1, _ = wsde_forward(cfg, Yw, layers, (W_n - W_t).view(S, 1, P), 0, 0, ctx.w_stale)
+                wtraj, z1, _ = wsde_forward(cfg, Yw, layers, (W_n - W_t).view(S, 1, P), 0, 0, ctx.w_stale, ctx.betas)
                 xs, acts = xpath_forward(cfg, Yx, wtraj, keep_acts=not cfg.remat)   # remat: K3 recomputes them from Y
                 cfg.set_step(tau, h)
                 a_x, gw_traj = xpath_backward(cfg, xs, wtraj, a_x, acts)
-                a_w, gl = wsde_backward(cfg, layers, wtraj, z1, gw_traj, gkl, a_w, True)
+                a_w, gl = wsde_backward(cfg, layers, wtraj, z1, gw_traj, gkl, a_w, True, ctx.betas)
                 gl = [t for lay in gl for t in lay]
                 if gacc is None:
                     gacc = gl
@@ -354,7 +372,7 @@ class SDEBNNAdjointSolve(torch.autograd.Function):
                     torch._foreach_add_(gacc, gl)
                 Yx, Yw, W_t = xs[1], wtraj[:, 1].contiguous(), W_n
         if gacc is None:
-            gacc = [torch.zeros_like(t) for lay in layers for t in lay]
+            gacc = [torch.zeros_like(t) for lay in layers for t in lay] + [torch.zeros_like(t) for t in ctx.betas]
         global LAST_RECONSTRUCTION
         LAST_RECONSTRUCTION = (Yx, Yw)  # y0 as the reverse solve reconstructs it (`y0_rec` of sde_vjp.py:162; diagnostics / tests)
         gw0 = a_w if ctx.w0_per_sample else a_w.sum(0)

@@ -53,6 +53,13 @@ class XpathDesc(C.Structure):
                 ("layers", ConvLayer * MAX_LAYERS), ("beta_off", C.c_int64 * MAX_LAYERS)]
 
 
+class SDELayerDesc(C.Structure):
+    _fields_ = [("S", C.c_int32), ("B", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("nt", C.c_int32), ("act", C.c_int32),
+                ("driftw", C.c_int32), ("diffw", C.c_int32), ("prior_ou", C.c_int32), ("diff_drift", C.c_int32),
+                ("stop_grad", C.c_int32), ("prior_solve", C.c_int32), ("w0_per_sample", C.c_int32), ("sigma", C.c_float),
+                ("P", C.c_int64), ("seed", C.c_uint64), ("stream_id", C.c_uint32), ("sample_offset", C.c_uint32)]
+
+
 class ToyDesc(C.Structure):
     _fields_ = [("n", C.c_int32), ("nt", C.c_int32), ("h1", C.c_int32), ("h2", C.c_int32),
                 ("sigma", C.c_float), ("theta", C.c_float)]
@@ -69,7 +76,7 @@ _EXPORTS = ["bsde_version", "bsde_last_error", "bsde_launch_count", "bsde_wsde_w
             "bsde_xpath_workspace_bytes", "bsde_xpath_acts_bytes", "bsde_xpath_fwd", "bsde_xpath_bwd", "bsde_step_update",
             "bsde_philox_increments", "bsde_toy_em_fwd", "bsde_toy_em_bwd", "bsde_chain_workspace_bytes", "bsde_chain_acts_floats",
             "bsde_chain_out_offset", "bsde_chain_fwd", "bsde_chain_bwd", "bsde_nchw_reinterp_axpy", "bsde_brownian_tree",
-            "bsde_step_update_prod", "bsde_brownian_tree_threefry", "bsde_threefry_split"]
+            "bsde_step_update_prod", "bsde_brownian_tree_threefry", "bsde_threefry_split", "bsde_sdelayer_fwd", "bsde_sdelayer_bwd"]
 
 
 def lib():
@@ -113,6 +120,8 @@ def lib():
                                               C.c_int64, C.c_int64, vp, vp]
     L.bsde_threefry_split.argtypes = [C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(C.c_uint32)]
     L.bsde_step_update_prod.argtypes = [C.c_int64, C.c_float, vp, vp, vp, vp, vp, vp]
+    L.bsde_sdelayer_fwd.argtypes = [C.POINTER(SDELayerDesc), C.POINTER(FwParams), vp, vp, vp, vp, vp, vp]
+    L.bsde_sdelayer_bwd.argtypes = [C.POINTER(SDELayerDesc), C.POINTER(FwParams), vp, vp, vp, vp, vp, vp, C.POINTER(FwParams), vp]
     L.bsde_toy_em_fwd.argtypes = [C.POINTER(ToyDesc), vp, vp, vp, C.c_uint64] + [vp] * 8 + [vp, vp, vp]
     L.bsde_toy_em_bwd.argtypes = [C.POINTER(ToyDesc), vp, vp, vp, vp] + [vp] * 8 + [vp] * 8 + [vp]
     if L.bsde_version() != 200:

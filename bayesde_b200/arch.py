@@ -40,7 +40,9 @@ def split(rng, n):
 ACTFNS = ("softplus", "tanh", "elu", "rbf", "swish")  # arch.py:31-32
 
 
-def _act(name, x):
+def _act(name, x, beta=None):
+    if name == "swish":  # arch.py:14-29: trainable beta per unit / channel
+        return x * torch.sigmoid(x * F.softplus(beta))
     if name == "softplus":
         return F.softplus(x)
     if name == "tanh":
@@ -73,8 +75,8 @@ def MLP(hidden_dims=(1, 64, 1), actfn="softplus", xt=False, ou_dw=False, p_scale
         raise NotImplementedError("MLP(xt=False): the fused path implements the time-dependent f_w only")
     if p_scale != -1.0:
         raise NotImplementedError("p_scale: arch.Exp is undefined in the reference (arch.py:65)")
-    if actfn not in ("softplus", "tanh", "elu", "rbf"):
-        raise NotImplementedError(f"fw_actfn={actfn!r} is not available in the fused B200 path")
+    if actfn not in ACTFNS:
+        raise KeyError(actfn)  # ACTFNS[actfn], arch.py:37
     if len(hidden_dims) < 1 or len(hidden_dims) > _lib.FW_MAX_MID + 1:
         raise ValueError(f"len(hidden_dims) must be in 1..{_lib.FW_MAX_MID + 1}")
     if hidden_dims[0] > _lib.FW_MAX_EDGE or hidden_dims[-1] > _lib.FW_MAX_EDGE or max(hidden_dims) > _lib.FW_MAX_HID:
@@ -95,18 +97,18 @@ def MLP(hidden_dims=(1, 64, 1), actfn="softplus", xt=False, ou_dw=False, p_scale
                 sw, sb = math.sqrt(2.0 / din), 1e-2  # he_normal / normal(1e-2), diffeq_layers.py:73
             mk = lambda *s, sd: (torch.randn(*s, generator=g) * sd).to(device)
             params.append((mk(din, dout, sd=sw), mk(dout, sd=sb), mk(dout, sd=sb), mk(dout, sd=sb), mk(dout, sd=sb)))
-            if not last:
-                params.append(())
+            if not last:  # the activation's parameters: () or, for the trainable swish, (beta,) = 0.5 (arch.py:14-22,41-42)
+                params.append((torch.full((dout,), 0.5).to(device),) if actfn == "swish" else ())
         return tuple(input_shape), (((), params) if ou_dw else params)
 
     def apply_fun(params, inputs, **kwargs):
         x, t = inputs
-        layers = [p for p in (params[1] if ou_dw else params) if len(p)]
+        layers, betas = fw_layers(params), fw_betas(params)
         h = x
         for i, (W, b, w_t, w_tb, b_t) in enumerate(layers):
             h = (h @ W + b) * torch.sigmoid(w_t * t + w_tb) + b_t * t  # diffeq_layers.py:84-95
             if i < len(layers) - 1:
-                h = _act(actfn, h)
+                h = _act(actfn, h, betas[i] if betas else None)
         return (h, 2 * t) if ou_dw else (h, t)  # arch.py:100-103 returns (t2, out2+out1) = (mlp_out, 2t)
 
     layer = FwLayer(init_fun, apply_fun)
@@ -119,7 +121,15 @@ def fw_layers(fw_params):
     p = fw_params
     if isinstance(p, (tuple, list)) and len(p) == 2 and isinstance(p[0], (tuple, list)) and len(p[0]) == 0:
         p = p[1]
-    return [q for q in p if len(q)]
+    return [q for q in p if len(q) == 5]
+
+
+def fw_betas(fw_params):
+    """The swish beta vectors (one per hidden layer) inside an MLP parameter pytree; [] for the other activations."""
+    p = fw_params
+    if isinstance(p, (tuple, list)) and len(p) == 2 and isinstance(p[0], (tuple, list)) and len(p[0]) == 0:
+        p = p[1]
+    return [q[0] for q in p if len(q) == 1]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -135,8 +145,8 @@ class FxSpec:
     """Conv stack of one SDEBNN block for a fixed NHWC input shape."""
 
     def __init__(self, block_type, input_shape, fx_dim, fx_actfn):
-        if fx_actfn not in ("softplus", "tanh", "elu", "rbf"):
-            raise NotImplementedError(f"fx_actfn={fx_actfn!r} is not available in the fused B200 path")
+        if fx_actfn not in ACTFNS:
+            raise KeyError(fx_actfn)  # ACTFNS[fx_actfn], arch.py:172
         _, H, W, C = input_shape
         self.block_type, self.fx_dim, self.actfn = block_type, fx_dim, fx_actfn
         self.H, self.W, self.C = int(H), int(W), int(C)
@@ -154,7 +164,7 @@ class FxSpec:
             raise ValueError(f"Invalid block_type {block_type}")  # arch.py:207
         self.layers = []
         off, h, w = 0, self.H, self.W
-        for (ci, co, k, s, tr) in convs:
+        for li, (ci, co, k, s, tr) in enumerate(convs):
             if not tr:
                 lo_h, _ = same_pads(h, k, s)
                 lo_w, _ = same_pads(w, k, s)
@@ -170,6 +180,11 @@ class FxSpec:
             self.layers.append(dict(cin=ci, cout=co, k=k, hin=h, win=w, hout=ho, wout=wo, w_off=off,
                                     b_off=off + nw, fan_in=k * k * (ci + 1), fan_out=k * k * co, **geo))
             off += nw + co
+            # trainable swish: the (beta,) leaf of the activation follows the conv's (W, b) in ravel_pytree order (arch.py:172-188)
+            self.layers[-1]["beta_off"] = -1
+            if fx_actfn == "swish" and li < len(convs) - 1:
+                self.layers[-1]["beta_off"] = off
+                off += fx_dim
             h, w = ho, wo
         if (h, w) != (self.H, self.W):
             raise AssertionError(f"fx needs to have the same input and output shapes but got "
@@ -198,6 +213,8 @@ class FxSpec:
             std = math.sqrt(2.0 / (L["fan_in"] + L["fan_out"]))
             w[L["w_off"]:L["b_off"]] = torch.randn(nw, generator=g) * std
             w[L["b_off"]:L["b_off"] + L["cout"]] = torch.randn(L["cout"], generator=g) * 1e-6
+            if L["beta_off"] >= 0:
+                w[L["beta_off"]:L["beta_off"] + self.fx_dim] = 0.5   # Swish_(out_dim, beta_init=0.5), arch.py:14
         return w.to(device)
 
 

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _fused, _lib
-from .arch import FxSpec, Layer, _gen, fw_layers, split
+from .arch import FxSpec, Layer, _gen, fw_betas, fw_layers, split
 from .sdeint import sdeint_ito, sdeint_ito_fixed_grid
 
 
@@ -50,7 +50,7 @@ class _AugDynamics:
         cfg.want_kltraj = True
         dW = sigma_noise.reshape(S, 1, P).to(torch.float32).contiguous() if sigma_noise is not None else torch.zeros(S, 1, P, device=y.device)
         with torch.no_grad():
-            wtraj, _, _ = _fused.wsde_forward(cfg, w, layers, dW, 0, 0, self.w_stale)
+            wtraj, _, _ = _fused.wsde_forward(cfg, w, layers, dW, 0, 0, self.w_stale, self._betas)
             xs, _ = _fused.xpath_forward(cfg, x, wtraj, keep_acts=False)
         return yy, xs[1].reshape(S, x_dim), wtraj[:, 1], cfg.kltraj[:, 1]
 
@@ -90,8 +90,10 @@ class _AugDynamics:
         cfg = _fused.BlockConfig(self.fx, self.fw, S, B, nsteps, self.diff_coef, bool(rep), time_grid, self.math,
                                  ts=ts_np, remat=self.remat)
         cfg.sample_offset = self.sample_offset
+        self._betas = []
         if self.w_drift:
             layers = fw_layers(args)
+            self._betas = fw_betas(args)
         else:
             layers = _fused.zero_fw_layers(self.P, device)
             cfg.fw = dict(hidden_dims=(1,), actfn="softplus", ou_dw=False)
@@ -129,7 +131,7 @@ class _AugDynamics:
             dW, seed, sid = None, int(rng[0]), int(rng[1])
         else:
             dW, seed, sid = None, int(rng), self.stream_id
-        flat = [t for lay in layers for t in lay]
+        flat = [t for lay in layers for t in lay] + list(self._betas)
         cfg.track = torch.is_grad_enabled()
         cfg.want_kltraj = bool(want_ys)
         xT, kl, wtraj = _fused.SDEBNNSolve.apply(cfg, dW, seed, sid, self.w_stale, x, w0, *flat)
@@ -162,7 +164,7 @@ class _AugDynamics:
         else:
             seed, sid = (int(rng[0]), int(rng[1])) if isinstance(rng, (tuple, list)) else (int(rng), self.stream_id)
             bm = BrownianTree(tsl[0], S * P, tsl[-1], (seed, sid), depth=10, rep=0, device=y0.device)
-        flat = [t for lay in layers for t in lay]
+        flat = [t for lay in layers for t in lay] + list(self._betas)
         return _fused.SDEBNNAdjointSolve.apply(cfg, tsl, float(dt), bm, self.w_stale, x, w0, *flat)
 
 

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbsde.so")
-SOURCES = ["api.cu", "wsde.cu", "tconv_simt.cu", "tconv_tc.cu", "tconv_win.cu", "tconv_tapn.cu", "wgrad_tc.cu", "wgrad_win.cu", "wgrad_thin.cu", "toy_em.cu"]
+SOURCES = ["api.cu", "swish.cu", "wsde.cu", "tconv_simt.cu", "tconv_tc.cu", "tconv_win.cu", "tconv_tapn.cu", "wgrad_tc.cu", "wgrad_win.cu", "wgrad_thin.cu", "toy_em.cu", "sdelayer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -81,7 +81,7 @@ class SDEBNNClassifier(nn.Module):
         out = []
         for (w0, _, fwp) in self.block_params():
             out.append(w0)
-            out += [t for lay in arch.fw_layers(fwp) for t in lay]
+            out += [t for lay in arch.fw_layers(fwp) for t in lay] + arch.fw_betas(fwp)
         (mean, logstd) = self.head_params()
         (Wm, bm), (Wl, bl) = mean[1], logstd[1]
         return out + [Wm, bm, Wl, bl]
@@ -92,7 +92,7 @@ class SDEBNNClassifier(nn.Module):
         flat_r = []
         for (w0, fw) in params_r:
             flat_r.append(w0)
-            flat_r += [t for lay in fw for t in lay]
+            flat_r += [t for lay in fw for t in lay[:5]] + [lay[5] for lay in fw if len(lay) > 5]   # swish betas last
         (Wm, bm), (Wl, bl) = head_r
         flat_r += [Wm, bm, Wl, bl]
         for p, r in zip(self.oracle_ordered_parameters(), flat_r):

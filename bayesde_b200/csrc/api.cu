@@ -71,6 +71,13 @@ size_t tconv_wgrad_ws_thin(const bsde_conv_layer* L, int S, int B);
 int tconv_wgrad_thin(const bsde_conv_layer* L, int S, int B, const float* in, const float* dy, float t, float scale,
                      float* gw, long long gw_sample_stride, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// trainable swish of f_x (swish.cu): elementwise activation / derivative + per-channel beta gradient
+size_t swish_partial_floats(int S, long long per_sample, int C);
+int swish_forward(const float* z, const float* w, long long wss, long long beta_off, int S, long long per_sample, int C, float* a,
+                  cudaStream_t st);
+int swish_backward(float* dz, const float* z, const float* w, long long wss, long long beta_off, int S, long long per_sample, int C,
+                   float scale, float* partial, float* gw, long long gss, cudaStream_t st);
+
 static size_t wgrad_ws(const bsde_conv_layer* L, int S, int B, int math) {
   size_t b = tconv_wgrad_ws_simt(L, S, B);
   if (math == BSDE_MATH_TC && tconv_wgrad_thin_supported(L, S, B)) b = std::max(b, tconv_wgrad_ws_thin(L, S, B));
@@ -136,6 +143,13 @@ static size_t act_elems(const bsde_xpath_desc* d, int l) {  // output of layer l
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// stored output of layer l: the activation a_l and, for the trainable swish (whose derivative needs the PRE-activation: it is not
+// monotone), z_l right behind it
+static size_t act_slot_bytes(const bsde_xpath_desc* d, int l) {
+  return align_up(act_elems(d, l) * sizeof(float)) * (d->act == BSDE_ACT_SWISH ? 2 : 1);
+}
+static float* swish_z(const bsde_xpath_desc* d, int l, float* a) { return a + align_up(act_elems(d, l) * sizeof(float)) / sizeof(float); }
+
 }  // namespace bsde
 
 using namespace bsde;
@@ -179,7 +193,11 @@ static int xpath_check(const bsde_xpath_desc* d) {
   BSDE_CHECK_ARG(d != nullptr, "NULL descriptor");
   BSDE_CHECK_ARG(d->nlayers >= 2 && d->nlayers <= BSDE_MAX_LAYERS, "nlayers=%d unsupported", d->nlayers);
   BSDE_CHECK_ARG(d->S >= 1 && d->B >= 1 && d->nit >= 1, "S, B, nit must be positive");
-  BSDE_CHECK_ARG((d->act >= BSDE_ACT_SOFTPLUS && d->act <= BSDE_ACT_ELU) || d->act == BSDE_ACT_RBF, "fx activation %d unsupported", d->act);
+  BSDE_CHECK_ARG((d->act >= BSDE_ACT_SOFTPLUS && d->act <= BSDE_ACT_ELU) || d->act == BSDE_ACT_RBF || d->act == BSDE_ACT_SWISH,
+                 "fx activation %d unsupported", d->act);
+  if (d->act == BSDE_ACT_SWISH)
+    for (int l = 0; l + 1 < d->nlayers; ++l)
+      BSDE_CHECK_ARG(d->beta_off[l] >= 0 && d->beta_off[l] + d->layers[l].cout <= d->P, "swish: beta_off[%d] outside w", l);
   const bsde_conv_layer& L0 = d->layers[0];
   const bsde_conv_layer& Ln = d->layers[d->nlayers - 1];
   BSDE_CHECK_ARG(L0.cin == Ln.cout && L0.hin == Ln.hout && L0.win == Ln.wout,
@@ -203,6 +221,17 @@ static size_t xpath_tc_bytes(const bsde_xpath_desc* d, int backward) {
     }
   }
   return align_up(m);
+}
+
+// per-CTA partial sums of the swish beta gradient (they share the weight-gradient scratch: launches are stream-ordered)
+static size_t xpath_swish_bytes(const bsde_xpath_desc* d) {
+  if (d->act != BSDE_ACT_SWISH) return 0;
+  size_t m = 0;
+  for (int l = 0; l + 1 < d->nlayers; ++l) {
+    const bsde_conv_layer& L = d->layers[l];
+    m = std::max(m, swish_partial_floats(d->S, (long long)d->B * L.hout * L.wout * L.cout, L.cout) * sizeof(float));
+  }
+  return m;
 }
 
 // Weights of ALL scan iterations are repacked up front, one launch per layer form, into
@@ -230,7 +259,7 @@ static size_t prepack_floats(const bsde_xpath_desc* d, int backward, bool need_f
   size_t tot = 0;
   const int n = d->nlayers;
   for (int l = 0; l < n; ++l) {
-    const int epi_f = l == n - 1 ? BSDE_EPI_EULER : BSDE_EPI_BIAS_ACT;
+    const int epi_f = l == n - 1 ? BSDE_EPI_EULER : (d->act == BSDE_ACT_SWISH ? BSDE_EPI_BIAS : BSDE_EPI_BIAS_ACT);
     if (need_fwd_forms && fast_form(&d->layers[l], d->S, d->B, epi_f))
       tot += (size_t)d->nit * d->S * fast_img_floats(&d->layers[l], d->S, d->B, epi_f);
     if (backward) {
@@ -249,7 +278,7 @@ static int prepack_all(const bsde_xpath_desc* d, int backward, bool need_fwd_for
   const int n = d->nlayers;
   const long long wss = (long long)(d->nit + 1) * d->P;
   for (int l = 0; l < n; ++l) {
-    const int epi_f = l == n - 1 ? BSDE_EPI_EULER : BSDE_EPI_BIAS_ACT;
+    const int epi_f = l == n - 1 ? BSDE_EPI_EULER : (d->act == BSDE_ACT_SWISH ? BSDE_EPI_BIAS : BSDE_EPI_BIAS_ACT);
     if (need_fwd_forms && fast_form(&d->layers[l], d->S, d->B, epi_f)) {
       pp.img[l] = buf; pp.per_iter[l] = (size_t)d->S * fast_img_floats(&d->layers[l], d->S, d->B, epi_f);
       if (int e = fast_repack(&d->layers[l], d->S, d->B, d->nit, d_wtraj, wss, d->P, epi_f, buf, st)) return e;
@@ -271,13 +300,14 @@ static int prepack_all(const bsde_xpath_desc* d, int backward, bool need_fwd_for
 extern "C" size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t backward) {
   if (!d || d->nlayers < 2 || d->nlayers > BSDE_MAX_LAYERS) return 0;
   size_t tot = xpath_tc_bytes(d, backward);
-  for (int l = 0; l + 1 < d->nlayers; ++l) tot += align_up(act_elems(d, l) * sizeof(float)) * (backward ? 2 : 1);
+  for (int l = 0; l + 1 < d->nlayers; ++l) tot += act_slot_bytes(d, l) * (backward ? 2 : 1);
   if (backward) {
     size_t wg = 0;
     for (int l = 0; l < d->nlayers; ++l) {
       size_t b = wgrad_ws(&d->layers[l], d->S, d->B, d->math);
       if (b > wg) wg = b;
     }
+    wg = std::max(wg, xpath_swish_bytes(d));
     tot += align_up(wg);
   }
   tot += align_up(prepack_floats(d, backward, true) * sizeof(float));
@@ -286,7 +316,7 @@ extern "C" size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t b
 
 static size_t xpath_acts_floats(const bsde_xpath_desc* d) {  // stored layer outputs of one scan iteration
   size_t tot = 0;
-  for (int l = 0; l + 1 < d->nlayers; ++l) tot += align_up(act_elems(d, l) * sizeof(float)) / sizeof(float);
+  for (int l = 0; l + 1 < d->nlayers; ++l) tot += act_slot_bytes(d, l) / sizeof(float);
   return tot;
 }
 
@@ -300,10 +330,19 @@ static int xpath_recompute(const bsde_xpath_desc* d, const float* x, const float
   const int n = d->nlayers;
   const long long wss = (long long)(d->nit + 1) * d->P;
   const float* in = x;
+  const bool sw = d->act == BSDE_ACT_SWISH;
   for (int l = 0; l + 1 < n; ++l) {
-    if (int e = conv_fwd(&d->layers[l], d->S, d->B, in, wk, wss, t, d->act, BSDE_EPI_BIAS_ACT, 1.f, nullptr,
-                         a[l], d->math, tc_ws, tc_bytes, st, pp.img[l] ? pp.img[l] + (size_t)k * pp.per_iter[l] : nullptr, nconv++ > 0))
+    // swish: the conv writes the pre-activation z_l (bias + time term, no activation), one elementwise pass applies beta's gate
+    if (int e = conv_fwd(&d->layers[l], d->S, d->B, in, wk, wss, t, sw ? BSDE_ACT_NONE : d->act, sw ? BSDE_EPI_BIAS : BSDE_EPI_BIAS_ACT,
+                         1.f, nullptr, sw ? swish_z(d, l, a[l]) : a[l], d->math, tc_ws, tc_bytes, st,
+                         pp.img[l] ? pp.img[l] + (size_t)k * pp.per_iter[l] : nullptr, nconv++ > 0))
       return e;
+    if (sw) {
+      const bsde_conv_layer& L = d->layers[l];
+      if (int e = swish_forward(swish_z(d, l, a[l]), wk, wss, d->beta_off[l], d->S, (long long)d->B * L.hout * L.wout * L.cout, L.cout,
+                                a[l], st))
+        return e;
+    }
     in = a[l];
   }
   return 0;
@@ -326,7 +365,7 @@ extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const
   void* tc_ws = ws;
   const size_t tc_bytes = xpath_tc_bytes(d, 0);
   ws += tc_bytes;
-  for (int l = 0; l + 1 < n; ++l) { a[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
+  for (int l = 0; l + 1 < n; ++l) { a[l] = (float*)ws; ws += act_slot_bytes(d, l); }
   const long long wss = (long long)(d->nit + 1) * d->P;
   const size_t acts_step = xpath_acts_floats(d);
   Prepack pp;
@@ -335,7 +374,7 @@ extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const
   for (int k = 0; k < d->nit; ++k) {
     if (d_acts) {  // keep this iteration's layer outputs for the reverse pass (remat = False)
       float* p = d_acts + (size_t)k * acts_step;
-      for (int l = 0; l + 1 < n; ++l) { a[l] = p; p += align_up(act_elems(d, l) * sizeof(float)) / sizeof(float); }
+      for (int l = 0; l + 1 < n; ++l) { a[l] = p; p += act_slot_bytes(d, l) / sizeof(float); }
     }
     const float* xk = d_xs + (size_t)k * d->x_numel;
     float* xn = d_xs + (size_t)(k + 1) * d->x_numel;
@@ -368,11 +407,12 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
   void* tc_ws = ws;
   const size_t tc_bytes = xpath_tc_bytes(d, 1);
   ws += tc_bytes;
-  for (int l = 0; l + 1 < n; ++l) { a[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
+  for (int l = 0; l + 1 < n; ++l) { a[l] = (float*)ws; ws += act_slot_bytes(d, l); }
   for (int l = 0; l + 1 < n; ++l) { dz[l] = (float*)ws; ws += align_up(act_elems(d, l) * sizeof(float)); }
   void* wg_ws = ws;
   size_t wgmax = 0;
   for (int l = 0; l < n; ++l) wgmax = std::max(wgmax, wgrad_ws(&d->layers[l], d->S, d->B, d->math));
+  wgmax = std::max(wgmax, xpath_swish_bytes(d));
   const size_t wg_bytes = align_up(wgmax);
   ws += wg_bytes;
   Prepack pp;
@@ -391,7 +431,7 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
     float* gwk = d_gw_traj + (size_t)k * d->P;
     if (d_acts) {
       float* p = const_cast<float*>(d_acts) + (size_t)k * xpath_acts_floats(d);
-      for (int l = 0; l + 1 < n; ++l) { a[l] = p; p += align_up(act_elems(d, l) * sizeof(float)) / sizeof(float); }
+      for (int l = 0; l + 1 < n; ++l) { a[l] = p; p += act_slot_bytes(d, l) / sizeof(float); }
     } else if (int e = xpath_recompute(d, xk, wk, t, a, tc_ws, tc_bytes, st, pp, k, nconv)) {
       return e;
     }
@@ -403,9 +443,16 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
       if (int e = conv_wgrad(&d->layers[l], d->S, d->B, lin, dy, t, sc, gwk, gss, d->math, wg_ws, wg_bytes, st)) return e;
       if (l > 0) {
         // dz_{l-1} = sc * dgrad(dy) * act'(a_{l-1})
-        if (int e = conv_fwd(&D[l], d->S, d->B, dy, wk, wss, t, d->act, BSDE_EPI_DACT, sc, a[l - 1], dz[l - 1],
+        const bool sw = d->act == BSDE_ACT_SWISH;
+        if (int e = conv_fwd(&D[l], d->S, d->B, dy, wk, wss, t, sw ? BSDE_ACT_NONE : d->act, BSDE_EPI_DACT, sc, a[l - 1], dz[l - 1],
                              d->math, tc_ws, tc_bytes, st, pp.img[n + l] ? pp.img[n + l] + (size_t)k * pp.per_iter[n + l] : nullptr, nconv++ > 0))
           return e;
+        if (sw) {  // dz <- dz * da/dz(z, beta) and dL/dbeta (beta is part of w: arch.py:172-174), from the stored pre-activation
+          const bsde_conv_layer& Lp = d->layers[l - 1];
+          if (int e = swish_backward(dz[l - 1], swish_z(d, l - 1, a[l - 1]), wk, wss, d->beta_off[l - 1], d->S,
+                                     (long long)d->B * Lp.hout * Lp.wout * Lp.cout, Lp.cout, 1.f, (float*)wg_ws, gwk, gss, st))
+            return e;
+        }
         dy = dz[l - 1];
       } else {
         // gx_k = gx_{k+1} + dgrad_0(dz_0)   (identity path of the Euler update)

@@ -735,10 +735,15 @@ static WinPlan win_plan(const bsde_conv_layer* L) {
   // TMA-fed window (input channels a multiple of 32, single input plane): the window buffer holds NR whole grid rows
   static const int tma_on = getenv("BSDE_TMA") ? atoi(getenv("BSDE_TMA")) : 1;
   if (tma_on && p.vec && (L->cin % 32) == 0 && p.NP == 1 && p.Wq + 1 <= 256) {
-    p.tma = 1;
-    p.NR = (p.lead + 128 + p.trail + p.pitch - 2) / p.pitch + 1;   // grid rows any 128-position window (+ halo) can touch
-    p.box_bytes = p.pitch * 128;
-    p.region = (p.NR * p.box_bytes + 128 + 1023) & ~1023;          // + one slack row for the last shifted read
+    const int nr = (p.lead + 128 + p.trail + p.pitch - 2) / p.pitch + 1;   // grid rows any 128-position window (+ halo) can touch
+    // one lane of the producer warp issues the box of one window row: grids narrower than 4 pixels (more than 32 rows per
+    // window) keep the cp.async-fed window (the barrier would otherwise wait for boxes that no lane issues)
+    if (nr <= 32) {
+      p.tma = 1;
+      p.NR = nr;
+      p.box_bytes = p.pitch * 128;
+      p.region = (p.NR * p.box_bytes + 128 + 1023) & ~1023;          // + one slack row for the last shifted read
+    }
   }
   p.w_bytes = p.nent * p.nks * p.npad * 32;
   p.tb_rows = L->has_time ? 1 + 16 * p.NA : 1;

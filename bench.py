@@ -48,6 +48,7 @@ def parse():
     p.add_argument("--cpu_batch", type=int, default=32, help="images in the bounded CPU sample (SURVEY 8.4: B = 32)")
     p.add_argument("--no_fp32_leg", action="store_true", help="skip the fp32-class (CUDA-core conv) throughput leg")
     p.add_argument("--no_cpu_baseline", action="store_true")
+    p.add_argument("--no_config5", action="store_true", help="skip the config-5 (torchbnn SDENet) leg that the default run appends as `config5`")
     p.add_argument("--config", type=int, default=4, choices=[4, 5],
                    help="4: the north-star JAX-front-end SDEBNN classifier (default); 5: BASELINE configs[4], the torchbnn SDENet "
                         "(3x32x32, blocks 2-2-2, hidden 32, w-net 1-128-1, midpoint dt 0.05, inhomogeneous) with the batch sharded over ranks")
@@ -432,6 +433,15 @@ def run_ours(args):
                                        "rel_diff": abs(loss_fast - loss_32) / max(abs(loss_32), 1e-30)}}
         del m32, t32
 
+    # ---- BASELINE configs[4] beside it (torch front end, same ranks, batch sharded through DistributedDataParallel): a second,
+    # driver-visible throughput at every N.  Not part of `value`.
+    c5 = None
+    if not args.no_config5 and args.shard == "batch":
+        try:
+            c5 = measure_config5(args, dev, rank, world, local)
+        except Exception as e:  # noqa: BLE001 -- an extra leg must not cost the bench line
+            c5 = {"unavailable": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -523,6 +533,8 @@ def run_ours(args):
                                 "model figure, not a bound"},
         "kernel_ms_per_step": {k: v / args.steps for k, v in ktime.items()},
     }
+    if c5 is not None:
+        line["config5"] = c5
     if world == 1 and not args.no_cpu_baseline:
         v, cores, sample, _, ran = cpu_reference_images_per_s(args, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ran": ran}
@@ -538,14 +550,9 @@ def run_ours(args):
 
 
 def run_config5(args):
-    """BASELINE configs[4]: torchbnn SDENet training step (examples/torch/sdebnn_classification.py:34-46: cross-entropy +
-    kl_coeff * logqp, Adam) at `--batch` images per GPU, midpoint dt 0.05 (20 steps, 40 evaluations of the 26-conv y_net),
-    batch sharded over ranks: every rank integrates the SAME weight path (same Philox key, counter-based) on its own images;
-    the one collective is the gradient all-reduce, here torch's DistributedDataParallel (bucketed, overlapped with backward)."""
+    """`bench.py --config 5`: the config-5 line alone (see measure_config5)."""
     import torch
     import torch.distributed as dist
-    import torch.nn.functional as F
-    from bayesde_b200 import _lib, torch_models as tm
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -559,6 +566,27 @@ def run_config5(args):
     os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    line = measure_config5(args, dev, rank, world, local, full=True)
+    if rank == 0:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_config5(args, dev, rank, world, local, full=False):
+    """BASELINE configs[4]: torchbnn SDENet training step (examples/torch/sdebnn_classification.py:34-46: cross-entropy +
+    kl_coeff * logqp, Adam) at `--batch` images per GPU, midpoint dt 0.05 (20 steps, 40 evaluations of the 26-conv y_net),
+    batch sharded over ranks: every rank integrates the SAME weight path (same Philox key, counter-based) on its own images;
+    the one collective is the gradient all-reduce, here torch's DistributedDataParallel (bucketed, overlapped with backward).
+    Called on every rank (the process group, if any, is already up); returns the JSON object on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from bayesde_b200 import _lib, torch_models as tm
+
     L = _lib.lib()
     torch.manual_seed(0)
     hidden = 32
@@ -624,17 +652,9 @@ def run_config5(args):
     launches = L.bsde_launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps)
+    del net, opt
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    sys.stdout.flush()
-    os.dup2(saved_stdout, 1)
-    os.close(saved_stdout)
-    peaks = {}
-    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk):
-        peaks = json.load(open(pk))
+        return None
     tf32_peak = measure_tf32_peak(dev)
     flops_eval = sum(2 * (l["hout"] * l["wout"] if not l["transpose"] else l["hin"] * l["win"]) * 9 * (l["cin"] + 1) * l["cout"]
                      for l in model.y_net.layers)
@@ -657,15 +677,13 @@ def run_config5(args):
                          "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
                          "peak_source": "measured live in this run: cuBLAS 8192^3 TF32 matmul", "traffic": None,
                          "algorithmic_flops_per_step": alg, "flops_per_image_eval": flops_eval}}
-    if world == 1 and not args.no_cpu_baseline:
+    if full and world == 1 and not args.no_cpu_baseline:
         try:
             v5, cores5, sample5 = cpu_torch_reference_images_per_s(8)
             line["cpu_baseline"] = {"value": v5, "unit": UNIT, "cores": cores5, "kind": "port", "sample": sample5}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"unavailable": repr(e)}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

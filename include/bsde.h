@@ -359,6 +359,48 @@ int bsde_toy_em_bwd(const bsde_toy_desc* d, const float* d_ts, const float* d_zt
                     float* d_DA1, float* d_DA2, float* d_DF, float* d_H1, float* d_H2, float* d_GB1,
                     float* d_GB2, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * config 1 (JAX toy): SDELayer -- augmented_post_drift / augmented_prior_drift / augmented_diffusion integrated by _sdeint
+ * brax/_impl/layers.py:54-157,164-248, brax/utils/sdeint.py:8-60, examples/jax/sdebnn_toy1d.py:32-95
+ * ---------------------------------------------------------------------------------------- */
+
+/* State row of one MC sample: [w (P), x (B*D), kl (1)] (ravel order of layers.py:116-118,159-162).  driftx = CSL(H) act CSL(H) act
+ * CSL(D) on the rows of x with ITS WEIGHTS TAKEN FROM w (ravel_pytree order: per layer W [din][dout], b, w_t, w_tb, b_t, then the
+ * (beta,) leaf of a trainable swish); driftw = P -> H -> H -> P ConcatSquashLineartx stack (bsde_fw_params with nhid = 2,
+ * dims = {H, H}; W1 [P][H], Wm[0] [H][H], W4 [H][P]; beta1 / betam[0] for swish), optionally added to the prior drift
+ * (`diff_drift`, layers.py:272-292); prior drift -w (`prior_ou`) or 0; diffusion sigma on the w rows (`diffw`), 0 elsewhere.
+ * Per step (sdeint.py:13-22): eps ~ N(0, I_P);  u = (dw - prior) / sigma;
+ *   w += h dw + sqrt(h) sigma eps;   x += h driftx(w, t, x);   kl += h (sum u^2 / 2 + sum u_sg eps)
+ * where u_sg is u evaluated with stop_gradient(driftw parameters) when `stop_grad` (layers.py:81-112; a value-neutral change that
+ * only redirects gradients).  `prior_solve` = 1 integrates augmented_prior_drift instead (dw = prior drift, u = dw / sigma). */
+typedef struct {
+  int32_t S;             /* MC samples (the reference vmaps apply_fn over rngs, sdebnn_toy1d.py:127): one CTA each */
+  int32_t B, D, H;       /* rows of x, width of x (x_dim + aug_dim <= 16), hidden width of both nets (<= 128) */
+  int32_t nt;            /* time points, nt - 1 steps */
+  int32_t act;           /* bsde_act of both nets */
+  int32_t driftw, diffw, prior_ou, diff_drift, stop_grad;   /* `setting` of sdebnn_toy1d.py:186-198 */
+  int32_t prior_solve;
+  int32_t w0_per_sample; /* d_w0 is [S][P] instead of [P] */
+  float sigma;           /* diff_const */
+  int64_t P;             /* w_dim */
+  uint64_t seed;         /* in-kernel Philox stream (when d_eps is NULL): counter (p, step, sample / 4, stream_id) */
+  uint32_t stream_id;
+  uint32_t sample_offset;
+} bsde_sdelayer_desc;
+
+/* d_ts [nt]; d_w0 [P] or [S][P]; d_x0 [B*D] (the same inputs for every sample); d_eps [S][nt-1][P] unit normals of the w rows
+ * (exact-comparison mode) or NULL; d_traj [S][nt][P + B*D + 1] receives every state, row 0 = the initial state
+ * (`sdeint` returns rows 1.., `_sdeint` the last row). */
+int bsde_sdelayer_fwd(const bsde_sdelayer_desc* d, const bsde_fw_params* fw, const float* d_ts, const float* d_w0,
+                      const float* d_x0, const float* d_eps, float* d_traj, void* stream);
+
+/* Reverse pass.  Cotangents: d_gtraj [S][nt][P + B*D + 1] (every state) or NULL, d_gT [S][P + B*D + 1] (final state only) or
+ * NULL.  d_g0 [S][P + B*D + 1] receives dL/d(initial state) per sample.  gfw: accumulators of the driftw parameter gradients
+ * with a LEADING SAMPLE DIMENSION ([S][P][H], [S][H], ...; zero them before the call; the caller sums over samples). */
+int bsde_sdelayer_bwd(const bsde_sdelayer_desc* d, const bsde_fw_params* fw, const float* d_ts, const float* d_eps,
+                      const float* d_traj, const float* d_gtraj, const float* d_gT, float* d_g0, const bsde_fw_params* gfw,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,7 +161,7 @@ def conv_general_dilated_nhwc(x, w, stride, pads, lhs_dilation=1):
         xn = xd
     (pt, pb), (pl, pr) = pads
     xn = F.pad(xn, (pl, pr, pt, pb))
-    out = F.conv2d(xn, w.permute(3, 2, 0, 1), stride=stride)
+    out = F.conv2d(xn.contiguous(), w.permute(3, 2, 0, 1).contiguous(), stride=stride)   # (torch's CPU conv backward needs contiguous weights)
     return out.permute(0, 2, 3, 1)
 
 
@@ -235,14 +235,15 @@ def fx_apply(flat_w, x, t, layout, actfn="softplus"):
 
 
 def concat_squash_linear(p, x, t):
-    W, b, w_t, w_tb, b_t = p
+    W, b, w_t, w_tb, b_t = p[:5]
     out = x @ W + b  # :89
     out = out * torch.sigmoid(w_t * t + w_tb)  # :91
     return out + b_t * t  # :93
 
 
 def fw_apply(fw_layers, w, t, actfn="softplus"):
-    """fw_layers: list of (W,b,w_t,w_tb,b_t), one per ConcatSquashLinear; act between.
+    """fw_layers: list of (W,b,w_t,w_tb,b_t), one per ConcatSquashLinear; act between.  With the trainable swish
+    (arch.py:14-29,41-42) every layer but the last carries the beta vector of the activation that follows it as a sixth entry.
 
     With ou_dw=True the reference wraps the MLP in arch.Additive but, because of the
     (out,t)/(t,out) unpack mismatch (quirk Q3; arch.py:100-103 vs diffeq_layers.py:95),
@@ -251,13 +252,14 @@ def fw_apply(fw_layers, w, t, actfn="softplus"):
     for i, p in enumerate(fw_layers):
         h = concat_squash_linear(p, h, t)
         if i < len(fw_layers) - 1:
-            h = act(actfn, h)
+            h = act(actfn, h, p[5] if len(p) > 5 else None)
     return h
 
 
-def init_fw(P, fw_dims, gen, dtype=torch.float32, last_std=0.0):
+def init_fw(P, fw_dims, gen, dtype=torch.float32, last_std=0.0, actfn="softplus", beta_jitter=0.0):
     """arch.py:34-74 + diffeq_layers.py:76-82 shapes; he-normal W, normal(1e-2) others;
-    last layer zeros (arch.py:51,59) unless last_std>0 (SURVEY §8.4 synthetic init)."""
+    last layer zeros (arch.py:51,59) unless last_std>0 (SURVEY §8.4 synthetic init).  actfn="swish": beta = 0.5 (arch.py:14)
+    as a sixth entry of every layer but the last (+ `beta_jitter` * N(0,1) so that tests see distinct values)."""
     dims = [P] + list(fw_dims) + [P]
     layers = []
     for i in range(len(dims) - 1):
@@ -268,8 +270,10 @@ def init_fw(P, fw_dims, gen, dtype=torch.float32, last_std=0.0):
         else:
             std_w, std_o = math.sqrt(2.0 / din), 1e-2
         mk = lambda *s, sd: (torch.randn(*s, generator=gen, dtype=torch.float64) * sd).to(dtype)
-        layers.append((mk(din, dout, sd=std_w), mk(dout, sd=std_o), mk(dout, sd=std_o),
-                       mk(dout, sd=std_o), mk(dout, sd=std_o)))
+        lay = (mk(din, dout, sd=std_w), mk(dout, sd=std_o), mk(dout, sd=std_o), mk(dout, sd=std_o), mk(dout, sd=std_o))
+        if actfn == "swish" and not last:
+            lay = lay + ((0.5 + mk(dout, sd=beta_jitter).double()).to(dtype),)
+        layers.append(lay)
     return layers
 
 
@@ -412,7 +416,7 @@ class SDEBNNClassifier:
         params = []
         for blk in self.blocks():
             w0 = init_fx(blk.layout, blk.P, gen, dtype)
-            fw = init_fw(blk.P, self.fw_dims, gen, dtype, last_std=fw_last_std)
+            fw = init_fw(blk.P, self.fw_dims, gen, dtype, last_std=fw_last_std, actfn=blk.fw_actfn)
             params.append((w0, fw))
             # brax.py:38-41: the stale vector is a fresh fx.init from PRNGKey(0)
             blk.w_stale = init_fx(blk.layout, blk.P, torch.Generator().manual_seed(1000 + len(params)), dtype)

@@ -7,6 +7,7 @@ Tolerances (fp32 path, `math="fp32"`; the reference states none -- SURVEY.md 8.3
   * sum-KL, loss:                                    rtol 1e-4
   * gradients vs fp64 oracle autograd:               rtol 1e-3 (atol scaled to the tensor's max)
 """
+import os
 import ctypes as C
 import math
 
@@ -34,6 +35,16 @@ def _close(a, b, rtol, atol, what=""):
 def _gclose(a, b, rtol=1e-3, what=""):
     b64 = b.detach().double().cpu()
     _close(a, b, rtol, rtol * 1e-2 * float(b64.abs().max()) + 1e-12, what)
+
+
+def _mark(msg):
+    """Progress marker (BSDE_TEST_MARKS=<file>): written and flushed BEFORE a launch, so that a hung kernel can be named."""
+    path = os.environ.get("BSDE_TEST_MARKS")
+    if path:
+        with open(path, "a") as f:
+            f.write(msg + "\n")
+            f.flush()
+            os.fsync(f.fileno())
 
 
 def _conv_struct(L):
@@ -100,9 +111,9 @@ def _product_fw_params(fw_layers, device):
     """oracle list of 5-tuples -> reference-shaped pytree ((), [lay, (), ..., lay]) on device."""
     tree = []
     for i, lay in enumerate(fw_layers):
-        tree.append(tuple(t.float().to(device).contiguous().requires_grad_(True) for t in lay))
-        if i < len(fw_layers) - 1:
-            tree.append(())
+        tree.append(tuple(t.float().to(device).contiguous().requires_grad_(True) for t in lay[:5]))
+        if i < len(fw_layers) - 1:   # the activation's parameters: () or the trainable swish's (beta,)
+            tree.append(tuple(t.float().to(device).contiguous().requires_grad_(True) for t in lay[5:]))
     return ((), tree)
 
 
@@ -112,7 +123,11 @@ def _block_case(S=2, B=2, H=8, C_in=5, fx_dim=8, nsteps=6, sigma=0.2, stl=False,
     blk = jp.SDEBNNBlock((B, H, H, C_in), 0, fx_dim, fx_actfn, fw_actfn, sigma, stl, nsteps,
                          time_grid_mode=time_grid)
     w0 = jp.init_fx(blk.layout, blk.P, g, torch.float64)
-    fw = jp.init_fw(blk.P, fw_dims, g, torch.float64, last_std=0.05)
+    fw = jp.init_fw(blk.P, fw_dims, g, torch.float64, last_std=0.05, actfn=fw_actfn, beta_jitter=0.2)
+    if fx_actfn == "swish":   # distinct beta per channel (the init value is the constant 0.5)
+        for e in blk.layout:
+            if e["kind"] == "beta":
+                w0[e["off"]:e["off"] + e["n"]] += 0.3 * torch.randn(e["n"], generator=g, dtype=torch.float64)
     x = torch.randn(S, B, H, H, C_in, generator=g, dtype=torch.float64)
     dW = torch.stack([jp.sample_increments(blk.P, nsteps, g, torch.float64, time_grid) for _ in range(S)])
     return blk, w0, fw, x, dW
@@ -131,7 +146,7 @@ def _oracle_block(blk, w0, fw, x, dW, gx_seed=1, kl_w=1e-3):
     g = torch.Generator().manual_seed(gx_seed)
     cot = torch.randn(xo.shape, generator=g, dtype=torch.float64)
     obj = (xo * cot).sum() + kl_w * kl.sum()
-    grads = torch.autograd.grad(obj, [x, w0] + [t for lay in fw for t in lay])
+    grads = torch.autograd.grad(obj, [x, w0] + [t for lay in fw for t in lay[:5]] + [lay[5] for lay in fw if len(lay) > 5])
     return xo, kl, wt, cot, grads
 
 
@@ -140,16 +155,23 @@ def _oracle_block(blk, w0, fw, x, dW, gx_seed=1, kl_w=1e-3):
                                 dict(fx_actfn="tanh", fw_actfn="tanh", fw_dims=(2,)),
                                 dict(fx_actfn="elu", fw_actfn="elu", fw_dims=(2, 8, 8, 2), sigma=1e-2),
                                 dict(fx_actfn="rbf", fw_actfn="rbf", fw_dims=(2, 8, 2)),
-                                dict(fx_actfn="rbf", fw_actfn="softplus", stl=True, S=1, B=3, H=4, C_in=20, fx_dim=16)])
+                                dict(fx_actfn="rbf", fw_actfn="softplus", stl=True, S=1, B=3, H=4, C_in=20, fx_dim=16),
+                                # trainable swish (arch.py:14-29): beta of f_x lives in w(t), beta of f_w is a parameter vector
+                                dict(fx_actfn="swish", fw_actfn="swish", fw_dims=(2, 8, 2)),
+                                dict(fx_actfn="swish", fw_actfn="softplus", stl=True, S=1, B=3, H=4, C_in=20, fx_dim=16),
+                                dict(fx_actfn="softplus", fw_actfn="swish", fw_dims=(2,)),
+                                dict(fx_actfn="swish", fw_actfn="swish", fw_dims=(1, 8, 8, 1), remat=True)])
 def test_sdebnn_block_forward_backward(built_lib, kw):
     """One SDEBNN block through the reference-shaped API vs the oracle: x_T, per-sample KL, the whole
     w trajectory (full_output), and gradients w.r.t. x, w0 and every f_w tensor."""
     from bayesde_b200 import arch, brax
+    kw = dict(kw)
+    remat = kw.pop("remat", False)
     blk, w0, fw, x, dW = _block_case(**kw)
     stl = kw.get("stl", False)
     fw_layer = arch.MLP(kw.get("fw_dims", (2, 16, 2)), actfn=kw.get("fw_actfn", "softplus"), xt=True, ou_dw=True)
     layer = brax.SDEBNN(0, blk.layout[0]["cout"], kw.get("fx_actfn", "softplus"), fw_layer, diff_coef=blk.diff_coef,
-                        stl=stl, xt=True, nsteps=blk.nsteps, time_grid=blk.time_grid_mode)
+                        stl=stl, xt=True, nsteps=blk.nsteps, time_grid=blk.time_grid_mode, remat=remat)
     # the oracle's stale vector must be the product's (fx.init(PRNGKey(0)) stand-in), brax.py:38-41
     _, (w_stale_like, _, _) = layer.init(0, tuple(x.shape[1:]))
     blk.w_stale = w_stale_like.double()
@@ -163,9 +185,11 @@ def test_sdebnn_block_forward_backward(built_lib, kw):
     _close(info["sdebnn_w"], wt_r, 1e-5, 1e-6, "w trajectory")
     _close(kl, kl_r, 1e-4, 1e-6, "sum KL")
     obj = (xo * cot.float().to(DEV)).sum() + 1e-3 * kl.sum()
-    leaves = [xd, w0d] + [t for lay in arch.fw_layers(fwd) for t in lay]
+    leaves = [xd, w0d] + [t for lay in arch.fw_layers(fwd) for t in lay] + arch.fw_betas(fwd)
     grads = torch.autograd.grad(obj, leaves)
-    names = ["x", "w0"] + [f"fw[{i}].{n}" for i in range(len(fw)) for n in ("W", "b", "w_t", "w_tb", "b_t")]
+    names = (["x", "w0"] + [f"fw[{i}].{n}" for i in range(len(fw)) for n in ("W", "b", "w_t", "w_tb", "b_t")]
+             + [f"fw[{i}].beta" for i in range(len(arch.fw_betas(fwd)))])
+    assert len(grads) == len(grads_r)
     # rbf: the data-gradient epilogues rebuild the pre-activation from the stored activation (sign in the last mantissa bit,
     # |x| = sqrt(-ln a), which loses relative precision near a = 1): 5e-3 instead of 1e-3 (measured worst entry 1.5e-5 of max)
     gt = 5e-3 if kw.get("fx_actfn") == "rbf" else 1e-3
@@ -434,6 +458,7 @@ def test_tconv_tc_layers_forward_and_dgrad(built_lib, C_in, fx_dim, H, B):
         nb = L.bsde_tconv_fwd_workspace_bytes(C.byref(cs), S, 1)
         assert nb > 0
         ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+        _mark(f"tc layers [{C_in}-{fx_dim}-{H}-{B}] layer {li} forward")
         st = L.bsde_tconv_fwd(C.byref(cs), S, B, _lib.ptr(xd), _lib.ptr(wd), P, t, 0, _lib.EPI_BIAS, 1.0, None,
                               _lib.ptr(out), 1, C.c_void_p(ws.data_ptr()), nb, _lib.stream_ptr())
         _lib.check(st, "tconv_fwd tc")
@@ -453,6 +478,7 @@ def test_tconv_tc_layers_forward_and_dgrad(built_lib, C_in, fx_dim, H, B):
         gx = torch.zeros(x.shape, device=DEV)
         nb = L.bsde_tconv_fwd_workspace_bytes(C.byref(D), S, 1)
         ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+        _mark(f"tc layers [{C_in}-{fx_dim}-{H}-{B}] layer {li} dgrad")
         st = L.bsde_tconv_fwd(C.byref(D), S, B, _lib.ptr(dy.float().to(DEV).contiguous()), _lib.ptr(wd), P, t, 0,
                               _lib.EPI_ACCUM, 1.0, _lib.ptr(gx), _lib.ptr(gx), 1, C.c_void_p(ws.data_ptr()), nb,
                               _lib.stream_ptr())
@@ -471,6 +497,7 @@ def test_tconv_tc_layers_forward_and_dgrad(built_lib, C_in, fx_dim, H, B):
         gwd = torch.zeros(S, P, device=DEV)
         nb = L.bsde_tconv_wgrad_workspace_bytes(C.byref(cs), S, B)
         ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+        _mark(f"tc layers [{C_in}-{fx_dim}-{H}-{B}] layer {li} wgrad")
         st = L.bsde_tconv_wgrad(C.byref(cs), S, B, _lib.ptr(xd), _lib.ptr(dy.float().to(DEV).contiguous()), t, 0.5,
                                 _lib.ptr(gwd), P, 1, C.c_void_p(ws.data_ptr()), nb, _lib.stream_ptr())
         _lib.check(st, "tconv_wgrad tc")
@@ -481,7 +508,8 @@ def test_tconv_tc_layers_forward_and_dgrad(built_lib, C_in, fx_dim, H, B):
 
 @pytest.mark.parametrize("kw", [dict(), dict(S=1, B=3, H=4, C_in=20, fx_dim=16, fw_dims=(1, 8, 1)),
                                 dict(S=2, B=4, H=8, C_in=80, fx_dim=64, nsteps=4),
-                                dict(fx_actfn="rbf", fw_actfn="rbf"), dict(fx_actfn="rbf", S=2, B=4, H=8, C_in=80, fx_dim=64, nsteps=4)])
+                                dict(fx_actfn="rbf", fw_actfn="rbf"), dict(fx_actfn="rbf", S=2, B=4, H=8, C_in=80, fx_dim=64, nsteps=4),
+                                dict(fx_actfn="swish", fw_actfn="swish", fx_dim=64), dict(fx_actfn="swish", S=2, B=4, H=8, C_in=20, fx_dim=64, nsteps=4)])
 def test_sdebnn_block_tc(built_lib, kw):
     """One SDEBNN block with math="tc" vs the fp64 oracle.  Stated tolerance (TF32 operands, 10-bit
     mantissa, nsteps-1 Euler steps): 5e-3 * max|ref| on x_T, 2e-2 * max|ref| on every gradient (the reverse
@@ -501,8 +529,9 @@ def test_sdebnn_block_tc(built_lib, kw):
     _close(info["sdebnn_w"], wt_r, 1e-5, 1e-6, "w trajectory")
     _close(kl, kl_r, 1e-4, 1e-6, "sum KL")
     obj = (xo * cot.float().to(DEV)).sum() + 1e-3 * kl.sum()
-    leaves = [xd, w0d] + [t for lay in arch.fw_layers(fwd) for t in lay]
+    leaves = [xd, w0d] + [t for lay in arch.fw_layers(fwd) for t in lay] + arch.fw_betas(fwd)
     grads = torch.autograd.grad(obj, leaves)
+    assert len(grads) == len(grads_r)
     for i, (a, b) in enumerate(zip(grads, grads_r)):
         # rbf: act' = -2 x a changes sign with the pre-activation, so the two-element gate gradients of the first f_w layer are sums
         # with heavy cancellation (|ref| ~ 1e-4) and TF32 rounding shows at 4e-2 of their own maximum: 8e-2
@@ -815,3 +844,128 @@ def test_config3_mnist_shape_and_q10(built_lib):
         _gclose(p.grad, gr, 2e-3, f"param {i} grad")
     with pytest.raises(AssertionError, match="same input and output shapes"):
         SDEBNNClassifier(nsamples=1, device=DEV, input_size=(28, 28, 1), aug=2, nblocks=(2, 2, 2), fx_dim=8, fw_dims=(2, 8, 2), nsteps=4)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# config 1 (row a20): SDELayer with the REFERENCE's dynamics (augmented_post_drift / augmented_prior_drift /
+# augmented_diffusion, brax/_impl/layers.py:54-157,164-248), one fused launch per solve (csrc/sdelayer.cu)
+# ---------------------------------------------------------------------------------------------------------
+def _toy_case(B, D, H, actfn, S, nt, seed=0, **flags):
+    from oracle import jax_toy as jt
+    g_ = torch.Generator().manual_seed(seed)
+    setting = jt.ToySetting(**flags)
+    orc = jt.SDELayerOracle(B, D, H, actfn, setting)
+    w0, lays = jt.init_toy(B, D, H, actfn, g_, driftw_scale=0.5, last_std=0.3, beta_jitter=0.2)
+    x = torch.randn(B, D, generator=g_, dtype=torch.float64)
+    eps = torch.randn(S, nt - 1, orc.P, generator=g_, dtype=torch.float64)
+    return orc, setting, w0, lays, x, eps
+
+
+def _toy_product_params(orc, w0, lays, setting, dev):
+    """Reference-shaped parameter tuple (W0 tree, W_driftwt, W_difft, W_priorwt, W0_post) from the oracle's containers."""
+    W0 = []
+    for i, e in enumerate(orc.layout):
+        din, dout = e["din"], e["dout"]
+        W0.append((w0[e["W"]:e["W"] + din * dout].reshape(din, dout), w0[e["b"]:e["b"] + dout], w0[e["wt"]:e["wt"] + dout],
+                   w0[e["wtb"]:e["wtb"] + dout], w0[e["bt"]:e["bt"] + dout]))
+        if i < 2:
+            W0.append((w0[e["beta"]:e["beta"] + dout],) if e["beta"] >= 0 else ())
+    W0 = [tuple(t.float().to(dev).contiguous().requires_grad_(True) for t in q) for q in W0]
+    tree = []
+    for i, lay in enumerate(lays):
+        tree.append(tuple(t.float().to(dev).contiguous().requires_grad_(True) for t in lay[:5]))
+        if i < 2:
+            tree.append(tuple(t.float().to(dev).contiguous().requires_grad_(True) for t in lay[5:]))
+    Wd = ((), tree) if setting["diff_drift"] else tree
+    return (W0, Wd, (), (), None)
+
+
+@pytest.mark.parametrize("kw", [dict(B=100, D=3, H=64, actfn="swish", S=2),                      # config 1 sizes: P = 5132
+                                dict(B=7, D=3, H=16, actfn="swish", S=3, stop_grad=False),
+                                dict(B=5, D=2, H=8, actfn="softplus", S=2, diff_drift=False),
+                                dict(B=5, D=3, H=32, actfn="tanh", S=1, prior_driftw="0"),
+                                dict(B=260, D=3, H=64, actfn="swish", S=1)])                      # rows of x in several chunks
+def test_jax_toy_sdelayer_vs_oracle(built_lib, kw):
+    """`brax_layers.SDELayer` (AugmentedLayer + SDELayer of examples/jax/sdebnn_toy1d.py:32-95) against the fp64 restatement of the
+    reference's own functions (oracle/jax_toy.py) on the same unit normals: posterior and prior (x, w, kl) at t = 1, and the
+    gradients of the toy's ELBO-shaped objective w.r.t. every leaf of W0 and of the posterior drift net W_driftwt -- including the
+    sticking-the-landing split (stop_gradient on the drift parameters in the second KL term, layers.py:81-112)."""
+    from bayesde_b200 import brax_layers as BL
+    kw = dict(kw)
+    B, D, H, actfn, S = (kw.pop(k) for k in ("B", "D", "H", "actfn", "S"))
+    orc, setting, w0, lays, x, eps = _toy_case(B, D, H, actfn, S, 20, **kw)
+    # oracle
+    w0r = w0.clone().requires_grad_(True)
+    laysr = [tuple(t.clone().requires_grad_(True) for t in lay) for lay in lays]
+    outs = [orc.apply(w0r, laysr, x, eps[s]) for s in range(S)]
+    xr, wr, klr, pxr, pwr, pklr = (torch.stack([o[i] for o in outs]) for i in range(6))
+    cot = torch.randn(xr.shape, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    obj_r = (xr[..., -1:] * cot[..., -1:]).sum() + 0.3 * klr.mean() + 0.1 * (wr ** 2).sum() + 0.05 * pklr.sum() + (pxr * cot).sum()
+    leaves_r = [w0r] + [t for lay in laysr for t in lay[:5]] + [lay[5] for lay in laysr if len(lay) > 5]
+    grads_r = torch.autograd.grad(obj_r, leaves_r)
+    # product
+    prior_layer = BL.DiffEqWrappertx(BL.Affine(-1, 0.0)) if setting["prior_driftw"] == "ou" else BL.DiffEqWrappertx(BL.Const(0.0))
+    act_l = BL.get_activn(actfn)
+    act_l = act_l(H) if actfn == "swish" else act_l
+    mk = lambda out: BL.serial_tx(BL.ConcatSquashLineartx(H), BL.DiffEqWrappertx(act_l), BL.ConcatSquashLineartx(H),
+                                  BL.DiffEqWrappertx(act_l), BL.ConcatSquashLineartx(out))
+    driftw = mk(orc.P)
+    if setting["diff_drift"]:
+        driftw = BL.Additive(prior_layer, driftw)
+    sde = BL.SDELayer(mk(D), prior_layer, driftw, BL.DiffEqWrappertx(BL.Const(setting["diff_const"])), D, orc.P,
+                      dict(setting, priorw0_sigma=-1.0, driftw_scale=1.0))
+    params = _toy_product_params(orc, w0, lays, setting, DEV)
+    xo, wo, klo, pxo, pwo, pklo = sde.apply(params, x.float().to(DEV), eps.float().to(DEV))
+    _close(xo, xr, 2e-4, 1e-5, "x(1)")
+    _close(wo, wr, 1e-4, 1e-5, "w(1)")
+    _close(klo, klr, 2e-4, 1e-4, "kl(1)")
+    _close(pxo, pxr, 2e-4, 1e-5, "prior x(1)")
+    _close(pwo, pwr, 1e-4, 1e-5, "prior w(1)")
+    _close(pklo, pklr, 2e-4, 1e-4, "prior kl(1)")
+    c = cot.float().to(DEV)
+    obj = (xo[..., -1:] * c[..., -1:]).sum() + 0.3 * klo.mean() + 0.1 * (wo ** 2).sum() + 0.05 * pklo.sum() + (pxo * c).sum()
+    W0, Wd = params[0], params[1]
+    tree = Wd[1] if setting["diff_drift"] else Wd
+    leaves = [t for q in W0 for t in q] + [t for q in tree if len(q) == 5 for t in q] + [q[0] for q in tree if len(q) == 1]
+    grads = torch.autograd.grad(obj, leaves)
+    # the oracle's W0 gradient is one flat vector in ravel order = the concatenation of the product's W0 leaves
+    gw0 = torch.cat([g.reshape(-1) for g in grads[:len([t for q in W0 for t in q])]])
+    _gclose(gw0, grads_r[0], 2e-3, "grad W0")
+    for i, (a, b) in enumerate(zip(grads[len([t for q in W0 for t in q]):], grads_r[1:])):
+        _gclose(a, b, 2e-3, f"grad W_driftwt leaf {i}")
+
+
+def test_jax_toy_sdelayer_entire_philox_and_mlp(built_lib):
+    """entire=True returns the 89-row trajectories on linspace(0, 1, 90) (layers.py:233-240) -- checked against the oracle --
+    and the Philox route through the script-level `mlp()` / `elbo()` is deterministic per seed, differentiable and finite."""
+    from bayesde_b200 import brax_layers as BL
+    orc, setting, w0, lays, x, _ = _toy_case(6, 3, 16, "swish", 1, 90)
+    eps = torch.randn(1, 89, orc.P, generator=torch.Generator().manual_seed(11), dtype=torch.float64)
+    ref = orc.apply(w0, lays, x, eps[0], nt=90, entire=True)
+    act_l = BL.get_activn("swish")(16)
+    mk = lambda out: BL.serial_tx(BL.ConcatSquashLineartx(16), BL.DiffEqWrappertx(act_l), BL.ConcatSquashLineartx(16),
+                                  BL.DiffEqWrappertx(act_l), BL.ConcatSquashLineartx(out))
+    prior_layer = BL.DiffEqWrappertx(BL.Affine(-1, 0.0))
+    sde = BL.SDELayer(mk(3), prior_layer, BL.Additive(prior_layer, mk(orc.P)), BL.DiffEqWrappertx(BL.Const(0.1)), 3, orc.P,
+                      dict(setting, priorw0_sigma=-1.0, driftw_scale=1.0))
+    out = sde.apply(_toy_product_params(orc, w0, lays, setting, DEV), x.float().to(DEV), eps[0].float().to(DEV), entire=True)
+    for name, a, b in zip(("xs", "ws", "kls", "prior xs", "prior ws", "prior kls"), out, ref):
+        assert a.shape == b.shape and a.shape[0] == 89
+        _close(a, b, 5e-4, 1e-4, f"entire {name}")
+    # script level: mlp() + elbo() with the in-kernel Philox stream
+    st = dict(driftw=True, diffw=True, diff_const=0.1, prior_driftw="ou", driftw_scale=0.1, stop_grad=True, aug_dim=2,
+              priorw0_sigma=-1.0, diff_drift=True)
+    (init_fn, apply_fn), P = BL.mlp(0, 1, 64, "swish", st)
+    assert P == 5132                                        # SURVEY 8.1 a20
+    _, params = init_fn(1, (-1, 1))
+    to_dev = lambda tr: BL._tree_map(lambda t: t.to(DEV).requires_grad_(True), tr)
+    params = [(), tuple(to_dev(p) if p is not None else None for p in params[1])]
+    xin = torch.linspace(-1, 1, 100, device=DEV).reshape(100, 1)
+    tgt = torch.cos(3 * xin)
+    l1 = BL.elbo(params, (xin, tgt), apply_fn, 7, 1.0, num_samples=10)
+    l2 = BL.elbo(params, (xin, tgt), apply_fn, 7, 1.0, num_samples=10)
+    l3 = BL.elbo(params, (xin, tgt), apply_fn, 8, 1.0, num_samples=10)
+    assert torch.equal(l1, l2) and not torch.equal(l1, l3) and torch.isfinite(l1)
+    leaves = [t for q in params[1][0] for t in q] + [t for q in params[1][1][1] for t in q]
+    grads = torch.autograd.grad(l1, leaves)
+    assert all(torch.isfinite(g).all() for g in grads) and any(g.abs().max() > 0 for g in grads)

@@ -35,12 +35,13 @@ def test_struct_sizes_match_c(built_lib, tmp_path):
     """ctypes mirrors of the POD structs have the C compiler's sizes."""
     from bayesde_b200 import _lib
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "bsde.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(bsde_fw_params),'
-                   'sizeof(bsde_wsde_desc), sizeof(bsde_conv_layer), sizeof(bsde_xpath_desc));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "bsde.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(bsde_fw_params),'
+                   'sizeof(bsde_wsde_desc), sizeof(bsde_conv_layer), sizeof(bsde_xpath_desc), sizeof(bsde_sdelayer_desc));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
-    assert sizes == [C.sizeof(_lib.FwParams), C.sizeof(_lib.WsdeDesc), C.sizeof(_lib.ConvLayer), C.sizeof(_lib.XpathDesc)]
+    assert sizes == [C.sizeof(_lib.FwParams), C.sizeof(_lib.WsdeDesc), C.sizeof(_lib.ConvLayer), C.sizeof(_lib.XpathDesc),
+                     C.sizeof(_lib.SDELayerDesc)]
 
 
 def test_no_cpu_fallback_and_error_mapping(built_lib):
@@ -118,6 +119,37 @@ def test_mlp_apply_quirk_q3_and_param_tree():
         arch.MLP((2, 8, 2), xt=False)
     with pytest.raises(ValueError):
         arch.MLP((8, 8, 2), xt=True)
+
+
+def test_swish_param_tree_and_layout_match_oracle():
+    """Trainable swish (arch.py:14-29): f_w carries a (beta,) = 0.5 leaf after every hidden layer (arch.py:41-42), f_x's beta
+    vectors live in the flat weight vector right after the conv they follow (ravel_pytree order, arch.py:172-188)."""
+    from bayesde_b200 import arch
+    fw = arch.MLP((2, 8, 2), actfn="swish", xt=True, ou_dw=True, nonzero_w=0.05, nonzero_b=0.05)
+    _, params = fw.init(3, (50,))
+    tree = params[1]
+    assert len(tree) == 7 and [len(q) for q in tree] == [5, 1, 5, 1, 5, 1, 5]
+    assert all(torch.equal(q[0], torch.full_like(q[0], 0.5)) for q in tree if len(q) == 1)
+    assert [b.numel() for b in arch.fw_betas(params)] == [2, 8, 2] and len(arch.fw_layers(params)) == 4
+    with torch.no_grad():
+        for b in arch.fw_betas(params):
+            b += 0.3 * torch.randn(b.shape)
+    w, t = torch.randn(50), torch.tensor(0.3)
+    out, _ = fw.apply(params, (w, t))
+    lays, betas = arch.fw_layers(params), arch.fw_betas(params)
+    ref = jp.fw_apply([lay + ((betas[i],) if i < len(betas) else ()) for i, lay in enumerate(lays)], w, t, "swish")
+    assert torch.allclose(out, ref)
+    for bt, cin in ((0, 5), (1, 20), (2, 80)):
+        spec = arch.FxSpec(bt, (1, 8, 8, cin), 64, "swish")
+        lay, P = jp.fx_layout(bt, cin, 64, "swish")
+        assert spec.P == P
+        convs, betas_o = [e for e in lay if e["kind"] == "conv"], [e for e in lay if e["kind"] == "beta"]
+        assert [L["w_off"] for L in spec.layers] == [e["w_off"] for e in convs]
+        assert [L["beta_off"] for L in spec.layers[:-1]] == [e["off"] for e in betas_o] and spec.layers[-1]["beta_off"] == -1
+        w0 = spec.init(0)
+        assert all(torch.equal(w0[e["off"]:e["off"] + 64], torch.full((64,), 0.5)) for e in betas_o)
+    with pytest.raises(KeyError):
+        arch.FxSpec(0, (1, 8, 8, 5), 64, "gelu")
 
 
 def test_classifier_parameter_count_and_split_determinism():

@@ -254,3 +254,62 @@ def test_torch_toy_oracle_matches_reference_run(tag):
         ref = torch.tensor(g[f"{tag}_g_" + k.replace("layers.0", "layers.0.module").replace("layers.1", "layers.1.module").replace(
             "layers.2", "layers.2.module").replace("layers.3", "layers.3.module").replace("layers.4", "layers.4.module")])
         assert torch.allclose(v.grad, ref, rtol=1e-3, atol=1e-6 + 1e-4 * ref.abs().max().item()), k
+
+
+def test_jax_toy_oracle_matches_layer_objects_and_stl_split():
+    """oracle/jax_toy.py (flat ravel-order offsets) against the host-side layer OBJECTS of bayesde_b200.brax_layers evaluated the
+    way brax/_impl/layers.py:54-118 composes them (driftx on the unravelled pytree, Additive(prior, driftw), Const diffusion):
+    two differently structured statements of the same functions must agree; and the sticking-the-landing switch changes no value
+    but removes the eps-term's gradient w.r.t. the drift parameters only (layers.py:81-112)."""
+    from oracle import jax_toy as jt
+    from bayesde_b200 import brax_layers as BL
+    B, D, H = 4, 3, 8
+    g = torch.Generator().manual_seed(0)
+    act_l = BL.get_activn("swish")(H)
+    mk = lambda out: BL.serial_tx(BL.ConcatSquashLineartx(H), BL.DiffEqWrappertx(act_l), BL.ConcatSquashLineartx(H),
+                                  BL.DiffEqWrappertx(act_l), BL.ConcatSquashLineartx(out))
+    driftx = mk(D)
+    _, W0 = driftx.init(1, (-1, D))
+    W0 = [tuple(t.double() + (0.2 * torch.randn(t.shape, generator=g, dtype=torch.float64) if len(q) == 1 else 0) for t in q) for q in W0]
+    flat = torch.cat([t.reshape(-1) for q in W0 for t in q])
+    orc = jt.SDELayerOracle(B, D, H, "swish", jt.ToySetting())
+    assert flat.numel() == orc.P
+    prior = BL.DiffEqWrappertx(BL.Affine(-1, 0.0))
+    driftw = BL.Additive(prior, mk(orc.P))
+    _, Wd = driftw.init(2, (-1, orc.P))
+    Wd = BL._tree_map(lambda t: t.double(), Wd)
+    with torch.no_grad():
+        Wd[1][-1][0].normal_(0, 0.1, generator=g)   # the zero-initialised last layer would make the drift trivial
+    x = torch.randn(B, D, generator=g, dtype=torch.float64)
+    t = torch.tensor(0.37, dtype=torch.float64)
+    eps = torch.randn(orc.P, generator=g, dtype=torch.float64)
+    # layer objects, composed as layers.py:54-118
+    _, dxt = driftx.apply(W0, (t, x))
+    _, dw = driftw.apply(Wd, (t, flat))
+    _, pw = prior.apply((), (t, flat))
+    u = (dw - pw) / 0.1
+    dkl = (u ** 2 / 2).sum() + (u * eps).sum()
+    lays = [q for q in Wd[1] if len(q) == 5]
+    betas = [q[0] for q in Wd[1] if len(q) == 1]
+    lays_o = [lay + ((betas[i],) if i < 2 else ()) for i, lay in enumerate(lays)]
+    aug = torch.cat([flat, x.reshape(-1), torch.zeros(1, dtype=torch.float64)])
+    f = orc.augmented_post_drift(lays_o, t, aug, eps)
+    assert torch.allclose(f[:orc.P], dw, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(f[orc.P:orc.P + B * D].reshape(B, D), dxt, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(f[-1], dkl, rtol=1e-12, atol=1e-12)
+    gd = orc.augmented_diffusion(t, aug)
+    assert torch.equal(gd[:orc.P], torch.full((orc.P,), 0.1, dtype=torch.float64)) and float(gd[orc.P:].abs().max()) == 0.0
+    # STL: same value, different gradient w.r.t. the drift parameters, identical gradient path through w of the first term
+    W = lays_o[-1][0].clone().requires_grad_(True)
+    lays_g = lays_o[:-1] + [(W,) + lays_o[-1][1:]]
+    kl_stl = orc.augmented_post_drift(lays_g, t, aug, eps)[-1]
+    orc2 = jt.SDELayerOracle(B, D, H, "swish", jt.ToySetting(stop_grad=False))
+    kl_full = orc2.augmented_post_drift(lays_g, t, aug, eps)[-1]
+    assert torch.allclose(kl_stl, kl_full, rtol=1e-13)
+    (g_stl,), (g_full,) = torch.autograd.grad(kl_stl, W), torch.autograd.grad(kl_full, W)
+    u_ = orc2.augmented_post_drift(lays_g, t, aug, torch.zeros_like(eps))[-1]     # eps = 0: only sum(u^2)/2
+    (g_u2,) = torch.autograd.grad(u_, W)
+    assert torch.allclose(g_stl, g_u2, rtol=1e-10, atol=1e-12) and not torch.allclose(g_full, g_u2, rtol=1e-3)
+    # prior solve: dw = -w, u = -w / sigma (layers.py:120-143)
+    fp = orc.augmented_prior_drift(t, aug, eps)
+    assert torch.allclose(fp[:orc.P], -flat) and torch.allclose(fp[-1], ((flat / 0.1) ** 2 / 2).sum() - (flat / 0.1 * eps).sum())
