@@ -13,6 +13,9 @@ namespace bsde {
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+static thread_local int g_sm_budget = 148;
+int sm_budget() { return g_sm_budget; }
+void set_sm_budget(int n) { g_sm_budget = n < 1 ? 1 : (n > 148 ? 148 : n); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -297,6 +300,40 @@ static int prepack_all(const bsde_xpath_desc* d, int backward, bool need_fwd_for
   return 0;
 }
 
+// side stream + events of the two-stream reverse pass, one set per device (created on first use, never destroyed)
+struct DualStreams {
+  cudaStream_t side;
+  cudaEvent_t start, d_done[BSDE_MAX_LAYERS], w_done[BSDE_MAX_LAYERS];
+};
+static bool dual_enabled() {
+  static const int on = [] { const char* e = getenv("BSDE_DUAL"); return e ? atoi(e) : 1; }();
+  return on != 0;
+}
+// SM budget of each stream: blocks whose position grid is small (B * H * W <= BSDE_DUAL_MAXPOS) run their launch pairs side by side
+// on half of the SMs each; larger ones keep full-size grids (the pair then overlaps only in its tails)
+static int dual_budget(long long positions) {
+  static const int b = [] { const char* e = getenv("BSDE_DUAL_BUDGET"); return e ? atoi(e) : 74; }();
+  static const long long maxpos = [] { const char* e = getenv("BSDE_DUAL_MAXPOS"); return e ? atoll(e) : 0LL; }();
+  return positions <= maxpos ? b : 148;
+}
+static DualStreams* dual_streams() {
+  static DualStreams pool[64];
+  static bool made[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!made[dev]) {
+    DualStreams& q = pool[dev];
+    if (cudaStreamCreateWithFlags(&q.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    bool ok = cudaEventCreateWithFlags(&q.start, cudaEventDisableTiming) == cudaSuccess;
+    for (int l = 0; l < BSDE_MAX_LAYERS; ++l)
+      ok = ok && cudaEventCreateWithFlags(&q.d_done[l], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&q.w_done[l], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return nullptr;
+    made[dev] = true;
+  }
+  return &pool[dev];
+}
+
 extern "C" size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t backward) {
   if (!d || d->nlayers < 2 || d->nlayers > BSDE_MAX_LAYERS) return 0;
   size_t tot = xpath_tc_bytes(d, backward);
@@ -424,6 +461,22 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
   bsde_conv_layer D[BSDE_MAX_LAYERS];
   for (int l = 0; l < n; ++l) D[l] = dgrad_layer(d->layers[l]);
 
+  // Two-stream reverse pass (tensor-core route): the weight gradient of layer l and the data gradient of layer l read the same dY
+  // and are independent of each other, and every kernel on this path is a persistent launch with ONE CTA per SM whose time at
+  // these sizes is dominated by per-launch latencies (prologue, weight image, tail) rather than by throughput.  The weight
+  // gradients go to a side stream, both streams size their grids for half of the SMs (sm_budget), so the pair is co-resident.
+  // Ordering by events: wgrad_l(k) after the launch that produced its dY; the launch that overwrites a buffer after its readers.
+  DualStreams* ds = nullptr;
+  if (d->math == BSDE_MATH_TC && d->act != BSDE_ACT_SWISH && dual_enabled()) ds = dual_streams();
+  bool have_w[BSDE_MAX_LAYERS] = {false, false, false, false};
+  if (ds) {
+    BSDE_CUDA_OK(cudaEventRecord(ds->start, st));
+    BSDE_CUDA_OK(cudaStreamWaitEvent(ds->side, ds->start, 0));
+    set_sm_budget(dual_budget((long long)d->B * d->layers[0].hin * d->layers[0].win));
+  }
+  struct BudgetReset { bool on; ~BudgetReset() { if (on) set_sm_budget(148); } } budget_reset{ds != nullptr};
+  cudaStream_t wst = ds ? ds->side : st;
+
   for (int k = d->nit - 1; k >= 0; --k) {
     const float t = h_tk[k], dt = h_dtk[k];
     const float* xk = d_xs + (size_t)k * d->x_numel;
@@ -432,18 +485,28 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
     if (d_acts) {
       float* p = const_cast<float*>(d_acts) + (size_t)k * xpath_acts_floats(d);
       for (int l = 0; l + 1 < n; ++l) { a[l] = p; p += act_slot_bytes(d, l) / sizeof(float); }
-    } else if (int e = xpath_recompute(d, xk, wk, t, a, tc_ws, tc_bytes, st, pp, k, nconv)) {
-      return e;
+    } else {
+      if (ds)   // the recompute overwrites the activations the previous iteration's weight gradients read
+        for (int l = 0; l < n; ++l)
+          if (have_w[l]) BSDE_CUDA_OK(cudaStreamWaitEvent(st, ds->w_done[l], 0));
+      if (int e = xpath_recompute(d, xk, wk, t, a, tc_ws, tc_bytes, st, pp, k, nconv)) return e;
+      if (ds) {
+        BSDE_CUDA_OK(cudaEventRecord(ds->start, st));
+        BSDE_CUDA_OK(cudaStreamWaitEvent(ds->side, ds->start, 0));
+      }
     }
     // walk the stack backwards; `dy` is dL/d(conv output of layer l)
     const float* dy = d_gx;  // for the last layer dL/d(conv out) = dt * gx  (scale folded below)
     for (int l = n - 1; l >= 0; --l) {
       const float* lin = l == 0 ? xk : a[l - 1];
       const float sc = (l == n - 1) ? dt : 1.f;
-      if (int e = conv_wgrad(&d->layers[l], d->S, d->B, lin, dy, t, sc, gwk, gss, d->math, wg_ws, wg_bytes, st)) return e;
+      if (ds) BSDE_CUDA_OK(cudaStreamWaitEvent(ds->side, ds->d_done[l], 0));   // dY of layer l is complete (gx: the previous dgrad_0)
+      if (int e = conv_wgrad(&d->layers[l], d->S, d->B, lin, dy, t, sc, gwk, gss, d->math, wg_ws, wg_bytes, wst)) return e;
+      if (ds) { BSDE_CUDA_OK(cudaEventRecord(ds->w_done[l], ds->side)); have_w[l] = true; }
       if (l > 0) {
         // dz_{l-1} = sc * dgrad(dy) * act'(a_{l-1})
         const bool sw = d->act == BSDE_ACT_SWISH;
+        if (ds && have_w[l - 1]) BSDE_CUDA_OK(cudaStreamWaitEvent(st, ds->w_done[l - 1], 0));   // readers of dz_{l-1} (previous iteration)
         if (int e = conv_fwd(&D[l], d->S, d->B, dy, wk, wss, t, sw ? BSDE_ACT_NONE : d->act, BSDE_EPI_DACT, sc, a[l - 1], dz[l - 1],
                              d->math, tc_ws, tc_bytes, st, pp.img[n + l] ? pp.img[n + l] + (size_t)k * pp.per_iter[n + l] : nullptr, nconv++ > 0))
           return e;
@@ -453,14 +516,21 @@ extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const
                                      (long long)d->B * Lp.hout * Lp.wout * Lp.cout, Lp.cout, 1.f, (float*)wg_ws, gwk, gss, st))
             return e;
         }
+        if (ds) BSDE_CUDA_OK(cudaEventRecord(ds->d_done[l - 1], st));
         dy = dz[l - 1];
       } else {
         // gx_k = gx_{k+1} + dgrad_0(dz_0)   (identity path of the Euler update)
+        if (ds) BSDE_CUDA_OK(cudaStreamWaitEvent(st, ds->w_done[n - 1], 0));   // the last layer's weight gradient reads gx_{k+1}
         if (int e = conv_fwd(&D[0], d->S, d->B, dy, wk, wss, t, d->act, BSDE_EPI_ACCUM, sc, d_gx, d_gx,
                              d->math, tc_ws, tc_bytes, st, pp.img[n] ? pp.img[n] + (size_t)k * pp.per_iter[n] : nullptr, nconv++ > 0))
           return e;
+        if (ds) BSDE_CUDA_OK(cudaEventRecord(ds->d_done[n - 1], st));
       }
     }
+  }
+  if (ds) {   // the caller's stream continues after the last weight gradient
+    BSDE_CUDA_OK(cudaEventRecord(ds->start, ds->side));
+    BSDE_CUDA_OK(cudaStreamWaitEvent(st, ds->start, 0));
   }
   return 0;
 }

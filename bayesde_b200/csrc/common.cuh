@@ -24,6 +24,10 @@ struct PerDeviceOnce {
   }
 };
 void count_launch(int n = 1);  // bookkeeping for bsde_launch_count()
+// SMs a persistent launch may size its grid for (default 148).  The two-stream reverse pass (api.cu) halves it so that a data-gradient
+// launch and the weight-gradient launch that reads the same dY are co-resident (every kernel here holds one CTA per SM).
+int sm_budget();
+void set_sm_budget(int n);
 
 #define BSDE_CHECK_ARG(cond, ...)        \
   do {                                   \

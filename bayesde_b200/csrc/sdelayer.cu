@@ -23,7 +23,7 @@
 
 namespace bsde {
 
-constexpr int SL_NT = 512;
+constexpr int SL_NT = 1024;
 
 struct SLOff {  // offsets of the driftx leaves inside w (ravel_pytree order)
   int W[3], b[3], wt[3], wtb[3], bt[3], beta[3];
@@ -59,6 +59,21 @@ __device__ __forceinline__ float sl_act_dbeta(int act, float y, float beta) {
   return y * y * sg * (1.f - sg) * sigmoidf_(beta);
 }
 
+// sum_i vec[i] * col[i * stride] with the global loads of 16 elements in flight before the first FMA (vec in shared memory)
+__device__ __forceinline__ float sl_dot_col(const float* __restrict__ col, long long stride, const float* vec, int n) {
+  float acc = 0.f;
+  int i = 0;
+  for (; i + 16 <= n; i += 16) {
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = __ldg(col + (long long)(i + u) * stride);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc = fmaf(vec[i + u], v[u], acc);
+  }
+  for (; i < n; ++i) acc = fmaf(vec[i], __ldg(col + (long long)i * stride), acc);
+  return acc;
+}
+
 // fixed-order block sum; `scr` holds SL_NT / 32 floats; every thread gets the result
 __device__ __forceinline__ float sl_block_sum(float v, float* scr) {
   v = warp_sum(v);
@@ -86,8 +101,20 @@ __device__ __forceinline__ void sl_driftw_hidden(const SLArgs& A, const float* s
   {
     const int j = tid % H, sl = tid / H;
     float acc = 0.f;
-    if (sl < slices)
-      for (int p = sl; p < P; p += slices) acc = fmaf(sw[p], __ldg(A.fw.W1 + (long long)p * H + j), acc);
+    if (sl < slices) {
+      // the loads of a group are issued before the first FMA that needs one (explicit arrays: the compiler otherwise serialises
+      // load -> FMA pairs on one register and the loop runs at one L2 latency per element)
+      const float* __restrict__ col = A.fw.W1 + j;
+      int p = sl;
+      for (; p + 15 * slices < P; p += 16 * slices) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldg(col + (long long)(p + u * slices) * H);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc = fmaf(sw[p + u * slices], v[u], acc);
+      }
+      for (; p < P; p += slices) acc = fmaf(sw[p], __ldg(col + (long long)p * H), acc);
+    }
     red[tid] = acc;
   }
   __syncthreads();
@@ -198,8 +225,7 @@ __global__ void __launch_bounds__(SL_NT) sdelayer_fwd_kernel(SLArgs A) {
       const float w = sw[p];
       float m = 0.f;
       if (mlp) {
-        float z = __ldg(A.fw.b4 + p);
-        for (int i = 0; i < H; ++i) z = fmaf(hd.h2[i], __ldg(A.fw.W4 + (long long)i * P + p), z);
+        float z = sl_dot_col(A.fw.W4 + p, P, hd.h2, H) + __ldg(A.fw.b4 + p);
         m = z * sigmoidf_(__ldg(A.fw.wt4 + p) * t + __ldg(A.fw.wtb4 + p)) + __ldg(A.fw.bt4 + p) * t;
       }
       const float prior = -ou * w;
@@ -288,8 +314,7 @@ __global__ void __launch_bounds__(SL_NT) sdelayer_bwd_kernel(SLArgs A) {
       const float w = sw[p];
       float z3 = 0.f, gt3 = 0.f, m = 0.f;
       if (mlp) {
-        z3 = __ldg(A.fw.b4 + p);
-        for (int i = 0; i < H; ++i) z3 = fmaf(hd.h2[i], __ldg(A.fw.W4 + (long long)i * P + p), z3);
+        z3 = sl_dot_col(A.fw.W4 + p, P, hd.h2, H) + __ldg(A.fw.b4 + p);
         gt3 = sigmoidf_(__ldg(A.fw.wt4 + p) * t + __ldg(A.fw.wtb4 + p));
         m = z3 * gt3 + __ldg(A.fw.bt4 + p) * t;
       }
@@ -319,7 +344,18 @@ __global__ void __launch_bounds__(SL_NT) sdelayer_bwd_kernel(SLArgs A) {
         A.gfw.wt4[(long long)s * P + p] += q * t;
         A.gfw.wtb4[(long long)s * P + p] += q;
         A.gfw.b4[(long long)s * P + p] += gzT;
-        for (int i = 0; i < H; ++i) gW4[(long long)i * P + p] += hd.h2[i] * gzT;
+        {   // read-modify-write of this sample's accumulator column: loads of a group first, then the stores (no aliasing between rows)
+          float* __restrict__ col = gW4 + p;
+          int i = 0;
+          for (; i + 8 <= H; i += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = col[(long long)(i + u) * P];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) col[(long long)(i + u) * P] = fmaf(hd.h2[i + u], gzT, v[u]);
+          }
+          for (; i < H; ++i) col[(long long)i * P] += hd.h2[i] * gzT;
+        }
       }
     }
     __syncthreads();
@@ -328,7 +364,15 @@ __global__ void __launch_bounds__(SL_NT) sdelayer_bwd_kernel(SLArgs A) {
       for (int i = warp; i < H; i += SL_NT / 32) {
         float at = 0.f, awv = 0.f;
         const float* row = A.fw.W4 + (long long)i * P;
-        for (int p = lane; p < P; p += 32) {
+        int p = lane;
+        for (; p + 15 * 32 < P; p += 16 * 32) {
+          float v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[u] = __ldg(row + p + u * 32);
+#pragma unroll
+          for (int u = 0; u < 16; ++u) { at = fmaf(v[u], gzt[p + u * 32], at); awv = fmaf(v[u], gzw[p + u * 32], awv); }
+        }
+        for (; p < P; p += 32) {
           const float wv = __ldg(row + p);
           at = fmaf(wv, gzt[p], at);
           awv = fmaf(wv, gzw[p], awv);
@@ -378,11 +422,20 @@ __global__ void __launch_bounds__(SL_NT) sdelayer_bwd_kernel(SLArgs A) {
       }
       __syncthreads();
       // ---- phase D: first layer ----------------------------------------------------------------------------------------------
-      for (int e1 = tid; e1 < (int)PH; e1 += SL_NT) gW1[e1] += sw[e1 / H] * gz2t[e1 % H];
+      {
+        int e1 = tid;
+        for (; e1 + 7 * SL_NT < (int)PH; e1 += 8 * SL_NT) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = gW1[e1 + u * SL_NT];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const int e = e1 + u * SL_NT; gW1[e] = fmaf(sw[e / H], gz2t[e % H], v[u]); }
+        }
+        for (; e1 < (int)PH; e1 += SL_NT) gW1[e1] += sw[e1 / H] * gz2t[e1 % H];
+      }
       for (int p = tid; p < P; p += SL_NT) {
         float acc = 0.f;
-        const float* row = A.fw.W1 + (long long)p * H;
-        for (int j = 0; j < H; ++j) acc = fmaf(__ldg(row + j), gz2w[j], acc);
+        acc = sl_dot_col(A.fw.W1 + (long long)p * H, 1, gz2w, H);
         daw[p] += acc;
       }
       __syncthreads();

@@ -433,7 +433,7 @@ int tconv_fwd_tapn(const bsde_conv_layer* L, int S, int B, const float* in, cons
   a.S = S; a.B = B;
   a.Q = B * p.IP;
   a.ntiles = (a.Q + 127) / 128;
-  a.G = std::max(1, std::min(148 / S, a.ntiles));
+  a.G = std::max(1, std::min(sm_budget() / S, a.ntiles));
   a.cin = L->cin; a.cout = L->cout; a.npad = p.npad; a.nks = p.nks; a.nhalf = p.nhalf; a.opitch = L->cout;
   a.hout = L->hout; a.wout = L->wout; a.has_time = L->has_time; a.epi = epi;
   a.Hq = p.Hq; a.Wq = p.Wq; a.pitch = p.pitch; a.IP = p.IP; a.NR = p.NR; a.box_bytes = p.box_bytes; a.region = p.region;

@@ -934,7 +934,7 @@ static int win_launch_one(const bsde_conv_layer* L, int S, int B, const float* i
   memset(&a, 0, sizeof(a));
   a.in = in; a.aux = aux; a.out = out; a.wimg = wimg; a.wimg_sample_stride = wimg_sample_stride; a.opitch = opitch;
   a.S = S; a.B = B;
-  a.G = std::max(1, 148 / S);
+  a.G = std::max(1, sm_budget() / S);
   a.Q = B * p.IP;
   a.ntiles = (a.Q + 127) / 128;
   a.G = std::min(a.G, a.ntiles);

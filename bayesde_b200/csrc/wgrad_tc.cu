@@ -457,7 +457,7 @@ static WgTcPlan wg_plan(const bsde_conv_layer* L, int S, int B) {
   p.stages = std::min(4, (200 * 1024) / stage_bytes);
   p.smem = 1024 + (size_t)p.stages * stage_bytes + 8 * 9 + 16;
   p.ok = cols_needed <= 512 && p.stages >= 2 && p.npad <= 256 && !(p.swapped && L->sn != 1);
-  int want = 148 / S;  // one CTA per SM (TMEM / smem allow a single resident CTA): a single wave
+  int want = sm_budget() / S;  // one CTA per SM (TMEM / smem allow a single resident CTA): a single wave
   if (want < 1) want = 1;
   int maxs = (p.Mper + 1023) / 1024;
   p.splits = std::max(1, std::min(want, maxs));

@@ -297,7 +297,7 @@ static ThinPlan thin_plan(const bsde_conv_layer* L) {
 
 static int thin_splits(const ThinPlan& p, int S, int B) {
   const int nst_total = (B * p.IP + WT_KS - 1) / WT_KS;
-  return std::max(1, std::min(148 / S, nst_total));
+  return std::max(1, std::min(sm_budget() / S, nst_total));
 }
 
 bool tconv_wgrad_thin_supported(const bsde_conv_layer* L, int S, int B) {

@@ -642,7 +642,7 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
   a.lboB = a.packed ? 128u : (uint32_t)a.regV;
   p.smem = 1024 + (size_t)a.nstages * a.stage_bytes + 2 * ((size_t)a.NPU * a.KS + (size_t)a.NPV * a.NPOSw) * 4 + 128;
 
-  a.SPL = std::max(1, 148 / (S * a.TG));
+  a.SPL = std::max(1, sm_budget() / (S * a.TG));
   a.chunk = (a.Q + a.SPL - 1) / a.SPL;
   a.chunk = (a.chunk + a.KS - 1) / a.KS * a.KS;
   a.SPL = (a.Q + a.chunk - 1) / a.chunk;

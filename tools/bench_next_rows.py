@@ -9,6 +9,9 @@
   N3  evaluation path: predict() of the config-4 classifier, S = 8 samples x 128 images: images/s.
   N4  config-5 SDENet training step (B = 128, midpoint dt 0.05): backprop-through-solver vs adjoint=True vs adaptive=True:
       ms per step, peak memory, accepted steps.
+  C1  config 1 (the JAX toy, examples/jax/sdebnn_toy1d.py --activn swish --aug_dim 2 --stop_grad --prior_dw ou): one ELBO
+      value_and_grad (10 samples x 100 points, hidden 64, P = 5132, posterior + prior solve of 19 steps) through the fused
+      SDELayer launches, and the oracle restatement (torch CPU fp64, all host threads) beside it.
 All times are CUDA events on the launching stream after warm-up; memory is torch.cuda.max_memory_allocated over the timed region."""
 import argparse
 import json
@@ -25,7 +28,7 @@ from bayesde_b200.sdeint import BrownianTree, PRNGKey, sdeint_ito, sdeint_ito_fi
 
 p = argparse.ArgumentParser()
 p.add_argument("--reps", type=int, default=5)
-p.add_argument("--rows", default="N1,N2,N3,N4")
+p.add_argument("--rows", default="N1,N2,N3,N4,C1")
 a = p.parse_args()
 dev = "cuda:0"
 rows = set(a.rows.split(","))
@@ -134,3 +137,54 @@ if "N4" in rows:
         extra = {"accepted_steps": len(m.adaptive_grid[0]), "nfe": m.nfe} if "adaptive" in kw else {"nfe": m.nfe}
         print(json.dumps({"row": "N4", "what": f"config-5 SDENet train step, B = 128, midpoint dt 0.05, {name}", "ms": ms,
                           "images_per_s": 128 / (ms * 1e-3), "peak_MiB": mem, **extra}), flush=True)
+
+
+if "C1" in rows:
+    import time
+    from bayesde_b200 import _lib, brax_layers as BL
+    st = dict(driftw=True, diffw=True, diff_const=0.1, prior_driftw="ou", driftw_scale=0.1, stop_grad=True, aug_dim=2,
+              priorw0_sigma=-1.0, diff_drift=True)
+    (init_fn, apply_fn), P = BL.mlp(0, 1, 64, "swish", st)
+    _, params = init_fn(1, (-1, 1))
+    to_dev = lambda tr: BL._tree_map(lambda t: t.to(dev).requires_grad_(True), tr)
+    params = [(), tuple(to_dev(q) if q is not None else None for q in params[1])]
+    xin = torch.linspace(-1, 1, 100, device=dev).reshape(100, 1)
+    tgt = torch.cos(3 * xin)
+    leaves = [t for q in params[1][0] for t in q] + [t for q in params[1][1][1] for t in q]
+    k = [0]
+
+    def step():
+        k[0] += 1
+        loss = BL.elbo(params, (xin, tgt), apply_fn, k[0], 1.0, num_samples=10)
+        torch.autograd.grad(loss, leaves)
+    L = _lib.lib()
+    n0 = L.bsde_launch_count()
+    step()
+    launches = L.bsde_launch_count() - n0
+    ms, mem = timed(step, a.reps * 4)
+    row = {"row": "C1", "what": "config 1 JAX toy: elbo value_and_grad, 10 samples x 100 points, hidden 64, P = 5132, swish, STL, OU prior "
+                                "(posterior + prior solve, 19 steps each)", "ms": ms, "steps_per_s": 1e3 / ms, "bsde_launches_per_step": int(launches),
+           "peak_MiB": mem}
+    try:   # the oracle restatement on the host cores (test infrastructure; timed here only as the CPU figure beside the GPU one)
+        from oracle import jax_toy as jt
+        g_ = torch.Generator().manual_seed(0)
+        orc = jt.SDELayerOracle(100, 3, 64, "swish", jt.ToySetting())
+        w0, lays = jt.init_toy(100, 3, 64, "swish", g_, driftw_scale=0.1, last_std=0.05)
+        x = torch.randn(100, 3, generator=g_, dtype=torch.float64)
+        eps = torch.randn(10, 19, orc.P, generator=g_, dtype=torch.float64)
+        w0 = w0.requires_grad_(True)
+        lays = [tuple(t.requires_grad_(True) for t in lay) for lay in lays]
+
+        def cpu_step():
+            outs = [orc.apply(w0, lays, x, eps[s_]) for s_ in range(10)]
+            loss = sum(o[0][..., -1].abs().mean() + o[2] for o in outs) / 10
+            torch.autograd.grad(loss, [w0] + [t for lay in lays for t in lay])
+        cpu_step()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            cpu_step()
+        row["cpu_oracle_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+        row["cpu_threads"] = torch.get_num_threads()
+    except Exception as e:  # noqa: BLE001
+        row["cpu_oracle_ms"] = repr(e)
+    print(json.dumps(row), flush=True)
