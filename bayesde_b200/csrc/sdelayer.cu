@@ -74,6 +74,30 @@ __device__ __forceinline__ float sl_dot_col(const float* __restrict__ col, long 
   return acc;
 }
 
+__host__ __device__ __forceinline__ int sl_al4(int x) { return (x + 3) & ~3; }
+
+// Small shared-memory product with a 1 x 4 register tile: for r < R, 4-column group j0 < N,
+//   acc[0..3] = sum_k A[r * a_rs + k * a_ks] * Bm[k * ldb + j0 .. j0 + 3]          (Bm rows 16-byte aligned, N % 4 == 0)
+// one scalar (warp-broadcast) and one 128-bit load per four FMAs instead of two loads per FMA; `store(r, j0, acc)` finishes.
+template <class Store>
+__device__ __forceinline__ void sl_mm4(const float* A, int a_rs, int a_ks, const float* Bm, int ldb, int R, int K, int N, Store&& store) {
+  const int n4 = N >> 2;
+  for (int idx = threadIdx.x; idx < R * n4; idx += SL_NT) {
+    const int r = idx / n4, j0 = (idx - r * n4) << 2;
+    const float* a = A + r * a_rs;
+    const float4* b = reinterpret_cast<const float4*>(Bm + j0);
+    const int ldb4 = ldb >> 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float av = a[k * a_ks];
+      const float4 bv = b[k * ldb4];
+      acc.x = fmaf(av, bv.x, acc.x); acc.y = fmaf(av, bv.y, acc.y); acc.z = fmaf(av, bv.z, acc.z); acc.w = fmaf(av, bv.w, acc.w);
+    }
+    store(r, j0, acc);
+  }
+}
+
 // fixed-order block sum; `scr` holds SL_NT / 32 floats; every thread gets the result
 __device__ __forceinline__ float sl_block_sum(float v, float* scr) {
   v = warp_sum(v);
@@ -161,13 +185,16 @@ __device__ __forceinline__ void sl_x_hidden(const SLArgs& A, const float* sw, co
     H1[idx] = sl_act(act, z * gx[j] + sw[A.xo.bt[0] + j] * t, swi ? sw[A.xo.beta[0] + j] : 0.f);
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < nr * H; idx += SL_NT) {
-    const int r = idx / H, j = idx - r * H;
-    float z = sw[A.xo.b[1] + j];
-    for (int i = 0; i < H; ++i) z = fmaf(H1[r * H + i], sw[A.xo.W[1] + i * H + j], z);
-    if (KEEP) Z2[idx] = z;
-    H2[idx] = sl_act(act, z * gx[H + j] + sw[A.xo.bt[1] + j] * t, swi ? sw[A.xo.beta[1] + j] : 0.f);
-  }
+  sl_mm4(H1, H, 1, sw + A.xo.W[1], H, nr, H, H, [&](int r, int j0, const float4& acc) {
+    const float zz[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      const float z = zz[u] + sw[A.xo.b[1] + j];
+      if (KEEP) Z2[r * H + j] = z;
+      H2[r * H + j] = sl_act(act, z * gx[H + j] + sw[A.xo.bt[1] + j] * t, swi ? sw[A.xo.beta[1] + j] : 0.f);
+    }
+  });
   __syncthreads();
 }
 
@@ -175,14 +202,14 @@ __device__ __forceinline__ void sl_x_hidden(const SLArgs& A, const float* sw, co
 // forward: one CTA per sample, all steps
 // ---------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SL_NT) sdelayer_fwd_kernel(SLArgs A) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int s = blockIdx.x, tid = threadIdx.x;
   const int P = (int)A.d.P, B = A.d.B, D = A.d.D, H = A.d.H, BD = B * D;
   const long long Dtot = (long long)P + BD + 1;
-  float* sw = sm;
+  float* sw = sm;                      // every segment starts on a 16-byte boundary (P, H are multiples of 4)
   float* sx = sw + P;
-  float* gx = sx + BD;
-  float* red = gx + 2 * H + D;
+  float* gx = sx + sl_al4(BD);
+  float* red = gx + sl_al4(2 * H + D);
   float* scr = red + SL_NT;
   SLHid hd;
   hd.z1 = scr + 32; hd.a1 = hd.z1 + H; hd.h1 = hd.a1 + H; hd.z2 = hd.h1 + H; hd.a2 = hd.z2 + H; hd.h2 = hd.a2 + H; hd.gA = hd.h2 + H; hd.gB = hd.gA + H;
@@ -248,7 +275,7 @@ __global__ void __launch_bounds__(SL_NT) sdelayer_fwd_kernel(SLArgs A) {
 // reverse pass
 // ---------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SL_NT) sdelayer_bwd_kernel(SLArgs A) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = (int)A.d.P, B = A.d.B, D = A.d.D, H = A.d.H, BD = B * D, act = A.d.act;
   const bool swi = act == BSDE_ACT_SWISH;
@@ -259,10 +286,10 @@ __global__ void __launch_bounds__(SL_NT) sdelayer_bwd_kernel(SLArgs A) {
   float* gzt = daw + P;
   float* gzw = A.d.stop_grad ? gzt + P : gzt;
   float* sx = gzt + (A.d.stop_grad ? 2 : 1) * P;
-  float* ax = sx + BD;
-  float* dax = ax + BD;
-  float* gx = dax + BD;
-  float* red = gx + 2 * H + D;
+  float* ax = sx + sl_al4(BD);
+  float* dax = ax + sl_al4(BD);
+  float* gx = dax + sl_al4(BD);
+  float* red = gx + sl_al4(2 * H + D);
   float* scr = red + SL_NT;
   SLHid hd;
   hd.z1 = scr + 32; hd.a1 = hd.z1 + H; hd.h1 = hd.a1 + H; hd.z2 = hd.h1 + H; hd.a2 = hd.z2 + H; hd.h2 = hd.a2 + H; hd.gA = hd.h2 + H; hd.gB = hd.gA + H;
@@ -271,11 +298,12 @@ __global__ void __launch_bounds__(SL_NT) sdelayer_bwd_kernel(SLArgs A) {
   float* gz2t = ghw + H;
   float* gz2w = gz2t + H;
   float* g3 = gz2w + H;       // per (row, d) scratch of driftx layer 3: GZ3, Q3, GDX  [Bc * D each]
-  float* Z1 = g3 + 3 * A.Bc * D;
+  float* Z1 = g3 + sl_al4(3 * A.Bc * D);
   float* Z2 = Z1 + A.Bc * H;
   float* H1 = Z2 + A.Bc * H;
   float* H2 = H1 + A.Bc * H;
   float* G = H2 + A.Bc * H;
+  float* WT = G + A.Bc * H;   // transposed copy of driftx's middle matrix at the current state: WT[j][i] = W[i][j]
   const float* tr = A.traj + (long long)s * A.d.nt * Dtot;
   const bool mlp = A.d.driftw && !A.d.prior_solve;
   const float ou = A.d.prior_ou ? 1.f : 0.f;
@@ -307,6 +335,7 @@ __global__ void __launch_bounds__(SL_NT) sdelayer_bwd_kernel(SLArgs A) {
     __syncthreads();
     if (mlp) sl_driftw_hidden(A, sw, t, hd, red);
     sl_x_gates(A, sw, t, gx);
+    for (int e2 = tid; e2 < H * H; e2 += SL_NT) WT[(e2 % H) * H + e2 / H] = sw[A.xo.W[1] + e2];
     __syncthreads();
 
     // ---- w rows: phase A, one thread per p -----------------------------------------------------------------------------
@@ -506,21 +535,19 @@ __global__ void __launch_bounds__(SL_NT) sdelayer_bwd_kernel(SLArgs A) {
         }
         __syncthreads();
         // pass B: W leaf [din][H]
-        for (int o = tid; o < din * H; o += SL_NT) {
-          const int i = o / H, j = o - i * H;
-          float acc = 0.f;
-          if (l == 1) for (int r = 0; r < nr; ++r) acc = fmaf(Hin[r * H + i], G[r * H + j], acc);
-          else for (int r = 0; r < nr; ++r) acc = fmaf(sx[(r0 + r) * D + i], G[r * H + j], acc);
-          daw[A.xo.W[l] + o] += acc;
+        {   // dW[i][j] = sum_r in[r][i] G[r][j]: the layer input read transposed (row stride 1, reduction stride = its pitch)
+          float* dW = daw + A.xo.W[l];
+          sl_mm4(l == 1 ? Hin : sx + r0 * D, 1, l == 1 ? H : D, G, H, din, nr, H, [&](int i, int j0, const float4& acc) {
+            float* q = dW + i * H + j0;
+            q[0] += acc.x; q[1] += acc.y; q[2] += acc.z; q[3] += acc.w;
+          });
         }
         // pass C: cotangent of the layer input
         if (l == 1) {
-          for (int idx = tid; idx < nr * H; idx += SL_NT) {   // into Z2 (its values were consumed by pass A)
-            const int r = idx / H, i = idx - r * H;
-            float acc = 0.f;
-            for (int j = 0; j < H; ++j) acc = fmaf(G[r * H + j], sw[A.xo.W[1] + i * H + j], acc);
-            Z2[idx] = acc;
-          }
+          // GH1[r][i] = sum_j G[r][j] W[i][j] = sum_j G[r][j] WT[j][i] (WT: this step's transposed copy), into Z2 (consumed by pass A)
+          sl_mm4(G, H, 1, WT, H, nr, H, H, [&](int r, int i0, const float4& acc) {
+            *reinterpret_cast<float4*>(Z2 + r * H + i0) = acc;
+          });
           __syncthreads();
           for (int idx = tid; idx < nr * H; idx += SL_NT) G[idx] = Z2[idx];
           __syncthreads();
@@ -552,7 +579,7 @@ __global__ void __launch_bounds__(SL_NT) sdelayer_bwd_kernel(SLArgs A) {
 static int sl_check(const bsde_sdelayer_desc* d, const bsde_fw_params* fw, SLOff& xo) {
   BSDE_CHECK_ARG(d != nullptr, "NULL descriptor");
   BSDE_CHECK_ARG(d->S >= 1 && d->B >= 1 && d->D >= 1 && d->nt >= 2, "S, B, D must be positive and nt >= 2");
-  BSDE_CHECK_ARG(d->H >= 1 && d->H <= 128, "hidden width %d unsupported (1..128)", d->H);
+  BSDE_CHECK_ARG(d->H >= 4 && d->H <= 128 && d->H % 4 == 0, "hidden width %d unsupported (a multiple of 4 in 4..128)", d->H);
   BSDE_CHECK_ARG(d->D <= 16, "x width %d unsupported (<= 16)", d->D);
   BSDE_CHECK_ARG((d->act >= BSDE_ACT_SOFTPLUS && d->act <= BSDE_ACT_ELU) || d->act == BSDE_ACT_RBF || d->act == BSDE_ACT_SWISH,
                  "activation %d unsupported", d->act);
@@ -580,10 +607,10 @@ static int sl_check(const bsde_sdelayer_desc* d, const bsde_fw_params* fw, SLOff
 }
 
 static size_t sl_fixed_floats(const bsde_sdelayer_desc* d, int backward) {
-  const size_t P = (size_t)d->P, BD = (size_t)d->B * d->D, H = d->H;
-  const size_t common = 2 * H + d->D + SL_NT + 32 + 8 * H;
+  const size_t P = (size_t)d->P, BD = (size_t)sl_al4(d->B * d->D), H = d->H;
+  const size_t common = sl_al4(2 * d->H + d->D) + SL_NT + 32 + 8 * H;
   if (!backward) return P + BD + common;
-  return (d->stop_grad ? 5 : 4) * P + 3 * BD + common + 4 * H;
+  return (d->stop_grad ? 5 : 4) * P + 3 * BD + common + 4 * H + H * H + 4;
 }
 static size_t sl_row_floats(const bsde_sdelayer_desc* d, int backward) { return backward ? 5 * (size_t)d->H + 3 * d->D : 2 * (size_t)d->H; }
 

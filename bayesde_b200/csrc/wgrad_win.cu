@@ -643,6 +643,10 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
   p.smem = 1024 + (size_t)a.nstages * a.stage_bytes + 2 * ((size_t)a.NPU * a.KS + (size_t)a.NPV * a.NPOSw) * 4 + 128;
 
   a.SPL = std::max(1, sm_budget() / (S * a.TG));
+  {   // tools only (BSDE_WW_MINST): at least this many stages per CTA -- fewer, longer CTAs and fewer partial tiles for small grids
+    static const int minst = getenv("BSDE_WW_MINST") ? atoi(getenv("BSDE_WW_MINST")) : 0;
+    if (minst > 0) a.SPL = std::max(1, std::min(a.SPL, (a.Q + minst * a.KS - 1) / (minst * a.KS)));
+  }
   a.chunk = (a.Q + a.SPL - 1) / a.SPL;
   a.chunk = (a.chunk + a.KS - 1) / a.KS * a.KS;
   a.SPL = (a.Q + a.chunk - 1) / a.chunk;
