@@ -564,6 +564,24 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
           if (a.mode == 3) { oy = 2 * y + (ac >> 1); ox = 2 * x + (ac & 1); }
           __syncwarp();
           w_pix[lane] = valid ? (img * a.hout + oy) * a.wout + ox : -1;
+          __syncwarp();   // the rows are read by other lanes right below
+        }
+        // combine epilogues (Euler / data-gradient / accumulate): the loads of the values already stored at this lane's output
+        // positions are issued FIRST, so that their L2 / DRAM latency runs under the TMEM load, the row arithmetic and the
+        // staging exchange (two epilogue warps per scheduler cannot hide it otherwise)
+        const int ncol = min(16, a.cout - n0);
+        const bool fast = vec_out && ncol == 16;
+        int pp[4];
+        float4 xv[4];
+        if (fast) {
+          const int n = n0 + c4 * 4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pp[j] = w_pix[r8 + 8 * j];
+          if (EPI >= BSDE_EPI_EULER) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              xv[j] = pp[j] >= 0 ? *reinterpret_cast<const float4*>(aux + (long long)pp[j] * a.opitch + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * a.NA + ac) * a.npad + n0), v);
@@ -599,22 +617,14 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
           dst[3 ^ fz] = make_float4(f[12], f[13], f[14], f[15]);
         }
         __syncwarp();
-        const int ncol = min(16, a.cout - n0);
-        if (vec_out && ncol == 16) {
+        if (fast) {
           // lane -> fixed column group c4, rows r8 + 8 j: 64 contiguous bytes per row
           const int n = n0 + c4 * 4;
-          int pp[4];
-          float4 qv[4], xv[4];
+          float4 qv[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int rr = r8 + 8 * j;
-            pp[j] = w_pix[rr];
             qv[j] = *reinterpret_cast<const float4*>(stage + rr * 16 + ((c4 ^ ((rr >> 1) & 3)) << 2));
-          }
-          if (EPI >= BSDE_EPI_EULER) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              xv[j] = pp[j] >= 0 ? *reinterpret_cast<const float4*>(aux + (long long)pp[j] * a.opitch + n) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
