@@ -198,7 +198,8 @@ def xpath_backward(cfg, xs, wtraj, gx, acts=None):
     d = cfg.xdesc()
     gx = gx.contiguous().clone()
     gw_traj = torch.empty(cfg.S, cfg.nit, cfg.P, device=xs.device, dtype=torch.float32)
-    nbytes = L.bsde_xpath_workspace_bytes(C.byref(d), 1)
+    # 2: reverse pass WITH stored activations (deferred, iteration-batched weight gradients keep dZ / gx of every iteration)
+    nbytes = L.bsde_xpath_workspace_bytes(C.byref(d), 2 if acts is not None else 1)
     ws = _lib.workspace(nbytes, xs.device, "xpath")
     st = L.bsde_xpath_bwd(C.byref(d), _lib.host_floats(cfg.tk), _lib.host_floats(cfg.dtk), _lib.ptr(wtraj),
                           _lib.ptr(xs), _lib.ptr(acts), _lib.ptr(gx), _lib.ptr(gw_traj), C.c_void_p(ws.data_ptr()), ws.numel(),

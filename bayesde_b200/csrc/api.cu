@@ -334,6 +334,86 @@ static DualStreams* dual_streams() {
   return &pool[dev];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Deferred, iteration-batched weight gradients (reverse pass with stored activations).
+//
+// The weight gradient of layer l at scan iteration k, G_k = sum over positions of in_k (x) dY_k, is independent of every other
+// iteration, and at the bench sizes a weight-gradient launch is dominated by per-launch fixed cost (tools/bench_tconv.py --B
+// 32..2048, profiles/r02_summary.md: 35-55 us of a 58-115 us call do not depend on the batch: split-K partial tiles of up to
+// 187 KB per CTA, their reduction launch, prologue / tail).  With the activations kept per iteration (remat = False) and dZ / gx
+// kept per iteration too, the (iteration, sample) pairs of a layer are laid out contiguously with ONE stride -- activations are
+// stored layer-major [layer][k][s] -- so a run of c iterations is exactly a launch with S * c "samples": c = 74 / S iterations
+// per launch give two CTAs per pair instead of 148 / S, a sixth of the partial tiles and a c-th of the launches.  The kernels are
+// unchanged; they run with t = 1, scale = 1 into a [k][s][P] buffer, and one finishing pass applies the per-iteration factors
+// (t_k on the time rows, dt_k on the last layer) while transposing to the [s][k][P] layout that K1' reads.
+// ---------------------------------------------------------------------------------------------
+struct FinalizeArgs {
+  const float* src;     // [nit][S][P]
+  float* dst;           // [S][nit][P]
+  const float* tk;      // [nit] device
+  const float* dtk;     // [nit] device
+  int S, nit, nlayers;
+  long long P;
+  long long w_off[BSDE_MAX_LAYERS], w_end[BSDE_MAX_LAYERS], b_off[BSDE_MAX_LAYERS];
+  int Kc[BSDE_MAX_LAYERS], cout[BSDE_MAX_LAYERS], time_row[BSDE_MAX_LAYERS];
+};
+
+__global__ void gw_finalize_kernel(FinalizeArgs a) {
+  const long long per = (long long)a.S * a.P;
+  const long long total = per * a.nit;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx / per);
+    const long long r = idx - (long long)k * per;
+    const int s = (int)(r / a.P);
+    const long long p = r - (long long)s * a.P;
+    float f = 1.f;
+    for (int l = 0; l < a.nlayers; ++l) {
+      const bool in_w = p >= a.w_off[l] && p < a.w_end[l];
+      const bool in_b = p >= a.b_off[l] && p < a.b_off[l] + a.cout[l];
+      if (in_w || in_b) {
+        if (l == a.nlayers - 1) f *= a.dtk[k];
+        if (in_w && a.time_row[l] >= 0 && (int)(((p - a.w_off[l]) / a.cout[l]) % a.Kc[l]) == a.time_row[l]) f *= a.tk[k];
+        break;
+      }
+    }
+    a.dst[((long long)s * a.nit + k) * a.P + p] = a.src[idx] * f;
+  }
+}
+
+static bool defer_enabled() {
+  static const int on = [] { const char* e = getenv("BSDE_DEFER"); return e ? atoi(e) : 1; }();
+  return on != 0;
+}
+// iterations per batched weight-gradient launch: two CTAs per (iteration, sample) pair on 148 SMs
+static int defer_chunk(const bsde_xpath_desc* d) { return std::max(1, std::min(d->nit, 74 / d->S)); }
+// extra floats of the deferred mode: dZ of every iteration, the gx trajectory, the [k][s][P] gradient buffer, (t_k, dt_k)
+static size_t defer_extra_floats(const bsde_xpath_desc* d) {
+  size_t f = 0;
+  for (int l = 0; l + 1 < d->nlayers; ++l) f += (size_t)d->nit * act_elems(d, l);
+  f += (size_t)(d->nit + 1) * (size_t)d->x_numel + (size_t)d->nit * d->S * (size_t)d->P + 2 * (size_t)d->nit + 64;
+  return f;
+}
+// Activations are stored layer-major [layer][k][s] (instead of [k][layer]) when the deferred mode applies: a function of the
+// descriptor only, so that bsde_xpath_fwd (which writes them) and bsde_xpath_bwd (which reads them) always agree.
+static bool xpath_layer_major(const bsde_xpath_desc* d) {
+  if (!defer_enabled() || d->math != BSDE_MATH_TC || d->act == BSDE_ACT_SWISH || d->nit < 2 || d->S > 74) return false;
+  for (int l = 0; l + 1 < d->nlayers; ++l)
+    if ((act_elems(d, l) * sizeof(float)) % 256 != 0) return false;          // slots must be exactly S * per-sample floats
+  for (int l = 0; l < d->nlayers; ++l) {                                     // dense HWIO leaves, time row last (JAX front end)
+    const bsde_conv_layer& L = d->layers[l];
+    const int Kc = L.cin + (L.has_time ? 1 : 0);
+    if (L.w_n_stride != 1 || L.w_k_stride != L.cout || L.w_tap_stride != (long long)Kc * L.cout || (L.has_time && L.time_first)) return false;
+  }
+  static const double cap_gb = [] { const char* e = getenv("BSDE_DEFER_MAX_GB"); return e ? atof(e) : 48.0; }();
+  return (double)defer_extra_floats(d) * 4.0 <= cap_gb * 1e9;
+}
+static size_t act_base_floats(const bsde_xpath_desc* d, int l) {  // layer-major: start of layer l's [nit][S][...] block
+  size_t off = 0;
+  for (int j = 0; j < l; ++j) off += (size_t)d->nit * act_elems(d, j);
+  return off;
+}
+
 extern "C" size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t backward) {
   if (!d || d->nlayers < 2 || d->nlayers > BSDE_MAX_LAYERS) return 0;
   size_t tot = xpath_tc_bytes(d, backward);
@@ -348,6 +428,12 @@ extern "C" size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t b
     tot += align_up(wg);
   }
   tot += align_up(prepack_floats(d, backward, true) * sizeof(float));
+  if (backward == 2 && xpath_layer_major(d)) {   // reverse pass with stored activations: deferred weight gradients
+    size_t wg = 0;
+    const int c = defer_chunk(d);
+    for (int l = 0; l < d->nlayers; ++l) wg = std::max(wg, wgrad_ws(&d->layers[l], d->S * c, d->B, d->math));
+    tot += align_up(wg) + align_up(defer_extra_floats(d) * sizeof(float));
+  }
   return tot;
 }
 
@@ -405,11 +491,14 @@ extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const
   for (int l = 0; l + 1 < n; ++l) { a[l] = (float*)ws; ws += act_slot_bytes(d, l); }
   const long long wss = (long long)(d->nit + 1) * d->P;
   const size_t acts_step = xpath_acts_floats(d);
+  const bool layer_major = xpath_layer_major(d);
   Prepack pp;
   if (int e = prepack_all(d, 0, true, d_wtraj, (float*)ws, pp, st)) return e;
   int nconv = 0;  // conv launches since the prepack: the first one must not read the images before its pdl_wait()
   for (int k = 0; k < d->nit; ++k) {
-    if (d_acts) {  // keep this iteration's layer outputs for the reverse pass (remat = False)
+    if (d_acts && layer_major) {  // [layer][k][s]: every layer's (iteration, sample) pairs are contiguous with one stride
+      for (int l = 0; l + 1 < n; ++l) a[l] = d_acts + act_base_floats(d, l) + (size_t)k * act_elems(d, l);
+    } else if (d_acts) {  // keep this iteration's layer outputs for the reverse pass (remat = False)
       float* p = d_acts + (size_t)k * acts_step;
       for (int l = 0; l + 1 < n; ++l) { a[l] = p; p += act_slot_bytes(d, l) / sizeof(float); }
     }
@@ -426,16 +515,117 @@ extern "C" int bsde_xpath_fwd(const bsde_xpath_desc* d, const float* h_tk, const
   return 0;
 }
 
+
+static int xpath_bwd_deferred(const bsde_xpath_desc* d, const float* h_tk, const float* h_dtk, const float* d_wtraj, const float* d_xs,
+                              const float* d_acts, float* d_gx, float* d_gw_traj, void* workspace, cudaStream_t st) {
+  const int n = d->nlayers, nit = d->nit, S = d->S;
+  char* ws = (char*)workspace;
+  void* tc_ws = ws;
+  const size_t tc_bytes = xpath_tc_bytes(d, 1);
+  ws += tc_bytes;
+  // (the per-iteration slots of the other mode stay unused: the layout of the common part is shared with bsde_xpath_workspace_bytes)
+  for (int l = 0; l + 1 < n; ++l) ws += act_slot_bytes(d, l) * 2;
+  {
+    size_t wgmax = 0;
+    for (int l = 0; l < n; ++l) wgmax = std::max(wgmax, wgrad_ws(&d->layers[l], S, d->B, d->math));
+    wgmax = std::max(wgmax, xpath_swish_bytes(d));
+    ws += align_up(wgmax);
+  }
+  Prepack pp;
+  if (int e = prepack_all(d, 1, false, d_wtraj, (float*)ws, pp, st)) return e;
+  ws += align_up(prepack_floats(d, 1, true) * sizeof(float));
+  const int c = defer_chunk(d);
+  size_t wgd = 0;
+  for (int l = 0; l < n; ++l) wgd = std::max(wgd, wgrad_ws(&d->layers[l], S * c, d->B, d->math));
+  void* wg_ws = ws;
+  const size_t wg_bytes = align_up(wgd);
+  ws += wg_bytes;
+  float* fp = (float*)ws;
+  float* dzs[BSDE_MAX_LAYERS];
+  for (int l = 0; l + 1 < n; ++l) { dzs[l] = fp; fp += (size_t)nit * act_elems(d, l); }
+  float* gxs = fp; fp += (size_t)(nit + 1) * (size_t)d->x_numel;
+  float* gw_ks = fp; fp += (size_t)nit * S * (size_t)d->P;
+  float* d_tk = fp; float* d_dtk = fp + nit;
+
+  BSDE_CUDA_OK(cudaMemcpyAsync(d_tk, h_tk, nit * sizeof(float), cudaMemcpyHostToDevice, st));
+  BSDE_CUDA_OK(cudaMemcpyAsync(d_dtk, h_dtk, nit * sizeof(float), cudaMemcpyHostToDevice, st));
+  BSDE_CUDA_OK(cudaMemcpyAsync(gxs + (size_t)nit * d->x_numel, d_gx, (size_t)d->x_numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+  const long long wss = (long long)(nit + 1) * d->P;
+  bsde_conv_layer D[BSDE_MAX_LAYERS];
+  for (int l = 0; l < n; ++l) D[l] = dgrad_layer(d->layers[l]);
+  DualStreams* ds = dual_enabled() ? dual_streams() : nullptr;
+  cudaStream_t wst = ds ? ds->side : st;
+  int nconv = 0;
+  int k_hi = nit - 1;   // top of the chunk whose weight gradients are still to be launched
+
+  for (int k = nit - 1; k >= 0; --k) {
+    const float t = h_tk[k], dt = h_dtk[k];
+    const float* wk = d_wtraj + (size_t)k * d->P;
+    const float* gx_in = gxs + (size_t)(k + 1) * d->x_numel;
+    float* gx_out = k == 0 ? d_gx : gxs + (size_t)k * d->x_numel;
+    const float* dy = gx_in;
+    for (int l = n - 1; l >= 1; --l) {
+      const float sc = (l == n - 1) ? dt : 1.f;
+      const float* al = d_acts + act_base_floats(d, l - 1) + (size_t)k * act_elems(d, l - 1);
+      float* out = dzs[l - 1] + (size_t)k * act_elems(d, l - 1);
+      if (int e = conv_fwd(&D[l], S, d->B, dy, wk, wss, t, d->act, BSDE_EPI_DACT, sc, al, out, d->math, tc_ws, tc_bytes, st,
+                           pp.img[n + l] ? pp.img[n + l] + (size_t)k * pp.per_iter[n + l] : nullptr, nconv++ > 0))
+        return e;
+      dy = out;
+    }
+    // gx_k = gx_{k+1} + dgrad_0(dz_0)   (identity path of the Euler update); the trajectory of gx is kept for the last layer's weight gradient
+    if (int e = conv_fwd(&D[0], S, d->B, dy, wk, wss, t, d->act, BSDE_EPI_ACCUM, n == 1 ? dt : 1.f, gx_in, gx_out, d->math, tc_ws, tc_bytes, st,
+                         pp.img[n] ? pp.img[n] + (size_t)k * pp.per_iter[n] : nullptr, nconv++ > 0))
+      return e;
+    // a chunk of c iterations is complete: its weight gradients, one launch per layer over S * c (iteration, sample) pairs
+    if (k_hi - k + 1 == c || k == 0) {
+      const int k_lo = k, cnt = k_hi - k_lo + 1;
+      if (ds) {
+        BSDE_CUDA_OK(cudaEventRecord(ds->start, st));
+        BSDE_CUDA_OK(cudaStreamWaitEvent(ds->side, ds->start, 0));
+      }
+      for (int l = n - 1; l >= 0; --l) {
+        const float* lin = l == 0 ? d_xs + (size_t)k_lo * d->x_numel : d_acts + act_base_floats(d, l - 1) + (size_t)k_lo * act_elems(d, l - 1);
+        const float* ldy = l == n - 1 ? gxs + (size_t)(k_lo + 1) * d->x_numel : dzs[l] + (size_t)k_lo * act_elems(d, l);
+        if (int e = conv_wgrad(&d->layers[l], S * cnt, d->B, lin, ldy, 1.f, 1.f, gw_ks + (size_t)k_lo * S * d->P, d->P, d->math, wg_ws, wg_bytes, wst))
+          return e;
+      }
+      k_hi = k - 1;
+    }
+  }
+  if (ds) {
+    BSDE_CUDA_OK(cudaEventRecord(ds->start, ds->side));
+    BSDE_CUDA_OK(cudaStreamWaitEvent(st, ds->start, 0));
+  }
+  FinalizeArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.src = gw_ks; fa.dst = d_gw_traj; fa.tk = d_tk; fa.dtk = d_dtk; fa.S = S; fa.nit = nit; fa.nlayers = n; fa.P = d->P;
+  for (int l = 0; l < n; ++l) {
+    const bsde_conv_layer& L = d->layers[l];
+    const int Kc = L.cin + (L.has_time ? 1 : 0);
+    fa.w_off[l] = L.w_off; fa.w_end[l] = L.w_off + (long long)L.ksize * L.ksize * Kc * L.cout; fa.b_off[l] = L.b_off;
+    fa.Kc[l] = Kc; fa.cout[l] = L.cout; fa.time_row[l] = L.has_time ? L.cin : -1;
+  }
+  const long long total = (long long)nit * S * d->P;
+  gw_finalize_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(fa);
+  BSDE_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 extern "C" int bsde_xpath_bwd(const bsde_xpath_desc* d, const float* h_tk, const float* h_dtk,
                               const float* d_wtraj, const float* d_xs, const float* d_acts, float* d_gx,
                               float* d_gw_traj, void* workspace, size_t workspace_bytes, void* stream) {
   if (int e = xpath_check(d)) return e;
   BSDE_CHECK_ARG(h_tk && h_dtk && d_wtraj && d_xs && d_gx && d_gw_traj, "NULL pointer");
-  const size_t need = bsde_xpath_workspace_bytes(d, 1);
+  const bool deferred = d_acts != nullptr && xpath_layer_major(d);
+  const size_t need = bsde_xpath_workspace_bytes(d, deferred ? 2 : 1);
   if (!workspace || workspace_bytes < need) {
     set_error("xpath_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
     return BSDE_ERR_WORKSPACE;
   }
+  if (deferred) return xpath_bwd_deferred(d, h_tk, h_dtk, d_wtraj, d_xs, d_acts, d_gx, d_gw_traj, workspace, (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   const int n = d->nlayers;
   float* a[BSDE_MAX_LAYERS];

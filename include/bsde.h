@@ -225,6 +225,9 @@ typedef struct {
                                         activation that follows conv l (arch.py:172-174; l < nlayers - 1); ignored otherwise */
 } bsde_xpath_desc;
 
+/* backward: 0 forward scan; 1 reverse pass that recomputes the activations (d_acts == NULL); 2 reverse pass with stored activations
+ * (d_acts != NULL): when the deferred mode applies (tensor-core route, nit >= 2, JAX weight layout) it also holds dZ and gx of
+ * every iteration and a [k][s][P] gradient buffer, so that the weight gradients of 74 / S iterations run as one launch per layer. */
 size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t backward);
 
 /* bytes of the optional per-iteration activation store (all nit iterations) */

@@ -553,8 +553,13 @@ def test_remat_modes_agree(built_lib, math):
         xo, kl = layer.apply((w0d, (), _product_fw_params(fw, DEV)), xd, dW.float().to(DEV))
         g = torch.autograd.grad(xo.square().sum() + 1e-3 * kl.sum(), [xd, w0d])
         res.append((xo.detach(), kl.detach(), g[0], g[1]))
-    for a, b in zip(*res):
-        assert torch.equal(a, b)
+    for i, (a, b) in enumerate(zip(*res)):
+        if math == "fp32" or i < 3:
+            assert torch.equal(a, b)      # same kernels on the same data: bit-identical (x_T, KL, dL/dx in both arithmetics)
+        else:
+            # tensor-core route: with stored activations the weight gradients of several scan iterations run as ONE launch
+            # (two CTAs per (iteration, sample) pair instead of 148 / S): same products, another split of the position sum
+            _gclose(a, b, 1e-4, "dL/dw0 remat vs stored activations")
 
 
 # ------------------------------------------------------------------------------------------------
