@@ -386,7 +386,21 @@ static bool defer_enabled() {
   return on != 0;
 }
 // iterations per batched weight-gradient launch: two CTAs per (iteration, sample) pair on 148 SMs
-static int defer_chunk(const bsde_xpath_desc* d) { return std::max(1, std::min(d->nit, 74 / d->S)); }
+static int defer_chunk(const bsde_xpath_desc* d) {
+  static const int ctas = [] { const char* e = getenv("BSDE_DEFER_CTAS"); return e ? atoi(e) : 2; }();   // CTAs per pair (tools)
+  return std::max(1, std::min(d->nit, 148 / (std::max(1, ctas) * d->S)));
+}
+// scratch of the batched weight-gradient launches: the largest over the chunk sizes that occur (c and the remainder nit % c:
+// a smaller chunk gets MORE splits per pair, so its partial tiles can be the larger ones)
+static size_t defer_wgrad_bytes(const bsde_xpath_desc* d) {
+  const int c = defer_chunk(d);
+  size_t wg = 0;
+  for (int cnt : {c, d->nit % c}) {
+    if (cnt < 1) continue;
+    for (int l = 0; l < d->nlayers; ++l) wg = std::max(wg, wgrad_ws(&d->layers[l], d->S * cnt, d->B, d->math));
+  }
+  return wg;
+}
 // extra floats of the deferred mode: dZ of every iteration, the gx trajectory, the [k][s][P] gradient buffer, (t_k, dt_k)
 static size_t defer_extra_floats(const bsde_xpath_desc* d) {
   size_t f = 0;
@@ -397,7 +411,7 @@ static size_t defer_extra_floats(const bsde_xpath_desc* d) {
 // Activations are stored layer-major [layer][k][s] (instead of [k][layer]) when the deferred mode applies: a function of the
 // descriptor only, so that bsde_xpath_fwd (which writes them) and bsde_xpath_bwd (which reads them) always agree.
 static bool xpath_layer_major(const bsde_xpath_desc* d) {
-  if (!defer_enabled() || d->math != BSDE_MATH_TC || d->act == BSDE_ACT_SWISH || d->nit < 2 || d->S > 74) return false;
+  if (!defer_enabled() || d->math != BSDE_MATH_TC || d->act == BSDE_ACT_SWISH || d->nit < 2 || d->S > 37) return false;
   for (int l = 0; l + 1 < d->nlayers; ++l)
     if ((act_elems(d, l) * sizeof(float)) % 256 != 0) return false;          // slots must be exactly S * per-sample floats
   for (int l = 0; l < d->nlayers; ++l) {                                     // dense HWIO leaves, time row last (JAX front end)
@@ -429,10 +443,7 @@ extern "C" size_t bsde_xpath_workspace_bytes(const bsde_xpath_desc* d, int32_t b
   }
   tot += align_up(prepack_floats(d, backward, true) * sizeof(float));
   if (backward == 2 && xpath_layer_major(d)) {   // reverse pass with stored activations: deferred weight gradients
-    size_t wg = 0;
-    const int c = defer_chunk(d);
-    for (int l = 0; l < d->nlayers; ++l) wg = std::max(wg, wgrad_ws(&d->layers[l], d->S * c, d->B, d->math));
-    tot += align_up(wg) + align_up(defer_extra_floats(d) * sizeof(float));
+    tot += align_up(defer_wgrad_bytes(d)) + align_up(defer_extra_floats(d) * sizeof(float));
   }
   return tot;
 }
@@ -535,10 +546,8 @@ static int xpath_bwd_deferred(const bsde_xpath_desc* d, const float* h_tk, const
   if (int e = prepack_all(d, 1, false, d_wtraj, (float*)ws, pp, st)) return e;
   ws += align_up(prepack_floats(d, 1, true) * sizeof(float));
   const int c = defer_chunk(d);
-  size_t wgd = 0;
-  for (int l = 0; l < n; ++l) wgd = std::max(wgd, wgrad_ws(&d->layers[l], S * c, d->B, d->math));
   void* wg_ws = ws;
-  const size_t wg_bytes = align_up(wgd);
+  const size_t wg_bytes = align_up(defer_wgrad_bytes(d));
   ws += wg_bytes;
   float* fp = (float*)ws;
   float* dzs[BSDE_MAX_LAYERS];
