@@ -289,15 +289,20 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
       }
     } else
     if (a.gather) {
-      // ---- stride-2 layers: per-(tap, half) gathered slabs; one table entry per output position of the tile
+      // ---- stride-2 layers: per-(tap, half) gathered slabs.  Per tile, one table entry per output position: the offset of
+      // input pixel (2y, 2x) and a bit mask of the taps whose source pixel is inside the image.  Every thread then keeps the
+      // source pointers and masks of its four rows in registers for the 18 slabs of the tile (one test, one 64-bit add and
+      // one select per 16-byte copy; the per-copy coordinate arithmetic made the producers the critical path: ncu source
+      // page, 60 % of the launch's instructions).
       const int r0 = pt >> 3;
       const uint32_t swz = (uint32_t)((c ^ (r0 & 7)) << 4);
+      constexpr int RPT = 128 / (WN_PROD / 8);   // rows per thread
 #pragma unroll 1
       for (int tile = g; tile < a.ntiles; tile += a.G) {
         asm volatile("bar.sync 1, %0;" ::"n"(WN_PROD) : "memory");
         if (pt < 128) {
           const int q = tile * 128 + pt;
-          int base = -1, yx = 0;
+          int base = 0, mask = 0;
           if (q < a.Q) {
             int img = (int)((float)q * rIP);
             int r = q - img * a.IP;
@@ -306,12 +311,23 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
             int x = r - y * a.pitch;
             if (x < 0) { --y; x += a.pitch; } else if (x >= a.pitch) { ++y; x -= a.pitch; }
             base = ((img * a.hin + 2 * y) * a.win + 2 * x) * a.cin;
-            yx = (y << 16) | x;
+            for (int e = 0; e < a.nent; ++e) {
+              const int iy = 2 * y + a.ent[e].kh * a.kn + a.off, ix = 2 * x + a.ent[e].kw * a.kn + a.off;
+              if ((unsigned)iy < (unsigned)a.hin && (unsigned)ix < (unsigned)a.win) mask |= 1 << e;
+            }
           }
           s_tab[2 * pt] = base;
-          s_tab[2 * pt + 1] = yx;
+          s_tab[2 * pt + 1] = mask;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(WN_PROD) : "memory");
+        const float* rp[RPT];
+        int rm[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+          const int r = r0 + k * (WN_PROD / 8);
+          rp[k] = in + s_tab[2 * r] + c * 4;
+          rm[k] = s_tab[2 * r + 1];
+        }
 #pragma unroll 1
         for (int e = 0; e < a.nent; ++e) {
           const int th = a.ent[e].kh * a.kn + a.off, tw = a.ent[e].kw * a.kn + a.off;
@@ -321,16 +337,13 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
             const int slot = cnt % a.ring;
             if (cnt >= (uint32_t)a.ring) mbar_wait(empty_bar(slot), ((cnt / a.ring) & 1) ^ 1);
             const uint32_t sb = s_ring + slot * a.slab_bytes + swz;
-            const int ch = h * 32 + c * 4;
-            const bool cok = ch < a.cin;
+            const bool cok = h * 32 + c * 4 < a.cin;
+            const int off = toff + h * 32;
             if (!(a.dbg & 1)) {
 #pragma unroll
-              for (int k = 0; k < 128 / (WN_PROD / 8); ++k) {
-                const int r = r0 + k * (WN_PROD / 8);
-                const int base = s_tab[2 * r], yx = s_tab[2 * r + 1];
-                const int iy = 2 * (yx >> 16) + th, ix = 2 * (yx & 0xFFFF) + tw;
-                const bool ok = base >= 0 && cok && (unsigned)iy < (unsigned)a.hin && (unsigned)ix < (unsigned)a.win;
-                cp_async16(sb + r * 128, ok ? in + base + toff + ch : in, ok);
+              for (int k = 0; k < RPT; ++k) {
+                const bool ok = cok && ((rm[k] >> e) & 1);
+                cp_async16(sb + (r0 + k * (WN_PROD / 8)) * 128, ok ? rp[k] + off : in, ok);
               }
             }
             cp_async_arrive_noinc(full_bar(slot));
@@ -563,7 +576,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
           int oy = y, ox = x;
           if (a.mode == 3) { oy = 2 * y + (ac >> 1); ox = 2 * x + (ac & 1); }
           __syncwarp();
-          w_pix[lane] = valid ? (img * a.hout + oy) * a.wout + ox : -1;
+          w_pix[lane] = valid ? ((img * a.hout + oy) * a.wout + ox) * a.opitch : -1;   // element offset of the output pixel (< 2^31: tconv_win_supported)
           __syncwarp();   // the rows are read by other lanes right below
         }
         // combine epilogues (Euler / data-gradient / accumulate): the loads of the values already stored at this lane's output
@@ -580,7 +593,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
           if (EPI >= BSDE_EPI_EULER) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              xv[j] = pp[j] >= 0 ? *reinterpret_cast<const float4*>(aux + (long long)pp[j] * a.opitch + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+              xv[j] = pp[j] >= 0 ? *reinterpret_cast<const float4*>(aux + (pp[j] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         uint32_t v[16];
@@ -634,7 +647,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
               qq.x = wn_combine<EPI, ACT>(qq.x, xv[j].x, a.scale); qq.y = wn_combine<EPI, ACT>(qq.y, xv[j].y, a.scale);
               qq.z = wn_combine<EPI, ACT>(qq.z, xv[j].z, a.scale); qq.w = wn_combine<EPI, ACT>(qq.w, xv[j].w, a.scale);
             }
-            *reinterpret_cast<float4*>(out + (long long)pp[j] * a.opitch + n) = qq;
+            *reinterpret_cast<float4*>(out + (pp[j] + n)) = qq;
           }
         } else {
           // partial chunk / cout not a multiple of 4: rows r8 + 8 j, columns c4 + 4 i
@@ -646,7 +659,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
 #pragma unroll 1
             for (int cc = c4; cc < ncol; cc += 4) {
               const float qq = stage[rr * 16 + ((((cc >> 2) ^ ((rr >> 1) & 3)) << 2) | (cc & 3))];
-              const long long o = (long long)pq * a.opitch + n0 + cc;
+              const int o = pq + n0 + cc;
               const float xx = EPI >= BSDE_EPI_EULER ? aux[o] : 0.f;
               out[o] = wn_combine<EPI, ACT>(qq, xx, a.scale);
             }
