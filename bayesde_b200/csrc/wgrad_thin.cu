@@ -167,8 +167,11 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_thin_kernel(const __grid_
         }
       }
     };
-    // this thread's fixed part of Bm: column n, k & 3 = kk  (four lanes -> one 16-byte chunk: conflict-free stores)
-    const int kk = tid & 3, n = tid >> 2;
+    // this thread's fixed part of Bm: column n (a warp covers 32 consecutive columns: conflict-free 16-byte stores) and the
+    // k-quads kq, kq + 4, ... of every stage: four window reads feed ONE 16-byte store of the K-major chunk [n][k .. k + 3]
+    // (the scalar form -- one 4-byte store per element -- made the builders the critical path: 62 % of the launch's
+    // instructions on the two lines of the read and the store, ncu source page)
+    const int n = (warp & 1) * 32 + lane, kq = warp >> 1;
     const int tap = n / a.cpt, c = n - tap * a.cpt;
     const bool real = n < a.ncols;
     // case B ones column: the valid flag of the shifted position
@@ -192,14 +195,23 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_thin_kernel(const __grid_
       if (it >= 2) mbar_wait(bempty(bb), ((it >> 1) & 1) ^ 1);
       const float* win = s_win + bb * a.NW * WT_CW;
       float* bt = g_b + bb * (WT_KS * WT_NPAD);
+      const float* wsrc = win + wofs * WT_CW + wc;
+      const float* wflag = win + a.halo * WT_CW + WT_CW - 1;
+      const int kreal = real ? a.Q - q0 : 0;               // positions k < kreal of this stage exist
 #pragma unroll 4
-      for (int k4 = 0; k4 < WT_KS / 4; ++k4) {
-        const int k = k4 * 4 + kk;
-        float v = 0.f;
-        if (real && q0 + k < a.Q) v = win[(k + wofs) * WT_CW + wc];
+      for (int i = 0; i < WT_KS / 16; ++i) {
+        const int k = (kq + 4 * i) * 4;
+        float4 v;
+        v.x = k + 0 < kreal ? wsrc[(k + 0) * WT_CW] : 0.f;
+        v.y = k + 1 < kreal ? wsrc[(k + 1) * WT_CW] : 0.f;
+        v.z = k + 2 < kreal ? wsrc[(k + 2) * WT_CW] : 0.f;
+        v.w = k + 3 < kreal ? wsrc[(k + 3) * WT_CW] : 0.f;
         // tile of k-step k >> 3: [chunk (k >> 2) & 1][n][4 floats]
-        bt[(k >> 3) * (WT_NPAD * 8) + (((k >> 2) & 1) * WT_NPAD + n) * 4 + kk] = v;
-        if (a.big_is_input) tsum = fmaf(win[(k + a.halo) * WT_CW + WT_CW - 1], v, tsum);
+        *reinterpret_cast<float4*>(bt + (k >> 3) * (WT_NPAD * 8) + (((k >> 2) & 1) * WT_NPAD + n) * 4) = v;
+        if (a.big_is_input) {
+          tsum = fmaf(wflag[(k + 0) * WT_CW], v.x, tsum); tsum = fmaf(wflag[(k + 1) * WT_CW], v.y, tsum);
+          tsum = fmaf(wflag[(k + 2) * WT_CW], v.z, tsum); tsum = fmaf(wflag[(k + 3) * WT_CW], v.w, tsum);
+        }
       }
       fence_proxy_async();
       mbar_arrive(bfull(bb));
@@ -214,9 +226,11 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_thin_kernel(const __grid_
     // =============================== epilogue ===============================
     float* __restrict__ part = a.partial + ((long long)(s * a.SPL + split) * a.rows) * a.cols;
     if (a.big_is_input) {
-      tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
-      tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
-      if (kk == 0 && real) {
+      // the four k-quad partial sums of column n live in four warps: fixed-order sum through the (now free) window buffer
+      s_win[kq * WT_NPAD + n] = tsum;
+      asm volatile("bar.sync 1, %0;" ::"n"(WT_BUILD) : "memory");
+      if (kq == 0 && real) {
+        tsum = (s_win[n] + s_win[WT_NPAD + n]) + (s_win[2 * WT_NPAD + n] + s_win[3 * WT_NPAD + n]);
         if (a.has_time) part[(long long)(tap * a.Kc + a.cin) * a.cols + c] = a.t * tsum;
         if (tap == 4) part[(long long)a.Ktot * a.cols + c] = tsum;
       }
