@@ -67,6 +67,7 @@ struct WinArgs {
   float t, scale;
   uint32_t aoff[WN_MAXENT];  // A start offset of each entry in 16-byte units (plane region + shifted row)
   uint32_t dcol[WN_MAXENT];  // accumulator column offset | (first tap of its accumulator) << 31
+  int pf;     // epilogue: L2 prefetch of the next tile's combine operand (BSDE_WIN_PF, default on)
   int wsafe;  // the weight image was written before the previous kernel in the stream started: load it before pdl_wait()
   int dbg;  // tools/ only (BSDE_WIN_DBG): 1 skip window copies, 2 skip MMAs, 4 skip epilogue stores
   WinEntry ent[WN_MAXENT];
@@ -563,6 +564,29 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
       }
       // border class of this position (selects the time-term row)
       const int cls = (((y == 0) | ((y == a.Hq - 1) << 1)) << 2) | ((x == 0) | ((x == a.Wq - 1) << 1));
+      if (EPI >= BSDE_EPI_EULER && a.pf) {
+        // combine operand of this CTA's NEXT tile -> L2 now (one tile of MMAs and epilogue ahead): the loads at the head of
+        // every item otherwise wait out a DRAM round trip with two warps per scheduler to cover it (data-gradient launches:
+        // 84 -> 188 us with the combine operand against without).  Warp `half` takes every second 128-byte line of a pixel.
+        const int qn = (tile + a.G) * 128 + quarter * 32 + lane;
+        if (qn < a.Q) {
+          int im = (int)((float)qn * e_rIP);
+          int r = qn - im * a.IP;
+          if (r < 0) { --im; r += a.IP; } else if (r >= a.IP) { ++im; r -= a.IP; }
+          int yn = (int)((float)r * e_rpitch);
+          int xn = r - yn * a.pitch;
+          if (xn < 0) { --yn; xn += a.pitch; } else if (xn >= a.pitch) { ++yn; xn -= a.pitch; }
+          if (yn < a.Hq && xn < a.Wq) {
+            const int nline = (a.cout * 4 + 127) >> 7;
+            for (int acn = 0; acn < a.NA; ++acn) {
+              int oy = yn, ox = xn;
+              if (a.mode == 3) { oy = 2 * yn + (acn >> 1); ox = 2 * xn + (acn & 1); }
+              const float* pa = aux + ((im * a.hout + oy) * a.wout + ox) * a.opitch;
+              for (int l = half; l < nline; l += 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + l * 32));
+            }
+          }
+        }
+      }
       mbar_wait(accf_bar(buf), (it / a.nbuf) & 1);
       tc_fence_after();
       int last_ac = -1;
@@ -970,6 +994,7 @@ static int win_launch_one(const bsde_conv_layer* L, int S, int B, const float* i
   a.hslab = p.hslab; a.nslab = p.nslab; a.region = p.region; a.gather = p.gather;
   a.tma = p.gather ? 0 : p.tma; a.NR = p.NR; a.box_bytes = p.box_bytes;
   a.t = t; a.scale = scale;
+  { static const int pf = getenv("BSDE_WIN_PF") ? atoi(getenv("BSDE_WIN_PF")) : 1; a.pf = pf; }
   { static const int dbg = getenv("BSDE_WIN_DBG") ? atoi(getenv("BSDE_WIN_DBG")) : 0; a.dbg = dbg; }
   for (int e = 0; e < p.nent; ++e) {
     a.ent[e] = p.ent[e];

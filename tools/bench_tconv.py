@@ -21,6 +21,7 @@ p.add_argument("--warm", type=int, default=3)
 p.add_argument("--no_wgrad", action="store_true")
 p.add_argument("--epi_bias", action="store_true", help="EPI_BIAS for the forward geometry too (the taps-on-N path serves BIAS / EULER / ACCUM)")
 p.add_argument("--layers", default="", help="comma list of layer indices (default all)")
+p.add_argument("--dact", action="store_true", help="data gradients with the EPI_DACT epilogue (scale * acc * act'(aux)), as the reverse pass runs them")
 a = p.parse_args()
 L = _lib.lib()
 dev = "cuda:0"
@@ -53,9 +54,13 @@ for g in [int(v) for v in a.groups.split(",")]:
             nb = L.bsde_tconv_fwd_workspace_bytes(C.byref(lay), a.S, math)
             ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
             epi = _lib.EPI_BIAS_ACT if (kind == "fwd" and not a.epi_bias) else _lib.EPI_BIAS
+            aux = None
+            if kind == "dgrad" and a.dact:
+                epi = _lib.EPI_DACT
+                aux = torch.rand(a.S, a.B, lay.hout, lay.wout, lay.cout, device=dev) + 0.1
 
             def run():
-                st = L.bsde_tconv_fwd(C.byref(lay), a.S, a.B, _lib.ptr(x), _lib.ptr(w), fx.P, 0.3, 0, epi, 1.0, None,
+                st = L.bsde_tconv_fwd(C.byref(lay), a.S, a.B, _lib.ptr(x), _lib.ptr(w), fx.P, 0.3, 0, epi, 1.0, _lib.ptr(aux) if aux is not None else None,
                                       _lib.ptr(out), math, C.c_void_p(ws.data_ptr()), nb, _lib.stream_ptr())
                 _lib.check(st, "tconv")
             for _ in range(a.warm):
