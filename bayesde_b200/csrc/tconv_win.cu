@@ -587,38 +587,53 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
           }
         }
       }
-      mbar_wait(accf_bar(buf), (it / a.nbuf) & 1);
-      tc_fence_after();
-      int last_ac = -1;
+      // element offsets (< 2^31: tconv_win_supported) of this tile's output pixels, accumulator 0: row `lane` publishes its own,
+      // every lane then keeps those of its four store rows r8 + 8 j for all items of the tile; accumulator ac of a
+      // transposed layer writes the pixel (ac >> 1) rows down and (ac & 1) columns right of it
+      int pp[4];
+      {
+        int oy = y, ox = x;
+        if (a.mode == 3) { oy = 2 * y; ox = 2 * x; }
+        __syncwarp();   // the previous tile's readers are done
+        w_pix[lane] = valid ? ((img * a.hout + oy) * a.wout + ox) * a.opitch : -1;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pp[j] = w_pix[r8 + 8 * j];
+      }
       int ac = 0, ch_i = half;  // item = ac * nchunk + ch_i, stepping by 2 without a division
       while (ch_i >= nchunk) { ch_i -= nchunk; ++ac; }
+      // combine epilogues (Euler / data-gradient / accumulate): the values already stored at the output positions are loaded ONE
+      // ITEM AHEAD (the first item's before the accumulator is even complete), so that their L2 latency runs under a whole item
+      // of TMEM load, row arithmetic, staging exchange and stores -- two epilogue warps per scheduler cannot hide it otherwise
+      float4 xn[4];
+#define WN_LOAD_AUX(ac_, ch_)                                                                                              \
+  {                                                                                                                        \
+    const int n0_ = (ch_) * 16;                                                                                            \
+    if (vec_out && a.cout - n0_ >= 16) {                                                                                   \
+      const int o_ = (a.mode == 3 ? (((ac_) >> 1) * a.wout + ((ac_) & 1)) * a.opitch : 0) + n0_ + c4 * 4;                  \
+      xn[0] = pp[0] >= 0 ? *reinterpret_cast<const float4*>(aux + (pp[0] + o_)) : make_float4(0.f, 0.f, 0.f, 0.f);         \
+      xn[1] = pp[1] >= 0 ? *reinterpret_cast<const float4*>(aux + (pp[1] + o_)) : make_float4(0.f, 0.f, 0.f, 0.f);         \
+      xn[2] = pp[2] >= 0 ? *reinterpret_cast<const float4*>(aux + (pp[2] + o_)) : make_float4(0.f, 0.f, 0.f, 0.f);         \
+      xn[3] = pp[3] >= 0 ? *reinterpret_cast<const float4*>(aux + (pp[3] + o_)) : make_float4(0.f, 0.f, 0.f, 0.f);         \
+    }                                                                                                                      \
+  }
+      const int na_run = (a.dbg & 8) ? 0 : a.NA;
+      if (EPI >= BSDE_EPI_EULER && ac < na_run) WN_LOAD_AUX(ac, ch_i)
+      mbar_wait(accf_bar(buf), (it / a.nbuf) & 1);
+      tc_fence_after();
 #pragma unroll 1
-      for (; ac < ((a.dbg & 8) ? 0 : a.NA);) {
+      for (; ac < na_run;) {
         const int n0 = ch_i * 16;
-        if (ac != last_ac) {
-          last_ac = ac;
-          int oy = y, ox = x;
-          if (a.mode == 3) { oy = 2 * y + (ac >> 1); ox = 2 * x + (ac & 1); }
-          __syncwarp();
-          w_pix[lane] = valid ? ((img * a.hout + oy) * a.wout + ox) * a.opitch : -1;   // element offset of the output pixel (< 2^31: tconv_win_supported)
-          __syncwarp();   // the rows are read by other lanes right below
-        }
-        // combine epilogues (Euler / data-gradient / accumulate): the loads of the values already stored at this lane's output
-        // positions are issued FIRST, so that their L2 / DRAM latency runs under the TMEM load, the row arithmetic and the
-        // staging exchange (two epilogue warps per scheduler cannot hide it otherwise)
+        const int dac = a.mode == 3 ? ((ac >> 1) * a.wout + (ac & 1)) * a.opitch : 0;
         const int ncol = min(16, a.cout - n0);
         const bool fast = vec_out && ncol == 16;
-        int pp[4];
+        int ac2 = ac, ch2 = ch_i + 2;
+        while (ch2 >= nchunk) { ch2 -= nchunk; ++ac2; }
         float4 xv[4];
-        if (fast) {
-          const int n = n0 + c4 * 4;
+        if (EPI >= BSDE_EPI_EULER) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) pp[j] = w_pix[r8 + 8 * j];
-          if (EPI >= BSDE_EPI_EULER) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              xv[j] = pp[j] >= 0 ? *reinterpret_cast<const float4*>(aux + (pp[j] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int j = 0; j < 4; ++j) xv[j] = xn[j];
+          if (ac2 < na_run) WN_LOAD_AUX(ac2, ch2)
         }
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * a.NA + ac) * a.npad + n0), v);
@@ -656,7 +671,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
         __syncwarp();
         if (fast) {
           // lane -> fixed column group c4, rows r8 + 8 j: 64 contiguous bytes per row
-          const int n = n0 + c4 * 4;
+          const int n = dac + n0 + c4 * 4;
           float4 qv[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -678,20 +693,20 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) {
             const int rr = r8 + 8 * j;
-            const int pq = w_pix[rr];
+            const int pq = w_pix[rr];   // (pp[] stays in registers: no dynamic index)
             if (pq < 0) continue;
 #pragma unroll 1
             for (int cc = c4; cc < ncol; cc += 4) {
               const float qq = stage[rr * 16 + ((((cc >> 2) ^ ((rr >> 1) & 3)) << 2) | (cc & 3))];
-              const int o = pq + n0 + cc;
+              const int o = pq + dac + n0 + cc;
               const float xx = EPI >= BSDE_EPI_EULER ? aux[o] : 0.f;
               out[o] = wn_combine<EPI, ACT>(qq, xx, a.scale);
             }
           }
         }
-        ch_i += 2;
-        while (ch_i >= nchunk) { ch_i -= nchunk; ++ac; }
+        ac = ac2; ch_i = ch2;
       }
+#undef WN_LOAD_AUX
       // this warp has drained its share of accumulator buffer `buf`
       tc_fence_before();
       __syncwarp();
