@@ -67,6 +67,9 @@ struct WwArgs {
   int tapj[2][WW_MAXENT][3];      // weight tap of N-block j (packed) or of the entry ([0])
   int bias_row[2][WW_MAXENT][3];  // >= 0: this (entry, block)'s ones sum is bias partial row Ktot + bias_row
   int packed, u_is_input;
+  int vpar;                       // V is held as parity planes (lhs-dilated forward layers)
+  int tapsplit;                   // the two CTA groups of a sample split the TAPS (by parity class of V), not the V channels
+  int vpl[2][4];                  // tapsplit: parity class held by V plane p of group g
   int cin, cout, Kc, Ktot, has_time, rows, cols;
   float t;
   int dbg;  // tools/ only (BSDE_WW_DBG): 1 skip copies, 2 skip MMAs, 4 skip the source tables
@@ -107,9 +110,9 @@ __device__ __forceinline__ bool ww_decode(int q, int Q, int IP, int pitch, int H
   if (x < 0) { --y; x += pitch; } else if (x >= pitch) { ++y; x -= pitch; }
   return y < Hq && x < Wq;
 }
-__device__ __forceinline__ int ww_plane_src(bool ok, int img, int y, int x, int np, int plane, int h, int w, int c) {
+__device__ __forceinline__ int ww_plane_src(bool ok, int img, int y, int x, bool par, int plane, int h, int w, int c) {
   if (!ok) return -1;
-  if (np == 4) { y = 2 * y + (plane >> 1); x = 2 * x + (plane & 1); }
+  if (par) { y = 2 * y + (plane >> 1); x = 2 * x + (plane & 1); }
   if (y >= h || x >= w) return -1;
   return ((img * h + y) * w + x) * c;
 }
@@ -196,16 +199,16 @@ __device__ __forceinline__ void ww_copy_rows(const float* __restrict__ src, cons
 
 // MMA issue loop of one CTA; NE > 0: entry count known at compile time (descriptor offsets stay in uniform registers)
 template <int NE>
-__device__ __forceinline__ void ww_issue(const WwArgs& a, int nst, int qbeg, uint32_t base, uint32_t bars, uint32_t tm) {
+__device__ __forceinline__ void ww_issue(const WwArgs& a, int tg, int nst, int qbeg, uint32_t base, uint32_t bars, uint32_t tm) {
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                          ((uint32_t)(a.Nmma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint64_t a_hi = desc_hi((uint32_t)a.regU, 512u, 1);
   const uint64_t b_hi = desc_hi(a.lboB, 512u, 1);
-  const int ncnt = NE > 0 ? NE : a.ncnt[0];
+  const int ncnt = NE > 0 ? NE : a.ncnt[tg];
   uint32_t ao[NE > 0 ? NE : 1], bo[NE > 0 ? NE : 1];
   if (NE > 0) {
 #pragma unroll
-    for (int e = 0; e < NE; ++e) { ao[e] = a.aoff[0][e]; bo[e] = a.boff[0][e]; }
+    for (int e = 0; e < NE; ++e) { ao[e] = a.aoff[tg][e]; bo[e] = a.boff[tg][e]; }
   }
   const uint32_t nm = (uint32_t)a.Nmma;
   const bool dbgm = g_ww_dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
@@ -235,8 +238,8 @@ __device__ __forceinline__ void ww_issue(const WwArgs& a, int nst, int qbeg, uin
       } else {
 #pragma unroll 1
         for (int e = 0; e < ncnt; ++e)
-          umma_tf32_elect(tm + (uint32_t)e * nm, a_hi | (uint64_t)((kofs + oU + a.aoff[0][e]) & 0x3FFFu),
-                          b_hi | (uint64_t)((kofs + oV + a.boff[0][e]) & 0x3FFFu), idesc, acc);
+          umma_tf32_elect(tm + (uint32_t)e * nm, a_hi | (uint64_t)((kofs + oU + a.aoff[tg][e]) & 0x3FFFu),
+                          b_hi | (uint64_t)((kofs + oV + a.boff[tg][e]) & 0x3FFFu), idesc, acc);
       }
     }
     umma_commit_elect(bars + 8u * (4 + st));
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
   const int s = blockIdx.x / (a.TG * a.SPL);
   const int rem = blockIdx.x - s * a.TG * a.SPL;
   const int vg = rem / a.SPL, split = rem - vg * a.SPL;  // this CTA's group of V channels (accumulator columns)
-  const int tg = 0;
+  const int tg = a.tapsplit ? vg : 0;   // entry table of this CTA
   const int qbeg = split * a.chunk, qend = min(a.Q, qbeg + a.chunk);
   const int nst = qend > qbeg ? (qend - qbeg + a.KS - 1) / a.KS : 0;
 
@@ -316,11 +319,12 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
       if (!(a.dbg & 4)) {
         if (!a.tmaU && tid < a.KS) {
           const bool ok = pu.q < qend && ww_pos_valid(pu, geo);
-          for (int p = 0; p < a.NPU; ++p) tU[p * a.KS + tid] = ww_plane_src(ok, pu.img, pu.y, pu.x, a.NPU, p, a.hU, a.wU, a.cu);
+          for (int p = 0; p < a.NPU; ++p) tU[p * a.KS + tid] = ww_plane_src(ok, pu.img, pu.y, pu.x, a.NPU == 4, p, a.hU, a.wU, a.cu);
         }
         if (!a.tmaV && tid < a.NPOSw) {
           const bool ok = ww_pos_valid(pv, geo);
-          for (int p = 0; p < a.NPV; ++p) tV[p * a.NPOSw + tid] = ww_plane_src(ok, pv.img, pv.y, pv.x, a.NPV, p, a.hV, a.wV, a.cv);
+          for (int p = 0; p < a.NPV; ++p)
+            tV[p * a.NPOSw + tid] = ww_plane_src(ok, pv.img, pv.y, pv.x, a.vpar != 0, a.tapsplit ? a.vpl[tg][p] : p, a.hV, a.wV, a.cv);
         }
         ww_pos_advance(pu, a.KS, geo);
         ww_pos_advance(pv, a.KS, geo);
@@ -448,9 +452,11 @@ __global__ void __launch_bounds__(WW_THREADS, 1) wgrad_win_kernel(const __grid_c
     // whole warp, uniform operands, one elected lane issues
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int ncnt = a.ncnt[tg];
-    if (ncnt == 9) ww_issue<9>(a, nst, qbeg, base, bars, tm);
-    else if (ncnt == 3) ww_issue<3>(a, nst, qbeg, base, bars, tm);
-    else ww_issue<0>(a, nst, qbeg, base, bars, tm);
+    if (ncnt == 9) ww_issue<9>(a, tg, nst, qbeg, base, bars, tm);
+    else if (ncnt == 5) ww_issue<5>(a, tg, nst, qbeg, base, bars, tm);
+    else if (ncnt == 4) ww_issue<4>(a, tg, nst, qbeg, base, bars, tm);
+    else if (ncnt == 3) ww_issue<3>(a, tg, nst, qbeg, base, bars, tm);
+    else ww_issue<0>(a, tg, nst, qbeg, base, bars, tm);
     __syncwarp();
   }
   tc_fence_before();
@@ -597,14 +603,37 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
   // 32-channel block (each CTA then loads all of U but only its block of V)
   a.TG = 1;
   a.vgch = 32 * a.nbV;
+  a.vpar = a.NPV == 4;
+  int egrp[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // CTA group of each entry
+  int per = ne;
   if (ne * a.Nmma > 512) {
     if (a.packed) return p;
-    a.TG = a.nbV;
-    a.nbV = 1;
-    a.vgch = 32;
-    a.Nmma = 32;
+    // lhs-dilated layers (V = four parity classes of dY): the two CTA groups split the TAPS by class -- {(1,1), (0,0)} = 4 + 1
+    // taps and {(0,1), (1,0)} = 2 + 2 taps -- and keep the full N: the same bytes per CTA as a split of the V channels (two
+    // of the four class planes, all channels), but 5 / 4 MMAs with N = 64 per k-step instead of 9 with N = 32 (the A operand
+    // is read once per MMA whatever N is: 240 / 192 instead of 360 shared-memory cycles per k-step).  BSDE_WW_TAPSPLIT=0: channels.
+    static const int tsp = getenv("BSDE_WW_TAPSPLIT") ? atoi(getenv("BSDE_WW_TAPSPLIT")) : 1;
+    if (tsp && mode == 3 && a.u_is_input && 5 * a.Nmma <= 512) {
+      a.tapsplit = 1;
+      a.TG = 2;
+      a.NPV = 2;
+      a.vgch = 0;
+      a.vpl[0][0] = 3; a.vpl[0][1] = 0; a.vpl[1][0] = 1; a.vpl[1][1] = 2;
+      per = 0;
+      int cnt[2] = {0, 0};
+      for (int i = 0; i < ne; ++i) {
+        const int cls = ents[i].vp;
+        egrp[i] = (cls == 3 || cls == 0) ? 0 : 1;
+        ents[i].vp = (cls == 3 || cls == 1) ? 0 : 1;   // local plane of the class inside its group
+        per = std::max(per, ++cnt[egrp[i]]);
+      }
+    } else {
+      a.TG = a.nbV;
+      a.nbV = 1;
+      a.vgch = 32;
+      a.Nmma = 32;
+    }
   }
-  const int per = ne;
   a.tmem_cols = ww_pow2_cols(per * a.Nmma);
   if (a.tmem_cols > 512) return p;
 
@@ -615,7 +644,7 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
   // (profiles/r01_summary.md): opt-in
   static const int tma_on = getenv("BSDE_WW_TMA") ? atoi(getenv("BSDE_WW_TMA")) : 0;
   a.tmaU = tma_on && (a.cu % 32) == 0 && 2 * a.pitch <= 256;
-  a.tmaV = tma_on && (a.cv % 32) == 0 && !a.v_ones && 2 * a.pitch <= 256;
+  a.tmaV = tma_on && (a.cv % 32) == 0 && !a.v_ones && 2 * a.pitch <= 256 && !a.tapsplit;
   a.box_bytes = a.pitch * 128;
   auto rup = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
   // larger stages first (the per-stage fixed cost is ~2-3 k cycles), then ring depth
@@ -653,7 +682,7 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
 
   for (int g = 0; g < 2; ++g) a.ncnt[g] = 0;
   for (int i = 0; i < ne; ++i) {
-    const int g = 0, k = a.ncnt[g]++;
+    const int g = egrp[i], k = a.ncnt[g]++;
     a.aoff[g][k] = (uint32_t)(ents[i].up * a.nbU * a.regU) >> 4;
     a.boff[g][k] = (uint32_t)(a.v_off + ents[i].vp * a.nbV * a.regV + (a.lead + ents[i].sh) * 128) >> 4;
     for (int j = 0; j < 3; ++j) { a.tapj[g][k][j] = ents[i].tapj[j]; a.bias_row[g][k][j] = ents[i].brow[j]; }
@@ -724,7 +753,7 @@ int tconv_wgrad_win(const bsde_conv_layer* L, int S, int B, const float* in, con
       return 0;
     };
     if (a.tmaU) { if (int e = make(&tmU, a.U, a.cu, a.wU, a.hU, a.NPU)) return e; }
-    if (a.tmaV) { if (int e = make(&tmV, a.V, a.cv, a.wV, a.hV, a.NPV)) return e; }
+    if (a.tmaV) { if (int e = make(&tmV, a.V, a.cv, a.wV, a.hV, a.vpar ? 4 : 1)) return e; }
   }
   BSDE_CUDA_OK(launch_pdl(wgrad_win_kernel, dim3(S * a.TG * a.SPL), dim3(WW_THREADS), p.smem, st, a, tmU, tmV));
   BSDE_CUDA_OK(cudaGetLastError());
