@@ -627,6 +627,16 @@ static WwPlan ww_plan(const bsde_conv_layer* L, int S, int B) {
         ents[i].vp = (cls == 3 || cls == 1) ? 0 : 1;   // local plane of the class inside its group
         per = std::max(per, ++cnt[egrp[i]]);
       }
+    } else if (tsp && mode == 1 && ne == 9 && 5 * a.Nmma <= 512) {
+      // stride-1 layers with a wide dY (64 / 80 channels): taps 0-4 (with the centre tap and its bias row) and taps 5-8, full N.
+      // Both groups stage the same rows; a split of the V channels into 32-channel groups would stage U once per group as well,
+      // issue 9 MMAs with N = 32 per k-step, and need THREE groups for 80 channels (216 CTAs for 72 pairs: one and a half waves)
+      a.tapsplit = 1;
+      a.TG = 2;
+      a.vgch = 0;
+      a.vpl[0][0] = a.vpl[1][0] = 0;
+      for (int i = 0; i < ne; ++i) egrp[i] = i >= 5 ? 1 : 0;
+      per = 5;
     } else {
       a.TG = a.nbV;
       a.nbV = 1;
