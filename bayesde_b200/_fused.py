@@ -70,6 +70,9 @@ def split_fw_flat(cfg, fw_flat):
     return layers, betas
 
 
+_GRID_CACHE = {}
+
+
 class BlockConfig:
     """Static description of one SDEBNN block's fused solve."""
 
@@ -97,7 +100,15 @@ class BlockConfig:
     def grid_on(self, device):
         key = str(device)
         if key not in self._dev:
-            self._dev[key] = (torch.from_numpy(self.tk).to(device), torch.from_numpy(self.dtk).to(device))
+            # whole-solve grids recur every step (a BlockConfig is built per call): their device copies are shared process-wide,
+            # so that no step pays a pageable host -> device copy (which stalls the host until the stream has drained)
+            gkey = (key, self.tk.tobytes(), self.dtk.tobytes()) if len(self.tk) > 1 else None
+            if gkey is not None and gkey in _GRID_CACHE:
+                self._dev[key] = _GRID_CACHE[gkey]
+            else:
+                self._dev[key] = (torch.from_numpy(self.tk).to(device), torch.from_numpy(self.dtk).to(device))
+                if gkey is not None and len(_GRID_CACHE) < 256:
+                    _GRID_CACHE[gkey] = self._dev[key]
         return self._dev[key]
 
     def xdesc(self):

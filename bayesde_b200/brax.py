@@ -188,13 +188,20 @@ def SDEBNN(fx_block_type, fx_dim, fx_actfn, fw, diff_coef=1e-4, name="sdebnn", s
     ts = torch.linspace(0.0, 1.0, nsteps)  # brax.py:31
     cache = {}
 
-    def make_layer(input_shape):
+    def make_layer(input_shape, device=None):
         key = tuple(input_shape)
         if key not in cache:
             fx = FxSpec(fx_block_type, (1,) + tuple(input_shape[-3:]), fx_dim, fx_actfn)
             # brax.py:38-41: g_aug's `flat_w` is a throw-away fx.init from PRNGKey(0) (quirk Q2)
             cache[key] = (fx, fx.init(0))
-        return cache[key]
+        if device is None:
+            return cache[key]
+        # the device copy is made once: a pageable host -> device copy per call stalls the host until the stream has drained
+        # (one pipeline bubble per block and step: tools/step_gaps.py)
+        dkey = (key, str(device))
+        if dkey not in cache:
+            cache[dkey] = (cache[key][0], cache[key][1].to(device))
+        return cache[dkey]
 
     def init_fun(rng, input_shape, device=None):
         fx, _ = make_layer(input_shape)
@@ -215,9 +222,9 @@ def SDEBNN(fx_block_type, fx_dim, fx_actfn, fw, diff_coef=1e-4, name="sdebnn", s
         if squeeze_s:
             x = x.unsqueeze(0)
         S = x.shape[0]
-        fx, w_stale = make_layer(x.shape[1:])
+        fx, w_stale = make_layer(x.shape[1:], x.device)
         P = fx.P
-        dyn = _AugDynamics(fx, fw.spec, x.shape, diff_coef, stl, w_drift, math, w_stale.to(x.device), stream_id,
+        dyn = _AugDynamics(fx, fw.spec, x.shape, diff_coef, stl, w_drift, math, w_stale, stream_id,
                            remat=remat)
         # ranks that shard the MC samples: local sample s is global sample mc_offset + s of mc_total (Philox sample counter)
         dyn.sample_offset = int(kwargs.get("mc_offset", 0))
