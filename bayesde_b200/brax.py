@@ -308,6 +308,11 @@ def _unflatten_like(flat, tree, lead=0):
 def normal_logprob(z, mean, log_std):
     """brax.py:171-178."""
     c = math.log(2 * math.pi)
+    if isinstance(log_std, (int, float)):
+        # a Python scalar stays on the host: a device tensor made from it is a pageable host -> device copy, which stalls the
+        # host until the stream has drained (the head's KL sits between the forward and the reverse pass of every step)
+        tmp = (z - mean) * math.exp(-log_std)
+        return -0.5 * (tmp * tmp + (2 * log_std + c))
     log_std = torch.as_tensor(log_std, dtype=z.dtype, device=z.device)
     tmp = (z - mean) * torch.exp(-log_std)
     return -0.5 * (tmp * tmp + 2 * log_std + c)

@@ -50,6 +50,18 @@ busy += cur_e - cur_s
 tot = sum(e - s for s, e, _ in iv)
 print(f"steps {a.steps}: span {span / 1e3 / a.steps:.2f} ms/step, busy (union) {busy / 1e3 / a.steps:.2f}, idle {(span - busy) / 1e3 / a.steps:.2f}, "
       f"sum of kernel times {tot / 1e3 / a.steps:.2f} ({len(iv) // a.steps} kernels/step, {len(gaps) // a.steps} gaps/step)")
+t0 = iv[0][0]
+print("largest single gaps (ms since the first kernel, us):")
+big = []
+cur_e, last_name = iv[0][1], iv[0][2]
+for s_, e_, n_ in iv[1:]:
+    if s_ > cur_e:
+        big.append((s_ - cur_e, (cur_e - t0) / 1e3, last_name, n_))
+        cur_e, last_name = e_, n_
+    elif e_ > cur_e:
+        cur_e, last_name = e_, n_
+for d, at, pn, nn in sorted(big, reverse=True)[:24]:
+    print(f"  {d:7.1f} us at {at:8.2f} ms   {pn[:46]} -> {nn[:46]}")
 import collections  # noqa: E402
 
 agg = collections.defaultdict(lambda: [0, 0.0])
