@@ -67,6 +67,7 @@ struct WinArgs {
   float t, scale;
   uint32_t aoff[WN_MAXENT];  // A start offset of each entry in 16-byte units (plane region + shifted row)
   uint32_t dcol[WN_MAXENT];  // accumulator column offset | (first tap of its accumulator) << 31
+  int rev;    // walk the tiles from the last to the first: a consumer then starts on what its producer wrote last (still in L2)
   int pf;     // epilogue: L2 prefetch of the next tile's combine operand (BSDE_WIN_PF, default on)
   int wsafe;  // the weight image was written before the previous kernel in the stream started: load it before pdl_wait()
   int dbg;  // tools/ only (BSDE_WIN_DBG): 1 skip window copies, 2 skip MMAs, 4 skip epilogue stores
@@ -258,7 +259,8 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
         const int rows_img = a.Hq + 1;
 #pragma unroll 1
         for (int tile = g; tile < a.ntiles; tile += a.G) {
-          const int n0 = tile * 128 - a.lead;
+          const int tl = a.rev ? a.ntiles - 1 - tile : tile;   // physical tile
+          const int n0 = tl * 128 - a.lead;
           const int g0 = (n0 + 2 * a.pitch) / a.pitch - 2 + pt;  // floor(n0 / pitch) + r, n0 >= -(pitch + 1)
           const int img = (g0 + rows_img) / rows_img - 1;         // floor(g0 / rows_img), g0 >= -2
           const int y = g0 - img * rows_img;
@@ -300,9 +302,10 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
       constexpr int RPT = 128 / (WN_PROD / 8);   // rows per thread
 #pragma unroll 1
       for (int tile = g; tile < a.ntiles; tile += a.G) {
+        const int tl = a.rev ? a.ntiles - 1 - tile : tile;   // physical tile
         asm volatile("bar.sync 1, %0;" ::"n"(WN_PROD) : "memory");
         if (pt < 128) {
-          const int q = tile * 128 + pt;
+          const int q = tl * 128 + pt;
           int base = 0, mask = 0;
           if (q < a.Q) {
             int img = (int)((float)q * rIP);
@@ -354,7 +357,8 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
     } else
 #pragma unroll 1
     for (int tile = g; tile < a.ntiles; tile += a.G) {
-      const int q0 = tile * 128 - a.lead;
+      const int tl = a.rev ? a.ntiles - 1 - tile : tile;   // physical tile
+      const int q0 = tl * 128 - a.lead;
       // decode the window positions once per tile into the shared source table (read by other producer threads)
       asm volatile("bar.sync 1, %0;" ::"n"(WN_PROD) : "memory");  // last tile's readers are done
 #pragma unroll 1
@@ -454,6 +458,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
       int it = 0;
 #pragma unroll 1
       for (int tile = g; tile < a.ntiles; tile += a.G, ++it) {
+        const int tl = a.rev ? a.ntiles - 1 - tile : tile;   // physical tile
         const int buf = it % a.nbuf;
         if (it >= a.nbuf) {
           mbar_wait(acce_bar(buf), ((it / a.nbuf) & 1) ^ 1);
@@ -462,7 +467,7 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
         const uint32_t dbase = tm + (uint32_t)(buf * a.NA * a.npad);
         uint32_t o0 = 0;  // TMA-fed window: positions of the first grid row before position q0 - lead, in 16-byte units
         if (a.tma) {
-          const int n0 = tile * 128 - a.lead;
+          const int n0 = tl * 128 - a.lead;
           const int g0 = (n0 + 2 * a.pitch) / a.pitch - 2;
           o0 = (uint32_t)(n0 - g0 * a.pitch) * 8u;
         }
@@ -549,8 +554,9 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
     int it = 0;
 #pragma unroll 1
     for (int tile = g; tile < a.ntiles; tile += a.G, ++it) {
+      const int tl = a.rev ? a.ntiles - 1 - tile : tile;   // physical tile
       const int buf = it % a.nbuf;
-      const int q = tile * 128 + quarter * 32 + lane;
+      const int q = tl * 128 + quarter * 32 + lane;
       bool valid = q < a.Q;
       int img = 0, y = 0, x = 0;
       if (valid) {
@@ -568,8 +574,9 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
         // combine operand of this CTA's NEXT tile -> L2 now (one tile of MMAs and epilogue ahead): the loads at the head of
         // every item otherwise wait out a DRAM round trip with two warps per scheduler to cover it (data-gradient launches:
         // 84 -> 188 us with the combine operand against without).  Warp `half` takes every second 128-byte line of a pixel.
-        const int qn = (tile + a.G) * 128 + quarter * 32 + lane;
-        if (qn < a.Q) {
+        const int tn = tile + a.G;
+        const int qn = (a.rev ? a.ntiles - 1 - tn : tn) * 128 + quarter * 32 + lane;
+        if (tn < a.ntiles && qn < a.Q) {
           int im = (int)((float)qn * e_rIP);
           int r = qn - im * a.IP;
           if (r < 0) { --im; r += a.IP; } else if (r >= a.IP) { ++im; r -= a.IP; }
@@ -958,6 +965,7 @@ int tconv_win_repack(const bsde_conv_layer* L, int S, int nit, const float* w, l
   return 0;
 }
 
+static thread_local int g_win_rev = 0;   // tile direction of the launches of the current tconv_fwd_win call
 static int win_launch_one(const bsde_conv_layer* L, int S, int B, const float* in, float t, int act, int epi, float scale,
                           const float* aux, float* out, int opitch, const float* wimg, long long wimg_sample_stride, int wsafe,
                           cudaStream_t st);
@@ -977,6 +985,11 @@ int tconv_fwd_win(const bsde_conv_layer* L, int S, int B, const float* in, const
     if (int e = tconv_win_repack(L, S, 1, w, w_sample_stride, 0, epi, (float*)ws, st)) return e;
   }
   const float* wimg = prepacked ? prepacked : (const float*)ws;
+  // consecutive launches of a chain are producer -> consumer over tensors larger than L2: they alternate the tile direction
+  static const int rev_on = getenv("BSDE_WIN_REV") ? atoi(getenv("BSDE_WIN_REV")) : 1;
+  static thread_local int rev_toggle = 0;
+  g_win_rev = rev_on ? rev_toggle : 0;
+  rev_toggle ^= 1;
   for (int i = 0; i < sp.n; ++i) {
     // slice i > 0 follows slice i-1 in the stream: its image was written before that kernel started
     const int wsafe = prepacked ? (i > 0 ? 1 : prepacked_safe) : 0;
@@ -1009,6 +1022,7 @@ static int win_launch_one(const bsde_conv_layer* L, int S, int B, const float* i
   a.hslab = p.hslab; a.nslab = p.nslab; a.region = p.region; a.gather = p.gather;
   a.tma = p.gather ? 0 : p.tma; a.NR = p.NR; a.box_bytes = p.box_bytes;
   a.t = t; a.scale = scale;
+  a.rev = g_win_rev;
   { static const int pf = getenv("BSDE_WIN_PF") ? atoi(getenv("BSDE_WIN_PF")) : 1; a.pf = pf; }
   { static const int dbg = getenv("BSDE_WIN_DBG") ? atoi(getenv("BSDE_WIN_DBG")) : 0; a.dbg = dbg; }
   for (int e = 0; e < p.nent; ++e) {
