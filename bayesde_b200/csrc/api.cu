@@ -348,36 +348,45 @@ static DualStreams* dual_streams() {
 // unchanged; they run with t = 1, scale = 1 into a [k][s][P] buffer, and one finishing pass applies the per-iteration factors
 // (t_k on the time rows, dt_k on the last layer) while transposing to the [s][k][P] layout that K1' reads.
 // ---------------------------------------------------------------------------------------------
+constexpr int FIN_INLINE = 128;
 struct FinalizeArgs {
   const float* src;     // [nit][S][P]
   float* dst;           // [S][nit][P]
-  const float* tk;      // [nit] device
+  const float* tk;      // [nit] device (grids longer than FIN_INLINE)
   const float* dtk;     // [nit] device
+  int inl;              // the time grid travels in the kernel parameters (no host -> device copy: a pageable copy stalls the host)
+  float tkv[FIN_INLINE], dtkv[FIN_INLINE];
   int S, nit, nlayers;
   long long P;
   long long w_off[BSDE_MAX_LAYERS], w_end[BSDE_MAX_LAYERS], b_off[BSDE_MAX_LAYERS];
   int Kc[BSDE_MAX_LAYERS], cout[BSDE_MAX_LAYERS], time_row[BSDE_MAX_LAYERS];
 };
 
+// one thread per (parameter p, sample s): the factor's structure (last layer -> dt_k, time row -> t_k) is found once, then the
+// nit iterations are streamed [k][s][P] -> [s][k][P] (coalesced in p on both sides; no per-element 64-bit divisions)
 __global__ void gw_finalize_kernel(FinalizeArgs a) {
-  const long long per = (long long)a.S * a.P;
-  const long long total = per * a.nit;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(idx / per);
-    const long long r = idx - (long long)k * per;
-    const int s = (int)(r / a.P);
-    const long long p = r - (long long)s * a.P;
-    float f = 1.f;
-    for (int l = 0; l < a.nlayers; ++l) {
-      const bool in_w = p >= a.w_off[l] && p < a.w_end[l];
-      const bool in_b = p >= a.b_off[l] && p < a.b_off[l] + a.cout[l];
-      if (in_w || in_b) {
-        if (l == a.nlayers - 1) f *= a.dtk[k];
-        if (in_w && a.time_row[l] >= 0 && (int)(((p - a.w_off[l]) / a.cout[l]) % a.Kc[l]) == a.time_row[l]) f *= a.tk[k];
-        break;
-      }
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
+  if (p >= a.P) return;
+  bool use_dt = false, use_t = false;
+  for (int l = 0; l < a.nlayers; ++l) {
+    const bool in_w = p >= a.w_off[l] && p < a.w_end[l];
+    const bool in_b = p >= a.b_off[l] && p < a.b_off[l] + a.cout[l];
+    if (in_w || in_b) {
+      use_dt = l == a.nlayers - 1;
+      use_t = in_w && a.time_row[l] >= 0 && (int)(((p - a.w_off[l]) / a.cout[l]) % a.Kc[l]) == a.time_row[l];
+      break;
     }
-    a.dst[((long long)s * a.nit + k) * a.P + p] = a.src[idx] * f;
+  }
+  const float* __restrict__ src = a.src + (long long)s * a.P + p;
+  float* __restrict__ dst = a.dst + (long long)s * a.nit * a.P + p;
+  const long long sstep = (long long)a.S * a.P;
+#pragma unroll 4
+  for (int k = 0; k < a.nit; ++k) {
+    float f = 1.f;
+    if (use_dt) f *= a.inl ? a.dtkv[k] : a.dtk[k];
+    if (use_t) f *= a.inl ? a.tkv[k] : a.tk[k];
+    dst[(long long)k * a.P] = src[(long long)k * sstep] * f;
   }
 }
 
@@ -556,8 +565,10 @@ static int xpath_bwd_deferred(const bsde_xpath_desc* d, const float* h_tk, const
   float* gw_ks = fp; fp += (size_t)nit * S * (size_t)d->P;
   float* d_tk = fp; float* d_dtk = fp + nit;
 
-  BSDE_CUDA_OK(cudaMemcpyAsync(d_tk, h_tk, nit * sizeof(float), cudaMemcpyHostToDevice, st));
-  BSDE_CUDA_OK(cudaMemcpyAsync(d_dtk, h_dtk, nit * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (nit > FIN_INLINE) {
+    BSDE_CUDA_OK(cudaMemcpyAsync(d_tk, h_tk, nit * sizeof(float), cudaMemcpyHostToDevice, st));
+    BSDE_CUDA_OK(cudaMemcpyAsync(d_dtk, h_dtk, nit * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
   BSDE_CUDA_OK(cudaMemcpyAsync(gxs + (size_t)nit * d->x_numel, d_gx, (size_t)d->x_numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
 
   const long long wss = (long long)(nit + 1) * d->P;
@@ -610,14 +621,15 @@ static int xpath_bwd_deferred(const bsde_xpath_desc* d, const float* h_tk, const
   FinalizeArgs fa;
   memset(&fa, 0, sizeof(fa));
   fa.src = gw_ks; fa.dst = d_gw_traj; fa.tk = d_tk; fa.dtk = d_dtk; fa.S = S; fa.nit = nit; fa.nlayers = n; fa.P = d->P;
+  fa.inl = nit <= FIN_INLINE;
+  if (fa.inl) { for (int k = 0; k < nit; ++k) { fa.tkv[k] = h_tk[k]; fa.dtkv[k] = h_dtk[k]; } }
   for (int l = 0; l < n; ++l) {
     const bsde_conv_layer& L = d->layers[l];
     const int Kc = L.cin + (L.has_time ? 1 : 0);
     fa.w_off[l] = L.w_off; fa.w_end[l] = L.w_off + (long long)L.ksize * L.ksize * Kc * L.cout; fa.b_off[l] = L.b_off;
     fa.Kc[l] = Kc; fa.cout[l] = L.cout; fa.time_row[l] = L.has_time ? L.cin : -1;
   }
-  const long long total = (long long)nit * S * d->P;
-  gw_finalize_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(fa);
+  gw_finalize_kernel<<<dim3((unsigned)((d->P + 255) / 256), (unsigned)S), 256, 0, st>>>(fa);
   BSDE_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

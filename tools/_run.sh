@@ -1,6 +1,9 @@
-out=gpurun_out; tag=r02i
-BENCH="python bench.py --steps 1 --warmup 1 --no_cpu_baseline --no_fp32_leg --no_config5"
-timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -c 7000 --csv --log-file $out/${tag}_launches.csv $BENCH > $out/${tag}_ncu_launches.log 2>&1; echo "launch list rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_win_kernel -s 40 -c 8 -o $out/${tag}_conv_win -f $BENCH > $out/${tag}_ncu_cw.log 2>&1; echo "ncu conv_win rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k "regex:wgrad_(win|thin)_kernel" -c 6 -o $out/${tag}_wgrad -f $BENCH > $out/${tag}_ncu_wg.log 2>&1; echo "ncu wgrad rc=$?"
-ls -la $out | grep r02i
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_config4_full.py -x -q -m gpu -k "block_tc or remat or classifier or config or golden or full_size" > gpurun_out/u23_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/u23_tests.log
+timeout 300 python tools/step_gaps.py --steps 2 > gpurun_out/u23_gaps.txt 2>&1; sed -n 3,4p gpurun_out/u23_gaps.txt; tail -8 gpurun_out/u23_gaps.txt
+B="python bench.py --steps 5 --warmup 3 --no_cpu_baseline --no_fp32_leg --no_config5"
+timeout 200 $B > gpurun_out/u23_b.json 2> gpurun_out/u23_b.err
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/u23_b.json").read().strip().splitlines()[-1])
+print(d["ms_per_step"], d["value"], d["e2e"]["value"], d.get("kernel_ms_per_step"), d["loss"]["last_timed_step"])
+PY
