@@ -272,3 +272,35 @@ def test_sass_carries_the_blackwell_instructions(built_lib):
     for kernel in ("conv_win_kernel", "wgrad_win_kernel", "wsde_fwd_kernel", "wsde_bwd_kernel", "brownian_tree_threefry_kernel"):
         assert kernel in sass, kernel
     assert "HMMA.16816" not in sass and "HGMMA" not in sass        # no mma.sync / wgmma tensor-core path in the library
+
+
+def test_host_path_makes_no_per_call_device_copies():
+    """The per-call host -> device copies of the step path are cached (a pageable copy stalls the host until the stream has
+    drained: profiles/r02_summary.md section 8): the scalar branch of normal_logprob (brax.py:171-178) equals the tensor branch and
+    the oracle, whole-solve time grids share one device copy per (grid, device), one-step grids (adjoint routes) are not cached."""
+    from bayesde_b200 import _fused, arch, brax
+    g = torch.Generator().manual_seed(0)
+    z, mean = torch.randn(4, 7, generator=g), torch.randn(7, generator=g)
+    ls = float(np.log(0.1))
+    a = brax.normal_logprob(z, mean, ls)
+    b = brax.normal_logprob(z, mean, torch.tensor(ls))
+    r = jp.normal_logprob(z.double(), mean.double(), torch.tensor(ls, dtype=torch.float64))
+    assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(a.double(), r, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(brax.normal_logprob(z, 0.0, ls).double(), jp.normal_logprob(z.double(), 0.0, torch.tensor(ls, dtype=torch.float64)),
+                          rtol=1e-5, atol=1e-5)
+
+    fx = arch.FxSpec(0, (1, 8, 8, 5), 8, "softplus")
+    fw = dict(hidden_dims=(2,), actfn="softplus", ou_dw=True)
+    c1 = _fused.BlockConfig(fx, fw, 2, 2, 6, 0.2, False, "reference")
+    c2 = _fused.BlockConfig(fx, fw, 2, 2, 6, 0.2, False, "reference")
+    t1, t2 = c1.grid_on("cpu"), c2.grid_on("cpu")
+    assert t1[0].data_ptr() == t2[0].data_ptr() and t1[1].data_ptr() == t2[1].data_ptr()
+    assert np.array_equal(t1[0].numpy(), c1.tk) and np.array_equal(t1[1].numpy(), c1.dtk)
+    c3 = _fused.BlockConfig(fx, fw, 2, 2, 6, 0.2, False, "uniform")
+    if not (np.array_equal(c3.tk, c1.tk) and np.array_equal(c3.dtk, c1.dtk)):
+        assert c3.grid_on("cpu")[1].data_ptr() != t1[1].data_ptr()
+    n = len(_fused._GRID_CACHE)
+    c1.set_step(0.25, 0.05)
+    s1 = c1.grid_on("cpu")
+    assert len(_fused._GRID_CACHE) == n and float(s1[0][0]) == 0.25 and abs(float(s1[1][0]) - 0.05) < 1e-7
