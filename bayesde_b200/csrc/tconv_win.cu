@@ -551,6 +551,13 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
     const int nchunk = (a.cout + 15) >> 4;
     const int c4 = lane & 3, r8 = lane >> 2;
     const float e_rIP = 1.0f / (float)a.IP, e_rpitch = 1.0f / (float)a.pitch;
+    // fold the time term into the table once per CTA: row 1 + ac * 16 + cls becomes bias + t * (time rows of that border class),
+    // so that an item costs one table read and one add per element instead of two reads, an add and a multiply-add
+    if (a.has_time) {
+      for (int r = warp; r < 16 * a.NA; r += WN_EPI_WARPS)
+        for (int n = lane; n < a.npad; n += 32) s_tb[(1 + r) * a.npad + n] = fmaf(a.t, s_tb[(1 + r) * a.npad + n], s_tb[n]);
+      asm volatile("bar.sync 2, %0;" ::"n"(WN_EPI_WARPS * 32) : "memory");
+    }
     int it = 0;
 #pragma unroll 1
     for (int tile = g; tile < a.ntiles; tile += a.G, ++it) {
@@ -647,18 +654,13 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
         // row form: bias, time term, activation on this lane's 16 accumulator columns
         float f[16];
         {
-          const float4* bt = reinterpret_cast<const float4*>(s_tb + n0);
-          const float4* tt = reinterpret_cast<const float4*>(s_tb + (1 + ac * 16 + cls) * a.npad + n0);
+          // one table row per (accumulator, border class): bias + t * (time rows of the taps inside the image), folded once per CTA
+          const float4* bt = reinterpret_cast<const float4*>(s_tb + (a.has_time ? (1 + ac * 16 + cls) * a.npad : 0) + n0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 b4 = bt[j];
             f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
             f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-            if (a.has_time) {
-              const float4 t4 = tt[j];
-              f[4 * j + 0] = fmaf(a.t, t4.x, f[4 * j + 0]); f[4 * j + 1] = fmaf(a.t, t4.y, f[4 * j + 1]);
-              f[4 * j + 2] = fmaf(a.t, t4.z, f[4 * j + 2]); f[4 * j + 3] = fmaf(a.t, t4.w, f[4 * j + 3]);
-            }
           }
           if (EPI == BSDE_EPI_BIAS_ACT) {
 #pragma unroll
