@@ -189,6 +189,40 @@ __device__ __forceinline__ float wn_combine(float q, float x, float scale) {
   return q;
 }
 
+// ---- packed pairs: Blackwell's FFMA2 / FADD2 / FMUL2 carry two fp32 operations per issue slot (same IEEE results as the scalar
+// forms: the epilogues are issue bound with two warps per scheduler, not FP32-pipe bound)
+__device__ __forceinline__ float2 wn_f2(float a) { return make_float2(a, a); }
+template <int ACT>
+__device__ __forceinline__ float2 wn_act_fwd2(float2 x) {
+  if (ACT == BSDE_ACT_SOFTPLUS) {
+    const float2 t = __fmul2_rn(x, wn_f2(-1.44269504f));
+    float2 e;
+    e.x = wn_ex2(-fabsf(t.x)); e.y = wn_ex2(-fabsf(t.y));
+    float2 p = wn_f2(0.03137759119272232f);
+    p = __ffma2_rn(p, e, wn_f2(-0.134135439991951f));
+    p = __ffma2_rn(p, e, wn_f2(0.2878262996673584f));
+    p = __ffma2_rn(p, e, wn_f2(-0.49134793877601624f));
+    p = __ffma2_rn(p, e, wn_f2(0.9994350075721741f));
+    return __ffma2_rn(p, e, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+  }
+  return make_float2(wn_act_fwd<ACT>(x.x), wn_act_fwd<ACT>(x.y));
+}
+template <int EPI, int ACT>
+__device__ __forceinline__ float2 wn_combine2(float2 q, float2 x, float scale) {
+  if (EPI == BSDE_EPI_DACT) {
+    float2 g;
+    if (ACT == BSDE_ACT_SOFTPLUS) {
+      const float2 t = __fmul2_rn(x, wn_f2(-1.44269504f));
+      g = __ffma2_rn(make_float2(wn_ex2(t.x), wn_ex2(t.y)), wn_f2(-1.f), wn_f2(1.f));
+    } else {
+      g = make_float2(wn_act_grad_out<ACT>(x.x), wn_act_grad_out<ACT>(x.y));
+    }
+    return __fmul2_rn(__fmul2_rn(wn_f2(scale), q), g);
+  }
+  if (EPI == BSDE_EPI_EULER || EPI == BSDE_EPI_ACCUM) return __ffma2_rn(wn_f2(scale), q, x);
+  return q;
+}
+
 template <bool VEC, int EPI, int ACT>
 __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_constant__ WinArgs a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
@@ -652,19 +686,19 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * a.NA + ac) * a.npad + n0), v);
         // row form: bias, time term, activation on this lane's 16 accumulator columns
-        float f[16];
+        float2 f[8];
         {
           // one table row per (accumulator, border class): bias + t * (time rows of the taps inside the image), folded once per CTA
           const float4* bt = reinterpret_cast<const float4*>(s_tb + (a.has_time ? (1 + ac * 16 + cls) * a.npad : 0) + n0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 b4 = bt[j];
-            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+            f[2 * j] = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), make_float2(b4.x, b4.y));
+            f[2 * j + 1] = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b4.z, b4.w));
           }
           if (EPI == BSDE_EPI_BIAS_ACT) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = wn_act_fwd<ACT>(f[j]);
+            for (int j = 0; j < 8; ++j) f[j] = wn_act_fwd2<ACT>(f[j]);
           }
         }
         __syncwarp();  // readers of the previous chunk are done with the staging rows
@@ -672,10 +706,10 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
           // row `lane`: 16-byte chunk c stored at position c ^ ((lane >> 1) & 3)  (conflict-free both ways)
           float4* dst = reinterpret_cast<float4*>(stage + lane * 16);
           const int fz = (lane >> 1) & 3;
-          dst[0 ^ fz] = make_float4(f[0], f[1], f[2], f[3]);
-          dst[1 ^ fz] = make_float4(f[4], f[5], f[6], f[7]);
-          dst[2 ^ fz] = make_float4(f[8], f[9], f[10], f[11]);
-          dst[3 ^ fz] = make_float4(f[12], f[13], f[14], f[15]);
+          dst[0 ^ fz] = make_float4(f[0].x, f[0].y, f[1].x, f[1].y);
+          dst[1 ^ fz] = make_float4(f[2].x, f[2].y, f[3].x, f[3].y);
+          dst[2 ^ fz] = make_float4(f[4].x, f[4].y, f[5].x, f[5].y);
+          dst[3 ^ fz] = make_float4(f[6].x, f[6].y, f[7].x, f[7].y);
         }
         __syncwarp();
         if (fast) {
@@ -692,8 +726,9 @@ __global__ void __launch_bounds__(WN_THREADS, 1) conv_win_kernel(const __grid_co
             if (pp[j] < 0 || (a.dbg & 4)) continue;
             float4 qq = qv[j];
             if (EPI >= BSDE_EPI_EULER) {
-              qq.x = wn_combine<EPI, ACT>(qq.x, xv[j].x, a.scale); qq.y = wn_combine<EPI, ACT>(qq.y, xv[j].y, a.scale);
-              qq.z = wn_combine<EPI, ACT>(qq.z, xv[j].z, a.scale); qq.w = wn_combine<EPI, ACT>(qq.w, xv[j].w, a.scale);
+              const float2 lo = wn_combine2<EPI, ACT>(make_float2(qq.x, qq.y), make_float2(xv[j].x, xv[j].y), a.scale);
+              const float2 hi = wn_combine2<EPI, ACT>(make_float2(qq.z, qq.w), make_float2(xv[j].z, xv[j].w), a.scale);
+              qq = make_float4(lo.x, lo.y, hi.x, hi.y);
             }
             *reinterpret_cast<float4*>(out + (pp[j] + n)) = qq;
           }
