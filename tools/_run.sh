@@ -1,8 +1,8 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_config4_full.py -x -q -m gpu -k "tconv or block or config or golden or edge or classifier or remat" > gpurun_out/u24_tests.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/u24_tests.log
-B="python bench.py --steps 5 --warmup 3 --no_cpu_baseline --no_fp32_leg --no_config5"
-timeout 200 $B > gpurun_out/u24_b.json 2> gpurun_out/u24_b.err
-python - <<PY
+timeout 1500 python -m pytest tests/ -x -q -m gpu > gpurun_out/r02l_tests_full.log 2>&1; echo "tests rc=$?"; tail -2 gpurun_out/r02l_tests_full.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 600 python bench.py > gpurun_out/r02l_bench.json 2> gpurun_out/r02l_bench.err; echo "bench rc=$?"
+python - <<'PY'
 import json
-d=json.loads(open("gpurun_out/u24_b.json").read().strip().splitlines()[-1])
-print(d["ms_per_step"], d["value"], d["e2e"]["value"], d.get("kernel_ms_per_step"), d["loss"]["last_timed_step"])
+d=json.loads(open("gpurun_out/r02l_bench.json").read().strip().splitlines()[-1])
+print({k:d[k] for k in ("value","ms_per_step","gpu_launches","value_fp32")}, d["e2e"]["value"], d["roofline"]["frac"], d["roofline"]["achieved"], d["roofline"]["peak"], d["roofline_hbm"]["frac"], d.get("config5",{}).get("value"), d["cpu_baseline"]["value"], d["kernel_ms_per_step"], d["clocks"], d["fp32_leg"]["same_seed_loss"])
 PY
